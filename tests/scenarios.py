@@ -1,0 +1,58 @@
+'''
+Scenario specifications shared by the golden-vector generator (oracle/gen_golden.py, which runs the
+unmodified reference), the oracle tests and the GPU parity tests.  A scenario is plain data:
+``pars`` (simulation parameters), ``interventions`` (list of (name, kwargs)), ``variants`` (list of
+kwargs); ``build(module, spec)`` instantiates it against any module exposing the reference's
+constructor names (the reference itself, oracle.cvoracle, or covasim_b200).
+'''
+import copy
+
+SCENARIOS = {
+    # reference tests/test_baselines.py:18-56 -- the sim behind tests/baseline.json
+    'baseline20k': dict(
+        pars=dict(use_waning=True, pop_size=20000, pop_infected=100, pop_type='hybrid', n_days=60, verbose=0, rand_seed=2),
+        interventions=[('change_beta', dict(days=40, changes=0.5)),
+                       ('test_prob', dict(start_day=20, symp_prob=0.1, asymp_prob=0.01)),
+                       ('contact_tracing', dict(trace_probs=0.3, start_day=50)),
+                       ('vaccinate_prob', dict(vaccine='pfizer', days=30, prob=0.1))],
+    ),
+    # BASELINE.json config 1: cv.Sim() defaults
+    'default20k': dict(pars=dict(verbose=0), interventions=[]),
+    # small hybrid with everything on, early start so that tracing/quarantine/vaccination all fire
+    'hybrid3k': dict(
+        pars=dict(pop_size=3000, pop_infected=60, pop_type='hybrid', n_days=45, verbose=0, rand_seed=11, beta=0.02),
+        interventions=[('test_prob', dict(start_day=5, symp_prob=0.3, asymp_prob=0.02, symp_quar_prob=0.6, asymp_quar_prob=0.1, test_delay=1, sensitivity=0.9, loss_prob=0.1)),
+                       ('contact_tracing', dict(trace_probs=dict(h=1.0, s=0.5, w=0.5, c=0.2), trace_time=dict(h=0, s=1, w=1, c=2), start_day=8)),
+                       ('vaccinate_prob', dict(vaccine='pfizer', days=[10, 12], prob=0.15)),
+                       ('change_beta', dict(days=[15, 30], changes=[0.6, 0.9], layers='c'))],
+    ),
+    # random population, no waning, no interventions
+    'random2k_nowaning': dict(pars=dict(pop_size=2000, pop_infected=30, n_days=40, verbose=0, rand_seed=5, use_waning=False, beta=0.025), interventions=[]),
+    # two extra variants, imports, bed limits, vaccination + booster
+    'variants4k': dict(
+        pars=dict(pop_size=4000, pop_infected=50, pop_type='hybrid', n_days=50, verbose=0, rand_seed=3, beta=0.02,
+                  n_imports=1.5, n_beds_hosp=5, n_beds_icu=1),
+        variants=[dict(variant='alpha', days=8, n_imports=20), dict(variant='delta', days=15, n_imports=25)],
+        interventions=[('test_prob', dict(start_day=3, symp_prob=0.2, asymp_prob=0.01)),
+                       ('contact_tracing', dict(trace_probs=0.4, start_day=6)),
+                       ('vaccinate_prob', dict(vaccine='pfizer', days=5, prob=0.3)),
+                       ('vaccinate_prob', dict(vaccine='jj', days=32, prob=0.2, booster=True, label='jj_boost'))],
+    ),
+    # dynamic layer (BASELINE.json config 5 member shape, scaled down)
+    'dynamic2k': dict(pars=dict(pop_size=2000, pop_infected=40, n_days=30, verbose=0, rand_seed=8, beta=0.02,
+                                dynam_layer=dict(a=1)), interventions=[]),
+}
+
+
+def build(mod, spec, **extra):
+    ''' Instantiate a scenario against module ``mod`` (reference covasim, oracle.cvoracle or covasim_b200) '''
+    spec = copy.deepcopy(spec)
+    pars = spec['pars']
+    ivs = [getattr(mod, name)(**kw) for name, kw in spec.get('interventions', [])]
+    vs = [mod.variant(**kw) for kw in spec.get('variants', [])]
+    kwargs = dict(pars)
+    kwargs['interventions'] = ivs
+    if vs:
+        kwargs['variants'] = vs
+    kwargs.update(extra)
+    return kwargs

@@ -1,5 +1,22 @@
 '''
 covasim_b200 -- B200-native implementation of Covasim's per-timestep simulation hot path.
-(Package body is filled in as the build proceeds; see DESIGN.md.)
+
+Usage mirrors the reference (``import covasim_b200 as cv``): ``cv.Sim(pop_size=..., pop_type='hybrid',
+interventions=[cv.test_prob(...), cv.contact_tracing(...)]).run()``; People and contact layers live on the
+GPU and every simulated day runs as hand-written sm_100a CUDA kernels behind a C ABI
+(include/covasim_b200.h, covasim_b200/libcovasim_b200.so).  There is no CPU fallback.
 '''
-__version__ = '0.1.0'
+from .version import __version__  # noqa: F401
+from . import defaults  # noqa: F401
+from . import parameters  # noqa: F401
+from .parameters import make_pars, get_prognoses  # noqa: F401
+from . import _capi  # noqa: F401  (loads libcovasim_b200.so; raises if it has not been built)
+from ._capi import CvbError  # noqa: F401
+from . import utils  # noqa: F401
+from .utils import *  # noqa: F401,F403
+from .base import Result, Layer, Contacts, AlreadyRunError  # noqa: F401
+from .people import People  # noqa: F401
+from .immunity import variant, calc_VE, calc_VE_symp, precompute_waning  # noqa: F401
+from .interventions import Intervention, change_beta, test_prob, contact_tracing, vaccinate_prob  # noqa: F401
+from .sim import Sim  # noqa: F401
+from . import ops  # noqa: F401

@@ -1,0 +1,217 @@
+// Handle management, binding and small shared utilities of libcovasim_b200.so.
+#include <stdarg.h>
+#include <string.h>
+#include <new>
+#include "cvb_internal.cuh"
+
+namespace cvb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    return (int)e;
+}
+
+template <typename T> static int ensure(T** p, int64_t* cap, int64_t need) {
+    if (need <= *cap) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    int64_t newcap = need + need / 4 + 1024;
+    CVB_CHECK(cudaMalloc((void**)p, (size_t)newcap * sizeof(T)));
+    *cap = newcap;
+    return 0;
+}
+int ensure_u32(unsigned int** p, int64_t* cap, int64_t need) { return ensure(p, cap, need); }
+int ensure_u8(uint8_t** p, int64_t* cap, int64_t need) { return ensure(p, cap, need); }
+int ensure_f64(double** p, int64_t* cap, int64_t need) { return ensure(p, cap, need); }
+
+// ---- exclusive scan of uint32 counts, in place (single CTA; inputs are per-tile counts, <= ~1e5) ----
+__global__ void __launch_bounds__(1024) scan_u32_kernel(unsigned int* data, int64_t n, unsigned long long* total_out) {
+    __shared__ int warp_sums[33];
+    unsigned long long running = 0;
+    for (int64_t base = 0; base < n; base += blockDim.x) {
+        int64_t i = base + threadIdx.x;
+        int v = i < n ? (int)data[i] : 0;
+        int total;
+        int excl = block_exclusive_scan(v, warp_sums, total);
+        if (i < n) data[i] = (unsigned int)(running + (unsigned long long)excl);
+        running += (unsigned long long)total;
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = running;
+}
+
+int exclusive_scan_u32(unsigned int* data, int64_t n, unsigned long long* total_out, cudaStream_t st) {
+    scan_u32_kernel<<<1, 1024, 0, st>>>(data, n, total_out);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void fill_f32_kernel(float* p, int64_t n, float v) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+}  // namespace cvb
+
+using namespace cvb;
+
+extern "C" {
+
+const char* cvb_last_error(void) { return g_err; }
+int32_t cvb_abi_version(void) { return CVB_ABI_VERSION; }
+
+/* sizes of the by-value structs, so a binding can verify its own layout */
+int cvb_struct_sizes(int64_t* out5) {
+    CVB_REQUIRE(out5, "cvb_struct_sizes: NULL output");
+    out5[0] = (int64_t)sizeof(cvb_pars); out5[1] = (int64_t)sizeof(cvb_dist); out5[2] = (int64_t)sizeof(cvb_test_prob_pars);
+    out5[3] = (int64_t)sizeof(cvb_trace_pars); out5[4] = (int64_t)sizeof(cvb_vaccinate_pars);
+    return 0;
+}
+
+int cvb_create(cvb_sim** out, int64_t n_agents, int32_t n_variants, int32_t npts, uint64_t seed) {
+    CVB_REQUIRE(out != nullptr, "cvb_create: out is NULL");
+    CVB_REQUIRE(n_agents > 0, "cvb_create: n_agents must be positive");
+    CVB_REQUIRE(n_variants >= 1 && n_variants <= CVB_MAX_VARIANTS, "cvb_create: n_variants must be in [1,%d]", CVB_MAX_VARIANTS);
+    CVB_REQUIRE(npts >= 1, "cvb_create: npts must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error("cvb_create: no CUDA device available (%s); covasim_b200 has no CPU fallback", cudaGetErrorString(e));
+        return 100;
+    }
+    cvb_sim* s = new (std::nothrow) cvb_sim();
+    CVB_REQUIRE(s != nullptr, "cvb_create: out of host memory");
+    memset(s, 0, sizeof(*s));
+    s->n = n_agents;
+    s->nv = n_variants;
+    s->npts = npts;
+    s->seed = seed;
+    cudaGetDevice(&s->device);
+    s->quar_horizon = 1;
+    int rc = 0;
+    do {
+        if ((rc = check_cuda(cudaMalloc((void**)&s->cand, (size_t)n_agents * sizeof(int32_t)), "cand"))) break;
+        if ((rc = check_cuda(cudaMalloc((void**)&s->infect_key, (size_t)n_agents * sizeof(unsigned long long)), "infect_key"))) break;
+        if ((rc = check_cuda(cudaMemset(s->infect_key, 0xFF, (size_t)n_agents * sizeof(unsigned long long)), "infect_key"))) break;
+        if ((rc = check_cuda(cudaMalloc((void**)&s->n_cand, 64), "n_cand"))) break;
+        if ((rc = check_cuda(cudaMemset(s->n_cand, 0, 64), "n_cand"))) break;
+        if ((rc = check_cuda(cudaMalloc((void**)&s->beds, (size_t)npts * 2 * sizeof(unsigned long long)), "beds"))) break;
+        if ((rc = check_cuda(cudaMemset(s->beds, 0, (size_t)npts * 2 * sizeof(unsigned long long)), "beds"))) break;
+        if ((rc = check_cuda(cudaMalloc((void**)&s->quar_ring, (size_t)n_agents * sizeof(float)), "quar_ring"))) break;
+        fill_f32_kernel<<<grid_for(n_agents), kThreads>>>(s->quar_ring, n_agents, -1.0f);
+        if ((rc = check_cuda(cudaGetLastError(), "fill quar_ring"))) break;
+        int64_t words = (n_agents + 31) / 32;
+        if ((rc = check_cuda(cudaMalloc((void**)&s->case_bits, (size_t)words * sizeof(unsigned int)), "case_bits"))) break;
+        if ((rc = check_cuda(cudaMemset(s->case_bits, 0, (size_t)words * sizeof(unsigned int)), "case_bits"))) break;
+        if ((rc = check_cuda(cudaMalloc((void**)&s->n_cases, 64), "n_cases"))) break;
+        if ((rc = check_cuda(cudaMemset(s->n_cases, 0, 64), "n_cases"))) break;
+        if ((rc = check_cuda(cudaMalloc((void**)&s->dev_scalars, 16 * sizeof(unsigned long long)), "dev_scalars"))) break;
+        if ((rc = check_cuda(cudaMemset(s->dev_scalars, 0, 16 * sizeof(unsigned long long)), "dev_scalars"))) break;
+        if ((rc = check_cuda(cudaMallocHost((void**)&s->host_scalars, 16 * sizeof(unsigned long long)), "host_scalars"))) break;
+        if ((rc = check_cuda(cudaDeviceSynchronize(), "cvb_create sync"))) break;
+    } while (0);
+    if (rc) { cvb_destroy(s); return rc; }
+    *out = s;
+    return 0;
+}
+
+int cvb_destroy(cvb_sim* s) {
+    if (!s) return 0;
+    cudaFree(s->cand); cudaFree(s->n_cand); cudaFree(s->infect_key); cudaFree(s->beds); cudaFree(s->quar_ring); cudaFree(s->case_bits);
+    cudaFree(s->n_cases); cudaFree(s->dev_scalars); cudaFree(s->rec.ts); cudaFree(s->rec.sus_extra); cudaFree(s->rec.ivar);
+    cudaFree(s->nab_kin); cudaFree(s->tile_cnt); cudaFree(s->hit_mask); cudaFree(s->flag_tmp); cudaFree(s->partial);
+    if (s->host_scalars) cudaFreeHost(s->host_scalars);
+    delete s;
+    return 0;
+}
+
+int cvb_set_seed(cvb_sim* s, uint64_t seed) {
+    CVB_REQUIRE(s, "cvb_set_seed: NULL handle");
+    s->seed = seed;
+    return 0;
+}
+
+int cvb_set_pars(cvb_sim* s, const cvb_pars* p) {
+    CVB_REQUIRE(s && p, "cvb_set_pars: NULL argument");
+    CVB_REQUIRE(p->n_variants == s->nv, "cvb_set_pars: n_variants %d does not match the handle's %d", p->n_variants, s->nv);
+    CVB_REQUIRE(p->n_layers >= 0 && p->n_layers <= CVB_MAX_LAYERS, "cvb_set_pars: n_layers must be in [0,%d]", CVB_MAX_LAYERS);
+    CVB_REQUIRE(p->n_vaccines >= 0 && p->n_vaccines <= CVB_MAX_VACCINES, "cvb_set_pars: n_vaccines must be in [0,%d]", CVB_MAX_VACCINES);
+    s->pars = *p;
+    s->pars_set = true;
+    return 0;
+}
+
+int cvb_set_nab_kin(cvb_sim* s, const double* host_kin, int64_t n) {
+    CVB_REQUIRE(s && host_kin && n > 0, "cvb_set_nab_kin: bad argument");
+    if (s->nab_kin) cudaFree(s->nab_kin);
+    s->nab_kin = nullptr;
+    CVB_CHECK(cudaMalloc((void**)&s->nab_kin, (size_t)n * sizeof(double)));
+    CVB_CHECK(cudaMemcpy(s->nab_kin, host_kin, (size_t)n * sizeof(double), cudaMemcpyHostToDevice));
+    s->nab_kin_len = n;
+    return 0;
+}
+
+int cvb_bind_field(cvb_sim* s, int32_t field, void* ptr) {
+    CVB_REQUIRE(s, "cvb_bind_field: NULL handle");
+    CVB_REQUIRE(field >= 0 && field < CVB_N_FIELDS, "cvb_bind_field: field id %d out of range", field);
+    CVB_REQUIRE(ptr != nullptr, "cvb_bind_field: NULL pointer for field %d", field);
+    s->people.f[field] = ptr;
+    return 0;
+}
+
+int cvb_bind_layer(cvb_sim* s, int32_t layer, int32_t* p1, int32_t* p2, float* beta, int64_t n_edges) {
+    CVB_REQUIRE(s, "cvb_bind_layer: NULL handle");
+    CVB_REQUIRE(layer >= 0 && layer < CVB_MAX_LAYERS, "cvb_bind_layer: layer %d out of range", layer);
+    CVB_REQUIRE(n_edges >= 0, "cvb_bind_layer: negative edge count");
+    CVB_REQUIRE(n_edges == 0 || (p1 && p2 && beta), "cvb_bind_layer: NULL edge array");
+    CVB_REQUIRE((((uintptr_t)p1 | (uintptr_t)p2 | (uintptr_t)beta) & 15) == 0,
+                "cvb_bind_layer: edge arrays must be 16-byte aligned (128-bit vector loads)");
+    s->layers[layer].p1 = p1;
+    s->layers[layer].p2 = p2;
+    s->layers[layer].beta = beta;
+    s->layers[layer].n_edges = n_edges;
+    return 0;
+}
+
+int cvb_bind_results(cvb_sim* s, int64_t* counters, int64_t* vcounters, double* sums) {
+    CVB_REQUIRE(s && counters && vcounters && sums, "cvb_bind_results: NULL argument");
+    s->res.counters = (unsigned long long*)counters;
+    s->res.vcounters = (unsigned long long*)vcounters;
+    s->res.sums = sums;
+    return 0;
+}
+
+int cvb_bind_log(cvb_sim* s, int32_t* source, int32_t* target, int32_t* date, int8_t* layer, int8_t* variant,
+                 int64_t cap, int64_t* count) {
+    CVB_REQUIRE(s && source && target && date && layer && variant && count && cap > 0, "cvb_bind_log: bad argument");
+    s->log.source = source; s->log.target = target; s->log.date = date; s->log.layer = layer; s->log.variant = variant;
+    s->log.cap = cap; s->log.count = (unsigned long long*)count;
+    return 0;
+}
+
+int cvb_set_quar_horizon(cvb_sim* s, int32_t horizon) {
+    CVB_REQUIRE(s && horizon >= 1 && horizon <= 64, "cvb_set_quar_horizon: horizon must be in [1,64]");
+    if (horizon <= s->quar_horizon) return 0;
+    // The ring is indexed by day % horizon, so it can only be re-sized while it is empty of future
+    // requests; the host calls this when a tracing intervention is initialised.
+    float* ring = nullptr;
+    CVB_CHECK(cudaMalloc((void**)&ring, (size_t)horizon * s->n * sizeof(float)));
+    fill_f32_kernel<<<grid_for(horizon * s->n), kThreads>>>(ring, horizon * s->n, -1.0f);
+    CVB_LAUNCH_CHECK();
+    CVB_CHECK(cudaDeviceSynchronize());
+    cudaFree(s->quar_ring);
+    s->quar_ring = ring;
+    s->quar_horizon = horizon;
+    return 0;
+}
+
+}  // extern "C"

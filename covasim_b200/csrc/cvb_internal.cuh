@@ -1,0 +1,179 @@
+// Internal definitions shared by the .cu files of libcovasim_b200.so: the handle, the by-value
+// kernel argument blocks, launch/error helpers and the block-level reduce / scan primitives.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "covasim_b200.h"
+#include "cvb_device.cuh"
+
+namespace cvb {
+
+constexpr int kThreads = 256;                 // CTA size of every streaming kernel
+constexpr int kEdgesPerThread = 4;            // 128-bit loads of p1 / p2 / beta
+constexpr int kTileEdges = kThreads * kEdgesPerThread;
+constexpr unsigned long long kEmptyKey = 0xFFFFFFFFFFFFFFFFull;
+
+// Device pointers of the per-agent arrays, passed to kernels by value (66 pointers = 528 B)
+struct PeoplePtrs {
+    void* f[CVB_N_FIELDS];
+    template <typename T> __host__ __device__ __forceinline__ T* get(int id) const { return (T*)f[id]; }
+};
+#define PF(P, name)  ((P).template get<float>(CVB_F_##name))
+#define PB(P, name)  ((P).template get<uint8_t>(CVB_F_##name))
+#define PI(P, name)  ((P).template get<int32_t>(CVB_F_##name))
+
+struct LayerPtrs {
+    int32_t* p1;
+    int32_t* p2;
+    float* beta;
+    int64_t n_edges;
+};
+
+struct LayerTable {                            // all layers, by value, for the fused edge pass
+    LayerPtrs l[CVB_MAX_LAYERS];
+    int64_t tile_start[CVB_MAX_LAYERS + 1];    // prefix sum of ceil(n_edges / kTileEdges)
+    int32_t n_layers;
+};
+
+struct ResultPtrs {
+    unsigned long long* counters;              // [npts][CVB_N_COUNTERS]
+    unsigned long long* vcounters;             // [npts][nv][CVB_N_VCOUNTERS]
+    double* sums;                              // [npts][4]
+};
+
+struct LogPtrs {
+    int32_t* source; int32_t* target; int32_t* date; int8_t* layer; int8_t* variant;
+    int64_t cap; unsigned long long* count;
+};
+
+// Transmission records written by prepare_transmission and gathered by the edge pass
+struct TransRecords {
+    float2* ts;          // [n_layers][N]  {rel_trans for the agent's own variant, rel_sus vs variant 0}
+    float* sus_extra;    // [n_layers][nv-1][N] rel_sus vs variants 1.. (nv > 1 only)
+    uint8_t* ivar;       // [N] variant carried by an infectious agent (nv > 1 only)
+};
+
+}  // namespace cvb
+
+struct cvb_sim {
+    int64_t n;
+    int32_t nv, npts, device;
+    uint64_t seed;
+    cvb_pars pars;
+    bool pars_set;
+    cvb::PeoplePtrs people;
+    cvb::LayerPtrs layers[CVB_MAX_LAYERS];
+    cvb::ResultPtrs res;
+    cvb::LogPtrs log;
+    // scratch owned by the library
+    cvb::TransRecords rec; int32_t rec_layers;
+    int32_t* cand; unsigned int* n_cand;            // today's newly infected candidates
+    unsigned long long* infect_key;                 // [N] winning transmission key per target (kEmptyKey = none)
+    unsigned long long* beds;                       // [npts][2] severe / critical after update_states_pre
+    double* nab_kin; int64_t nab_kin_len;           // NAb kinetics table (immunity.py:298)
+    float* quar_ring; int32_t quar_horizon;         // [quar_horizon][N] pending quarantine end days, -1 = none
+    unsigned int* case_bits; unsigned int* n_cases; // contact tracing: bitmap of today's cases
+    // scan / compaction workspace
+    unsigned int* tile_cnt; int64_t tile_cnt_cap;   // per-tile counts (and their exclusive scan, in place)
+    uint8_t* hit_mask; int64_t hit_mask_cap;
+    uint8_t* flag_tmp; int64_t flag_tmp_cap;
+    double* partial; int64_t partial_cap;           // per-block partial sums
+    unsigned long long* dev_scalars;                // small device scratch for counts returned to the host
+    unsigned long long* host_scalars;               // pinned mirror
+};
+
+namespace cvb {
+
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+int ensure_u32(unsigned int** p, int64_t* cap, int64_t need);
+int ensure_u8(uint8_t** p, int64_t* cap, int64_t need);
+int ensure_f64(double** p, int64_t* cap, int64_t need);
+int exclusive_scan_u32(unsigned int* data, int64_t n, unsigned long long* total_out, cudaStream_t st);
+
+#define CVB_CHECK(call) do { int rc_ = cvb::check_cuda((call), #call); if (rc_) return rc_; } while (0)
+#define CVB_REQUIRE(cond, ...) do { if (!(cond)) { cvb::set_error(__VA_ARGS__); return 1; } } while (0)
+#define CVB_LAUNCH_CHECK() CVB_CHECK(cudaGetLastError())
+
+inline int grid_for(int64_t n, int per_block = kThreads, int64_t cap = 148 * 16) {
+    int64_t g = (n + per_block - 1) / per_block;
+    if (g < 1) g = 1;
+    if (g > cap) g = cap;
+    return (int)g;
+}
+
+#if defined(__CUDACC__)
+// ---- warp / block primitives ---------------------------------------------------------------
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+// Sum `v` over the CTA and add the result to *dst with ONE global atomic (Guideline 12)
+__device__ __forceinline__ void block_add(unsigned long long* dst, int v, int* smem_slot) {
+    int w = __reduce_add_sync(0xFFFFFFFFu, v);
+    if (lane_id() == 0 && w) atomicAdd(smem_slot, w);
+}
+
+// Exclusive prefix sum of one int per thread across a CTA of kThreads threads; returns the thread's
+// offset and, through `total`, the CTA sum.  `warp_sums` is shared int[kThreads/32].
+__device__ __forceinline__ int block_exclusive_scan(int v, int* warp_sums, int& total) {
+    int lane = lane_id(), w = warp_id();
+    int incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_sums[w] = incl;
+    __syncthreads();
+    int nw = blockDim.x >> 5;
+    if (w == 0) {
+        int s = lane < nw ? warp_sums[lane] : 0;
+        int si = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int o = __shfl_up_sync(0xFFFFFFFFu, si, d);
+            if (lane >= d) si += o;
+        }
+        if (lane < nw) warp_sums[lane] = si - s;          // exclusive warp offsets
+        if (lane == nw - 1) warp_sums[nw] = si;           // total
+    }
+    __syncthreads();
+    total = warp_sums[nw];
+    int out = warp_sums[w] + incl - v;
+    __syncthreads();
+    return out;
+}
+
+// Warp-aggregated "append one item": returns this lane's slot in a global list (Guideline 12)
+__device__ __forceinline__ unsigned long long warp_append(unsigned long long* counter) {
+    unsigned mask = __activemask();
+    int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if (lane_id() == leader) base = atomicAdd(counter, (unsigned long long)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane_id()) - 1u));
+}
+__device__ __forceinline__ unsigned int warp_append32(unsigned int* counter) {
+    unsigned mask = __activemask();
+    int leader = __ffs(mask) - 1;
+    unsigned int base = 0;
+    if (lane_id() == leader) base = atomicAdd(counter, (unsigned int)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + __popc(mask & ((1u << lane_id()) - 1u));
+}
+
+// 128-bit streaming loads that do not allocate in L1 (edge arrays are read exactly once per pass)
+__device__ __forceinline__ int4 ld_stream(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+#endif
+
+}  // namespace cvb

@@ -1,0 +1,258 @@
+// People.infect (reference people.py:435-586) + update_peak_nab (immunity.py:138-202), native-RNG form.
+//
+// One thread per newly infected agent.  Every random draw is a pure function of
+// (seed, P_INFECT, day, agent, slot), so the result does not depend on the order in which the edge
+// pass discovered the targets.  Slots: 0 exp2inf, 1 symptomatic?, 2 asym2rec|inf2sym, 3 severe?,
+// 4 mild2rec|sym2sev, 5 critical?, 6 sev2rec|sev2crit, 7 dies?, 8 crit2rec|crit2die, 9 nab_init.
+#include "cvb_internal.cuh"
+
+namespace cvb {
+
+int build_layer_table(cvb_sim* s, LayerTable& L);
+
+enum { INF_INFECTIONS = 0, INF_REINFECTIONS, INF_NK };
+
+struct InfectArgs {
+    uint64_t seed;
+    int64_t n;
+    int32_t t;
+    int32_t count_flows;     // 0 for seed infections at initialisation (reference sim.py:505-532: flows are discarded)
+    int32_t list_layer_code; // layer code logged for list-mode keys (CVB_LAYER_SEED / CVB_LAYER_IMPORT)
+};
+
+__device__ __forceinline__ double draw_dur(const cvb_pars& pars, int which, uint64_t seed, int32_t t, int64_t i, uint32_t slot) {
+    const cvb_dist& d = pars.dur[which];
+    if (d.kind == CVB_DIST_ZERO) return 0.0;
+    return dist_from_normal(d, keyed_normal(seed, P_INFECT, 0, t, i, slot));
+}
+
+__global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __grid_constant__ cvb_pars pars, const __grid_constant__ LayerTable L,
+        const __grid_constant__ InfectArgs ia, const int32_t* __restrict__ cand, const unsigned int* __restrict__ n_cand_ptr,
+        unsigned long long* __restrict__ infect_key, const unsigned long long* __restrict__ beds, ResultPtrs res, LogPtrs log) {
+    __shared__ int s_cnt[INF_NK + 3 * CVB_MAX_VARIANTS];
+    const int NK = INF_NK + 3 * CVB_MAX_VARIANTS;
+    if (threadIdx.x < NK) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    int c[INF_NK] = {0, 0};
+    int cv[3 * CVB_MAX_VARIANTS];
+#pragma unroll
+    for (int k = 0; k < 3 * CVB_MAX_VARIANTS; ++k) cv[k] = 0;
+
+    const int64_t n = ia.n;
+    const int32_t t = ia.t;
+    const unsigned int n_cand = *n_cand_ptr;
+    const bool hosp_max = pars.n_beds_hosp >= 0 && (long long)beds[(int64_t)t * 2 + 0] > pars.n_beds_hosp;
+    const bool icu_max = pars.n_beds_icu >= 0 && (long long)beds[(int64_t)t * 2 + 1] > pars.n_beds_icu;
+    const float tf = (float)t;
+
+    for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_cand; j += gridDim.x * blockDim.x) {
+        const int64_t i = cand[j];
+        const unsigned long long key = infect_key[i];
+        infect_key[i] = kEmptyKey;
+        if (key == kEmptyKey) continue;
+        const int v = (int)(key >> 56) & 0x7F;
+        const int lfield = (int)(key >> 48) & 0xFF;
+        const int dir = (int)(key >> 40) & 1;
+        const int64_t e = (int64_t)(key & 0xFFFFFFFFFFull);
+        int32_t source = -1;
+        int layer_code = ia.list_layer_code;
+        if (lfield != 0xFF) {
+            source = dir == 0 ? L.l[lfield].p1[e] : L.l[lfield].p2[e];
+            layer_code = lfield;
+        }
+        if (!PB(P, susceptible)[i]) continue;                      // people.py:470-473
+
+        // breakthrough infections (people.py:486-491, 501)
+        if (PF(P, peak_nab)[i] != 0.0f) {
+            int nb = PI(P, n_breakthroughs)[i];
+            if (nb == 0) PF(P, rel_trans)[i] = fmul(PF(P, rel_trans)[i], pars.trans_redux);
+            PI(P, n_breakthroughs)[i] = nb + 1;
+        }
+        // flags (people.py:494-503)
+        PB(P, susceptible)[i] = 0; PB(P, naive)[i] = 0; PB(P, recovered)[i] = 0; PB(P, diagnosed)[i] = 0; PB(P, exposed)[i] = 1;
+        PI(P, n_infections)[i] += 1;
+        PF(P, exposed_variant)[i] = (float)v;
+        PB(P, exposed_by_variant)[(int64_t)v * n + i] = 1;
+        ++c[INF_INFECTIONS];
+        c[INF_REINFECTIONS] += !is_nan(PF(P, date_recovered)[i]);
+        // infection log (people.py:508-511)
+        {
+            unsigned long long pos = warp_append(log.count);
+            if ((int64_t)pos < log.cap) {
+                log.source[pos] = source; log.target[pos] = (int32_t)i; log.date[pos] = t;
+                log.layer[pos] = (int8_t)layer_code; log.variant[pos] = (int8_t)v;
+            }
+        }
+        // exposed -> infectious (people.py:513-520)
+        const float e2i = (float)draw_dur(pars, CVB_DUR_exp2inf, ia.seed, t, i, 0);
+        PF(P, dur_exp2inf)[i] = e2i;
+        PF(P, date_exposed)[i] = tf;
+        const float d_inf = fadd(e2i, tf);
+        PF(P, date_infectious)[i] = d_inf;
+        float d_symp = nanf32(), d_sev = nanf32(), d_crit = nanf32(), d_rec = nanf32();
+        PF(P, date_diagnosed)[i] = nanf32();
+        float dur_disease;
+        int symp_class;     // 0 asymptomatic, 1 mild, 2 severe (incl. critical) -- for NAb scaling
+        bool is_symp_f = false, is_sev_f = false;
+
+        // prognosis tree (people.py:522-580)
+        const float p_symp = prog_prob_imm(pars.rel_symp[v], PF(P, symp_prob)[i], PF(P, symp_imm)[(int64_t)v * n + i]);
+        if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, i, 1) < (double)p_symp)) {
+            const double d = draw_dur(pars, CVB_DUR_asym2rec, ia.seed, t, i, 2);
+            d_rec = (float)dadd((double)d_inf, d);
+            dur_disease = (float)dadd((double)e2i, d);
+            symp_class = 0;
+        } else {
+            is_symp_f = true;
+            const float i2s = (float)draw_dur(pars, CVB_DUR_inf2sym, ia.seed, t, i, 2);
+            PF(P, dur_inf2sym)[i] = i2s;
+            d_symp = fadd(d_inf, i2s);
+            const float p_sev = prog_prob_imm(pars.rel_severe[v], PF(P, severe_prob)[i], PF(P, sev_imm)[(int64_t)v * n + i]);
+            if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, i, 3) < (double)p_sev)) {
+                const double d = draw_dur(pars, CVB_DUR_mild2rec, ia.seed, t, i, 4);
+                d_rec = (float)dadd((double)d_symp, d);
+                dur_disease = (float)dadd((double)fadd(e2i, i2s), d);
+                symp_class = 1;
+            } else {
+                is_sev_f = true;
+                symp_class = 2;
+                const float s2s = (float)draw_dur(pars, CVB_DUR_sym2sev, ia.seed, t, i, 4);
+                PF(P, dur_sym2sev)[i] = s2s;
+                d_sev = fadd(d_symp, s2s);
+                const float p_crit = prog_prob_fac(pars.rel_crit[v], PF(P, crit_prob)[i], hosp_max ? pars.no_hosp_factor : 1.0f);
+                if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, i, 5) < (double)p_crit)) {
+                    const double d = draw_dur(pars, CVB_DUR_sev2rec, ia.seed, t, i, 6);
+                    d_rec = (float)dadd((double)d_sev, d);
+                    dur_disease = (float)dadd((double)fadd(fadd(e2i, i2s), s2s), d);
+                } else {
+                    const float s2c = (float)draw_dur(pars, CVB_DUR_sev2crit, ia.seed, t, i, 6);
+                    PF(P, dur_sev2crit)[i] = s2c;
+                    d_crit = fadd(d_sev, s2c);
+                    const float p_death = prog_prob_fac(pars.rel_death[v], PF(P, death_prob)[i], icu_max ? pars.no_icu_factor : 1.0f);
+                    const float pre = fadd(fadd(fadd(e2i, i2s), s2s), s2c);
+                    if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, i, 7) < (double)p_death)) {
+                        const double d = draw_dur(pars, CVB_DUR_crit2rec, ia.seed, t, i, 8);
+                        d_rec = (float)dadd((double)d_crit, d);
+                        dur_disease = (float)dadd((double)pre, d);
+                    } else {
+                        const double d = draw_dur(pars, CVB_DUR_crit2die, ia.seed, t, i, 8);
+                        PF(P, date_dead)[i] = (float)dadd((double)d_crit, d);
+                        dur_disease = (float)dadd((double)pre, d);
+                        d_rec = nanf32();
+                    }
+                }
+            }
+        }
+        PF(P, date_symptomatic)[i] = d_symp;
+        PF(P, date_severe)[i] = d_sev;
+        PF(P, date_critical)[i] = d_crit;
+        PF(P, date_recovered)[i] = d_rec;
+        PF(P, dur_disease)[i] = dur_disease;
+#pragma unroll
+        for (int k = 0; k < CVB_MAX_VARIANTS; ++k) {
+            cv[3 * k + 0] += (k == v);
+            cv[3 * k + 1] += (k == v) && is_symp_f;
+            cv[3 * k + 2] += (k == v) && is_sev_f;
+        }
+
+        // NAbs (immunity.py:138-202 with symp != None)
+        if (pars.use_waning) {
+            if (PF(P, nab)[i] > 0.0f) {
+                PF(P, peak_nab)[i] = fmul(PF(P, peak_nab)[i], pars.nab_boost);
+            } else {
+                double x = dist_from_normal(pars.nab_init, keyed_normal(ia.seed, P_INFECT, 0, t, i, 9));
+                double level = pow(2.0, x);
+                double scale = symp_class == 0 ? pars.rel_imm_asymp : (symp_class == 1 ? pars.rel_imm_mild : pars.rel_imm_severe);
+                PF(P, peak_nab)[i] = (float)dmul(dmul(level, scale), pars.nab_norm);
+            }
+            PI(P, t_nab_event)[i] = t;
+        }
+    }
+
+#pragma unroll
+    for (int k = 0; k < INF_NK; ++k) {
+        int w = __reduce_add_sync(0xFFFFFFFFu, c[k]);
+        if (lane_id() == 0 && w) atomicAdd(&s_cnt[k], w);
+    }
+#pragma unroll
+    for (int k = 0; k < 3 * CVB_MAX_VARIANTS; ++k) {
+        int w = __reduce_add_sync(0xFFFFFFFFu, cv[k]);
+        if (lane_id() == 0 && w) atomicAdd(&s_cnt[INF_NK + k], w);
+    }
+    __syncthreads();
+    if (ia.count_flows && threadIdx.x < NK && s_cnt[threadIdx.x]) {
+        const int k = threadIdx.x;
+        const unsigned long long val = (unsigned long long)s_cnt[k];
+        unsigned long long* row = res.counters + (int64_t)t * CVB_N_COUNTERS;
+        if (k == INF_INFECTIONS) atomicAdd(row + CVB_C_new_infections, val);
+        else if (k == INF_REINFECTIONS) atomicAdd(row + CVB_C_new_reinfections, val);
+        else {
+            const int q = k - INF_NK, var = q / 3, which = q % 3;
+            if (var < pars.n_variants) {
+                const int id = which == 0 ? CVB_VC_new_infections_by_variant : (which == 1 ? CVB_VC_new_symptomatic_by_variant : CVB_VC_new_severe_by_variant);
+                atomicAdd(res.vcounters + ((int64_t)t * pars.n_variants + var) * CVB_N_VCOUNTERS + id, val);
+            }
+        }
+    }
+}
+
+// List mode: claim each listed agent once (first occurrence wins, like np.unique(return_index=True))
+__global__ void claim_list_kernel(const int32_t* __restrict__ inds, int64_t n_inds, int32_t variant, int64_t n,
+        unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand) {
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_inds; j += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = inds[j];
+        if (i < 0 || i >= n) continue;
+        unsigned long long key = ((unsigned long long)variant << 56) | (0xFFull << 48) | (unsigned long long)j;
+        unsigned long long old = atomicMin(infect_key + i, key);
+        if (old == kEmptyKey) { unsigned int pos = warp_append32(n_cand); cand[pos] = (int32_t)i; }
+    }
+}
+
+__global__ void reset_u32_kernel(unsigned int* p) { *p = 0; }
+
+static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t list_layer_code, int64_t max_items, cudaStream_t st) {
+    CVB_REQUIRE(s->log.count, "infect: infection log is not bound (cvb_bind_log)");
+    LayerTable L;
+    if (build_layer_table(s, L)) return 1;
+    InfectArgs ia;
+    ia.seed = s->seed; ia.n = s->n; ia.t = t; ia.count_flows = count_flows; ia.list_layer_code = list_layer_code;
+    int grid = grid_for(max_items, kThreads, 148 * 4);
+    infect_kernel<<<grid, kThreads, 0, st>>>(s->people, s->pars, L, ia, s->cand, s->n_cand, s->infect_key, s->beds, s->res, s->log);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace cvb
+
+using namespace cvb;
+
+extern "C" {
+
+int cvb_infect_winners(cvb_sim* s, int32_t t, cvb_stream st) {
+    CVB_REQUIRE(s && s->pars_set && s->res.counters, "cvb_infect_winners: handle not ready");
+    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_infect_winners: day %d outside [0,%d)", t, s->npts);
+    // the number of candidates is only known on the device: size the grid for a large outbreak and let
+    // surplus CTAs exit after one load of n_cand
+    int64_t guess = s->n / 16 + 1024;
+    return launch_infect(s, t, 1, CVB_LAYER_SEED, guess, (cudaStream_t)st);
+}
+
+int cvb_infect_list(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant, int32_t layer_code, int32_t t,
+                    int32_t count_flows, cvb_stream st_) {
+    cudaStream_t st = (cudaStream_t)st_;
+    CVB_REQUIRE(s && s->pars_set && s->res.counters, "cvb_infect_list: handle not ready");
+    CVB_REQUIRE(variant >= 0 && variant < s->nv, "cvb_infect_list: variant %d out of range", variant);
+    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_infect_list: day %d outside [0,%d)", t, s->npts);
+    if (n == 0) return 0;
+    CVB_REQUIRE(inds, "cvb_infect_list: NULL index array");
+    reset_u32_kernel<<<1, 1, 0, st>>>(s->n_cand);
+    CVB_LAUNCH_CHECK();
+    claim_list_kernel<<<grid_for(n), kThreads, 0, st>>>(inds, n, variant, s->n, s->infect_key, s->cand, s->n_cand);
+    CVB_LAUNCH_CHECK();
+    if (launch_infect(s, t, count_flows, layer_code, n, st)) return 1;
+    reset_u32_kernel<<<1, 1, 0, st>>>(s->n_cand);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

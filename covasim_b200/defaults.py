@@ -36,11 +36,10 @@ durs = ('dur_exp2inf', 'dur_inf2sym', 'dur_sym2sev', 'dur_sev2crit', 'dur_diseas
 all_states = (person_fields + states + variant_states + by_variant_states + imm_states
               + nab_states + vacc_states + dates + durs)
 
-# Extra device-only fields that have no counterpart in the reference's People
-#   pend_quar_end : per-agent max end-day of quarantine requests that start today (replaces the
-#                   host dict People._pending_quarantine, reference people.py:116, 335-346, 638)
-#   infect_key    : per-agent 64-bit "winning transmission" key (atomicMin target of the edge pass)
-device_fields = ('pend_quar_end', 'infect_key')
+# Device-only per-agent scratch (the pending-quarantine ring that replaces the host dict
+# People._pending_quarantine, reference people.py:116, 335-346, 638; and the 64-bit "winning
+# transmission" key that the edge pass atomicMin's into) is owned by the library, not bound from here.
+device_fields = ()
 
 
 def field_dtype(name):
@@ -49,8 +48,6 @@ def field_dtype(name):
         return np.bool_
     if name in person_int_fields or name in vacc_states or name == 't_nab_event':
         return default_int
-    if name == 'infect_key':
-        return np.uint64
     return default_float
 
 

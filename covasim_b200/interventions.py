@@ -1,0 +1,266 @@
+'''
+Interventions: the plug-in boundary of the hot path (reference covasim/interventions.py).
+
+``Intervention`` keeps the reference's contract -- ``initialize(sim)``, ``apply(sim)`` called once per
+day from inside ``Sim.step`` in list order, ``finalize(sim)`` -- and plain callables are accepted too
+(reference sim.py:596-597).  Custom interventions read and write ``sim.people.<field>`` device tensors.
+
+The built-ins that appear in the benchmark configurations run as device passes in native-RNG mode:
+``test_prob`` (one per-agent kernel), ``contact_tracing`` (case bitmap + one edge pass per traced layer)
+and ``vaccinate_prob`` (one per-agent kernel); ``change_beta`` only edits parameters.
+'''
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import parameters as cvpar
+from . import _capi
+
+__all__ = ['Intervention', 'change_beta', 'test_prob', 'contact_tracing', 'vaccinate_prob', 'find_day', 'process_days']
+
+
+def find_day(arr, t=None, interv=None, sim=None, which='first'):
+    ''' Indices of ``arr`` equal to day t (reference interventions.py:22-53) '''
+    if callable(arr):
+        arr = np.atleast_1d(arr(interv, sim))
+    all_inds = np.nonzero(np.asarray(arr) == t)[0]
+    if len(all_inds) == 0 or which == 'all':
+        return all_inds
+    return [all_inds[0]] if which == 'first' else [all_inds[-1]]
+
+
+def process_days(sim, days):
+    ''' Sorted integer day array (reference interventions.py:78-99) '''
+    if callable(days):
+        return days
+    days = list(np.atleast_1d(days)) if not isinstance(days, str) else [days]
+    out = []
+    for d in days:
+        if d in ['end', -1]:
+            d = sim['end_day']
+        out.append(sim.day(d))
+    return np.sort(np.array(out))
+
+
+class Intervention:
+    ''' Base class (reference interventions.py:223-410) '''
+
+    def __init__(self, label=None, **kwargs):
+        self.label = label if label is not None else self.__class__.__name__
+        self.days = []
+        self.initialized = False
+        self.finalized = False
+
+    def __call__(self, *args, **kwargs):
+        if not self.initialized:
+            raise RuntimeError(f'Intervention (label={self.label}, {type(self)}) has not been initialized')
+        return self.apply(*args, **kwargs)
+
+    def initialize(self, sim=None):
+        self.initialized = True
+        self.finalized = False
+
+    def finalize(self, sim=None):
+        if self.finalized:
+            raise RuntimeError('Intervention already finalized')
+        self.finalized = True
+
+    def apply(self, sim):
+        raise NotImplementedError
+
+    def shrink(self, in_place=False):
+        return self
+
+
+class change_beta(Intervention):
+    ''' Scale overall or per-layer beta on given days (reference interventions.py:533-586) '''
+
+    def __init__(self, days, changes, layers=None, **kwargs):
+        super().__init__(**kwargs)
+        self.days, self.changes, self.layers = days, changes, layers
+        self.orig_betas = None
+
+    def initialize(self, sim):
+        super().initialize()
+        self.days = process_days(sim, self.days)
+        self.changes = np.atleast_1d(np.array(self.changes, dtype=float))
+        if len(self.days) != len(self.changes):
+            raise ValueError(f'Number of days supplied ({len(self.days)}) does not match number of changes ({len(self.changes)})')
+        layers = self.layers if isinstance(self.layers, (list, tuple)) else [self.layers]
+        self.orig_betas = {}
+        for lk in layers:
+            self.orig_betas['overall' if lk is None else lk] = sim['beta'] if lk is None else sim['beta_layer'][lk]
+
+    def apply(self, sim):
+        for ind in find_day(self.days, sim.t, interv=self, sim=sim):
+            for lk, b in self.orig_betas.items():
+                if lk == 'overall':
+                    sim['beta'] = b * self.changes[ind]
+                else:
+                    sim['beta_layer'][lk] = b * self.changes[ind]
+
+
+_QUAR_POLICY = dict(start=0, end=1, both=2, daily=3)
+
+
+class test_prob(Intervention):
+    '''
+    Probability-based testing (reference interventions.py:857-981 + people.py:589-617).  One per-agent
+    device pass: test probability from symptom / quarantine / diagnosis state, keyed Bernoulli draws
+    for "tests today", "test is positive" (sensitivity) and "not lost to follow-up".
+    Not built: swab_delay, ili_prev, subtarget, callable quar_policy.
+    '''
+
+    def __init__(self, symp_prob, asymp_prob=0.0, symp_quar_prob=None, asymp_quar_prob=None, quar_policy=None, subtarget=None,
+                 ili_prev=None, sensitivity=1.0, loss_prob=0.0, test_delay=0, start_day=0, end_day=None, swab_delay=None, **kwargs):
+        super().__init__(**kwargs)
+        if subtarget is not None or ili_prev is not None or swab_delay is not None:
+            raise NotImplementedError('test_prob: subtarget / ili_prev / swab_delay are outside the built path')
+        self.symp_prob, self.asymp_prob = symp_prob, asymp_prob
+        self.symp_quar_prob = symp_prob if symp_quar_prob is None else symp_quar_prob
+        self.asymp_quar_prob = asymp_prob if asymp_quar_prob is None else asymp_quar_prob
+        self.quar_policy = quar_policy if quar_policy else 'start'
+        if self.quar_policy not in _QUAR_POLICY:
+            raise NotImplementedError(f'test_prob: quar_policy "{self.quar_policy}" is not built (choices: {list(_QUAR_POLICY)})')
+        self.sensitivity, self.loss_prob, self.test_delay = sensitivity, loss_prob, test_delay
+        self.start_day, self.end_day = start_day, end_day
+
+    def initialize(self, sim):
+        super().initialize()
+        self.start_day = sim.day(self.start_day)
+        self.end_day = sim.day(self.end_day)
+        self.days = [self.start_day, self.end_day]
+        self.index = sim.intervention_index(self)
+        self._c = _capi.cvb_test_prob_pars(symp_prob=self.symp_prob, asymp_prob=self.asymp_prob, symp_quar_prob=self.symp_quar_prob,
+                                           asymp_quar_prob=self.asymp_quar_prob, sensitivity=self.sensitivity, loss_prob=self.loss_prob,
+                                           quar_policy=_QUAR_POLICY[self.quar_policy], test_delay=int(self.test_delay), index=self.index)
+
+    def apply(self, sim):
+        t = sim.t
+        if t < self.start_day or (self.end_day is not None and t > self.end_day):
+            return
+        _capi.call('cvb_test_prob', sim._handle, t, C.byref(self._c), sim._stream_ptr)
+
+
+class contact_tracing(Intervention):
+    '''
+    Trace the contacts of today's newly diagnosed agents and queue their quarantine (reference
+    interventions.py:984-1145).  Device form: bitmap of today's cases, then one streaming pass over each
+    traced layer's (p1, p2) that notifies the partner of every case with a Bernoulli(trace_prob) keyed
+    per (layer, contact) -- the reference's binomial_filter over the unique contact set.
+    Not built: capacity.
+    '''
+
+    def __init__(self, trace_probs=None, trace_time=None, start_day=0, end_day=None, presumptive=False, quar_period=None, capacity=None, **kwargs):
+        super().__init__(**kwargs)
+        if capacity is not None:
+            raise NotImplementedError('contact_tracing: capacity is outside the built path')
+        self.trace_probs, self.trace_time = trace_probs, trace_time
+        self.start_day, self.end_day, self.presumptive, self.quar_period = start_day, end_day, presumptive, quar_period
+
+    def initialize(self, sim):
+        super().initialize()
+        self.start_day = sim.day(self.start_day)
+        self.end_day = sim.day(self.end_day)
+        self.days = [self.start_day, self.end_day]
+        lkeys = sim.people.layer_keys()
+        tp = 1.0 if self.trace_probs is None else self.trace_probs
+        tt = 0.0 if self.trace_time is None else self.trace_time
+        self.trace_probs = dict(tp) if isinstance(tp, dict) else {k: tp for k in lkeys}
+        self.trace_time = dict(tt) if isinstance(tt, dict) else {k: tt for k in lkeys}
+        if self.quar_period is None:
+            self.quar_period = sim['quar_period']
+        self.index = sim.intervention_index(self)
+        c = _capi.cvb_trace_pars(presumptive=int(bool(self.presumptive)), quar_period=int(self.quar_period), index=self.index)
+        for i, lk in enumerate(lkeys):
+            c.trace_prob[i] = float(self.trace_probs.get(lk, 0.0))
+            c.trace_time[i] = int(self.trace_time.get(lk, 0))
+        self._c = c
+        sim._set_quar_horizon(int(max(self.trace_time.values(), default=0)) + 1)
+
+    def apply(self, sim):
+        t = sim.t
+        if t < self.start_day or (self.end_day is not None and t > self.end_day):
+            return
+        _capi.call('cvb_contact_tracing', sim._handle, t, C.byref(self._c), sim._stream_ptr)
+
+
+class vaccinate_prob(Intervention):
+    '''
+    Probability-based vaccination with scheduled second doses (reference interventions.py:1257-1662).
+    One per-agent device pass on first-dose days and on days when second doses are due.
+    Not built: subtarget, target_eff.
+    '''
+
+    def __init__(self, vaccine, days, label=None, prob=None, subtarget=None, booster=False, **kwargs):
+        super().__init__(**kwargs)
+        if subtarget is not None:
+            raise NotImplementedError('vaccinate_prob: subtarget is outside the built path')
+        self.vaccine, self.days, self.label = vaccine, days, label
+        self.prob = 1.0 if prob is None else prob
+        self.booster = booster
+        self.index = None
+        self.p = None
+
+    def initialize(self, sim):
+        super().initialize()
+        if isinstance(self.vaccine, str):
+            choices, mapping = cvpar.get_vaccine_choices()
+            key = self.vaccine.lower()
+            for txt in ['.', ' ', '&', '-', 'vaccine']:
+                key = key.replace(txt, '')
+            if key not in mapping:
+                raise NotImplementedError(f'The selected vaccine "{self.vaccine}" is not implemented; choices are: {choices}')
+            key = mapping[key]
+            self.p = dict(cvpar.get_vaccine_variant_pars(vaccine=key))
+            self.p.update(cvpar.get_vaccine_dose_pars(vaccine=key))
+            if self.label is None:
+                self.label = key
+        elif isinstance(self.vaccine, dict):
+            self.p = dict(self.vaccine)
+            if self.label is None:
+                self.label = self.p.pop('label', 'custom')
+        else:
+            raise ValueError(f'Could not understand vaccine of type {type(self.vaccine)}')
+        if 'target_eff' in self.p:
+            raise NotImplementedError('vaccinate_prob: target_eff is outside the built path')
+        for k, v in cvpar.get_vaccine_dose_pars(default=True).items():
+            self.p.setdefault(k, v)
+        dflt = cvpar.get_vaccine_variant_pars(default=True)
+        for k in sim['variant_pars'].keys():
+            self.p.setdefault(k, dflt.get(k, 1.0))
+        doses, interval = self.p['doses'], self.p['interval']
+        if doses == 1 and interval is not None:
+            raise ValueError("Can't use dosing intervals for vaccines with only one dose.")
+        if doses == 2 and interval is None:
+            raise ValueError('Must specify a dosing interval if using a vaccine with more than one dose.')
+        if doses > 2:
+            raise NotImplementedError('Scheduling three or more doses not yet supported; use a booster vaccine instead')
+        sim['vaccine_pars'][self.label] = self.p
+        self.index = list(sim['vaccine_pars'].keys()).index(self.label)
+        sim['vaccine_map'][self.index] = self.label
+        self.days = process_days(sim, self.days)
+        self.iindex = sim.intervention_index(self)
+        dev = sim.people.device
+        self.doses = torch.zeros(sim.n, dtype=torch.int32, device=dev)              # doses given by *this* intervention
+        self.due_day = torch.full((sim.n,), -1, dtype=torch.int32, device=dev)     # device form of second_dose_days
+        self._due_days = set()
+        self._c = _capi.cvb_vaccinate_pars(prob=float(self.prob), nab_init=_capi.dist_struct(self.p['nab_init']), nab_boost=float(self.p['nab_boost']),
+                                           booster=int(bool(self.booster)), vaccine_index=self.index, max_doses=int(doses), index=self.iindex,
+                                           interval=-1 if interval is None else int(interval), n_days=int(sim['n_days']))
+        sim._pars_dirty = True
+
+    def apply(self, sim):
+        t = sim.t
+        if t < np.min(self.days):
+            return
+        first = bool(np.any(self.days == t))
+        if first and self.p['interval'] is not None and t + self.p['interval'] < sim['n_days']:
+            self._due_days.add(t + int(self.p['interval']))
+        second = t in self._due_days
+        if not (first or second):
+            return
+        self._c.first_dose_today = int(first)
+        self._c.second_dose_today = int(second)
+        _capi.call('cvb_vaccinate_prob', sim._handle, t, C.byref(self._c), self.doses.data_ptr(), self.due_day.data_ptr(), sim._stream_ptr)

@@ -1,0 +1,194 @@
+'''
+People: the structure-of-arrays agent state, resident on the GPU (reference covasim/people.py,
+base.py:877-1465).
+
+Every field of ``defaults.all_states`` is one device tensor (bool -> torch.bool, one byte per agent, the
+same layout as the reference's NumPy bool arrays; float32 dates with NaN = "not set"; int32 counters)
+bound once to the simulation handle, so kernels and Python interventions see the same memory.
+``people.<field>`` / ``people[<field>]`` return the tensor; assignment copies in place so the bound
+pointer never changes.
+'''
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import defaults as cvd
+from . import utils as cvu
+from . import _capi
+from .base import Contacts, Layer
+
+__all__ = ['People']
+
+_TORCH_DTYPE = {np.dtype(np.bool_): torch.bool, np.dtype(np.int32): torch.int32, np.dtype(np.float32): torch.float32}
+
+
+class People:
+
+    def __init__(self, pars, device, uid=None, age=None, sex=None, contacts=None):
+        object.__setattr__(self, '_arrays', {})
+        self.pars = pars
+        self.device = torch.device(device)
+        self.t = 0
+        n = int(pars['pop_size'])
+        nv = int(pars['n_variants'])
+        self.n, self.nv = n, nv
+        self._sim = None
+        self.infection_log_cap = 0
+        A = self._arrays
+        for name in cvd.all_states:
+            dt = _TORCH_DTYPE[np.dtype(cvd.field_dtype(name))]
+            shape = (nv, n) if cvd.field_is_2d(name) else (n,)
+            if name == 'uid':
+                A[name] = torch.arange(n, dtype=torch.int32, device=self.device)
+            elif name in cvd.states:
+                A[name] = torch.full(shape, name in ('susceptible', 'naive'), dtype=dt, device=self.device)
+            elif dt == torch.float32 and name not in cvd.imm_states and name not in ('peak_nab', 'nab'):
+                A[name] = torch.full(shape, float('nan'), dtype=dt, device=self.device)
+            else:
+                A[name] = torch.zeros(shape, dtype=dt, device=self.device)
+        if age is not None:
+            self['age'] = age
+        if sex is not None:
+            self['sex'] = sex
+        self.contacts = Contacts()
+        if contacts is not None:
+            for lk, layer in contacts.items():
+                if not isinstance(layer, Layer):
+                    layer = Layer(layer['p1'], layer['p2'], layer.get('beta'), label=lk, device=self.device)
+                else:
+                    layer.to(self.device)
+                self.contacts[lk] = layer
+
+    # ---- array access -------------------------------------------------------------------------
+    def __getattr__(self, name):
+        arrays = object.__getattribute__(self, '_arrays')
+        if name in arrays:
+            return arrays[name]
+        raise AttributeError(name)
+
+    def __setattr__(self, name, value):
+        if name in self._arrays:
+            self[name] = value
+        else:
+            object.__setattr__(self, name, value)
+
+    def __getitem__(self, key):
+        return self._arrays[key]
+
+    def __setitem__(self, key, value):
+        ''' In-place assignment: keeps the device pointer bound to the kernels valid '''
+        dst = self._arrays[key]
+        src = value if isinstance(value, torch.Tensor) else torch.as_tensor(np.asarray(value))
+        dst.copy_(src.to(device=dst.device, dtype=dst.dtype) if src.shape == dst.shape else src.to(device=dst.device, dtype=dst.dtype).expand_as(dst))
+
+    def __len__(self):
+        return self.n
+
+    def keys(self):
+        return list(self._arrays.keys())
+
+    def layer_keys(self):
+        return list(self.contacts.keys())
+
+    def to_numpy(self, key):
+        return self._arrays[key].cpu().numpy()
+
+    # ---- counting helpers (reference base.py:1091-1145) -----------------------------------------
+    def true(self, key):
+        return cvu.true(self[key])
+
+    def false(self, key):
+        return cvu.false(self[key])
+
+    def defined(self, key):
+        return cvu.defined(self[key])
+
+    def undefined(self, key):
+        return cvu.undefined(self[key])
+
+    def count(self, key):
+        return int(torch.count_nonzero(self[key]).item())
+
+    def count_by_variant(self, key, variant):
+        return int(torch.count_nonzero(self[key][variant, :]).item())
+
+    def count_not(self, key):
+        return self.n - self.count(key)
+
+    # ---- binding --------------------------------------------------------------------------------
+    def _bind(self, sim):
+        self._sim = sim
+        for name, fid in cvd.FIELD_IDS.items():
+            _capi.call('cvb_bind_field', sim._handle, fid, self._arrays[name].data_ptr())
+        for i, layer in enumerate(self.contacts.values()):
+            layer._bind(sim, i)
+
+    # ---- prognoses (reference people.py:139-161) ------------------------------------------------
+    def set_prognoses(self, rng):
+        pars = self.pars
+        rng.set_seed(pars['rand_seed'])
+        progs = pars['prognoses']
+        age = self.to_numpy('age')
+        inds = np.digitize(age, progs['age_cutoffs']) - 1
+        self['symp_prob'] = progs['symp_probs'][inds]
+        self['severe_prob'] = progs['severe_probs'][inds] * progs['comorbidities'][inds]
+        self['crit_prob'] = progs['crit_probs'][inds]
+        self['death_prob'] = progs['death_probs'][inds]
+        self['rel_sus'] = progs['sus_ORs'][inds]
+        bd = pars['beta_dist']
+        if bd['dist'] != 'neg_binomial':
+            raise NotImplementedError('beta_dist must be neg_binomial')
+        step = bd.get('step', 1)
+        p = bd['par2'] / (bd['par1'] / step + bd['par2'])                                    # reference utils.py:409-426
+        draws = rng.np_.negative_binomial(n=bd['par2'], p=p, size=len(inds)) * step
+        self['rel_trans'] = progs['trans_ORs'][inds] * draws
+
+    # ---- events ---------------------------------------------------------------------------------
+    def infect(self, inds, hosp_max=None, icu_max=None, source=None, layer=None, variant=0, count_flows=True):
+        '''
+        Infect agents and sample their disease course on the device (reference people.py:435-586).
+        ``hosp_max`` / ``icu_max`` are evaluated on the device from the day's severe / critical counts;
+        duplicates and non-susceptible agents are dropped.  ``source`` is not needed: importations and seed
+        infections have none, and transmissions are infected by the fused edge pass.
+        '''
+        sim = self._sim
+        inds = torch.as_tensor(inds, dtype=torch.int32, device=self.device).contiguous()
+        if len(inds) == 0:
+            return inds
+        code = {'seed_infection': _capi.LAYER_SEED, 'importation': _capi.LAYER_IMPORT}.get(layer, _capi.LAYER_IMPORT)
+        _capi.call('cvb_infect_list', sim._handle, inds.data_ptr(), len(inds), int(variant), code, int(sim.t), int(bool(count_flows)), sim._stream_ptr)
+        return inds
+
+    def schedule_quarantine(self, inds, start_date=None, period=None):
+        ''' Queue quarantine requests on the device ring (reference people.py:620-640) '''
+        sim = self._sim
+        start_date = sim.t if start_date is None else int(start_date)
+        period = self.pars['quar_period'] if period is None else int(period)
+        if start_date - sim.t + 1 > sim._quar_horizon:
+            sim._set_quar_horizon(start_date - sim.t + 1)
+        inds = torch.as_tensor(inds, dtype=torch.int32, device=self.device).contiguous()
+        if len(inds):
+            _capi.call('cvb_schedule_quarantine', sim._handle, inds.data_ptr(), len(inds), start_date, float(start_date + period), sim._stream_ptr)
+
+    def make_naive(self, inds, reset_vx=False):
+        ''' Reset agents to the never-infected state (reference people.py:378-409) '''
+        inds = torch.as_tensor(inds, dtype=torch.int64, device=self.device)
+        A = self._arrays
+        for key in cvd.states:
+            if key in ('susceptible', 'naive'):
+                A[key][inds] = True
+            elif key != 'vaccinated' or reset_vx:
+                A[key][inds] = False
+        for key in cvd.variant_states:
+            A[key][inds] = float('nan')
+        for key in cvd.by_variant_states:
+            A[key][:, inds] = False
+        non_vx = inds if reset_vx else inds[~A['vaccinated'][inds]]
+        for key in cvd.imm_states:
+            A[key][:, non_vx] = 0
+        for key in cvd.nab_states + cvd.vacc_states:
+            A[key][non_vx] = 0
+        for key in cvd.dates + cvd.durs:
+            if key != 'date_vaccinated' or reset_vx:
+                A[key][inds] = float('nan')

@@ -1,0 +1,568 @@
+'''
+Sim: host-side orchestration of one simulation (reference covasim/sim.py).
+
+The host stays Python and keeps the reference's public contract -- ``Sim(pars, **kwargs)``,
+``initialize() / step() / run(until) / finalize()``, ``sim[par]``, ``sim.results[key].values``,
+``sim.summary``, ``sim.people``, interventions and analyzers called once per day from inside ``step``
+(reference sim.py:558-685) -- while every per-agent and per-edge computation of the day runs as CUDA
+kernels on device-resident People / Layer arrays through the C ABI (include/covasim_b200.h).
+
+Per-day results are accumulated on the device (one row of int64 counters per day) and copied to the host
+once, in ``finalize`` (or on demand through ``sync_results``); ``step`` never synchronises with the GPU.
+'''
+import copy
+import ctypes as C
+import datetime as dt
+
+import numpy as np
+import torch
+
+from . import defaults as cvd
+from . import parameters as cvpar
+from . import population as cvpop
+from . import immunity as cvimm
+from . import utils as cvu
+from . import _capi
+from .base import Result, AlreadyRunError
+from .people import People
+
+__all__ = ['Sim']
+
+f32 = np.float32
+
+
+class Sim:
+
+    def __init__(self, pars=None, popdict=None, label=None, device=None, rng='philox', pop_exact=None, **kwargs):
+        kw = dict(pars or {})
+        kw.update(kwargs)
+        for alias, key in (('n_agents', 'pop_size'), ('init_infected', 'pop_infected')):       # reference base.py:266-273
+            if alias in kw:
+                kw[key] = kw.pop(alias)
+        self.pars = cvpar.make_pars(**kw)
+        self.pars['pop_size'] = int(self.pars['pop_size'])
+        for key in ('interventions', 'analyzers', 'variants'):
+            if not isinstance(self.pars[key], list):
+                self.pars[key] = [self.pars[key]]
+        if rng not in ('philox',):
+            raise NotImplementedError(f'rng mode "{rng}" is not available (choices: philox)')
+        self.rng_mode = rng
+        self.label = label
+        self.popdict = popdict
+        self.pop_exact = pop_exact
+        self.device = torch.device(device) if device is not None else torch.device('cuda', torch.cuda.current_device() if torch.cuda.is_available() else 0)
+        self.rng = cvu.HostStreams()
+        self.people = None
+        self.results = {}
+        self.summary = None
+        self.t = None
+        self.initialized = False
+        self.complete = False
+        self.results_ready = False
+        self._handle = None
+        self._stream_ptr = None
+        self._orig_pars = None
+        self._pars_key = None
+        self._pars_dirty = True
+        self._quar_horizon = 1
+        self._host_adds = {}
+
+    # ---- dict-like parameter access (reference base.py:63-114) -----------------------------------
+    def __getitem__(self, key):
+        try:
+            return self.pars[key]
+        except KeyError:
+            raise KeyError(f'Key "{key}" not found; available keys: {", ".join(self.pars.keys())}')
+
+    def __setitem__(self, key, value):
+        if key not in self.pars:
+            raise KeyError(f'Key "{key}" not found; available keys: {", ".join(self.pars.keys())}')
+        self.pars[key] = value
+
+    def __del__(self):
+        self._destroy()
+
+    def _destroy(self):
+        h, self._handle = getattr(self, '_handle', None), None
+        if h is not None:
+            try:
+                _capi.lib.cvb_destroy(h)
+            except Exception:
+                pass
+
+    # ---- time helpers (reference base.py:325-441) --------------------------------------------------
+    @property
+    def n(self):
+        return int(self.pars['pop_size'])
+
+    @property
+    def npts(self):
+        return int(self.pars['n_days']) + 1
+
+    @property
+    def tvec(self):
+        return np.arange(self.npts)
+
+    @property
+    def scaled_pop_size(self):
+        return self.pars['pop_size'] * self.pars['pop_scale']
+
+    def _start_date(self):
+        sd = self.pars['start_day']
+        if isinstance(sd, str):
+            return dt.datetime.strptime(sd, '%Y-%m-%d').date()
+        if isinstance(sd, dt.datetime):
+            return sd.date()
+        if isinstance(sd, dt.date):
+            return sd
+        return dt.date(2020, 3, 1) + dt.timedelta(days=int(sd))
+
+    def day(self, day, *args):
+        ''' Convert a date / string / int to a day index (reference base.py:346-389) '''
+        if day is None:
+            return None
+        if isinstance(day, (int, np.integer, float)):
+            return int(day)
+        if isinstance(day, str):
+            day = dt.datetime.strptime(day, '%Y-%m-%d').date()
+        if isinstance(day, dt.datetime):
+            day = day.date()
+        return (day - self._start_date()).days
+
+    def date(self, ind, as_date=False):
+        ''' Convert a day index to a date string (reference base.py:392-430) '''
+        d = self._start_date() + dt.timedelta(days=int(ind))
+        return d if as_date else d.strftime('%Y-%m-%d')
+
+    @property
+    def datevec(self):
+        return [self.date(i) for i in range(self.npts)]
+
+    def result_keys(self, which='main'):
+        if which == 'variant':
+            return list(self.results['variant'].keys())
+        return [k for k in self.results.keys() if isinstance(self.results[k], Result)]
+
+    def intervention_index(self, obj):
+        return [id(i) for i in self.pars['interventions']].index(id(obj))
+
+    def get_interventions(self, which=None):
+        ivs = self.pars['interventions']
+        if which is None:
+            return list(ivs)
+        if isinstance(which, int):
+            return ivs[which]
+        return [i for i in ivs if (isinstance(which, type) and isinstance(i, which)) or getattr(i, 'label', None) == which]
+
+    def copy(self):
+        ''' Deep copy of an un-initialised or host-only sim (device state is rebuilt by initialize) '''
+        if self.initialized:
+            raise NotImplementedError('copying an initialized sim is not built; copy before initialize()')
+        return copy.deepcopy(self)
+
+    # ---- initialisation (reference sim.py:94-125) --------------------------------------------------
+    def set_seed(self, seed=-1):
+        if seed != -1:
+            self.pars['rand_seed'] = seed
+        self.rng.set_seed(self.pars['rand_seed'])
+        if self._handle is not None:
+            _capi.call('cvb_set_seed', self._handle, int(self.rng.seed))
+
+    def initialize(self, reset=False, init_infections=True, **kwargs):
+        if not torch.cuda.is_available():
+            raise _capi.CvbError('covasim_b200 needs a CUDA device: there is no CPU fallback')
+        pars = self.pars
+        self.t = 0
+        self._validate_pars()
+        self.set_seed()
+        for v in pars['variants']:
+            if not isinstance(v, cvimm.variant):
+                raise TypeError(f'Variant {v} is not a cv.variant object; please create using cv.variant()')
+            if not v.initialized:
+                v.initialize(self)
+        pars['n_variants'] = len(pars['variant_pars'])
+        if pars['n_variants'] > _capi.MAX_VARIANTS:
+            raise ValueError(f'at most {_capi.MAX_VARIANTS} variants are supported')
+        cvimm.init_immunity(self)
+        self._init_results()
+        self._init_people(**kwargs)
+        self._create_handle()
+        if init_infections:
+            self.init_infections()
+        for iv in pars['interventions']:
+            if hasattr(iv, 'initialize'):
+                iv.initialize(self)
+        for an in pars['analyzers']:
+            if hasattr(an, 'initialize'):
+                an.initialize(self)
+        self.set_seed()
+        self.initialized = True
+        self.complete = False
+        self.results_ready = False
+        self._orig_pars = None
+        return self
+
+    def _validate_pars(self):
+        pars = self.pars
+        if pars['end_day'] is not None:
+            pars['n_days'] = self.day(pars['end_day'])
+        pars['n_days'] = int(pars['n_days'])
+        if pars['pop_scale'] != 1 and pars['rescale']:
+            raise NotImplementedError('dynamic rescaling (pop_scale > 1 with rescale=True; reference sim.py:535-555) is not built; use rescale=False')
+        if pars['frac_susceptible'] < 1:
+            raise NotImplementedError('frac_susceptible < 1 is not built')
+
+    def _init_results(self):
+        ''' Result containers (reference sim.py:284-351) '''
+        npts, nv = self.npts, self.pars['n_variants']
+        R = {}
+        for k in cvd.cum_result_flows + cvd.new_result_flows + tuple(f'n_{s}' for s in cvd.result_stocks):
+            R[k] = Result(k, npts=npts)
+        for k in cvd.other_results:
+            R[k] = Result(k, npts=npts, scale=k not in cvd.unscaled_results)
+        V = {}
+        for k in ('prevalence_by_variant', 'incidence_by_variant'):
+            V[k] = Result(k, npts=npts, scale=False, n_variants=nv)
+        for k in cvd.cum_result_flows_by_variant + cvd.new_result_flows_by_variant + tuple(f'n_{s}' for s in cvd.result_stocks_by_variant):
+            V[k] = Result(k, npts=npts, n_variants=nv)
+        R['variant'] = V
+        R['date'] = self.datevec
+        R['t'] = self.tvec
+        self.results = R
+        scale = 1 if self.pars['rescale'] else self.pars['pop_scale']
+        self.rescale_vec = scale * np.ones(npts)
+        self.results_ready = False
+        self._host_adds = {}
+
+    def _init_people(self, **kwargs):
+        pars = self.pars
+        if pars['prognoses'] is None:
+            pars['prognoses'] = cvpar.get_prognoses(pars['prog_by_age'])
+        pop = self.popdict
+        if pop is None:
+            exact = self.pop_exact if self.pop_exact is not None else (pars['pop_size'] <= 200_000)
+            pop = cvpop.make_randpop(pars, self.rng, exact=exact)
+        self.people = People(pars, self.device, age=pop['age'], sex=pop['sex'], contacts=pop['contacts'])
+        self.popdict = None
+        lkeys = self.people.layer_keys()
+        if len(lkeys) > _capi.MAX_LAYERS:
+            raise ValueError(f'at most {_capi.MAX_LAYERS} contact layers are supported')
+        cvpar.reset_layer_pars(pars, layer_keys=lkeys, force=False)
+        self.people.set_prognoses(self.rng)
+
+    def _create_handle(self):
+        self._destroy()
+        pars = self.pars
+        npts, nv = self.npts, pars['n_variants']
+        h = C.c_void_p()
+        _capi.call('cvb_create', C.byref(h), self.n, nv, npts, int(pars['rand_seed']))
+        self._handle = h
+        self._stream_ptr = None            # legacy default stream; torch's current stream is the same unless changed
+        dev = self.device
+        self._counters = torch.zeros((npts, cvd.N_COUNTERS), dtype=torch.int64, device=dev)
+        self._vcounters = torch.zeros((npts, nv, cvd.N_VCOUNTERS), dtype=torch.int64, device=dev)
+        self._sums = torch.zeros((npts, 4), dtype=torch.float64, device=dev)
+        _capi.call('cvb_bind_results', h, self._counters.data_ptr(), self._vcounters.data_ptr(), self._sums.data_ptr())
+        cap = int(max(4 * self.n, 1024))
+        self._log = dict(source=torch.empty(cap, dtype=torch.int32, device=dev), target=torch.empty(cap, dtype=torch.int32, device=dev),
+                         date=torch.empty(cap, dtype=torch.int32, device=dev), layer=torch.empty(cap, dtype=torch.int8, device=dev),
+                         variant=torch.empty(cap, dtype=torch.int8, device=dev), count=torch.zeros(1, dtype=torch.int64, device=dev))
+        L = self._log
+        _capi.call('cvb_bind_log', h, L['source'].data_ptr(), L['target'].data_ptr(), L['date'].data_ptr(), L['layer'].data_ptr(),
+                   L['variant'].data_ptr(), cap, L['count'].data_ptr())
+        self.people._bind(self)
+        if pars['use_waning']:
+            kin = np.ascontiguousarray(pars['nab_kin'], dtype=np.float64)
+            _capi.call('cvb_set_nab_kin', h, kin.ctypes.data, len(kin))
+        self._quar_horizon = 1
+        self._pars_dirty = True
+        self._push_pars()
+
+    def _set_quar_horizon(self, horizon):
+        if horizon > self._quar_horizon:
+            _capi.call('cvb_set_quar_horizon', self._handle, int(horizon))
+            self._quar_horizon = int(horizon)
+
+    # ---- parameters -> device struct ---------------------------------------------------------------
+    def _pars_fingerprint(self):
+        p = self.pars
+        return (p['beta'], p['rel_beta'], p['asymp_factor'], tuple(p['beta_layer'].values()), tuple(p['iso_factor'].values()),
+                tuple(p['quar_factor'].values()), p['n_beds_hosp'], p['n_beds_icu'], p['no_hosp_factor'], p['no_icu_factor'],
+                p['rel_symp_prob'], p['rel_severe_prob'], p['rel_crit_prob'], p['rel_death_prob'], p['trans_redux'], p['nab_boost'],
+                tuple(tuple(v.values()) for v in p['variant_pars'].values()), len(p['vaccine_pars']), p['quar_period'],
+                tuple(p['viral_dist'].values()))
+
+    def _push_pars(self):
+        ''' Re-send the scalar block when an intervention changed a parameter (reference sim.py:602-642 re-reads them daily) '''
+        key = self._pars_fingerprint()
+        if not self._pars_dirty and key == self._pars_key:
+            return
+        p = self.pars
+        nv = p['n_variants']
+        lkeys = self.people.layer_keys()
+        c = _capi.cvb_pars()
+        c.n_variants, c.n_layers, c.use_waning, c.n_vaccines = nv, len(lkeys), int(bool(p['use_waning'])), len(p['vaccine_pars'])
+        c.quar_period = int(p['quar_period'])
+        c.has_vaccine_pars = int(len(p['vaccine_pars']) > 0)
+        c.n_beds_hosp = -1 if p['n_beds_hosp'] is None else int(p['n_beds_hosp'])
+        c.n_beds_icu = -1 if p['n_beds_icu'] is None else int(p['n_beds_icu'])
+        c.asymp_factor = p['asymp_factor']
+        vd = p['viral_dist']
+        c.frac_time, c.load_ratio, c.high_cap = vd['frac_time'], vd['load_ratio'], vd['high_cap']
+        c.trans_redux, c.no_hosp_factor, c.no_icu_factor, c.nab_boost = p['trans_redux'], p['no_hosp_factor'], p['no_icu_factor'], p['nab_boost']
+        for v in range(nv):
+            vp = p['variant_pars'][p['variant_map'][v]]
+            c.beta[v] = float(f32(p['beta'] * p['rel_beta'] * vp['rel_beta']))                # reference sim.py:627
+            for name, key_ in (('rel_symp', 'rel_symp_prob'), ('rel_severe', 'rel_severe_prob'), ('rel_crit', 'rel_crit_prob'), ('rel_death', 'rel_death_prob')):
+                val = p[key_] * (vp[key_] if v else 1.0)                                       # reference people.py:476-481
+                getattr(c, name)[v] = float(f32(val))
+        for i, lk in enumerate(lkeys):
+            c.beta_layer[i], c.iso_factor[i], c.quar_factor[i] = p['beta_layer'][lk], p['iso_factor'][lk], p['quar_factor'][lk]
+        if p['use_waning']:
+            imm = np.asarray(p['immunity'], dtype=np.float32)
+            for a in range(nv):
+                for b in range(nv):
+                    c.immunity[a][b] = float(imm[a, b])
+            for num, vkey in p['vaccine_map'].items():
+                if num >= _capi.MAX_VACCINES:
+                    raise ValueError(f'at most {_capi.MAX_VACCINES} vaccines are supported')
+                for v in range(nv):
+                    c.vaccine_imm[num][v] = float(p['vaccine_pars'][vkey][p['variant_map'][v]])
+            e = p['nab_eff']
+            c.exp_alpha_inf, c.beta_inf = float(np.exp(e['alpha_inf'])), e['beta_inf']
+            c.exp_alpha_symp_inf, c.beta_symp_inf = float(np.exp(e['alpha_symp_inf'])), e['beta_symp_inf']
+            c.exp_alpha_sev_symp, c.beta_sev_symp = float(np.exp(e['alpha_sev_symp'])), e['beta_sev_symp']
+            c.nab_norm = 1 + e['alpha_inf_diff']
+            ris = p['rel_imm_symp']
+            c.rel_imm_asymp, c.rel_imm_mild, c.rel_imm_severe = ris['asymp'], ris['mild'], ris['severe']
+            c.nab_init = _capi.dist_struct(p['nab_init'])
+        for i, name in enumerate(_capi.DUR_ORDER):
+            c.dur[i] = _capi.dist_struct(p['dur'][name])
+        _capi.call('cvb_set_pars', self._handle, C.byref(c))
+        self._cpars = c
+        self._pars_key = key
+        self._pars_dirty = False
+
+    # ---- seeding (reference sim.py:505-532) ----------------------------------------------------------
+    def init_infections(self, force=False):
+        pars = self.pars
+        if pars['pop_infected']:
+            inds = self.rng.nb.choice(pars['pop_size'], int(pars['pop_infected']), replace=False)       # cvu.choose: Numba stream
+            self.people.infect(inds, layer='seed_infection', count_flows=False)
+
+    def _host_add(self, key, t, value):
+        ''' Host-side contribution to a result (e.g. n_imports), merged with the device counters at sync time '''
+        arr = self._host_adds.setdefault(key, np.zeros(self.npts))
+        arr[t] += value
+
+    # ---- one day (reference sim.py:558-685) ----------------------------------------------------------
+    def step(self):
+        if self.complete:
+            raise AlreadyRunError('Simulation already complete (call sim.initialize() to re-run)')
+        t, pars, people, h, st = self.t, self.pars, self.people, self._handle, self._stream_ptr
+        people.t = t
+        call = _capi.call
+        self._push_pars()
+        call('cvb_update_states_pre', h, t, st)
+        for lkey, dyn in pars['dynam_layer'].items():                                 # reference people.py:199-206
+            if dyn:
+                people.contacts[lkey].update(people)
+        if pars['n_imports']:                                                          # reference sim.py:583-588
+            n_imports = int(self.rng.nb.poisson(f32(pars['n_imports'] / self.rescale_vec[t]), 1)[0])
+            if n_imports > 0:
+                who = self.rng.nb.choice(pars['pop_size'], n_imports, replace=False)
+                people.infect(who, layer='importation')
+                self._host_add('n_imports', t, n_imports)
+        for v in pars['variants']:
+            v.apply(self)
+        for iv in pars['interventions']:
+            iv(self)
+        self._push_pars()
+        call('cvb_update_states_post', h, t, st)
+        call('cvb_prepare_transmission', h, t, st)
+        call('cvb_edge_pass', h, t, st)
+        call('cvb_infect_winners', h, t, st)
+        call('cvb_update_nab_count', h, t, st)
+        for an in pars['analyzers']:
+            an(self)
+        self.t += 1
+        if self.t == self.npts:
+            self.complete = True
+
+    def run(self, until=None, reset_seed=True, restore_pars=True, verbose=None, **kwargs):
+        ''' Run to the end (or to ``until``) and finalize (reference sim.py:688-761) '''
+        if not self.initialized:
+            self.initialize()
+        if self._orig_pars is None:
+            self._orig_pars = {k: copy.deepcopy(v) for k, v in self.pars.items() if k not in ('interventions', 'analyzers', 'variants', 'prognoses', 'nab_kin')}
+        if reset_seed:
+            self.set_seed()
+        until = self.npts if until is None else self.day(until)
+        if until > self.npts:
+            raise AlreadyRunError(f'Requested to run until t={until} but the simulation end is t={self.npts}')
+        if self.t >= until:
+            raise AlreadyRunError(f'Simulation is currently at t={self.t}, requested to run until t={until} which has already been reached')
+        if self.complete:
+            raise AlreadyRunError('Simulation is already complete (call sim.initialize() to re-run)')
+        while self.t < until:
+            if self.pars['stopping_func'] and self.pars['stopping_func'](self):
+                return self
+            self.step()
+        if self.complete:
+            self.finalize(restore_pars=restore_pars)
+        return self
+
+    # ---- results ---------------------------------------------------------------------------------------
+    def sync_results(self):
+        ''' Copy the device counter tables into the host Result arrays (raw per-day values, unscaled) '''
+        torch.cuda.synchronize(self.device)
+        cnt = self._counters.cpu().numpy().astype(np.float64)
+        vcnt = self._vcounters.cpu().numpy().astype(np.float64)
+        sums = self._sums.cpu().numpy()
+        R = self.results
+        nv = self.pars['n_variants']
+        for k, cid in cvd.COUNTER_IDS.items():
+            if k in R:
+                R[k].values[:] = cnt[:, cid]
+        factor = self.pars['pop_scale'] / self.rescale_vec             # reference interventions.py:979, 1477
+        for k in ('new_tests', 'new_doses', 'new_vaccinated'):
+            R[k].values[:] = R[k].values * factor
+        for k, add in self._host_adds.items():
+            R[k].values[:] = R[k].values + add
+        for k, vid in cvd.VCOUNTER_IDS.items():
+            R['variant'][k].values[:] = vcnt[:, :, vid].T
+        n_alive = cnt[:, cvd.COUNTER_IDS['n_alive_agents']]
+        with np.errstate(all='ignore'):
+            R['pop_nabs'].values[:] = np.where(n_alive > 0, sums[:, 0] / n_alive, 0.0)
+            R['pop_protection'].values[:] = sums[:, 1] / (nv * self.n)
+            R['pop_symp_protection'].values[:] = sums[:, 2] / (nv * self.n)
+        return self.results
+
+    @property
+    def infection_log(self):
+        ''' The infection log as host arrays sorted by (date, variant, layer, target) (reference people.py:508-511) '''
+        torch.cuda.synchronize(self.device)
+        L = self._log
+        n = min(int(L['count'].item()), len(L['source']))
+        out = {k: L[k][:n].cpu().numpy() for k in ('source', 'target', 'date', 'layer', 'variant')}
+        order = np.lexsort((out['target'], out['layer'], out['variant'], out['date']))
+        return {k: v[order] for k, v in out.items()}
+
+    def finalize(self, restore_pars=True, **kwargs):
+        ''' Cumulative and derived results (reference sim.py:764-1072) '''
+        if self.results_ready:
+            raise AlreadyRunError('Simulation has already been finalized')
+        self.sync_results()
+        R, pars = self.results, self.pars
+        rv = self.rescale_vec
+        for k in self.result_keys():
+            if R[k].scale:
+                R[k].values *= rv
+        for k in self.result_keys('variant'):
+            if R['variant'][k].scale:
+                R['variant'][k].values = R['variant'][k].values * rv[None, :]
+        for k in cvd.result_flows:
+            R[f'cum_{k}'].values[:] = np.cumsum(R[f'new_{k}'].values)
+        for k in cvd.result_flows_by_variant:
+            R['variant'][f'cum_{k}'].values[:] = np.cumsum(R['variant'][f'new_{k}'].values, axis=1)
+        R['cum_infections'].values += pars['pop_infected'] * rv[0]
+        R['variant']['cum_infections_by_variant'].values += pars['pop_infected'] * rv[0]
+        for iv in pars['interventions']:
+            if hasattr(iv, 'finalize'):
+                iv.finalize(self)
+        for an in pars['analyzers']:
+            if hasattr(an, 'finalize'):
+                an.finalize(self)
+        self.results_ready = True
+        self.t -= 1
+        self.compute_results()
+        if restore_pars and self._orig_pars:
+            for k, v in self._orig_pars.items():
+                self.pars[k] = v
+            self._orig_pars = None
+            self._pars_dirty = True
+        return self
+
+    def compute_results(self):
+        self.compute_states()
+        self.compute_yield()
+        self.compute_doubling()
+        self.compute_r_eff()
+        self.compute_summary()
+
+    def compute_states(self):
+        ''' reference sim.py:808-837 '''
+        R = self.results
+        v = lambda k: R[k].values
+        count_recov = 1 - self.pars['use_waning']
+        with np.errstate(all='ignore'):
+            R['n_alive'].values[:] = self.scaled_pop_size - v('cum_deaths')
+            R['n_naive'].values[:] = self.scaled_pop_size - v('cum_deaths') - v('n_recovered') - v('n_exposed')
+            R['n_susceptible'].values[:] = v('n_alive') - v('n_exposed') - count_recov * v('cum_recoveries')
+            R['n_preinfectious'].values[:] = v('n_exposed') - v('n_infectious')
+            R['n_removed'].values[:] = count_recov * v('cum_recoveries') + v('cum_deaths')
+            R['prevalence'].values[:] = v('n_exposed') / v('n_alive')
+            R['incidence'].values[:] = v('new_infections') / v('n_susceptible')
+            R['frac_vaccinated'].values[:] = v('n_vaccinated') / v('n_alive')
+            V = R['variant']
+            V['incidence_by_variant'].values[:] = V['new_infections_by_variant'].values / v('n_susceptible')[None, :]
+            V['prevalence_by_variant'].values[:] = V['new_infections_by_variant'].values / v('n_alive')[None, :]
+
+    def compute_yield(self):
+        ''' reference sim.py:840-855 '''
+        R = self.results
+        v = lambda k: R[k].values
+        with np.errstate(all='ignore'):
+            nz = np.nonzero(v('new_tests'))[0]
+            R['test_yield'].values[nz] = v('new_diagnoses')[nz] / v('new_tests')[nz]
+            nz = np.nonzero(v('n_infectious'))[0]
+            denom = v('n_infectious')[nz] / (v('n_alive')[nz] - v('cum_diagnoses')[nz])
+            R['rel_test_yield'].values[nz] = v('test_yield')[nz] / denom
+
+    def compute_doubling(self, window=3, max_doubling_time=30):
+        ''' reference sim.py:858-885 '''
+        ci = self.results['cum_infections'].values
+        now, prev = ci[window:], ci[:-window]
+        use = (prev > 0) & (now > prev)
+        out = np.full(self.npts, np.nan)
+        tail = out[window:]
+        with np.errstate(all='ignore'):
+            tail[use] = np.minimum(window * np.log(2) / np.log(now[use] / prev[use]), max_doubling_time)
+        self.results['doubling_time'].values[:] = out
+        return out
+
+    def compute_r_eff(self, method='daily', smoothing=2, window=7):
+        ''' Effective reproduction number, 'daily' method (reference sim.py:888-946) '''
+        if method != 'daily':
+            raise NotImplementedError("only the default r_eff method 'daily' is built")
+        P = self.people
+        d_rec, d_dead, d_inf = P.to_numpy('date_recovered'), P.to_numpy('date_dead'), P.to_numpy('date_infectious')
+        rec = np.nonzero(~np.isnan(d_rec))[0]
+        dead = np.nonzero(~np.isnan(d_dead))[0]
+        outcome = np.concatenate((d_rec[rec], d_dead[dead]))
+        both = np.concatenate((rec, dead))
+        mean_inf = outcome.mean() - d_inf[both].mean() if len(outcome) else 0
+        R = self.results
+        new_inf = R['new_infections'].values - R['n_imports'].values
+        n_inf = R['n_infectious'].values
+        raw = mean_inf * np.divide(new_inf, n_inf, out=np.zeros(self.npts), where=n_inf > 0)
+        if len(raw) >= 3:
+            dur = self.pars['dur']
+            initial = int(min(len(raw), dur['exp2inf']['par1'] + dur['asym2rec']['par1']))
+            for i in range(initial):
+                raw[i] = raw[i:initial].mean()
+            sm = raw.copy()
+            for _ in range(smoothing):
+                sm = np.convolve(np.concatenate([[sm[0]], sm, [sm[-1]]]), [0.25, 0.5, 0.25], mode='valid')
+            sm[:smoothing] = raw[:smoothing]
+            sm[-smoothing:] = raw[-smoothing:]
+            raw = sm
+        R['r_eff'].values[:] = raw
+        return raw
+
+    def compute_summary(self, t=None):
+        ''' reference sim.py:1040-1072 '''
+        if t is None:
+            t = self.t
+        self.summary = {k: float(self.results[k].values[t]) for k in self.result_keys()}
+        return self.summary

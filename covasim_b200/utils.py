@@ -1,0 +1,116 @@
+'''
+Index helpers and seeding: the part of the reference's cv.utils that interventions and analyzers call
+on People arrays (reference covasim/utils.py:487-669), here for device tensors.  They return int64
+index tensors on the array's device, like the reference's ``arr.nonzero()[0]``.
+'''
+import random
+
+import numpy as np
+import torch
+
+__all__ = ['true', 'false', 'defined', 'undefined', 'itrue', 'ifalse', 'idefined', 'iundefined',
+           'itruei', 'ifalsei', 'idefinedi', 'iundefinedi', 'set_seed', 'HostStreams', 'n_binomial', 'binomial_arr']
+
+
+def _t(arr):
+    return arr if isinstance(arr, torch.Tensor) else torch.as_tensor(np.asarray(arr))
+
+
+def true(arr):
+    ''' Indices of non-zero entries (reference utils.py:494-506) '''
+    return torch.nonzero(_t(arr)).flatten()
+
+
+def false(arr):
+    ''' Indices of zero entries (reference utils.py:509-520) '''
+    a = _t(arr)
+    return torch.nonzero(a == 0).flatten()
+
+
+def defined(arr):
+    ''' Indices of non-NaN entries (reference utils.py:523-534) '''
+    return torch.nonzero(~torch.isnan(_t(arr))).flatten()
+
+
+def undefined(arr):
+    ''' Indices of NaN entries (reference utils.py:537-548) '''
+    return torch.nonzero(torch.isnan(_t(arr))).flatten()
+
+
+def itrue(arr, inds):
+    ''' inds[arr]: arr is a boolean array the same length as inds (reference utils.py:551-563) '''
+    return _t(inds)[_t(arr).bool()]
+
+
+def ifalse(arr, inds):
+    return _t(inds)[~_t(arr).bool()]
+
+
+def idefined(arr, inds):
+    return _t(inds)[~torch.isnan(_t(arr))]
+
+
+def iundefined(arr, inds):
+    return _t(inds)[torch.isnan(_t(arr))]
+
+
+def itruei(arr, inds):
+    ''' inds[arr[inds]]: arr is a full-length array (reference utils.py:611-623) '''
+    inds = _t(inds)
+    return inds[_t(arr)[inds].bool()]
+
+
+def ifalsei(arr, inds):
+    inds = _t(inds)
+    return inds[~_t(arr)[inds].bool()]
+
+
+def idefinedi(arr, inds):
+    inds = _t(inds)
+    return inds[~torch.isnan(_t(arr)[inds])]
+
+
+def iundefinedi(arr, inds):
+    inds = _t(inds)
+    return inds[torch.isnan(_t(arr)[inds])]
+
+
+class HostStreams:
+    '''
+    The reference's two MT19937 streams (reference utils.py:271-298): ``np_`` plays the role of NumPy's
+    global stream and ``nb`` of Numba's.  Same algorithm, same seed, independent state -- verified in
+    lockstep against the reference by oracle/gen_golden.py.  In native-RNG mode only rare host-side set
+    choices (seed infections, importations) use them; everything per-agent / per-edge is Philox on the device.
+    '''
+
+    def __init__(self, seed=None):
+        self.np_ = np.random.RandomState()
+        self.nb = np.random.RandomState()
+        self.seed = None
+        if seed is not None:
+            self.set_seed(seed)
+
+    def set_seed(self, seed=None):
+        if seed is None:
+            self.np_.seed()
+            seed = int(self.np_.randint(int(1e9)))
+        self.seed = int(seed)
+        self.np_.seed(self.seed)
+        self.nb.seed(self.seed)
+        random.seed(self.seed)
+
+
+def set_seed(seed=None):
+    ''' Seed NumPy's global stream and Python's ``random`` (reference utils.py:271-298); sims keep their own HostStreams '''
+    if seed is not None:
+        seed = int(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+
+
+def n_binomial(prob, n):
+    return np.random.random(n) < prob
+
+
+def binomial_arr(prob_arr):
+    return np.random.random(len(prob_arr)) < prob_arr

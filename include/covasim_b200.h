@@ -1,0 +1,193 @@
+/*
+ * covasim_b200 -- C ABI of the B200-native Covasim hot path (libcovasim_b200.so).
+ *
+ * The reference (Covasim 3.1.7) has no FFI for this path: its "operator API" is the set of Python
+ * functions Sim.step() calls by name (covasim/sim.py:558-685).  Each entry point below replaces one of
+ * them and cites it.  Conventions:
+ *   - plain pointers and sizes only; every array pointer is a DEVICE pointer unless marked "host";
+ *   - the caller owns all array memory (the Python host binds torch tensors' data_ptr());
+ *     the library owns only its scratch, freed by cvb_destroy();
+ *   - every function returns 0 on success, non-zero on failure; cvb_last_error() gives the message;
+ *   - `cvb_stream` is a cudaStream_t (NULL = the legacy default stream);
+ *   - a cvb_sim handle is not thread-safe; distinct handles are independent (ensembles run one
+ *     handle per member, each on its own stream);
+ *   - bool arrays are one byte per agent (NumPy/torch bool layout), dates are float32 with NaN =
+ *     "not set", exactly as in the reference's People (covasim/people.py:47-118).
+ */
+#ifndef COVASIM_B200_H
+#define COVASIM_B200_H
+
+#include <stdint.h>
+#include "cvb_fields.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVB_MAX_VARIANTS 8
+#define CVB_MAX_LAYERS   8
+#define CVB_MAX_VACCINES 8
+#define CVB_N_DURS       9
+#define CVB_ABI_VERSION  1
+
+typedef struct cvb_sim cvb_sim;
+typedef void* cvb_stream;
+
+/* Duration / NAb distributions (reference utils.py:156-237).  For the lognormal kinds `a`,`b` are the
+ * mean and sigma of the UNDERLYING normal (utils.py:223-225), computed by the host in float64. */
+enum cvb_dist_kind { CVB_DIST_ZERO = 0, CVB_DIST_NORMAL = 1, CVB_DIST_NORMAL_POS = 2, CVB_DIST_NORMAL_INT = 3,
+                     CVB_DIST_LOGNORMAL = 4, CVB_DIST_LOGNORMAL_INT = 5 };
+typedef struct cvb_dist { int32_t kind; int32_t pad_; double a; double b; } cvb_dist;
+
+/* Order of cvb_pars.dur[] (reference parameters.py:85-95) */
+enum cvb_dur { CVB_DUR_exp2inf = 0, CVB_DUR_inf2sym, CVB_DUR_sym2sev, CVB_DUR_sev2crit, CVB_DUR_asym2rec,
+               CVB_DUR_mild2rec, CVB_DUR_sev2rec, CVB_DUR_crit2rec, CVB_DUR_crit2die };
+
+/* Layer codes stored in the infection log for infections that did not come through a contact layer */
+#define CVB_LAYER_SEED   (-1)
+#define CVB_LAYER_IMPORT (-2)
+
+/* Scalars the kernels read.  Interventions may change them between days (reference sim.py:602-642
+ * re-reads them every step), so the host re-sends the struct whenever it changes. */
+typedef struct cvb_pars {
+    int32_t n_variants, n_layers, use_waning, n_vaccines;
+    int32_t quar_period, has_vaccine_pars;
+    int64_t n_beds_hosp, n_beds_icu;                 /* < 0: no limit (reference sim.py:579-580) */
+    float asymp_factor, frac_time, load_ratio, high_cap;
+    float trans_redux, no_hosp_factor, no_icu_factor, nab_boost;
+    float beta[CVB_MAX_VARIANTS];                    /* f32(beta*rel_beta*variant rel_beta), sim.py:627 */
+    float rel_symp[CVB_MAX_VARIANTS], rel_severe[CVB_MAX_VARIANTS];
+    float rel_crit[CVB_MAX_VARIANTS], rel_death[CVB_MAX_VARIANTS];   /* people.py:476-481 */
+    float beta_layer[CVB_MAX_LAYERS], iso_factor[CVB_MAX_LAYERS], quar_factor[CVB_MAX_LAYERS];
+    float immunity[CVB_MAX_VARIANTS][CVB_MAX_VARIANTS];              /* immunity.py:284-295 */
+    double vaccine_imm[CVB_MAX_VACCINES][CVB_MAX_VARIANTS];          /* immunity.py:332-341 */
+    double exp_alpha_inf, beta_inf, exp_alpha_symp_inf, beta_symp_inf, exp_alpha_sev_symp, beta_sev_symp; /* immunity.py:216-247 */
+    double rel_imm_asymp, rel_imm_mild, rel_imm_severe, nab_norm;    /* immunity.py:184-194; nab_norm = 1+alpha_inf_diff */
+    cvb_dist dur[CVB_N_DURS];
+    cvb_dist nab_init;
+} cvb_pars;
+
+const char* cvb_last_error(void);
+int32_t cvb_abi_version(void);
+/* sizeof of {cvb_pars, cvb_dist, cvb_test_prob_pars, cvb_trace_pars, cvb_vaccinate_pars} -> host int64[5] */
+int cvb_struct_sizes(int64_t* out5);
+
+/* ------------------------------------------------------------------------------------------------
+ * Handle: sizes, bound arrays, parameters, scratch.
+ * ---------------------------------------------------------------------------------------------- */
+int cvb_create(cvb_sim** out, int64_t n_agents, int32_t n_variants, int32_t npts, uint64_t seed);
+int cvb_destroy(cvb_sim* s);
+int cvb_set_seed(cvb_sim* s, uint64_t seed);
+int cvb_set_pars(cvb_sim* s, const cvb_pars* host_pars);
+/* Bind one per-agent array (length n_agents, or n_variants*n_agents for the by-variant / immunity
+ * fields).  Replaces People.__setitem__ on the NumPy arrays (reference base.py:1007-1027). */
+int cvb_bind_field(cvb_sim* s, int32_t field, void* ptr);
+/* Bind one contact layer's edge list (reference base.py:1651-1676: p1:int32[E], p2:int32[E], beta:f32[E]) */
+int cvb_bind_layer(cvb_sim* s, int32_t layer, int32_t* p1, int32_t* p2, float* beta, int64_t n_edges);
+/* Per-day result tables: counters int64[npts][CVB_N_COUNTERS], vcounters int64[npts][n_variants][CVB_N_VCOUNTERS],
+ * sums double[npts][4] = {sum nab over alive, sum sus_imm, sum symp_imm, unused} (reference sim.py:652-674) */
+int cvb_bind_results(cvb_sim* s, int64_t* counters, int64_t* vcounters, double* sums);
+/* Device infection log (reference people.py:508-511): parallel arrays of capacity `cap`, *count is device int64 */
+int cvb_bind_log(cvb_sim* s, int32_t* source, int32_t* target, int32_t* date, int8_t* layer, int8_t* variant,
+                 int64_t cap, int64_t* count);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stateless operators: 1:1 with the reference's Numba kernels (covasim/utils.py:39-147).
+ * ---------------------------------------------------------------------------------------------- */
+/* utils.py:39-79 compute_viral_load */
+int cvb_compute_viral_load(int32_t t, const float* date_inf, const float* date_rec, const float* date_dead,
+                           float frac_time, float load_ratio, float high_cap, float* out, int64_t n, cvb_stream st);
+/* utils.py:82-90 compute_trans_sus */
+int cvb_compute_trans_sus(const float* rel_trans, const float* rel_sus, const uint8_t* inf, const uint8_t* sus,
+                          float beta_layer, const float* viral_load, const uint8_t* symp, const uint8_t* iso,
+                          const uint8_t* quar, float asymp_factor, float iso_factor, float quar_factor,
+                          const float* immunity_factors, float* out_trans, float* out_sus, int64_t n, cvb_stream st);
+/* utils.py:93-128 compute_infections, replay form.  The reference draws one uniform per edge-direction
+ * whose float32 probability is non-zero, in edge order, direction p1->p2 first.  _count reports how many
+ * draws each direction consumes (host int64[2]; synchronises the stream); _draw consumes
+ * n_draws[0]+n_draws[1] uniforms (device, float64) and writes the ordered (source, target) lists
+ * (capacity n_draws[0]+n_draws[1]) and their length (host int64). */
+int cvb_infections_count(cvb_sim* s, float beta, const int32_t* p1, const int32_t* p2, const float* layer_betas,
+                         int64_t n_edges, const float* rel_trans, const float* rel_sus, int64_t* host_n_draws,
+                         cvb_stream st);
+int cvb_infections_draw(cvb_sim* s, float beta, const int32_t* p1, const int32_t* p2, const float* layer_betas,
+                        int64_t n_edges, const float* rel_trans, const float* rel_sus, const double* uniforms,
+                        int32_t* out_src, int32_t* out_tgt, int64_t* host_n_out, cvb_stream st);
+/* utils.py:131-147 find_contacts + base.py:1842-1844: sorted unique partners of `inds` (int64[n_inds]);
+ * out has capacity n_agents; *host_n_out receives the count (synchronises) */
+int cvb_find_contacts(cvb_sim* s, const int32_t* p1, const int32_t* p2, int64_t n_edges, const int64_t* inds,
+                      int64_t n_inds, int32_t* out, int64_t* host_n_out, cvb_stream st);
+/* utils.py:494-506 true(): ascending indices of non-zero bytes; *host_n_out receives the count (synchronises) */
+int cvb_true_indices(cvb_sim* s, const uint8_t* flags, int64_t n, int32_t* out, int64_t* host_n_out, cvb_stream st);
+
+/* ------------------------------------------------------------------------------------------------
+ * One simulated day on the bound People / Layers (reference sim.py:558-685).
+ * ---------------------------------------------------------------------------------------------- */
+/* people.py:164-186 update_states_pre (+ immunity.py:303-350 check_immunity when use_waning) */
+int cvb_update_states_pre(cvb_sim* s, int32_t t, cvb_stream st);
+/* people.py:620-640 schedule_quarantine: request quarantine of `inds` starting on start_day and ending on
+ * end_day.  The host dict People._pending_quarantine becomes a device ring of per-agent "max requested
+ * end day" slots indexed by start_day % horizon (requests for one agent and start day are order-
+ * independent: the reference extends to the max end and counts the agent once, people.py:339-346). */
+int cvb_schedule_quarantine(cvb_sim* s, const int32_t* inds, int64_t n, int32_t start_day, float end_day, cvb_stream st);
+/* how many days ahead requests may start (1 = today only); grows the ring, call before any request is pending */
+int cvb_set_quar_horizon(cvb_sim* s, int32_t horizon);
+/* immunity.py:298 pars['nab_kin']: per-day NAb increments (host float64[n]) */
+int cvb_set_nab_kin(cvb_sim* s, const double* host_kin, int64_t n);
+/* people.py:189-196 update_states_post (check_diagnosed, check_quar, check_enter_iso) */
+int cvb_update_states_post(cvb_sim* s, int32_t t, cvb_stream st);
+/* sim.py:602-643: viral load + per-layer {rel_trans, rel_sus} records for the fused edge pass */
+int cvb_prepare_transmission(cvb_sim* s, int32_t t, cvb_stream st);
+/* sim.py:622-649 native-RNG form: ONE pass over every layer's edges, both directions, all variants;
+ * per-edge Philox4x32-10 uniforms keyed (seed, day, layer, edge); winners by atomicMin of
+ * (variant, layer, direction, edge) per target == the reference's first-occurrence rule (people.py:465-467) */
+int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st);
+/* people.py:435-586 infect (+ immunity.py:138-202 update_peak_nab) for the edge pass's winners; keyed draws */
+int cvb_infect_winners(cvb_sim* s, int32_t t, cvb_stream st);
+/* people.py:435-586 infect for an explicit index list (seed infections sim.py:528, imports sim.py:587,
+ * variant imports immunity.py:128); duplicates / non-susceptibles are dropped; keyed draws */
+int cvb_infect_list(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant, int32_t layer_code, int32_t t,
+                    int32_t count_flows /* 0 for seed infections at initialisation: their flows are discarded */,
+                    cvb_stream st);
+/* immunity.py:205-213 update_nab + sim.py:652-674 stock counts and population means */
+int cvb_update_nab_count(cvb_sim* s, int32_t t, cvb_stream st);
+/* All of the above for day t in reference order, with no built-in interventions in between */
+int cvb_step_day(cvb_sim* s, int32_t t, cvb_stream st);
+
+/* ------------------------------------------------------------------------------------------------
+ * Built-in interventions as device passes ("next" rows of SURVEY.md section 8(f)).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cvb_test_prob_pars {        /* interventions.py:857-981 */
+    double symp_prob, asymp_prob, symp_quar_prob, asymp_quar_prob, sensitivity, loss_prob;
+    int32_t quar_policy;                   /* 0 start, 1 end, 2 both, 3 daily */
+    int32_t test_delay, index, pad_;
+} cvb_test_prob_pars;
+int cvb_test_prob(cvb_sim* s, int32_t t, const cvb_test_prob_pars* host_pars, cvb_stream st);
+
+typedef struct cvb_trace_pars {            /* interventions.py:984-1145 */
+    double trace_prob[CVB_MAX_LAYERS];
+    int32_t trace_time[CVB_MAX_LAYERS];
+    int32_t presumptive, quar_period, index, pad_;
+} cvb_trace_pars;
+/* Marks contacts of today's cases, sets known_contact/date_known_contact and queues quarantine.
+ * Requests with trace_time 0 go to pend_quar_end; later ones to the per-day ring. */
+int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* host_pars, cvb_stream st);
+
+typedef struct cvb_vaccinate_pars {        /* interventions.py:1257-1662 */
+    double prob;
+    cvb_dist nab_init;
+    float nab_boost;
+    int32_t booster, vaccine_index, max_doses, index, first_dose_today, second_dose_today, interval, n_days;
+} cvb_vaccinate_pars;
+/* `iv_doses` int32[n] is this intervention's own dose count, `due_day` int32[n] the day an agent's second
+ * dose is due (-1 none) -- the device form of second_dose_days (interventions.py:1655-1660) */
+int cvb_vaccinate_prob(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* host_pars, int32_t* iv_doses, int32_t* due_day,
+                       cvb_stream st);
+
+/* base.py:1849-1876 Layer.update with frac=1: regenerate every edge of a dynamic layer on the device */
+int cvb_layer_regenerate(cvb_sim* s, int32_t layer, int32_t t, cvb_stream st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,143 @@
+'''
+GPU parity of the stateless operators (the device forms of the reference's four Numba kernels) against
+(a) the inputs/outputs recorded from the unmodified reference (tests/golden) and (b) the oracle on
+seeded synthetic inputs, including empty, ragged and unaligned sizes.  All through the C ABI.
+'''
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import cvoracle as cvo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def cv():
+    import covasim_b200
+    return covasim_b200
+
+
+def digest(arr):
+    return hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
+
+
+_layers = {}
+
+
+def layers_of(name):
+    ''' The scenario's static contact layers, regenerated from the seed by the oracle's population builder '''
+    if name not in _layers:
+        import scenarios
+        sim = cvo.OracleSim(**scenarios.build(cvo, scenarios.SCENARIOS[name]), rng='mt')
+        sim.initialize()
+        _layers[name] = sim.contacts
+    return _layers[name]
+
+
+@pytest.mark.parametrize('name,day', [('hybrid3k', 12), ('hybrid3k', 25), ('variants4k', 20)])
+def test_reference_kernel_vectors(cv, golden, name, day):
+    g = golden(name)
+    pre = f'k{day}/'
+    vl = cv.ops.compute_viral_load(int(g[pre + 'vl/t']), g[pre + 'vl/date_inf'], g[pre + 'vl/date_rec'], g[pre + 'vl/date_dead'],
+                                   float(g[pre + 'vl/frac_time']), float(g[pre + 'vl/load_ratio']), float(g[pre + 'vl/high_cap']))
+    assert np.array_equal(vl.cpu().numpy(), g[pre + 'vl/out'])
+    contacts = layers_of(name)
+    by_len = {len(l['p1']): l for l in contacts.values()}
+    n_calls = int(g[pre + 'n_calls'])
+    assert n_calls > 0
+    for j in range(n_calls):
+        a = {k.split('/')[-1]: g[k] for k in g.files if k.startswith(f'{pre}ts{j}/')}
+        rt, rs = cv.ops.compute_trans_sus(a['rel_trans'], a['rel_sus'], a['inf'], a['sus'], float(a['beta_layer']), a['viral_load'],
+                                          a['symp'], a['iso'], a['quar'], float(a['asymp_factor']), float(a['iso_factor']),
+                                          float(a['quar_factor']), a['immunity_factors'])
+        assert np.array_equal(rt.cpu().numpy(), a['out_trans'])
+        assert np.array_equal(rs.cpu().numpy(), a['out_sus'])
+        c = {k.split('/')[-1]: g[k] for k in g.files if k.startswith(f'{pre}ci{j}/')}
+        layer = by_len[int(c['n_edges'])]
+        assert digest(layer['p1']) == str(c['p1_digest'])
+        u = np.concatenate([c['u_dir1'], c['u_dir2']])
+        src, tgt, n_draws = cv.ops.compute_infections(float(c['beta']), layer['p1'], layer['p2'], layer['beta'], c['rel_trans'], c['rel_sus'],
+                                                      lambda n: u[:n])
+        assert n_draws == (len(c['u_dir1']), len(c['u_dir2']))          # consumes exactly the reference's draws
+        assert np.array_equal(src.cpu().numpy(), c['out_src'])
+        assert np.array_equal(tgt.cpu().numpy(), c['out_tgt'])
+    for lk, layer in contacts.items():
+        out = cv.ops.find_contacts(layer['p1'], layer['p2'], g[f'{pre}fc/{lk}/inds'], n_agents=len(g[pre + 'vl/out']))
+        assert np.array_equal(out.cpu().numpy(), g[f'{pre}fc/{lk}/out'])
+
+
+@pytest.mark.parametrize('n_agents,n_edges', [(50, 0), (50, 1), (1000, 1023), (1000, 1024), (1000, 1025), (30000, 200003), (200000, 3000001)])
+def test_compute_infections_vs_oracle(cv, n_agents, n_edges):
+    rng = np.random.RandomState(n_edges + 1)
+    p1 = np.sort(rng.randint(0, n_agents, n_edges)).astype(np.int32)
+    p2 = rng.randint(0, n_agents, n_edges).astype(np.int32)
+    lb = np.where(rng.random_sample(n_edges) < 0.1, 0.0, 1.0).astype(np.float32) * rng.random_sample(n_edges).astype(np.float32)
+    infectious = rng.random_sample(n_agents) < 0.15
+    rel_trans = np.where(infectious, rng.gamma(0.5, 2.0, n_agents), 0).astype(np.float32)
+    rel_sus = np.where(~infectious & (rng.random_sample(n_agents) < 0.7), rng.random_sample(n_agents), 0).astype(np.float32)
+    drawn = []
+    stream = np.random.RandomState(7)
+
+    def draw_oracle(direction, edges):
+        u = stream.random_sample(len(edges))
+        drawn.append(u)
+        return u
+    beta = 0.3
+    src_o, tgt_o = cvo.compute_infections(beta, p1, p2, lb, rel_trans, rel_sus, draw_oracle)
+    u = np.concatenate(drawn)
+    src, tgt, n_draws = cv.ops.compute_infections(beta, p1, p2, lb, rel_trans, rel_sus, lambda n: u[:n])
+    assert n_draws == (len(drawn[0]), len(drawn[1]))
+    assert np.array_equal(src.cpu().numpy(), src_o)
+    assert np.array_equal(tgt.cpu().numpy(), tgt_o)
+    if n_edges:
+        who = np.nonzero(infectious)[0][:: 7]
+        out = cv.ops.find_contacts(p1, p2, who, n_agents=n_agents)
+        assert np.array_equal(out.cpu().numpy(), cvo.find_contacts(p1, p2, who))
+
+
+def test_unaligned_edge_arrays(cv):
+    ''' Views that are not 16-byte aligned take the scalar-load path and must give the same answer '''
+    import torch
+    rng = np.random.RandomState(3)
+    n, e = 5000, 40001
+    p1 = np.sort(rng.randint(0, n, e + 1)).astype(np.int32)
+    p2 = rng.randint(0, n, e + 1).astype(np.int32)
+    lb = np.ones(e + 1, dtype=np.float32)
+    rel_trans = np.where(rng.random_sample(n) < 0.2, 1.5, 0).astype(np.float32)
+    rel_sus = np.where(rel_trans == 0, 0.8, 0).astype(np.float32)
+    d_p1, d_p2, d_lb = (torch.as_tensor(x).cuda()[1:] for x in (p1, p2, lb))      # offset by one element = 4 bytes
+    stream = np.random.RandomState(11)
+    drawn = []
+    src_o, tgt_o = cvo.compute_infections(0.4, p1[1:], p2[1:], lb[1:], rel_trans, rel_sus, lambda d, ed: drawn.append(stream.random_sample(len(ed))) or drawn[-1])
+    u = np.concatenate(drawn)
+    src, tgt, _ = cv.ops.compute_infections(0.4, d_p1, d_p2, d_lb, rel_trans, rel_sus, lambda k: u[:k])
+    assert np.array_equal(src.cpu().numpy(), src_o) and np.array_equal(tgt.cpu().numpy(), tgt_o)
+
+
+@pytest.mark.parametrize('n', [1, 31, 1023, 1024, 1025, 100003, 5000000])
+def test_true_indices(cv, n):
+    import ctypes as C
+    import torch
+    rng = np.random.RandomState(n)
+    flags = rng.random_sample(n) < (0.5 if n < 2000 else 0.03)
+    ws = cv.ops.Workspace(n)
+    d = torch.as_tensor(flags).cuda()
+    out = torch.empty(n, dtype=torch.int32, device='cuda')
+    n_out = C.c_int64(0)
+    cv._capi.call('cvb_true_indices', ws.handle, d.data_ptr(), n, out.data_ptr(), C.byref(n_out), None)
+    assert np.array_equal(out[:n_out.value].cpu().numpy(), np.nonzero(flags)[0])
+    assert np.array_equal(cv.true(d).cpu().numpy(), np.nonzero(flags)[0])
+
+
+def test_viral_load_edge_cases(cv):
+    ''' NaN dates, zero-length infectious periods, negative days (historical interventions run with t < 0) '''
+    nan = np.nan
+    d_inf = np.array([nan, 3, 3, 3, 10, 0, -5], dtype=np.float32)
+    d_rec = np.array([nan, 3, 20, nan, 12, 40, 9], dtype=np.float32)
+    d_dead = np.array([nan, nan, nan, 15, nan, nan, nan], dtype=np.float32)
+    for t in (-3, 0, 4, 11, 30):
+        got = cv.ops.compute_viral_load(t, d_inf, d_rec, d_dead, 0.3, 2.0, 4.0).cpu().numpy()
+        want = cvo.compute_viral_load(t, d_inf, d_rec, d_dead, 0.3, 2.0, 4.0)
+        assert np.array_equal(got, want)

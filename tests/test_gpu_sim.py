@@ -1,0 +1,128 @@
+'''
+Whole-path GPU parity: covasim_b200 (native-RNG mode, fused edge pass) against the oracle in Philox mode,
+same scenario, same population, stepped in lockstep with every People array compared every day, then
+results and the infection log.  Bit-exact for flags / dates / counters / infection log; 1e-6 relative for
+NAb and immunity floats.  Plus the reference's RNG-free known-answer tests and its state-diagram invariants.
+'''
+import numpy as np
+import pytest
+
+import parity
+import scenarios
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def cv():
+    import covasim_b200
+    return covasim_b200
+
+
+@pytest.mark.parametrize('name', ['random2k_nowaning', 'dynamic2k', 'hybrid3k', 'variants4k'])
+def test_lockstep_parity(cv, name):
+    sim, orc = parity.build_pair(cv, name)
+    parity.run_lockstep(sim, orc)
+    assert sim.summary['cum_infections'] > scenarios.SCENARIOS[name]['pars']['pop_infected']     # the epidemic actually ran
+
+
+@pytest.mark.parametrize('name', ['default20k', 'baseline20k'])
+def test_endpoint_parity_20k(cv, name):
+    ''' The two 20k-agent configurations (BASELINE.json config 1 and the reference's own baseline test sim) '''
+    sim, orc = parity.build_pair(cv, name)
+    sim.run()
+    orc.run()
+    parity.compare_people(sim, orc, 'at the end')
+    parity.compare_results(sim, orc)
+    parity.compare_log(sim, orc)
+
+
+def test_step_by_step_equals_run(cv):
+    ''' reference tests/test_resume.py:120-138: a step() loop and run(until=..) + run() are the same simulation '''
+    spec = scenarios.SCENARIOS['hybrid3k']
+    a = cv.Sim(**scenarios.build(cv, spec)).run()
+    b = cv.Sim(**scenarios.build(cv, spec))
+    b.run(until=20)
+    b.run()
+    c = cv.Sim(**scenarios.build(cv, spec))
+    c.initialize()
+    while not c.complete:
+        c.step()
+    c.finalize()
+    for k in a.result_keys():
+        assert np.array_equal(a.results[k].values, b.results[k].values, equal_nan=True), k
+        assert np.array_equal(a.results[k].values, c.results[k].values, equal_nan=True), k
+
+
+def test_no_transmission_when_beta_is_zero(cv):
+    ''' reference tests/unittests/test_transmission.py:16-35 '''
+    sim = cv.Sim(pop_size=5000, pop_infected=50, n_days=30, beta=0.0, rand_seed=4).run()
+    assert sim.results['new_infections'].values.sum() == 0
+    assert sim.summary['cum_infections'] == 50
+
+
+def test_everyone_dies(cv):
+    ''' reference tests/unittests/test_mortality.py:13-24 '''
+    big = 1e6
+    sim = cv.Sim(pop_size=500, pop_infected=500, n_days=120, rand_seed=4, use_waning=False, rel_symp_prob=big, rel_severe_prob=big,
+                 rel_crit_prob=big, rel_death_prob=big).run()
+    assert sim.summary['cum_deaths'] == 500
+
+
+def test_exact_progression_days(cv):
+    ''' reference tests/unittests/test_progression.py:17-108: zero-variance durations put every transition on the exact day '''
+    dur = {k: dict(dist='normal_int', par1=v, par2=0.0) for k, v in dict(exp2inf=3, inf2sym=2, sym2sev=4, sev2crit=3, asym2rec=7, mild2rec=7,
+                                                                          sev2rec=9, crit2rec=9, crit2die=5).items()}
+    big = 1e6
+    sim = cv.Sim(pop_size=300, pop_infected=300, n_days=40, rand_seed=1, use_waning=False, dur=dur, rel_symp_prob=big, rel_severe_prob=big,
+                 rel_crit_prob=big, rel_death_prob=big).run()
+    r = sim.results
+    assert r['new_infectious'].values[3] == 300 and r['new_infectious'].values.sum() == 300
+    assert r['new_symptomatic'].values[5] == 300
+    assert r['new_severe'].values[9] == 300
+    assert r['new_critical'].values[12] == 300
+    assert r['new_deaths'].values[17] == 300
+
+
+STATE_MATRIX = '''
+susceptible   1  0 -1 -1 -1 -1 -1  0  0 -1 -1  0  0  0
+naive         1  1 -1 -1 -1 -1 -1  0 -1 -1 -1  0  0  0
+exposed      -1 -1  1  0  0  0  0  0  0 -1 -1  0  0  0
+infectious   -1 -1  1  1  0  0  0  0  0 -1 -1  0  0  0
+symptomatic  -1 -1  1  1  1  0  0  0  0 -1 -1  0  0  0
+severe       -1 -1  1  1  1  1  0  0  0 -1 -1  0  0  0
+critical     -1 -1  1  1  1  1  1  0  0 -1 -1  0  0  0
+tested        0  0  0  0  0  0  0  1  0  0  0  0  0  0
+diagnosed     0  0  0  0  0  0  0  1  1  0  0  0  0  0
+recovered    -1 -1 -1 -1 -1 -1 -1  0  0  1 -1  0  0  0
+dead         -1 -1 -1 -1 -1 -1 -1  0  0 -1  1 -1 -1  0
+known_contact 0  0  0  0  0  0  0  0  0  0 -1  1  0  0
+quarantined   0  0  0  0  0  0  0  0  0  0 -1  1  1  0
+vaccinated    0  0  0  0  0  0  0  0  0  0  0  0  0  1
+'''
+
+
+@pytest.mark.parametrize('use_waning', [False, True])
+def test_state_diagram(cv, use_waning):
+    ''' reference tests/test_immunity.py:25-85 + tests/state_diagram.xlsx (transcribed in SURVEY.md Appendix B) '''
+    rows = [l.split() for l in STATE_MATRIX.strip().splitlines()]
+    names = [r[0] for r in rows]
+    M = np.array([[int(x) for x in r[1:]] for r in rows])
+    if use_waning:
+        M[names.index('susceptible'), names.index('recovered')] = 0
+        M[names.index('recovered'), names.index('susceptible')] = 1
+    sim = cv.Sim(pop_size=2000, pop_infected=40, n_days=70, rand_seed=1, use_waning=use_waning, beta=0.03, pop_type='hybrid',
+                 interventions=[cv.test_prob(symp_prob=0.4, asymp_prob=0.02, start_day=5),
+                                cv.contact_tracing(trace_probs=0.5, start_day=8),
+                                cv.vaccinate_prob('pfizer', days=10, prob=0.3)] if use_waning else
+                 [cv.test_prob(symp_prob=0.4, asymp_prob=0.02, start_day=5), cv.contact_tracing(trace_probs=0.5, start_day=8)])
+    sim.run()
+    P = {k: sim.people.to_numpy(k) for k in names}
+    for i, s1 in enumerate(names):
+        on = P[s1]
+        assert on.any() or s1 in ('critical', 'vaccinated'), f'nobody is {s1}: the check would be vacuous'
+        for j, s2 in enumerate(names):
+            if M[i, j] == 1:
+                assert P[s2][on].all(), f'{s1} must imply {s2}'
+            elif M[i, j] == -1:
+                assert not P[s2][on].any(), f'{s1} must exclude {s2}'

@@ -1,0 +1,362 @@
+#!/usr/bin/env python
+'''
+bench.py -- agent-days/s of the per-timestep simulation hot path on the BASELINE.json workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (config.workload = "C2"): one 1M-agent hybrid sim (h/s/w/c layers, ~17.8M edges), 180 days
+(181 time points), cv.test_prob(symp_prob=0.1, asymp_prob=0.01, start_day=20) +
+cv.contact_tracing(trace_probs=0.3, start_day=30), 0.5 % initially infected, synthetic population.
+
+One "step" = one complete run of that sim (181 simulated days of the hot path).
+  value : agent-days/s with the initial People + Layer arrays already resident in HBM; timed on the
+          device with CUDA events around the 181 Sim.step() calls.
+  e2e   : the same through the public API with HOST buffers inside the timed region: Sim.restore()
+          (H2D of every People array and edge list from pinned memory) + Sim.run() (181 days +
+          finalize(), which reads the result tables back to the host).
+  roofline : the fused edge pass -- algorithmic bytes (12*E + 8*N per launch) / mean launch duration,
+          measured live with CUDA events around each cvb_edge_pass launch of the timed steps.
+  cpu_baseline : the oracle (NumPy port of the reference algorithm) continuing the SAME sim from the GPU's
+          day-40 state for a bounded number of days on one host core (rank 0, N=1 only).
+
+N > 1 (torchrun): weak scaling -- every rank runs its own member of an ensemble (same configuration,
+seed + rank; reference run.py:1363-1365), no data-path collective; value = total agent-days / max time.
+
+--impl reference: times the oracle port (the reference's CPU algorithm; the reference itself is Python and
+cannot travel to the GPU box) on the same configuration, each step a bounded sample of the workload.
+'''
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = 'agent-days/sec (1M-agent hybrid)'
+UNIT = 'agent-days/s'
+
+
+def workload_pars(args, seed):
+    return dict(pop_size=args.pop_size, pop_type='hybrid', n_days=args.n_days, pop_infected=max(1, int(0.005 * args.pop_size)),
+                rand_seed=seed, verbose=0)
+
+
+def workload_interventions(mod):
+    return [mod.test_prob(symp_prob=0.1, asymp_prob=0.01, start_day=20), mod.contact_tracing(trace_probs=0.3, start_day=30)]
+
+
+def config_block(args, extra=None):
+    cfg = dict(workload='C2', pop_size=args.pop_size, pop_type='hybrid', n_days=args.n_days, npts=args.n_days + 1,
+               interventions='test_prob(symp_prob=0.1,asymp_prob=0.01,start_day=20)+contact_tracing(trace_probs=0.3,start_day=30)',
+               pop_infected=max(1, int(0.005 * args.pop_size)), rng='philox (native)',
+               l2_policy='per-day working set (edge lists + People arrays, ~420 MB at 1M agents) exceeds the 126 MB L2')
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    ''' nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe) '''
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.path = tempfile.mktemp(suffix='.csv')
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, 'w')
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu_index}', f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, smax, reasons = [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        for line in open(self.path):
+            parts = [x.strip() for x in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['no samples'])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(smax)), reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ---------------------------------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import covasim_b200 as cv
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (covasim_b200 has no CPU fallback)')
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    n_gpus = world
+
+    pars = workload_pars(args, seed=1 + rank)
+    sim = cv.Sim(pars, interventions=workload_interventions(cv), pop_exact=False)
+    t0 = time.time()
+    sim.initialize()
+    t_init = time.time() - t0
+    snap = sim.snapshot(pinned=True)                    # the step's inputs, in pinned host memory
+    dev_snap = {k: sim.people[k].clone() for k in sim.people.keys()}      # device-resident copy for the `value` leg
+    n_edges = {lk: len(l) for lk, l in sim.people.contacts.items()}
+    E, N, npts = sum(n_edges.values()), sim.n, sim.npts
+    agent_days = N * npts
+
+    def reset_on_device():
+        ''' Rewind to day 0 without touching the host: inputs stay resident in HBM '''
+        for k, v in dev_snap.items():
+            sim.people[k].copy_(v)
+        sim.restore_light(snap)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: device-resident inputs, CUDA events around the day loop --------------------------------
+    for _ in range(args.warmup):
+        reset_on_device()
+        while not sim.complete:
+            sim.step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = cv._capi.lib.cvb_launch_count()
+    sim.kernel_timers = {}
+    dev_ms = 0.0
+    barrier()
+    for _ in range(args.steps):
+        reset_on_device()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        while not sim.complete:
+            sim.step()
+        b.record()
+        barrier()
+        dev_ms += max_over_ranks(a.elapsed_time(b))
+    launches = cv._capi.lib.cvb_launch_count() - launches0
+    timers, sim.kernel_timers = sim.kernel_timers, None
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = dev_ms / args.steps
+    value = n_gpus * agent_days / (ms_per_step / 1e3)
+
+    # per-kernel device time from the CUDA events recorded around every C-ABI call of the timed steps
+    kernel_ms = {name: float(np.sum([x.elapsed_time(y) for x, y in evs])) / args.steps for name, evs in timers.items()}
+    edge_calls = len(timers.get('cvb_edge_pass', [])) / max(args.steps, 1)
+    edge_ms_per_launch = kernel_ms.get('cvb_edge_pass', 0.0) / max(edge_calls, 1)
+    algo_bytes = 12 * E + 8 * N
+    peak, peak_src = measured_peak_gbs()
+    achieved = algo_bytes / (edge_ms_per_launch * 1e-3) / 1e9 if edge_ms_per_launch > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'edge_pass_traffic.json')
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get('dram_bytes_per_launch')
+        except Exception:
+            traffic = None
+    roofline = dict(bound='hbm', kernel='edge_pass_kernel', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak, traffic=traffic,
+                    algorithmic_bytes_per_launch=algo_bytes, us_per_launch=edge_ms_per_launch * 1e3, peak_source=peak_src,
+                    share_of_step=kernel_ms.get('cvb_edge_pass', 0.0) / ms_per_step if ms_per_step else None)
+
+    # ---- e2e: host buffers in, results out, through the public API -----------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        sim.restore(snap)
+        sim.run()
+    e2e_s = 0.0
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        sim.restore(snap)                 # H2D: People arrays + edge lists from pinned host memory
+        sim.run()                          # 181 days + finalize (D2H of the result tables)
+        torch.cuda.synchronize()
+        e2e_s += max_over_ranks(time.perf_counter() - t0)
+    e2e_value = n_gpus * agent_days / (e2e_s / args.steps)
+    summary = dict(cum_infections=sim.summary['cum_infections'], cum_deaths=sim.summary['cum_deaths'],
+                   cum_diagnoses=sim.summary['cum_diagnoses'], cum_quarantined=sim.summary['cum_quarantined'])
+
+    # ---- cpu_baseline: the oracle continues the same sim from the GPU's day-40 state (rank 0, N = 1) ----------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_from_gpu_state(args, cv, sim, snap)
+
+    if rank == 0:
+        out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=n_gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
+                   higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                   config=config_block(args, dict(edges=E, edges_by_layer=n_edges, parallelism=f'ensemble x{n_gpus} (one member per GPU, no collective)' if n_gpus > 1 else 'single GPU',
+                                                  init_s=t_init)),
+                   clocks=clocks,
+                   e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=sim.h2d_bytes(snap), d2h_bytes_per_step=sim.d2h_bytes(), ms_per_step=1e3 * e2e_s / args.steps),
+                   gpu_launches=int(launches), roofline=roofline, kernel_ms_per_step=kernel_ms, us_per_day=1e3 * ms_per_step / npts,
+                   epidemic=summary)
+        if cpu is not None:
+            out['cpu_baseline'] = cpu
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline_from_gpu_state(args, cv, sim, snap, t0=40, budget_s=20.0):
+    ''' Time the oracle on days [t0, t0+k) of the same sim, starting from the device state at day t0 '''
+    from oracle import cvoracle as cvo
+    import torch
+    t0 = min(t0, max(args.n_days - 4, 0))
+    sim.restore(snap)
+    sim.set_seed()
+    while sim.t < t0:
+        sim.step()
+    torch.cuda.synchronize()
+    pop = dict(age=sim.people.to_numpy('age').astype(np.float64), sex=sim.people.to_numpy('sex'),
+               contacts={lk: l.to_numpy() for lk, l in sim.people.contacts.items()})
+    orc = cvo.OracleSim(workload_pars(args, seed=1), interventions=workload_interventions(cvo), rng='philox', popdict=pop)
+    orc.keep_log = False
+    orc.initialize()
+    for k in cvo.cvd.all_states:
+        orc.P[k] = sim.people.to_numpy(k).copy()
+    orc.t = t0
+    orc.rng.set_seed(1)
+    orc.step()                                           # warm-up day (page faults, allocator)
+    days, t_start = 0, time.perf_counter()
+    while time.perf_counter() - t_start < budget_s and orc.t < orc.npts - 1 and days < 40:
+        orc.step()
+        days += 1
+    el = time.perf_counter() - t_start
+    return dict(value=args.pop_size * days / el, unit=UNIT, cores=1, kind='port',
+                sample=f'oracle (NumPy port of the reference algorithm) on days {t0 + 1}..{t0 + days} of the same sim, continued from the GPU state; {el / days:.3f} s/day',
+                s_per_day=el / days)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference arm: the reference's CPU algorithm (oracle port) on the same configuration
+# ---------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import cvoracle as cvo
+    total = args.steps + args.warmup
+    budget = 150.0 / max(total, 1)                        # seconds per step so the whole run ends within a few minutes
+    pars = workload_pars(args, seed=1)
+    t0 = time.time()
+    base = cvo.OracleSim(pars, interventions=workload_interventions(cvo), rng='mt')
+    base.keep_log = False
+    base.initialize()
+    t_init = time.time() - t0
+    P0 = {k: v.copy() for k, v in base.P.items()}
+    # calibrate the sample length on two days
+    t1 = time.perf_counter()
+    base.rng.set_seed(pars['rand_seed'])
+    base.step()
+    base.step()
+    per_day = (time.perf_counter() - t1) / 2
+    days = int(min(args.n_days + 1, max(4, budget / max(per_day, 1e-6))))
+
+    def one_step():
+        for k, v in P0.items():
+            base.P[k][...] = v
+        base.t = 0
+        base.pending_quar = {}
+        base.pars['n_days'] = args.n_days
+        base.rng.set_seed(pars['rand_seed'])
+        ts = time.perf_counter()
+        for _ in range(days):
+            base.step()
+        return time.perf_counter() - ts
+
+    for _ in range(args.warmup):
+        one_step()
+    times = [one_step() for _ in range(args.steps)]
+    el = float(np.mean(times))
+    value = args.pop_size * days / el
+    sample = f'first {days} of {args.n_days + 1} days of the same sim per step ({el / days:.3f} s/day), oracle port of the reference algorithm, MT19937 streams'
+    out = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el,
+               higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+               config=config_block(args, dict(rng='mt19937 (reference streams)', init_s=t_init)),
+               cpu_baseline=dict(value=value, unit=UNIT, cores=1, kind='port', sample=sample),
+               e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--pop-size', type=int, default=1_000_000)
+    ap.add_argument('--n-days', type=int, default=180)
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

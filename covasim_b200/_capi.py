@@ -76,6 +76,7 @@ PROTOTYPES = dict(
     cvb_create=[C.POINTER(_P), _i64, _i32, _i32, _u64],
     cvb_destroy=[_P],
     cvb_set_seed=[_P, _u64],
+    cvb_reset=[_P, _P],
     cvb_set_pars=[_P, C.POINTER(cvb_pars)],
     cvb_set_nab_kin=[_P, _P, _i64],
     cvb_set_quar_horizon=[_P, _i32],
@@ -95,7 +96,7 @@ PROTOTYPES = dict(
     cvb_prepare_transmission=[_P, _i32, _P],
     cvb_edge_pass=[_P, _i32, _P],
     cvb_infect_winners=[_P, _i32, _P],
-    cvb_infect_list=[_P, _P, _i64, _i32, _i32, _i32, _i32, _P],
+    cvb_infect_list=[_P, _P, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _P],
     cvb_update_nab_count=[_P, _i32, _P],
     cvb_step_day=[_P, _i32, _P],
     cvb_test_prob=[_P, _i32, C.POINTER(cvb_test_prob_pars), _P],
@@ -103,7 +104,7 @@ PROTOTYPES = dict(
     cvb_vaccinate_prob=[_P, _i32, C.POINTER(cvb_vaccinate_pars), _P, _P, _P],
     cvb_layer_regenerate=[_P, _i32, _i32, _P],
 )
-OTHER_SYMBOLS = ('cvb_last_error', 'cvb_abi_version')
+OTHER_SYMBOLS = ('cvb_last_error', 'cvb_abi_version', 'cvb_launch_count')
 
 
 def load_library(path=LIB_PATH):
@@ -128,6 +129,8 @@ def load_library(path=LIB_PATH):
     lib.cvb_last_error.argtypes = []
     lib.cvb_abi_version.restype = C.c_int32
     lib.cvb_abi_version.argtypes = []
+    lib.cvb_launch_count.restype = C.c_int64
+    lib.cvb_launch_count.argtypes = []
     return lib
 
 

@@ -7,6 +7,7 @@
 namespace cvb {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -68,6 +69,7 @@ extern "C" {
 
 const char* cvb_last_error(void) { return g_err; }
 int32_t cvb_abi_version(void) { return CVB_ABI_VERSION; }
+int64_t cvb_launch_count(void) { return (int64_t)g_launches; }
 
 /* sizes of the by-value structs, so a binding can verify its own layout */
 int cvb_struct_sizes(int64_t* out5) {
@@ -131,6 +133,18 @@ int cvb_destroy(cvb_sim* s) {
     cudaFree(s->nab_kin); cudaFree(s->tile_cnt); cudaFree(s->hit_mask); cudaFree(s->flag_tmp); cudaFree(s->partial);
     if (s->host_scalars) cudaFreeHost(s->host_scalars);
     delete s;
+    return 0;
+}
+
+int cvb_reset(cvb_sim* s, cvb_stream st_) {
+    CVB_REQUIRE(s, "cvb_reset: NULL handle");
+    cudaStream_t st = (cudaStream_t)st_;
+    CVB_CHECK(cudaMemsetAsync(s->infect_key, 0xFF, (size_t)s->n * sizeof(unsigned long long), st));
+    CVB_CHECK(cudaMemsetAsync(s->n_cand, 0, 64, st));
+    CVB_CHECK(cudaMemsetAsync(s->n_cases, 0, 64, st));
+    CVB_CHECK(cudaMemsetAsync(s->beds, 0, (size_t)s->npts * 2 * sizeof(unsigned long long), st));
+    fill_f32_kernel<<<grid_for((int64_t)s->quar_horizon * s->n), kThreads, 0, st>>>(s->quar_ring, (int64_t)s->quar_horizon * s->n, -1.0f);
+    CVB_LAUNCH_CHECK();
     return 0;
 }
 

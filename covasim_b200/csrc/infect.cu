@@ -18,6 +18,7 @@ struct InfectArgs {
     int32_t t;
     int32_t count_flows;     // 0 for seed infections at initialisation (reference sim.py:505-532: flows are discarded)
     int32_t list_layer_code; // layer code logged for list-mode keys (CVB_LAYER_SEED / CVB_LAYER_IMPORT)
+    int32_t hosp_max, icu_max; // 0 / 1 as given by the caller, -1 = evaluate from today's severe / critical counts (sim.py:579-580)
 };
 
 __device__ __forceinline__ double draw_dur(const cvb_pars& pars, int which, uint64_t seed, int32_t t, int64_t i, uint32_t slot) {
@@ -41,8 +42,8 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
     const int64_t n = ia.n;
     const int32_t t = ia.t;
     const unsigned int n_cand = *n_cand_ptr;
-    const bool hosp_max = pars.n_beds_hosp >= 0 && (long long)beds[(int64_t)t * 2 + 0] > pars.n_beds_hosp;
-    const bool icu_max = pars.n_beds_icu >= 0 && (long long)beds[(int64_t)t * 2 + 1] > pars.n_beds_icu;
+    const bool hosp_max = ia.hosp_max >= 0 ? ia.hosp_max != 0 : (pars.n_beds_hosp >= 0 && (long long)beds[(int64_t)t * 2 + 0] > pars.n_beds_hosp);
+    const bool icu_max = ia.icu_max >= 0 ? ia.icu_max != 0 : (pars.n_beds_icu >= 0 && (long long)beds[(int64_t)t * 2 + 1] > pars.n_beds_icu);
     const float tf = (float)t;
 
     for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_cand; j += gridDim.x * blockDim.x) {
@@ -210,12 +211,14 @@ __global__ void claim_list_kernel(const int32_t* __restrict__ inds, int64_t n_in
 
 __global__ void reset_u32_kernel(unsigned int* p) { *p = 0; }
 
-static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t list_layer_code, int64_t max_items, cudaStream_t st) {
+static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t list_layer_code, int32_t hosp_max, int32_t icu_max,
+                         int64_t max_items, cudaStream_t st) {
     CVB_REQUIRE(s->log.count, "infect: infection log is not bound (cvb_bind_log)");
     LayerTable L;
     if (build_layer_table(s, L)) return 1;
     InfectArgs ia;
     ia.seed = s->seed; ia.n = s->n; ia.t = t; ia.count_flows = count_flows; ia.list_layer_code = list_layer_code;
+    ia.hosp_max = hosp_max; ia.icu_max = icu_max;
     int grid = grid_for(max_items, kThreads, 148 * 4);
     infect_kernel<<<grid, kThreads, 0, st>>>(s->people, s->pars, L, ia, s->cand, s->n_cand, s->infect_key, s->beds, s->res, s->log);
     CVB_LAUNCH_CHECK();
@@ -234,11 +237,11 @@ int cvb_infect_winners(cvb_sim* s, int32_t t, cvb_stream st) {
     // the number of candidates is only known on the device: size the grid for a large outbreak and let
     // surplus CTAs exit after one load of n_cand
     int64_t guess = s->n / 16 + 1024;
-    return launch_infect(s, t, 1, CVB_LAYER_SEED, guess, (cudaStream_t)st);
+    return launch_infect(s, t, 1, CVB_LAYER_SEED, -1, -1, guess, (cudaStream_t)st);
 }
 
 int cvb_infect_list(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant, int32_t layer_code, int32_t t,
-                    int32_t count_flows, cvb_stream st_) {
+                    int32_t count_flows, int32_t hosp_max, int32_t icu_max, cvb_stream st_) {
     cudaStream_t st = (cudaStream_t)st_;
     CVB_REQUIRE(s && s->pars_set && s->res.counters, "cvb_infect_list: handle not ready");
     CVB_REQUIRE(variant >= 0 && variant < s->nv, "cvb_infect_list: variant %d out of range", variant);
@@ -249,7 +252,7 @@ int cvb_infect_list(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant,
     CVB_LAUNCH_CHECK();
     claim_list_kernel<<<grid_for(n), kThreads, 0, st>>>(inds, n, variant, s->n, s->infect_key, s->cand, s->n_cand);
     CVB_LAUNCH_CHECK();
-    if (launch_infect(s, t, count_flows, layer_code, n, st)) return 1;
+    if (launch_infect(s, t, count_flows, layer_code, hosp_max, icu_max, n, st)) return 1;
     reset_u32_kernel<<<1, 1, 0, st>>>(s->n_cand);
     CVB_LAUNCH_CHECK();
     return 0;

@@ -148,8 +148,10 @@ class People:
     def infect(self, inds, hosp_max=None, icu_max=None, source=None, layer=None, variant=0, count_flows=True):
         '''
         Infect agents and sample their disease course on the device (reference people.py:435-586).
-        ``hosp_max`` / ``icu_max`` are evaluated on the device from the day's severe / critical counts;
-        duplicates and non-susceptible agents are dropped.  ``source`` is not needed: importations and seed
+        ``hosp_max`` / ``icu_max``: None or False = beds available (the reference's default, used for seed
+        infections and variant importations), True = no beds, 'auto' = decided on the device from today's
+        severe / critical counts against n_beds_* (what Sim.step passes; reference sim.py:579-580).
+        Duplicates and non-susceptible agents are dropped.  ``source`` is not needed: importations and seed
         infections have none, and transmissions are infected by the fused edge pass.
         '''
         sim = self._sim
@@ -157,7 +159,9 @@ class People:
         if len(inds) == 0:
             return inds
         code = {'seed_infection': _capi.LAYER_SEED, 'importation': _capi.LAYER_IMPORT}.get(layer, _capi.LAYER_IMPORT)
-        _capi.call('cvb_infect_list', sim._handle, inds.data_ptr(), len(inds), int(variant), code, int(sim.t), int(bool(count_flows)), sim._stream_ptr)
+        beds = lambda x: -1 if isinstance(x, str) and x == 'auto' else int(bool(x))
+        _capi.call('cvb_infect_list', sim._handle, inds.data_ptr(), len(inds), int(variant), code, int(sim.t), int(bool(count_flows)),
+                   beds(hosp_max), beds(icu_max), sim._stream_ptr)
         return inds
 
     def schedule_quarantine(self, inds, start_date=None, period=None):

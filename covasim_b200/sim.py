@@ -66,6 +66,7 @@ class Sim:
         self._pars_dirty = True
         self._quar_horizon = 1
         self._host_adds = {}
+        self.kernel_timers = None          # set to {} to time every C-ABI call of step() with CUDA events
 
     # ---- dict-like parameter access (reference base.py:63-114) -----------------------------------
     def __getitem__(self, key):
@@ -283,6 +284,92 @@ class Sim:
             _capi.call('cvb_set_quar_horizon', self._handle, int(horizon))
             self._quar_horizon = int(horizon)
 
+    # ---- checkpoint / restore (reference base.py:682-741 Sim.save/load, sim.py:688-761 resume) ----------
+    def snapshot(self, pinned=True):
+        '''
+        Host copy of everything a run mutates: every People array, every layer's edge list, the RNG streams,
+        the clock, the result tables and the intervention-owned device arrays.  With ``pinned=True`` the
+        buffers are page-locked so ``restore`` is one asynchronous H2D copy per array.
+        '''
+        torch.cuda.synchronize(self.device)
+
+        def host(t):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=pinned)
+            h.copy_(t)
+            return h
+        snap = dict(t=self.t, complete=self.complete,
+                    people={k: host(self.people[k]) for k in self.people.keys()},
+                    layers={lk: {c: host(l[c]) for c in l.columns} for lk, l in self.people.contacts.items()},
+                    counters=host(self._counters), vcounters=host(self._vcounters), sums=host(self._sums),
+                    log_count=host(self._log['count']), host_adds={k: v.copy() for k, v in self._host_adds.items()},
+                    rng=(self.rng.seed, self.rng.np_.get_state(), self.rng.nb.get_state()),
+                    pars={k: copy.deepcopy(v) for k, v in self.pars.items() if k not in ('interventions', 'analyzers', 'variants', 'prognoses', 'nab_kin')},
+                    iv=[{k: host(v) for k, v in vars(iv).items() if isinstance(v, torch.Tensor)} if hasattr(iv, '__dict__') else {}
+                        for iv in self.pars['interventions']])
+        torch.cuda.synchronize(self.device)
+        return snap
+
+    def restore_light(self, snap):
+        ''' restore() without the People / Layer copies: for callers that rewound those arrays on the device themselves '''
+        return self.restore(snap, arrays=False)
+
+    def restore(self, snap, arrays=True):
+        ''' Put a snapshot back on the device (asynchronous copies from pinned memory) and rewind the clock '''
+        if snap['t'] != 0 and self._quar_horizon > 1:
+            raise NotImplementedError('restoring mid-run with delayed quarantine requests pending is not built')
+        if arrays:
+            for k, h in snap['people'].items():
+                self.people[k].copy_(h, non_blocking=True)
+            for lk, cols in snap['layers'].items():
+                layer = self.people.contacts[lk]
+                for c, h in cols.items():
+                    if layer[c].shape == h.shape:
+                        layer[c].copy_(h, non_blocking=True)
+                    else:
+                        layer[c] = h
+        self._counters.copy_(snap['counters'], non_blocking=True)
+        self._vcounters.copy_(snap['vcounters'], non_blocking=True)
+        self._sums.copy_(snap['sums'], non_blocking=True)
+        self._log['count'].copy_(snap['log_count'], non_blocking=True)
+        for iv, saved in zip(self.pars['interventions'], snap['iv']):
+            for k, h in saved.items():
+                getattr(iv, k).copy_(h, non_blocking=True)
+            if hasattr(iv, '_due_days'):
+                iv._due_days = set()
+            if hasattr(iv, 'finalized'):
+                iv.finalized = False
+        _capi.call('cvb_reset', self._handle, self._stream_ptr)
+        self._host_adds = {k: v.copy() for k, v in snap['host_adds'].items()}
+        seed, np_state, nb_state = snap['rng']
+        self.rng.seed = seed
+        self.rng.np_.set_state(np_state)
+        self.rng.nb.set_state(nb_state)
+        for k, v in snap['pars'].items():
+            self.pars[k] = copy.deepcopy(v)
+        self._pars_dirty = True
+        self.t = snap['t']
+        self.complete = snap['complete']
+        self.results_ready = False
+        self._orig_pars = None
+        for k in self.result_keys():
+            self.results[k].values[:] = 0
+        for k in self.result_keys('variant'):
+            self.results['variant'][k].values[:] = 0
+        return self
+
+    def h2d_bytes(self, snap):
+        ''' Bytes restore() copies host -> device '''
+        n = sum(h.numel() * h.element_size() for h in snap['people'].values())
+        n += sum(h.numel() * h.element_size() for cols in snap['layers'].values() for h in cols.values())
+        n += sum(snap[k].numel() * snap[k].element_size() for k in ('counters', 'vcounters', 'sums', 'log_count'))
+        n += sum(h.numel() * h.element_size() for saved in snap['iv'] for h in saved.values())
+        return int(n)
+
+    def d2h_bytes(self):
+        ''' Bytes finalize() reads device -> host (result tables + the three date arrays compute_r_eff needs) '''
+        n = sum(t.numel() * t.element_size() for t in (self._counters, self._vcounters, self._sums))
+        return int(n + 3 * 4 * self.n)
+
     # ---- parameters -> device struct ---------------------------------------------------------------
     def _pars_fingerprint(self):
         p = self.pars
@@ -361,7 +448,7 @@ class Sim:
             raise AlreadyRunError('Simulation already complete (call sim.initialize() to re-run)')
         t, pars, people, h, st = self.t, self.pars, self.people, self._handle, self._stream_ptr
         people.t = t
-        call = _capi.call
+        call = _capi.call if self.kernel_timers is None else self._timed_call
         self._push_pars()
         call('cvb_update_states_pre', h, t, st)
         for lkey, dyn in pars['dynam_layer'].items():                                 # reference people.py:199-206
@@ -371,7 +458,7 @@ class Sim:
             n_imports = int(self.rng.nb.poisson(f32(pars['n_imports'] / self.rescale_vec[t]), 1)[0])
             if n_imports > 0:
                 who = self.rng.nb.choice(pars['pop_size'], n_imports, replace=False)
-                people.infect(who, layer='importation')
+                people.infect(who, hosp_max='auto', icu_max='auto', layer='importation')
                 self._host_add('n_imports', t, n_imports)
         for v in pars['variants']:
             v.apply(self)
@@ -388,6 +475,14 @@ class Sim:
         self.t += 1
         if self.t == self.npts:
             self.complete = True
+
+    def _timed_call(self, name, *args):
+        ''' _capi.call bracketed by CUDA events on the launching stream (bench.py's per-kernel timing) '''
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _capi.call(name, *args)
+        b.record()
+        self.kernel_timers.setdefault(name, []).append((a, b))
 
     def run(self, until=None, reset_seed=True, restore_pars=True, verbose=None, **kwargs):
         ''' Run to the end (or to ``until``) and finalize (reference sim.py:688-761) '''

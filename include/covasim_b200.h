@@ -69,6 +69,8 @@ typedef struct cvb_pars {
 
 const char* cvb_last_error(void);
 int32_t cvb_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (for bench.py's gpu_launches) */
+int64_t cvb_launch_count(void);
 /* sizeof of {cvb_pars, cvb_dist, cvb_test_prob_pars, cvb_trace_pars, cvb_vaccinate_pars} -> host int64[5] */
 int cvb_struct_sizes(int64_t* out5);
 
@@ -78,6 +80,9 @@ int cvb_struct_sizes(int64_t* out5);
 int cvb_create(cvb_sim** out, int64_t n_agents, int32_t n_variants, int32_t npts, uint64_t seed);
 int cvb_destroy(cvb_sim* s);
 int cvb_set_seed(cvb_sim* s, uint64_t seed);
+/* Clear the library-owned per-run scratch (pending-quarantine ring, winner keys, bed counts) so that the
+ * handle can run the same simulation again from a restored People state (Sim.restore) */
+int cvb_reset(cvb_sim* s, cvb_stream st);
 int cvb_set_pars(cvb_sim* s, const cvb_pars* host_pars);
 /* Bind one per-agent array (length n_agents, or n_variants*n_agents for the by-variant / immunity
  * fields).  Replaces People.__setitem__ on the NumPy arrays (reference base.py:1007-1027). */
@@ -148,6 +153,8 @@ int cvb_infect_winners(cvb_sim* s, int32_t t, cvb_stream st);
  * variant imports immunity.py:128); duplicates / non-susceptibles are dropped; keyed draws */
 int cvb_infect_list(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant, int32_t layer_code, int32_t t,
                     int32_t count_flows /* 0 for seed infections at initialisation: their flows are discarded */,
+                    int32_t hosp_max, int32_t icu_max /* 0 / 1 as the caller decided (people.py:435), -1: from today's severe /
+                                                         critical counts vs n_beds_* (sim.py:579-580) */,
                     cvb_stream st);
 /* immunity.py:205-213 update_nab + sim.py:652-674 stock counts and population means */
 int cvb_update_nab_count(cvb_sim* s, int32_t t, cvb_stream st);

@@ -94,6 +94,7 @@ PROTOTYPES = dict(
     cvb_schedule_quarantine=[_P, _P, _i64, _i32, _f32, _P],
     cvb_update_states_post=[_P, _i32, _P],
     cvb_prepare_transmission=[_P, _i32, _P],
+    cvb_post_and_prepare=[_P, _i32, _P],
     cvb_edge_pass=[_P, _i32, _P],
     cvb_infect_winners=[_P, _i32, _P],
     cvb_infect_list=[_P, _P, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _P],

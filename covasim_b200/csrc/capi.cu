@@ -114,6 +114,8 @@ int cvb_create(cvb_sim** out, int64_t n_agents, int32_t n_variants, int32_t npts
         int64_t words = (n_agents + 31) / 32;
         if ((rc = check_cuda(cudaMalloc((void**)&s->case_bits, (size_t)words * sizeof(unsigned int)), "case_bits"))) break;
         if ((rc = check_cuda(cudaMemset(s->case_bits, 0, (size_t)words * sizeof(unsigned int)), "case_bits"))) break;
+        if ((rc = check_cuda(cudaMalloc((void**)&s->inf_bits, (size_t)(words + 4) * sizeof(unsigned int)), "inf_bits"))) break;
+        if ((rc = check_cuda(cudaMemset(s->inf_bits, 0, (size_t)(words + 4) * sizeof(unsigned int)), "inf_bits"))) break;
         if ((rc = check_cuda(cudaMalloc((void**)&s->n_cases, 64), "n_cases"))) break;
         if ((rc = check_cuda(cudaMemset(s->n_cases, 0, 64), "n_cases"))) break;
         if ((rc = check_cuda(cudaMalloc((void**)&s->dev_scalars, 16 * sizeof(unsigned long long)), "dev_scalars"))) break;
@@ -128,7 +130,7 @@ int cvb_create(cvb_sim** out, int64_t n_agents, int32_t n_variants, int32_t npts
 
 int cvb_destroy(cvb_sim* s) {
     if (!s) return 0;
-    cudaFree(s->cand); cudaFree(s->n_cand); cudaFree(s->infect_key); cudaFree(s->beds); cudaFree(s->quar_ring); cudaFree(s->case_bits);
+    cudaFree(s->cand); cudaFree(s->n_cand); cudaFree(s->infect_key); cudaFree(s->beds); cudaFree(s->quar_ring); cudaFree(s->case_bits); cudaFree(s->inf_bits);
     cudaFree(s->n_cases); cudaFree(s->dev_scalars); cudaFree(s->rec.ts); cudaFree(s->rec.sus_extra); cudaFree(s->rec.ivar);
     cudaFree(s->nab_kin); cudaFree(s->tile_cnt); cudaFree(s->hit_mask); cudaFree(s->flag_tmp); cudaFree(s->partial);
     if (s->host_scalars) cudaFreeHost(s->host_scalars);

@@ -74,6 +74,7 @@ struct cvb_sim {
     double* nab_kin; int64_t nab_kin_len;           // NAb kinetics table (immunity.py:298)
     float* quar_ring; int32_t quar_horizon;         // [quar_horizon][N] pending quarantine end days, -1 = none
     unsigned int* case_bits; unsigned int* n_cases; // contact tracing: bitmap of today's cases
+    unsigned int* inf_bits;                         // [ceil(N/32)] agents that can transmit today (written by prepare_transmission)
     // scan / compaction workspace
     unsigned int* tile_cnt; int64_t tile_cnt_cap;   // per-tile counts (and their exclusive scan, in place)
     uint8_t* hit_mask; int64_t hit_mask_cap;
@@ -163,6 +164,48 @@ __device__ __forceinline__ unsigned int warp_append32(unsigned int* counter) {
     base = __shfl_sync(mask, base, leader);
     return base + __popc(mask & ((1u << lane_id()) - 1u));
 }
+
+// ---- four agents per thread: vector loads of the structure-of-arrays fields -------------------------
+constexpr int kAPT = 4;                                    // agents per thread
+
+__device__ __forceinline__ void load4(const float* __restrict__ p, int64_t i0, int64_t n, bool vec, float fill, float o[4]) {
+    if (vec && i0 + 4 <= n) {
+        float4 v = *reinterpret_cast<const float4*>(p + i0);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = (i0 + k < n) ? p[i0 + k] : fill;
+    }
+}
+__device__ __forceinline__ void load4(const int32_t* __restrict__ p, int64_t i0, int64_t n, bool vec, int32_t o[4]) {
+    if (vec && i0 + 4 <= n) {
+        int4 v = *reinterpret_cast<const int4*>(p + i0);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) o[k] = (i0 + k < n) ? p[i0 + k] : 0;
+    }
+}
+// four bool bytes as one 32-bit word (byte k = agent i0+k)
+__device__ __forceinline__ uint32_t load4b(const uint8_t* __restrict__ p, int64_t i0, int64_t n, bool vec) {
+    if (vec && i0 + 4 <= n) return *reinterpret_cast<const uint32_t*>(p + i0);
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (i0 + k < n) w |= (uint32_t)p[i0 + k] << (8 * k);
+    return w;
+}
+__device__ __forceinline__ bool flag(uint32_t w, int k) { return ((w >> (8 * k)) & 0xFFu) != 0; }
+__device__ __forceinline__ int count4(uint32_t w) { return __popc(__vcmpne4(w, 0u) & 0x01010101u); }
+
+template <int NK>
+__device__ __forceinline__ void reduce_counters(const int (&c)[NK], int* s_cnt) {
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        int w = __reduce_add_sync(0xFFFFFFFFu, c[k]);
+        if (lane_id() == 0 && w) atomicAdd(&s_cnt[k], w);
+    }
+}
+
 
 // 128-bit streaming loads that do not allocate in L1 (edge arrays are read exactly once per pass)
 __device__ __forceinline__ int4 ld_stream(const int4* p) {

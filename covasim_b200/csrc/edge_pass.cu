@@ -4,12 +4,22 @@
 // + compute_infections per variant and layer, both directions) and re-gathers per-agent values with
 // fancy indexing each time.  Here every edge (p1:int32, p2:int32, beta:f32 = 12 bytes) of every layer
 // is streamed from HBM exactly ONCE per day with 128-bit coalesced loads; both directions and all
-// variants are evaluated from the two 8-byte {rel_trans, rel_sus} records of its endpoints (written by
-// prepare_transmission; L2-resident gathers).  Algorithmic bytes per day: 12*E_total + 8*N.
+// variants are evaluated from the 8-byte {rel_trans, rel_sus} records of its endpoints (written by
+// prepare_transmission).  Algorithmic bytes per day: 12*E_total + 8*N.
+//
+// Structure of one CTA (v2; see profiles/r1 for why):
+//   1. the day's "can transmit" bitmap (1 bit per agent, written by prepare_transmission) is staged in
+//      SHARED MEMORY (125 KB at 1M agents; a global/L1 path is used when it does not fit);
+//   2. each thread streams 4 edges and tests the two endpoint bits -- at the epidemic peak ~80 % of the
+//      edges have no infectious endpoint and are dropped here, after 12 bytes of HBM traffic and two
+//      shared-memory bit tests, without any L2 gather;
+//   3. surviving edges are appended to a per-warp queue in shared memory (ballot + popc compaction) and
+//      drained 32 at a time, so the expensive part -- two L2 gathers of the endpoint records, the
+//      float32 probability chain and the Philox4x32-10 draw -- always runs on full warps instead of on
+//      every warp that happens to contain one live lane.
 //
 // Randomness: one Philox4x32-10 call per LIVE edge (non-zero probability in either direction), keyed
 // (seed, P_EDGE, layer, day, edge index): words 0-1 give the p1->p2 uniform, words 2-3 the p2->p1 one.
-// Dead edges (>= 85 % of them even at the epidemic peak) cost no RNG work.
 //
 // Output: for each target hit at least once, infect_key[target] = min over successful transmissions
 // of (variant, layer, direction, edge) -- exactly the reference's winner: variants and layers are
@@ -24,8 +34,11 @@ struct EdgeParams {
     float beta[CVB_MAX_VARIANTS];
     uint64_t seed;
     int64_t n;
+    int64_t n_words;        // words of the transmit bitmap
     int32_t t, nv;
 };
+
+constexpr int kQueueCap = 160;            // < 32 left over + up to 128 appended per iteration
 
 __device__ __forceinline__ void record_hit(unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand,
                                            unsigned int* __restrict__ n_cand, int target, unsigned long long key) {
@@ -36,84 +49,148 @@ __device__ __forceinline__ void record_hit(unsigned long long* __restrict__ infe
     }
 }
 
+// Evaluate one candidate edge in both directions (reference utils.py:113-123) and record transmissions
 template <bool MULTI>
-__global__ void __launch_bounds__(kThreads) edge_pass_kernel(const __grid_constant__ LayerTable L, TransRecords rec,
-        const __grid_constant__ EdgeParams ep, unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand,
-        unsigned int* __restrict__ n_cand) {
+__device__ __forceinline__ void process_edge(const TransRecords& rec, const EdgeParams& ep, int a, int b, float w, int l, int64_t e,
+        unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand) {
     const int64_t n = ep.n;
+    const float2* __restrict__ ts = rec.ts + (int64_t)l * n;
+    const float2 ra = __ldg(ts + a), rb = __ldg(ts + b);
+    float p01 = 0.0f, p10 = 0.0f;
+    int va = 0, vb = 0;
+    if (ra.x != 0.0f) {                       // a can transmit on this layer
+        float sb = rb.y;
+        if (MULTI) {
+            va = rec.ivar[a];
+            if (va > 0) sb = __ldg(rec.sus_extra + ((int64_t)l * (ep.nv - 1) + (va - 1)) * n + b);
+        }
+        p01 = edge_prob(ep.beta[va], w, ra.x, sb);
+    }
+    if (rb.x != 0.0f) {                       // b can transmit on this layer
+        float sa = ra.y;
+        if (MULTI) {
+            vb = rec.ivar[b];
+            if (vb > 0) sa = __ldg(rec.sus_extra + ((int64_t)l * (ep.nv - 1) + (vb - 1)) * n + a);
+        }
+        p10 = edge_prob(ep.beta[vb], w, rb.x, sa);
+    }
+    if (p01 != 0.0f || p10 != 0.0f) {
+        const u32x4 r = keyed_words(ep.seed, P_EDGE, (uint32_t)l, ep.t, e, 0);
+        const unsigned long long base = ((unsigned long long)l << 48) | (unsigned long long)e;
+        if (p01 != 0.0f && u53(r.x, r.y) < (double)p01)
+            record_hit(infect_key, cand, n_cand, b, ((unsigned long long)va << 56) | base);
+        if (p10 != 0.0f && u53(r.z, r.w) < (double)p10)
+            record_hit(infect_key, cand, n_cand, a, ((unsigned long long)vb << 56) | (1ull << 40) | base);
+    }
+}
+
+template <bool MULTI, bool SMEM_BITS, int THREADS>
+__global__ void __launch_bounds__(THREADS) edge_pass_kernel(const __grid_constant__ LayerTable L, TransRecords rec,
+        const __grid_constant__ EdgeParams ep, const unsigned int* __restrict__ inf_bits, unsigned long long* __restrict__ infect_key,
+        int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kWarps = THREADS / 32;
+    constexpr int kTile = THREADS * kEdgesPerThread;
+    // layout: [queue entries uint4 x kWarps*kQueueCap][queue meta u16 x kWarps*kQueueCap][bitmap words]
+    uint4* q_edge = reinterpret_cast<uint4*>(smem_raw) + warp_id() * kQueueCap;
+    unsigned short* q_meta = reinterpret_cast<unsigned short*>(smem_raw + (size_t)kWarps * kQueueCap * sizeof(uint4)) + warp_id() * kQueueCap;
+    const unsigned int* bits = inf_bits;
+    if (SMEM_BITS) {
+        unsigned int* s_bits = reinterpret_cast<unsigned int*>(smem_raw + (size_t)kWarps * kQueueCap * (sizeof(uint4) + sizeof(unsigned short)));
+        for (int64_t wd = threadIdx.x; wd < ep.n_words; wd += THREADS) s_bits[wd] = inf_bits[wd];
+        bits = s_bits;
+        __syncthreads();
+    }
+    const int lane = lane_id();
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int qn = 0;                                                     // warp-uniform queue length
+
     const int64_t total_tiles = L.tile_start[L.n_layers];
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int l = 0;
 #pragma unroll
         for (int q = 1; q < CVB_MAX_LAYERS; ++q) l += (q < L.n_layers && tile >= L.tile_start[q]);
         const LayerPtrs& lay = L.l[l];
-        const int64_t e0 = (tile - L.tile_start[l]) * kTileEdges + (int64_t)threadIdx.x * kEdgesPerThread;
-        if (e0 >= lay.n_edges) continue;
+        const int64_t e0 = (tile - L.tile_start[l]) * kTile + (int64_t)threadIdx.x * kEdgesPerThread;
         int a[4], b[4];
         float w[4];
-        int cnt;
+        int cnt = 0;
         if (e0 + 4 <= lay.n_edges) {
-            int4 va = ld_stream(reinterpret_cast<const int4*>(lay.p1 + e0));
-            int4 vb = ld_stream(reinterpret_cast<const int4*>(lay.p2 + e0));
-            float4 vw = ld_stream(reinterpret_cast<const float4*>(lay.beta + e0));
+            const int4 va = ld_stream(reinterpret_cast<const int4*>(lay.p1 + e0));
+            const int4 vb = ld_stream(reinterpret_cast<const int4*>(lay.p2 + e0));
+            const float4 vw = ld_stream(reinterpret_cast<const float4*>(lay.beta + e0));
             a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w;
             b[0] = vb.x; b[1] = vb.y; b[2] = vb.z; b[3] = vb.w;
             w[0] = vw.x; w[1] = vw.y; w[2] = vw.z; w[3] = vw.w;
             cnt = 4;
-        } else {
+        } else if (e0 < lay.n_edges) {
             cnt = (int)(lay.n_edges - e0);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                bool ok = k < cnt;
+                const bool ok = k < cnt;
                 a[k] = ok ? lay.p1[e0 + k] : 0; b[k] = ok ? lay.p2[e0 + k] : 0; w[k] = ok ? lay.beta[e0 + k] : 0.0f;
             }
-        }
-        const float2* __restrict__ ts = rec.ts + (int64_t)l * n;
-        // issue all eight gathers before using any of them (memory-level parallelism, Guideline 7)
-        float2 ra[4], rb[4];
+        } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { ra[k] = __ldg(ts + a[k]); rb[k] = __ldg(ts + b[k]); }
+            for (int k = 0; k < 4; ++k) { a[k] = 0; b[k] = 0; w[k] = 0.0f; }
+        }
+        // prefilter: keep an edge only if one endpoint can transmit (2 bit tests in shared memory)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            if (k >= cnt) break;
-            float p01 = 0.0f, p10 = 0.0f;
-            int va_ = 0, vb_ = 0;
-            if (ra[k].x != 0.0f) {                       // a can transmit
-                float sb = rb[k].y;
-                if (MULTI) {
-                    va_ = rec.ivar[a[k]];
-                    if (va_ > 0) sb = __ldg(rec.sus_extra + ((int64_t)l * (ep.nv - 1) + (va_ - 1)) * n + b[k]);
-                }
-                p01 = edge_prob(ep.beta[va_], w[k], ra[k].x, sb);
+            const unsigned short meta = (unsigned short)((l << 8) | (int)(((e0 + k) >> 32) & 0xFF));
+            bool keep = false;
+            if (k < cnt) {
+                const unsigned wa = bits[a[k] >> 5], wb = bits[b[k] >> 5];
+                keep = (((wa >> (a[k] & 31)) | (wb >> (b[k] & 31))) & 1u) != 0;
             }
-            if (rb[k].x != 0.0f) {                       // b can transmit
-                float sa = ra[k].y;
-                if (MULTI) {
-                    vb_ = rec.ivar[b[k]];
-                    if (vb_ > 0) sa = __ldg(rec.sus_extra + ((int64_t)l * (ep.nv - 1) + (vb_ - 1)) * n + a[k]);
-                }
-                p10 = edge_prob(ep.beta[vb_], w[k], rb[k].x, sa);
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+            if (keep) {
+                const int pos = qn + __popc(m & lt_mask);
+                q_edge[pos] = make_uint4((unsigned)a[k], (unsigned)b[k], __float_as_uint(w[k]), (unsigned)((e0 + k) & 0xFFFFFFFFll));
+                q_meta[pos] = meta;
             }
-            if (p01 != 0.0f || p10 != 0.0f) {
-                const int64_t e = e0 + k;
-                u32x4 r = keyed_words(ep.seed, P_EDGE, (uint32_t)l, ep.t, e, 0);
-                unsigned long long base = ((unsigned long long)l << 48) | (unsigned long long)e;
-                if (p01 != 0.0f && u53(r.x, r.y) < (double)p01)
-                    record_hit(infect_key, cand, n_cand, b[k], ((unsigned long long)va_ << 56) | base);
-                if (p10 != 0.0f && u53(r.z, r.w) < (double)p10)
-                    record_hit(infect_key, cand, n_cand, a[k], ((unsigned long long)vb_ << 56) | (1ull << 40) | base);
-            }
+            qn += __popc(m);
         }
+        __syncwarp();
+        // drain full warps of candidates
+        while (qn >= 32) {
+            qn -= 32;
+            const uint4 c = q_edge[qn + lane];
+            const unsigned short cm = q_meta[qn + lane];
+            __syncwarp();
+            process_edge<MULTI>(rec, ep, (int)c.x, (int)c.y, __uint_as_float(c.z), cm >> 8, ((int64_t)(cm & 0xFF) << 32) | c.w,
+                                infect_key, cand, n_cand);
+        }
+        __syncwarp();
     }
+    if (lane < qn) {                                                // leftovers
+        const uint4 c = q_edge[lane];
+        const unsigned short cm = q_meta[lane];
+        process_edge<MULTI>(rec, ep, (int)c.x, (int)c.y, __uint_as_float(c.z), cm >> 8, ((int64_t)(cm & 0xFF) << 32) | c.w,
+                            infect_key, cand, n_cand);
+    }
+}
+
+int build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges);
+
+template <bool MULTI, bool SMEM_BITS, int THREADS>
+static int launch_edge_pass(cvb_sim* s, const LayerTable& L, const EdgeParams& ep, size_t smem, int grid, cudaStream_t st) {
+    auto kern = edge_pass_kernel<MULTI, SMEM_BITS, THREADS>;
+    static bool configured = false;                                  // per instantiation
+    if (!configured) {
+        CVB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    kern<<<grid, THREADS, smem, st>>>(L, s->rec, ep, s->inf_bits, s->infect_key, s->cand, s->n_cand);
+    CVB_LAUNCH_CHECK();
+    return 0;
 }
 
 }  // namespace cvb
 
 using namespace cvb;
 
-namespace cvb { int build_layer_table(cvb_sim* s, LayerTable& L); }
-
-int cvb::build_layer_table(cvb_sim* s, LayerTable& L) {
+int cvb::build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges) {
     L.n_layers = s->pars.n_layers;
     int64_t acc = 0;
     for (int l = 0; l < CVB_MAX_LAYERS; ++l) {
@@ -122,7 +199,7 @@ int cvb::build_layer_table(cvb_sim* s, LayerTable& L) {
             L.l[l] = s->layers[l];
             CVB_REQUIRE(L.l[l].n_edges == 0 || L.l[l].p1, "layer %d is not bound (cvb_bind_layer)", l);
             CVB_REQUIRE(L.l[l].n_edges < (1ll << 40), "layer %d has too many edges for the 40-bit edge field", l);
-            acc += (L.l[l].n_edges + kTileEdges - 1) / kTileEdges;
+            acc += (L.l[l].n_edges + tile_edges - 1) / tile_edges;
         } else {
             L.l[l] = LayerPtrs{nullptr, nullptr, nullptr, 0};
         }
@@ -131,22 +208,45 @@ int cvb::build_layer_table(cvb_sim* s, LayerTable& L) {
     return 0;
 }
 
-extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st) {
+extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
+    cudaStream_t st = (cudaStream_t)st_;
     CVB_REQUIRE(s && s->pars_set, "cvb_edge_pass: handle not ready");
     CVB_REQUIRE(s->rec.ts && s->rec_layers >= s->pars.n_layers, "cvb_edge_pass: call cvb_prepare_transmission first");
-    LayerTable L;
-    if (build_layer_table(s, L)) return 1;
-    int64_t total_tiles = L.tile_start[L.n_layers];
-    if (total_tiles == 0) return 0;
     EdgeParams ep;
     for (int v = 0; v < CVB_MAX_VARIANTS; ++v) ep.beta[v] = s->pars.beta[v];
     ep.seed = s->seed; ep.n = s->n; ep.t = t; ep.nv = s->nv;
-    // persistent-style grid: a multiple of the SM count, 8 resident CTAs of 256 threads per SM
-    int grid = (int)(total_tiles < 148 * 8 ? total_tiles : 148 * 8);
-    if (s->nv > 1)
-        edge_pass_kernel<true><<<grid, kThreads, 0, (cudaStream_t)st>>>(L, s->rec, ep, s->infect_key, s->cand, s->n_cand);
-    else
-        edge_pass_kernel<false><<<grid, kThreads, 0, (cudaStream_t)st>>>(L, s->rec, ep, s->infect_key, s->cand, s->n_cand);
-    CVB_LAUNCH_CHECK();
-    return 0;
+    ep.n_words = (s->n + 31) / 32;
+    const bool multi = s->nv > 1;
+    // shared-memory budget: per-warp candidate queue (18 B x 160 entries) + the transmit bitmap
+    const size_t bitmap_bytes = (size_t)ep.n_words * sizeof(unsigned int);
+    const size_t queue_1024 = (size_t)32 * kQueueCap * (sizeof(uint4) + sizeof(unsigned short));
+    const size_t queue_512 = queue_1024 / 2, queue_256 = queue_1024 / 4;
+    const size_t limit = 227 * 1024;
+    LayerTable L;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
+    if (bitmap_bytes + queue_1024 <= limit) {
+        // one persistent 1024-thread CTA per SM, bitmap in shared memory
+        if (build_layer_table(s, L, 1024 * kEdgesPerThread)) return 1;
+        const int64_t tiles = L.tile_start[L.n_layers];
+        if (tiles == 0) return 0;
+        const int grid = (int)(tiles < n_sm ? tiles : n_sm);
+        return multi ? launch_edge_pass<true, true, 1024>(s, L, ep, bitmap_bytes + queue_1024, grid, st)
+                     : launch_edge_pass<false, true, 1024>(s, L, ep, bitmap_bytes + queue_1024, grid, st);
+    }
+    if (bitmap_bytes + queue_512 <= limit) {
+        if (build_layer_table(s, L, 512 * kEdgesPerThread)) return 1;
+        const int64_t tiles = L.tile_start[L.n_layers];
+        if (tiles == 0) return 0;
+        const int grid = (int)(tiles < n_sm ? tiles : n_sm);
+        return multi ? launch_edge_pass<true, true, 512>(s, L, ep, bitmap_bytes + queue_512, grid, st)
+                     : launch_edge_pass<false, true, 512>(s, L, ep, bitmap_bytes + queue_512, grid, st);
+    }
+    // large populations: bitmap stays in global memory (L1/L2-cached bit tests), 8 CTAs of 256 threads per SM
+    if (build_layer_table(s, L, 256 * kEdgesPerThread)) return 1;
+    const int64_t tiles = L.tile_start[L.n_layers];
+    if (tiles == 0) return 0;
+    const int grid = (int)(tiles < (int64_t)n_sm * 8 ? tiles : (int64_t)n_sm * 8);
+    return multi ? launch_edge_pass<true, false, 256>(s, L, ep, queue_256, grid, st)
+                 : launch_edge_pass<false, false, 256>(s, L, ep, queue_256, grid, st);
 }

@@ -5,6 +5,7 @@
 //   Layer.update (frac = 1)            reference base.py:1849-1876
 // All Bernoulli draws are keyed per agent (or per agent x layer for tracing), so results are
 // independent of thread order; see oracle/cvoracle.py for the CPU restatement they are tested against.
+#include <string.h>
 #include "cvb_internal.cuh"
 
 namespace cvb {
@@ -13,41 +14,55 @@ namespace cvb {
 // test_prob
 // ================================================================================================
 __global__ void __launch_bounds__(kThreads) test_prob_kernel(PeoplePtrs P, const __grid_constant__ cvb_test_prob_pars tp, uint64_t seed,
-        int64_t n, int32_t t, unsigned long long* __restrict__ counters) {
+        int64_t n, int32_t t, bool vec, unsigned long long* __restrict__ counters) {
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
     int c = 0;
     const float tf = (float)t;
+    const float qnan = nanf32();
     const uint8_t* symptomatic = PB(P, symptomatic); const uint8_t* diagnosed = PB(P, diagnosed); const uint8_t* quarantined = PB(P, quarantined);
     const uint8_t* infectious = PB(P, infectious); uint8_t* tested = PB(P, tested);
     const float* d_quar = PF(P, date_quarantined); const float* d_end_quar = PF(P, date_end_quarantine);
     float* d_tested = PF(P, date_tested); float* d_diag = PF(P, date_diagnosed); float* d_pos = PF(P, date_pos_test);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double prob = 0.0;
-        if (!diagnosed[i]) {                                           // interventions.py:973
-            const bool symp = symptomatic[i] != 0;
+    const int policy = tp.quar_policy;
+    const int64_t n_groups = (n + kAPT - 1) / kAPT;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = g * kAPT;
+        const uint32_t w_symp = load4b(symptomatic, i0, n, vec), w_diag = load4b(diagnosed, i0, n, vec), w_inf = load4b(infectious, i0, n, vec);
+        uint32_t w_quar = 0;
+        float dq[4] = {qnan, qnan, qnan, qnan}, deq[4] = {qnan, qnan, qnan, qnan}, ddiag[4];
+        if (policy == 0 || policy == 2) load4(d_quar, i0, n, vec, qnan, dq);
+        if (policy == 1 || policy == 2) load4(d_end_quar, i0, n, vec, qnan, deq);
+        if (policy == 3) w_quar = load4b(quarantined, i0, n, vec);
+        load4(d_diag, i0, n, vec, qnan, ddiag);
+#pragma unroll
+        for (int k = 0; k < kAPT; ++k) {
+            const int64_t i = i0 + k;
+            if (i >= n) break;
+            if (flag(w_diag, k)) continue;                             // diagnosed people do not test (interventions.py:973)
+            const bool symp = flag(w_symp, k);
             bool qt;                                                   // interventions.py:691-715 get_quar_inds
-            switch (tp.quar_policy) {
-                case 0:  qt = d_quar[i] == tf - 1.0f; break;
-                case 1:  qt = d_end_quar[i] == tf + 1.0f; break;
-                case 2:  qt = (d_quar[i] == tf - 1.0f) || (d_end_quar[i] == tf + 1.0f); break;
-                default: qt = quarantined[i] != 0; break;
+            switch (policy) {
+                case 0:  qt = dq[k] == tf - 1.0f; break;
+                case 1:  qt = deq[k] == tf + 1.0f; break;
+                case 2:  qt = (dq[k] == tf - 1.0f) || (deq[k] == tf + 1.0f); break;
+                default: qt = flag(w_quar, k); break;
             }
-            prob = qt ? (symp ? tp.symp_quar_prob : tp.asymp_quar_prob) : (symp ? tp.symp_prob : tp.asymp_prob);
+            const double prob = qt ? (symp ? tp.symp_quar_prob : tp.asymp_quar_prob) : (symp ? tp.symp_prob : tp.asymp_prob);
+            if (!(prob > 0.0)) continue;
+            if (!(keyed_uniform(seed, P_TEST, (uint32_t)tp.index, t, i, 0) < prob)) continue;
+            // People.test (people.py:589-617)
+            ++c;
+            tested[i] = 1;
+            d_tested[i] = tf;
+            if (!flag(w_inf, k)) continue;
+            if (!(keyed_uniform(seed, P_TEST_SENS, (uint32_t)tp.index, t, i, 0) < tp.sensitivity)) continue;
+            if (!is_nan(ddiag[k])) continue;
+            if (!(keyed_uniform(seed, P_TEST_LOSS, (uint32_t)tp.index, t, i, 0) < 1.0 - tp.loss_prob)) continue;
+            d_diag[i] = (float)(t + tp.test_delay);
+            d_pos[i] = tf;
         }
-        if (!(prob > 0.0)) continue;
-        if (!(keyed_uniform(seed, P_TEST, (uint32_t)tp.index, t, i, 0) < prob)) continue;
-        // People.test (people.py:589-617)
-        ++c;
-        tested[i] = 1;
-        d_tested[i] = tf;
-        if (!infectious[i]) continue;
-        if (!(keyed_uniform(seed, P_TEST_SENS, (uint32_t)tp.index, t, i, 0) < tp.sensitivity)) continue;
-        if (!is_nan(d_diag[i])) continue;
-        if (!(keyed_uniform(seed, P_TEST_LOSS, (uint32_t)tp.index, t, i, 0) < 1.0 - tp.loss_prob)) continue;
-        d_diag[i] = (float)(t + tp.test_delay);
-        d_pos[i] = tf;
     }
     int w = __reduce_add_sync(0xFFFFFFFFu, c);
     if (lane_id() == 0 && w) atomicAdd(&s_cnt, w);
@@ -58,70 +73,103 @@ __global__ void __launch_bounds__(kThreads) test_prob_kernel(PeoplePtrs P, const
 // ================================================================================================
 // contact_tracing
 // ================================================================================================
-__global__ void __launch_bounds__(kThreads) trace_select_kernel(PeoplePtrs P, int64_t n, int32_t t, int presumptive,
-        unsigned int* __restrict__ case_bits, unsigned int* __restrict__ n_cases) {
-    // one warp covers 32 consecutive agents = one bitmap word, written without atomics
+// Today's cases as a bitmap: each thread tests 4 agents (one 128-bit load), 8 lanes assemble a 32-bit word
+__global__ void __launch_bounds__(kThreads) trace_select_kernel(PeoplePtrs P, int64_t n, int32_t t, int presumptive, bool vec,
+        unsigned int* __restrict__ case_bits) {
     const float tf = (float)t;
     const float* d_diag = PF(P, date_diagnosed); const float* d_tested = PF(P, date_tested); const uint8_t* exposed = PB(P, exposed);
-    const int64_t n_words = (n + 31) / 32;
-    int found = 0;
-    for (int64_t wd = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / 32; wd < n_words; wd += ((int64_t)gridDim.x * blockDim.x) / 32) {
-        int64_t i = wd * 32 + lane_id();
-        bool is_case = false;
-        if (i < n) is_case = presumptive ? (d_tested[i] == tf && exposed[i] != 0) : (d_diag[i] == tf);
-        unsigned bits = __ballot_sync(0xFFFFFFFFu, is_case);
-        if (lane_id() == 0) { case_bits[wd] = bits; found += __popc(bits); }
+    const int64_t n_groups = (n + 3) / 4;
+    const int64_t n_groups_pad = (n_groups + 31) / 32 * 32;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups_pad; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = g * 4;
+        float d[4];
+        unsigned nib = 0;
+        if (!presumptive) {
+            if (vec && i0 + 4 <= n) { float4 v = *reinterpret_cast<const float4*>(d_diag + i0); d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w; }
+            else { for (int k = 0; k < 4; ++k) d[k] = (i0 + k < n) ? d_diag[i0 + k] : -1.0f; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) nib |= (unsigned)(i0 + k < n && d[k] == tf) << k;
+        } else {
+            for (int k = 0; k < 4; ++k) nib |= (unsigned)(i0 + k < n && d_tested[i0 + k] == tf && exposed[i0 + k] != 0) << k;
+        }
+        unsigned word = nib << (4 * (lane_id() & 7));
+        word |= __shfl_xor_sync(0xFFFFFFFFu, word, 1);
+        word |= __shfl_xor_sync(0xFFFFFFFFu, word, 2);
+        word |= __shfl_xor_sync(0xFFFFFFFFu, word, 4);
+        const int64_t widx = (i0 - (int64_t)(lane_id() & 7) * 4) / 32;
+        if ((lane_id() & 7) == 0 && widx * 32 < n) case_bits[widx] = word;
     }
-    if (found) atomicAdd(n_cases, (unsigned int)found);
 }
 
-struct TraceArgs {
-    double trace_prob;
+struct TraceTable {                      // the traced layers of one contact_tracing intervention, by value
+    const int32_t* p1[CVB_MAX_LAYERS];
+    const int32_t* p2[CVB_MAX_LAYERS];
+    int* quar_slot[CVB_MAX_LAYERS];      // ring slot of the day the contact is notified (t + trace_time)
+    double trace_prob[CVB_MAX_LAYERS];
+    int64_t n_edges[CVB_MAX_LAYERS];
+    int64_t tile_start[CVB_MAX_LAYERS + 1];
+    float notify_day[CVB_MAX_LAYERS];
+    int32_t layer_id[CVB_MAX_LAYERS];
+    int32_t n_entries;
+    float end_day;                       // t + quar_period (start + (quar_period - trace_time), interventions.py:1144)
     uint64_t seed;
-    int64_t n, n_edges;
-    int32_t t, layer, sub, notify_day;   // sub = (intervention index << 8) | layer
-    float end_day;
+    int64_t n, n_words;
+    int32_t t, index;
 };
 
-__device__ __forceinline__ void trace_notify(PeoplePtrs& P, const TraceArgs& ta, int c, int* __restrict__ quar_slot) {
-    if (!(keyed_uniform(ta.seed, P_TRACE, (uint32_t)ta.sub, ta.t, c, 0) < ta.trace_prob)) return;
+__device__ __forceinline__ void trace_notify(const PeoplePtrs& P, const TraceTable& T, int q, int c) {
+    const uint32_t sub = ((uint32_t)T.index << 8) | (uint32_t)T.layer_id[q];
+    if (!(keyed_uniform(T.seed, P_TRACE, sub, T.t, c, 0) < T.trace_prob[q])) return;     // binomial_filter, interventions.py:1116
     if (PB(P, dead)[c]) return;                                        // interventions.py:1139-1141
     PB(P, known_contact)[c] = 1;
     // date_known_contact = fmin(old, notify_day): for non-negative floats and NaN the unsigned bit
     // patterns order the same way (NaN = 0x7fc00000 is the largest), so atomicMin does fmin
-    atomicMin((unsigned int*)PF(P, date_known_contact) + c, (unsigned int)__float_as_int((float)ta.notify_day));
-    atomicMax(quar_slot + c, __float_as_int(ta.end_day));              // people.py:620-640 schedule_quarantine
+    atomicMin((unsigned int*)PF(P, date_known_contact) + c, (unsigned int)__float_as_int(T.notify_day[q]));
+    atomicMax(T.quar_slot[q] + c, __float_as_int(T.end_day));          // people.py:620-640 schedule_quarantine
 }
 
-__global__ void __launch_bounds__(kThreads) trace_edges_kernel(PeoplePtrs P, const __grid_constant__ TraceArgs ta,
-        const int32_t* __restrict__ p1, const int32_t* __restrict__ p2, const unsigned int* __restrict__ case_bits,
-        const unsigned int* __restrict__ n_cases, int* __restrict__ quar_slot) {
-    if (*n_cases == 0) return;                                         // nobody to trace today
-    const int64_t n_tiles = (ta.n_edges + kTileEdges - 1) / kTileEdges;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t e0 = tile * kTileEdges + (int64_t)threadIdx.x * kEdgesPerThread;
-        if (e0 >= ta.n_edges) continue;
+// One streaming pass over (p1, p2) of every traced layer; the case bitmap is staged in shared memory when it fits
+template <bool SMEM_BITS, int THREADS>
+__global__ void __launch_bounds__(THREADS) trace_edges_kernel(PeoplePtrs P, const __grid_constant__ TraceTable T,
+                                                              const unsigned int* __restrict__ case_bits) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kTile = THREADS * kEdgesPerThread;
+    const unsigned int* bits = case_bits;
+    if (SMEM_BITS) {
+        unsigned int* s_bits = reinterpret_cast<unsigned int*>(smem_raw);
+        unsigned any = 0;
+        for (int64_t wd = threadIdx.x; wd < T.n_words; wd += THREADS) { const unsigned v = case_bits[wd]; s_bits[wd] = v; any |= v; }
+        if (!__syncthreads_or((int)(any != 0))) return;              // nobody was diagnosed today
+        bits = s_bits;
+    }
+    const int64_t total_tiles = T.tile_start[T.n_entries];
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int q = 0;
+#pragma unroll
+        for (int j = 1; j < CVB_MAX_LAYERS; ++j) q += (j < T.n_entries && tile >= T.tile_start[j]);
+        const int64_t ne = T.n_edges[q];
+        const int64_t e0 = (tile - T.tile_start[q]) * kTile + (int64_t)threadIdx.x * kEdgesPerThread;
+        if (e0 >= ne) continue;
+        const int32_t* __restrict__ p1 = T.p1[q];
+        const int32_t* __restrict__ p2 = T.p2[q];
         int a[4], b[4], cnt;
-        if (e0 + 4 <= ta.n_edges) {
-            int4 va = ld_stream(reinterpret_cast<const int4*>(p1 + e0)), vb = ld_stream(reinterpret_cast<const int4*>(p2 + e0));
+        if (e0 + 4 <= ne) {
+            const int4 va = ld_stream(reinterpret_cast<const int4*>(p1 + e0)), vb = ld_stream(reinterpret_cast<const int4*>(p2 + e0));
             a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w; b[0] = vb.x; b[1] = vb.y; b[2] = vb.z; b[3] = vb.w; cnt = 4;
         } else {
-            cnt = (int)(ta.n_edges - e0);
+            cnt = (int)(ne - e0);
+#pragma unroll
             for (int k = 0; k < 4; ++k) { a[k] = k < cnt ? p1[e0 + k] : 0; b[k] = k < cnt ? p2[e0 + k] : 0; }
         }
-        unsigned wa[4], wb[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { wa[k] = __ldg(case_bits + (a[k] >> 5)); wb[k] = __ldg(case_bits + (b[k] >> 5)); }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             if (k >= cnt) break;
-            if ((wa[k] >> (a[k] & 31)) & 1u) trace_notify(P, ta, b[k], quar_slot);
-            if ((wb[k] >> (b[k] & 31)) & 1u) trace_notify(P, ta, a[k], quar_slot);
+            const unsigned wa = bits[a[k] >> 5], wb = bits[b[k] >> 5];
+            if ((wa >> (a[k] & 31)) & 1u) trace_notify(P, T, q, b[k]);
+            if ((wb >> (b[k] & 31)) & 1u) trace_notify(P, T, q, a[k]);
         }
     }
 }
-
-__global__ void reset_cases_kernel(unsigned int* n_cases) { *n_cases = 0; }
 
 // ================================================================================================
 // vaccinate_prob
@@ -198,7 +246,10 @@ extern "C" {
 int cvb_test_prob(cvb_sim* s, int32_t t, const cvb_test_prob_pars* tp, cvb_stream st) {
     CVB_REQUIRE(s && tp && s->res.counters, "cvb_test_prob: handle not ready");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_test_prob: day %d outside [0,%d)", t, s->npts);
-    test_prob_kernel<<<grid_for(s->n), kThreads, 0, (cudaStream_t)st>>>(s->people, *tp, s->seed, s->n, t, s->res.counters);
+    uintptr_t al = 0;
+    for (int f = 0; f < CVB_N_FIELDS; ++f) al |= (uintptr_t)s->people.f[f];
+    test_prob_kernel<<<grid_for((s->n + kAPT - 1) / kAPT, kThreads, 148 * 8), kThreads, 0, (cudaStream_t)st>>>(
+        s->people, *tp, s->seed, s->n, t, (al & 15) == 0 && s->n % 4 == 0, s->res.counters);
     CVB_LAUNCH_CHECK();
     return 0;
 }
@@ -207,27 +258,52 @@ int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_str
     cudaStream_t st = (cudaStream_t)st_;
     CVB_REQUIRE(s && tr && s->pars_set, "cvb_contact_tracing: handle not ready");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_contact_tracing: day %d outside [0,%d)", t, s->npts);
-    reset_cases_kernel<<<1, 1, 0, st>>>(s->n_cases);
+    uintptr_t al = (uintptr_t)s->people.f[CVB_F_date_diagnosed];
+    trace_select_kernel<<<grid_for((s->n + 3) / 4, kThreads, 148 * 8), kThreads, 0, st>>>(s->people, s->n, t, tr->presumptive,
+                                                                                    (al & 15) == 0, s->case_bits);
     CVB_LAUNCH_CHECK();
-    trace_select_kernel<<<grid_for(s->n), kThreads, 0, st>>>(s->people, s->n, t, tr->presumptive, s->case_bits, s->n_cases);
-    CVB_LAUNCH_CHECK();
+    TraceTable T;
+    memset(&T, 0, sizeof(T));
+    T.seed = s->seed; T.n = s->n; T.n_words = (s->n + 31) / 32; T.t = t; T.index = tr->index;
+    T.end_day = (float)(t + tr->quar_period);
+    const size_t bitmap_bytes = (size_t)T.n_words * sizeof(unsigned int);
+    const bool smem_bits = bitmap_bytes <= 200 * 1024;
+    const int threads = smem_bits ? 1024 : 256;
+    const int tile_edges = threads * kEdgesPerThread;
+    int64_t acc = 0;
+    int q = 0;
     for (int l = 0; l < s->pars.n_layers; ++l) {
         if (!(tr->trace_prob[l] > 0.0) || s->layers[l].n_edges == 0) continue;
         CVB_REQUIRE(tr->trace_time[l] >= 0 && tr->trace_time[l] < s->quar_horizon,
                     "cvb_contact_tracing: trace_time %d needs cvb_set_quar_horizon(%d)", tr->trace_time[l], tr->trace_time[l] + 1);
-        TraceArgs ta;
-        ta.trace_prob = tr->trace_prob[l];
-        ta.seed = s->seed; ta.n = s->n; ta.n_edges = s->layers[l].n_edges;
-        ta.t = t; ta.layer = l; ta.sub = (tr->index << 8) | l;
-        ta.notify_day = t + tr->trace_time[l];
-        ta.end_day = (float)(t + tr->quar_period);                    // start + (quar_period - trace_time), interventions.py:1144
-        int slot = ta.notify_day % s->quar_horizon;
-        int64_t n_tiles = (ta.n_edges + kTileEdges - 1) / kTileEdges;
-        int grid = (int)(n_tiles < 148 * 8 ? n_tiles : 148 * 8);
-        trace_edges_kernel<<<grid, kThreads, 0, st>>>(s->people, ta, s->layers[l].p1, s->layers[l].p2, s->case_bits, s->n_cases,
-                                                      (int*)(s->quar_ring + (int64_t)slot * s->n));
-        CVB_LAUNCH_CHECK();
+        const int notify = t + tr->trace_time[l];
+        T.p1[q] = s->layers[l].p1; T.p2[q] = s->layers[l].p2; T.n_edges[q] = s->layers[l].n_edges;
+        T.quar_slot[q] = (int*)(s->quar_ring + (int64_t)(notify % s->quar_horizon) * s->n);
+        T.trace_prob[q] = tr->trace_prob[l];
+        T.notify_day[q] = (float)notify;
+        T.layer_id[q] = l;
+        T.tile_start[q] = acc;
+        acc += (T.n_edges[q] + tile_edges - 1) / tile_edges;
+        ++q;
     }
+    T.n_entries = q;
+    for (int j = q; j <= CVB_MAX_LAYERS; ++j) T.tile_start[j] = acc;
+    if (acc == 0) return 0;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
+    if (smem_bits) {
+        static bool configured = false;
+        if (!configured) {
+            CVB_CHECK(cudaFuncSetAttribute(trace_edges_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            configured = true;
+        }
+        const int grid = (int)(acc < n_sm ? acc : n_sm);
+        trace_edges_kernel<true, 1024><<<grid, 1024, bitmap_bytes, st>>>(s->people, T, s->case_bits);
+    } else {
+        const int grid = (int)(acc < (int64_t)n_sm * 8 ? acc : (int64_t)n_sm * 8);
+        trace_edges_kernel<false, 256><<<grid, 256, 0, st>>>(s->people, T, s->case_bits);
+    }
+    CVB_LAUNCH_CHECK();
     return 0;
 }
 
@@ -252,8 +328,7 @@ int cvb_layer_regenerate(cvb_sim* s, int32_t layer, int32_t t, cvb_stream st) {
 int cvb_step_day(cvb_sim* s, int32_t t, cvb_stream st) {
     int rc;
     if ((rc = cvb_update_states_pre(s, t, st))) return rc;
-    if ((rc = cvb_update_states_post(s, t, st))) return rc;
-    if ((rc = cvb_prepare_transmission(s, t, st))) return rc;
+    if ((rc = cvb_post_and_prepare(s, t, st))) return rc;
     if ((rc = cvb_edge_pass(s, t, st))) return rc;
     if ((rc = cvb_infect_winners(s, t, st))) return rc;
     return cvb_update_nab_count(s, t, st);

@@ -465,8 +465,7 @@ class Sim:
         for iv in pars['interventions']:
             iv(self)
         self._push_pars()
-        call('cvb_update_states_post', h, t, st)
-        call('cvb_prepare_transmission', h, t, st)
+        call('cvb_post_and_prepare', h, t, st)
         call('cvb_edge_pass', h, t, st)
         call('cvb_infect_winners', h, t, st)
         call('cvb_update_nab_count', h, t, st)

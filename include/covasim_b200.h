@@ -143,6 +143,8 @@ int cvb_set_nab_kin(cvb_sim* s, const double* host_kin, int64_t n);
 int cvb_update_states_post(cvb_sim* s, int32_t t, cvb_stream st);
 /* sim.py:602-643: viral load + per-layer {rel_trans, rel_sus} records for the fused edge pass */
 int cvb_prepare_transmission(cvb_sim* s, int32_t t, cvb_stream st);
+/* update_states_post and prepare_transmission as ONE pass over the agents (what Sim.step uses) */
+int cvb_post_and_prepare(cvb_sim* s, int32_t t, cvb_stream st);
 /* sim.py:622-649 native-RNG form: ONE pass over every layer's edges, both directions, all variants;
  * per-edge Philox4x32-10 uniforms keyed (seed, day, layer, edge); winners by atomicMin of
  * (variant, layer, direction, edge) per target == the reference's first-occurrence rule (people.py:465-467) */

@@ -82,6 +82,7 @@ PROTOTYPES = dict(
     cvb_set_quar_horizon=[_P, _i32],
     cvb_bind_field=[_P, _i32, _P],
     cvb_bind_layer=[_P, _i32, _P, _P, _P, _i64],
+    cvb_bind_adjacency=[_P, _P, _P, _i64, C.c_uint32],
     cvb_bind_results=[_P, _P, _P, _P],
     cvb_bind_log=[_P, _P, _P, _P, _P, _P, _i64, _P],
     cvb_compute_viral_load=[_i32, _P, _P, _P, _f32, _f32, _f32, _P, _i64, _P],

@@ -107,6 +107,8 @@ class Layer:
         old = self._cols[key]
         if len(value) == len(old):
             old.copy_(torch.as_tensor(value).to(device=old.device, dtype=old.dtype))      # in place: the bound pointer stays valid
+            if self._sim is not None:
+                self._sim._adj_dirty = True
         else:
             self._set(key, value)
             self._rebind()
@@ -116,6 +118,8 @@ class Layer:
         self._rebind()
 
     def _rebind(self):
+        if self._sim is not None:
+            self._sim._adj_dirty = True             # the adjacency index no longer matches this edge list
         if self._sim is not None and self._sim._handle is not None:
             c = self._cols
             _capi.call('cvb_bind_layer', self._sim._handle, self._index, c['p1'].data_ptr(), c['p2'].data_ptr(), c['beta'].data_ptr(), len(self))

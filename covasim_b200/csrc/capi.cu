@@ -116,6 +116,12 @@ int cvb_create(cvb_sim** out, int64_t n_agents, int32_t n_variants, int32_t npts
         if ((rc = check_cuda(cudaMemset(s->case_bits, 0, (size_t)words * sizeof(unsigned int)), "case_bits"))) break;
         if ((rc = check_cuda(cudaMalloc((void**)&s->inf_bits, (size_t)(words + 4) * sizeof(unsigned int)), "inf_bits"))) break;
         if ((rc = check_cuda(cudaMemset(s->inf_bits, 0, (size_t)(words + 4) * sizeof(unsigned int)), "inf_bits"))) break;
+        if ((rc = check_cuda(cudaMalloc((void**)&s->trans_list, (size_t)n_agents * sizeof(int32_t)), "trans_list"))) break;
+        if ((rc = check_cuda(cudaMalloc((void**)&s->case_list, (size_t)n_agents * sizeof(int32_t)), "case_list"))) break;
+        if ((rc = check_cuda(cudaMalloc((void**)&s->n_trans, 64), "n_trans"))) break;
+        if ((rc = check_cuda(cudaMemset(s->n_trans, 0, 64), "n_trans"))) break;
+        if ((rc = check_cuda(cudaMalloc((void**)&s->n_case_list, 64), "n_case_list"))) break;
+        if ((rc = check_cuda(cudaMemset(s->n_case_list, 0, 64), "n_case_list"))) break;
         if ((rc = check_cuda(cudaMalloc((void**)&s->n_cases, 64), "n_cases"))) break;
         if ((rc = check_cuda(cudaMemset(s->n_cases, 0, 64), "n_cases"))) break;
         if ((rc = check_cuda(cudaMalloc((void**)&s->dev_scalars, 16 * sizeof(unsigned long long)), "dev_scalars"))) break;
@@ -131,6 +137,7 @@ int cvb_create(cvb_sim** out, int64_t n_agents, int32_t n_variants, int32_t npts
 int cvb_destroy(cvb_sim* s) {
     if (!s) return 0;
     cudaFree(s->cand); cudaFree(s->n_cand); cudaFree(s->infect_key); cudaFree(s->beds); cudaFree(s->quar_ring); cudaFree(s->case_bits); cudaFree(s->inf_bits);
+    cudaFree(s->trans_list); cudaFree(s->case_list); cudaFree(s->n_trans); cudaFree(s->n_case_list);
     cudaFree(s->n_cases); cudaFree(s->dev_scalars); cudaFree(s->rec.ts); cudaFree(s->rec.sus_extra); cudaFree(s->rec.ivar);
     cudaFree(s->nab_kin); cudaFree(s->tile_cnt); cudaFree(s->hit_mask); cudaFree(s->flag_tmp); cudaFree(s->partial);
     if (s->host_scalars) cudaFreeHost(s->host_scalars);
@@ -195,6 +202,18 @@ int cvb_bind_layer(cvb_sim* s, int32_t layer, int32_t* p1, int32_t* p2, float* b
     s->layers[layer].p2 = p2;
     s->layers[layer].beta = beta;
     s->layers[layer].n_edges = n_edges;
+    return 0;
+}
+
+int cvb_bind_adjacency(cvb_sim* s, const int64_t* adj_ptr, const void* adj, int64_t n_entries, uint32_t layer_mask) {
+    CVB_REQUIRE(s, "cvb_bind_adjacency: NULL handle");
+    if (layer_mask == 0 || n_entries == 0) {             // unbind: every layer goes through the dense passes
+        s->adj_ptr = nullptr; s->adj = nullptr; s->adj_entries = 0; s->adj_layer_mask = 0;
+        return 0;
+    }
+    CVB_REQUIRE(adj_ptr && adj, "cvb_bind_adjacency: NULL array");
+    CVB_REQUIRE(((uintptr_t)adj & 15) == 0, "cvb_bind_adjacency: entries must be 16-byte aligned");
+    s->adj_ptr = (const long long*)adj_ptr; s->adj = (const uint4*)adj; s->adj_entries = n_entries; s->adj_layer_mask = layer_mask;
     return 0;
 }
 

@@ -32,8 +32,9 @@ struct LayerPtrs {
 
 struct LayerTable {                            // all layers, by value, for the fused edge pass
     LayerPtrs l[CVB_MAX_LAYERS];
-    int64_t tile_start[CVB_MAX_LAYERS + 1];    // prefix sum of ceil(n_edges / kTileEdges)
-    int32_t n_layers;
+    int64_t tile_start[CVB_MAX_LAYERS + 1];    // prefix sum of ceil(n_edges / tile size) over the table's entries
+    int32_t layer_id[CVB_MAX_LAYERS];          // the layer each entry is (entries may skip layers)
+    int32_t n_layers;                          // number of entries
 };
 
 struct ResultPtrs {
@@ -75,6 +76,10 @@ struct cvb_sim {
     float* quar_ring; int32_t quar_horizon;         // [quar_horizon][N] pending quarantine end days, -1 = none
     unsigned int* case_bits; unsigned int* n_cases; // contact tracing: bitmap of today's cases
     unsigned int* inf_bits;                         // [ceil(N/32)] agents that can transmit today (written by prepare_transmission)
+    int32_t* trans_list; unsigned int* n_trans;     // the same set as a compact (unordered) list
+    int32_t* case_list; unsigned int* n_case_list;  // contact tracing: today's cases as a compact list
+    // bidirectional adjacency (CSR over agents) of the static layers, bound by the host (cvb_bind_adjacency)
+    const long long* adj_ptr; const uint4* adj; int64_t adj_entries; uint32_t adj_layer_mask;
     // scan / compaction workspace
     unsigned int* tile_cnt; int64_t tile_cnt_cap;   // per-tile counts (and their exclusive scan, in place)
     uint8_t* hit_mask; int64_t hit_mask_cap;

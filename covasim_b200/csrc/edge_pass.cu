@@ -107,11 +107,12 @@ __global__ void __launch_bounds__(THREADS) edge_pass_kernel(const __grid_constan
 
     const int64_t total_tiles = L.tile_start[L.n_layers];
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int l = 0;
+        int q_ = 0;
 #pragma unroll
-        for (int q = 1; q < CVB_MAX_LAYERS; ++q) l += (q < L.n_layers && tile >= L.tile_start[q]);
-        const LayerPtrs& lay = L.l[l];
-        const int64_t e0 = (tile - L.tile_start[l]) * kTile + (int64_t)threadIdx.x * kEdgesPerThread;
+        for (int q = 1; q < CVB_MAX_LAYERS; ++q) q_ += (q < L.n_layers && tile >= L.tile_start[q]);
+        const LayerPtrs& lay = L.l[q_];
+        const int l = L.layer_id[q_];
+        const int64_t e0 = (tile - L.tile_start[q_]) * kTile + (int64_t)threadIdx.x * kEdgesPerThread;
         int a[4], b[4];
         float w[4];
         int cnt = 0;
@@ -171,7 +172,48 @@ __global__ void __launch_bounds__(THREADS) edge_pass_kernel(const __grid_constan
     }
 }
 
-int build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges);
+// ---- sparse form: only the edges of today's transmitters, through the bidirectional adjacency ----------
+// One warp per transmitter; lanes stride over its adjacency range (all static layers, both directions:
+// ~36 entries of 16 bytes per agent in a hybrid population, contiguous).  Same probability chain, same
+// Philox key (layer, edge) and same winner key as the dense pass, so results are identical.
+template <bool MULTI>
+__global__ void __launch_bounds__(kThreads) edge_pass_sparse_kernel(TransRecords rec, const __grid_constant__ EdgeParams ep,
+        const long long* __restrict__ adj_ptr, const uint4* __restrict__ adj, const int32_t* __restrict__ trans_list,
+        const unsigned int* __restrict__ n_trans_ptr, unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand,
+        unsigned int* __restrict__ n_cand) {
+    const unsigned int n_trans = *n_trans_ptr;
+    const int64_t n = ep.n;
+    const int lane = lane_id();
+    const unsigned int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int ti = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ti < n_trans; ti += warps_total) {
+        const int i = trans_list[ti];
+        const long long beg = adj_ptr[i], end = adj_ptr[i + 1];
+        const int vi = MULTI ? (int)rec.ivar[i] : 0;
+        const float beta_v = ep.beta[vi];
+        for (long long off = beg + lane; off < end; off += 32) {
+            const uint4 en = __ldg(adj + off);
+            const int j = (int)en.x;
+            const int l = (int)(en.z >> 1);
+            const int dir = (int)(en.z & 1u);
+            const float t_i = __ldg(&rec.ts[(int64_t)l * n + i].x);
+            if (t_i == 0.0f) continue;                        // cannot transmit on this layer
+            float s_j;
+            if (MULTI && vi > 0) s_j = __ldg(rec.sus_extra + ((int64_t)l * (ep.nv - 1) + (vi - 1)) * n + j);
+            else s_j = __ldg(&rec.ts[(int64_t)l * n + j].y);
+            const float p = edge_prob(beta_v, __uint_as_float(en.w), t_i, s_j);
+            if (p != 0.0f) {
+                const int64_t e = (int64_t)en.y;
+                const u32x4 r = keyed_words(ep.seed, P_EDGE, (uint32_t)l, ep.t, e, 0);
+                const double u = dir == 0 ? u53(r.x, r.y) : u53(r.z, r.w);
+                if (u < (double)p)
+                    record_hit(infect_key, cand, n_cand, j, ((unsigned long long)vi << 56) | ((unsigned long long)l << 48) |
+                                                            ((unsigned long long)dir << 40) | (unsigned long long)e);
+            }
+        }
+    }
+}
+
+int build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges, uint32_t skip_mask);
 
 template <bool MULTI, bool SMEM_BITS, int THREADS>
 static int launch_edge_pass(cvb_sim* s, const LayerTable& L, const EdgeParams& ep, size_t smem, int grid, cudaStream_t st) {
@@ -190,21 +232,22 @@ static int launch_edge_pass(cvb_sim* s, const LayerTable& L, const EdgeParams& e
 
 using namespace cvb;
 
-int cvb::build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges) {
-    L.n_layers = s->pars.n_layers;
+int cvb::build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges, uint32_t skip_mask) {
     int64_t acc = 0;
-    for (int l = 0; l < CVB_MAX_LAYERS; ++l) {
-        L.tile_start[l] = acc;
-        if (l < L.n_layers) {
-            L.l[l] = s->layers[l];
-            CVB_REQUIRE(L.l[l].n_edges == 0 || L.l[l].p1, "layer %d is not bound (cvb_bind_layer)", l);
-            CVB_REQUIRE(L.l[l].n_edges < (1ll << 40), "layer %d has too many edges for the 40-bit edge field", l);
-            acc += (L.l[l].n_edges + tile_edges - 1) / tile_edges;
-        } else {
-            L.l[l] = LayerPtrs{nullptr, nullptr, nullptr, 0};
-        }
+    int q = 0;
+    for (int l = 0; l < s->pars.n_layers; ++l) {
+        if (skip_mask & (1u << l)) continue;
+        L.l[q] = s->layers[l];
+        L.layer_id[q] = l;
+        CVB_REQUIRE(L.l[q].n_edges == 0 || L.l[q].p1, "layer %d is not bound (cvb_bind_layer)", l);
+        CVB_REQUIRE(L.l[q].n_edges < (1ll << 40), "layer %d has too many edges for the 40-bit edge field", l);
+        L.tile_start[q] = acc;
+        acc += (L.l[q].n_edges + tile_edges - 1) / tile_edges;
+        ++q;
     }
-    for (int l = L.n_layers; l <= CVB_MAX_LAYERS; ++l) L.tile_start[l] = acc;
+    L.n_layers = q;
+    for (int j = q; j < CVB_MAX_LAYERS; ++j) { L.l[j] = LayerPtrs{nullptr, nullptr, nullptr, 0}; L.layer_id[j] = 0; }
+    for (int j = q; j <= CVB_MAX_LAYERS; ++j) L.tile_start[j] = acc;
     return 0;
 }
 
@@ -217,7 +260,22 @@ extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
     ep.seed = s->seed; ep.n = s->n; ep.t = t; ep.nv = s->nv;
     ep.n_words = (s->n + 31) / 32;
     const bool multi = s->nv > 1;
-    // shared-memory budget: per-warp candidate queue (18 B x 160 entries) + the transmit bitmap
+    uint32_t skip_mask = 0;
+    if (s->adj && s->adj_layer_mask) {
+        // static layers: visit only the adjacency ranges of today's transmitters (a device-side count: the grid is
+        // sized for a large outbreak and surplus warps exit after one load)
+        skip_mask = s->adj_layer_mask;
+        const int grid = 148 * 8;
+        if (multi) edge_pass_sparse_kernel<true><<<grid, kThreads, 0, st>>>(s->rec, ep, s->adj_ptr, s->adj, s->trans_list, s->n_trans,
+                                                                          s->infect_key, s->cand, s->n_cand);
+        else edge_pass_sparse_kernel<false><<<grid, kThreads, 0, st>>>(s->rec, ep, s->adj_ptr, s->adj, s->trans_list, s->n_trans,
+                                                                      s->infect_key, s->cand, s->n_cand);
+        CVB_LAUNCH_CHECK();
+        bool rest = false;
+        for (int l = 0; l < s->pars.n_layers; ++l) rest |= !(skip_mask & (1u << l)) && s->layers[l].n_edges > 0;
+        if (!rest) return 0;
+    }
+    // dense streaming pass over the remaining (dynamic) layers.  Shared-memory budget: per-warp candidate queue (18 B x 160 entries) + the transmit bitmap
     const size_t bitmap_bytes = (size_t)ep.n_words * sizeof(unsigned int);
     const size_t queue_1024 = (size_t)32 * kQueueCap * (sizeof(uint4) + sizeof(unsigned short));
     const size_t queue_512 = queue_1024 / 2, queue_256 = queue_1024 / 4;
@@ -227,7 +285,7 @@ extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
     if (bitmap_bytes + queue_1024 <= limit) {
         // one persistent 1024-thread CTA per SM, bitmap in shared memory
-        if (build_layer_table(s, L, 1024 * kEdgesPerThread)) return 1;
+        if (build_layer_table(s, L, 1024 * kEdgesPerThread, skip_mask)) return 1;
         const int64_t tiles = L.tile_start[L.n_layers];
         if (tiles == 0) return 0;
         const int grid = (int)(tiles < n_sm ? tiles : n_sm);
@@ -235,7 +293,7 @@ extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
                      : launch_edge_pass<false, true, 1024>(s, L, ep, bitmap_bytes + queue_1024, grid, st);
     }
     if (bitmap_bytes + queue_512 <= limit) {
-        if (build_layer_table(s, L, 512 * kEdgesPerThread)) return 1;
+        if (build_layer_table(s, L, 512 * kEdgesPerThread, skip_mask)) return 1;
         const int64_t tiles = L.tile_start[L.n_layers];
         if (tiles == 0) return 0;
         const int grid = (int)(tiles < n_sm ? tiles : n_sm);
@@ -243,7 +301,7 @@ extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
                      : launch_edge_pass<false, true, 512>(s, L, ep, bitmap_bytes + queue_512, grid, st);
     }
     // large populations: bitmap stays in global memory (L1/L2-cached bit tests), 8 CTAs of 256 threads per SM
-    if (build_layer_table(s, L, 256 * kEdgesPerThread)) return 1;
+    if (build_layer_table(s, L, 256 * kEdgesPerThread, skip_mask)) return 1;
     const int64_t tiles = L.tile_start[L.n_layers];
     if (tiles == 0) return 0;
     const int grid = (int)(tiles < (int64_t)n_sm * 8 ? tiles : (int64_t)n_sm * 8);

@@ -8,7 +8,7 @@
 
 namespace cvb {
 
-int build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges);
+int build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges, uint32_t skip_mask);
 
 enum { INF_INFECTIONS = 0, INF_REINFECTIONS, INF_NK };
 
@@ -215,7 +215,7 @@ static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t lis
                          int64_t max_items, cudaStream_t st) {
     CVB_REQUIRE(s->log.count, "infect: infection log is not bound (cvb_bind_log)");
     LayerTable L;
-    if (build_layer_table(s, L, kTileEdges)) return 1;
+    if (build_layer_table(s, L, kTileEdges, 0)) return 1;          // no layer skipped: entry index == layer id
     InfectArgs ia;
     ia.seed = s->seed; ia.n = s->n; ia.t = t; ia.count_flows = count_flows; ia.list_layer_code = list_layer_code;
     ia.hosp_max = hosp_max; ia.icu_max = icu_max;

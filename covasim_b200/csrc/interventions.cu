@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(kThreads) test_prob_kernel(PeoplePtrs P, const
 // ================================================================================================
 // Today's cases as a bitmap: each thread tests 4 agents (one 128-bit load), 8 lanes assemble a 32-bit word
 __global__ void __launch_bounds__(kThreads) trace_select_kernel(PeoplePtrs P, int64_t n, int32_t t, int presumptive, bool vec,
-        unsigned int* __restrict__ case_bits) {
+        unsigned int* __restrict__ case_bits, int32_t* __restrict__ case_list, unsigned int* __restrict__ n_case_list) {
     const float tf = (float)t;
     const float* d_diag = PF(P, date_diagnosed); const float* d_tested = PF(P, date_tested); const uint8_t* exposed = PB(P, exposed);
     const int64_t n_groups = (n + 3) / 4;
@@ -98,6 +98,11 @@ __global__ void __launch_bounds__(kThreads) trace_select_kernel(PeoplePtrs P, in
         word |= __shfl_xor_sync(0xFFFFFFFFu, word, 4);
         const int64_t widx = (i0 - (int64_t)(lane_id() & 7) * 4) / 32;
         if ((lane_id() & 7) == 0 && widx * 32 < n) case_bits[widx] = word;
+        if (nib) {                                                  // and as a compact list for the adjacency form
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (nib & (1u << k)) case_list[atomicAdd(n_case_list, 1u)] = (int32_t)(i0 + k);
+        }
     }
 }
 
@@ -110,6 +115,7 @@ struct TraceTable {                      // the traced layers of one contact_tra
     int64_t tile_start[CVB_MAX_LAYERS + 1];
     float notify_day[CVB_MAX_LAYERS];
     int32_t layer_id[CVB_MAX_LAYERS];
+    int32_t entry_of_layer[CVB_MAX_LAYERS];   // inverse of layer_id (-1: layer not traced)
     int32_t n_entries;
     float end_day;                       // t + quar_period (start + (quar_period - trace_time), interventions.py:1144)
     uint64_t seed;
@@ -126,6 +132,27 @@ __device__ __forceinline__ void trace_notify(const PeoplePtrs& P, const TraceTab
     // patterns order the same way (NaN = 0x7fc00000 is the largest), so atomicMin does fmin
     atomicMin((unsigned int*)PF(P, date_known_contact) + c, (unsigned int)__float_as_int(T.notify_day[q]));
     atomicMax(T.quar_slot[q] + c, __float_as_int(T.end_day));          // people.py:620-640 schedule_quarantine
+}
+
+// Adjacency form: one warp per case walks the case's own edges (static layers, both directions)
+__global__ void __launch_bounds__(kThreads) trace_sparse_kernel(PeoplePtrs P, const __grid_constant__ TraceTable T,
+        const long long* __restrict__ adj_ptr, const uint4* __restrict__ adj, const int32_t* __restrict__ case_list,
+        const unsigned int* __restrict__ n_case_ptr, uint32_t layer_mask) {
+    const unsigned int n_cases = *n_case_ptr;
+    const int lane = lane_id();
+    const unsigned int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < n_cases; ci += warps_total) {
+        const int i = case_list[ci];
+        const long long beg = adj_ptr[i], end = adj_ptr[i + 1];
+        for (long long off = beg + lane; off < end; off += 32) {
+            const uint4 en = __ldg(adj + off);
+            const int l = (int)(en.z >> 1);
+            if (!((layer_mask >> l) & 1u)) continue;
+            const int q = T.entry_of_layer[l];
+            if (q < 0) continue;                                       // layer not traced
+            trace_notify(P, T, q, (int)en.x);
+        }
+    }
 }
 
 // One streaming pass over (p1, p2) of every traced layer; the case bitmap is staged in shared memory when it fits
@@ -259,9 +286,11 @@ int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_str
     CVB_REQUIRE(s && tr && s->pars_set, "cvb_contact_tracing: handle not ready");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_contact_tracing: day %d outside [0,%d)", t, s->npts);
     uintptr_t al = (uintptr_t)s->people.f[CVB_F_date_diagnosed];
+    CVB_CHECK(cudaMemsetAsync(s->n_case_list, 0, sizeof(unsigned int), st));
     trace_select_kernel<<<grid_for((s->n + 3) / 4, kThreads, 148 * 8), kThreads, 0, st>>>(s->people, s->n, t, tr->presumptive,
-                                                                                    (al & 15) == 0, s->case_bits);
+                                                                                    (al & 15) == 0, s->case_bits, s->case_list, s->n_case_list);
     CVB_LAUNCH_CHECK();
+    const uint32_t adj_mask = (s->adj && s->adj_layer_mask) ? s->adj_layer_mask : 0u;
     TraceTable T;
     memset(&T, 0, sizeof(T));
     T.seed = s->seed; T.n = s->n; T.n_words = (s->n + 31) / 32; T.t = t; T.index = tr->index;
@@ -270,24 +299,35 @@ int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_str
     const bool smem_bits = bitmap_bytes <= 200 * 1024;
     const int threads = smem_bits ? 1024 : 256;
     const int tile_edges = threads * kEdgesPerThread;
+    // every traced layer gets a table entry (probability, notification day, ring slot); only the layers that are
+    // NOT covered by the adjacency contribute tiles to the dense streaming pass
     int64_t acc = 0;
     int q = 0;
+    bool any_sparse = false;
+    for (int l = 0; l < CVB_MAX_LAYERS; ++l) T.entry_of_layer[l] = -1;
     for (int l = 0; l < s->pars.n_layers; ++l) {
         if (!(tr->trace_prob[l] > 0.0) || s->layers[l].n_edges == 0) continue;
         CVB_REQUIRE(tr->trace_time[l] >= 0 && tr->trace_time[l] < s->quar_horizon,
                     "cvb_contact_tracing: trace_time %d needs cvb_set_quar_horizon(%d)", tr->trace_time[l], tr->trace_time[l] + 1);
         const int notify = t + tr->trace_time[l];
-        T.p1[q] = s->layers[l].p1; T.p2[q] = s->layers[l].p2; T.n_edges[q] = s->layers[l].n_edges;
+        const bool sparse = (adj_mask >> l) & 1u;
+        any_sparse |= sparse;
+        T.p1[q] = s->layers[l].p1; T.p2[q] = s->layers[l].p2; T.n_edges[q] = sparse ? 0 : s->layers[l].n_edges;
         T.quar_slot[q] = (int*)(s->quar_ring + (int64_t)(notify % s->quar_horizon) * s->n);
         T.trace_prob[q] = tr->trace_prob[l];
         T.notify_day[q] = (float)notify;
         T.layer_id[q] = l;
+        T.entry_of_layer[l] = q;
         T.tile_start[q] = acc;
         acc += (T.n_edges[q] + tile_edges - 1) / tile_edges;
         ++q;
     }
     T.n_entries = q;
     for (int j = q; j <= CVB_MAX_LAYERS; ++j) T.tile_start[j] = acc;
+    if (any_sparse) {
+        trace_sparse_kernel<<<148 * 2, kThreads, 0, st>>>(s->people, T, s->adj_ptr, s->adj, s->case_list, s->n_case_list, adj_mask);
+        CVB_LAUNCH_CHECK();
+    }
     if (acc == 0) return 0;
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);

@@ -186,7 +186,7 @@ enum { POST_DIAGNOSES = 0, POST_QUARANTINED, POST_ISOLATED, POST_NK };
 template <bool DO_POST, bool DO_PREP>
 __global__ void __launch_bounds__(kThreads) post_prepare_kernel(PeoplePtrs P, const __grid_constant__ cvb_pars pars, int64_t n, int32_t t, bool vec,
         float* __restrict__ quar_slot, unsigned long long* __restrict__ counters, TransRecords rec, unsigned int* __restrict__ inf_bits,
-        unsigned int* __restrict__ n_cand) {
+        int32_t* __restrict__ trans_list, unsigned int* __restrict__ n_trans, unsigned int* __restrict__ n_cand) {
     __shared__ int s_cnt[POST_NK];
     if (threadIdx.x < POST_NK) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -294,7 +294,10 @@ __global__ void __launch_bounds__(kThreads) post_prepare_kernel(PeoplePtrs P, co
                         rec.sus_extra[((int64_t)l * (nv - 1) + (v - 1)) * n + i] =
                             sus ? rel_sus_layer(rs, true, quar, pars.quar_factor[l], sus_imm[(int64_t)v * n + i]) : 0.0f;
                 }
-                if (any_trans) inf_nibble |= 1u << k;
+                if (any_trans) {
+                    inf_nibble |= 1u << k;
+                    trans_list[warp_append32(n_trans)] = (int32_t)i;       // compact (unordered) list of today's transmitters
+                }
             }
         }
         if (DO_PREP) {
@@ -477,8 +480,9 @@ static int ensure_records(cvb_sim* s) {
 template <bool DO_POST, bool DO_PREP>
 static int launch_post_prepare(cvb_sim* s, int32_t t, cudaStream_t st) {
     const int slot = t % s->quar_horizon;
+    if (DO_PREP) CVB_CHECK(cudaMemsetAsync(s->n_trans, 0, sizeof(unsigned int), st));
     post_prepare_kernel<DO_POST, DO_PREP><<<grid_agents(s->n), kThreads, 0, st>>>(s->people, s->pars, s->n, t, vector_ok(s),
-        s->quar_ring + (int64_t)slot * s->n, s->res.counters, s->rec, s->inf_bits, s->n_cand);
+        s->quar_ring + (int64_t)slot * s->n, s->res.counters, s->rec, s->inf_bits, s->trans_list, s->n_trans, s->n_cand);
     CVB_LAUNCH_CHECK();
     return 0;
 }

@@ -33,7 +33,7 @@ f32 = np.float32
 
 class Sim:
 
-    def __init__(self, pars=None, popdict=None, label=None, device=None, rng='philox', pop_exact=None, **kwargs):
+    def __init__(self, pars=None, popdict=None, label=None, device=None, rng='philox', pop_exact=None, use_adjacency=True, **kwargs):
         kw = dict(pars or {})
         kw.update(kwargs)
         for alias, key in (('n_agents', 'pop_size'), ('init_infected', 'pop_infected')):       # reference base.py:266-273
@@ -67,6 +67,9 @@ class Sim:
         self._quar_horizon = 1
         self._host_adds = {}
         self.kernel_timers = None          # set to {} to time every C-ABI call of step() with CUDA events
+        self.use_adjacency = use_adjacency   # False: stream every layer densely each day (the reference's access pattern)
+        self._adj = None
+        self._adj_dirty = False
 
     # ---- dict-like parameter access (reference base.py:63-114) -----------------------------------
     def __getitem__(self, key):
@@ -278,6 +281,52 @@ class Sim:
         self._quar_horizon = 1
         self._pars_dirty = True
         self._push_pars()
+        self._build_adjacency()
+
+    def _build_adjacency(self):
+        '''
+        Device-resident bidirectional adjacency (CSR over agents) of the static layers -- the CSR form of the
+        reference's Contacts (base.py:1509-1876).  For agent i, entries adj[ptr[i]:ptr[i+1]] are 16 bytes each:
+        (neighbour, edge index within its layer, (layer << 1) | direction, beta).  Built once (and again if a layer's
+        edge list is changed through the Layer API); transmission and tracing then visit only the edges of
+        today's transmitters / cases.  Dynamic layers (regenerated every day) keep the dense streaming passes.
+        '''
+        self._adj_dirty = False
+        people, pars = self.people, self.pars
+        static = [i for i, lk in enumerate(people.layer_keys()) if not pars['dynam_layer'].get(lk) and len(people.contacts[lk]) > 0]
+        if not self.use_adjacency or not static:
+            self._adj = None
+            _capi.call('cvb_bind_adjacency', self._handle, None, None, 0, 0)
+            return
+        dev = self.device
+        src, nbr, eid, meta, wts = [], [], [], [], []
+        for i in static:
+            layer = list(people.contacts.values())[i]
+            E = len(layer)
+            if E >= 2 ** 31:
+                raise ValueError('a layer with 2^31 or more edges cannot be indexed by the adjacency')
+            e = torch.arange(E, dtype=torch.int32, device=dev)
+            for d, (a, b) in enumerate(((layer['p1'], layer['p2']), (layer['p2'], layer['p1']))):
+                src.append(a)
+                nbr.append(b)
+                eid.append(e)
+                meta.append(torch.full((E,), (i << 1) | d, dtype=torch.int32, device=dev))
+                wts.append(layer['beta'])
+        src = torch.cat(src)
+        order = torch.sort(src, stable=True).indices
+        M = int(src.numel())
+        adj = torch.empty((M, 4), dtype=torch.int32, device=dev)
+        adj[:, 0] = torch.cat(nbr)[order]
+        adj[:, 1] = torch.cat(eid)[order]
+        adj[:, 2] = torch.cat(meta)[order]
+        adj[:, 3] = torch.cat(wts)[order].view(torch.int32)
+        ptr = torch.zeros(self.n + 1, dtype=torch.int64, device=dev)
+        ptr[1:] = torch.cumsum(torch.bincount(src.to(torch.int64), minlength=self.n), 0)
+        mask = 0
+        for i in static:
+            mask |= 1 << i
+        self._adj = (ptr, adj)                      # keep the tensors alive while they are bound
+        _capi.call('cvb_bind_adjacency', self._handle, ptr.data_ptr(), adj.data_ptr(), M, mask)
 
     def _set_quar_horizon(self, horizon):
         if horizon > self._quar_horizon:
@@ -450,6 +499,8 @@ class Sim:
         people.t = t
         call = _capi.call if self.kernel_timers is None else self._timed_call
         self._push_pars()
+        if self._adj_dirty:
+            self._build_adjacency()
         call('cvb_update_states_pre', h, t, st)
         for lkey, dyn in pars['dynam_layer'].items():                                 # reference people.py:199-206
             if dyn:

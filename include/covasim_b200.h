@@ -89,6 +89,14 @@ int cvb_set_pars(cvb_sim* s, const cvb_pars* host_pars);
 int cvb_bind_field(cvb_sim* s, int32_t field, void* ptr);
 /* Bind one contact layer's edge list (reference base.py:1651-1676: p1:int32[E], p2:int32[E], beta:f32[E]) */
 int cvb_bind_layer(cvb_sim* s, int32_t layer, int32_t* p1, int32_t* p2, float* beta, int64_t n_edges);
+/* Bidirectional adjacency of the STATIC layers (the CSR form of Base.Contacts): for agent i the entries
+ * adj[adj_ptr[i] .. adj_ptr[i+1]) list every edge it belongs to as 16 bytes
+ *   {uint32 neighbour, uint32 edge index within its layer, uint32 (layer << 1) | direction, float32 beta}
+ * with direction 0 if i is the edge's p1 and 1 if it is its p2.  layer_mask has bit l set for every layer the
+ * adjacency covers; transmission and contact tracing then visit only the edges of transmitters / cases for
+ * those layers (same results as the dense passes: same Philox keys, same winner keys) and stream the rest
+ * (dynamic layers) densely.  Pass layer_mask = 0 to unbind. */
+int cvb_bind_adjacency(cvb_sim* s, const int64_t* adj_ptr, const void* adj, int64_t n_entries, uint32_t layer_mask);
 /* Per-day result tables: counters int64[npts][CVB_N_COUNTERS], vcounters int64[npts][n_variants][CVB_N_VCOUNTERS],
  * sums double[npts][4] = {sum nab over alive, sum sus_imm, sum symp_imm, unused} (reference sim.py:652-674) */
 int cvb_bind_results(cvb_sim* s, int64_t* counters, int64_t* vcounters, double* sums);

@@ -26,6 +26,74 @@ def test_lockstep_parity(cv, name):
     assert sim.summary['cum_infections'] > scenarios.SCENARIOS[name]['pars']['pop_infected']     # the epidemic actually ran
 
 
+ODD_SPEC = dict(
+    # population size not a multiple of 4 (scalar tail path of the 4-agents-per-thread kernels), 2 variants, all interventions
+    pars=dict(pop_size=2501, pop_infected=45, pop_type='hybrid', n_days=35, verbose=0, rand_seed=21, beta=0.025, n_imports=0.8),
+    variants=[dict(variant='delta', days=6, n_imports=15)],
+    interventions=[('test_prob', dict(start_day=3, symp_prob=0.3, asymp_prob=0.02, quar_policy='both', test_delay=1)),
+                   ('contact_tracing', dict(trace_probs=dict(h=0.9, s=0.4, w=0.4, c=0.1), trace_time=dict(h=0, s=1, w=1, c=3), start_day=5)),
+                   ('vaccinate_prob', dict(vaccine='moderna', days=7, prob=0.2))])
+
+
+def test_dense_and_adjacency_paths_agree(cv):
+    ''' use_adjacency=False streams every layer densely (the reference's access pattern); both must match the oracle '''
+    spec = scenarios.SCENARIOS['hybrid3k']
+    sim = cv.Sim(**scenarios.build(cv, spec), use_adjacency=False)
+    sim.initialize()
+    import numpy as np
+    from oracle import cvoracle as cvo
+    pop = dict(age=sim.people.to_numpy('age').astype(np.float64), sex=sim.people.to_numpy('sex'),
+               contacts={lk: l.to_numpy() for lk, l in sim.people.contacts.items()})
+    orc = cvo.OracleSim(**scenarios.build(cvo, spec), rng='philox', popdict=pop)
+    orc.initialize()
+    parity.run_lockstep(sim, orc, every=5)
+
+
+class clip_layer:
+    ''' Test-only intervention: on `day`, drop the first `frac` of a layer's edges (what cv.clip_edges does, reference
+    interventions.py:589-666 + base.py:1742-1757 Layer.pop_inds); works on both the device sim and the oracle '''
+    def __init__(self, day, lkey, frac):
+        self.day, self.lkey, self.frac = day, lkey, frac
+        self.initialized = False
+
+    def initialize(self, sim):
+        self.initialized = True
+
+    def __call__(self, sim):
+        if sim.t != self.day:
+            return
+        import numpy as np
+        if hasattr(sim, 'P'):                                   # oracle
+            layer = sim.contacts[self.lkey]
+            k = int(len(layer['p1']) * self.frac)
+            for c in ('p1', 'p2', 'beta'):
+                layer[c] = layer[c][k:].copy()
+        else:
+            layer = sim.people.contacts[self.lkey]
+            k = int(len(layer) * self.frac)
+            layer.pop_inds(np.arange(k))
+
+
+def test_layer_edit_rebuilds_adjacency(cv):
+    import numpy as np
+    from oracle import cvoracle as cvo
+    pars = dict(pop_size=3000, pop_infected=60, pop_type='hybrid', n_days=30, verbose=0, rand_seed=13, beta=0.03)
+    sim = cv.Sim(pars, interventions=[clip_layer(8, 'c', 0.5), cv.test_prob(symp_prob=0.3, start_day=3), cv.contact_tracing(trace_probs=0.5, start_day=4)])
+    sim.initialize()
+    pop = dict(age=sim.people.to_numpy('age').astype(np.float64), sex=sim.people.to_numpy('sex'),
+               contacts={lk: l.to_numpy() for lk, l in sim.people.contacts.items()})
+    orc = cvo.OracleSim(pars, interventions=[clip_layer(8, 'c', 0.5), cvo.test_prob(symp_prob=0.3, start_day=3), cvo.contact_tracing(trace_probs=0.5, start_day=4)],
+                        rng='philox', popdict=pop)
+    orc.initialize()
+    parity.run_lockstep(sim, orc)
+    assert len(sim.people.contacts['c']) == len(orc.contacts['c']['p1']) < len(pop['contacts']['c']['p1'])
+
+
+def test_lockstep_parity_odd_population(cv):
+    sim, orc = parity.build_pair(cv, spec=ODD_SPEC)
+    parity.run_lockstep(sim, orc)
+
+
 @pytest.mark.parametrize('name', ['default20k', 'baseline20k'])
 def test_endpoint_parity_20k(cv, name):
     ''' The two 20k-agent configurations (BASELINE.json config 1 and the reference's own baseline test sim) '''

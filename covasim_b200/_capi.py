@@ -77,6 +77,7 @@ PROTOTYPES = dict(
     cvb_destroy=[_P],
     cvb_set_seed=[_P, _u64],
     cvb_reset=[_P, _P],
+    cvb_get_edge_work=[_P, _P],
     cvb_set_pars=[_P, C.POINTER(cvb_pars)],
     cvb_set_nab_kin=[_P, _P, _i64],
     cvb_set_quar_horizon=[_P, _i32],

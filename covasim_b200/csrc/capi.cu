@@ -108,6 +108,8 @@ int cvb_create(cvb_sim** out, int64_t n_agents, int32_t n_variants, int32_t npts
         if ((rc = check_cuda(cudaMemset(s->n_cand, 0, 64), "n_cand"))) break;
         if ((rc = check_cuda(cudaMalloc((void**)&s->beds, (size_t)npts * 2 * sizeof(unsigned long long)), "beds"))) break;
         if ((rc = check_cuda(cudaMemset(s->beds, 0, (size_t)npts * 2 * sizeof(unsigned long long)), "beds"))) break;
+        if ((rc = check_cuda(cudaMalloc((void**)&s->edge_work, (size_t)npts * 2 * sizeof(unsigned long long)), "edge_work"))) break;
+        if ((rc = check_cuda(cudaMemset(s->edge_work, 0, (size_t)npts * 2 * sizeof(unsigned long long)), "edge_work"))) break;
         if ((rc = check_cuda(cudaMalloc((void**)&s->quar_ring, (size_t)n_agents * sizeof(float)), "quar_ring"))) break;
         fill_f32_kernel<<<grid_for(n_agents), kThreads>>>(s->quar_ring, n_agents, -1.0f);
         if ((rc = check_cuda(cudaGetLastError(), "fill quar_ring"))) break;
@@ -136,7 +138,7 @@ int cvb_create(cvb_sim** out, int64_t n_agents, int32_t n_variants, int32_t npts
 
 int cvb_destroy(cvb_sim* s) {
     if (!s) return 0;
-    cudaFree(s->cand); cudaFree(s->n_cand); cudaFree(s->infect_key); cudaFree(s->beds); cudaFree(s->quar_ring); cudaFree(s->case_bits); cudaFree(s->inf_bits);
+    cudaFree(s->cand); cudaFree(s->n_cand); cudaFree(s->infect_key); cudaFree(s->beds); cudaFree(s->edge_work); cudaFree(s->quar_ring); cudaFree(s->case_bits); cudaFree(s->inf_bits);
     cudaFree(s->trans_list); cudaFree(s->case_list); cudaFree(s->n_trans); cudaFree(s->n_case_list);
     cudaFree(s->n_cases); cudaFree(s->dev_scalars); cudaFree(s->rec.ts); cudaFree(s->rec.sus_extra); cudaFree(s->rec.ivar);
     cudaFree(s->nab_kin); cudaFree(s->tile_cnt); cudaFree(s->hit_mask); cudaFree(s->flag_tmp); cudaFree(s->partial);
@@ -152,8 +154,15 @@ int cvb_reset(cvb_sim* s, cvb_stream st_) {
     CVB_CHECK(cudaMemsetAsync(s->n_cand, 0, 64, st));
     CVB_CHECK(cudaMemsetAsync(s->n_cases, 0, 64, st));
     CVB_CHECK(cudaMemsetAsync(s->beds, 0, (size_t)s->npts * 2 * sizeof(unsigned long long), st));
+    CVB_CHECK(cudaMemsetAsync(s->edge_work, 0, (size_t)s->npts * 2 * sizeof(unsigned long long), st));
     fill_f32_kernel<<<grid_for((int64_t)s->quar_horizon * s->n), kThreads, 0, st>>>(s->quar_ring, (int64_t)s->quar_horizon * s->n, -1.0f);
     CVB_LAUNCH_CHECK();
+    return 0;
+}
+
+int cvb_get_edge_work(cvb_sim* s, int64_t* host_out /* [npts][2] */) {
+    CVB_REQUIRE(s && host_out, "cvb_get_edge_work: NULL argument");
+    CVB_CHECK(cudaMemcpy(host_out, s->edge_work, (size_t)s->npts * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return 0;
 }
 

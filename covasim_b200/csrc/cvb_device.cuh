@@ -168,6 +168,16 @@ CVB_HD float calc_ve(double enab, double exp_alpha, double beta) {
     return (float)(lo / dadd(1.0, lo));
 }
 
+// The three protection axes share the NAb level: pow(x, b) = exp(b * log(x)) with ONE log (x > 0).  Relative
+// error ~1e-15, far below the float32 rounding of the stored result (the parity tests allow 1e-6 on these fields).
+CVB_HD void calc_ve3(double enab, double ea0, double b0, double ea1, double b1, double ea2, double b2, float& s0, float& s1, float& s2) {
+    const double lg = log(enab);
+    const double l0 = dmul(ea0, exp(dmul(b0, lg))), l1 = dmul(ea1, exp(dmul(b1, lg))), l2 = dmul(ea2, exp(dmul(b2, lg)));
+    s0 = (float)(l0 / dadd(1.0, l0));
+    s1 = (float)(l1 / dadd(1.0, l1));
+    s2 = (float)(l2 / dadd(1.0, l2));
+}
+
 // ---- A9: one day of NAb kinetics (reference immunity.py:205-213) -----------------------------
 CVB_HD float nab_step(float nab, float peak, double kin) {
     float v = (float)dadd((double)nab, dmul(kin, (double)peak));

@@ -180,14 +180,16 @@ template <bool MULTI>
 __global__ void __launch_bounds__(kThreads) edge_pass_sparse_kernel(TransRecords rec, const __grid_constant__ EdgeParams ep,
         const long long* __restrict__ adj_ptr, const uint4* __restrict__ adj, const int32_t* __restrict__ trans_list,
         const unsigned int* __restrict__ n_trans_ptr, unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand,
-        unsigned int* __restrict__ n_cand) {
+        unsigned int* __restrict__ n_cand, unsigned long long* __restrict__ work_row) {
     const unsigned int n_trans = *n_trans_ptr;
+    unsigned long long visited = 0;
     const int64_t n = ep.n;
     const int lane = lane_id();
     const unsigned int warps_total = (gridDim.x * blockDim.x) >> 5;
     for (unsigned int ti = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ti < n_trans; ti += warps_total) {
         const int i = trans_list[ti];
         const long long beg = adj_ptr[i], end = adj_ptr[i + 1];
+        visited += (unsigned long long)(end - beg);
         const int vi = MULTI ? (int)rec.ivar[i] : 0;
         const float beta_v = ep.beta[vi];
         for (long long off = beg + lane; off < end; off += 32) {
@@ -211,6 +213,9 @@ __global__ void __launch_bounds__(kThreads) edge_pass_sparse_kernel(TransRecords
             }
         }
     }
+    // work accounting for the roofline: adjacency entries visited and transmitters today
+    if (lane == 0 && visited) atomicAdd(work_row, visited);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(work_row + 1, (unsigned long long)n_trans);
 }
 
 int build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges, uint32_t skip_mask);
@@ -254,6 +259,7 @@ int cvb::build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges, uint32_t s
 extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
     cudaStream_t st = (cudaStream_t)st_;
     CVB_REQUIRE(s && s->pars_set, "cvb_edge_pass: handle not ready");
+    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_edge_pass: day %d outside [0,%d)", t, s->npts);
     CVB_REQUIRE(s->rec.ts && s->rec_layers >= s->pars.n_layers, "cvb_edge_pass: call cvb_prepare_transmission first");
     EdgeParams ep;
     for (int v = 0; v < CVB_MAX_VARIANTS; ++v) ep.beta[v] = s->pars.beta[v];
@@ -266,10 +272,11 @@ extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
         // sized for a large outbreak and surplus warps exit after one load)
         skip_mask = s->adj_layer_mask;
         const int grid = 148 * 8;
+        unsigned long long* work_row = s->edge_work + (int64_t)t * 2;
         if (multi) edge_pass_sparse_kernel<true><<<grid, kThreads, 0, st>>>(s->rec, ep, s->adj_ptr, s->adj, s->trans_list, s->n_trans,
-                                                                          s->infect_key, s->cand, s->n_cand);
+                                                                          s->infect_key, s->cand, s->n_cand, work_row);
         else edge_pass_sparse_kernel<false><<<grid, kThreads, 0, st>>>(s->rec, ep, s->adj_ptr, s->adj, s->trans_list, s->n_trans,
-                                                                      s->infect_key, s->cand, s->n_cand);
+                                                                      s->infect_key, s->cand, s->n_cand, work_row);
         CVB_LAUNCH_CHECK();
         bool rest = false;
         for (int l = 0; l < s->pars.n_layers; ++l) rest |= !(skip_mask & (1u << l)) && s->layers[l].n_edges > 0;

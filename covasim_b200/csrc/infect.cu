@@ -61,21 +61,29 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
             source = dir == 0 ? L.l[lfield].p1[e] : L.l[lfield].p2[e];
             layer_code = lfield;
         }
-        if (!PB(P, susceptible)[i]) continue;                      // people.py:470-473
+        // every per-agent input is loaded here, before the first store, so the loads are independent and in flight
+        // together (the stores below may alias them as far as the compiler knows)
+        const bool is_sus = PB(P, susceptible)[i] != 0;
+        const float in_peak = PF(P, peak_nab)[i], in_nab = PF(P, nab)[i], in_rel_trans = PF(P, rel_trans)[i];
+        const int in_nbreak = PI(P, n_breakthroughs)[i], in_ninf = PI(P, n_infections)[i];
+        const float in_drec = PF(P, date_recovered)[i];
+        const float in_symp_prob = PF(P, symp_prob)[i], in_sev_prob = PF(P, severe_prob)[i], in_crit_prob = PF(P, crit_prob)[i],
+                    in_death_prob = PF(P, death_prob)[i];
+        const float in_symp_imm = PF(P, symp_imm)[(int64_t)v * n + i], in_sev_imm = PF(P, sev_imm)[(int64_t)v * n + i];
+        if (!is_sus) continue;                                     // people.py:470-473
 
         // breakthrough infections (people.py:486-491, 501)
-        if (PF(P, peak_nab)[i] != 0.0f) {
-            int nb = PI(P, n_breakthroughs)[i];
-            if (nb == 0) PF(P, rel_trans)[i] = fmul(PF(P, rel_trans)[i], pars.trans_redux);
-            PI(P, n_breakthroughs)[i] = nb + 1;
+        if (in_peak != 0.0f) {
+            if (in_nbreak == 0) PF(P, rel_trans)[i] = fmul(in_rel_trans, pars.trans_redux);
+            PI(P, n_breakthroughs)[i] = in_nbreak + 1;
         }
         // flags (people.py:494-503)
         PB(P, susceptible)[i] = 0; PB(P, naive)[i] = 0; PB(P, recovered)[i] = 0; PB(P, diagnosed)[i] = 0; PB(P, exposed)[i] = 1;
-        PI(P, n_infections)[i] += 1;
+        PI(P, n_infections)[i] = in_ninf + 1;
         PF(P, exposed_variant)[i] = (float)v;
         PB(P, exposed_by_variant)[(int64_t)v * n + i] = 1;
         ++c[INF_INFECTIONS];
-        c[INF_REINFECTIONS] += !is_nan(PF(P, date_recovered)[i]);
+        c[INF_REINFECTIONS] += !is_nan(in_drec);
         // infection log (people.py:508-511)
         {
             unsigned long long pos = warp_append(log.count);
@@ -97,7 +105,7 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
         bool is_symp_f = false, is_sev_f = false;
 
         // prognosis tree (people.py:522-580)
-        const float p_symp = prog_prob_imm(pars.rel_symp[v], PF(P, symp_prob)[i], PF(P, symp_imm)[(int64_t)v * n + i]);
+        const float p_symp = prog_prob_imm(pars.rel_symp[v], in_symp_prob, in_symp_imm);
         if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, i, 1) < (double)p_symp)) {
             const double d = draw_dur(pars, CVB_DUR_asym2rec, ia.seed, t, i, 2);
             d_rec = (float)dadd((double)d_inf, d);
@@ -108,7 +116,7 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
             const float i2s = (float)draw_dur(pars, CVB_DUR_inf2sym, ia.seed, t, i, 2);
             PF(P, dur_inf2sym)[i] = i2s;
             d_symp = fadd(d_inf, i2s);
-            const float p_sev = prog_prob_imm(pars.rel_severe[v], PF(P, severe_prob)[i], PF(P, sev_imm)[(int64_t)v * n + i]);
+            const float p_sev = prog_prob_imm(pars.rel_severe[v], in_sev_prob, in_sev_imm);
             if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, i, 3) < (double)p_sev)) {
                 const double d = draw_dur(pars, CVB_DUR_mild2rec, ia.seed, t, i, 4);
                 d_rec = (float)dadd((double)d_symp, d);
@@ -120,7 +128,7 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
                 const float s2s = (float)draw_dur(pars, CVB_DUR_sym2sev, ia.seed, t, i, 4);
                 PF(P, dur_sym2sev)[i] = s2s;
                 d_sev = fadd(d_symp, s2s);
-                const float p_crit = prog_prob_fac(pars.rel_crit[v], PF(P, crit_prob)[i], hosp_max ? pars.no_hosp_factor : 1.0f);
+                const float p_crit = prog_prob_fac(pars.rel_crit[v], in_crit_prob, hosp_max ? pars.no_hosp_factor : 1.0f);
                 if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, i, 5) < (double)p_crit)) {
                     const double d = draw_dur(pars, CVB_DUR_sev2rec, ia.seed, t, i, 6);
                     d_rec = (float)dadd((double)d_sev, d);
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
                     const float s2c = (float)draw_dur(pars, CVB_DUR_sev2crit, ia.seed, t, i, 6);
                     PF(P, dur_sev2crit)[i] = s2c;
                     d_crit = fadd(d_sev, s2c);
-                    const float p_death = prog_prob_fac(pars.rel_death[v], PF(P, death_prob)[i], icu_max ? pars.no_icu_factor : 1.0f);
+                    const float p_death = prog_prob_fac(pars.rel_death[v], in_death_prob, icu_max ? pars.no_icu_factor : 1.0f);
                     const float pre = fadd(fadd(fadd(e2i, i2s), s2s), s2c);
                     if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, i, 7) < (double)p_death)) {
                         const double d = draw_dur(pars, CVB_DUR_crit2rec, ia.seed, t, i, 8);
@@ -158,8 +166,8 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
 
         // NAbs (immunity.py:138-202 with symp != None)
         if (pars.use_waning) {
-            if (PF(P, nab)[i] > 0.0f) {
-                PF(P, peak_nab)[i] = fmul(PF(P, peak_nab)[i], pars.nab_boost);
+            if (in_nab > 0.0f) {
+                PF(P, peak_nab)[i] = fmul(in_peak, pars.nab_boost);
             } else {
                 double x = dist_from_normal(pars.nab_init, keyed_normal(ia.seed, P_INFECT, 0, t, i, 9));
                 double level = pow(2.0, x);
@@ -236,7 +244,7 @@ int cvb_infect_winners(cvb_sim* s, int32_t t, cvb_stream st) {
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_infect_winners: day %d outside [0,%d)", t, s->npts);
     // the number of candidates is only known on the device: size the grid for a large outbreak and let
     // surplus CTAs exit after one load of n_cand
-    int64_t guess = s->n / 16 + 1024;
+    int64_t guess = s->n / 64 + 1024;
     return launch_infect(s, t, 1, CVB_LAYER_SEED, -1, -1, guess, (cudaStream_t)st);
 }
 

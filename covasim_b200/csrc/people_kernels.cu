@@ -139,11 +139,9 @@ __global__ void __launch_bounds__(kThreads) states_pre_kernel(PeoplePtrs P, cons
                     const double vaccine = (vacc && vsi >= 0 && vsi < CVB_MAX_VACCINES) ? pars.vaccine_imm[vsi][v] : 0.0;
                     const double enab = dmul((double)nb[k], fmax(natural, vaccine));
                     float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
-                    if (enab != 0.0) {       // 0**beta == 0 -> protection exactly 0
-                        s0 = calc_ve(enab, pars.exp_alpha_inf, pars.beta_inf);
-                        s1 = calc_ve(enab, pars.exp_alpha_symp_inf, pars.beta_symp_inf);
-                        s2 = calc_ve(enab, pars.exp_alpha_sev_symp, pars.beta_sev_symp);
-                    }
+                    if (enab > 0.0)          // 0**beta == 0 -> protection exactly 0
+                        calc_ve3(enab, pars.exp_alpha_inf, pars.beta_inf, pars.exp_alpha_symp_inf, pars.beta_symp_inf,
+                                 pars.exp_alpha_sev_symp, pars.beta_sev_symp, s0, s1, s2);
                     sus_imm[(int64_t)v * n + i] = s0;
                     symp_imm[(int64_t)v * n + i] = s1;
                     sev_imm[(int64_t)v * n + i] = s2;

@@ -183,6 +183,8 @@ class contact_tracing(Intervention):
         t = sim.t
         if t < self.start_day or (self.end_day is not None and t > self.end_day):
             return
+        if sim._adj_dirty:
+            sim._build_adjacency()
         _capi.call('cvb_contact_tracing', sim._handle, t, C.byref(self._c), sim._stream_ptr)
 
 

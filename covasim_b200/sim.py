@@ -406,6 +406,12 @@ class Sim:
             self.results['variant'][k].values[:] = 0
         return self
 
+    def edge_work(self):
+        ''' Per-day (adjacency entries visited, transmitters) of the sparse edge pass, int64[npts, 2] '''
+        out = np.zeros((self.npts, 2), dtype=np.int64)
+        _capi.call('cvb_get_edge_work', self._handle, out.ctypes.data)
+        return out
+
     def h2d_bytes(self, snap):
         ''' Bytes restore() copies host -> device '''
         n = sum(h.numel() * h.element_size() for h in snap['people'].values())
@@ -516,6 +522,8 @@ class Sim:
         for iv in pars['interventions']:
             iv(self)
         self._push_pars()
+        if self._adj_dirty:                    # an intervention edited a layer's edge list
+            self._build_adjacency()
         call('cvb_post_and_prepare', h, t, st)
         call('cvb_edge_pass', h, t, st)
         call('cvb_infect_winners', h, t, st)

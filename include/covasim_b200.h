@@ -80,6 +80,9 @@ int cvb_struct_sizes(int64_t* out5);
 int cvb_create(cvb_sim** out, int64_t n_agents, int32_t n_variants, int32_t npts, uint64_t seed);
 int cvb_destroy(cvb_sim* s);
 int cvb_set_seed(cvb_sim* s, uint64_t seed);
+/* Work done by the adjacency form of the edge pass, per day: host int64[npts][2] = {adjacency entries visited,
+ * transmitters}.  bench.py derives the kernel's algorithmic bytes from it. */
+int cvb_get_edge_work(cvb_sim* s, int64_t* host_out);
 /* Clear the library-owned per-run scratch (pending-quarantine ring, winner keys, bed counts) so that the
  * handle can run the same simulation again from a restored People state (Sim.restore) */
 int cvb_reset(cvb_sim* s, cvb_stream st);

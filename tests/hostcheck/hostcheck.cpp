@@ -46,6 +46,13 @@ void hc_calc_ve(const double* enab, double exp_alpha, double beta, float* out, l
     for (long i = 0; i < n; ++i) out[i] = enab[i] != 0.0 ? cvb::calc_ve(enab[i], exp_alpha, beta) : 0.0f;
 }
 
+void hc_calc_ve3(const double* enab, double ea0, double b0, double ea1, double b1, double ea2, double b2, float* o0, float* o1, float* o2, long n) {
+    for (long i = 0; i < n; ++i) {
+        o0[i] = o1[i] = o2[i] = 0.0f;
+        if (enab[i] > 0.0) cvb::calc_ve3(enab[i], ea0, b0, ea1, b1, ea2, b2, o0[i], o1[i], o2[i]);
+    }
+}
+
 void hc_nab_step(const float* nab, const float* peak, const double* kin, float* out, long n) {
     for (long i = 0; i < n; ++i) out[i] = cvb::nab_step(nab[i], peak[i], kin[i]);
 }

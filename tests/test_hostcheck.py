@@ -39,8 +39,8 @@ def test_viral_load_and_trans_sus_vs_reference_vectors(hc, golden, name, day):
     pre = f'k{day}/'
     di, dr, dd = g[pre + 'vl/date_inf'], g[pre + 'vl/date_rec'], g[pre + 'vl/date_dead']
     out = np.empty_like(di)
-    hc.hc_viral_load(C.c_int(int(g[pre + 'vl/t'])), ptr(di), ptr(dr), ptr(dd), C.c_float(g[pre + 'vl/frac_time']),
-                     C.c_float(g[pre + 'vl/load_ratio']), C.c_float(g[pre + 'vl/high_cap']), ptr(out), C.c_long(len(di)))
+    hc.hc_viral_load(C.c_int(int(g[pre + 'vl/t'])), ptr(di), ptr(dr), ptr(dd), C.c_float(float(g[pre + 'vl/frac_time'])),
+                     C.c_float(float(g[pre + 'vl/load_ratio'])), C.c_float(float(g[pre + 'vl/high_cap'])), ptr(out), C.c_long(len(di)))
     assert np.array_equal(out, g[pre + 'vl/out'])
     for j in range(int(g[pre + 'n_calls'])):
         a = {k.split('/')[-1]: np.ascontiguousarray(g[k]) for k in g.files if k.startswith(f'{pre}ts{j}/')}
@@ -48,9 +48,9 @@ def test_viral_load_and_trans_sus_vs_reference_vectors(hc, golden, name, day):
         ot, os_ = np.empty(n, np.float32), np.empty(n, np.float32)
         u8 = lambda x: np.ascontiguousarray(x.astype(np.uint8))
         inf, sus, symp, iso, quar = u8(a['inf']), u8(a['sus']), u8(a['symp']), u8(a['iso']), u8(a['quar'])
-        hc.hc_trans_sus(ptr(a['rel_trans']), ptr(a['rel_sus']), ptr(inf), ptr(sus), C.c_float(a['beta_layer']), ptr(a['viral_load']),
-                        ptr(symp), ptr(iso), ptr(quar), C.c_float(a['asymp_factor']), C.c_float(a['iso_factor']),
-                        C.c_float(a['quar_factor']), ptr(a['immunity_factors']), ptr(ot), ptr(os_), C.c_long(n))
+        hc.hc_trans_sus(ptr(a['rel_trans']), ptr(a['rel_sus']), ptr(inf), ptr(sus), C.c_float(float(a['beta_layer'])), ptr(a['viral_load']),
+                        ptr(symp), ptr(iso), ptr(quar), C.c_float(float(a['asymp_factor'])), C.c_float(float(a['iso_factor'])),
+                        C.c_float(float(a['quar_factor'])), ptr(a['immunity_factors']), ptr(ot), ptr(os_), C.c_long(n))
         assert np.array_equal(ot, a['out_trans'])
         assert np.array_equal(os_, a['out_sus'])
 
@@ -82,6 +82,11 @@ def test_distributions_and_immunity_math(hc):
     for alpha, beta in [(1.08, 0.967), (-0.739, 0.038), (-0.014, 0.079)]:
         hc.hc_calc_ve(ptr(enab), C.c_double(np.exp(alpha)), C.c_double(beta), ptr(ve), C.c_long(len(enab)))
         np.testing.assert_allclose(ve, cvo.calc_VE(enab, alpha, beta).astype(np.float32), rtol=1e-6, atol=0)
+    o = [np.empty(len(enab), np.float32) for _ in range(3)]
+    ab = [(1.08, 0.967), (-0.739, 0.038), (-0.014, 0.079)]
+    hc.hc_calc_ve3(ptr(enab), *[C.c_double(x) for a, b in ab for x in (np.exp(a), b)], ptr(o[0]), ptr(o[1]), ptr(o[2]), C.c_long(len(enab)))
+    for (a, b), got in zip(ab, o):
+        np.testing.assert_allclose(got, cvo.calc_VE(enab, a, b).astype(np.float32), rtol=2e-7, atol=0)      # at most one float32 ulp
     nab = np.abs(rng.standard_normal(4000)).astype(np.float32)
     peak = (nab + np.abs(rng.standard_normal(4000)) * 0.1).astype(np.float32)
     kin = rng.standard_normal(4000) * 0.05

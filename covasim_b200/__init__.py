@@ -19,4 +19,5 @@ from .people import People  # noqa: F401
 from .immunity import variant, calc_VE, calc_VE_symp, precompute_waning  # noqa: F401
 from .interventions import Intervention, change_beta, test_prob, contact_tracing, vaccinate_prob  # noqa: F401
 from .sim import Sim  # noqa: F401
+from .run import MultiSim, multi_run  # noqa: F401
 from . import ops  # noqa: F401

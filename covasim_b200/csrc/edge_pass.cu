@@ -223,10 +223,11 @@ int build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges, uint32_t skip_m
 template <bool MULTI, bool SMEM_BITS, int THREADS>
 static int launch_edge_pass(cvb_sim* s, const LayerTable& L, const EdgeParams& ep, size_t smem, int grid, cudaStream_t st) {
     auto kern = edge_pass_kernel<MULTI, SMEM_BITS, THREADS>;
-    static bool configured = false;                                  // per instantiation
-    if (!configured) {
+    static bool configured[64] = {false};                            // per instantiation and per device
+    const int dev = s->device & 63;
+    if (!configured[dev]) {
         CVB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        configured = true;
+        configured[dev] = true;
     }
     kern<<<grid, THREADS, smem, st>>>(L, s->rec, ep, s->inf_bits, s->infect_key, s->cand, s->n_cand);
     CVB_LAUNCH_CHECK();

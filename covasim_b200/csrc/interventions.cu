@@ -332,10 +332,10 @@ int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_str
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
     if (smem_bits) {
-        static bool configured = false;
-        if (!configured) {
+        static bool configured[64] = {false};                        // the attribute is per device
+        if (!configured[s->device & 63]) {
             CVB_CHECK(cudaFuncSetAttribute(trace_edges_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-            configured = true;
+            configured[s->device & 63] = true;
         }
         const int grid = (int)(acc < n_sm ? acc : n_sm);
         trace_edges_kernel<true, 1024><<<grid, 1024, bitmap_bytes, st>>>(s->people, T, s->case_bits);

@@ -256,6 +256,7 @@ class Sim:
 
     def _create_handle(self):
         self._destroy()
+        torch.cuda.set_device(self.device)
         pars = self.pars
         npts, nv = self.npts, pars['n_variants']
         h = C.c_void_p()
@@ -502,6 +503,8 @@ class Sim:
         if self.complete:
             raise AlreadyRunError('Simulation already complete (call sim.initialize() to re-run)')
         t, pars, people, h, st = self.t, self.pars, self.people, self._handle, self._stream_ptr
+        if torch.cuda.current_device() != self.device.index:      # ensembles keep members on several GPUs in one process
+            torch.cuda.set_device(self.device)
         people.t = t
         call = _capi.call if self.kernel_timers is None else self._timed_call
         self._push_pars()

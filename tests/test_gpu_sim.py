@@ -194,3 +194,20 @@ def test_state_diagram(cv, use_waning):
                 assert P[s2][on].all(), f'{s1} must imply {s2}'
             elif M[i, j] == -1:
                 assert not P[s2][on].any(), f'{s1} must exclude {s2}'
+
+
+def test_multisim_members_equal_individual_runs(cv):
+    ''' reference tests/test_run.py: MultiSim members are the base sim with rand_seed + i (run.py:1363-1365) '''
+    pars = dict(pop_size=3000, pop_infected=40, pop_type='hybrid', n_days=25, rand_seed=5, beta=0.025)
+    make = lambda seed: cv.Sim(dict(pars, rand_seed=seed), interventions=[cv.test_prob(symp_prob=0.2, start_day=5)])
+    msim = cv.MultiSim(make(5), n_runs=4)
+    msim.run()
+    for i in range(4):
+        solo = make(5 + i).run()
+        for k in ('new_infections', 'cum_infections', 'n_exposed', 'new_diagnoses', 'cum_deaths'):
+            assert np.array_equal(msim.member_results[i][k], solo.results[k].values), (i, k)
+    msim.reduce()
+    lo, mid, hi = msim.results['cum_infections'].low, msim.results['cum_infections'].values, msim.results['cum_infections'].high
+    assert np.all(lo <= mid) and np.all(mid <= hi)
+    finals = msim.summarize('cum_infections')
+    assert len(set(finals.tolist())) > 1                      # different seeds, different epidemics

@@ -155,6 +155,11 @@ class People:
         infections have none, and transmissions are infected by the fused edge pass.
         '''
         sim = self._sim
+        if sim.rng_mode == 'mt':                       # replay mode: the reference's stream order, host draws
+            from . import replay
+            return replay.infect(sim, inds, hosp_max=bool(hosp_max) if not isinstance(hosp_max, str) else False,
+                                 icu_max=bool(icu_max) if not isinstance(icu_max, str) else False, source=source, layer=layer,
+                                 variant=variant, count_flows=count_flows)
         inds = torch.as_tensor(inds, dtype=torch.int32, device=self.device).contiguous()
         if len(inds) == 0:
             return inds

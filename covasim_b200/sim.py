@@ -44,8 +44,8 @@ class Sim:
         for key in ('interventions', 'analyzers', 'variants'):
             if not isinstance(self.pars[key], list):
                 self.pars[key] = [self.pars[key]]
-        if rng not in ('philox',):
-            raise NotImplementedError(f'rng mode "{rng}" is not available (choices: philox)')
+        if rng not in ('philox', 'mt'):
+            raise NotImplementedError(f'rng mode "{rng}" is not available (choices: philox (native), mt (replay of the reference streams))')
         self.rng_mode = rng
         self.label = label
         self.popdict = popdict
@@ -294,6 +294,9 @@ class Sim:
         '''
         self._adj_dirty = False
         people, pars = self.people, self.pars
+        if self.rng_mode == 'mt':                      # replay mode walks the edge lists in the reference's order
+            self._adj = None
+            return
         static = [i for i, lk in enumerate(people.layer_keys()) if not pars['dynam_layer'].get(lk) and len(people.contacts[lk]) > 0]
         if not self.use_adjacency or not static:
             self._adj = None
@@ -493,6 +496,24 @@ class Sim:
             inds = self.rng.nb.choice(pars['pop_size'], int(pars['pop_infected']), replace=False)       # cvu.choose: Numba stream
             self.people.infect(inds, layer='seed_infection', count_flows=False)
 
+    def _log_append(self, source, target, layer, variant):
+        ''' Append transmissions to the device infection log from Python (replay mode); the kernels append directly '''
+        L = self._log
+        n = len(target)
+        if n == 0:
+            return
+        pos = int(L['count'].item())
+        end = min(pos + n, len(L['source']))
+        k = end - pos
+        lkeys = self.people.layer_keys()
+        code = lkeys.index(layer) if layer in lkeys else {'seed_infection': _capi.LAYER_SEED}.get(layer, _capi.LAYER_IMPORT)
+        L['target'][pos:end] = target[:k].to(torch.int32)
+        L['source'][pos:end] = -1 if source is None else source[:k].to(torch.int32)
+        L['date'][pos:end] = int(self.t)
+        L['layer'][pos:end] = code
+        L['variant'][pos:end] = int(variant)
+        L['count'] += n
+
     def _host_add(self, key, t, value):
         ''' Host-side contribution to a result (e.g. n_imports), merged with the device counters at sync time '''
         arr = self._host_adds.setdefault(key, np.zeros(self.npts))
@@ -502,6 +523,11 @@ class Sim:
     def step(self):
         if self.complete:
             raise AlreadyRunError('Simulation already complete (call sim.initialize() to re-run)')
+        if self.rng_mode == 'mt':
+            from . import replay
+            if torch.cuda.current_device() != self.device.index:
+                torch.cuda.set_device(self.device)
+            return replay.step(self)
         t, pars, people, h, st = self.t, self.pars, self.people, self._handle, self._stream_ptr
         if torch.cuda.current_device() != self.device.index:      # ensembles keep members on several GPUs in one process
             torch.cuda.set_device(self.device)

@@ -84,6 +84,9 @@ PROTOTYPES = dict(
     cvb_bind_field=[_P, _i32, _P],
     cvb_bind_layer=[_P, _i32, _P, _P, _P, _i64],
     cvb_bind_adjacency=[_P, _P, _P, _i64, C.c_uint32],
+    cvb_set_partition=[_P, _i64, _i64, _i64, _i32, _P, _P, _P, _P, _P, _i64],
+    cvb_bind_partition_adjacency=[_P, _P, _P, _i64, C.c_uint32],
+    cvb_partition_status=[_P, _P],
     cvb_bind_results=[_P, _P, _P, _P],
     cvb_bind_log=[_P, _P, _P, _P, _P, _P, _i64, _P],
     cvb_compute_viral_load=[_i32, _P, _P, _P, _f32, _f32, _f32, _P, _i64, _P],
@@ -104,6 +107,8 @@ PROTOTYPES = dict(
     cvb_step_day=[_P, _i32, _P],
     cvb_test_prob=[_P, _i32, C.POINTER(cvb_test_prob_pars), _P],
     cvb_contact_tracing=[_P, _i32, C.POINTER(cvb_trace_pars), _P],
+    cvb_trace_select_cases=[_P, _i32, C.POINTER(cvb_trace_pars), _P],
+    cvb_trace_notify_contacts=[_P, _i32, C.POINTER(cvb_trace_pars), _P],
     cvb_vaccinate_prob=[_P, _i32, C.POINTER(cvb_vaccinate_pars), _P, _P, _P],
     cvb_layer_regenerate=[_P, _i32, _i32, _P],
 )

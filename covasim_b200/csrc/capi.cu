@@ -142,6 +142,7 @@ int cvb_destroy(cvb_sim* s) {
     cudaFree(s->trans_list); cudaFree(s->case_list); cudaFree(s->n_trans); cudaFree(s->n_case_list);
     cudaFree(s->n_cases); cudaFree(s->dev_scalars); cudaFree(s->rec.ts); cudaFree(s->rec.sus_extra); cudaFree(s->rec.ivar);
     cudaFree(s->nab_kin); cudaFree(s->tile_cnt); cudaFree(s->hit_mask); cudaFree(s->flag_tmp); cudaFree(s->partial);
+    cudaFree(s->glist); cudaFree(s->n_glist); cudaFree(s->hit_src); cudaFree(s->hit_key); cudaFree(s->part_flags);
     if (s->host_scalars) cudaFreeHost(s->host_scalars);
     delete s;
     return 0;
@@ -155,6 +156,7 @@ int cvb_reset(cvb_sim* s, cvb_stream st_) {
     CVB_CHECK(cudaMemsetAsync(s->n_cases, 0, 64, st));
     CVB_CHECK(cudaMemsetAsync(s->beds, 0, (size_t)s->npts * 2 * sizeof(unsigned long long), st));
     CVB_CHECK(cudaMemsetAsync(s->edge_work, 0, (size_t)s->npts * 2 * sizeof(unsigned long long), st));
+    if (s->part_flags) CVB_CHECK(cudaMemsetAsync(s->part_flags, 0, 64, st));
     fill_f32_kernel<<<grid_for((int64_t)s->quar_horizon * s->n), kThreads, 0, st>>>(s->quar_ring, (int64_t)s->quar_horizon * s->n, -1.0f);
     CVB_LAUNCH_CHECK();
     return 0;
@@ -223,6 +225,57 @@ int cvb_bind_adjacency(cvb_sim* s, const int64_t* adj_ptr, const void* adj, int6
     CVB_REQUIRE(adj_ptr && adj, "cvb_bind_adjacency: NULL array");
     CVB_REQUIRE(((uintptr_t)adj & 15) == 0, "cvb_bind_adjacency: entries must be 16-byte aligned");
     s->adj_ptr = (const long long*)adj_ptr; s->adj = (const uint4*)adj; s->adj_entries = n_entries; s->adj_layer_mask = layer_mask;
+    return 0;
+}
+
+int cvb_set_partition(cvb_sim* s, int64_t id0, int64_t n_global, int64_t chunk, int32_t world, const float* rel_trans_global,
+                      uint8_t* codes_local, const uint8_t* codes_global, uint32_t* case_bits_local, const uint32_t* case_bits_global,
+                      int64_t hit_capacity) {
+    CVB_REQUIRE(s, "cvb_set_partition: NULL handle");
+    CVB_REQUIRE(world >= 1 && chunk > 0 && chunk % 32 == 0, "cvb_set_partition: chunk must be a positive multiple of 32");
+    CVB_REQUIRE(id0 >= 0 && id0 % chunk == 0 && id0 + s->n <= n_global && s->n <= chunk, "cvb_set_partition: agents [%lld, %lld) do not fit chunk %lld of %lld",
+                (long long)id0, (long long)(id0 + s->n), (long long)chunk, (long long)n_global);
+    CVB_REQUIRE(n_global <= (int64_t)world * chunk && (int64_t)world * chunk < (1ll << 31), "cvb_set_partition: world * chunk must cover n_global and fit int32");
+    CVB_REQUIRE(s->nv <= 7, "cvb_set_partition: at most 7 variants fit the 1-byte transmit code");
+    CVB_REQUIRE(rel_trans_global && codes_local && codes_global && case_bits_local && case_bits_global, "cvb_set_partition: NULL array");
+    CVB_REQUIRE((((uintptr_t)codes_local | (uintptr_t)codes_global | (uintptr_t)case_bits_local | (uintptr_t)case_bits_global) & 15) == 0,
+                "cvb_set_partition: arrays must be 16-byte aligned");
+    s->id0 = id0; s->n_global = n_global; s->chunk = chunk; s->n_slots = (int64_t)world * chunk;
+    s->rel_trans_global = rel_trans_global;
+    s->codes_local = codes_local; s->codes_global = codes_global;
+    s->case_bits_local = case_bits_local; s->case_bits_global = case_bits_global;
+    if (hit_capacity < s->n) hit_capacity = s->n;
+    if (hit_capacity < 65536) hit_capacity = 65536;
+    cudaFree(s->cand); cudaFree(s->hit_src); cudaFree(s->hit_key); cudaFree(s->glist); cudaFree(s->n_glist); cudaFree(s->part_flags);
+    s->cand = nullptr; s->hit_src = nullptr; s->hit_key = nullptr; s->glist = nullptr; s->n_glist = nullptr; s->part_flags = nullptr;
+    CVB_CHECK(cudaMalloc((void**)&s->cand, (size_t)hit_capacity * sizeof(int32_t)));
+    CVB_CHECK(cudaMalloc((void**)&s->hit_src, (size_t)hit_capacity * sizeof(int32_t)));
+    CVB_CHECK(cudaMalloc((void**)&s->hit_key, (size_t)hit_capacity * sizeof(unsigned long long)));
+    s->hit_cap = hit_capacity;
+    s->glist_cap = s->n_slots;
+    CVB_CHECK(cudaMalloc((void**)&s->glist, (size_t)s->glist_cap * sizeof(int32_t)));
+    CVB_CHECK(cudaMalloc((void**)&s->n_glist, 64));
+    CVB_CHECK(cudaMemset(s->n_glist, 0, 64));
+    CVB_CHECK(cudaMalloc((void**)&s->part_flags, 64));
+    CVB_CHECK(cudaMemset(s->part_flags, 0, 64));
+    s->partitioned = 1;
+    return 0;
+}
+
+int cvb_bind_partition_adjacency(cvb_sim* s, const int64_t* adj_ptr, const void* adj, int64_t n_entries, uint32_t layer_mask) {
+    CVB_REQUIRE(s && s->partitioned, "cvb_bind_partition_adjacency: call cvb_set_partition first");
+    CVB_REQUIRE(adj_ptr && layer_mask, "cvb_bind_partition_adjacency: NULL row pointers / empty layer mask");
+    CVB_REQUIRE(n_entries == 0 || adj, "cvb_bind_partition_adjacency: NULL entries");
+    CVB_REQUIRE(((uintptr_t)adj & 15) == 0, "cvb_bind_partition_adjacency: entries must be 16-byte aligned");
+    s->padj_ptr = (const long long*)adj_ptr; s->padj = (const uint4*)adj; s->padj_entries = n_entries; s->padj_layer_mask = layer_mask;
+    return 0;
+}
+
+int cvb_partition_status(cvb_sim* s, int64_t* host_out2) {
+    CVB_REQUIRE(s && s->partitioned && host_out2, "cvb_partition_status: not a partitioned handle");
+    unsigned int f[2] = {0, 0};
+    CVB_CHECK(cudaMemcpy(f, s->part_flags, sizeof(f), cudaMemcpyDeviceToHost));
+    host_out2[0] = f[0]; host_out2[1] = f[1];
     return 0;
 }
 

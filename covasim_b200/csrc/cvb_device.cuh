@@ -127,15 +127,28 @@ CVB_HD double dist_from_normal(const cvb_dist& d, double z) {
 }
 
 // ---- A2: viral load (reference utils.py:39-79) -----------------------------------------------
-CVB_HD float viral_load(int32_t t, float d_inf, float d_rec, float d_dead, float frac_time, float load_ratio, float high_cap) {
+// split in two so that the agent-partitioned form can ship the 1-bit "early" decision instead of three dates
+CVB_HD bool viral_load_early(int32_t t, float d_inf, float d_rec, float d_dead, float frac_time, float high_cap) {
     float stop = is_nan(d_dead) ? d_rec : d_dead;
     float total = fsub(stop, d_inf);
     float trans_day = fmul(frac_time, total);
     float trans_point = (trans_day > high_cap) ? fdiv(high_cap, total) : frac_time;
     // the comparison is evaluated in float64 (int32 - float32 promotes in the reference)
-    bool early = ((double)t - (double)d_inf) / (double)total < (double)trans_point;
+    return ((double)t - (double)d_inf) / (double)total < (double)trans_point;
+}
+CVB_HD float viral_load_value(bool early, float frac_time, float load_ratio) {
     float denom = fadd(1.0f, fmul(frac_time, fsub(load_ratio, 1.0f)));
     return early ? fdiv(load_ratio, denom) : fdiv(1.0f, denom);
+}
+CVB_HD float viral_load(int32_t t, float d_inf, float d_rec, float d_dead, float frac_time, float load_ratio, float high_cap) {
+    return viral_load_value(viral_load_early(t, d_inf, d_rec, d_dead, frac_time, high_cap), frac_time, load_ratio);
+}
+
+// ---- transmit code: what another GPU needs to rebuild an agent's per-layer transmissibility (1 byte) ----
+// bits 0-2: carried variant + 1 (0 = cannot transmit today), 3: symptomatic, 4: isolated, 5: quarantined,
+// 6: early (high) viral load, 7: rel_trans has been reduced by a breakthrough infection (people.py:486-491)
+CVB_HD uint8_t transmit_code(int variant, bool symp, bool iso, bool quar, bool early, bool redux) {
+    return (uint8_t)(((variant + 1) & 7) | (symp ? 8 : 0) | (iso ? 16 : 0) | (quar ? 32 : 0) | (early ? 64 : 0) | (redux ? 128 : 0));
 }
 
 // ---- A3: transmissibility / susceptibility for one layer (reference utils.py:82-90) -------------

@@ -81,6 +81,18 @@ struct cvb_sim {
     int32_t* case_list; unsigned int* n_case_list;  // contact tracing: today's cases as a compact list
     // bidirectional adjacency (CSR over agents) of the static layers, bound by the host (cvb_bind_adjacency)
     const long long* adj_ptr; const uint4* adj; int64_t adj_entries; uint32_t adj_layer_mask;
+    // agent partition of one large simulation over several GPUs (cvb_set_partition): this handle owns the agents
+    // [id0, id0 + n) of n_global.  Per-agent Philox keys and logged ids use GLOBAL ids, so a partitioned run is
+    // bit-identical to the single-GPU run of the same simulation.
+    int64_t id0, n_global, chunk; int32_t partitioned;
+    const float* rel_trans_global;                  // [n_global] transmissibility at initialisation (replicated)
+    uint8_t* codes_local; const uint8_t* codes_global;   // [chunk] written by prepare_transmission / [world*chunk] all-gathered by the host
+    unsigned int* case_bits_local; const unsigned int* case_bits_global;   // [chunk/32] / [world*chunk/32]
+    int64_t n_slots;                                // world * chunk: number of global code slots
+    const long long* padj_ptr; const uint4* padj; int64_t padj_entries; uint32_t padj_layer_mask;   // rows: GLOBAL source slot; entries: LOCAL target
+    int32_t* glist; unsigned int* n_glist; int64_t glist_cap;   // compact list of global transmitters / cases
+    int32_t* hit_src; unsigned long long* hit_key; int64_t hit_cap;   // per successful transmission (parallel to cand)
+    unsigned int* part_flags;                       // [0] hits dropped (capacity), [1] agents whose rel_trans the code cannot express
     // scan / compaction workspace
     unsigned int* tile_cnt; int64_t tile_cnt_cap;   // per-tile counts (and their exclusive scan, in place)
     uint8_t* hit_mask; int64_t hit_mask_cap;
@@ -98,6 +110,8 @@ int ensure_u32(unsigned int** p, int64_t* cap, int64_t need);
 int ensure_u8(uint8_t** p, int64_t* cap, int64_t need);
 int ensure_f64(double** p, int64_t* cap, int64_t need);
 int exclusive_scan_u32(unsigned int* data, int64_t n, unsigned long long* total_out, cudaStream_t st);
+// agent-partitioned runs: set bits of a gathered bitmap -> s->glist / s->n_glist (edge_pass.cu)
+int list_from_bits(cvb_sim* s, const unsigned int* bits, int64_t n_words, cudaStream_t st);
 
 #define CVB_CHECK(call) do { int rc_ = cvb::check_cuda((call), #call); if (rc_) return rc_; } while (0)
 #define CVB_REQUIRE(cond, ...) do { if (!(cond)) { cvb::set_error(__VA_ARGS__); return 1; } } while (0)

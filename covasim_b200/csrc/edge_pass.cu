@@ -218,6 +218,125 @@ __global__ void __launch_bounds__(kThreads) edge_pass_sparse_kernel(TransRecords
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(work_row + 1, (unsigned long long)n_trans);
 }
 
+// ---- agent-partitioned form (one large simulation over several GPUs) ------------------------------------
+// Every GPU owns a contiguous range of agents and evaluates the transmissions whose TARGET it owns.  Its
+// adjacency has one row per GLOBAL agent (the possible sources) holding the edges that end in a LOCAL
+// target.  What it needs to know about a remote source is one byte (transmit_code) all-gathered by the host
+// once per day plus the replicated initial rel_trans; per-layer transmissibility is rebuilt from those with
+// the same float32 chain as prepare_transmission, so probabilities, Philox keys (layer, edge) and winner keys
+// are those of the single-GPU run, bit for bit.
+
+// Warp-level reservation: every lane asks for `c` slots of a global list; one atomic per warp
+__device__ __forceinline__ unsigned int warp_reserve(unsigned int* counter, int c) {
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane_id() >= d) incl += o;
+    }
+    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    unsigned int base = 0;
+    if (lane_id() == 31 && total) base = atomicAdd(counter, (unsigned int)total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31);
+    return base + (unsigned int)(incl - c);
+}
+
+// non-zero bytes of the gathered code array -> compact (unordered) list of global transmitter ids
+__global__ void __launch_bounds__(kThreads) codes_to_list_kernel(const uint8_t* __restrict__ codes, int64_t n_slots,
+        int32_t* __restrict__ list, unsigned int* __restrict__ n_list) {
+    const int64_t n16 = n_slots / 16;                                 // n_slots is a multiple of 32
+    const int64_t n16_pad = (n16 + 31) / 32 * 32;                     // whole warps stay in the loop (shuffles)
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n16_pad; g += (int64_t)gridDim.x * blockDim.x) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (g < n16) v = __ldg(reinterpret_cast<const uint4*>(codes) + g);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const int c = count4(v.x) + count4(v.y) + count4(v.z) + count4(v.w);
+        if (!__any_sync(0xFFFFFFFFu, c != 0)) continue;
+        unsigned int pos = warp_reserve(n_list, c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((w[q] >> (8 * k)) & 0xFFu) list[pos++] = (int32_t)(g * 16 + q * 4 + k);
+    }
+}
+
+// set bits of a gathered bitmap -> compact (unordered) list of global ids
+__global__ void __launch_bounds__(kThreads) bits_to_list_kernel(const unsigned int* __restrict__ bits, int64_t n_words,
+        int32_t* __restrict__ list, unsigned int* __restrict__ n_list) {
+    const int64_t n_pad = (n_words + 31) / 32 * 32;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_pad; g += (int64_t)gridDim.x * blockDim.x) {
+        unsigned w = g < n_words ? __ldg(bits + g) : 0u;
+        if (!__any_sync(0xFFFFFFFFu, w != 0u)) continue;
+        unsigned int pos = warp_reserve(n_list, __popc(w));
+        while (w) {
+            const int b = __ffs(w) - 1;
+            w &= w - 1;
+            list[pos++] = (int32_t)(g * 32 + b);
+        }
+    }
+}
+
+struct PartHits {                         // one entry per successful transmission (parallel arrays, shared counter)
+    int32_t* tgt; int32_t* src; unsigned long long* key; unsigned int* n; unsigned int* dropped; int64_t cap;
+};
+
+template <bool MULTI>
+__global__ void __launch_bounds__(kThreads) edge_pass_partition_kernel(TransRecords rec, const __grid_constant__ EdgeParams ep,
+        const __grid_constant__ cvb_pars pars, const long long* __restrict__ adj_ptr, const uint4* __restrict__ adj,
+        const int32_t* __restrict__ glist, const unsigned int* __restrict__ n_glist, const uint8_t* __restrict__ codes,
+        const float* __restrict__ base_trans, unsigned long long* __restrict__ infect_key, PartHits hits,
+        unsigned long long* __restrict__ work_row) {
+    const unsigned int n_trans = *n_glist;
+    unsigned long long visited = 0;
+    const int64_t n = ep.n;                                              // local agents
+    const int lane = lane_id();
+    const unsigned int warps_total = (gridDim.x * blockDim.x) >> 5;
+    const float vl_early = viral_load_value(true, pars.frac_time, pars.load_ratio);
+    const float vl_late = viral_load_value(false, pars.frac_time, pars.load_ratio);
+    for (unsigned int ti = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ti < n_trans; ti += warps_total) {
+        const int i = glist[ti];                                         // global id of the source
+        const long long beg = adj_ptr[i], end = adj_ptr[i + 1];
+        if (beg == end) continue;                                        // no contact on this GPU
+        visited += (unsigned long long)(end - beg);
+        const unsigned code = codes[i];
+        const int vi = (int)(code & 7u) - 1;
+        const bool symp = code & 8u, iso = code & 16u, quar = code & 32u, early = code & 64u;
+        float rt = __ldg(base_trans + i);
+        if (code & 128u) rt = fmul(rt, pars.trans_redux);
+        const float vl = early ? vl_early : vl_late;
+        const float beta_v = ep.beta[vi];
+        for (long long off = beg + lane; off < end; off += 32) {
+            const uint4 en = __ldg(adj + off);
+            const int j = (int)en.x;                                     // LOCAL target
+            const int l = (int)(en.z >> 1);
+            const int dir = (int)(en.z & 1u);
+            const float t_i = rel_trans_layer(rt, true, symp, iso, quar, pars.asymp_factor, pars.iso_factor[l], pars.quar_factor[l],
+                                              pars.beta_layer[l], vl);
+            if (t_i == 0.0f) continue;
+            float s_j;
+            if (MULTI && vi > 0) s_j = __ldg(rec.sus_extra + ((int64_t)l * (ep.nv - 1) + (vi - 1)) * n + j);
+            else s_j = __ldg(&rec.ts[(int64_t)l * n + j].y);
+            const float p = edge_prob(beta_v, __uint_as_float(en.w), t_i, s_j);
+            if (p != 0.0f) {
+                const int64_t e = (int64_t)en.y;
+                const u32x4 r = keyed_words(ep.seed, P_EDGE, (uint32_t)l, ep.t, e, 0);
+                const double u = dir == 0 ? u53(r.x, r.y) : u53(r.z, r.w);
+                if (u < (double)p) {
+                    const unsigned long long key = ((unsigned long long)vi << 56) | ((unsigned long long)l << 48) |
+                                                   ((unsigned long long)dir << 40) | (unsigned long long)e;
+                    atomicMin(infect_key + j, key);
+                    const unsigned int pos = warp_append32(hits.n);
+                    if ((int64_t)pos < hits.cap) { hits.tgt[pos] = j; hits.src[pos] = i; hits.key[pos] = key; }
+                    else atomicAdd(hits.dropped, 1u);
+                }
+            }
+        }
+    }
+    if (lane == 0 && visited) atomicAdd(work_row, visited);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(work_row + 1, (unsigned long long)n_trans);
+}
+
 int build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges, uint32_t skip_mask);
 
 template <bool MULTI, bool SMEM_BITS, int THREADS>
@@ -237,6 +356,13 @@ static int launch_edge_pass(cvb_sim* s, const LayerTable& L, const EdgeParams& e
 }  // namespace cvb
 
 using namespace cvb;
+
+int cvb::list_from_bits(cvb_sim* s, const unsigned int* bits, int64_t n_words, cudaStream_t st) {
+    CVB_CHECK(cudaMemsetAsync(s->n_glist, 0, sizeof(unsigned int), st));
+    bits_to_list_kernel<<<grid_for(n_words, kThreads, 148 * 8), kThreads, 0, st>>>(bits, n_words, s->glist, s->n_glist);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
 
 int cvb::build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges, uint32_t skip_mask) {
     int64_t acc = 0;
@@ -268,6 +394,24 @@ extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
     ep.n_words = (s->n + 31) / 32;
     const bool multi = s->nv > 1;
     uint32_t skip_mask = 0;
+    if (s->partitioned) {
+        // agent-partitioned form: global transmitter list from the all-gathered codes, then the local adjacency rows
+        CVB_REQUIRE(s->padj_ptr && s->padj && s->codes_global, "cvb_edge_pass: partitioned handle without adjacency / codes (cvb_bind_partition_adjacency, cvb_set_partition)");
+        for (int l = 0; l < s->pars.n_layers; ++l)
+            CVB_REQUIRE(((s->padj_layer_mask >> l) & 1u) || s->layers[l].n_edges == 0, "cvb_edge_pass: layer %d is not covered by the partitioned adjacency (dynamic layers cannot be partitioned)", l);
+        CVB_CHECK(cudaMemsetAsync(s->n_glist, 0, sizeof(unsigned int), st));
+        codes_to_list_kernel<<<grid_for(s->n_slots / 16, kThreads, 148 * 8), kThreads, 0, st>>>(s->codes_global, s->n_slots, s->glist, s->n_glist);
+        CVB_LAUNCH_CHECK();
+        PartHits hits{s->cand, s->hit_src, s->hit_key, s->n_cand, s->part_flags, s->hit_cap};
+        unsigned long long* work_row = s->edge_work + (int64_t)t * 2;
+        const int grid = 148 * 8;
+        if (multi) edge_pass_partition_kernel<true><<<grid, kThreads, 0, st>>>(s->rec, ep, s->pars, s->padj_ptr, s->padj, s->glist, s->n_glist,
+                                                                             s->codes_global, s->rel_trans_global, s->infect_key, hits, work_row);
+        else edge_pass_partition_kernel<false><<<grid, kThreads, 0, st>>>(s->rec, ep, s->pars, s->padj_ptr, s->padj, s->glist, s->n_glist,
+                                                                         s->codes_global, s->rel_trans_global, s->infect_key, hits, work_row);
+        CVB_LAUNCH_CHECK();
+        return 0;
+    }
     if (s->adj && s->adj_layer_mask) {
         // static layers: visit only the adjacency ranges of today's transmitters (a device-side count: the grid is
         // sized for a large outbreak and surplus warps exit after one load)

@@ -19,6 +19,10 @@ struct InfectArgs {
     int32_t count_flows;     // 0 for seed infections at initialisation (reference sim.py:505-532: flows are discarded)
     int32_t list_layer_code; // layer code logged for list-mode keys (CVB_LAYER_SEED / CVB_LAYER_IMPORT)
     int32_t hosp_max, icu_max; // 0 / 1 as given by the caller, -1 = evaluate from today's severe / critical counts (sim.py:579-580)
+    int64_t id0;             // global id of local agent 0 (agent-partitioned runs; 0 otherwise): Philox keys and the log use global ids
+    const int32_t* hit_src;  // partitioned edge pass: cand[] lists every successful transmission, with its source and key; the
+    const unsigned long long* hit_key;   // entry whose key equals infect_key[target] is the winner (NULL: cand[] lists unique targets)
+    int64_t hit_cap;
 };
 
 __device__ __forceinline__ double draw_dur(const cvb_pars& pars, int which, uint64_t seed, int32_t t, int64_t i, uint32_t slot) {
@@ -41,16 +45,24 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
 
     const int64_t n = ia.n;
     const int32_t t = ia.t;
-    const unsigned int n_cand = *n_cand_ptr;
+    unsigned int n_cand = *n_cand_ptr;
+    if (ia.hit_key && (int64_t)n_cand > ia.hit_cap) n_cand = (unsigned int)ia.hit_cap;
     const bool hosp_max = ia.hosp_max >= 0 ? ia.hosp_max != 0 : (pars.n_beds_hosp >= 0 && (long long)beds[(int64_t)t * 2 + 0] > pars.n_beds_hosp);
     const bool icu_max = ia.icu_max >= 0 ? ia.icu_max != 0 : (pars.n_beds_icu >= 0 && (long long)beds[(int64_t)t * 2 + 1] > pars.n_beds_icu);
     const float tf = (float)t;
 
     for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_cand; j += gridDim.x * blockDim.x) {
         const int64_t i = cand[j];
-        const unsigned long long key = infect_key[i];
-        infect_key[i] = kEmptyKey;
-        if (key == kEmptyKey) continue;
+        unsigned long long key;
+        if (ia.hit_key) {                                          // one entry per hit: only the winning one proceeds
+            key = ia.hit_key[j];
+            if (infect_key[i] != key) continue;
+            infect_key[i] = kEmptyKey;
+        } else {
+            key = infect_key[i];
+            infect_key[i] = kEmptyKey;
+            if (key == kEmptyKey) continue;
+        }
         const int v = (int)(key >> 56) & 0x7F;
         const int lfield = (int)(key >> 48) & 0xFF;
         const int dir = (int)(key >> 40) & 1;
@@ -58,9 +70,10 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
         int32_t source = -1;
         int layer_code = ia.list_layer_code;
         if (lfield != 0xFF) {
-            source = dir == 0 ? L.l[lfield].p1[e] : L.l[lfield].p2[e];
+            source = ia.hit_src ? ia.hit_src[j] : (dir == 0 ? L.l[lfield].p1[e] : L.l[lfield].p2[e]);
             layer_code = lfield;
         }
+        const int64_t gi = i + ia.id0;                             // global id: Philox index and logged target
         // every per-agent input is loaded here, before the first store, so the loads are independent and in flight
         // together (the stores below may alias them as far as the compiler knows)
         const bool is_sus = PB(P, susceptible)[i] != 0;
@@ -88,12 +101,12 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
         {
             unsigned long long pos = warp_append(log.count);
             if ((int64_t)pos < log.cap) {
-                log.source[pos] = source; log.target[pos] = (int32_t)i; log.date[pos] = t;
+                log.source[pos] = source; log.target[pos] = (int32_t)gi; log.date[pos] = t;
                 log.layer[pos] = (int8_t)layer_code; log.variant[pos] = (int8_t)v;
             }
         }
         // exposed -> infectious (people.py:513-520)
-        const float e2i = (float)draw_dur(pars, CVB_DUR_exp2inf, ia.seed, t, i, 0);
+        const float e2i = (float)draw_dur(pars, CVB_DUR_exp2inf, ia.seed, t, gi, 0);
         PF(P, dur_exp2inf)[i] = e2i;
         PF(P, date_exposed)[i] = tf;
         const float d_inf = fadd(e2i, tf);
@@ -106,45 +119,45 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
 
         // prognosis tree (people.py:522-580)
         const float p_symp = prog_prob_imm(pars.rel_symp[v], in_symp_prob, in_symp_imm);
-        if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, i, 1) < (double)p_symp)) {
-            const double d = draw_dur(pars, CVB_DUR_asym2rec, ia.seed, t, i, 2);
+        if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, gi, 1) < (double)p_symp)) {
+            const double d = draw_dur(pars, CVB_DUR_asym2rec, ia.seed, t, gi, 2);
             d_rec = (float)dadd((double)d_inf, d);
             dur_disease = (float)dadd((double)e2i, d);
             symp_class = 0;
         } else {
             is_symp_f = true;
-            const float i2s = (float)draw_dur(pars, CVB_DUR_inf2sym, ia.seed, t, i, 2);
+            const float i2s = (float)draw_dur(pars, CVB_DUR_inf2sym, ia.seed, t, gi, 2);
             PF(P, dur_inf2sym)[i] = i2s;
             d_symp = fadd(d_inf, i2s);
             const float p_sev = prog_prob_imm(pars.rel_severe[v], in_sev_prob, in_sev_imm);
-            if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, i, 3) < (double)p_sev)) {
-                const double d = draw_dur(pars, CVB_DUR_mild2rec, ia.seed, t, i, 4);
+            if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, gi, 3) < (double)p_sev)) {
+                const double d = draw_dur(pars, CVB_DUR_mild2rec, ia.seed, t, gi, 4);
                 d_rec = (float)dadd((double)d_symp, d);
                 dur_disease = (float)dadd((double)fadd(e2i, i2s), d);
                 symp_class = 1;
             } else {
                 is_sev_f = true;
                 symp_class = 2;
-                const float s2s = (float)draw_dur(pars, CVB_DUR_sym2sev, ia.seed, t, i, 4);
+                const float s2s = (float)draw_dur(pars, CVB_DUR_sym2sev, ia.seed, t, gi, 4);
                 PF(P, dur_sym2sev)[i] = s2s;
                 d_sev = fadd(d_symp, s2s);
                 const float p_crit = prog_prob_fac(pars.rel_crit[v], in_crit_prob, hosp_max ? pars.no_hosp_factor : 1.0f);
-                if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, i, 5) < (double)p_crit)) {
-                    const double d = draw_dur(pars, CVB_DUR_sev2rec, ia.seed, t, i, 6);
+                if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, gi, 5) < (double)p_crit)) {
+                    const double d = draw_dur(pars, CVB_DUR_sev2rec, ia.seed, t, gi, 6);
                     d_rec = (float)dadd((double)d_sev, d);
                     dur_disease = (float)dadd((double)fadd(fadd(e2i, i2s), s2s), d);
                 } else {
-                    const float s2c = (float)draw_dur(pars, CVB_DUR_sev2crit, ia.seed, t, i, 6);
+                    const float s2c = (float)draw_dur(pars, CVB_DUR_sev2crit, ia.seed, t, gi, 6);
                     PF(P, dur_sev2crit)[i] = s2c;
                     d_crit = fadd(d_sev, s2c);
                     const float p_death = prog_prob_fac(pars.rel_death[v], in_death_prob, icu_max ? pars.no_icu_factor : 1.0f);
                     const float pre = fadd(fadd(fadd(e2i, i2s), s2s), s2c);
-                    if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, i, 7) < (double)p_death)) {
-                        const double d = draw_dur(pars, CVB_DUR_crit2rec, ia.seed, t, i, 8);
+                    if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, gi, 7) < (double)p_death)) {
+                        const double d = draw_dur(pars, CVB_DUR_crit2rec, ia.seed, t, gi, 8);
                         d_rec = (float)dadd((double)d_crit, d);
                         dur_disease = (float)dadd((double)pre, d);
                     } else {
-                        const double d = draw_dur(pars, CVB_DUR_crit2die, ia.seed, t, i, 8);
+                        const double d = draw_dur(pars, CVB_DUR_crit2die, ia.seed, t, gi, 8);
                         PF(P, date_dead)[i] = (float)dadd((double)d_crit, d);
                         dur_disease = (float)dadd((double)pre, d);
                         d_rec = nanf32();
@@ -169,7 +182,7 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
             if (in_nab > 0.0f) {
                 PF(P, peak_nab)[i] = fmul(in_peak, pars.nab_boost);
             } else {
-                double x = dist_from_normal(pars.nab_init, keyed_normal(ia.seed, P_INFECT, 0, t, i, 9));
+                double x = dist_from_normal(pars.nab_init, keyed_normal(ia.seed, P_INFECT, 0, t, gi, 9));
                 double level = pow(2.0, x);
                 double scale = symp_class == 0 ? pars.rel_imm_asymp : (symp_class == 1 ? pars.rel_imm_mild : pars.rel_imm_severe);
                 PF(P, peak_nab)[i] = (float)dmul(dmul(level, scale), pars.nab_norm);
@@ -220,13 +233,15 @@ __global__ void claim_list_kernel(const int32_t* __restrict__ inds, int64_t n_in
 __global__ void reset_u32_kernel(unsigned int* p) { *p = 0; }
 
 static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t list_layer_code, int32_t hosp_max, int32_t icu_max,
-                         int64_t max_items, cudaStream_t st) {
+                         int64_t max_items, cudaStream_t st, bool hits = false) {
     CVB_REQUIRE(s->log.count, "infect: infection log is not bound (cvb_bind_log)");
     LayerTable L;
     if (build_layer_table(s, L, kTileEdges, 0)) return 1;          // no layer skipped: entry index == layer id
     InfectArgs ia;
     ia.seed = s->seed; ia.n = s->n; ia.t = t; ia.count_flows = count_flows; ia.list_layer_code = list_layer_code;
     ia.hosp_max = hosp_max; ia.icu_max = icu_max;
+    ia.id0 = s->partitioned ? s->id0 : 0;
+    ia.hit_src = hits ? s->hit_src : nullptr; ia.hit_key = hits ? s->hit_key : nullptr; ia.hit_cap = s->hit_cap;
     int grid = grid_for(max_items, kThreads, 148 * 4);
     infect_kernel<<<grid, kThreads, 0, st>>>(s->people, s->pars, L, ia, s->cand, s->n_cand, s->infect_key, s->beds, s->res, s->log);
     CVB_LAUNCH_CHECK();
@@ -245,7 +260,7 @@ int cvb_infect_winners(cvb_sim* s, int32_t t, cvb_stream st) {
     // the number of candidates is only known on the device: size the grid for a large outbreak and let
     // surplus CTAs exit after one load of n_cand
     int64_t guess = s->n / 64 + 1024;
-    return launch_infect(s, t, 1, CVB_LAYER_SEED, -1, -1, guess, (cudaStream_t)st);
+    return launch_infect(s, t, 1, CVB_LAYER_SEED, -1, -1, guess, (cudaStream_t)st, s->partitioned != 0);
 }
 
 int cvb_infect_list(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant, int32_t layer_code, int32_t t,

@@ -14,7 +14,7 @@ namespace cvb {
 // test_prob
 // ================================================================================================
 __global__ void __launch_bounds__(kThreads) test_prob_kernel(PeoplePtrs P, const __grid_constant__ cvb_test_prob_pars tp, uint64_t seed,
-        int64_t n, int32_t t, bool vec, unsigned long long* __restrict__ counters) {
+        int64_t n, int64_t id0, int32_t t, bool vec, unsigned long long* __restrict__ counters) {
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
@@ -51,15 +51,15 @@ __global__ void __launch_bounds__(kThreads) test_prob_kernel(PeoplePtrs P, const
             }
             const double prob = qt ? (symp ? tp.symp_quar_prob : tp.asymp_quar_prob) : (symp ? tp.symp_prob : tp.asymp_prob);
             if (!(prob > 0.0)) continue;
-            if (!(keyed_uniform(seed, P_TEST, (uint32_t)tp.index, t, i, 0) < prob)) continue;
+            if (!(keyed_uniform(seed, P_TEST, (uint32_t)tp.index, t, i + id0, 0) < prob)) continue;
             // People.test (people.py:589-617)
             ++c;
             tested[i] = 1;
             d_tested[i] = tf;
             if (!flag(w_inf, k)) continue;
-            if (!(keyed_uniform(seed, P_TEST_SENS, (uint32_t)tp.index, t, i, 0) < tp.sensitivity)) continue;
+            if (!(keyed_uniform(seed, P_TEST_SENS, (uint32_t)tp.index, t, i + id0, 0) < tp.sensitivity)) continue;
             if (!is_nan(ddiag[k])) continue;
-            if (!(keyed_uniform(seed, P_TEST_LOSS, (uint32_t)tp.index, t, i, 0) < 1.0 - tp.loss_prob)) continue;
+            if (!(keyed_uniform(seed, P_TEST_LOSS, (uint32_t)tp.index, t, i + id0, 0) < 1.0 - tp.loss_prob)) continue;
             d_diag[i] = (float)(t + tp.test_delay);
             d_pos[i] = tf;
         }
@@ -120,12 +120,13 @@ struct TraceTable {                      // the traced layers of one contact_tra
     float end_day;                       // t + quar_period (start + (quar_period - trace_time), interventions.py:1144)
     uint64_t seed;
     int64_t n, n_words;
+    int64_t id0;                         // global id of local agent 0 (agent-partitioned runs): Philox keys use global ids
     int32_t t, index;
 };
 
 __device__ __forceinline__ void trace_notify(const PeoplePtrs& P, const TraceTable& T, int q, int c) {
     const uint32_t sub = ((uint32_t)T.index << 8) | (uint32_t)T.layer_id[q];
-    if (!(keyed_uniform(T.seed, P_TRACE, sub, T.t, c, 0) < T.trace_prob[q])) return;     // binomial_filter, interventions.py:1116
+    if (!(keyed_uniform(T.seed, P_TRACE, sub, T.t, (int64_t)c + T.id0, 0) < T.trace_prob[q])) return;     // binomial_filter, interventions.py:1116
     if (PB(P, dead)[c]) return;                                        // interventions.py:1139-1141
     PB(P, known_contact)[c] = 1;
     // date_known_contact = fmin(old, notify_day): for non-negative floats and NaN the unsigned bit
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(THREADS) trace_edges_kernel(PeoplePtrs P, cons
 // vaccinate_prob
 // ================================================================================================
 __global__ void __launch_bounds__(kThreads) vaccinate_kernel(PeoplePtrs P, const __grid_constant__ cvb_vaccinate_pars vp, uint64_t seed,
-        int64_t n, int32_t t, int32_t* __restrict__ iv_doses, int32_t* __restrict__ due_day, unsigned long long* __restrict__ counters) {
+        int64_t n, int64_t id0, int32_t t, int32_t* __restrict__ iv_doses, int32_t* __restrict__ due_day, unsigned long long* __restrict__ counters) {
     __shared__ int s_cnt[2];
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(kThreads) vaccinate_kernel(PeoplePtrs P, const
         const bool vacc = vaccinated[i] != 0;
         if (vp.first_dose_today) {                                     // interventions.py:1631-1653 select_people
             const bool eligible = vp.booster ? vacc : !vacc;
-            if (eligible && vp.prob > 0.0 && keyed_uniform(seed, P_VACC, (uint32_t)vp.index, t, i, 0) < vp.prob) {
+            if (eligible && vp.prob > 0.0 && keyed_uniform(seed, P_VACC, (uint32_t)vp.index, t, i + id0, 0) < vp.prob) {
                 picked = true;
                 if (vp.interval >= 0 && t + vp.interval < vp.n_days) due_day[i] = t + vp.interval;
             }
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(kThreads) vaccinate_kernel(PeoplePtrs P, const
         if (PF(P, nab)[i] > 0.0f) {
             PF(P, peak_nab)[i] = fmul(PF(P, peak_nab)[i], vp.nab_boost);
         } else {
-            double x = dist_from_normal(vp.nab_init, keyed_normal(seed, P_NAB_VACC, (uint32_t)vp.index, t, i, 0));
+            double x = dist_from_normal(vp.nab_init, keyed_normal(seed, P_NAB_VACC, (uint32_t)vp.index, t, i + id0, 0));
             PF(P, peak_nab)[i] = (float)pow(2.0, x);
         }
         PI(P, t_nab_event)[i] = t;
@@ -276,41 +277,39 @@ int cvb_test_prob(cvb_sim* s, int32_t t, const cvb_test_prob_pars* tp, cvb_strea
     uintptr_t al = 0;
     for (int f = 0; f < CVB_N_FIELDS; ++f) al |= (uintptr_t)s->people.f[f];
     test_prob_kernel<<<grid_for((s->n + kAPT - 1) / kAPT, kThreads, 148 * 8), kThreads, 0, (cudaStream_t)st>>>(
-        s->people, *tp, s->seed, s->n, t, (al & 15) == 0 && s->n % 4 == 0, s->res.counters);
+        s->people, *tp, s->seed, s->n, s->partitioned ? s->id0 : 0, t, (al & 15) == 0 && s->n % 4 == 0, s->res.counters);
     CVB_LAUNCH_CHECK();
     return 0;
 }
 
-int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_stream st_) {
-    cudaStream_t st = (cudaStream_t)st_;
-    CVB_REQUIRE(s && tr && s->pars_set, "cvb_contact_tracing: handle not ready");
-    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_contact_tracing: day %d outside [0,%d)", t, s->npts);
+// today's cases -> bitmap (+ compact list): phase one of contact tracing
+static int trace_select(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cudaStream_t st) {
     uintptr_t al = (uintptr_t)s->people.f[CVB_F_date_diagnosed];
     CVB_CHECK(cudaMemsetAsync(s->n_case_list, 0, sizeof(unsigned int), st));
     trace_select_kernel<<<grid_for((s->n + 3) / 4, kThreads, 148 * 8), kThreads, 0, st>>>(s->people, s->n, t, tr->presumptive,
-                                                                                    (al & 15) == 0, s->case_bits, s->case_list, s->n_case_list);
+        (al & 15) == 0, s->partitioned ? s->case_bits_local : s->case_bits, s->case_list, s->n_case_list);
     CVB_LAUNCH_CHECK();
-    const uint32_t adj_mask = (s->adj && s->adj_layer_mask) ? s->adj_layer_mask : 0u;
-    TraceTable T;
+    return 0;
+}
+
+// every traced layer gets a table entry (probability, notification day, ring slot); only the layers that are NOT
+// covered by an adjacency (`adj_mask`) contribute tiles to the dense streaming pass
+static int build_trace_table(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, uint32_t adj_mask, int tile_edges, TraceTable& T,
+                             int64_t& acc, bool& any_sparse) {
     memset(&T, 0, sizeof(T));
     T.seed = s->seed; T.n = s->n; T.n_words = (s->n + 31) / 32; T.t = t; T.index = tr->index;
+    T.id0 = s->partitioned ? s->id0 : 0;
     T.end_day = (float)(t + tr->quar_period);
-    const size_t bitmap_bytes = (size_t)T.n_words * sizeof(unsigned int);
-    const bool smem_bits = bitmap_bytes <= 200 * 1024;
-    const int threads = smem_bits ? 1024 : 256;
-    const int tile_edges = threads * kEdgesPerThread;
-    // every traced layer gets a table entry (probability, notification day, ring slot); only the layers that are
-    // NOT covered by the adjacency contribute tiles to the dense streaming pass
-    int64_t acc = 0;
+    acc = 0;
+    any_sparse = false;
     int q = 0;
-    bool any_sparse = false;
     for (int l = 0; l < CVB_MAX_LAYERS; ++l) T.entry_of_layer[l] = -1;
     for (int l = 0; l < s->pars.n_layers; ++l) {
-        if (!(tr->trace_prob[l] > 0.0) || s->layers[l].n_edges == 0) continue;
+        const bool sparse = (adj_mask >> l) & 1u;
+        if (!(tr->trace_prob[l] > 0.0) || (s->layers[l].n_edges == 0 && !sparse)) continue;
         CVB_REQUIRE(tr->trace_time[l] >= 0 && tr->trace_time[l] < s->quar_horizon,
                     "cvb_contact_tracing: trace_time %d needs cvb_set_quar_horizon(%d)", tr->trace_time[l], tr->trace_time[l] + 1);
         const int notify = t + tr->trace_time[l];
-        const bool sparse = (adj_mask >> l) & 1u;
         any_sparse |= sparse;
         T.p1[q] = s->layers[l].p1; T.p2[q] = s->layers[l].p2; T.n_edges[q] = sparse ? 0 : s->layers[l].n_edges;
         T.quar_slot[q] = (int*)(s->quar_ring + (int64_t)(notify % s->quar_horizon) * s->n);
@@ -324,6 +323,47 @@ int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_str
     }
     T.n_entries = q;
     for (int j = q; j <= CVB_MAX_LAYERS; ++j) T.tile_start[j] = acc;
+    return 0;
+}
+
+int cvb_trace_select_cases(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_stream st) {
+    CVB_REQUIRE(s && tr && s->pars_set, "cvb_trace_select_cases: handle not ready");
+    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_trace_select_cases: day %d outside [0,%d)", t, s->npts);
+    return trace_select(s, t, tr, (cudaStream_t)st);
+}
+
+int cvb_trace_notify_contacts(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_stream st_) {
+    cudaStream_t st = (cudaStream_t)st_;
+    CVB_REQUIRE(s && tr && s->pars_set, "cvb_trace_notify_contacts: handle not ready");
+    CVB_REQUIRE(s->partitioned, "cvb_trace_notify_contacts: only for agent-partitioned handles (use cvb_contact_tracing)");
+    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_trace_notify_contacts: day %d outside [0,%d)", t, s->npts);
+    CVB_REQUIRE(s->padj_ptr && s->case_bits_global, "cvb_trace_notify_contacts: partitioned adjacency / case bitmap not bound");
+    TraceTable T;
+    int64_t acc;
+    bool any_sparse;
+    if (build_trace_table(s, t, tr, s->padj_layer_mask, kTileEdges, T, acc, any_sparse)) return 1;
+    CVB_REQUIRE(acc == 0, "cvb_trace_notify_contacts: a traced layer is not covered by the partitioned adjacency");
+    if (!any_sparse) return 0;
+    if (cvb::list_from_bits(s, s->case_bits_global, s->n_slots / 32, st)) return 1;
+    trace_sparse_kernel<<<148 * 2, kThreads, 0, st>>>(s->people, T, s->padj_ptr, s->padj, s->glist, s->n_glist, s->padj_layer_mask);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
+
+int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_stream st_) {
+    cudaStream_t st = (cudaStream_t)st_;
+    CVB_REQUIRE(s && tr && s->pars_set, "cvb_contact_tracing: handle not ready");
+    CVB_REQUIRE(!s->partitioned, "cvb_contact_tracing: agent-partitioned handles trace in two phases (cvb_trace_select_cases, all-gather, cvb_trace_notify_contacts)");
+    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_contact_tracing: day %d outside [0,%d)", t, s->npts);
+    if (trace_select(s, t, tr, st)) return 1;
+    const uint32_t adj_mask = (s->adj && s->adj_layer_mask) ? s->adj_layer_mask : 0u;
+    const size_t bitmap_bytes = (size_t)((s->n + 31) / 32) * sizeof(unsigned int);
+    const bool smem_bits = bitmap_bytes <= 200 * 1024;
+    const int threads = smem_bits ? 1024 : 256;
+    TraceTable T;
+    int64_t acc;
+    bool any_sparse;
+    if (build_trace_table(s, t, tr, adj_mask, threads * kEdgesPerThread, T, acc, any_sparse)) return 1;
     if (any_sparse) {
         trace_sparse_kernel<<<148 * 2, kThreads, 0, st>>>(s->people, T, s->adj_ptr, s->adj, s->case_list, s->n_case_list, adj_mask);
         CVB_LAUNCH_CHECK();
@@ -351,7 +391,7 @@ int cvb_vaccinate_prob(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* vp, int3
     CVB_REQUIRE(s && vp && iv_doses && due_day && s->res.counters, "cvb_vaccinate_prob: bad argument");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_vaccinate_prob: day %d outside [0,%d)", t, s->npts);
     CVB_REQUIRE(vp->vaccine_index >= 0 && vp->vaccine_index < CVB_MAX_VACCINES, "cvb_vaccinate_prob: vaccine index out of range");
-    vaccinate_kernel<<<grid_for(s->n), kThreads, 0, (cudaStream_t)st>>>(s->people, *vp, s->seed, s->n, t, iv_doses, due_day, s->res.counters);
+    vaccinate_kernel<<<grid_for(s->n), kThreads, 0, (cudaStream_t)st>>>(s->people, *vp, s->seed, s->n, s->partitioned ? s->id0 : 0, t, iv_doses, due_day, s->res.counters);
     CVB_LAUNCH_CHECK();
     return 0;
 }

@@ -184,7 +184,8 @@ enum { POST_DIAGNOSES = 0, POST_QUARANTINED, POST_ISOLATED, POST_NK };
 template <bool DO_POST, bool DO_PREP>
 __global__ void __launch_bounds__(kThreads) post_prepare_kernel(PeoplePtrs P, const __grid_constant__ cvb_pars pars, int64_t n, int32_t t, bool vec,
         float* __restrict__ quar_slot, unsigned long long* __restrict__ counters, TransRecords rec, unsigned int* __restrict__ inf_bits,
-        int32_t* __restrict__ trans_list, unsigned int* __restrict__ n_trans, unsigned int* __restrict__ n_cand) {
+        int32_t* __restrict__ trans_list, unsigned int* __restrict__ n_trans, unsigned int* __restrict__ n_cand,
+        uint8_t* __restrict__ codes, const float* __restrict__ base_trans, unsigned int* __restrict__ part_flags) {
     __shared__ int s_cnt[POST_NK];
     if (threadIdx.x < POST_NK) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -227,6 +228,7 @@ __global__ void __launch_bounds__(kThreads) post_prepare_kernel(PeoplePtrs P, co
             }
         }
         unsigned inf_nibble = 0;
+        uint32_t code_word = 0;                                     // partitioned form: the four agents' transmit codes
 #pragma unroll
         for (int k = 0; k < kAPT; ++k) {
             const int64_t i = i0 + k;
@@ -273,9 +275,11 @@ __global__ void __launch_bounds__(kThreads) post_prepare_kernel(PeoplePtrs P, co
                     var = (int)iv4[k];
                     if (!(var >= 0 && var < nv)) { inf = false; var = 0; }      // infectious_variant == v is never true (sim.py:629)
                 }
+                bool early = false;
                 if (inf) {
                     rt = rt4[k];
-                    vl = viral_load(t, dinf[k], drec[k], ddead[k], pars.frac_time, pars.load_ratio, pars.high_cap);
+                    early = viral_load_early(t, dinf[k], drec[k], ddead[k], pars.frac_time, pars.high_cap);
+                    vl = viral_load_value(early, pars.frac_time, pars.load_ratio);
                 }
                 const bool symp = flag(w_symp, k);
                 const float rs = sus ? rs4[k] : 0.0f;
@@ -294,9 +298,21 @@ __global__ void __launch_bounds__(kThreads) post_prepare_kernel(PeoplePtrs P, co
                 }
                 if (any_trans) {
                     inf_nibble |= 1u << k;
-                    trans_list[warp_append32(n_trans)] = (int32_t)i;       // compact (unordered) list of today's transmitters
+                    if (codes) {
+                        // another GPU rebuilds this agent's transmissibility from its initial rel_trans and this byte
+                        const float base = base_trans[i];
+                        const bool redux = rt != base;
+                        if (redux && rt != fmul(base, pars.trans_redux)) atomicAdd(part_flags + 1, 1u);
+                        code_word |= (uint32_t)transmit_code(var, symp, iso, quar, early, redux) << (8 * k);
+                    } else {
+                        trans_list[warp_append32(n_trans)] = (int32_t)i;   // compact (unordered) list of today's transmitters
+                    }
                 }
             }
+        }
+        if (DO_PREP && codes) {
+            if (vec && i0 + 4 <= n) *reinterpret_cast<uint32_t*>(codes + i0) = code_word;
+            else for (int k = 0; k < kAPT && i0 + k < n; ++k) codes[i0 + k] = (uint8_t)(code_word >> (8 * k));
         }
         if (DO_PREP) {
             // bitmap of agents that can transmit in at least one layer: lane L holds bits 4(L&7).. of word (L>>3)
@@ -480,7 +496,8 @@ static int launch_post_prepare(cvb_sim* s, int32_t t, cudaStream_t st) {
     const int slot = t % s->quar_horizon;
     if (DO_PREP) CVB_CHECK(cudaMemsetAsync(s->n_trans, 0, sizeof(unsigned int), st));
     post_prepare_kernel<DO_POST, DO_PREP><<<grid_agents(s->n), kThreads, 0, st>>>(s->people, s->pars, s->n, t, vector_ok(s),
-        s->quar_ring + (int64_t)slot * s->n, s->res.counters, s->rec, s->inf_bits, s->trans_list, s->n_trans, s->n_cand);
+        s->quar_ring + (int64_t)slot * s->n, s->res.counters, s->rec, s->inf_bits, s->trans_list, s->n_trans, s->n_cand,
+        s->partitioned ? s->codes_local : nullptr, s->partitioned ? s->rel_trans_global + s->id0 : nullptr, s->part_flags);
     CVB_LAUNCH_CHECK();
     return 0;
 }

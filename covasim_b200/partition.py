@@ -1,0 +1,180 @@
+'''
+Agent partition of ONE large simulation over several GPUs (BASELINE config 4).
+
+The reference runs a simulation in one process on one core (sim.py:558-685).  Here a population too large or
+too slow for one GPU is split into contiguous agent ranges, one per rank.  Each rank
+
+* holds the People arrays of its own agents only;
+* evaluates the transmissions (and contact-tracing notifications) whose TARGET it owns, from an adjacency
+  with one row per GLOBAL source holding the edges that end in a local target;
+* needs one byte per agent per day about the rest of the population (``transmit_code``: variant, symptomatic,
+  isolated, quarantined, early viral load, breakthrough), exchanged with ONE fixed-size all-gather
+  (``ncclAllGather`` over NVLink through torch.distributed), and a second all-gather of a 1-bit-per-agent
+  case bitmap on days a contact_tracing intervention is active.
+
+Because every random draw is a pure function of (seed, purpose, day, GLOBAL agent or edge id), a partitioned
+run reproduces the single-GPU run of the same simulation bit for bit (tests/test_gpu_partition.py), for any
+number of ranks.
+
+Two communicators implement the exchanges: ``DistComm`` (torch.distributed: NCCL on GPUs, gloo in the CPU
+tests of the host logic) and ``LocalComm`` (several ranks of one process on ONE GPU, one thread per rank --
+how the single-GPU test box exercises the partitioned kernels).
+'''
+import threading
+
+import numpy as np
+import torch
+
+__all__ = ['plan', 'build_partition_adjacency', 'DistComm', 'LocalComm', 'run_local']
+
+
+def plan(n_global, world):
+    ''' Chunk size (a multiple of 32) and the agent range [lo, hi) of every rank; every rank but the last owns exactly ``chunk`` agents '''
+    n_global, world = int(n_global), int(world)
+    chunk = -(-n_global // world)
+    chunk = -(-chunk // 32) * 32
+    ranges = [(min(r * chunk, n_global), min((r + 1) * chunk, n_global)) for r in range(world)]
+    if any(hi <= lo for lo, hi in ranges):
+        raise ValueError(f'{n_global} agents cannot be split over {world} ranks in chunks of {chunk}: a rank would own no agents')
+    return chunk, ranges
+
+
+def build_partition_adjacency(layers, layer_ids, lo, hi, n_slots, device):
+    '''
+    Rows = GLOBAL source id (``n_slots + 1`` row pointers), entries = the edges that end in a LOCAL target
+    ``lo <= target < hi`` as int32[M, 4] = (target - lo, edge index within its layer, (layer << 1) | direction,
+    beta bits) -- the entry format of ``cvb_bind_adjacency`` (direction 0: source is the edge's p1).
+    ``layers`` is a list of dicts of 1-D tensors / arrays (p1, p2, beta) holding the WHOLE population's edges.
+    Pure torch, device independent (the CPU tests check it against a brute-force loop).
+    '''
+    dev = torch.device(device)
+    src, tgt, eid, meta, wts = [], [], [], [], []
+    for l, layer in zip(layer_ids, layers):
+        p1 = torch.as_tensor(layer['p1']).to(dev, torch.int64)
+        p2 = torch.as_tensor(layer['p2']).to(dev, torch.int64)
+        beta = torch.as_tensor(layer['beta']).to(dev, torch.float32)
+        if p1.numel() >= 2 ** 31:
+            raise ValueError('a layer with 2^31 or more edges cannot be indexed by the adjacency')
+        e = torch.arange(p1.numel(), dtype=torch.int64, device=dev)
+        for d, (a, b) in enumerate(((p1, p2), (p2, p1))):
+            keep = (b >= lo) & (b < hi)
+            src.append(a[keep])
+            tgt.append(b[keep] - lo)
+            eid.append(e[keep])
+            meta.append(torch.full((int(keep.sum()),), (l << 1) | d, dtype=torch.int64, device=dev))
+            wts.append(beta[keep])
+    src = torch.cat(src) if src else torch.zeros(0, dtype=torch.int64, device=dev)
+    order = torch.sort(src, stable=True).indices
+    M = int(src.numel())
+    adj = torch.empty((max(M, 1), 4), dtype=torch.int32, device=dev)
+    if M:
+        adj[:M, 0] = torch.cat(tgt)[order].to(torch.int32)
+        adj[:M, 1] = torch.cat(eid)[order].to(torch.int32)
+        adj[:M, 2] = torch.cat(meta)[order].to(torch.int32)
+        adj[:M, 3] = torch.cat(wts)[order].view(torch.int32)
+    ptr = torch.zeros(n_slots + 1, dtype=torch.int64, device=dev)
+    ptr[1:] = torch.cumsum(torch.bincount(src, minlength=n_slots), 0)
+    return ptr, adj, M
+
+
+class DistComm:
+    ''' The exchanges of a partitioned run over torch.distributed (one process per GPU) '''
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError('partition=True needs an initialised torch.distributed process group (torchrun)')
+        self.dist = dist
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+
+    def all_gather(self, out, inp):
+        ''' out[r * len(inp) : (r + 1) * len(inp)] = rank r's inp (one ncclAllGather; stream-ordered, no host sync) '''
+        self.dist.all_gather_into_tensor(out, inp, group=self.group)
+
+    def all_reduce_sum(self, t):
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+
+    def gather_objects(self, obj):
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj, group=self.group)
+        return out
+
+
+class _LocalShared:
+    def __init__(self, world):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+
+
+class LocalComm:
+    '''
+    Several ranks inside one process on one GPU (one thread per rank, see ``run_local``).  Every rank issues its
+    kernels on the same (legacy default) stream, so copies issued between two thread barriers are ordered against
+    every rank's kernels exactly as an all-gather on that stream would be.
+    '''
+
+    def __init__(self, shared, rank):
+        self.shared, self.rank, self.world = shared, rank, shared.world
+
+    @staticmethod
+    def make(world):
+        shared = _LocalShared(world)
+        return [LocalComm(shared, r) for r in range(world)]
+
+    def _exchange(self, value):
+        s = self.shared
+        s.slots[self.rank] = value
+        s.barrier.wait()
+        vals = list(s.slots)
+        s.barrier.wait()
+        return vals
+
+    def all_gather(self, out, inp):
+        parts = self._exchange(inp)
+        n = inp.numel()
+        for r, p in enumerate(parts):
+            out[r * n:(r + 1) * n].copy_(p)
+        self.shared.barrier.wait()          # nobody overwrites its input before every rank has issued its copies
+
+    def all_reduce_sum(self, t):
+        parts = self._exchange(t.clone())
+        t.zero_()
+        for p in parts:
+            t.add_(p.to(t.device))
+        self.shared.barrier.wait()
+
+    def gather_objects(self, obj):
+        return self._exchange(obj)
+
+
+def run_local(sims, fn=None):
+    '''
+    Run the ranks of a LocalComm-partitioned simulation, one thread per rank; ``fn(sim)`` defaults to
+    ``sim.run()``.  Returns the list of results; re-raises the first exception of any rank.
+    '''
+    fn = fn or (lambda sim: sim.run())
+    out, errs = [None] * len(sims), []
+
+    def work(k):
+        try:
+            if torch.cuda.is_available():
+                torch.cuda.set_device(sims[k].device)
+            out[k] = fn(sims[k])
+        except BaseException as e:          # noqa: BLE001 -- reported to the caller below
+            errs.append(e)
+            try:
+                sims[k]._comm.shared.barrier.abort()
+            except Exception:
+                pass
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(len(sims))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    if errs:
+        real = [e for e in errs if not isinstance(e, threading.BrokenBarrierError)]
+        raise (real or errs)[0]
+    return out

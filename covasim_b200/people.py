@@ -25,14 +25,17 @@ _TORCH_DTYPE = {np.dtype(np.bool_): torch.bool, np.dtype(np.int32): torch.int32,
 
 class People:
 
-    def __init__(self, pars, device, uid=None, age=None, sex=None, contacts=None):
+    def __init__(self, pars, device, uid=None, age=None, sex=None, contacts=None, local_range=None):
         object.__setattr__(self, '_arrays', {})
         self.pars = pars
         self.device = torch.device(device)
         self.t = 0
-        n = int(pars['pop_size'])
+        # agent-partitioned runs (partition.py): this object holds the agents [id0, id0 + n) of pop_size
+        lo, hi = (0, int(pars['pop_size'])) if local_range is None else (int(local_range[0]), int(local_range[1]))
+        n = hi - lo
         nv = int(pars['n_variants'])
-        self.n, self.nv = n, nv
+        self.n, self.nv, self.id0, self.n_global = n, nv, lo, int(pars['pop_size'])
+        self.rel_trans_global = None
         self._sim = None
         self.infection_log_cap = 0
         A = self._arrays
@@ -40,17 +43,23 @@ class People:
             dt = _TORCH_DTYPE[np.dtype(cvd.field_dtype(name))]
             shape = (nv, n) if cvd.field_is_2d(name) else (n,)
             if name == 'uid':
-                A[name] = torch.arange(n, dtype=torch.int32, device=self.device)
+                A[name] = torch.arange(lo, hi, dtype=torch.int32, device=self.device)
             elif name in cvd.states:
                 A[name] = torch.full(shape, name in ('susceptible', 'naive'), dtype=dt, device=self.device)
             elif dt == torch.float32 and name not in cvd.imm_states and name not in ('peak_nab', 'nab'):
                 A[name] = torch.full(shape, float('nan'), dtype=dt, device=self.device)
             else:
                 A[name] = torch.zeros(shape, dtype=dt, device=self.device)
+        self._age_global = None
         if age is not None:
+            age = np.asarray(age)
+            if local_range is not None and len(age) == self.n_global:
+                self._age_global = age                  # prognoses are drawn for the whole population, then sliced
+                age = age[lo:hi]
             self['age'] = age
         if sex is not None:
-            self['sex'] = sex
+            sex = np.asarray(sex)
+            self['sex'] = sex[lo:hi] if (local_range is not None and len(sex) == self.n_global) else sex
         self.contacts = Contacts()
         if contacts is not None:
             for lk, layer in contacts.items():
@@ -129,20 +138,26 @@ class People:
         pars = self.pars
         rng.set_seed(pars['rand_seed'])
         progs = pars['prognoses']
-        age = self.to_numpy('age')
+        part = self._age_global is not None
+        age = np.asarray(self._age_global, dtype=np.float32) if part else self.to_numpy('age')      # the People array is float32
         inds = np.digitize(age, progs['age_cutoffs']) - 1
-        self['symp_prob'] = progs['symp_probs'][inds]
-        self['severe_prob'] = progs['severe_probs'][inds] * progs['comorbidities'][inds]
-        self['crit_prob'] = progs['crit_probs'][inds]
-        self['death_prob'] = progs['death_probs'][inds]
-        self['rel_sus'] = progs['sus_ORs'][inds]
+        loc = slice(self.id0, self.id0 + self.n) if part else slice(None)
+        self['symp_prob'] = progs['symp_probs'][inds][loc]
+        self['severe_prob'] = (progs['severe_probs'][inds] * progs['comorbidities'][inds])[loc]
+        self['crit_prob'] = progs['crit_probs'][inds][loc]
+        self['death_prob'] = progs['death_probs'][inds][loc]
+        self['rel_sus'] = progs['sus_ORs'][inds][loc]
         bd = pars['beta_dist']
         if bd['dist'] != 'neg_binomial':
             raise NotImplementedError('beta_dist must be neg_binomial')
         step = bd.get('step', 1)
         p = bd['par2'] / (bd['par1'] / step + bd['par2'])                                    # reference utils.py:409-426
         draws = rng.np_.negative_binomial(n=bd['par2'], p=p, size=len(inds)) * step
-        self['rel_trans'] = progs['trans_ORs'][inds] * draws
+        rel_trans = progs['trans_ORs'][inds] * draws
+        self['rel_trans'] = rel_trans[loc]
+        if part:            # every rank keeps the whole population's initial transmissibility (4 B per agent)
+            self.rel_trans_global = torch.as_tensor(np.asarray(rel_trans, dtype=np.float32), device=self.device)
+            self._age_global = None
 
     # ---- events ---------------------------------------------------------------------------------
     def infect(self, inds, hosp_max=None, icu_max=None, source=None, layer=None, variant=0, count_flows=True):
@@ -161,6 +176,9 @@ class People:
                                  icu_max=bool(icu_max) if not isinstance(icu_max, str) else False, source=source, layer=layer,
                                  variant=variant, count_flows=count_flows)
         inds = torch.as_tensor(inds, dtype=torch.int32, device=self.device).contiguous()
+        if sim._comm is not None:                      # partitioned: `inds` are global ids; this rank infects the ones it owns
+            inds = inds[(inds >= self.id0) & (inds < self.id0 + self.n)] - self.id0
+            inds = inds.contiguous()
         if len(inds) == 0:
             return inds
         code = {'seed_infection': _capi.LAYER_SEED, 'importation': _capi.LAYER_IMPORT}.get(layer, _capi.LAYER_IMPORT)

@@ -100,6 +100,28 @@ int cvb_bind_layer(cvb_sim* s, int32_t layer, int32_t* p1, int32_t* p2, float* b
  * those layers (same results as the dense passes: same Philox keys, same winner keys) and stream the rest
  * (dynamic layers) densely.  Pass layer_mask = 0 to unbind. */
 int cvb_bind_adjacency(cvb_sim* s, const int64_t* adj_ptr, const void* adj, int64_t n_entries, uint32_t layer_mask);
+/* ------------------------------------------------------------------------------------------------
+ * Agent partition of ONE large simulation over several GPUs (BASELINE config 4).
+ * Rank r owns the agents [r*chunk, r*chunk + n_agents) of n_global (chunk a multiple of 32; every rank but the
+ * last owns exactly `chunk` agents) and evaluates the transmissions and contact notifications whose TARGET it
+ * owns.  Per-agent Philox keys and logged ids are GLOBAL ids, so results are bit-identical to the single-GPU run.
+ * Per day the HOST performs two fixed-size exchanges (ncclAllGather through torch.distributed):
+ *   codes_local  uint8[chunk]     written by cvb_post_and_prepare   -> codes_global  uint8[world*chunk]   read by cvb_edge_pass
+ *   case_bits_local u32[chunk/32] written by cvb_trace_select_cases -> case_bits_global u32[world*chunk/32] read by cvb_trace_notify_contacts
+ * One code byte (variant, symptomatic, isolated, quarantined, early viral load, breakthrough) plus the replicated
+ * initial rel_trans float32[n_global] is all a GPU needs to rebuild a remote source's per-layer transmissibility.
+ * hit_capacity bounds the successful transmissions a rank can record per day (>= n_agents is used if smaller).
+ * ---------------------------------------------------------------------------------------------- */
+int cvb_set_partition(cvb_sim* s, int64_t id0, int64_t n_global, int64_t chunk, int32_t world, const float* rel_trans_global,
+                      uint8_t* codes_local, const uint8_t* codes_global, uint32_t* case_bits_local, const uint32_t* case_bits_global,
+                      int64_t hit_capacity);
+/* Adjacency of a partitioned handle: rows adj_ptr[0 .. world*chunk] are indexed by the GLOBAL id of the source; the
+ * 16-byte entries are those of cvb_bind_adjacency with `neighbour` = LOCAL index of the target */
+int cvb_bind_partition_adjacency(cvb_sim* s, const int64_t* adj_ptr, const void* adj, int64_t n_entries, uint32_t layer_mask);
+/* host int64[2] = {transmissions dropped because hit_capacity was too small, agents whose rel_trans the code cannot
+ * express}; both must be 0 for a valid run (synchronises) */
+int cvb_partition_status(cvb_sim* s, int64_t* host_out2);
+
 /* Per-day result tables: counters int64[npts][CVB_N_COUNTERS], vcounters int64[npts][n_variants][CVB_N_VCOUNTERS],
  * sums double[npts][4] = {sum nab over alive, sum sus_imm, sum symp_imm, unused} (reference sim.py:652-674) */
 int cvb_bind_results(cvb_sim* s, int64_t* counters, int64_t* vcounters, double* sums);
@@ -192,6 +214,10 @@ typedef struct cvb_trace_pars {            /* interventions.py:984-1145 */
 /* Marks contacts of today's cases, sets known_contact/date_known_contact and queues quarantine.
  * Requests with trace_time 0 go to pend_quar_end; later ones to the per-day ring. */
 int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* host_pars, cvb_stream st);
+/* The same in two phases for agent-partitioned handles: select today's local cases into case_bits_local; (the host
+ * all-gathers the bitmap); notify the LOCAL contacts of every GLOBAL case */
+int cvb_trace_select_cases(cvb_sim* s, int32_t t, const cvb_trace_pars* host_pars, cvb_stream st);
+int cvb_trace_notify_contacts(cvb_sim* s, int32_t t, const cvb_trace_pars* host_pars, cvb_stream st);
 
 typedef struct cvb_vaccinate_pars {        /* interventions.py:1257-1662 */
     double prob;

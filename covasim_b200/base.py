@@ -133,7 +133,7 @@ class Layer:
             raise RuntimeError('Layer.find_contacts needs a layer attached to a sim')
         sim = self._sim
         inds = torch.as_tensor(inds, dtype=torch.int64, device=self.device).contiguous()
-        out = torch.empty(sim.n, dtype=torch.int32, device=self.device)
+        out = torch.empty(sim.n_local, dtype=torch.int32, device=self.device)
         n_out = C.c_int64(0)
         _capi.call('cvb_find_contacts', sim._handle, self['p1'].data_ptr(), self['p2'].data_ptr(), len(self), inds.data_ptr(), len(inds),
                    out.data_ptr(), C.byref(n_out), sim._stream_ptr)

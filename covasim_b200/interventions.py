@@ -183,6 +183,11 @@ class contact_tracing(Intervention):
         t = sim.t
         if t < self.start_day or (self.end_day is not None and t > self.end_day):
             return
+        if sim._comm is not None:          # agent-partitioned: local cases -> all-gathered bitmap -> local contacts of every case
+            _capi.call('cvb_trace_select_cases', sim._handle, t, C.byref(self._c), sim._stream_ptr)
+            sim._exchange_cases()
+            _capi.call('cvb_trace_notify_contacts', sim._handle, t, C.byref(self._c), sim._stream_ptr)
+            return
         if sim._adj_dirty:
             sim._build_adjacency()
         _capi.call('cvb_contact_tracing', sim._handle, t, C.byref(self._c), sim._stream_ptr)
@@ -245,8 +250,8 @@ class vaccinate_prob(Intervention):
         self.days = process_days(sim, self.days)
         self.iindex = sim.intervention_index(self)
         dev = sim.people.device
-        self.doses = torch.zeros(sim.n, dtype=torch.int32, device=dev)              # doses given by *this* intervention
-        self.due_day = torch.full((sim.n,), -1, dtype=torch.int32, device=dev)     # device form of second_dose_days
+        self.doses = torch.zeros(sim.n_local, dtype=torch.int32, device=dev)              # doses given by *this* intervention
+        self.due_day = torch.full((sim.n_local,), -1, dtype=torch.int32, device=dev)     # device form of second_dose_days
         self._due_days = set()
         self._second = {}                          # replay mode: day -> indices due for their second dose
         self._c = _capi.cvb_vaccinate_pars(prob=float(self.prob), nab_init=_capi.dist_struct(self.p['nab_init']), nab_boost=float(self.p['nab_boost']),

@@ -33,7 +33,8 @@ f32 = np.float32
 
 class Sim:
 
-    def __init__(self, pars=None, popdict=None, label=None, device=None, rng='philox', pop_exact=None, use_adjacency=True, **kwargs):
+    def __init__(self, pars=None, popdict=None, label=None, device=None, rng='philox', pop_exact=None, use_adjacency=True, partition=None,
+                 hit_capacity=0, **kwargs):
         kw = dict(pars or {})
         kw.update(kwargs)
         for alias, key in (('n_agents', 'pop_size'), ('init_infected', 'pop_infected')):       # reference base.py:266-273
@@ -70,6 +71,14 @@ class Sim:
         self.use_adjacency = use_adjacency   # False: stream every layer densely each day (the reference's access pattern)
         self._adj = None
         self._adj_dirty = False
+        # agent partition over several GPUs (partition.py): None = the whole population on this GPU; True = one rank of
+        # the torch.distributed world; or a communicator object (partition.DistComm / partition.LocalComm)
+        self._partition = partition
+        self._comm = None
+        self._hit_capacity = int(hit_capacity)
+        self._part_bufs = None
+        if partition is not None and partition is not False and rng != 'philox':
+            raise NotImplementedError('agent partitioning needs the native RNG (rng="philox"): replay mode follows the reference\'s sequential streams')
 
     # ---- dict-like parameter access (reference base.py:63-114) -----------------------------------
     def __getitem__(self, key):
@@ -98,6 +107,15 @@ class Sim:
     @property
     def n(self):
         return int(self.pars['pop_size'])
+
+    @property
+    def n_local(self):
+        ''' Agents held on this GPU: all of them unless the simulation is agent-partitioned '''
+        return self.people.n if self.people is not None else self.n
+
+    @property
+    def id0(self):
+        return self.people.id0 if self.people is not None else 0
 
     @property
     def npts(self):
@@ -246,7 +264,22 @@ class Sim:
         if pop is None:
             exact = self.pop_exact if self.pop_exact is not None else (pars['pop_size'] <= 200_000)
             pop = cvpop.make_randpop(pars, self.rng, exact=exact)
-        self.people = People(pars, self.device, age=pop['age'], sex=pop['sex'], contacts=pop['contacts'])
+        if self._partition is not None and self._partition is not False:
+            from . import partition as cvpart
+            self._comm = cvpart.DistComm() if self._partition is True else self._partition
+            if any(pars['dynam_layer'].get(lk) for lk in pop['contacts'].keys()):
+                raise NotImplementedError('dynamic layers cannot be agent-partitioned (their edges are regenerated over the whole population every day)')
+            if pars['n_beds_hosp'] is not None or pars['n_beds_icu'] is not None:
+                raise NotImplementedError('bed limits (n_beds_hosp / n_beds_icu) need a global count every day and are not built for agent-partitioned runs')
+            self._chunk, ranges = cvpart.plan(self.n, self._comm.world)
+            lo, hi = ranges[self._comm.rank]
+            # every rank builds the same population from the same seed and keeps its own agents; the edge lists stay on the
+            # host until the partitioned adjacency is built from them (_create_handle)
+            self._global_layers = pop['contacts']
+            empty = {lk: dict(p1=np.zeros(0, dtype=np.int32), p2=np.zeros(0, dtype=np.int32), beta=np.zeros(0, dtype=np.float32)) for lk in pop['contacts'].keys()}
+            self.people = People(pars, self.device, age=pop['age'], sex=pop['sex'], contacts=empty, local_range=(lo, hi))
+        else:
+            self.people = People(pars, self.device, age=pop['age'], sex=pop['sex'], contacts=pop['contacts'])
         self.popdict = None
         lkeys = self.people.layer_keys()
         if len(lkeys) > _capi.MAX_LAYERS:
@@ -260,7 +293,7 @@ class Sim:
         pars = self.pars
         npts, nv = self.npts, pars['n_variants']
         h = C.c_void_p()
-        _capi.call('cvb_create', C.byref(h), self.n, nv, npts, int(pars['rand_seed']))
+        _capi.call('cvb_create', C.byref(h), self.n_local, nv, npts, int(pars['rand_seed']))
         self._handle = h
         self._stream_ptr = None            # legacy default stream; torch's current stream is the same unless changed
         dev = self.device
@@ -268,7 +301,7 @@ class Sim:
         self._vcounters = torch.zeros((npts, nv, cvd.N_VCOUNTERS), dtype=torch.int64, device=dev)
         self._sums = torch.zeros((npts, 4), dtype=torch.float64, device=dev)
         _capi.call('cvb_bind_results', h, self._counters.data_ptr(), self._vcounters.data_ptr(), self._sums.data_ptr())
-        cap = int(max(4 * self.n, 1024))
+        cap = int(max(4 * self.n_local, 1024))
         self._log = dict(source=torch.empty(cap, dtype=torch.int32, device=dev), target=torch.empty(cap, dtype=torch.int32, device=dev),
                          date=torch.empty(cap, dtype=torch.int32, device=dev), layer=torch.empty(cap, dtype=torch.int8, device=dev),
                          variant=torch.empty(cap, dtype=torch.int8, device=dev), count=torch.zeros(1, dtype=torch.int64, device=dev))
@@ -282,7 +315,52 @@ class Sim:
         self._quar_horizon = 1
         self._pars_dirty = True
         self._push_pars()
-        self._build_adjacency()
+        if self._comm is not None:
+            self._bind_partition()
+        else:
+            self._build_adjacency()
+
+    def _bind_partition(self):
+        '''
+        Agent-partitioned run: exchange buffers + the adjacency of the edges that end in a local target, one row per
+        GLOBAL source (partition.build_partition_adjacency; reference Contacts base.py:1509-1876).
+        '''
+        from . import partition as cvpart
+        comm, dev, chunk = self._comm, self.device, self._chunk
+        n_slots = comm.world * chunk
+        B = dict(codes_local=torch.zeros(chunk, dtype=torch.uint8, device=dev), codes_global=torch.zeros(n_slots, dtype=torch.uint8, device=dev),
+                 case_local=torch.zeros(chunk // 32, dtype=torch.int32, device=dev), case_global=torch.zeros(n_slots // 32, dtype=torch.int32, device=dev))
+        self._part_bufs = B
+        _capi.call('cvb_set_partition', self._handle, self.id0, self.n, chunk, comm.world, self.people.rel_trans_global.data_ptr(),
+                   B['codes_local'].data_ptr(), B['codes_global'].data_ptr(), B['case_local'].data_ptr(), B['case_global'].data_ptr(),
+                   self._hit_capacity)
+        lkeys = self.people.layer_keys()
+        ids = [i for i, lk in enumerate(lkeys) if len(self._global_layers[lk]['p1']) > 0]
+        ptr, adj, M = cvpart.build_partition_adjacency([self._global_layers[lkeys[i]] for i in ids], ids, self.id0, self.id0 + self.n_local, n_slots, dev)
+        self._global_layers = None
+        mask = 0
+        for i in range(len(lkeys)):
+            mask |= 1 << i
+        self._adj = (ptr, adj)
+        self._adj_dirty = False
+        _capi.call('cvb_bind_partition_adjacency', self._handle, ptr.data_ptr(), adj.data_ptr(), M, mask)
+
+    def _exchange_codes(self):
+        ''' One fixed-size all-gather per day: every agent's 1-byte transmit code (stream-ordered, no host synchronisation) '''
+        B = self._part_bufs
+        self._comm.all_gather(B['codes_global'], B['codes_local'])
+
+    def _exchange_cases(self):
+        ''' All-gather of today's case bitmap (1 bit per agent), on days a contact_tracing intervention is active '''
+        B = self._part_bufs
+        self._comm.all_gather(B['case_global'], B['case_local'])
+
+    def _global_true(self, key):
+        ''' Global ids of the agents whose flag ``key`` is set, over all ranks (host array; rare events only) '''
+        local = (torch.nonzero(self.people[key]).flatten() + self.id0).cpu().numpy()
+        if self._comm is None:
+            return local
+        return np.concatenate(self._comm.gather_objects(local))
 
     def _build_adjacency(self):
         '''
@@ -293,6 +371,8 @@ class Sim:
         today's transmitters / cases.  Dynamic layers (regenerated every day) keep the dense streaming passes.
         '''
         self._adj_dirty = False
+        if self._comm is not None:
+            raise NotImplementedError('contact layers of an agent-partitioned simulation cannot be edited after initialisation')
         people, pars = self.people, self.pars
         if self.rng_mode == 'mt':                      # replay mode walks the edge lists in the reference's order
             self._adj = None
@@ -427,7 +507,7 @@ class Sim:
     def d2h_bytes(self):
         ''' Bytes finalize() reads device -> host (result tables + the three date arrays compute_r_eff needs) '''
         n = sum(t.numel() * t.element_size() for t in (self._counters, self._vcounters, self._sums))
-        return int(n + 3 * 4 * self.n)
+        return int(n + 3 * 4 * self.n_local)
 
     # ---- parameters -> device struct ---------------------------------------------------------------
     def _pars_fingerprint(self):
@@ -554,6 +634,8 @@ class Sim:
         if self._adj_dirty:                    # an intervention edited a layer's edge list
             self._build_adjacency()
         call('cvb_post_and_prepare', h, t, st)
+        if self._comm is not None:
+            self._exchange_codes()
         call('cvb_edge_pass', h, t, st)
         call('cvb_infect_winners', h, t, st)
         call('cvb_update_nab_count', h, t, st)
@@ -598,9 +680,23 @@ class Sim:
     def sync_results(self):
         ''' Copy the device counter tables into the host Result arrays (raw per-day values, unscaled) '''
         torch.cuda.synchronize(self.device)
-        cnt = self._counters.cpu().numpy().astype(np.float64)
-        vcnt = self._vcounters.cpu().numpy().astype(np.float64)
-        sums = self._sums.cpu().numpy()
+        counters, vcounters, sums_t = self._counters, self._vcounters, self._sums
+        if self._comm is not None:             # partitioned: every table is a sum over ranks (one collective per table, once per run)
+            status = np.zeros(2, dtype=np.int64)
+            _capi.call('cvb_partition_status', self._handle, status.ctypes.data)
+            counters, vcounters, sums_t = counters.clone(), vcounters.clone(), sums_t.clone()
+            flags = torch.as_tensor(status, device=self.device)
+            for tsr in (counters, vcounters, sums_t, flags):
+                self._comm.all_reduce_sum(tsr)
+            dropped, bad_trans = (int(x) for x in flags.cpu().numpy())
+            if dropped:
+                raise RuntimeError(f'{dropped} transmissions were dropped: raise hit_capacity (Sim(..., hit_capacity=...))')
+            if bad_trans:
+                raise RuntimeError(f'rel_trans of {bad_trans} infectious agent-days was neither its initial value nor that value times trans_redux: '
+                                   'agent-partitioned runs rebuild remote transmissibility from the initial value')
+        cnt = counters.cpu().numpy().astype(np.float64)
+        vcnt = vcounters.cpu().numpy().astype(np.float64)
+        sums = sums_t.cpu().numpy()
         R = self.results
         nv = self.pars['n_variants']
         for k, cid in cvd.COUNTER_IDS.items():
@@ -627,6 +723,9 @@ class Sim:
         L = self._log
         n = min(int(L['count'].item()), len(L['source']))
         out = {k: L[k][:n].cpu().numpy() for k in ('source', 'target', 'date', 'layer', 'variant')}
+        if self._comm is not None:             # every rank logs the infections of its own agents (global ids)
+            parts = self._comm.gather_objects(out)
+            out = {k: np.concatenate([p[k] for p in parts]) for k in out}
         order = np.lexsort((out['target'], out['layer'], out['variant'], out['date']))
         return {k: v[order] for k, v in out.items()}
 
@@ -723,7 +822,13 @@ class Sim:
         dead = np.nonzero(~np.isnan(d_dead))[0]
         outcome = np.concatenate((d_rec[rec], d_dead[dead]))
         both = np.concatenate((rec, dead))
-        mean_inf = outcome.mean() - d_inf[both].mean() if len(outcome) else 0
+        if self._comm is not None:             # means over the whole population from per-rank float64 sums
+            acc = torch.tensor([outcome.astype(np.float64).sum(), d_inf[both].astype(np.float64).sum(), float(len(outcome))], dtype=torch.float64, device=self.device)
+            self._comm.all_reduce_sum(acc)
+            so, si, cnt_ = (float(x) for x in acc.cpu().numpy())
+            mean_inf = so / cnt_ - si / cnt_ if cnt_ else 0
+        else:
+            mean_inf = outcome.mean() - d_inf[both].mean() if len(outcome) else 0
         R = self.results
         new_inf = R['new_infections'].values - R['n_imports'].values
         n_inf = R['n_infectious'].values

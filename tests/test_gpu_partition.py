@@ -1,0 +1,99 @@
+'''
+Agent-partitioned simulation (BASELINE config 4) against the single-GPU run of the
+SAME simulation: every random draw is keyed on global agent / edge ids, so the People arrays (concatenated over
+ranks), every result series and the infection log must be IDENTICAL for any number of ranks -- and the single-GPU
+run is itself checked bit for bit against the oracle in test_gpu_sim.py.
+
+The ranks run as threads of this process on one GPU (partition.LocalComm: the same kernels and the same exchange
+points as under torchrun, with device copies instead of ncclAllGather), so the test runs on the one-GPU box;
+tests/multi_gpu_partition.py runs the same comparison under torchrun with NCCL.
+'''
+import numpy as np
+import pytest
+import torch
+
+import scenarios
+
+pytestmark = pytest.mark.gpu
+
+PART_SCENARIOS = {
+    # testing + tracing with delays + vaccination + per-layer beta changes (hybrid3k of scenarios.py)
+    'hybrid3k': scenarios.SCENARIOS['hybrid3k'],
+    # three variants, importations, vaccine + booster (variants4k without the bed limits, which need a daily global count)
+    'variants4k': dict(pars={k: v for k, v in scenarios.SCENARIOS['variants4k']['pars'].items() if not k.startswith('n_beds')},
+                       variants=scenarios.SCENARIOS['variants4k']['variants'], interventions=scenarios.SCENARIOS['variants4k']['interventions']),
+    'random2k_nowaning': scenarios.SCENARIOS['random2k_nowaning'],
+    # population size not divisible by 32 * world
+    'odd5003': dict(pars=dict(pop_size=5003, pop_infected=80, pop_type='hybrid', n_days=35, verbose=0, rand_seed=4, beta=0.02),
+                    interventions=[('test_prob', dict(start_day=4, symp_prob=0.3, asymp_prob=0.02)),
+                                   ('contact_tracing', dict(trace_probs=0.5, trace_time=1, start_day=6))]),
+}
+
+
+def run_partitioned(cv, spec, world):
+    from covasim_b200 import partition as cvpart
+    comms = cvpart.LocalComm.make(world)
+    sims = [cv.Sim(**scenarios.build(cv, spec), partition=comms[r]) for r in range(world)]
+    cvpart.run_local(sims, lambda s: s.initialize())
+    cvpart.run_local(sims, lambda s: s.run())
+    logs = cvpart.run_local(sims, lambda s: s.infection_log)
+    return sims, logs
+
+
+@pytest.mark.parametrize('name,world', [('hybrid3k', 2), ('hybrid3k', 3), ('variants4k', 2), ('random2k_nowaning', 4), ('odd5003', 3)])
+def test_partitioned_equals_single(name, world):
+    import covasim_b200 as cv
+    spec = PART_SCENARIOS[name]
+    ref = cv.Sim(**scenarios.build(cv, spec))
+    ref.run()
+    sims, logs = run_partitioned(cv, spec, world)
+    # ranges tile the population
+    assert [s.id0 for s in sims] == list(np.cumsum([0] + [s.n_local for s in sims[:-1]]))
+    assert sum(s.n_local for s in sims) == ref.n
+    # every People array, concatenated over ranks, is identical (floats included: same arithmetic, same keys)
+    for k in ref.people.keys():
+        whole = ref.people.to_numpy(k)
+        parts = np.concatenate([s.people.to_numpy(k) for s in sims], axis=-1)
+        assert np.array_equal(whole, parts, equal_nan=(whole.dtype.kind == 'f')), f'{name} x{world}: People.{k} differs'
+    # results: counters are integers (exact); the three float64 population sums differ only by summation order
+    for s in sims:
+        for k in ref.result_keys():
+            a, b = s.results[k].values, ref.results[k].values
+            # r_eff: the single-GPU run takes float32 means of the date arrays like the reference (sim.py:915-923), the
+            # partitioned run combines per-rank float64 sums
+            assert np.allclose(a, b, rtol=1e-6 if k == 'r_eff' else 1e-12, atol=0, equal_nan=True), f'{name} x{world}: result {k} differs'
+        for k in ref.result_keys('variant'):
+            assert np.array_equal(s.results['variant'][k].values, ref.results['variant'][k].values), f'{name} x{world}: variant/{k} differs'
+        assert s.summary['cum_infections'] == ref.summary['cum_infections']
+    # infection log: same transmissions, same sources, same layers
+    want = ref.infection_log
+    for log in logs:
+        for k in ('source', 'target', 'date', 'layer', 'variant'):
+            assert np.array_equal(log[k], want[k]), f'{name} x{world}: infection log {k} differs'
+    assert ref.summary['cum_infections'] > 4 * spec['pars']['pop_infected']         # the epidemic actually spread
+
+
+def test_partitioned_rejects_what_it_cannot_do():
+    import covasim_b200 as cv
+    from covasim_b200 import partition as cvpart
+    comm = cvpart.LocalComm.make(1)[0]
+    with pytest.raises(NotImplementedError):
+        cv.Sim(pop_size=2000, n_days=5, dynam_layer=dict(a=1), partition=comm).initialize()
+    with pytest.raises(NotImplementedError):
+        cv.Sim(pop_size=2000, n_days=5, n_beds_hosp=10, partition=comm).initialize()
+    with pytest.raises(NotImplementedError):
+        cv.Sim(pop_size=2000, n_days=5, rng='mt', partition=comm)
+    with pytest.raises(ValueError):
+        cvpart.plan(40, 4)                      # chunks of 32: the last ranks would own nobody
+
+
+def test_hit_capacity_overflow_is_reported():
+    ''' A day with more successful transmissions than hit_capacity must fail loudly, never drop infections silently '''
+    import covasim_b200 as cv
+    from covasim_b200 import partition as cvpart
+    comms = cvpart.LocalComm.make(2)
+    # 100k agents, everyone very infectious: far more than the 65536-hit floor on the first days
+    sims = [cv.Sim(pop_size=150_000, pop_infected=30_000, n_days=8, beta=0.9, verbose=0, partition=comms[r], pop_exact=False) for r in range(2)]
+    cvpart.run_local(sims, lambda s: s.initialize())
+    with pytest.raises(RuntimeError, match='hit_capacity'):
+        cvpart.run_local(sims, lambda s: s.run())

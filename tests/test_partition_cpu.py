@@ -1,0 +1,147 @@
+'''
+CPU tests of the host logic of the agent-partitioned run (covasim_b200/partition.py): the partition plan, the
+partitioned adjacency against a brute-force construction, and the two communicators -- torch.distributed with a
+world_size-2 gloo group, and the in-process LocalComm.  The kernels themselves are covered on the GPU
+(tests/test_gpu_partition.py).
+'''
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_plan():
+    from covasim_b200 import partition as cvpart
+    chunk, ranges = cvpart.plan(1_000_000, 8)
+    assert chunk == 125_024 and chunk % 32 == 0
+    assert ranges[0] == (0, chunk) and ranges[-1] == (7 * chunk, 1_000_000)
+    assert all(hi - lo == chunk for lo, hi in ranges[:-1])
+    chunk, ranges = cvpart.plan(5003, 3)
+    assert chunk == 1696 and ranges == [(0, 1696), (1696, 3392), (3392, 5003)]
+    with pytest.raises(ValueError):
+        cvpart.plan(64, 3)
+
+
+def random_layers(rng, n, sizes):
+    out = []
+    for e in sizes:
+        out.append(dict(p1=np.sort(rng.randint(0, n, e)).astype(np.int32), p2=rng.randint(0, n, e).astype(np.int32), beta=rng.random_sample(e).astype(np.float32)))
+    return out
+
+
+def brute_rows(layers, ids, lo, hi):
+    ''' {source: sorted list of (local target, edge, meta, beta bits)} by plain loops '''
+    rows = {}
+    for l, layer in zip(ids, layers):
+        for e, (a, b, w) in enumerate(zip(layer['p1'], layer['p2'], layer['beta'])):
+            wb = int(np.float32(w).view(np.int32))
+            if lo <= b < hi:
+                rows.setdefault(int(a), []).append((int(b) - lo, e, (l << 1) | 0, wb))
+            if lo <= a < hi:
+                rows.setdefault(int(b), []).append((int(a) - lo, e, (l << 1) | 1, wb))
+    return {k: sorted(v) for k, v in rows.items()}
+
+
+@pytest.mark.parametrize('world', [1, 2, 3])
+def test_partition_adjacency_matches_brute_force(world):
+    from covasim_b200 import partition as cvpart
+    rng = np.random.RandomState(world)
+    n = 700
+    layers = random_layers(rng, n, [900, 0, 1500])
+    layers[0]['p2'][:5] = layers[0]['p1'][:5]                 # self-loops and duplicate edges are legal
+    layers[2]['p1'][10:14] = layers[2]['p1'][10]
+    layers[2]['p2'][10:14] = layers[2]['p2'][10]
+    ids = [0, 2, 3]
+    chunk, ranges = cvpart.plan(n, world)
+    total = 0
+    for lo, hi in ranges:
+        ptr, adj, M = cvpart.build_partition_adjacency(layers, ids, lo, hi, world * chunk, 'cpu')
+        ptr, adj = ptr.numpy(), adj.numpy()
+        assert ptr.shape == (world * chunk + 1,) and ptr[-1] == M
+        want = brute_rows(layers, ids, lo, hi)
+        for src in range(world * chunk):
+            got = sorted(tuple(int(x) for x in row) for row in adj[ptr[src]:ptr[src + 1]])
+            assert got == want.get(src, []), f'row {src} of range [{lo},{hi})'
+        total += M
+    assert total == 2 * sum(len(l['p1']) for l in layers)     # every directed edge lives on exactly one rank
+
+
+def _dist_worker(rank, world, port, q):
+    for p in (ROOT, os.path.join(ROOT, 'tests')):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from covasim_b200 import partition as cvpart
+    comm = cvpart.DistComm()
+    chunk = 64
+    codes_local = torch.full((chunk,), rank + 1, dtype=torch.uint8)
+    codes_global = torch.zeros(world * chunk, dtype=torch.uint8)
+    comm.all_gather(codes_global, codes_local)
+    bits_local = torch.full((chunk // 32,), 100 + rank, dtype=torch.int32)
+    bits_global = torch.zeros(world * chunk // 32, dtype=torch.int32)
+    comm.all_gather(bits_global, bits_local)
+    table = torch.arange(6, dtype=torch.int64).reshape(2, 3) * (rank + 1)
+    comm.all_reduce_sum(table)
+    objs = comm.gather_objects(dict(rank=rank, ids=np.arange(rank + 2)))
+    q.put((rank, codes_global.numpy(), bits_global.numpy(), table.numpy(), [o['rank'] for o in objs], [len(o['ids']) for o in objs]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_distcomm_gloo_world2():
+    world = 2
+    port = 29600 + (os.getpid() % 2000)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dist_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, codes, bits, table, ranks, lens in got:
+        assert np.array_equal(codes, np.repeat([1, 2], 64))
+        assert np.array_equal(bits, np.repeat([100, 101], 2))
+        assert np.array_equal(table, np.arange(6).reshape(2, 3) * 3)
+        assert ranks == [0, 1] and lens == [2, 3]
+
+
+def test_localcomm_threads():
+    import threading
+    from covasim_b200 import partition as cvpart
+    world = 3
+    comms = cvpart.LocalComm.make(world)
+    out = [None] * world
+
+    def work(r):
+        c = comms[r]
+        res = []
+        for day in range(20):                                  # many rounds: the barriers must keep the ranks in step
+            loc = torch.full((32,), 10 * day + r, dtype=torch.uint8)
+            glob = torch.zeros(32 * world, dtype=torch.uint8)
+            c.all_gather(glob, loc)
+            res.append(glob.numpy().copy())
+        t = torch.tensor([r + 1.0, 2.0 * r], dtype=torch.float64)
+        c.all_reduce_sum(t)
+        objs = c.gather_objects(('rank', r))
+        out[r] = (res, t.numpy(), objs)
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=60)
+    for r in range(world):
+        res, t, objs = out[r]
+        for day, g in enumerate(res):
+            assert np.array_equal(g, np.repeat([10 * day, 10 * day + 1, 10 * day + 2], 32))
+        assert np.array_equal(t, [6.0, 6.0])
+        assert objs == [('rank', 0), ('rank', 1), ('rank', 2)]

@@ -244,8 +244,8 @@ int cvb_set_partition(cvb_sim* s, int64_t id0, int64_t n_global, int64_t chunk, 
     s->rel_trans_global = rel_trans_global;
     s->codes_local = codes_local; s->codes_global = codes_global;
     s->case_bits_local = case_bits_local; s->case_bits_global = case_bits_global;
-    if (hit_capacity < s->n) hit_capacity = s->n;
-    if (hit_capacity < 65536) hit_capacity = 65536;
+    if (hit_capacity <= 0) hit_capacity = s->n > 65536 ? s->n : 65536;   // default: one successful transmission per local agent per day
+    if (hit_capacity < 1024) hit_capacity = 1024;
     cudaFree(s->cand); cudaFree(s->hit_src); cudaFree(s->hit_key); cudaFree(s->glist); cudaFree(s->n_glist); cudaFree(s->part_flags);
     s->cand = nullptr; s->hit_src = nullptr; s->hit_key = nullptr; s->glist = nullptr; s->n_glist = nullptr; s->part_flags = nullptr;
     CVB_CHECK(cudaMalloc((void**)&s->cand, (size_t)hit_capacity * sizeof(int32_t)));

@@ -109,10 +109,12 @@ CVB_HD double keyed_uniform(uint64_t seed, uint32_t purpose, uint32_t sub, int32
     return u53(w.x, w.y);
 }
 // Box-Muller, cosine branch (oracle/philox.py:keyed_normal)
-CVB_HD double keyed_normal(uint64_t seed, uint32_t purpose, uint32_t sub, int32_t day, int64_t index, uint32_t slot) {
-    u32x4 w = keyed_words(seed, purpose, sub, day, index, slot);
+CVB_HD double normal_from_words(const u32x4 w) {
     double u1 = u53(w.x, w.y), u2 = u53(w.z, w.w);
     return dmul(sqrt(dmul(-2.0, log(1.0 - u1))), cos(dmul(6.283185307179586, u2)));
+}
+CVB_HD double keyed_normal(uint64_t seed, uint32_t purpose, uint32_t sub, int32_t day, int64_t index, uint32_t slot) {
+    return normal_from_words(keyed_words(seed, purpose, sub, day, index, slot));
 }
 // One draw of a cvb_dist from a standard normal z (reference utils.py:211-231)
 CVB_HD double dist_from_normal(const cvb_dist& d, double z) {

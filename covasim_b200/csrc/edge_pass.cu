@@ -26,6 +26,7 @@
 // processed in order, infect() drops already-infected targets, and np.unique(return_index=True)
 // keeps the first occurrence in [direction 0 edges..., direction 1 edges...] (people.py:465-473).
 // The first hit on a target also appends it to the day's candidate list (warp-aggregated atomics).
+#include <stdlib.h>
 #include "cvb_internal.cuh"
 
 namespace cvb {
@@ -49,13 +50,18 @@ __device__ __forceinline__ void record_hit(unsigned long long* __restrict__ infe
     }
 }
 
-// Evaluate one candidate edge in both directions (reference utils.py:113-123) and record transmissions
-template <bool MULTI>
-__device__ __forceinline__ void process_edge(const TransRecords& rec, const EdgeParams& ep, int a, int b, float w, int l, int64_t e,
-        unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand) {
-    const int64_t n = ep.n;
+// Evaluate one candidate edge in both directions (reference utils.py:113-123) and record transmissions.  Split in two so
+// that the dense pass can issue the two record gathers of a batch of candidates and consume them one batch later.
+__device__ __forceinline__ void gather_records(const TransRecords& rec, int64_t n, int a, int b, int l, float2& ra, float2& rb) {
     const float2* __restrict__ ts = rec.ts + (int64_t)l * n;
-    const float2 ra = __ldg(ts + a), rb = __ldg(ts + b);
+    ra = __ldg(ts + a);
+    rb = __ldg(ts + b);
+}
+
+template <bool MULTI>
+__device__ __forceinline__ void finish_edge(const TransRecords& rec, const EdgeParams& ep, int a, int b, float w, int l, int64_t e,
+        const float2 ra, const float2 rb, unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand) {
+    const int64_t n = ep.n;
     float p01 = 0.0f, p10 = 0.0f;
     int va = 0, vb = 0;
     if (ra.x != 0.0f) {                       // a can transmit on this layer
@@ -84,91 +90,163 @@ __device__ __forceinline__ void process_edge(const TransRecords& rec, const Edge
     }
 }
 
-template <bool MULTI, bool SMEM_BITS, int THREADS>
+template <bool MULTI>
+__device__ __forceinline__ void process_edge(const TransRecords& rec, const EdgeParams& ep, int a, int b, float w, int l, int64_t e,
+        unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand) {
+    float2 ra, rb;
+    gather_records(rec, ep.n, a, b, l, ra, rb);
+    finish_edge<MULTI>(rec, ep, a, b, w, l, e, ra, rb, infect_key, cand, n_cand);
+}
+
+// One bit test per endpoint: word >> (index mod 32) with the hardware's wrap-around funnel shift (no mask instruction)
+__device__ __forceinline__ unsigned endpoint_bit(unsigned word, int index) { return __funnelshift_r(word, 0u, (unsigned)index); }
+
+struct EdgeQuad {                       // four consecutive edges of one layer, as loaded by one thread
+    int4 a, b;
+    float4 w;
+    int cnt;                            // how many of the four exist (4 except at the ragged end of a layer)
+};
+
+__device__ __forceinline__ void load_quad(const int32_t* __restrict__ p1, const int32_t* __restrict__ p2, const float* __restrict__ beta,
+                                          int64_t n_edges, unsigned q, EdgeQuad& Q) {
+    const int64_t e0 = (int64_t)q * 4;
+    if (e0 + 4 <= n_edges) {
+        Q.a = ld_stream(reinterpret_cast<const int4*>(p1) + q);
+        Q.b = ld_stream(reinterpret_cast<const int4*>(p2) + q);
+        Q.w = ld_stream(reinterpret_cast<const float4*>(beta) + q);
+        Q.cnt = 4;
+    } else {                                                        // ragged end (or a lane past the end): scalar loads
+        int* pa = reinterpret_cast<int*>(&Q.a); int* pb = reinterpret_cast<int*>(&Q.b); float* pw = reinterpret_cast<float*>(&Q.w);
+        Q.cnt = e0 < n_edges ? (int)(n_edges - e0) : 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const bool ok = k < Q.cnt;
+            pa[k] = ok ? p1[e0 + k] : 0; pb[k] = ok ? p2[e0 + k] : 0; pw[k] = ok ? beta[e0 + k] : 0.0f;
+        }
+    }
+}
+
+// THREADS per CTA (one persistent CTA per SM when the bitmap is staged in shared memory) and QPT quads (of four edges)
+// per thread per iteration.  More quads per thread = more independent loads in flight per warp (3*QPT 128-bit streaming
+// loads + 8*QPT shared-memory bit lookups issued back to back) at the price of registers, i.e. of warps per SM.
+// Ask L2 for the cache line holding `p` (fire and forget): the streaming loads two tiles later then find their data in L2
+// (~0.4 us) instead of HBM (~2 us under load), so the bytes a warp must keep in flight in REGISTERS shrink accordingly
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+template <bool MULTI, bool SMEM_BITS, int THREADS, int QPT, int PF>
 __global__ void __launch_bounds__(THREADS) edge_pass_kernel(const __grid_constant__ LayerTable L, TransRecords rec,
         const __grid_constant__ EdgeParams ep, const unsigned int* __restrict__ inf_bits, unsigned long long* __restrict__ infect_key,
         int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kWarps = THREADS / 32;
-    constexpr int kTile = THREADS * kEdgesPerThread;
-    // layout: [queue entries uint4 x kWarps*kQueueCap][queue meta u16 x kWarps*kQueueCap][bitmap words]
+    // layout: [queue entries uint4 x kWarps*kQueueCap][bitmap words].  A queue holds candidate edges of ONE layer (it is
+    // flushed when the CTA finishes a layer), so an entry is just {p1, p2, beta, edge index}.
     uint4* q_edge = reinterpret_cast<uint4*>(smem_raw) + warp_id() * kQueueCap;
-    unsigned short* q_meta = reinterpret_cast<unsigned short*>(smem_raw + (size_t)kWarps * kQueueCap * sizeof(uint4)) + warp_id() * kQueueCap;
     const unsigned int* bits = inf_bits;
     if (SMEM_BITS) {
-        unsigned int* s_bits = reinterpret_cast<unsigned int*>(smem_raw + (size_t)kWarps * kQueueCap * (sizeof(uint4) + sizeof(unsigned short)));
-        for (int64_t wd = threadIdx.x; wd < ep.n_words; wd += THREADS) s_bits[wd] = inf_bits[wd];
+        unsigned int* s_bits = reinterpret_cast<unsigned int*>(smem_raw + (size_t)kWarps * kQueueCap * sizeof(uint4));
+        const int64_t n4 = ep.n_words >> 2;                            // 128-bit copies, then the tail
+        for (int64_t wd = threadIdx.x; wd < n4; wd += THREADS) reinterpret_cast<uint4*>(s_bits)[wd] = __ldg(reinterpret_cast<const uint4*>(inf_bits) + wd);
+        for (int64_t wd = (n4 << 2) + threadIdx.x; wd < ep.n_words; wd += THREADS) s_bits[wd] = inf_bits[wd];
         bits = s_bits;
         __syncthreads();
     }
     const int lane = lane_id();
     const unsigned lt_mask = (1u << lane) - 1u;
-    int qn = 0;                                                     // warp-uniform queue length
+    constexpr unsigned kTileQuads = THREADS * QPT;                  // quads per CTA per iteration (build_layer_table's tile = 4x this)
+    const unsigned stride = gridDim.x * kTileQuads;
 
-    const int64_t total_tiles = L.tile_start[L.n_layers];
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int q_ = 0;
+    for (int entry = 0; entry < L.n_layers; ++entry) {
+        const int32_t* __restrict__ p1 = L.l[entry].p1;
+        const int32_t* __restrict__ p2 = L.l[entry].p2;
+        const float* __restrict__ beta = L.l[entry].beta;
+        const int64_t n_edges = L.l[entry].n_edges;
+        const int l = L.layer_id[entry];
+        const unsigned nq = (unsigned)((n_edges + 3) >> 2);           // quads of this layer (n_edges < 2^32)
+        // the CTA's first tile in this layer continues the round-robin over ALL layers' tiles, so the load stays balanced
+        const unsigned rot = (unsigned)(L.tile_start[entry] % gridDim.x);
+        const unsigned first = (blockIdx.x + gridDim.x - rot) % gridDim.x;
+        // quad j of this thread in a tile is first_quad + j * THREADS: every 128-bit load of a warp is one contiguous 512 B
+        unsigned q = first * kTileQuads + threadIdx.x;                // q - lane is warp-uniform
+        int qn = 0;                                                   // warp-uniform queue length
+        // deferred drain: the record gathers of a batch of 32 candidates are issued when the batch is popped and consumed
+        // when the NEXT batch is popped, so their L2 / HBM latency overlaps the filtering of the following quads
+        bool pend = false;                                            // warp-uniform
+        uint4 pc = make_uint4(0u, 0u, 0u, 0u);
+        float2 pra = make_float2(0.f, 0.f), prb = make_float2(0.f, 0.f);
+
+        auto load_tile = [&](unsigned qq, EdgeQuad (&T)[QPT]) {
 #pragma unroll
-        for (int q = 1; q < CVB_MAX_LAYERS; ++q) q_ += (q < L.n_layers && tile >= L.tile_start[q]);
-        const LayerPtrs& lay = L.l[q_];
-        const int l = L.layer_id[q_];
-        const int64_t e0 = (tile - L.tile_start[q_]) * kTile + (int64_t)threadIdx.x * kEdgesPerThread;
-        int a[4], b[4];
-        float w[4];
-        int cnt = 0;
-        if (e0 + 4 <= lay.n_edges) {
-            const int4 va = ld_stream(reinterpret_cast<const int4*>(lay.p1 + e0));
-            const int4 vb = ld_stream(reinterpret_cast<const int4*>(lay.p2 + e0));
-            const float4 vw = ld_stream(reinterpret_cast<const float4*>(lay.beta + e0));
-            a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w;
-            b[0] = vb.x; b[1] = vb.y; b[2] = vb.z; b[3] = vb.w;
-            w[0] = vw.x; w[1] = vw.y; w[2] = vw.z; w[3] = vw.w;
-            cnt = 4;
-        } else if (e0 < lay.n_edges) {
-            cnt = (int)(lay.n_edges - e0);
+            for (int j = 0; j < QPT; ++j) load_quad(p1, p2, beta, n_edges, qq + (unsigned)j * THREADS, T[j]);
+            if (PF > 0) {                                             // L2 prefetch of the tile PF iterations ahead of this load
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const bool ok = k < cnt;
-                a[k] = ok ? lay.p1[e0 + k] : 0; b[k] = ok ? lay.p2[e0 + k] : 0; w[k] = ok ? lay.beta[e0 + k] : 0.0f;
+                for (int j = 0; j < QPT; ++j) {
+                    const unsigned qp = qq + (unsigned)PF * stride + (unsigned)j * THREADS;
+                    if (qp < nq && (lane & 7) == 0) {                 // one request per 128-byte line
+                        prefetch_l2(reinterpret_cast<const int4*>(p1) + qp);
+                        prefetch_l2(reinterpret_cast<const int4*>(p2) + qp);
+                        prefetch_l2(reinterpret_cast<const float4*>(beta) + qp);
+                    }
+                }
             }
-        } else {
+        };
+        // filter QPT quads per lane into the warp's queue and drain full warps of candidates
+        auto filter_tile = [&](const EdgeQuad (&T)[QPT], unsigned qq) {
+            // keep an edge only if one endpoint can transmit.  All 8*QPT bitmap words are requested before any is used, so
+            // the shared-memory latency is paid once per tile, not once per edge.
+            unsigned wa[QPT][4], wb[QPT][4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) { a[k] = 0; b[k] = 0; w[k] = 0.0f; }
+            for (int j = 0; j < QPT; ++j) {
+                const int a[4] = {T[j].a.x, T[j].a.y, T[j].a.z, T[j].a.w}, b[4] = {T[j].b.x, T[j].b.y, T[j].b.z, T[j].b.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { wa[j][k] = bits[a[k] >> 5]; wb[j][k] = bits[b[k] >> 5]; }
+            }
+#pragma unroll
+            for (int j = 0; j < QPT; ++j) {
+                const int a[4] = {T[j].a.x, T[j].a.y, T[j].a.z, T[j].a.w}, b[4] = {T[j].b.x, T[j].b.y, T[j].b.z, T[j].b.w};
+                const float w[4] = {T[j].w.x, T[j].w.y, T[j].w.z, T[j].w.w};
+                const unsigned e_base = (qq + (unsigned)j * THREADS) * 4u;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool keep = ((endpoint_bit(wa[j][k], a[k]) | endpoint_bit(wb[j][k], b[k])) & 1u) != 0 && k < T[j].cnt;
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+                    if (keep) q_edge[qn + __popc(m & lt_mask)] = make_uint4((unsigned)a[k], (unsigned)b[k], __float_as_uint(w[k]), e_base + (unsigned)k);
+                    qn += __popc(m);
+                }
+                __syncwarp();
+                while (qn >= 32) {
+                    qn -= 32;
+                    const uint4 c = q_edge[qn + lane];
+                    __syncwarp();
+                    float2 ra, rb;
+                    gather_records(rec, ep.n, (int)c.x, (int)c.y, l, ra, rb);
+                    if (pend) finish_edge<MULTI>(rec, ep, (int)pc.x, (int)pc.y, __uint_as_float(pc.z), l, (int64_t)pc.w, pra, prb, infect_key, cand, n_cand);
+                    pc = c; pra = ra; prb = rb; pend = true;
+                }
+                __syncwarp();
+            }
+        };
+
+        // software pipeline, two register sets: the 3*QPT 128-bit loads of the NEXT tile are in flight while this one is
+        // filtered and drained
+        EdgeQuad A[QPT], B[QPT];
+        unsigned qbase = q - lane;
+        if (qbase < nq) load_tile(q, A);
+        while (qbase < nq) {
+            const unsigned q2 = q + stride, qbase2 = qbase + stride;
+            if (qbase2 < nq) load_tile(q2, B);
+            filter_tile(A, q);
+            if (qbase2 >= nq) break;
+            q = q2 + stride; qbase = qbase2 + stride;
+            if (qbase < nq) load_tile(q, A);
+            filter_tile(B, q2);
         }
-        // prefilter: keep an edge only if one endpoint can transmit (2 bit tests in shared memory)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned short meta = (unsigned short)((l << 8) | (int)(((e0 + k) >> 32) & 0xFF));
-            bool keep = false;
-            if (k < cnt) {
-                const unsigned wa = bits[a[k] >> 5], wb = bits[b[k] >> 5];
-                keep = (((wa >> (a[k] & 31)) | (wb >> (b[k] & 31))) & 1u) != 0;
-            }
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
-            if (keep) {
-                const int pos = qn + __popc(m & lt_mask);
-                q_edge[pos] = make_uint4((unsigned)a[k], (unsigned)b[k], __float_as_uint(w[k]), (unsigned)((e0 + k) & 0xFFFFFFFFll));
-                q_meta[pos] = meta;
-            }
-            qn += __popc(m);
+        if (pend) finish_edge<MULTI>(rec, ep, (int)pc.x, (int)pc.y, __uint_as_float(pc.z), l, (int64_t)pc.w, pra, prb, infect_key, cand, n_cand);
+        if (lane < qn) {                                              // leftovers of this layer
+            const uint4 c = q_edge[lane];
+            process_edge<MULTI>(rec, ep, (int)c.x, (int)c.y, __uint_as_float(c.z), l, (int64_t)c.w, infect_key, cand, n_cand);
         }
         __syncwarp();
-        // drain full warps of candidates
-        while (qn >= 32) {
-            qn -= 32;
-            const uint4 c = q_edge[qn + lane];
-            const unsigned short cm = q_meta[qn + lane];
-            __syncwarp();
-            process_edge<MULTI>(rec, ep, (int)c.x, (int)c.y, __uint_as_float(c.z), cm >> 8, ((int64_t)(cm & 0xFF) << 32) | c.w,
-                                infect_key, cand, n_cand);
-        }
-        __syncwarp();
-    }
-    if (lane < qn) {                                                // leftovers
-        const uint4 c = q_edge[lane];
-        const unsigned short cm = q_meta[lane];
-        process_edge<MULTI>(rec, ep, (int)c.x, (int)c.y, __uint_as_float(c.z), cm >> 8, ((int64_t)(cm & 0xFF) << 32) | c.w,
-                            infect_key, cand, n_cand);
     }
 }
 
@@ -339,9 +417,18 @@ __global__ void __launch_bounds__(kThreads) edge_pass_partition_kernel(TransReco
 
 int build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges, uint32_t skip_mask);
 
-template <bool MULTI, bool SMEM_BITS, int THREADS>
-static int launch_edge_pass(cvb_sim* s, const LayerTable& L, const EdgeParams& ep, size_t smem, int grid, cudaStream_t st) {
-    auto kern = edge_pass_kernel<MULTI, SMEM_BITS, THREADS>;
+template <bool MULTI, bool SMEM_BITS, int THREADS, int QPT, int PF>
+static int launch_edge_pass(cvb_sim* s, uint32_t skip_mask, const EdgeParams& ep, size_t bitmap_bytes, int ctas_per_sm, cudaStream_t st) {
+    auto kern = edge_pass_kernel<MULTI, SMEM_BITS, THREADS, QPT, PF>;
+    LayerTable L;
+    if (build_layer_table(s, L, THREADS * QPT * kEdgesPerThread, skip_mask)) return 1;
+    const int64_t tiles = L.tile_start[L.n_layers];
+    if (tiles == 0) return 0;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
+    const int64_t max_grid = (int64_t)n_sm * ctas_per_sm;
+    const int grid = (int)(tiles < max_grid ? tiles : max_grid);
+    const size_t smem = (size_t)(THREADS / 32) * kQueueCap * sizeof(uint4) + (SMEM_BITS ? bitmap_bytes : 0);
     static bool configured[64] = {false};                            // per instantiation and per device
     const int dev = s->device & 63;
     if (!configured[dev]) {
@@ -372,7 +459,7 @@ int cvb::build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges, uint32_t s
         L.l[q] = s->layers[l];
         L.layer_id[q] = l;
         CVB_REQUIRE(L.l[q].n_edges == 0 || L.l[q].p1, "layer %d is not bound (cvb_bind_layer)", l);
-        CVB_REQUIRE(L.l[q].n_edges < (1ll << 40), "layer %d has too many edges for the 40-bit edge field", l);
+        CVB_REQUIRE(L.l[q].n_edges < (1ll << 32), "layer %d has too many edges for the 32-bit edge index of the streaming pass", l);
         L.tile_start[q] = acc;
         acc += (L.l[q].n_edges + tile_edges - 1) / tile_edges;
         ++q;
@@ -427,36 +514,28 @@ extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
         for (int l = 0; l < s->pars.n_layers; ++l) rest |= !(skip_mask & (1u << l)) && s->layers[l].n_edges > 0;
         if (!rest) return 0;
     }
-    // dense streaming pass over the remaining (dynamic) layers.  Shared-memory budget: per-warp candidate queue (18 B x 160 entries) + the transmit bitmap
+    // dense streaming pass over the remaining (dynamic) layers.  Shared-memory budget: per-warp candidate queue (16 B x 160
+    // entries) + the transmit bitmap; one persistent CTA per SM while the bitmap fits, else L1/L2-cached bit tests.
+    bool rest = false;
+    for (int l = 0; l < s->pars.n_layers; ++l) rest |= !(skip_mask & (1u << l)) && s->layers[l].n_edges > 0;
+    if (!rest) return 0;
     const size_t bitmap_bytes = (size_t)ep.n_words * sizeof(unsigned int);
-    const size_t queue_1024 = (size_t)32 * kQueueCap * (sizeof(uint4) + sizeof(unsigned short));
-    const size_t queue_512 = queue_1024 / 2, queue_256 = queue_1024 / 4;
     const size_t limit = 227 * 1024;
-    LayerTable L;
-    int n_sm = 148;
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
-    if (bitmap_bytes + queue_1024 <= limit) {
-        // one persistent 1024-thread CTA per SM, bitmap in shared memory
-        if (build_layer_table(s, L, 1024 * kEdgesPerThread, skip_mask)) return 1;
-        const int64_t tiles = L.tile_start[L.n_layers];
-        if (tiles == 0) return 0;
-        const int grid = (int)(tiles < n_sm ? tiles : n_sm);
-        return multi ? launch_edge_pass<true, true, 1024>(s, L, ep, bitmap_bytes + queue_1024, grid, st)
-                     : launch_edge_pass<false, true, 1024>(s, L, ep, bitmap_bytes + queue_1024, grid, st);
+    auto queue_bytes = [](int threads) { return (size_t)(threads / 32) * kQueueCap * sizeof(uint4); };
+    // Tile shape chosen on the B200 (profiles/r1/README.md, "dense edge pass v4"): 512 threads x 2 quads per thread beats 1024 x 1
+    // (more independent loads per warp: the pass is latency bound, not issue bound), L2 prefetch one tile ahead.
+    // CVB_DENSE_VARIANT selects the other shapes for profiling.
+    static int variant = -1;
+    if (variant < 0) { const char* v = getenv("CVB_DENSE_VARIANT"); variant = v ? atoi(v) : 0; }
+#define CVB_DENSE(THREADS, QPT, SMEM, CTAS, PF) \
+    return multi ? launch_edge_pass<true, SMEM, THREADS, QPT, PF>(s, skip_mask, ep, bitmap_bytes, CTAS, st) \
+                 : launch_edge_pass<false, SMEM, THREADS, QPT, PF>(s, skip_mask, ep, bitmap_bytes, CTAS, st)
+    if (bitmap_bytes + queue_bytes(1024) <= limit && variant == 1) { CVB_DENSE(1024, 1, true, 1, 1); }
+    if (bitmap_bytes + queue_bytes(512) <= limit) {
+        if (variant == 2) { CVB_DENSE(512, 2, true, 1, 0); }
+        CVB_DENSE(512, 2, true, 1, 1);
     }
-    if (bitmap_bytes + queue_512 <= limit) {
-        if (build_layer_table(s, L, 512 * kEdgesPerThread, skip_mask)) return 1;
-        const int64_t tiles = L.tile_start[L.n_layers];
-        if (tiles == 0) return 0;
-        const int grid = (int)(tiles < n_sm ? tiles : n_sm);
-        return multi ? launch_edge_pass<true, true, 512>(s, L, ep, bitmap_bytes + queue_512, grid, st)
-                     : launch_edge_pass<false, true, 512>(s, L, ep, bitmap_bytes + queue_512, grid, st);
-    }
-    // large populations: bitmap stays in global memory (L1/L2-cached bit tests), 8 CTAs of 256 threads per SM
-    if (build_layer_table(s, L, 256 * kEdgesPerThread, skip_mask)) return 1;
-    const int64_t tiles = L.tile_start[L.n_layers];
-    if (tiles == 0) return 0;
-    const int grid = (int)(tiles < (int64_t)n_sm * 8 ? tiles : (int64_t)n_sm * 8);
-    return multi ? launch_edge_pass<true, false, 256>(s, L, ep, queue_256, grid, st)
-                 : launch_edge_pass<false, false, 256>(s, L, ep, queue_256, grid, st);
+    // large populations: bitmap stays in global memory (L1/L2-cached bit tests), 256-thread CTAs
+    CVB_DENSE(256, 1, false, 4, 1);
+#undef CVB_DENSE
 }

@@ -1,6 +1,6 @@
 // People.infect (reference people.py:435-586) + update_peak_nab (immunity.py:138-202), native-RNG form.
 //
-// One thread per newly infected agent.  Every random draw is a pure function of
+// Sixteen lanes per newly infected agent.  Every random draw is a pure function of
 // (seed, P_INFECT, day, agent, slot), so the result does not depend on the order in which the edge
 // pass discovered the targets.  Slots: 0 exp2inf, 1 symptomatic?, 2 asym2rec|inf2sym, 3 severe?,
 // 4 mild2rec|sym2sev, 5 critical?, 6 sev2rec|sev2crit, 7 dies?, 8 crit2rec|crit2die, 9 nab_init.
@@ -25,12 +25,6 @@ struct InfectArgs {
     int64_t hit_cap;
 };
 
-__device__ __forceinline__ double draw_dur(const cvb_pars& pars, int which, uint64_t seed, int32_t t, int64_t i, uint32_t slot) {
-    const cvb_dist& d = pars.dur[which];
-    if (d.kind == CVB_DIST_ZERO) return 0.0;
-    return dist_from_normal(d, keyed_normal(seed, P_INFECT, 0, t, i, slot));
-}
-
 __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __grid_constant__ cvb_pars pars, const __grid_constant__ LayerTable L,
         const __grid_constant__ InfectArgs ia, const int32_t* __restrict__ cand, const unsigned int* __restrict__ n_cand_ptr,
         unsigned long long* __restrict__ infect_key, const unsigned long long* __restrict__ beds, ResultPtrs res, LogPtrs log) {
@@ -51,8 +45,47 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
     const bool icu_max = ia.icu_max >= 0 ? ia.icu_max != 0 : (pars.n_beds_icu >= 0 && (long long)beds[(int64_t)t * 2 + 1] > pars.n_beds_icu);
     const float tf = (float)t;
 
-    for (unsigned int j = blockIdx.x * blockDim.x + threadIdx.x; j < n_cand; j += gridDim.x * blockDim.x) {
-        const int64_t i = cand[j];
+    // Sixteen lanes per newly infected agent: lane s of the half-warp computes the Philox draw of slot s (its uniform, and
+    // for the duration / NAb slots the normal deviate pushed through BOTH distributions the slot may feed), so the ~10
+    // float64 Box-Muller + exp chains of one agent run side by side instead of one after the other; lane 0 of the
+    // half-warp then walks the prognosis tree with the finished values.  (One thread per agent spent its time on
+    // instruction-cache misses and dependent float64 latency: profiles/r1.)
+    const int lane = lane_id(), half = lane >> 4, slot = lane & 15, base = half << 4;
+    const unsigned int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int jw = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; jw < n_cand; jw += warps_total * 2) {
+        const unsigned int j = jw + half;
+        const bool valid = j < n_cand;
+        const int64_t i = valid ? cand[j] : 0;
+        const int64_t gi = i + ia.id0;                             // global id: Philox index and logged target
+        const u32x4 words = keyed_words(ia.seed, P_INFECT, 0, t, gi, (uint32_t)slot);
+        const double u_mine = u53(words.x, words.y);
+        double d0 = 0.0, d1 = 0.0;
+        if (slot <= 9 && !(slot & 1 && slot != 9)) {                // slots 0, 2, 4, 6, 8 (durations) and 9 (initial NAb level)
+            // ONE copy of the Box-Muller / exp code for every slot (the kernel is launched cold every day with a handful
+            // of warps: its time is instruction fetch, so code size matters more than the selects below)
+            const double z = normal_from_words(words);
+            const int ka = slot == 0 ? CVB_DUR_exp2inf : slot == 2 ? CVB_DUR_asym2rec : slot == 4 ? CVB_DUR_mild2rec : slot == 6 ? CVB_DUR_sev2rec : CVB_DUR_crit2rec;
+            const int kb = slot == 2 ? CVB_DUR_inf2sym : slot == 4 ? CVB_DUR_sym2sev : slot == 6 ? CVB_DUR_sev2crit : CVB_DUR_crit2die;
+            const cvb_dist da = slot == 9 ? pars.nab_init : pars.dur[ka];
+            cvb_dist db = pars.dur[kb];
+            if (slot == 0 || slot == 9) db.kind = CVB_DIST_ZERO;
+#pragma unroll 1
+            for (int alt = 0; alt < 2; ++alt) {
+                const double d = dist_from_normal(alt ? db : da, z);
+                if (alt) d1 = d; else d0 = d;
+            }
+        }
+        const double x_exp2inf = __shfl_sync(0xFFFFFFFFu, d0, base + 0);
+        const double u_symp = __shfl_sync(0xFFFFFFFFu, u_mine, base + 1);
+        const double x_asym2rec = __shfl_sync(0xFFFFFFFFu, d0, base + 2), x_inf2sym = __shfl_sync(0xFFFFFFFFu, d1, base + 2);
+        const double u_sev = __shfl_sync(0xFFFFFFFFu, u_mine, base + 3);
+        const double x_mild2rec = __shfl_sync(0xFFFFFFFFu, d0, base + 4), x_sym2sev = __shfl_sync(0xFFFFFFFFu, d1, base + 4);
+        const double u_crit = __shfl_sync(0xFFFFFFFFu, u_mine, base + 5);
+        const double x_sev2rec = __shfl_sync(0xFFFFFFFFu, d0, base + 6), x_sev2crit = __shfl_sync(0xFFFFFFFFu, d1, base + 6);
+        const double u_death = __shfl_sync(0xFFFFFFFFu, u_mine, base + 7);
+        const double x_crit2rec = __shfl_sync(0xFFFFFFFFu, d0, base + 8), x_crit2die = __shfl_sync(0xFFFFFFFFu, d1, base + 8);
+        const double x_nab = __shfl_sync(0xFFFFFFFFu, d0, base + 9);
+        if (slot != 0 || !valid) continue;                         // the half-warp's leader applies the infection
         unsigned long long key;
         if (ia.hit_key) {                                          // one entry per hit: only the winning one proceeds
             key = ia.hit_key[j];
@@ -73,7 +106,6 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
             source = ia.hit_src ? ia.hit_src[j] : (dir == 0 ? L.l[lfield].p1[e] : L.l[lfield].p2[e]);
             layer_code = lfield;
         }
-        const int64_t gi = i + ia.id0;                             // global id: Philox index and logged target
         // every per-agent input is loaded here, before the first store, so the loads are independent and in flight
         // together (the stores below may alias them as far as the compiler knows)
         const bool is_sus = PB(P, susceptible)[i] != 0;
@@ -106,7 +138,7 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
             }
         }
         // exposed -> infectious (people.py:513-520)
-        const float e2i = (float)draw_dur(pars, CVB_DUR_exp2inf, ia.seed, t, gi, 0);
+        const float e2i = (float)x_exp2inf;
         PF(P, dur_exp2inf)[i] = e2i;
         PF(P, date_exposed)[i] = tf;
         const float d_inf = fadd(e2i, tf);
@@ -119,45 +151,45 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
 
         // prognosis tree (people.py:522-580)
         const float p_symp = prog_prob_imm(pars.rel_symp[v], in_symp_prob, in_symp_imm);
-        if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, gi, 1) < (double)p_symp)) {
-            const double d = draw_dur(pars, CVB_DUR_asym2rec, ia.seed, t, gi, 2);
+        if (!(u_symp < (double)p_symp)) {
+            const double d = x_asym2rec;
             d_rec = (float)dadd((double)d_inf, d);
             dur_disease = (float)dadd((double)e2i, d);
             symp_class = 0;
         } else {
             is_symp_f = true;
-            const float i2s = (float)draw_dur(pars, CVB_DUR_inf2sym, ia.seed, t, gi, 2);
+            const float i2s = (float)x_inf2sym;
             PF(P, dur_inf2sym)[i] = i2s;
             d_symp = fadd(d_inf, i2s);
             const float p_sev = prog_prob_imm(pars.rel_severe[v], in_sev_prob, in_sev_imm);
-            if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, gi, 3) < (double)p_sev)) {
-                const double d = draw_dur(pars, CVB_DUR_mild2rec, ia.seed, t, gi, 4);
+            if (!(u_sev < (double)p_sev)) {
+                const double d = x_mild2rec;
                 d_rec = (float)dadd((double)d_symp, d);
                 dur_disease = (float)dadd((double)fadd(e2i, i2s), d);
                 symp_class = 1;
             } else {
                 is_sev_f = true;
                 symp_class = 2;
-                const float s2s = (float)draw_dur(pars, CVB_DUR_sym2sev, ia.seed, t, gi, 4);
+                const float s2s = (float)x_sym2sev;
                 PF(P, dur_sym2sev)[i] = s2s;
                 d_sev = fadd(d_symp, s2s);
                 const float p_crit = prog_prob_fac(pars.rel_crit[v], in_crit_prob, hosp_max ? pars.no_hosp_factor : 1.0f);
-                if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, gi, 5) < (double)p_crit)) {
-                    const double d = draw_dur(pars, CVB_DUR_sev2rec, ia.seed, t, gi, 6);
+                if (!(u_crit < (double)p_crit)) {
+                    const double d = x_sev2rec;
                     d_rec = (float)dadd((double)d_sev, d);
                     dur_disease = (float)dadd((double)fadd(fadd(e2i, i2s), s2s), d);
                 } else {
-                    const float s2c = (float)draw_dur(pars, CVB_DUR_sev2crit, ia.seed, t, gi, 6);
+                    const float s2c = (float)x_sev2crit;
                     PF(P, dur_sev2crit)[i] = s2c;
                     d_crit = fadd(d_sev, s2c);
                     const float p_death = prog_prob_fac(pars.rel_death[v], in_death_prob, icu_max ? pars.no_icu_factor : 1.0f);
                     const float pre = fadd(fadd(fadd(e2i, i2s), s2s), s2c);
-                    if (!(keyed_uniform(ia.seed, P_INFECT, 0, t, gi, 7) < (double)p_death)) {
-                        const double d = draw_dur(pars, CVB_DUR_crit2rec, ia.seed, t, gi, 8);
+                    if (!(u_death < (double)p_death)) {
+                        const double d = x_crit2rec;
                         d_rec = (float)dadd((double)d_crit, d);
                         dur_disease = (float)dadd((double)pre, d);
                     } else {
-                        const double d = draw_dur(pars, CVB_DUR_crit2die, ia.seed, t, gi, 8);
+                        const double d = x_crit2die;
                         PF(P, date_dead)[i] = (float)dadd((double)d_crit, d);
                         dur_disease = (float)dadd((double)pre, d);
                         d_rec = nanf32();
@@ -182,8 +214,8 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
             if (in_nab > 0.0f) {
                 PF(P, peak_nab)[i] = fmul(in_peak, pars.nab_boost);
             } else {
-                double x = dist_from_normal(pars.nab_init, keyed_normal(ia.seed, P_INFECT, 0, t, gi, 9));
-                double level = pow(2.0, x);
+                double x = x_nab;
+                double level = exp2(x);                   // 2**x (NumPy pow in the reference; peak_nab is compared at 1e-6)
                 double scale = symp_class == 0 ? pars.rel_imm_asymp : (symp_class == 1 ? pars.rel_imm_mild : pars.rel_imm_severe);
                 PF(P, peak_nab)[i] = (float)dmul(dmul(level, scale), pars.nab_norm);
             }
@@ -242,7 +274,7 @@ static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t lis
     ia.hosp_max = hosp_max; ia.icu_max = icu_max;
     ia.id0 = s->partitioned ? s->id0 : 0;
     ia.hit_src = hits ? s->hit_src : nullptr; ia.hit_key = hits ? s->hit_key : nullptr; ia.hit_cap = s->hit_cap;
-    int grid = grid_for(max_items, kThreads, 148 * 4);
+    int grid = grid_for(max_items * 16, kThreads, 148 * 4);       // sixteen lanes per agent
     infect_kernel<<<grid, kThreads, 0, st>>>(s->people, s->pars, L, ia, s->cand, s->n_cand, s->infect_key, s->beds, s->res, s->log);
     CVB_LAUNCH_CHECK();
     return 0;

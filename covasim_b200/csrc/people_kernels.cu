@@ -21,9 +21,35 @@ namespace cvb {
 enum { PRE_INFECTIOUS = 0, PRE_SYMPTOMATIC, PRE_SEVERE, PRE_CRITICAL, PRE_RECOVERIES, PRE_DEATHS, PRE_KNOWN_DEATHS,
        PRE_BED_SEVERE, PRE_BED_CRITICAL, PRE_NK };
 
+// check_immunity for one queued agent x variant (immunity.py:303-350): float64 arithmetic, rounded once to float32.
+// entry = {agent, nab bits, packed (variant | recovered variant + 1 << 4 | vaccine source << 8 | vaccinated << 12), -}
+__device__ __forceinline__ void immunity_eval(const uint4 en, int64_t n, const cvb_pars& pars, float* __restrict__ sus_imm,
+                                              float* __restrict__ symp_imm, float* __restrict__ sev_imm) {
+    const int64_t i = (int64_t)en.x;
+    const float nab = __uint_as_float(en.y);
+    const int v = (int)(en.z & 15u), rvi = (int)((en.z >> 4) & 15u) - 1, vsi = (int)((en.z >> 8) & 15u);
+    const bool vacc = (en.z >> 12) & 1u;
+    const double natural = rvi >= 0 ? (double)pars.immunity[v][rvi] : 0.0;
+    const double vaccine = vacc ? pars.vaccine_imm[vsi][v] : 0.0;
+    const double enab = dmul((double)nab, fmax(natural, vaccine));
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
+    if (enab > 0.0)          // 0**beta == 0 -> protection exactly 0
+        calc_ve3(enab, pars.exp_alpha_inf, pars.beta_inf, pars.exp_alpha_symp_inf, pars.beta_symp_inf,
+                 pars.exp_alpha_sev_symp, pars.beta_sev_symp, s0, s1, s2);
+    sus_imm[(int64_t)v * n + i] = s0;
+    symp_imm[(int64_t)v * n + i] = s1;
+    sev_imm[(int64_t)v * n + i] = s2;
+}
+
+constexpr int kImmQueueCap = 64;            // < 32 left over + up to 32 appended per (agent slot, variant) step
+
 __global__ void __launch_bounds__(kThreads) states_pre_kernel(PeoplePtrs P, const __grid_constant__ cvb_pars pars, int64_t n, int32_t t, bool vec,
         unsigned long long* __restrict__ counters, unsigned long long* __restrict__ vcounters, unsigned long long* __restrict__ beds) {
     __shared__ int s_cnt[PRE_NK + CVB_MAX_VARIANTS];
+    __shared__ uint4 s_queue[(kThreads / 32) * kImmQueueCap];
+    uint4* q_imm = s_queue + warp_id() * kImmQueueCap;
+    int qn = 0;                                                     // warp-uniform queue length
+    const unsigned lt_mask = (1u << lane_id()) - 1u;
     const int nv = pars.n_variants;
     const bool waning = pars.use_waning != 0;
     const bool vaxpars = pars.has_vaccine_pars != 0;
@@ -50,8 +76,10 @@ __global__ void __launch_bounds__(kThreads) states_pre_kernel(PeoplePtrs P, cons
     float* sus_imm = PF(P, sus_imm); float* symp_imm = PF(P, symp_imm); float* sev_imm = PF(P, sev_imm);
     const float qnan = nanf32();
 
+    // the loop is warp-uniform (whole warps stay in it: the immunity queue is filled with ballots); agents past n are inert
     const int64_t n_groups = (n + kAPT - 1) / kAPT;
-    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n_groups_pad = (n_groups + 31) / 32 * 32;
+    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups_pad; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i0 = g * kAPT;
         // ---- all loads up front (independent, coalesced) ----
         const uint32_t w_exp = load4b(exposed, i0, n, vec), w_inf = load4b(infectious, i0, n, vec), w_symp = load4b(symptomatic, i0, n, vec);
@@ -73,14 +101,15 @@ __global__ void __launch_bounds__(kThreads) states_pre_kernel(PeoplePtrs P, cons
             load4(d_inf, i0, n, vec, qnan, di); load4(d_symp, i0, n, vec, qnan, ds); load4(d_sev, i0, n, vec, qnan, dv);
             load4(d_crit, i0, n, vec, qnan, dc); load4(d_dead, i0, n, vec, qnan, dd); load4(exp_var, i0, n, vec, qnan, ev);
         }
+        float rec_var_now[4];
 #pragma unroll
         for (int k = 0; k < kAPT; ++k) {
             const int64_t i = i0 + k;
-            if (i >= n) break;
+            rec_var_now[k] = rv[k];
+            if (i >= n) continue;
             const bool was_exposed = flag(w_exp, k);               // is_exp is taken once, before any transition (people.py:169)
             bool sev_now = flag(w_sev, k), crit_now = flag(w_crit, k);
             bool diag_now = flag(w_diag, k);
-            float rec_var_now = rv[k];
             if (was_exposed) {
                 // infectious (people.py:222-232)
                 if (!flag(w_inf, k) && due(di[k], t)) {
@@ -103,7 +132,7 @@ __global__ void __launch_bounds__(kThreads) states_pre_kernel(PeoplePtrs P, cons
                     exposed[i] = 0; infectious[i] = 0; symptomatic[i] = 0; severe[i] = 0; critical[i] = 0;
                     sev_now = false; crit_now = false;
                     recovered[i] = 1;
-                    rec_var[i] = ev[k]; rec_var_now = ev[k];
+                    rec_var[i] = ev[k]; rec_var_now[k] = ev[k];
                     inf_var[i] = qnan;
                     exp_var[i] = qnan;
                     for (int v = 0; v < nv; ++v) { exp_by_var[(int64_t)v * n + i] = 0; inf_by_var[(int64_t)v * n + i] = 0; }
@@ -121,34 +150,51 @@ __global__ void __launch_bounds__(kThreads) states_pre_kernel(PeoplePtrs P, cons
                     susceptible[i] = 0; exposed[i] = 0; infectious[i] = 0; symptomatic[i] = 0; severe[i] = 0; critical[i] = 0;
                     sev_now = false; crit_now = false;
                     known_contact[i] = 0; quarantined[i] = 0; recovered[i] = 0;
-                    inf_var[i] = qnan; exp_var[i] = qnan; rec_var[i] = qnan; rec_var_now = qnan;
+                    inf_var[i] = qnan; exp_var[i] = qnan; rec_var[i] = qnan; rec_var_now[k] = qnan;
                     ++c[PRE_DEATHS];
                 }
             }
             c[PRE_BED_SEVERE] += sev_now;
             c[PRE_BED_CRITICAL] += crit_now;
+        }
 
-            // check_immunity (immunity.py:303-350): float64 arithmetic, rounded once to float32
-            if (waning) {
+        // check_immunity (immunity.py:303-350).  The float64 log / exp work is needed only for agents with neutralising
+        // antibodies and a non-zero immunity factor.  Evaluating it in the per-agent loop above would make every warp that
+        // holds ONE such agent among its 128 run the ~300-instruction path (four times); instead those agents are appended
+        // to the warp's shared-memory queue (ballot compaction) and evaluated 32 at a time by full warps.
+        if (waning) {
+#pragma unroll
+            for (int k = 0; k < kAPT; ++k) {
+                const int64_t i = i0 + k;
+                const bool valid = i < n;
                 const bool was_inf = due(dr[k], t);
-                const int rvi = was_inf ? (int)rec_var_now : -1;
-                const bool vacc = vaxpars && flag(w_vacc, k);
+                const int rvi = was_inf ? (int)rec_var_now[k] : -1;
+                const bool rv_ok = rvi >= 0 && rvi < nv;
                 const int vsi = vs[k];
+                const bool vacc = vaxpars && flag(w_vacc, k) && vsi >= 0 && vsi < CVB_MAX_VACCINES;
+                const bool heavy = valid && nb[k] > 0.0f && (rv_ok || vacc);
+                const unsigned packed = ((unsigned)(rv_ok ? rvi + 1 : 0) << 4) | ((unsigned)(vacc ? vsi : 0) << 8) | ((unsigned)vacc << 12);
                 for (int v = 0; v < nv; ++v) {
-                    const double natural = (rvi >= 0 && rvi < nv) ? (double)pars.immunity[v][rvi] : 0.0;
-                    const double vaccine = (vacc && vsi >= 0 && vsi < CVB_MAX_VACCINES) ? pars.vaccine_imm[vsi][v] : 0.0;
-                    const double enab = dmul((double)nb[k], fmax(natural, vaccine));
-                    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f;
-                    if (enab > 0.0)          // 0**beta == 0 -> protection exactly 0
-                        calc_ve3(enab, pars.exp_alpha_inf, pars.beta_inf, pars.exp_alpha_symp_inf, pars.beta_symp_inf,
-                                 pars.exp_alpha_sev_symp, pars.beta_sev_symp, s0, s1, s2);
-                    sus_imm[(int64_t)v * n + i] = s0;
-                    symp_imm[(int64_t)v * n + i] = s1;
-                    sev_imm[(int64_t)v * n + i] = s2;
+                    if (valid && !heavy) {                         // no NAbs or no immunity source: protection exactly 0
+                        sus_imm[(int64_t)v * n + i] = 0.0f;
+                        symp_imm[(int64_t)v * n + i] = 0.0f;
+                        sev_imm[(int64_t)v * n + i] = 0.0f;
+                    }
+                    const unsigned m = __ballot_sync(0xFFFFFFFFu, heavy);
+                    if (heavy) q_imm[qn + __popc(m & lt_mask)] = make_uint4((unsigned)i, __float_as_uint(nb[k]), packed | (unsigned)v, 0u);
+                    qn += __popc(m);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        qn -= 32;
+                        const uint4 en = q_imm[qn + lane_id()];
+                        __syncwarp();
+                        immunity_eval(en, n, pars, sus_imm, symp_imm, sev_imm);
+                    }
                 }
             }
         }
     }
+    if (waning && lane_id() < qn) immunity_eval(q_imm[lane_id()], n, pars, sus_imm, symp_imm, sev_imm);
     reduce_counters(c, s_cnt);
     reduce_counters(cv, s_cnt + PRE_NK);
     __syncthreads();
@@ -349,8 +395,10 @@ __global__ void schedule_quar_kernel(const int32_t* __restrict__ inds, int64_t n
 constexpr int kNStocks = 13;
 __global__ void __launch_bounds__(kThreads) nab_count_kernel(PeoplePtrs P, const __grid_constant__ cvb_pars pars, int64_t n, int32_t t, bool vec,
         const double* __restrict__ nab_kin, int64_t nab_kin_len, unsigned long long* __restrict__ counters,
-        unsigned long long* __restrict__ vcounters, double* __restrict__ partial) {
+        unsigned long long* __restrict__ vcounters, double* __restrict__ partial, unsigned int* __restrict__ ticket,
+        double* __restrict__ sums_row) {
     __shared__ int s_cnt[kNStocks + 1 + 2 * CVB_MAX_VARIANTS];
+    __shared__ bool s_last;
     __shared__ double s_sum[3][kThreads / 32];
     const int nv = pars.n_variants;
     const bool waning = pars.use_waning != 0;
@@ -441,17 +489,24 @@ __global__ void __launch_bounds__(kThreads) nab_count_kernel(PeoplePtrs P, const
                                     ((q & 1) ? CVB_VC_n_infectious_by_variant : CVB_VC_n_exposed_by_variant), v);
         }
     }
+    // The last CTA to finish adds up the per-CTA partial sums (no second launch): one warp per sum, lanes stride over the
+    // partials in a fixed pattern, then a fixed shuffle tree -- the result does not depend on which CTA came last.
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last && threadIdx.x < 96) {
+        __threadfence();
+        const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        double v = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(partial + (int64_t)b * 3 + q);
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
+        if (lane == 0) sums_row[q] = v;
+        if (threadIdx.x == 0) *ticket = 0;                          // ready for the next launch
+    }
 }
 
-// one warp per sum, lanes stride over the CTA partials in a fixed pattern, then a fixed shuffle tree: deterministic
-__global__ void __launch_bounds__(96) finish_sums_kernel(const double* __restrict__ partial, int n_blocks, double* __restrict__ sums_row) {
-    const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double v = 0.0;
-    for (int b = lane; b < n_blocks; b += 32) v += partial[(int64_t)b * 3 + q];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
-    if (lane == 0) sums_row[q] = v;
-}
 
 }  // namespace cvb
 
@@ -550,9 +605,8 @@ int cvb_update_nab_count(cvb_sim* s, int32_t t, cvb_stream st) {
     int grid = grid_for((s->n + kAPT - 1) / kAPT, kThreads, 148 * 4);
     if (ensure_f64(&s->partial, &s->partial_cap, (int64_t)grid * 3)) return 1;
     nab_count_kernel<<<grid, kThreads, 0, (cudaStream_t)st>>>(s->people, s->pars, s->n, t, vector_ok(s), s->nab_kin, s->nab_kin_len,
-                                                             s->res.counters, s->res.vcounters, s->partial);
-    CVB_LAUNCH_CHECK();
-    finish_sums_kernel<<<1, 96, 0, (cudaStream_t)st>>>(s->partial, grid, s->res.sums + (int64_t)t * 4);
+                                                             s->res.counters, s->res.vcounters, s->partial,
+                                                             reinterpret_cast<unsigned int*>(s->dev_scalars + 8), s->res.sums + (int64_t)t * 4);
     CVB_LAUNCH_CHECK();
     return 0;
 }

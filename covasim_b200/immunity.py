@@ -53,10 +53,14 @@ class variant:
     def apply(self, sim):
         ''' Import infections of this variant (reference immunity.py:117-130); host NumPy-stream draws, device infect '''
         if np.any(self.days == sim.t):
-            sus = sim._global_true('susceptible')          # global ids (all ranks of an agent-partitioned run)
             scale = sim.rescale_vec[sim.t] if self.rescale else 1.0
             n_imports = int(np.floor(self.n_imports / scale + sim.rng.np_.random_sample()))      # sc.randround
-            who = sim.rng.np_.choice(sus, n_imports, replace=False)
+            if sim.rng_mode == 'mt':                   # replay mode: the reference's O(N) permutation, same stream use
+                import torch
+                sus = torch.nonzero(sim.people.susceptible).flatten().cpu().numpy()
+                who = sim.rng.np_.choice(sus, n_imports, replace=False)
+            else:
+                who, _ = sim._choose_true('susceptible', sim.rng.np_, n_imports)
             sim.people.infect(who, layer='importation', variant=self.index)
             sim._host_add('n_imports', sim.t, n_imports)
 

@@ -140,7 +140,7 @@ class test_prob(Intervention):
         t = sim.t
         if t < self.start_day or (self.end_day is not None and t > self.end_day):
             return
-        _capi.call('cvb_test_prob', sim._handle, t, C.byref(self._c), sim._stream_ptr)
+        sim._call('cvb_test_prob', sim._handle, t, C.byref(self._c), sim._stream_ptr)
 
 
 class contact_tracing(Intervention):
@@ -184,13 +184,13 @@ class contact_tracing(Intervention):
         if t < self.start_day or (self.end_day is not None and t > self.end_day):
             return
         if sim._comm is not None:          # agent-partitioned: local cases -> all-gathered bitmap -> local contacts of every case
-            _capi.call('cvb_trace_select_cases', sim._handle, t, C.byref(self._c), sim._stream_ptr)
+            sim._call('cvb_trace_select_cases', sim._handle, t, C.byref(self._c), sim._stream_ptr)
             sim._exchange_cases()
-            _capi.call('cvb_trace_notify_contacts', sim._handle, t, C.byref(self._c), sim._stream_ptr)
+            sim._call('cvb_trace_notify_contacts', sim._handle, t, C.byref(self._c), sim._stream_ptr)
             return
         if sim._adj_dirty:
             sim._build_adjacency()
-        _capi.call('cvb_contact_tracing', sim._handle, t, C.byref(self._c), sim._stream_ptr)
+        sim._call('cvb_contact_tracing', sim._handle, t, C.byref(self._c), sim._stream_ptr)
 
 
 class vaccinate_prob(Intervention):
@@ -271,4 +271,4 @@ class vaccinate_prob(Intervention):
             return
         self._c.first_dose_today = int(first)
         self._c.second_dose_today = int(second)
-        _capi.call('cvb_vaccinate_prob', sim._handle, t, C.byref(self._c), self.doses.data_ptr(), self.due_day.data_ptr(), sim._stream_ptr)
+        sim._call('cvb_vaccinate_prob', sim._handle, t, C.byref(self._c), self.doses.data_ptr(), self.due_day.data_ptr(), sim._stream_ptr)

@@ -355,12 +355,22 @@ class Sim:
         B = self._part_bufs
         self._comm.all_gather(B['case_global'], B['case_local'])
 
-    def _global_true(self, key):
-        ''' Global ids of the agents whose flag ``key`` is set, over all ranks (host array; rare events only) '''
-        local = (torch.nonzero(self.people[key]).flatten() + self.id0).cpu().numpy()
-        if self._comm is None:
-            return local
-        return np.concatenate(self._comm.gather_objects(local))
+    def _choose_true(self, key, stream, k):
+        '''
+        Up to ``k`` distinct agents among those whose flag ``key`` is set, over all ranks: positions in the ascending list
+        of flagged agents are drawn on the host (cvu.choose_distinct), the flagged list itself never leaves the device.
+        Returns (global ids owned by this rank as a device tensor, number chosen overall).
+        '''
+        nz = torch.nonzero(self.people[key]).flatten()
+        counts = [int(nz.numel())] if self._comm is None else [int(c) for c in self._comm.gather_objects(int(nz.numel()))]
+        total = sum(counts)
+        k = min(int(k), total)
+        pos = cvu.choose_distinct(stream, total, k) if k > 0 else np.zeros(0, dtype=np.int64)
+        rank = 0 if self._comm is None else self._comm.rank
+        off = sum(counts[:rank])
+        mine = pos[(pos >= off) & (pos < off + counts[rank])] - off
+        who = nz[torch.as_tensor(mine, dtype=torch.int64, device=self.device)] + self.id0
+        return who.to(torch.int32), k
 
     def _build_adjacency(self):
         '''
@@ -573,7 +583,10 @@ class Sim:
     def init_infections(self, force=False):
         pars = self.pars
         if pars['pop_infected']:
-            inds = self.rng.nb.choice(pars['pop_size'], int(pars['pop_infected']), replace=False)       # cvu.choose: Numba stream
+            if self.rng_mode == 'mt':
+                inds = self.rng.nb.choice(pars['pop_size'], int(pars['pop_infected']), replace=False)   # cvu.choose: Numba stream
+            else:
+                inds = cvu.choose_distinct(self.rng.nb, pars['pop_size'], int(pars['pop_infected']))
             self.people.infect(inds, layer='seed_infection', count_flows=False)
 
     def _log_append(self, source, target, layer, variant):
@@ -623,7 +636,7 @@ class Sim:
         if pars['n_imports']:                                                          # reference sim.py:583-588
             n_imports = int(self.rng.nb.poisson(f32(pars['n_imports'] / self.rescale_vec[t]), 1)[0])
             if n_imports > 0:
-                who = self.rng.nb.choice(pars['pop_size'], n_imports, replace=False)
+                who = cvu.choose_distinct(self.rng.nb, pars['pop_size'], n_imports)          # (replay mode has its own step)
                 people.infect(who, hosp_max='auto', icu_max='auto', layer='importation')
                 self._host_add('n_imports', t, n_imports)
         for v in pars['variants']:
@@ -644,6 +657,12 @@ class Sim:
         self.t += 1
         if self.t == self.npts:
             self.complete = True
+
+    def _call(self, name, *args):
+        ''' C-ABI call, timed with CUDA events when ``kernel_timers`` is a dict (interventions use this too) '''
+        if self.kernel_timers is None:
+            return _capi.call(name, *args)
+        return self._timed_call(name, *args)
 
     def _timed_call(self, name, *args):
         ''' _capi.call bracketed by CUDA events on the launching stream (bench.py's per-kernel timing) '''

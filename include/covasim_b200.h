@@ -110,7 +110,8 @@ int cvb_bind_adjacency(cvb_sim* s, const int64_t* adj_ptr, const void* adj, int6
  *   case_bits_local u32[chunk/32] written by cvb_trace_select_cases -> case_bits_global u32[world*chunk/32] read by cvb_trace_notify_contacts
  * One code byte (variant, symptomatic, isolated, quarantined, early viral load, breakthrough) plus the replicated
  * initial rel_trans float32[n_global] is all a GPU needs to rebuild a remote source's per-layer transmissibility.
- * hit_capacity bounds the successful transmissions a rank can record per day (>= n_agents is used if smaller).
+ * hit_capacity bounds the successful transmissions a rank can record per day (<= 0: max(n_agents, 65536)); a day that
+ * exceeds it is reported by cvb_partition_status, never dropped silently.
  * ---------------------------------------------------------------------------------------------- */
 int cvb_set_partition(cvb_sim* s, int64_t id0, int64_t n_global, int64_t chunk, int32_t world, const float* rel_trans_global,
                       uint8_t* codes_local, const uint8_t* codes_global, uint32_t* case_bits_local, const uint32_t* case_bits_global,

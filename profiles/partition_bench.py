@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+'''
+Throughput of ONE large agent-partitioned simulation (BASELINE config 4 recipe, scaled): hybrid population, alpha + delta
+variants, waning immunity, test_prob + contact_tracing + vaccinate_prob + booster.
+
+    python profiles/partition_bench.py --pop-size 4000000 --n-days 60                               # 1 GPU, unpartitioned
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29512 \
+        profiles/partition_bench.py --pop-size 4000000 --n-days 60                                  # N GPUs, NCCL all-gathers
+
+Prints one JSON line (rank 0): agent-days/s over the day loop (CUDA events, max over ranks), the per-day exchange volume
+and the summary of the epidemic (identical for every N: the run is bit-reproducible across partitionings).
+'''
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--pop-size', type=int, default=4_000_000)
+    ap.add_argument('--n-days', type=int, default=60)
+    ap.add_argument('--reps', type=int, default=2)
+    ap.add_argument('--profile', action='store_true', help='CUDA-event time of every C-ABI call of one extra run')
+    args = ap.parse_args()
+    import torch.distributed as dist
+    import covasim_b200 as cv
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    n = args.pop_size
+    pars = dict(pop_size=n, pop_type='hybrid', n_days=args.n_days, pop_infected=max(1, n // 200), rand_seed=1, verbose=0, use_waning=True)
+    variants = [cv.variant('alpha', days=5, n_imports=max(10, n // 20000)), cv.variant('delta', days=15, n_imports=max(10, n // 20000))]
+    ivs = [cv.test_prob(symp_prob=0.1, asymp_prob=0.01, start_day=10), cv.contact_tracing(trace_probs=0.3, start_day=15),
+           cv.vaccinate_prob('pfizer', days=list(range(10, 30)), prob=0.01), cv.vaccinate_prob('pfizer', days=[40], prob=0.05, booster=True, label='booster')]
+    t0 = time.time()
+    sim = cv.Sim(pars, variants=variants, interventions=ivs, pop_exact=False, partition=True if world > 1 else None)
+    sim.initialize()
+    torch.cuda.synchronize()
+    t_init = time.time() - t0
+    snap = sim.snapshot(pinned=False)
+    best = None
+    for rep in range(args.reps + 1):
+        sim.restore(snap)
+        sim.set_seed()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        while not sim.complete:
+            sim.step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            tt = torch.tensor([ms], device='cuda', dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        if rep > 0:
+            best = ms if best is None else min(best, ms)
+        sim.finalize()
+    kernels = None
+    if args.profile:
+        sim.restore(snap)
+        sim.set_seed()
+        sim.kernel_timers = {}
+        while not sim.complete:
+            sim.step()
+        torch.cuda.synchronize()
+        kernels = {k: round(float(np.sum([x.elapsed_time(y) for x, y in v])) * 1e3 / sim.npts, 1) for k, v in sim.kernel_timers.items()}
+        sim.kernel_timers = None
+        sim.finalize()
+    if rank == 0:
+        out = dict(kernel_us_per_day=kernels, workload='C4 recipe (hybrid, alpha+delta, waning, test_prob+contact_tracing+vaccinate_prob+booster)', pop_size=n, n_days=args.n_days,
+                   n_gpus=world, partitioned=world > 1, ms_per_run=best, us_per_day=1e3 * best / sim.npts, agent_days_per_s=n * sim.npts / (best / 1e3),
+                   init_s=t_init, exchange_bytes_per_day_per_rank=(sim._chunk * world + sim._chunk * world // 8) if world > 1 else 0,
+                   cum_infections=sim.summary['cum_infections'], cum_deaths=sim.summary['cum_deaths'], cum_diagnoses=sim.summary['cum_diagnoses'],
+                   cum_doses=sim.summary['cum_doses'], edges_local=None if sim._adj is None else int(sim._adj[1].shape[0]))
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -92,8 +92,8 @@ def test_hit_capacity_overflow_is_reported():
     import covasim_b200 as cv
     from covasim_b200 import partition as cvpart
     comms = cvpart.LocalComm.make(2)
-    # 100k agents, everyone very infectious: far more than the 65536-hit floor on the first days
-    sims = [cv.Sim(pop_size=150_000, pop_infected=30_000, n_days=8, beta=0.9, verbose=0, partition=comms[r], pop_exact=False) for r in range(2)]
+    # very infectious and a deliberately tiny capacity: more successful transmissions per day than the 1024 slots
+    sims = [cv.Sim(pop_size=20_000, pop_infected=4_000, n_days=10, beta=0.5, verbose=0, partition=comms[r], hit_capacity=1024) for r in range(2)]
     cvpart.run_local(sims, lambda s: s.initialize())
     with pytest.raises(RuntimeError, match='hit_capacity'):
         cvpart.run_local(sims, lambda s: s.run())

@@ -359,7 +359,9 @@ struct PartHits {                         // one entry per successful transmissi
     int32_t* tgt; int32_t* src; unsigned long long* key; unsigned int* n; unsigned int* dropped; int64_t cap;
 };
 
-template <bool MULTI>
+// LANES lanes per transmitter (32, 16 or 8): with W ranks a transmitter's row holds ~36/W local entries, so a full warp per
+// row would idle most of its lanes
+template <bool MULTI, int LANES>
 __global__ void __launch_bounds__(kThreads) edge_pass_partition_kernel(TransRecords rec, const __grid_constant__ EdgeParams ep,
         const __grid_constant__ cvb_pars pars, const long long* __restrict__ adj_ptr, const uint4* __restrict__ adj,
         const int32_t* __restrict__ glist, const unsigned int* __restrict__ n_glist, const uint8_t* __restrict__ codes,
@@ -368,11 +370,11 @@ __global__ void __launch_bounds__(kThreads) edge_pass_partition_kernel(TransReco
     const unsigned int n_trans = *n_glist;
     unsigned long long visited = 0;
     const int64_t n = ep.n;                                              // local agents
-    const int lane = lane_id();
-    const unsigned int warps_total = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & (LANES - 1);
+    const unsigned int groups_total = (gridDim.x * blockDim.x) / LANES;
     const float vl_early = viral_load_value(true, pars.frac_time, pars.load_ratio);
     const float vl_late = viral_load_value(false, pars.frac_time, pars.load_ratio);
-    for (unsigned int ti = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ti < n_trans; ti += warps_total) {
+    for (unsigned int ti = (blockIdx.x * blockDim.x + threadIdx.x) / LANES; ti < n_trans; ti += groups_total) {
         const int i = glist[ti];                                         // global id of the source
         const long long beg = adj_ptr[i], end = adj_ptr[i + 1];
         if (beg == end) continue;                                        // no contact on this GPU
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(kThreads) edge_pass_partition_kernel(TransReco
         if (code & 128u) rt = fmul(rt, pars.trans_redux);
         const float vl = early ? vl_early : vl_late;
         const float beta_v = ep.beta[vi];
-        for (long long off = beg + lane; off < end; off += 32) {
+        for (long long off = beg + lane; off < end; off += LANES) {
             const uint4 en = __ldg(adj + off);
             const int j = (int)en.x;                                     // LOCAL target
             const int l = (int)(en.z >> 1);
@@ -404,7 +406,7 @@ __global__ void __launch_bounds__(kThreads) edge_pass_partition_kernel(TransReco
                     const unsigned long long key = ((unsigned long long)vi << 56) | ((unsigned long long)l << 48) |
                                                    ((unsigned long long)dir << 40) | (unsigned long long)e;
                     atomicMin(infect_key + j, key);
-                    const unsigned int pos = warp_append32(hits.n);
+                    const unsigned int pos = warp_append32(hits.n);      // aggregated over the lanes active here (any group)
                     if ((int64_t)pos < hits.cap) { hits.tgt[pos] = j; hits.src[pos] = i; hits.key[pos] = key; }
                     else atomicAdd(hits.dropped, 1u);
                 }
@@ -492,10 +494,14 @@ extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
         PartHits hits{s->cand, s->hit_src, s->hit_key, s->n_cand, s->part_flags, s->hit_cap};
         unsigned long long* work_row = s->edge_work + (int64_t)t * 2;
         const int grid = 148 * 8;
-        if (multi) edge_pass_partition_kernel<true><<<grid, kThreads, 0, st>>>(s->rec, ep, s->pars, s->padj_ptr, s->padj, s->glist, s->n_glist,
-                                                                             s->codes_global, s->rel_trans_global, s->infect_key, hits, work_row);
-        else edge_pass_partition_kernel<false><<<grid, kThreads, 0, st>>>(s->rec, ep, s->pars, s->padj_ptr, s->padj, s->glist, s->n_glist,
-                                                                         s->codes_global, s->rel_trans_global, s->infect_key, hits, work_row);
+        // lanes per transmitter from the mean local row length (entries per agent slot, both directions)
+        const double mean_row = (double)s->padj_entries / (double)(s->n_global > 0 ? s->n_global : 1);
+#define CVB_PART(M, LN) edge_pass_partition_kernel<M, LN><<<grid, kThreads, 0, st>>>(s->rec, ep, s->pars, s->padj_ptr, s->padj, s->glist, s->n_glist, \
+                                                                                    s->codes_global, s->rel_trans_global, s->infect_key, hits, work_row)
+        if (mean_row >= 24.0) { if (multi) CVB_PART(true, 32); else CVB_PART(false, 32); }
+        else if (mean_row >= 12.0) { if (multi) CVB_PART(true, 16); else CVB_PART(false, 16); }
+        else { if (multi) CVB_PART(true, 8); else CVB_PART(false, 8); }
+#undef CVB_PART
         CVB_LAUNCH_CHECK();
         return 0;
     }

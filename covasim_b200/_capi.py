@@ -89,6 +89,7 @@ PROTOTYPES = dict(
     cvb_partition_status=[_P, _P],
     cvb_bind_results=[_P, _P, _P, _P],
     cvb_bind_log=[_P, _P, _P, _P, _P, _P, _i64, _P],
+    cvb_keyed_uniform=[_u64, C.c_uint32, C.c_uint32, _i32, _i64, _i64, C.c_uint32, _P, _P],
     cvb_compute_viral_load=[_i32, _P, _P, _P, _f32, _f32, _f32, _P, _i64, _P],
     cvb_compute_trans_sus=[_P, _P, _P, _P, _f32, _P, _P, _P, _P, _f32, _f32, _f32, _P, _P, _P, _i64, _P],
     cvb_infections_count=[_P, _f32, _P, _P, _P, _i64, _P, _P, C.POINTER(_i64), _P],

@@ -69,7 +69,7 @@ CVB_HD bool due(float date, int t) { return (float)t >= date; }
 
 // ---- Philox4x32-10 (Salmon et al., SC'11) -----------------------------------------------------
 enum purpose : uint32_t { P_EDGE = 1, P_INFECT = 2, P_TEST = 3, P_TEST_SENS = 4, P_TEST_LOSS = 5, P_TRACE = 6,
-                          P_VACC = 7, P_NAB_VACC = 8, P_DYNLAYER = 9 };
+                          P_VACC = 7, P_NAB_VACC = 8, P_DYNLAYER = 9, P_POP = 10 };
 
 struct u32x4 { uint32_t x, y, z, w; };
 

@@ -16,6 +16,13 @@ __global__ void __launch_bounds__(kThreads) viral_load_kernel(int32_t t, const f
 }
 
 // ---- A3 ---------------------------------------------------------------------------------------
+// keyed uniforms for the device-side population generator (covasim_b200/population.py:make_keyed_pop)
+__global__ void __launch_bounds__(kThreads) keyed_uniform_kernel(uint64_t seed, uint32_t purpose, uint32_t sub, int32_t day, int64_t index0,
+        int64_t n, uint32_t slot, double* __restrict__ out) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        out[k] = keyed_uniform(seed, purpose, sub, day, index0 + k, slot);
+}
+
 __global__ void __launch_bounds__(kThreads) trans_sus_kernel(const float* __restrict__ rel_trans, const float* __restrict__ rel_sus,
         const uint8_t* __restrict__ inf, const uint8_t* __restrict__ sus, float beta_layer, const float* __restrict__ vload,
         const uint8_t* __restrict__ symp, const uint8_t* __restrict__ iso, const uint8_t* __restrict__ quar,
@@ -238,6 +245,15 @@ static inline bool aligned16(const void* a, const void* b, const void* c) {
 using namespace cvb;
 
 extern "C" {
+
+int cvb_keyed_uniform(uint64_t seed, uint32_t purpose, uint32_t sub, int32_t day, int64_t index0, int64_t n, uint32_t slot,
+                      double* out, cvb_stream st) {
+    CVB_REQUIRE(n >= 0 && (n == 0 || out), "cvb_keyed_uniform: bad argument");
+    if (n == 0) return 0;
+    keyed_uniform_kernel<<<grid_for(n, kThreads, 148 * 16), kThreads, 0, (cudaStream_t)st>>>(seed, purpose, sub, day, index0, n, slot, out);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
 
 int cvb_compute_viral_load(int32_t t, const float* date_inf, const float* date_rec, const float* date_dead,
                            float frac_time, float load_ratio, float high_cap, float* out, int64_t n, cvb_stream st) {

@@ -25,7 +25,7 @@ import threading
 import numpy as np
 import torch
 
-__all__ = ['plan', 'build_partition_adjacency', 'DistComm', 'LocalComm', 'run_local']
+__all__ = ['plan', 'build_partition_adjacency', 'build_partition_adjacency_chunks', 'DistComm', 'LocalComm', 'run_local']
 
 
 def plan(n_global, world):
@@ -47,33 +47,50 @@ def build_partition_adjacency(layers, layer_ids, lo, hi, n_slots, device):
     ``layers`` is a list of dicts of 1-D tensors / arrays (p1, p2, beta) holding the WHOLE population's edges.
     Pure torch, device independent (the CPU tests check it against a brute-force loop).
     '''
+    def chunks():
+        for l, layer in zip(layer_ids, layers):
+            yield l, torch.as_tensor(layer['p1']), torch.as_tensor(layer['p2']), torch.as_tensor(layer['beta']), 0
+    return build_partition_adjacency_chunks(chunks(), lo, hi, n_slots, device)
+
+
+def build_partition_adjacency_chunks(chunks, lo, hi, n_slots, device):
+    '''
+    The same from a stream of edge chunks ``(layer id, p1, p2, beta or None, index of the chunk's first edge within its
+    layer)`` -- what the device-side population generator yields -- so that the whole population's edge lists never have
+    to exist at once: only the entries with a local target are kept.
+    '''
     dev = torch.device(device)
-    src, tgt, eid, meta, wts = [], [], [], [], []
-    for l, layer in zip(layer_ids, layers):
-        p1 = torch.as_tensor(layer['p1']).to(dev, torch.int64)
-        p2 = torch.as_tensor(layer['p2']).to(dev, torch.int64)
-        beta = torch.as_tensor(layer['beta']).to(dev, torch.float32)
-        if p1.numel() >= 2 ** 31:
+    src, cols = [], []
+    for l, p1, p2, beta, e0 in chunks:
+        p1 = p1.to(dev, torch.int64)
+        p2 = p2.to(dev, torch.int64)
+        E = p1.numel()
+        if e0 + E >= 2 ** 31:
             raise ValueError('a layer with 2^31 or more edges cannot be indexed by the adjacency')
-        e = torch.arange(p1.numel(), dtype=torch.int64, device=dev)
+        wbits = (torch.ones(E, dtype=torch.float32, device=dev) if beta is None else beta.to(dev, torch.float32)).view(torch.int32)
+        e = torch.arange(e0, e0 + E, dtype=torch.int32, device=dev)
         for d, (a, b) in enumerate(((p1, p2), (p2, p1))):
             keep = (b >= lo) & (b < hi)
+            k = int(keep.sum())
+            ent = torch.empty((k, 4), dtype=torch.int32, device=dev)
+            ent[:, 0] = (b[keep] - lo).to(torch.int32)
+            ent[:, 1] = e[keep]
+            ent[:, 2] = (l << 1) | d
+            ent[:, 3] = wbits[keep]
             src.append(a[keep])
-            tgt.append(b[keep] - lo)
-            eid.append(e[keep])
-            meta.append(torch.full((int(keep.sum()),), (l << 1) | d, dtype=torch.int64, device=dev))
-            wts.append(beta[keep])
+            cols.append(ent)
     src = torch.cat(src) if src else torch.zeros(0, dtype=torch.int64, device=dev)
-    order = torch.sort(src, stable=True).indices
     M = int(src.numel())
     adj = torch.empty((max(M, 1), 4), dtype=torch.int32, device=dev)
-    if M:
-        adj[:M, 0] = torch.cat(tgt)[order].to(torch.int32)
-        adj[:M, 1] = torch.cat(eid)[order].to(torch.int32)
-        adj[:M, 2] = torch.cat(meta)[order].to(torch.int32)
-        adj[:M, 3] = torch.cat(wts)[order].view(torch.int32)
     ptr = torch.zeros(n_slots + 1, dtype=torch.int64, device=dev)
-    ptr[1:] = torch.cumsum(torch.bincount(src, minlength=n_slots), 0)
+    if M:
+        # rows in ascending source order; within a row the order of (layer, direction, edge) as streamed (stable sort)
+        order = torch.sort(src, stable=True).indices
+        torch.cumsum(torch.bincount(src, minlength=n_slots), 0, out=ptr[1:])
+        del src
+        ent = torch.cat(cols)
+        del cols
+        torch.index_select(ent, 0, order, out=adj[:M])
     return ptr, adj, M
 
 

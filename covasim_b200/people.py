@@ -52,13 +52,15 @@ class People:
                 A[name] = torch.zeros(shape, dtype=dt, device=self.device)
         self._age_global = None
         if age is not None:
-            age = np.asarray(age)
+            if not isinstance(age, torch.Tensor):
+                age = np.asarray(age)
             if local_range is not None and len(age) == self.n_global:
                 self._age_global = age                  # prognoses are drawn for the whole population, then sliced
                 age = age[lo:hi]
             self['age'] = age
         if sex is not None:
-            sex = np.asarray(sex)
+            if not isinstance(sex, torch.Tensor):
+                sex = np.asarray(sex)
             self['sex'] = sex[lo:hi] if (local_range is not None and len(sex) == self.n_global) else sex
         self.contacts = Contacts()
         if contacts is not None:
@@ -139,7 +141,10 @@ class People:
         rng.set_seed(pars['rand_seed'])
         progs = pars['prognoses']
         part = self._age_global is not None
-        age = np.asarray(self._age_global, dtype=np.float32) if part else self.to_numpy('age')      # the People array is float32
+        if part:                                           # the People array is float32
+            age = self._age_global.to(torch.float32).cpu().numpy() if isinstance(self._age_global, torch.Tensor) else np.asarray(self._age_global, dtype=np.float32)
+        else:
+            age = self.to_numpy('age')
         inds = np.digitize(age, progs['age_cutoffs']) - 1
         loc = slice(self.id0, self.id0 + self.n) if part else slice(None)
         self['symp_prob'] = progs['symp_probs'][inds][loc]

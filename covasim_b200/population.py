@@ -143,3 +143,174 @@ def make_randpop(pars, rng, exact=True, sex_ratio=0.5):
     for layer in layers.values():
         layer['beta'] = np.ones(len(layer['p1']), dtype=f32)
     return dict(uid=np.arange(n, dtype=i32), age=ages, sex=sexes, contacts=layers, layer_keys=list(pars['contacts'].keys()))
+
+
+# ===================================================================================================
+# Device-side generation: the same distributions, drawn from keyed Philox uniforms
+# ===================================================================================================
+#
+# The reference builds a population with Python loops over agents (population.py:143-364: 11.7 s at 1M agents, tens of GB
+# of Python lists at 100M).  Here every draw is a pure function of (seed, P_POP, sub, index, slot), so the population can
+# be generated ON THE DEVICE, in agent chunks, identically on every rank of an agent-partitioned run, and without ever
+# holding all edges at once.  Everything except the uniforms themselves is torch index arithmetic (init-time plumbing);
+# the uniforms come from the library's Philox kernel (cvb_keyed_uniform).  oracle/cvoracle.py:make_keyed_pop is the NumPy
+# restatement this is tested against, bit for bit (tests/test_gpu_popgen.py, tests/test_popgen_cpu.py).
+#
+#   agent i          : sex = u(sub 0, i, slot 0) < 0.5;  age bin from u(sub 0, i, slot 1) through the cumulative age
+#                      pyramid, age = lo + width * u(sub 0, i, slot 2)            (population.py:186-204)
+#   random layer L   : position i of the layer's eligible list gets round(Poisson(n) / 2) edges, Poisson by inverse CDF of
+#                      u(sub L, i, slot 0); edge e (running index within the layer) goes to eligible position
+#                      floor(u(sub L, e, slot 1) * m)                               (population.py:239-283)
+#   household layer  : cluster c has Poisson(n) members, inverse CDF of u(sub H, c, slot 0); consecutive agents; the last
+#                      cluster is truncated; all pairs a < b, ordered by (a, b)     (population.py:286-329)
+
+P_POP = 10
+SUB_AGENT = 0
+_LAYER_SUB = dict(h=1, s=2, w=3, c=4, a=5)
+
+
+def poisson_cdf(lam):
+    ''' Cumulative distribution of Poisson(lam) in float64, long enough that the tail is below 2^-60 '''
+    lam = float(lam)
+    kmax = int(lam + 12 * np.sqrt(lam + 1) + 40)
+    k = np.arange(1, kmax + 1, dtype=np.float64)
+    logp = np.concatenate([[-lam], -lam + np.cumsum(np.log(lam) - np.log(k))]) if lam > 0 else np.concatenate([[0.0], np.full(kmax, -np.inf)])
+    return np.cumsum(np.exp(logp))
+
+
+def device_uniforms(seed, device):
+    ''' uniforms(sub, index0, n, slot) -> float64[n] on ``device`` from the library's Philox kernel '''
+    import torch
+    from . import _capi
+
+    def fn(sub, index0, n, slot):
+        out = torch.empty(int(n), dtype=torch.float64, device=device)
+        if n:
+            with torch.cuda.device(device):
+                _capi.call('cvb_keyed_uniform', int(seed), P_POP, int(sub), 0, int(index0), int(n), int(slot), out.data_ptr(), None)
+        return out
+    return fn
+
+
+class KeyedPop:
+    '''
+    A population defined by keyed draws.  ``ages`` / ``sexes`` are whole-population device tensors; a layer's edges are
+    produced on demand for any range of its eligible positions (``layer_edges``), each with its running index inside the
+    layer -- which is also the index the transmission kernels key their per-edge draws on.
+    '''
+
+    def __init__(self, pars, seed, device, uniforms, school_ages=(6, 22), work_ages=(22, 65)):
+        import torch
+        self.torch = torch
+        self.device = torch.device(device)
+        self.seed = int(seed)
+        self.u = uniforms
+        n = self.n = int(pars['pop_size'])
+        dev = self.device
+        age_data = cvd.default_age_data
+        lo = torch.as_tensor(age_data[:, 0].astype(np.float64), device=dev)
+        width = torch.as_tensor((age_data[:, 1] + 1 - age_data[:, 0]).astype(np.float64), device=dev)
+        probs = age_data[:, 2] / age_data[:, 2].sum()
+        cum = torch.as_tensor(np.cumsum(probs), device=dev)
+        self.sexes = (self.u(SUB_AGENT, 0, n, 0) < 0.5).to(torch.int32)
+        bins = torch.searchsorted(cum, self.u(SUB_AGENT, 0, n, 1)).clamp_(max=len(probs) - 1)
+        self.ages = lo[bins] + width[bins] * self.u(SUB_AGENT, 0, n, 2)
+        self.plans = {}
+        contacts = pars['contacts']
+        if pars['pop_type'] == 'random':
+            for lk, nc in contacts.items():
+                self.plans[lk] = self._plan_random(lk, None, nc)
+        elif pars['pop_type'] == 'hybrid':
+            nc = dict(h=4, s=20, w=20, c=20)
+            nc.update(contacts)
+            ages32 = self.ages.to(torch.float32)              # the People array is float32; band membership uses what the sim sees
+            for lk in contacts.keys():                         # parameter order h, s, w, c = layer index order
+                if lk == 'h':
+                    self.plans[lk] = self._plan_households(nc['h'])
+                elif lk == 'c':
+                    self.plans[lk] = self._plan_random(lk, None, nc['c'])
+                elif lk in ('s', 'w'):
+                    a0, a1 = school_ages if lk == 's' else work_ages
+                    elig = torch.nonzero((ages32 >= a0) & (ages32 < a1)).flatten()
+                    self.plans[lk] = self._plan_random(lk, elig, nc[lk])
+                else:
+                    raise NotImplementedError(f'hybrid populations have layers h, s, w, c; got "{lk}"')
+        else:
+            raise NotImplementedError(f'Population type "{pars["pop_type"]}" is not built (choices: random, hybrid)')
+
+    # ---- plans: per eligible position, how many edges it starts and where they sit in the layer ----------------
+    def _poisson(self, lam, sub, index0, n):
+        torch = self.torch
+        cdf = torch.as_tensor(poisson_cdf(lam), device=self.device)
+        return torch.searchsorted(cdf, self.u(sub, index0, n, 0), right=True)
+
+    def _finish_plan(self, plan, counts):
+        torch = self.torch
+        offsets = torch.zeros(len(counts) + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(counts, 0, out=offsets[1:])
+        plan.update(counts=counts, offsets=offsets, n_edges=int(offsets[-1].item()))
+        if plan['n_edges'] >= 2 ** 31:
+            raise ValueError(f'layer with {plan["n_edges"]} edges: at most 2^31 - 1 edges per layer')
+        return plan
+
+    def _plan_random(self, lk, mapping, n_contacts):
+        torch = self.torch
+        m = self.n if mapping is None else int(mapping.numel())
+        sub = _LAYER_SUB.get(lk, 5)
+        counts = torch.round(self._poisson(n_contacts, sub, 0, m).to(torch.float64) / 2.0).to(torch.int64)      # half to even, like np.round
+        return self._finish_plan(dict(kind='random', sub=sub, mapping=mapping, m=m), counts)
+
+    def _plan_households(self, cluster_size):
+        torch = self.torch
+        n, sub = self.n, _LAYER_SUB['h']
+        sizes, covered, c0 = [], 0, 0
+        while covered < n:
+            block = max(1024, int((n - covered) / max(float(cluster_size), 0.5) * 1.2) + 16)
+            draw = self._poisson(cluster_size, sub, c0, block)
+            sizes.append(draw)
+            covered += int(draw.sum().item())
+            c0 += block
+        ends = torch.cumsum(torch.cat(sizes), 0)
+        k = int(torch.searchsorted(ends, torch.tensor([n], device=self.device, dtype=ends.dtype))[0].item()) + 1      # first end >= n
+        ends = ends[:k].clone()
+        ends[-1] = n                                            # the last cluster is truncated (population.py:309-310)
+        agents = torch.arange(n, dtype=torch.int64, device=self.device)
+        cluster_end = ends[torch.searchsorted(ends, agents, right=True)]
+        counts = cluster_end - agents - 1                       # agent a pairs with a+1 .. end-1
+        return self._finish_plan(dict(kind='households', sub=sub, mapping=None, m=n, ends=ends), counts)
+
+    # ---- edges -------------------------------------------------------------------------------------------
+    def layer_edges(self, lk, i0=0, i1=None):
+        '''
+        Edges started by eligible positions [i0, i1) of layer ``lk``: (p1:int32, p2:int32, e0) where e0 is the running
+        index of the first of them inside the layer (edges are ordered by position, then by draw).
+        '''
+        torch = self.torch
+        plan = self.plans[lk]
+        i1 = plan['m'] if i1 is None else min(int(i1), plan['m'])
+        counts = plan['counts'][i0:i1]
+        e0, e1 = int(plan['offsets'][i0].item()), int(plan['offsets'][i1].item())
+        pos = torch.repeat_interleave(torch.arange(i0, i1, dtype=torch.int64, device=self.device), counts, output_size=e1 - e0)
+        if plan['kind'] == 'households':
+            run = torch.arange(e0, e1, dtype=torch.int64, device=self.device) - plan['offsets'][pos]
+            p1, p2 = pos, pos + 1 + run
+        else:
+            m = plan['m']
+            tpos = torch.floor(self.u(plan['sub'], e0, e1 - e0, 1) * m).to(torch.int64).clamp_(max=m - 1)
+            if plan['mapping'] is None:
+                p1, p2 = pos, tpos
+            else:
+                p1, p2 = plan['mapping'][pos], plan['mapping'][tpos]
+        return p1.to(torch.int32), p2.to(torch.int32), e0
+
+    def layer_keys(self):
+        return list(self.plans.keys())
+
+    def materialize(self):
+        ''' The whole population in make_randpop's format (device tensors) '''
+        torch = self.torch
+        contacts = {}
+        for lk in self.plans:
+            p1, p2, _ = self.layer_edges(lk)
+            contacts[lk] = dict(p1=p1, p2=p2, beta=torch.ones(p1.numel(), dtype=torch.float32, device=self.device))
+        return dict(age=self.ages, sex=self.sexes, contacts=contacts, layer_keys=list(self.plans.keys()))

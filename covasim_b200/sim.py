@@ -34,7 +34,7 @@ f32 = np.float32
 class Sim:
 
     def __init__(self, pars=None, popdict=None, label=None, device=None, rng='philox', pop_exact=None, use_adjacency=True, partition=None,
-                 hit_capacity=0, **kwargs):
+                 hit_capacity=0, pop_gen='host', **kwargs):
         kw = dict(pars or {})
         kw.update(kwargs)
         for alias, key in (('n_agents', 'pop_size'), ('init_infected', 'pop_infected')):       # reference base.py:266-273
@@ -73,6 +73,12 @@ class Sim:
         self._adj_dirty = False
         # agent partition over several GPUs (partition.py): None = the whole population on this GPU; True = one rank of
         # the torch.distributed world; or a communicator object (partition.DistComm / partition.LocalComm)
+        # 'host': the reference's generators on the host (population.py; bit-exact with the reference when pop_exact);
+        # 'device': the same distributions from keyed Philox draws, generated on the GPU (population.KeyedPop)
+        if pop_gen not in ('host', 'device'):
+            raise ValueError(f'pop_gen must be "host" or "device", not "{pop_gen}"')
+        self.pop_gen = pop_gen
+        self._keyed_pop = None
         self._partition = partition
         self._comm = None
         self._hit_capacity = int(hit_capacity)
@@ -261,10 +267,21 @@ class Sim:
         if pars['prognoses'] is None:
             pars['prognoses'] = cvpar.get_prognoses(pars['prog_by_age'])
         pop = self.popdict
+        partitioned = self._partition is not None and self._partition is not False
+        if pop is None and self.pop_gen == 'device':
+            if self.rng_mode == 'mt':
+                raise NotImplementedError('pop_gen="device" draws the population from keyed Philox uniforms; replay mode needs the reference\'s generators (pop_gen="host")')
+            torch.cuda.set_device(self.device)
+            gen = cvpop.KeyedPop(pars, pars['rand_seed'], self.device, cvpop.device_uniforms(pars['rand_seed'], self.device))
+            if partitioned:                            # edges are streamed in chunks into the partitioned adjacency (_bind_partition)
+                self._keyed_pop = gen
+                pop = dict(age=gen.ages, sex=gen.sexes, contacts={lk: None for lk in gen.layer_keys()})
+            else:
+                pop = gen.materialize()
         if pop is None:
             exact = self.pop_exact if self.pop_exact is not None else (pars['pop_size'] <= 200_000)
             pop = cvpop.make_randpop(pars, self.rng, exact=exact)
-        if self._partition is not None and self._partition is not False:
+        if partitioned:
             from . import partition as cvpart
             self._comm = cvpart.DistComm() if self._partition is True else self._partition
             if any(pars['dynam_layer'].get(lk) for lk in pop['contacts'].keys()):
@@ -335,8 +352,19 @@ class Sim:
                    B['codes_local'].data_ptr(), B['codes_global'].data_ptr(), B['case_local'].data_ptr(), B['case_global'].data_ptr(),
                    self._hit_capacity)
         lkeys = self.people.layer_keys()
-        ids = [i for i, lk in enumerate(lkeys) if len(self._global_layers[lk]['p1']) > 0]
-        ptr, adj, M = cvpart.build_partition_adjacency([self._global_layers[lkeys[i]] for i in ids], ids, self.id0, self.id0 + self.n_local, n_slots, dev)
+        if self._keyed_pop is not None:
+            gen, step = self._keyed_pop, 4_000_000
+
+            def chunks():                              # agent chunks of every layer, never the whole edge list
+                for i, lk in enumerate(lkeys):
+                    for a in range(0, gen.plans[lk]['m'], step):
+                        p1, p2, e0 = gen.layer_edges(lk, a, a + step)
+                        yield i, p1, p2, None, e0
+            ptr, adj, M = cvpart.build_partition_adjacency_chunks(chunks(), self.id0, self.id0 + self.n_local, n_slots, dev)
+            self._keyed_pop = None
+        else:
+            ids = [i for i, lk in enumerate(lkeys) if len(self._global_layers[lk]['p1']) > 0]
+            ptr, adj, M = cvpart.build_partition_adjacency([self._global_layers[lkeys[i]] for i in ids], ids, self.id0, self.id0 + self.n_local, n_slots, dev)
         self._global_layers = None
         mask = 0
         for i in range(len(lkeys)):

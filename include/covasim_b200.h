@@ -133,6 +133,11 @@ int cvb_bind_log(cvb_sim* s, int32_t* source, int32_t* target, int32_t* date, in
 /* ------------------------------------------------------------------------------------------------
  * Stateless operators: 1:1 with the reference's Numba kernels (covasim/utils.py:39-147).
  * ---------------------------------------------------------------------------------------------- */
+/* Counter-based uniforms: out[k] = 53-bit uniform in [0,1) from Philox4x32-10 with key (seed, purpose, sub) and counter
+ * (index0 + k, day, slot) -- the keyed draw every native-RNG kernel uses (csrc/cvb_device.cuh:keyed_uniform).  The device-side
+ * population generator (reference population.py:143-364 make_randpop / make_*_contacts) is built from it. */
+int cvb_keyed_uniform(uint64_t seed, uint32_t purpose, uint32_t sub, int32_t day, int64_t index0, int64_t n, uint32_t slot,
+                      double* out, cvb_stream st);
 /* utils.py:39-79 compute_viral_load */
 int cvb_compute_viral_load(int32_t t, const float* date_inf, const float* date_rec, const float* date_dead,
                            float frac_time, float load_ratio, float high_cap, float* out, int64_t n, cvb_stream st);

@@ -122,6 +122,86 @@ def choose_distinct(stream, n, k):
     return out[:k]
 
 
+def poisson_cdf(lam):
+    ''' Cumulative distribution of Poisson(lam) in float64 (same table as covasim_b200/population.py:poisson_cdf) '''
+    lam = float(lam)
+    kmax = int(lam + 12 * np.sqrt(lam + 1) + 40)
+    k = np.arange(1, kmax + 1, dtype=np.float64)
+    logp = np.concatenate([[-lam], -lam + np.cumsum(np.log(lam) - np.log(k))]) if lam > 0 else np.concatenate([[0.0], np.full(kmax, -np.inf)])
+    return np.cumsum(np.exp(logp))
+
+
+def make_keyed_pop(pars, seed, school_ages=(6, 22), work_ages=(22, 65)):
+    '''
+    NumPy restatement of the keyed (device-side) population generator, covasim_b200/population.py:KeyedPop: the
+    distributions of the reference's make_randpop / make_random_contacts / make_microstructured_contacts /
+    make_hybrid_contacts (population.py:143-364), every draw a keyed Philox uniform (purpose 10).
+    '''
+    P_POP = 10
+    subs = dict(h=1, s=2, w=3, c=4, a=5)
+    n = int(pars['pop_size'])
+    u = lambda sub, index0, m, slot: ph.keyed_uniform(seed, P_POP, sub, 0, np.arange(index0, index0 + m, dtype=np.int64), slot)
+    age_data = cvd.default_age_data
+    lo, width = age_data[:, 0].astype(np.float64), (age_data[:, 1] + 1 - age_data[:, 0]).astype(np.float64)
+    probs = age_data[:, 2] / age_data[:, 2].sum()
+    sexes = (u(0, 0, n, 0) < 0.5).astype(np.int32)
+    bins = np.minimum(np.searchsorted(np.cumsum(probs), u(0, 0, n, 1)), len(probs) - 1)
+    ages = lo[bins] + width[bins] * u(0, 0, n, 2)
+
+    def poisson(lam, sub, index0, m):
+        return np.searchsorted(poisson_cdf(lam), u(sub, index0, m, 0), side='right')
+
+    def random_layer(lk, mapping, nc):
+        m = n if mapping is None else len(mapping)
+        counts = np.round(poisson(nc, subs.get(lk, 5), 0, m).astype(np.float64) / 2.0).astype(np.int64)
+        total = int(counts.sum())
+        pos = np.repeat(np.arange(m, dtype=np.int64), counts)
+        tpos = np.minimum(np.floor(u(subs.get(lk, 5), 0, total, 1) * m).astype(np.int64), m - 1)
+        if mapping is not None:
+            pos, tpos = mapping[pos], mapping[tpos]
+        return dict(p1=pos.astype(i32), p2=tpos.astype(i32), beta=np.ones(total, dtype=f32))
+
+    def households(cluster_size):
+        sizes, covered, c0 = [], 0, 0
+        while covered < n:
+            block = max(1024, int((n - covered) / max(float(cluster_size), 0.5) * 1.2) + 16)
+            draw = poisson(cluster_size, subs['h'], c0, block)
+            sizes.append(draw)
+            covered += int(draw.sum())
+            c0 += block
+        ends = np.cumsum(np.concatenate(sizes))
+        k = int(np.searchsorted(ends, n)) + 1
+        ends = ends[:k].copy()
+        ends[-1] = n
+        p1, p2 = [], []
+        start = 0
+        for end in ends.tolist():                      # plain loops: the restatement the vectorised device code is checked against
+            for a in range(start, end):
+                for b in range(a + 1, end):
+                    p1.append(a)
+                    p2.append(b)
+            start = end
+        return dict(p1=np.array(p1, dtype=i32), p2=np.array(p2, dtype=i32), beta=np.ones(len(p1), dtype=f32))
+
+    contacts = {}
+    if pars['pop_type'] == 'random':
+        for lk, nc in pars['contacts'].items():
+            contacts[lk] = random_layer(lk, None, nc)
+    else:
+        nc = dict(h=4, s=20, w=20, c=20)
+        nc.update(pars['contacts'])
+        ages32 = ages.astype(np.float32)
+        for lk in pars['contacts'].keys():
+            if lk == 'h':
+                contacts[lk] = households(nc['h'])
+            elif lk == 'c':
+                contacts[lk] = random_layer(lk, None, nc['c'])
+            else:
+                a0, a1 = school_ages if lk == 's' else work_ages
+                contacts[lk] = random_layer(lk, np.nonzero((ages32 >= a0) & (ages32 < a1))[0], nc[lk])
+    return dict(age=ages, sex=sexes, contacts=contacts, layer_keys=list(contacts.keys()))
+
+
 def lognormal_pars(par1, par2):
     ''' Mean/sigma of the underlying normal (reference utils.py:223-225) '''
     mean = np.log(par1 ** 2 / np.sqrt(par2 ** 2 + par1 ** 2))

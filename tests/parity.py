@@ -13,10 +13,10 @@ TOL_FIELDS = {'sus_imm': 1e-6, 'symp_imm': 1e-6, 'sev_imm': 1e-6, 'peak_nab': 1e
 LOOSE_RESULTS = {'pop_nabs': 1e-6, 'pop_protection': 1e-6, 'pop_symp_protection': 1e-6}
 
 
-def build_pair(cv, name=None, spec=None, **extra):
-    ''' (device sim, oracle sim), both initialised, sharing one population '''
+def build_pair(cv, name=None, spec=None, sim_kwargs=None, **extra):
+    ''' (device sim, oracle sim), both initialised, sharing one population; ``sim_kwargs`` go to the device sim only '''
     spec = spec or scenarios.SCENARIOS[name]
-    sim = cv.Sim(**scenarios.build(cv, spec, **extra))
+    sim = cv.Sim(**scenarios.build(cv, spec, **extra), **(sim_kwargs or {}))
     sim.initialize()
     pop = dict(age=sim.people.to_numpy('age').astype(np.float64), sex=sim.people.to_numpy('sex'),
                contacts={lk: l.to_numpy() for lk, l in sim.people.contacts.items()})

@@ -372,15 +372,10 @@ def run_reference(args):
     base.initialize()
     t_init = time.time() - t0
     P0 = {k: v.copy() for k, v in base.P.items()}
-    # calibrate the sample length on two days
-    t1 = time.perf_counter()
-    base.rng.set_seed(pars['rand_seed'])
-    base.step()
-    base.step()
-    per_day = (time.perf_counter() - t1) / 2
-    days = int(min(args.n_days + 1, max(4, budget / max(per_day, 1e-6))))
+    state = dict(days=0)
 
     def one_step():
+        ''' One bounded sample: the sim from day 0 for at most `budget` seconds (or to its end); returns (seconds, days done) '''
         for k, v in P0.items():
             base.P[k][...] = v
         base.t = 0
@@ -388,16 +383,21 @@ def run_reference(args):
         base.pars['n_days'] = args.n_days
         base.rng.set_seed(pars['rand_seed'])
         ts = time.perf_counter()
-        for _ in range(days):
+        days = 0
+        while days < args.n_days + 1 and (days < 4 or time.perf_counter() - ts < budget):
             base.step()
-        return time.perf_counter() - ts
+            days += 1
+        state['days'] = days
+        return time.perf_counter() - ts, days
 
     for _ in range(args.warmup):
         one_step()
-    times = [one_step() for _ in range(args.steps)]
-    el = float(np.mean(times))
+    runs = [one_step() for _ in range(args.steps)]
+    el = float(np.sum([r[0] for r in runs])) / args.steps
+    days = float(np.sum([r[1] for r in runs])) / args.steps
     value = args.pop_size * days / el
-    sample = f'first {days} of {args.n_days + 1} days of the same sim per step ({el / days:.3f} s/day), oracle port of the reference algorithm, MT19937 streams'
+    sample = (f'first {days:.0f} of {args.n_days + 1} days of the same sim per step (time-bounded at {budget:.0f} s per step; {el / days:.3f} s/day), '
+              'oracle port of the reference algorithm (NumPy, 1 host core), MT19937 streams')
     out = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el,
                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                config=config_block(args, dict(rng='mt19937 (reference streams)', init_s=t_init)),

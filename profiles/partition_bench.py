@@ -28,6 +28,7 @@ def main():
     ap.add_argument('--pop-size', type=int, default=4_000_000)
     ap.add_argument('--n-days', type=int, default=60)
     ap.add_argument('--reps', type=int, default=2)
+    ap.add_argument('--pop-gen', default='host', choices=['host', 'device'])
     ap.add_argument('--profile', action='store_true', help='CUDA-event time of every C-ABI call of one extra run')
     args = ap.parse_args()
     import torch.distributed as dist
@@ -44,7 +45,7 @@ def main():
     ivs = [cv.test_prob(symp_prob=0.1, asymp_prob=0.01, start_day=10), cv.contact_tracing(trace_probs=0.3, start_day=15),
            cv.vaccinate_prob('pfizer', days=list(range(10, 30)), prob=0.01), cv.vaccinate_prob('pfizer', days=[40], prob=0.05, booster=True, label='booster')]
     t0 = time.time()
-    sim = cv.Sim(pars, variants=variants, interventions=ivs, pop_exact=False, partition=True if world > 1 else None)
+    sim = cv.Sim(pars, variants=variants, interventions=ivs, pop_exact=False, partition=True if world > 1 else None, pop_gen=args.pop_gen)
     sim.initialize()
     torch.cuda.synchronize()
     t_init = time.time() - t0
@@ -84,7 +85,7 @@ def main():
     if rank == 0:
         out = dict(kernel_us_per_day=kernels, workload='C4 recipe (hybrid, alpha+delta, waning, test_prob+contact_tracing+vaccinate_prob+booster)', pop_size=n, n_days=args.n_days,
                    n_gpus=world, partitioned=world > 1, ms_per_run=best, us_per_day=1e3 * best / sim.npts, agent_days_per_s=n * sim.npts / (best / 1e3),
-                   init_s=t_init, exchange_bytes_per_day_per_rank=(sim._chunk * world + sim._chunk * world // 8) if world > 1 else 0,
+                   init_s=t_init, pop_gen=args.pop_gen, hbm_gb=torch.cuda.max_memory_allocated() / 1e9, exchange_bytes_per_day_per_rank=(sim._chunk * world + sim._chunk * world // 8) if world > 1 else 0,
                    cum_infections=sim.summary['cum_infections'], cum_deaths=sim.summary['cum_deaths'], cum_diagnoses=sim.summary['cum_diagnoses'],
                    cum_doses=sim.summary['cum_doses'], edges_local=None if sim._adj is None else int(sim._adj[1].shape[0]))
         print(json.dumps(out), flush=True)

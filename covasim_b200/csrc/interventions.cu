@@ -13,7 +13,7 @@ namespace cvb {
 // ================================================================================================
 // test_prob
 // ================================================================================================
-__global__ void __launch_bounds__(kThreads) test_prob_kernel(PeoplePtrs P, const __grid_constant__ cvb_test_prob_pars tp, uint64_t seed,
+__global__ void __launch_bounds__(kThreads, 3) test_prob_kernel(PeoplePtrs P, const __grid_constant__ cvb_test_prob_pars tp, uint64_t seed,
         int64_t n, int64_t id0, int32_t t, bool vec, unsigned long long* __restrict__ counters) {
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;

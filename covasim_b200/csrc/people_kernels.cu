@@ -393,7 +393,7 @@ __global__ void schedule_quar_kernel(const int32_t* __restrict__ inds, int64_t n
 // update_nab + stock counts + population means
 // ================================================================================================
 constexpr int kNStocks = 13;
-__global__ void __launch_bounds__(kThreads) nab_count_kernel(PeoplePtrs P, const __grid_constant__ cvb_pars pars, int64_t n, int32_t t, bool vec,
+__global__ void __launch_bounds__(kThreads, 3) nab_count_kernel(PeoplePtrs P, const __grid_constant__ cvb_pars pars, int64_t n, int32_t t, bool vec,
         const double* __restrict__ nab_kin, int64_t nab_kin_len, unsigned long long* __restrict__ counters,
         unsigned long long* __restrict__ vcounters, double* __restrict__ partial, unsigned int* __restrict__ ticket,
         double* __restrict__ sums_row) {

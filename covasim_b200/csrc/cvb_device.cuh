@@ -172,6 +172,27 @@ CVB_HD float rel_sus_layer(float rel_sus, bool sus, bool quar, float quar_factor
     return (float)dmul((double)r, 1.0 - (double)imm);      // float64 multiply, rounded once to float32
 }
 
+// ---- per-agent transmission record (16 bytes) and what the edge passes rebuild from it ---------------------------
+// prepare_transmission writes ONE record per agent instead of one {rel_trans, rel_sus} pair per layer; the per-layer factors
+// are applied by the edge pass for the edges it actually evaluates, with the same float32 chain (rel_trans_layer /
+// rel_sus_layer above), so probabilities are bit-identical to the per-layer tables of the reference (utils.py:82-90).
+//   t    : rel_trans if the agent can transmit today, else 0
+//   s    : rel_sus if the agent is susceptible, else 0
+//   imm0 : sus_imm against variant 0 (other variants are read from the People array)
+//   code : transmit_code bits; bits 0-2 = 0 for agents that cannot transmit, bit 5 (quarantined) is set for everyone
+struct AgentRecord { float t, s, imm0; uint32_t code; };
+
+CVB_HD float record_trans(float t, uint32_t code, float asymp_factor, float iso_factor, float quar_factor, float beta_layer,
+                          float vl_early, float vl_late) {
+    return rel_trans_layer(t, true, (code & 8u) != 0, (code & 16u) != 0, (code & 32u) != 0, asymp_factor, iso_factor, quar_factor,
+                           beta_layer, (code & 64u) ? vl_early : vl_late);
+}
+// rel_sus_layer(s, true, quar, quar_factor, imm) without the float64 round trip when imm == 0: r * (1 - 0) == r exactly
+CVB_HD float record_sus(float s, uint32_t code, float quar_factor, float imm) {
+    const float r = (code & 32u) ? fmul(s, quar_factor) : s;
+    return imm == 0.0f ? r : (float)dmul((double)r, 1.0 - (double)imm);
+}
+
 // ---- A4: per-edge transmission probability (reference utils.py:117) ---------------------------
 CVB_HD float edge_prob(float beta, float layer_beta, float trans_src, float sus_tgt) {
     return fmul(fmul(fmul(beta, layer_beta), trans_src), sus_tgt);

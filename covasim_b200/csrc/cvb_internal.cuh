@@ -48,11 +48,11 @@ struct LogPtrs {
     int64_t cap; unsigned long long* count;
 };
 
-// Transmission records written by prepare_transmission and gathered by the edge pass
+// Transmission records written by prepare_transmission and gathered by the edge pass: one 16-byte AgentRecord per agent
+// (cvb_device.cuh); susceptibility against variants > 0 comes straight from the People array sus_imm
 struct TransRecords {
-    float2* ts;          // [n_layers][N]  {rel_trans for the agent's own variant, rel_sus vs variant 0}
-    float* sus_extra;    // [n_layers][nv-1][N] rel_sus vs variants 1.. (nv > 1 only)
-    uint8_t* ivar;       // [N] variant carried by an infectious agent (nv > 1 only)
+    float4* rec;             // [N] AgentRecord {t, s, imm0, code}
+    const float* sus_imm;    // People.sus_imm [n_variants][N]
 };
 
 }  // namespace cvb

@@ -33,6 +33,8 @@ namespace cvb {
 
 struct EdgeParams {
     float beta[CVB_MAX_VARIANTS];
+    float beta_layer[CVB_MAX_LAYERS], iso_factor[CVB_MAX_LAYERS], quar_factor[CVB_MAX_LAYERS];   // sim.py:640-642
+    float asymp_factor, vl_early, vl_late, pad_;
     uint64_t seed;
     int64_t n;
     int64_t n_words;        // words of the transmit bitmap
@@ -52,34 +54,32 @@ __device__ __forceinline__ void record_hit(unsigned long long* __restrict__ infe
 
 // Evaluate one candidate edge in both directions (reference utils.py:113-123) and record transmissions.  Split in two so
 // that the dense pass can issue the two record gathers of a batch of candidates and consume them one batch later.
-__device__ __forceinline__ void gather_records(const TransRecords& rec, int64_t n, int a, int b, int l, float2& ra, float2& rb) {
-    const float2* __restrict__ ts = rec.ts + (int64_t)l * n;
-    ra = __ldg(ts + a);
-    rb = __ldg(ts + b);
+__device__ __forceinline__ void gather_records(const TransRecords& rec, int a, int b, float4& ra, float4& rb) {
+    ra = __ldg(rec.rec + a);
+    rb = __ldg(rec.rec + b);
+}
+
+// probability that `src` (record rs_) infects `tgt` (record rt_) over an edge of weight w on layer l; 0 if src cannot transmit
+template <bool MULTI>
+__device__ __forceinline__ float direction_prob(const TransRecords& rec, const EdgeParams& ep, const float4 rs_, const float4 rt_, int tgt,
+                                                float w, int l, int& variant) {
+    const uint32_t cs = __float_as_uint(rs_.w);
+    variant = 0;
+    if (!(cs & 7u) || rt_.y == 0.0f) return 0.0f;                  // source cannot transmit / target not susceptible
+    variant = (int)(cs & 7u) - 1;
+    const float t = record_trans(rs_.x, cs, ep.asymp_factor, ep.iso_factor[l], ep.quar_factor[l], ep.beta_layer[l], ep.vl_early, ep.vl_late);
+    float imm = rt_.z;
+    if (MULTI && variant > 0) imm = __ldg(rec.sus_imm + (int64_t)variant * ep.n + tgt);
+    const float sus = record_sus(rt_.y, __float_as_uint(rt_.w), ep.quar_factor[l], imm);
+    return edge_prob(ep.beta[variant], w, t, sus);
 }
 
 template <bool MULTI>
 __device__ __forceinline__ void finish_edge(const TransRecords& rec, const EdgeParams& ep, int a, int b, float w, int l, int64_t e,
-        const float2 ra, const float2 rb, unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand) {
-    const int64_t n = ep.n;
-    float p01 = 0.0f, p10 = 0.0f;
-    int va = 0, vb = 0;
-    if (ra.x != 0.0f) {                       // a can transmit on this layer
-        float sb = rb.y;
-        if (MULTI) {
-            va = rec.ivar[a];
-            if (va > 0) sb = __ldg(rec.sus_extra + ((int64_t)l * (ep.nv - 1) + (va - 1)) * n + b);
-        }
-        p01 = edge_prob(ep.beta[va], w, ra.x, sb);
-    }
-    if (rb.x != 0.0f) {                       // b can transmit on this layer
-        float sa = ra.y;
-        if (MULTI) {
-            vb = rec.ivar[b];
-            if (vb > 0) sa = __ldg(rec.sus_extra + ((int64_t)l * (ep.nv - 1) + (vb - 1)) * n + a);
-        }
-        p10 = edge_prob(ep.beta[vb], w, rb.x, sa);
-    }
+        const float4 ra, const float4 rb, unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand) {
+    int va, vb;
+    const float p01 = direction_prob<MULTI>(rec, ep, ra, rb, b, w, l, va);
+    const float p10 = direction_prob<MULTI>(rec, ep, rb, ra, a, w, l, vb);
     if (p01 != 0.0f || p10 != 0.0f) {
         const u32x4 r = keyed_words(ep.seed, P_EDGE, (uint32_t)l, ep.t, e, 0);
         const unsigned long long base = ((unsigned long long)l << 48) | (unsigned long long)e;
@@ -93,8 +93,8 @@ __device__ __forceinline__ void finish_edge(const TransRecords& rec, const EdgeP
 template <bool MULTI>
 __device__ __forceinline__ void process_edge(const TransRecords& rec, const EdgeParams& ep, int a, int b, float w, int l, int64_t e,
         unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand) {
-    float2 ra, rb;
-    gather_records(rec, ep.n, a, b, l, ra, rb);
+    float4 ra, rb;
+    gather_records(rec, a, b, ra, rb);
     finish_edge<MULTI>(rec, ep, a, b, w, l, e, ra, rb, infect_key, cand, n_cand);
 }
 
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(THREADS) edge_pass_kernel(const __grid_constan
         // when the NEXT batch is popped, so their L2 / HBM latency overlaps the filtering of the following quads
         bool pend = false;                                            // warp-uniform
         uint4 pc = make_uint4(0u, 0u, 0u, 0u);
-        float2 pra = make_float2(0.f, 0.f), prb = make_float2(0.f, 0.f);
+        float4 pra = make_float4(0.f, 0.f, 0.f, 0.f), prb = make_float4(0.f, 0.f, 0.f, 0.f);
 
         auto load_tile = [&](unsigned qq, EdgeQuad (&T)[QPT]) {
 #pragma unroll
@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(THREADS) edge_pass_kernel(const __grid_constan
                     qn -= 32;
                     const uint4 c = q_edge[qn + lane];
                     __syncwarp();
-                    float2 ra, rb;
-                    gather_records(rec, ep.n, (int)c.x, (int)c.y, l, ra, rb);
+                    float4 ra, rb;
+                    gather_records(rec, (int)c.x, (int)c.y, ra, rb);
                     if (pend) finish_edge<MULTI>(rec, ep, (int)pc.x, (int)pc.y, __uint_as_float(pc.z), l, (int64_t)pc.w, pra, prb, infect_key, cand, n_cand);
                     pc = c; pra = ra; prb = rb; pend = true;
                 }
@@ -268,18 +268,22 @@ __global__ void __launch_bounds__(kThreads) edge_pass_sparse_kernel(TransRecords
         const int i = trans_list[ti];
         const long long beg = adj_ptr[i], end = adj_ptr[i + 1];
         visited += (unsigned long long)(end - beg);
-        const int vi = MULTI ? (int)rec.ivar[i] : 0;
-        const float beta_v = ep.beta[vi];
+        const float4 ri = __ldg(rec.rec + i);                           // the transmitter's own record
+        const uint32_t ci = __float_as_uint(ri.w);
+        const int vi = (int)(ci & 7u) - 1;
+        const float beta_v = ep.beta[vi < 0 ? 0 : vi];
         for (long long off = beg + lane; off < end; off += 32) {
             const uint4 en = __ldg(adj + off);
             const int j = (int)en.x;
             const int l = (int)(en.z >> 1);
             const int dir = (int)(en.z & 1u);
-            const float t_i = __ldg(&rec.ts[(int64_t)l * n + i].x);
+            const float t_i = record_trans(ri.x, ci, ep.asymp_factor, ep.iso_factor[l], ep.quar_factor[l], ep.beta_layer[l], ep.vl_early, ep.vl_late);
             if (t_i == 0.0f) continue;                        // cannot transmit on this layer
-            float s_j;
-            if (MULTI && vi > 0) s_j = __ldg(rec.sus_extra + ((int64_t)l * (ep.nv - 1) + (vi - 1)) * n + j);
-            else s_j = __ldg(&rec.ts[(int64_t)l * n + j].y);
+            const float4 rj = __ldg(rec.rec + j);
+            if (rj.y == 0.0f) continue;                       // target not susceptible
+            float imm = rj.z;
+            if (MULTI && vi > 0) imm = __ldg(rec.sus_imm + (int64_t)vi * n + j);
+            const float s_j = record_sus(rj.y, __float_as_uint(rj.w), ep.quar_factor[l], imm);
             const float p = edge_prob(beta_v, __uint_as_float(en.w), t_i, s_j);
             if (p != 0.0f) {
                 const int64_t e = (int64_t)en.y;
@@ -394,9 +398,11 @@ __global__ void __launch_bounds__(kThreads) edge_pass_partition_kernel(TransReco
             const float t_i = rel_trans_layer(rt, true, symp, iso, quar, pars.asymp_factor, pars.iso_factor[l], pars.quar_factor[l],
                                               pars.beta_layer[l], vl);
             if (t_i == 0.0f) continue;
-            float s_j;
-            if (MULTI && vi > 0) s_j = __ldg(rec.sus_extra + ((int64_t)l * (ep.nv - 1) + (vi - 1)) * n + j);
-            else s_j = __ldg(&rec.ts[(int64_t)l * n + j].y);
+            const float4 rj = __ldg(rec.rec + j);
+            if (rj.y == 0.0f) continue;                                  // target not susceptible
+            float imm = rj.z;
+            if (MULTI && vi > 0) imm = __ldg(rec.sus_imm + (int64_t)vi * n + j);
+            const float s_j = record_sus(rj.y, __float_as_uint(rj.w), pars.quar_factor[l], imm);
             const float p = edge_prob(beta_v, __uint_as_float(en.w), t_i, s_j);
             if (p != 0.0f) {
                 const int64_t e = (int64_t)en.y;
@@ -476,10 +482,14 @@ extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
     cudaStream_t st = (cudaStream_t)st_;
     CVB_REQUIRE(s && s->pars_set, "cvb_edge_pass: handle not ready");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_edge_pass: day %d outside [0,%d)", t, s->npts);
-    CVB_REQUIRE(s->rec.ts && s->rec_layers >= s->pars.n_layers, "cvb_edge_pass: call cvb_prepare_transmission first");
+    CVB_REQUIRE(s->rec.rec && s->rec_layers >= s->pars.n_layers, "cvb_edge_pass: call cvb_prepare_transmission first");
     EdgeParams ep;
     for (int v = 0; v < CVB_MAX_VARIANTS; ++v) ep.beta[v] = s->pars.beta[v];
     ep.seed = s->seed; ep.n = s->n; ep.t = t; ep.nv = s->nv;
+    for (int l = 0; l < CVB_MAX_LAYERS; ++l) { ep.beta_layer[l] = s->pars.beta_layer[l]; ep.iso_factor[l] = s->pars.iso_factor[l]; ep.quar_factor[l] = s->pars.quar_factor[l]; }
+    ep.asymp_factor = s->pars.asymp_factor; ep.pad_ = 0.0f;
+    ep.vl_early = viral_load_value(true, s->pars.frac_time, s->pars.load_ratio);
+    ep.vl_late = viral_load_value(false, s->pars.frac_time, s->pars.load_ratio);
     ep.n_words = (s->n + 31) / 32;
     const bool multi = s->nv > 1;
     uint32_t skip_mask = 0;

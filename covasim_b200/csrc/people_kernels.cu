@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kThreads) post_prepare_kernel(PeoplePtrs P, co
     if (threadIdx.x < POST_NK) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     int c[POST_NK] = {0, 0, 0};
-    const int nv = pars.n_variants, nl = pars.n_layers;
+    const int nv = pars.n_variants;
     if (DO_PREP && blockIdx.x == 0 && threadIdx.x == 0) *n_cand = 0;      // today's candidate list starts empty
     uint8_t* diagnosed = PB(P, diagnosed); uint8_t* quarantined = PB(P, quarantined); uint8_t* isolated = PB(P, isolated);
     const uint8_t* dead = PB(P, dead); const uint8_t* recovered = PB(P, recovered);
@@ -275,6 +275,9 @@ __global__ void __launch_bounds__(kThreads) post_prepare_kernel(PeoplePtrs P, co
         }
         unsigned inf_nibble = 0;
         uint32_t code_word = 0;                                     // partitioned form: the four agents' transmit codes
+        float4 out4[4];
+#pragma unroll
+        for (int k = 0; k < kAPT; ++k) out4[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
         for (int k = 0; k < kAPT; ++k) {
             const int64_t i = i0 + k;
@@ -313,47 +316,41 @@ __global__ void __launch_bounds__(kThreads) post_prepare_kernel(PeoplePtrs P, co
                 }
             }
             if (DO_PREP) {
+                // prepare_transmission (sim.py:602-643): ONE 16-byte record per agent; the edge pass applies the per-layer
+                // factors to the edges it evaluates (cvb_device.cuh:AgentRecord)
                 bool inf = flag(w_inf, k);
                 const bool sus = flag(w_sus, k);
                 int var = 0;
-                float rt = 0.0f, vl = 0.0f;
                 if (inf) {
                     var = (int)iv4[k];
                     if (!(var >= 0 && var < nv)) { inf = false; var = 0; }      // infectious_variant == v is never true (sim.py:629)
                 }
-                bool early = false;
-                if (inf) {
-                    rt = rt4[k];
-                    early = viral_load_early(t, dinf[k], drec[k], ddead[k], pars.frac_time, pars.high_cap);
-                    vl = viral_load_value(early, pars.frac_time, pars.load_ratio);
-                }
                 const bool symp = flag(w_symp, k);
-                const float rs = sus ? rs4[k] : 0.0f;
-                if (nv > 1) rec.ivar[i] = (uint8_t)var;
-                bool any_trans = false;
-                for (int l = 0; l < nl; ++l) {
-                    float2 o;
-                    o.x = inf ? rel_trans_layer(rt, true, symp, iso, quar, pars.asymp_factor, pars.iso_factor[l], pars.quar_factor[l],
-                                                pars.beta_layer[l], vl) : 0.0f;
-                    o.y = sus ? rel_sus_layer(rs, true, quar, pars.quar_factor[l], imm0[k]) : 0.0f;
-                    any_trans |= (o.x != 0.0f);
-                    rec.ts[(int64_t)l * n + i] = o;
-                    for (int v = 1; v < nv; ++v)
-                        rec.sus_extra[((int64_t)l * (nv - 1) + (v - 1)) * n + i] =
-                            sus ? rel_sus_layer(rs, true, quar, pars.quar_factor[l], sus_imm[(int64_t)v * n + i]) : 0.0f;
-                }
-                if (any_trans) {
-                    inf_nibble |= 1u << k;
-                    if (codes) {
-                        // another GPU rebuilds this agent's transmissibility from its initial rel_trans and this byte
+                uint32_t code = quar ? 32u : 0u;                              // the quarantine bit matters for targets too
+                float rt = 0.0f;
+                if (inf && rt4[k] != 0.0f) {                                   // can transmit (a zero rel_trans never does)
+                    rt = rt4[k];
+                    const bool early = viral_load_early(t, dinf[k], drec[k], ddead[k], pars.frac_time, pars.high_cap);
+                    bool redux = false;
+                    if (codes) {                                               // partitioned: other GPUs rebuild rt from its initial value
                         const float base = base_trans[i];
-                        const bool redux = rt != base;
+                        redux = rt != base;
                         if (redux && rt != fmul(base, pars.trans_redux)) atomicAdd(part_flags + 1, 1u);
-                        code_word |= (uint32_t)transmit_code(var, symp, iso, quar, early, redux) << (8 * k);
-                    } else {
-                        trans_list[warp_append32(n_trans)] = (int32_t)i;   // compact (unordered) list of today's transmitters
                     }
+                    code = transmit_code(var, symp, iso, quar, early, redux);
+                    inf_nibble |= 1u << k;
+                    if (codes) code_word |= code << (8 * k);
+                    else trans_list[warp_append32(n_trans)] = (int32_t)i;    // compact (unordered) list of today's transmitters
                 }
+                out4[k] = make_float4(rt, sus ? rs4[k] : 0.0f, imm0[k], __uint_as_float(code));
+            }
+        }
+        if (DO_PREP) {
+            if (vec && i0 + 4 <= n) {
+#pragma unroll
+                for (int k = 0; k < kAPT; ++k) rec.rec[i0 + k] = out4[k];
+            } else {
+                for (int k = 0; k < kAPT && i0 + k < n; ++k) rec.rec[i0 + k] = out4[k];
             }
         }
         if (DO_PREP && codes) {
@@ -531,18 +528,10 @@ static bool vector_ok(const cvb_sim* s) {
 static int grid_agents(int64_t n) { return grid_for((n + kAPT - 1) / kAPT, kThreads, 148 * 8); }
 
 static int ensure_records(cvb_sim* s) {
-    const int nl = s->pars.n_layers;
-    CVB_REQUIRE(nl >= 1, "prepare_transmission: no contact layers");
-    if (s->rec_layers < nl) {
-        cudaFree(s->rec.ts); cudaFree(s->rec.sus_extra); cudaFree(s->rec.ivar);
-        s->rec.ts = nullptr; s->rec.sus_extra = nullptr; s->rec.ivar = nullptr; s->rec_layers = 0;
-        CVB_CHECK(cudaMalloc((void**)&s->rec.ts, (size_t)nl * s->n * sizeof(float2)));
-        if (s->nv > 1) {
-            CVB_CHECK(cudaMalloc((void**)&s->rec.sus_extra, (size_t)nl * (s->nv - 1) * s->n * sizeof(float)));
-            CVB_CHECK(cudaMalloc((void**)&s->rec.ivar, (size_t)s->n));
-        }
-        s->rec_layers = nl;
-    }
+    CVB_REQUIRE(s->pars.n_layers >= 1, "prepare_transmission: no contact layers");
+    if (!s->rec.rec) CVB_CHECK(cudaMalloc((void**)&s->rec.rec, (size_t)s->n * sizeof(float4)));
+    s->rec.sus_imm = (const float*)s->people.f[CVB_F_sus_imm];
+    s->rec_layers = s->pars.n_layers;
     return 0;
 }
 

@@ -19,6 +19,22 @@ void hc_trans_sus(const float* rt, const float* rs, const unsigned char* inf, co
     }
 }
 
+// the 16-byte agent record path (prepare_transmission writes one record per agent, the edge pass applies the layer factors):
+// must give exactly the per-layer tables of hc_trans_sus
+void hc_record_trans_sus(const float* rt, const float* rs, const unsigned char* inf, const unsigned char* sus, float beta_layer,
+                         const unsigned char* early, const unsigned char* symp, const unsigned char* iso, const unsigned char* quar,
+                         float af, float isf, float qf, const float* imm, float frac_time, float load_ratio, float* ot, float* os, long n) {
+    const float vl_early = cvb::viral_load_value(true, frac_time, load_ratio), vl_late = cvb::viral_load_value(false, frac_time, load_ratio);
+    for (long i = 0; i < n; ++i) {
+        unsigned code = quar[i] ? 32u : 0u;
+        float t = 0.0f;
+        if (inf[i] && rt[i] != 0.0f) { t = rt[i]; code = cvb::transmit_code(0, symp[i] != 0, iso[i] != 0, quar[i] != 0, early[i] != 0, false); }
+        const float s = sus[i] ? rs[i] : 0.0f;
+        ot[i] = (code & 7u) ? cvb::record_trans(t, code, af, isf, qf, beta_layer, vl_early, vl_late) : 0.0f;
+        os[i] = s != 0.0f ? cvb::record_sus(s, code, qf, imm[i]) : 0.0f;
+    }
+}
+
 void hc_edge_prob(float beta, const float* lb, const float* ts, const float* st, float* out, long n) {
     for (long i = 0; i < n; ++i) out[i] = cvb::edge_prob(beta, lb[i], ts[i], st[i]);
 }

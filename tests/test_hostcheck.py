@@ -114,3 +114,31 @@ def test_edge_probability_matches_oracle(hc):
     hc.hc_edge_prob(C.c_float(0.016), ptr(lb), ptr(ts), ptr(st), ptr(out), C.c_long(n))
     want = (((np.float32(0.016) * lb).astype(np.float32) * ts).astype(np.float32) * st).astype(np.float32)
     assert np.array_equal(out, want)
+
+
+def test_agent_record_path_equals_per_layer_tables(hc):
+    '''
+    prepare_transmission writes ONE 16-byte record per agent and the edge pass applies the per-layer factors to the edges it
+    evaluates; for every combination of flags this must give exactly the per-layer {rel_trans, rel_sus} tables of the
+    reference's compute_trans_sus (utils.py:82-90), which hc_trans_sus restates and the vectors test above pins.
+    '''
+    rng = np.random.RandomState(3)
+    n = 20000
+    f32 = np.float32
+    rt = (rng.gamma(0.45, 2.2, n) * (rng.random_sample(n) < 0.8)).astype(f32)
+    rs = rng.choice([0.34, 0.67, 1.0, 1.24, 1.47], n).astype(f32)
+    flags = {k: (rng.random_sample(n) < p).astype(np.uint8) for k, p in dict(inf=0.5, sus=0.6, symp=0.5, iso=0.3, quar=0.3, early=0.5).items()}
+    imm = (rng.random_sample(n) * (rng.random_sample(n) < 0.5)).astype(f32)
+    frac_time, load_ratio = f32(0.3), f32(2.0)
+    vl = np.where(flags['early'], f32(load_ratio) / (f32(1) + frac_time * (load_ratio - f32(1))), f32(1) / (f32(1) + frac_time * (load_ratio - f32(1)))).astype(f32)
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    for beta_layer, af, isf, qf in [(3.0, 1.0, 0.3, 0.6), (0.6, 0.5, 0.1, 0.2), (0.3, 1.0, 0.0, 1.0)]:
+        ot, os_ = np.zeros(n, f32), np.zeros(n, f32)
+        hc.hc_trans_sus(ptr(rt), ptr(rs), ptr(flags['inf']), ptr(flags['sus']), C.c_float(beta_layer), ptr(vl), ptr(flags['symp']), ptr(flags['iso']),
+                        ptr(flags['quar']), C.c_float(af), C.c_float(isf), C.c_float(qf), ptr(imm), ptr(ot), ptr(os_), C.c_long(n))
+        rt2, rs2 = np.zeros(n, f32), np.zeros(n, f32)
+        hc.hc_record_trans_sus(ptr(rt), ptr(rs), ptr(flags['inf']), ptr(flags['sus']), C.c_float(beta_layer), ptr(flags['early']), ptr(flags['symp']),
+                               ptr(flags['iso']), ptr(flags['quar']), C.c_float(af), C.c_float(isf), C.c_float(qf), ptr(imm), C.c_float(frac_time),
+                               C.c_float(load_ratio), ptr(rt2), ptr(rs2), C.c_long(n))
+        assert np.array_equal(ot, rt2) and np.array_equal(os_, rs2)
+        assert np.count_nonzero(ot) > 1000 and np.count_nonzero(os_) > 1000

@@ -216,7 +216,7 @@ def run_b200(args):
     # ALGORITHMIC bytes per launch: every array a kernel must read or write, once
     algo = {
         'cvb_update_states_pre': (9 + 16 + 12 * nv) * N,      # 9 flags + date_recovered, date_end_isolation, nab, recovered_variant; writes 3 x nv protections
-        'cvb_post_and_prepare': (8 + 28 + 8 * L) * N + N // 8,  # 8 flags + 7 float32 fields; writes L {trans, sus} records + transmit bitmap
+        'cvb_post_and_prepare': (8 + 28 + 16) * N + N // 8,     # 8 flags + 7 float32 fields; writes one 16-byte agent record + transmit bitmap
         'cvb_update_nab_count': (13 + 12 + 2 * nv + 8 * nv) * N,
         'cvb_infect_winners': None,
         'cvb_edge_pass': float(24 * work[:, 0].sum() + 28 * work[:, 1].sum()) / max(npts, 1) if sim._adj is not None else 12 * E + 8 * N,

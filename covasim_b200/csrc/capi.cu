@@ -140,7 +140,7 @@ int cvb_destroy(cvb_sim* s) {
     if (!s) return 0;
     cudaFree(s->cand); cudaFree(s->n_cand); cudaFree(s->infect_key); cudaFree(s->beds); cudaFree(s->edge_work); cudaFree(s->quar_ring); cudaFree(s->case_bits); cudaFree(s->inf_bits);
     cudaFree(s->trans_list); cudaFree(s->case_list); cudaFree(s->n_trans); cudaFree(s->n_case_list);
-    cudaFree(s->n_cases); cudaFree(s->dev_scalars); cudaFree(s->rec.rec);
+    cudaFree(s->n_cases); cudaFree(s->dev_scalars); cudaFree(s->rec_store); cudaFree(s->ts8_store);
     cudaFree(s->nab_kin); cudaFree(s->tile_cnt); cudaFree(s->hit_mask); cudaFree(s->flag_tmp); cudaFree(s->partial);
     cudaFree(s->glist); cudaFree(s->n_glist); cudaFree(s->hit_src); cudaFree(s->hit_key); cudaFree(s->part_flags);
     if (s->host_scalars) cudaFreeHost(s->host_scalars);

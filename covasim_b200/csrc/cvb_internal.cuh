@@ -53,6 +53,9 @@ struct LogPtrs {
 struct TransRecords {
     float4* rec;             // [N] AgentRecord {t, s, imm0, code}
     const float* sus_imm;    // People.sus_imm [n_variants][N]
+    float2* ts8;             // [n_layers][N] {rel_trans, rel_sus} per layer, written only for the layers the dense streaming
+                             // pass will read (dynamic layers / no adjacency) when n_variants == 1; NULL otherwise
+    uint32_t ts8_mask;       // the layers ts8 holds today
 };
 
 }  // namespace cvb
@@ -69,6 +72,8 @@ struct cvb_sim {
     cvb::LogPtrs log;
     // scratch owned by the library
     cvb::TransRecords rec; int32_t rec_layers;
+    float2* ts8_store; int32_t ts8_layers;          // backing store of rec.ts8
+    float4* rec_store;                              // backing store of rec.rec
     int32_t* cand; unsigned int* n_cand;            // today's newly infected candidates
     unsigned long long* infect_key;                 // [N] winning transmission key per target (kEmptyKey = none)
     unsigned long long* beds;                       // [npts][2] severe / critical after update_states_pre

@@ -90,11 +90,38 @@ __device__ __forceinline__ void finish_edge(const TransRecords& rec, const EdgeP
     }
 }
 
+// the dense pass gathers 8-byte per-layer pairs with one variant (MULTI = false) and 16-byte agent records otherwise
+template <bool MULTI> struct RecType { typedef float4 type; };
+template <> struct RecType<false> { typedef float2 type; };
+
+// ---- the same for the per-layer {rel_trans, rel_sus} pairs (one variant; what the dense streaming pass gathers) ----
+__device__ __forceinline__ void gather_records(const TransRecords& rec, int64_t n, int l, int a, int b, float2& ra, float2& rb) {
+    const float2* __restrict__ ts = rec.ts8 + (int64_t)l * n;
+    ra = __ldg(ts + a);
+    rb = __ldg(ts + b);
+}
+__device__ __forceinline__ void gather_records(const TransRecords& rec, int64_t, int, int a, int b, float4& ra, float4& rb) {
+    gather_records(rec, a, b, ra, rb);
+}
+
+template <bool MULTI>
+__device__ __forceinline__ void finish_edge(const TransRecords& rec, const EdgeParams& ep, int a, int b, float w, int l, int64_t e,
+        const float2 ra, const float2 rb, unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand) {
+    const float p01 = ra.x != 0.0f ? edge_prob(ep.beta[0], w, ra.x, rb.y) : 0.0f;
+    const float p10 = rb.x != 0.0f ? edge_prob(ep.beta[0], w, rb.x, ra.y) : 0.0f;
+    if (p01 != 0.0f || p10 != 0.0f) {
+        const u32x4 r = keyed_words(ep.seed, P_EDGE, (uint32_t)l, ep.t, e, 0);
+        const unsigned long long base = ((unsigned long long)l << 48) | (unsigned long long)e;
+        if (p01 != 0.0f && u53(r.x, r.y) < (double)p01) record_hit(infect_key, cand, n_cand, b, base);
+        if (p10 != 0.0f && u53(r.z, r.w) < (double)p10) record_hit(infect_key, cand, n_cand, a, (1ull << 40) | base);
+    }
+}
+
 template <bool MULTI>
 __device__ __forceinline__ void process_edge(const TransRecords& rec, const EdgeParams& ep, int a, int b, float w, int l, int64_t e,
         unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand) {
-    float4 ra, rb;
-    gather_records(rec, a, b, ra, rb);
+    typename RecType<MULTI>::type ra, rb;
+    gather_records(rec, ep.n, l, a, b, ra, rb);
     finish_edge<MULTI>(rec, ep, a, b, w, l, e, ra, rb, infect_key, cand, n_cand);
 }
 
@@ -173,7 +200,7 @@ __global__ void __launch_bounds__(THREADS) edge_pass_kernel(const __grid_constan
         // when the NEXT batch is popped, so their L2 / HBM latency overlaps the filtering of the following quads
         bool pend = false;                                            // warp-uniform
         uint4 pc = make_uint4(0u, 0u, 0u, 0u);
-        float4 pra = make_float4(0.f, 0.f, 0.f, 0.f), prb = make_float4(0.f, 0.f, 0.f, 0.f);
+        typename RecType<MULTI>::type pra = {}, prb = {};
 
         auto load_tile = [&](unsigned qq, EdgeQuad (&T)[QPT]) {
 #pragma unroll
@@ -218,8 +245,8 @@ __global__ void __launch_bounds__(THREADS) edge_pass_kernel(const __grid_constan
                     qn -= 32;
                     const uint4 c = q_edge[qn + lane];
                     __syncwarp();
-                    float4 ra, rb;
-                    gather_records(rec, (int)c.x, (int)c.y, ra, rb);
+                    typename RecType<MULTI>::type ra, rb;
+                    gather_records(rec, ep.n, l, (int)c.x, (int)c.y, ra, rb);
                     if (pend) finish_edge<MULTI>(rec, ep, (int)pc.x, (int)pc.y, __uint_as_float(pc.z), l, (int64_t)pc.w, pra, prb, infect_key, cand, n_cand);
                     pc = c; pra = ra; prb = rb; pend = true;
                 }
@@ -482,7 +509,7 @@ extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
     cudaStream_t st = (cudaStream_t)st_;
     CVB_REQUIRE(s && s->pars_set, "cvb_edge_pass: handle not ready");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_edge_pass: day %d outside [0,%d)", t, s->npts);
-    CVB_REQUIRE(s->rec.rec && s->rec_layers >= s->pars.n_layers, "cvb_edge_pass: call cvb_prepare_transmission first");
+    CVB_REQUIRE((s->rec.rec || s->rec.ts8) && s->rec_layers >= s->pars.n_layers, "cvb_edge_pass: call cvb_prepare_transmission first");
     EdgeParams ep;
     for (int v = 0; v < CVB_MAX_VARIANTS; ++v) ep.beta[v] = s->pars.beta[v];
     ep.seed = s->seed; ep.n = s->n; ep.t = t; ep.nv = s->nv;
@@ -493,6 +520,7 @@ extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
     ep.n_words = (s->n + 31) / 32;
     const bool multi = s->nv > 1;
     uint32_t skip_mask = 0;
+    CVB_REQUIRE(s->rec.rec || !(s->partitioned || (s->adj && s->adj_layer_mask) || multi), "cvb_edge_pass: agent records missing (layers changed since cvb_prepare_transmission)");
     if (s->partitioned) {
         // agent-partitioned form: global transmitter list from the all-gathered codes, then the local adjacency rows
         CVB_REQUIRE(s->padj_ptr && s->padj && s->codes_global, "cvb_edge_pass: partitioned handle without adjacency / codes (cvb_bind_partition_adjacency, cvb_set_partition)");
@@ -535,6 +563,11 @@ extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
     bool rest = false;
     for (int l = 0; l < s->pars.n_layers; ++l) rest |= !(skip_mask & (1u << l)) && s->layers[l].n_edges > 0;
     if (!rest) return 0;
+    if (!multi) {
+        for (int l = 0; l < s->pars.n_layers; ++l)
+            CVB_REQUIRE((skip_mask >> l) & 1u || s->layers[l].n_edges == 0 || (s->rec.ts8 && ((s->rec.ts8_mask >> l) & 1u)),
+                        "cvb_edge_pass: layer %d changed between cvb_prepare_transmission and cvb_edge_pass (its per-layer records are missing)", l);
+    }
     const size_t bitmap_bytes = (size_t)ep.n_words * sizeof(unsigned int);
     const size_t limit = 227 * 1024;
     auto queue_bytes = [](int threads) { return (size_t)(threads / 32) * kQueueCap * sizeof(uint4); };

@@ -342,10 +342,27 @@ __global__ void __launch_bounds__(kThreads) post_prepare_kernel(PeoplePtrs P, co
                     if (codes) code_word |= code << (8 * k);
                     else trans_list[warp_append32(n_trans)] = (int32_t)i;    // compact (unordered) list of today's transmitters
                 }
-                out4[k] = make_float4(rt, sus ? rs4[k] : 0.0f, imm0[k], __uint_as_float(code));
+                // With one variant, immunity is applied here for agents who are not quarantined (their susceptibility is the
+                // same on every layer), so the edge pass does the float64 product only for quarantined targets.
+                float s_rec = sus ? rs4[k] : 0.0f, imm_rec = imm0[k];
+                if (nv == 1 && !quar) { s_rec = record_sus(s_rec, 0u, 1.0f, imm_rec); imm_rec = 0.0f; }
+                out4[k] = make_float4(rt, s_rec, imm_rec, __uint_as_float(code));
+                if (rec.ts8) {
+                    // the layers the dense streaming pass reads get the reference's per-layer pair as well: that pass
+                    // evaluates ~20 % of ALL edges, so the layer factors are cheaper applied once per agent here
+                    const float vl = rt != 0.0f ? viral_load_value((code & 64u) != 0, pars.frac_time, pars.load_ratio) : 0.0f;
+                    for (int l = 0; l < pars.n_layers; ++l) {
+                        if (!((rec.ts8_mask >> l) & 1u)) continue;
+                        float2 o;
+                        o.x = rt != 0.0f ? rel_trans_layer(rt, true, symp, iso, quar, pars.asymp_factor, pars.iso_factor[l], pars.quar_factor[l],
+                                                           pars.beta_layer[l], vl) : 0.0f;
+                        o.y = sus ? rel_sus_layer(rs4[k], true, quar, pars.quar_factor[l], imm0[k]) : 0.0f;
+                        rec.ts8[(int64_t)l * n + i] = o;
+                    }
+                }
             }
         }
-        if (DO_PREP) {
+        if (DO_PREP && rec.rec) {                                  // (not needed when every layer goes through the dense pass)
             if (vec && i0 + 4 <= n) {
 #pragma unroll
                 for (int k = 0; k < kAPT; ++k) rec.rec[i0 + k] = out4[k];
@@ -529,8 +546,26 @@ static int grid_agents(int64_t n) { return grid_for((n + kAPT - 1) / kAPT, kThre
 
 static int ensure_records(cvb_sim* s) {
     CVB_REQUIRE(s->pars.n_layers >= 1, "prepare_transmission: no contact layers");
-    if (!s->rec.rec) CVB_CHECK(cudaMalloc((void**)&s->rec.rec, (size_t)s->n * sizeof(float4)));
+    if (!s->rec_store) CVB_CHECK(cudaMalloc((void**)&s->rec_store, (size_t)s->n * sizeof(float4)));
     s->rec.sus_imm = (const float*)s->people.f[CVB_F_sus_imm];
+    // layers the dense streaming pass will read today: not covered by an adjacency, not partitioned, non-empty
+    uint32_t dense = 0;
+    if (!s->partitioned && s->nv == 1)
+        for (int l = 0; l < s->pars.n_layers; ++l)
+            if (s->layers[l].n_edges > 0 && !((s->adj && ((s->adj_layer_mask >> l) & 1u)))) dense |= 1u << l;
+    if (dense && (!s->ts8_store || s->ts8_layers < s->pars.n_layers)) {
+        cudaFree(s->ts8_store);
+        s->ts8_store = nullptr;
+        CVB_CHECK(cudaMalloc((void**)&s->ts8_store, (size_t)s->pars.n_layers * s->n * sizeof(float2)));
+        s->ts8_layers = s->pars.n_layers;
+    }
+    s->rec.ts8 = dense ? s->ts8_store : nullptr;
+    s->rec.ts8_mask = dense;
+    // the 16-byte agent records feed the adjacency / partitioned passes and the multi-variant dense pass; when every non-empty
+    // layer is read through ts8 nobody needs them
+    uint32_t nonempty = 0;
+    for (int l = 0; l < s->pars.n_layers; ++l) if (s->layers[l].n_edges > 0) nonempty |= 1u << l;
+    s->rec.rec = (dense && dense == nonempty) ? nullptr : s->rec_store;
     s->rec_layers = s->pars.n_layers;
     return 0;
 }

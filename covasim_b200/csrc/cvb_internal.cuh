@@ -222,12 +222,15 @@ __device__ __forceinline__ uint32_t load4b(const uint8_t* __restrict__ p, int64_
 __device__ __forceinline__ bool flag(uint32_t w, int k) { return ((w >> (8 * k)) & 0xFFu) != 0; }
 __device__ __forceinline__ int count4(uint32_t w) { return __popc(__vcmpne4(w, 0u) & 0x01010101u); }
 
+// Per-thread event counters -> CTA totals in shared memory.  Most counters are flows of rare events (a death, a new
+// diagnosis): a warp whose 32 lanes all hold 0 skips the reduction after one vote.
 template <int NK>
 __device__ __forceinline__ void reduce_counters(const int (&c)[NK], int* s_cnt) {
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
+        if (!__any_sync(0xFFFFFFFFu, c[k] != 0)) continue;
         int w = __reduce_add_sync(0xFFFFFFFFu, c[k]);
-        if (lane_id() == 0 && w) atomicAdd(&s_cnt[k], w);
+        if (lane_id() == 0) atomicAdd(&s_cnt[k], w);
     }
 }
 

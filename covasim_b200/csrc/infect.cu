@@ -223,16 +223,8 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
         }
     }
 
-#pragma unroll
-    for (int k = 0; k < INF_NK; ++k) {
-        int w = __reduce_add_sync(0xFFFFFFFFu, c[k]);
-        if (lane_id() == 0 && w) atomicAdd(&s_cnt[k], w);
-    }
-#pragma unroll
-    for (int k = 0; k < 3 * CVB_MAX_VARIANTS; ++k) {
-        int w = __reduce_add_sync(0xFFFFFFFFu, cv[k]);
-        if (lane_id() == 0 && w) atomicAdd(&s_cnt[INF_NK + k], w);
-    }
+    reduce_counters(c, s_cnt);
+    reduce_counters(cv, s_cnt + INF_NK);
     __syncthreads();
     if (ia.count_flows && threadIdx.x < NK && s_cnt[threadIdx.x]) {
         const int k = threadIdx.x;

@@ -248,7 +248,8 @@ int cvb_set_partition(cvb_sim* s, int64_t id0, int64_t n_global, int64_t chunk, 
     if (hit_capacity < 1024) hit_capacity = 1024;
     cudaFree(s->cand); cudaFree(s->hit_src); cudaFree(s->hit_key); cudaFree(s->glist); cudaFree(s->n_glist); cudaFree(s->part_flags);
     s->cand = nullptr; s->hit_src = nullptr; s->hit_key = nullptr; s->glist = nullptr; s->n_glist = nullptr; s->part_flags = nullptr;
-    CVB_CHECK(cudaMalloc((void**)&s->cand, (size_t)hit_capacity * sizeof(int32_t)));
+    // cand doubles as the unique-target list of cvb_infect_list (up to n_agents entries), so it never shrinks below n_agents
+    CVB_CHECK(cudaMalloc((void**)&s->cand, (size_t)(hit_capacity > s->n ? hit_capacity : s->n) * sizeof(int32_t)));
     CVB_CHECK(cudaMalloc((void**)&s->hit_src, (size_t)hit_capacity * sizeof(int32_t)));
     CVB_CHECK(cudaMalloc((void**)&s->hit_key, (size_t)hit_capacity * sizeof(unsigned long long)));
     s->hit_cap = hit_capacity;

@@ -17,7 +17,7 @@ import torch
 from . import parameters as cvpar
 from . import _capi
 
-__all__ = ['Intervention', 'change_beta', 'test_prob', 'contact_tracing', 'vaccinate_prob', 'find_day', 'process_days']
+__all__ = ['Intervention', 'dynamic_pars', 'change_beta', 'test_prob', 'contact_tracing', 'vaccinate_prob', 'find_day', 'process_days']
 
 
 def find_day(arr, t=None, interv=None, sim=None, which='first'):
@@ -71,6 +71,42 @@ class Intervention:
 
     def shrink(self, in_place=False):
         return self
+
+
+class dynamic_pars(Intervention):
+    '''
+    Change simulation parameters on given days (reference interventions.py:411-479): ``pars`` maps a parameter name to
+    ``dict(days=..., vals=...)``; dict values update a nested parameter (e.g. ``beta_layer``).  Parameters may also be given as
+    keyword arguments.  The device copy of the scalar block is refreshed the same day (Sim.step re-sends it when it changed).
+    '''
+
+    def __init__(self, pars=None, **kwargs):
+        pars = dict(pars or {})
+        sim_par_keys = list(cvpar.make_pars().keys())
+        for k in [k for k in kwargs if k in sim_par_keys]:
+            pars[k] = kwargs.pop(k)
+        super().__init__(**kwargs)
+        for parkey, spec in pars.items():
+            for subkey in ('days', 'vals'):
+                if subkey not in spec:
+                    raise KeyError(f'Parameter {parkey} is missing subkey {subkey}')
+                if isinstance(spec[subkey], (int, float, np.integer, np.floating)):
+                    spec[subkey] = np.atleast_1d(spec[subkey])
+            if len(spec['days']) != len(spec['vals']):
+                raise ValueError(f'Length of days ({len(spec["days"])}) does not match length of values ({len(spec["vals"])}) for parameter {parkey}')
+        self.pars = pars
+
+    def apply(self, sim):
+        t = sim.t
+        for parkey, spec in self.pars.items():
+            for ind in find_day(spec['days'], t, interv=self, sim=sim):
+                self.days.append(t)
+                val = spec['vals'][ind]
+                if isinstance(val, dict):
+                    sim[parkey].update(val)
+                else:
+                    sim[parkey] = val
+                sim._pars_dirty = True
 
 
 class change_beta(Intervention):

@@ -797,6 +797,30 @@ class Intervention:
         return self.apply(sim)
 
 
+class dynamic_pars(Intervention):
+    ''' Set parameters on given days (reference interventions.py:411-479) '''
+    def __init__(self, pars=None, **kwargs):
+        self.pars = dict(pars or {})
+        self.pars.update(kwargs)
+        for spec in self.pars.values():
+            for sub in ('days', 'vals'):
+                if np.isscalar(spec[sub]):
+                    spec[sub] = np.atleast_1d(spec[sub])
+
+    def initialize(self, sim):
+        pass
+
+    def apply(self, sim):
+        for parkey, spec in self.pars.items():
+            hit = np.nonzero(np.asarray(spec['days']) == sim.t)[0]
+            for ind in hit[:1]:
+                val = spec['vals'][ind]
+                if isinstance(val, dict):
+                    sim.pars[parkey].update(val)
+                else:
+                    sim.pars[parkey] = val
+
+
 class change_beta(Intervention):
     ''' Scale beta (overall or per layer) on given days (reference interventions.py:533-586) '''
     def __init__(self, days, changes, layers=None):

@@ -33,7 +33,7 @@ from oracle import cvoracle as cvo  # noqa: E402
 import scenarios  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
-FULL_PEOPLE = {'hybrid3k', 'random2k_nowaning', 'variants4k', 'dynamic2k'}
+FULL_PEOPLE = {'hybrid3k', 'random2k_nowaning', 'variants4k', 'dynamic2k', 'dynpars3k'}
 KERNEL_DAYS = {'hybrid3k': [12, 25], 'variants4k': [20], 'baseline20k': []}
 
 
@@ -191,7 +191,10 @@ def run_scenario(name, spec):
 
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
+    only = set(sys.argv[1:])                          # python -m oracle.gen_golden [scenario ...]: regenerate a subset
     for name, spec in scenarios.SCENARIOS.items():
+        if only and name not in only:
+            continue
         sim, out = run_scenario(name, spec)
         if name == 'baseline20k':
             with open(os.path.join(refenv.REFERENCE, 'tests', 'baseline.json')) as f:

@@ -38,6 +38,13 @@ SCENARIOS = {
                        ('vaccinate_prob', dict(vaccine='pfizer', days=5, prob=0.3)),
                        ('vaccinate_prob', dict(vaccine='jj', days=32, prob=0.2, booster=True, label='jj_boost'))],
     ),
+    # parameters edited during the run (dynamic_pars): transmissibility down and up again, deadlier disease, daily importations on and off
+    'dynpars3k': dict(
+        pars=dict(pop_size=3000, pop_infected=40, pop_type='hybrid', n_days=40, verbose=0, rand_seed=21, beta=0.02),
+        interventions=[('dynamic_pars', dict(pars={'beta': dict(days=[10, 25], vals=[0.008, 0.025]), 'rel_death_prob': dict(days=15, vals=3.0),
+                                                   'n_imports': dict(days=[5, 30], vals=[3, 0])})),
+                       ('test_prob', dict(start_day=5, symp_prob=0.2, asymp_prob=0.01))],
+    ),
     # dynamic layer (BASELINE.json config 5 member shape, scaled down)
     'dynamic2k': dict(pars=dict(pop_size=2000, pop_infected=40, n_days=30, verbose=0, rand_seed=8, beta=0.02,
                                 dynam_layer=dict(a=1)), interventions=[]),

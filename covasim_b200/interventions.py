@@ -17,7 +17,7 @@ import torch
 from . import parameters as cvpar
 from . import _capi
 
-__all__ = ['Intervention', 'dynamic_pars', 'change_beta', 'test_prob', 'contact_tracing', 'vaccinate_prob', 'find_day', 'process_days']
+__all__ = ['Intervention', 'dynamic_pars', 'change_beta', 'clip_edges', 'test_prob', 'contact_tracing', 'vaccinate_prob', 'find_day', 'process_days']
 
 
 def find_day(arr, t=None, interv=None, sim=None, which='first'):
@@ -135,6 +135,56 @@ class change_beta(Intervention):
                     sim['beta'] = b * self.changes[ind]
                 else:
                     sim['beta_layer'][lk] = b * self.changes[ind]
+
+
+class clip_edges(Intervention):
+    '''
+    Remove a fraction of a layer's contacts on given days and put them back later (reference interventions.py:589-667).
+    The edges move between the simulation's device-resident layer and a layer owned by the intervention
+    (``Layer.pop_inds`` / ``Layer.append``); the adjacency is rebuilt before the next transmission pass.  Which edges move is a
+    host-side set choice from the Numba stream (the reference's cvu.choose; the O(k) sampler in native-RNG mode).
+    '''
+
+    def __init__(self, days, changes, layers=None, **kwargs):
+        super().__init__(**kwargs)
+        self.days, self.changes, self.layers = days, changes, layers
+        self.contacts = None
+
+    def initialize(self, sim):
+        super().initialize()
+        if sim._comm is not None:
+            raise NotImplementedError('clip_edges edits contact layers during the run, which agent-partitioned simulations do not support')
+        self.days = process_days(sim, self.days)
+        self.changes = np.atleast_1d(np.array(self.changes, dtype=float))
+        if len(self.days) != len(self.changes):
+            raise ValueError(f'Number of days supplied ({len(self.days)}) does not match number of changes ({len(self.changes)})')
+        lkeys = sim.people.layer_keys()
+        self.layers = lkeys if self.layers is None else ([self.layers] if isinstance(self.layers, str) else list(self.layers))
+        from .base import Layer
+        self.contacts = {lk: Layer(label=lk, device=sim.people.device) for lk in self.layers}
+
+    def apply(self, sim):
+        for ind in find_day(self.days, sim.t, interv=self, sim=sim):
+            for lkey in self.layers:
+                s_layer, i_layer = sim.people.contacts[lkey], self.contacts[lkey]
+                n_sim, n_int = len(s_layer), len(i_layer)
+                n_contacts = n_sim + n_int
+                if not n_contacts:
+                    continue
+                prop_to_move = n_sim / n_contacts - self.changes[ind]
+                n_to_move = int(prop_to_move * n_contacts)
+                src, dst, n_src = (s_layer, i_layer, n_sim) if n_to_move > 0 else (i_layer, s_layer, n_int)
+                k = abs(n_to_move)
+                if sim.rng_mode == 'mt':
+                    inds = sim.rng.nb.choice(n_src, k, replace=False)                  # cvu.choose: Numba stream
+                else:
+                    from . import utils as cvu
+                    inds = cvu.choose_distinct(sim.rng.nb, n_src, k)
+                dst.append(src.pop_inds(inds))
+
+    def finalize(self, sim=None):
+        super().finalize()
+        self.contacts = None
 
 
 _QUAR_POLICY = dict(start=0, end=1, both=2, daily=3)

@@ -844,6 +844,39 @@ class change_beta(Intervention):
                     sim.pars['beta_layer'][lk] = b * self.changes[ind]
 
 
+class clip_edges(Intervention):
+    ''' Move a fraction of a layer's edges out of the simulation and back (reference interventions.py:589-667) '''
+    def __init__(self, days, changes, layers=None):
+        self.days, self.changes, self.layers = days, changes, layers
+
+    def initialize(self, sim):
+        self.days = np.sort(np.atleast_1d(np.array([sim.day(d) for d in np.atleast_1d(self.days)])))
+        self.changes = np.atleast_1d(np.array(self.changes, dtype=float))
+        self.layers = list(sim.contacts.keys()) if self.layers is None else ([self.layers] if isinstance(self.layers, str) else list(self.layers))
+        self.contacts = {lk: dict(p1=np.zeros(0, dtype=i32), p2=np.zeros(0, dtype=i32), beta=np.zeros(0, dtype=f32)) for lk in self.layers}
+
+    @staticmethod
+    def _move(src, dst, inds):                      # base.py:1742-1771 pop_inds + append
+        for k in ('p1', 'p2', 'beta'):
+            dst[k] = np.concatenate([dst[k], src[k][inds]])
+            src[k] = np.delete(src[k], inds)
+
+    def apply(self, sim):
+        hit = np.nonzero(self.days == sim.t)[0]
+        for ind in hit[:1]:
+            for lkey in self.layers:
+                s_layer, i_layer = sim.contacts[lkey], self.contacts[lkey]
+                n_sim, n_int = len(s_layer['p1']), len(i_layer['p1'])
+                n_contacts = n_sim + n_int
+                if not n_contacts:
+                    continue
+                n_to_move = int((n_sim / n_contacts - self.changes[ind]) * n_contacts)
+                if n_to_move > 0:
+                    self._move(s_layer, i_layer, sim.rng.choose('nb', n_sim, n_to_move))
+                else:
+                    self._move(i_layer, s_layer, sim.rng.choose('nb', n_int, abs(n_to_move)))
+
+
 class test_prob(Intervention):
     ''' Probability-based testing (reference interventions.py:857-981); swab_delay / ili_prev / subtarget not built '''
     def __init__(self, symp_prob, asymp_prob=0.0, symp_quar_prob=None, asymp_quar_prob=None, quar_policy=None,

@@ -33,7 +33,7 @@ from oracle import cvoracle as cvo  # noqa: E402
 import scenarios  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
-FULL_PEOPLE = {'hybrid3k', 'random2k_nowaning', 'variants4k', 'dynamic2k', 'dynpars3k'}
+FULL_PEOPLE = {'hybrid3k', 'random2k_nowaning', 'variants4k', 'dynamic2k', 'dynpars3k', 'clip3k'}
 KERNEL_DAYS = {'hybrid3k': [12, 25], 'variants4k': [20], 'baseline20k': []}
 
 
@@ -160,6 +160,9 @@ def run_scenario(name, spec):
                             continue        # the layer arrays are regenerated from the seed by the tests
                         out[f'k{t}/ci{j}/{k}'] = np.asarray(v)
                 out[f'k{t}/n_calls'] = np.int64(len(cap.get('ci', [])))
+        for lk, layer in sim.people.contacts.items():          # layers as the run left them (clip_edges moves edges)
+            out[f'final_contacts_digest/{lk}'] = np.array(digest(layer['p1']) + digest(layer['p2']))
+            out[f'final_contacts_len/{lk}'] = np.int64(len(layer))
         sim.finalize()
     finally:
         mirror.restore()

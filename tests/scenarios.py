@@ -45,6 +45,14 @@ SCENARIOS = {
                                                    'n_imports': dict(days=[5, 30], vals=[3, 0])})),
                        ('test_prob', dict(start_day=5, symp_prob=0.2, asymp_prob=0.01))],
     ),
+    # contacts removed and restored during the run (clip_edges), with tracing over the clipped network
+    'clip3k': dict(
+        pars=dict(pop_size=3000, pop_infected=50, pop_type='hybrid', n_days=40, verbose=0, rand_seed=31, beta=0.022),
+        interventions=[('clip_edges', dict(days=[8, 25], changes=[0.3, 1.0], layers=['s', 'w'])),
+                       ('clip_edges', dict(days=12, changes=0.5)),
+                       ('test_prob', dict(start_day=4, symp_prob=0.3, asymp_prob=0.02)),
+                       ('contact_tracing', dict(trace_probs=0.5, start_day=6))],
+    ),
     # dynamic layer (BASELINE.json config 5 member shape, scaled down)
     'dynamic2k': dict(pars=dict(pop_size=2000, pop_infected=40, n_days=30, verbose=0, rand_seed=8, beta=0.02,
                                 dynam_layer=dict(a=1)), interventions=[]),

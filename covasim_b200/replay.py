@@ -326,6 +326,7 @@ def step(sim):
     t, pars, P, h, st = sim.t, sim.pars, sim.people, sim._handle, sim._stream_ptr
     call = _capi.call
     P.t = t
+    sim.rescale()
     sim._push_pars()
     call('cvb_update_states_pre', h, t, st)
     for lkey, dyn in pars['dynam_layer'].items():

@@ -235,8 +235,8 @@ class Sim:
         if pars['end_day'] is not None:
             pars['n_days'] = self.day(pars['end_day'])
         pars['n_days'] = int(pars['n_days'])
-        if pars['pop_scale'] != 1 and pars['rescale']:
-            raise NotImplementedError('dynamic rescaling (pop_scale > 1 with rescale=True; reference sim.py:535-555) is not built; use rescale=False')
+        if pars['pop_scale'] != 1 and pars['rescale'] and self._partition not in (None, False):
+            raise NotImplementedError('dynamic rescaling needs a global count of non-naive agents every day and is not built for agent-partitioned runs; use rescale=False')
         if pars['frac_susceptible'] < 1:
             raise NotImplementedError('frac_susceptible < 1 is not built')
 
@@ -654,6 +654,7 @@ class Sim:
             torch.cuda.set_device(self.device)
         people.t = t
         call = _capi.call if self.kernel_timers is None else self._timed_call
+        self.rescale()
         self._push_pars()
         if self._adj_dirty:
             self._build_adjacency()
@@ -691,6 +692,30 @@ class Sim:
         if self.kernel_timers is None:
             return _capi.call(name, *args)
         return self._timed_call(name, *args)
+
+    def rescale(self):
+        '''
+        Dynamic rescaling (reference sim.py:535-555): once more than rescale_threshold of the agents are no longer naive, a
+        random share of them is made naive again and every agent stands for more people from today on.  Needs one count per
+        day (a device synchronisation) while there is still room to rescale; the chosen agents are reset on the device.
+        '''
+        pars = self.pars
+        if not pars['rescale']:
+            return
+        pop_scale, current = pars['pop_scale'], self.rescale_vec[self.t]
+        if current < pop_scale:
+            not_naive = torch.nonzero(~self.people.naive).flatten()
+            n_not_naive, n_people = int(not_naive.numel()), pars['pop_size']
+            ratio, threshold = n_not_naive / n_people, pars['rescale_threshold']
+            if ratio > threshold:
+                scaling = min(max(ratio / threshold, pars['rescale_factor']), pop_scale / current)
+                self.rescale_vec[self.t:] *= scaling
+                n = int(round(n_not_naive * (1.0 - 1.0 / scaling)))
+                if self.rng_mode == 'mt':
+                    choices = self.rng.nb.choice(n_not_naive, n, replace=False)                # cvu.choose: Numba stream
+                else:
+                    choices = cvu.choose_distinct(self.rng.nb, n_not_naive, n)
+                self.people.make_naive(not_naive[torch.as_tensor(choices, dtype=torch.int64, device=self.device)])
 
     def _timed_call(self, name, *args):
         ''' _capi.call bracketed by CUDA events on the launching stream (bench.py's per-kernel timing) '''

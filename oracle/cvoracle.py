@@ -1173,11 +1173,47 @@ class OracleSim:
             inds = self.rng.choose('nb', pars['pop_size'], int(pars['pop_infected']))
             self.infect(inds, layer='seed_infection')
 
+    def make_naive(self, inds, reset_vx=False):
+        ''' Back to the never-infected state (reference people.py:378-409); used by dynamic rescaling '''
+        P = self.P
+        for key in cvd.states:
+            if key in ('susceptible', 'naive'):
+                P[key][inds] = True
+            elif key != 'vaccinated' or reset_vx:
+                P[key][inds] = False
+        for key in cvd.variant_states:
+            P[key][inds] = np.nan
+        for key in cvd.by_variant_states:
+            P[key][:, inds] = False
+        non_vx = inds if reset_vx else inds[~P['vaccinated'][inds]]
+        for key in cvd.imm_states:
+            P[key][:, non_vx] = 0
+        for key in cvd.nab_states + cvd.vacc_states:
+            P[key][non_vx] = 0
+        for key in cvd.dates + cvd.durs:
+            if key != 'date_vaccinated' or reset_vx:
+                P[key][inds] = np.nan
+
+    def rescale(self):
+        ''' Dynamic rescaling (reference sim.py:535-555): when too many agents are no longer naive, each agent starts to stand for more people '''
+        pars = self.pars
+        if not pars['rescale']:
+            return
+        pop_scale, current = pars['pop_scale'], self.rescale_vec[self.t]
+        if current < pop_scale:
+            not_naive = np.nonzero(~self.P['naive'])[0]
+            n_not_naive, n_people = len(not_naive), pars['pop_size']
+            ratio, threshold = n_not_naive / n_people, pars['rescale_threshold']
+            if ratio > threshold:
+                scaling = min(max(ratio / threshold, pars['rescale_factor']), pop_scale / current)
+                self.rescale_vec[self.t:] *= scaling
+                n = int(round(n_not_naive * (1.0 - 1.0 / scaling)))
+                self.make_naive(not_naive[self.rng.choose('nb', n_not_naive, n)])
+
     def step(self):
         ''' One simulated day (reference sim.py:558-685) '''
         t, P, pars = self.t, self.P, self.pars
-        if pars['rescale'] and pars['pop_scale'] > 1:
-            raise NotImplementedError('dynamic rescaling is outside the built path')
+        self.rescale()
         self.flows = {k: 0 for k in cvd.new_result_flows}
         self.vflows = {k: np.zeros(pars['n_variants']) for k in cvd.new_result_flows_by_variant}
         update_states_pre(P, pars, t, self.flows, self.vflows)

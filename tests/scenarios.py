@@ -53,6 +53,12 @@ SCENARIOS = {
                        ('test_prob', dict(start_day=4, symp_prob=0.3, asymp_prob=0.02)),
                        ('contact_tracing', dict(trace_probs=0.5, start_day=6))],
     ),
+    # dynamic rescaling: 3000 agents standing for up to 24000 people (reference sim.py:535-555)
+    'rescale3k': dict(
+        pars=dict(pop_size=3000, pop_scale=8, rescale=True, pop_infected=60, pop_type='hybrid', n_days=40, verbose=0, rand_seed=41, beta=0.025),
+        interventions=[('test_prob', dict(start_day=5, symp_prob=0.2, asymp_prob=0.01)),
+                       ('vaccinate_prob', dict(vaccine='pfizer', days=12, prob=0.2))],
+    ),
     # dynamic layer (BASELINE.json config 5 member shape, scaled down)
     'dynamic2k': dict(pars=dict(pop_size=2000, pop_infected=40, n_days=30, verbose=0, rand_seed=8, beta=0.02,
                                 dynam_layer=dict(a=1)), interventions=[]),

@@ -17,14 +17,14 @@ import torch
 from . import parameters as cvpar
 from . import _capi
 
-__all__ = ['Intervention', 'dynamic_pars', 'change_beta', 'clip_edges', 'test_prob', 'contact_tracing', 'vaccinate_prob', 'find_day', 'process_days']
+__all__ = ['Intervention', 'dynamic_pars', 'sequence', 'change_beta', 'clip_edges', 'test_prob', 'contact_tracing', 'vaccinate_prob', 'find_day', 'process_days']
 
 
 def find_day(arr, t=None, interv=None, sim=None, which='first'):
     ''' Indices of ``arr`` equal to day t (reference interventions.py:22-53) '''
     if callable(arr):
         arr = np.atleast_1d(arr(interv, sim))
-    all_inds = np.nonzero(np.asarray(arr) == t)[0]
+    all_inds = np.nonzero(np.asarray(arr))[0] if t is None else np.nonzero(np.asarray(arr) == t)[0]     # t None: indices of True entries
     if len(all_inds) == 0 or which == 'all':
         return all_inds
     return [all_inds[0]] if which == 'first' else [all_inds[-1]]
@@ -107,6 +107,44 @@ class dynamic_pars(Intervention):
                 else:
                     sim[parkey] = val
                 sim._pars_dirty = True
+
+
+class sequence(Intervention):
+    '''
+    Switch between interventions: ``interventions[i]`` is applied from ``days[i]`` until ``days[i+1]`` (reference
+    interventions.py:482-523).  The nested interventions are initialised with the sequence and get their own index (after the
+    top-level ones, see Sim.intervention_index), which keys their random draws.
+    '''
+
+    def __init__(self, days, interventions, **kwargs):
+        super().__init__(**kwargs)
+        if len(np.atleast_1d(days)) != len(interventions):
+            raise ValueError('sequence: one start day per intervention')
+        self.days = list(np.atleast_1d(days))
+        self.interventions = list(interventions)
+
+    def initialize(self, sim):
+        super().initialize()
+        self.days = [sim.day(d) for d in self.days]
+        self.days_arr = np.array(self.days + [sim.npts])
+        for iv in self.interventions:
+            iv.initialize(sim)
+
+    def active(self, sim):
+        ''' The intervention in force today, or None '''
+        inds = find_day(self.days_arr <= sim.t, which='last')
+        return self.interventions[inds[0]] if len(inds) else None
+
+    def apply(self, sim):
+        iv = self.active(sim)
+        if iv is not None:
+            return iv.apply(sim)
+
+    def finalize(self, sim=None):
+        super().finalize()
+        for iv in self.interventions:
+            if hasattr(iv, 'finalize'):
+                iv.finalize(sim)
 
 
 class change_beta(Intervention):

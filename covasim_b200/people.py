@@ -203,8 +203,17 @@ class People:
         if len(inds):
             _capi.call('cvb_schedule_quarantine', sim._handle, inds.data_ptr(), len(inds), start_date, float(start_date + period), sim._stream_ptr)
 
+    def make_nonnaive(self, inds):
+        ''' Reset agents and mark them neither susceptible nor naive (reference people.py:412-431); ``inds`` are global ids '''
+        inds = torch.as_tensor(inds, dtype=torch.int64, device=self.device)
+        if self._sim is not None and self._sim._comm is not None:      # partitioned: this rank resets the agents it owns
+            inds = inds[(inds >= self.id0) & (inds < self.id0 + self.n)] - self.id0
+        self.make_naive(inds)
+        self._arrays['susceptible'][inds] = False
+        self._arrays['naive'][inds] = False
+
     def make_naive(self, inds, reset_vx=False):
-        ''' Reset agents to the never-infected state (reference people.py:378-409) '''
+        ''' Reset agents to the never-infected state (reference people.py:378-409); ``inds`` index this object's arrays '''
         inds = torch.as_tensor(inds, dtype=torch.int64, device=self.device)
         A = self._arrays
         for key in cvd.states:

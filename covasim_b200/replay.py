@@ -342,8 +342,14 @@ def step(sim):
             sim._host_add('n_imports', t, n_imports)
     for v in pars['variants']:
         v.apply(sim)
-    for iv in pars['interventions']:
-        if isinstance(iv, test_prob):
+    from .interventions import sequence
+
+    def apply_intervention(iv):
+        if isinstance(iv, sequence):                      # the intervention in force today, through the same dispatch
+            inner = iv.active(sim)
+            if inner is not None:
+                apply_intervention(inner)
+        elif isinstance(iv, test_prob):
             if not (t < iv.start_day or (iv.end_day is not None and t > iv.end_day)):
                 test_prob_apply(iv, sim)
         elif isinstance(iv, contact_tracing):
@@ -353,6 +359,8 @@ def step(sim):
             vaccinate_apply(iv, sim)
         else:
             iv(sim)
+    for iv in pars['interventions']:
+        apply_intervention(iv)
     sim._push_pars()
     call('cvb_update_states_post', h, t, st)
 

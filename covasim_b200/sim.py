@@ -172,7 +172,15 @@ class Sim:
         return [k for k in self.results.keys() if isinstance(self.results[k], Result)]
 
     def intervention_index(self, obj):
-        return [id(i) for i in self.pars['interventions']].index(id(obj))
+        ''' Position in the intervention list; interventions nested in others (cv.sequence) are numbered after the top-level ones '''
+        flat = []
+
+        def walk(ivs):
+            flat.extend(ivs)
+            for iv in ivs:
+                walk(list(getattr(iv, 'interventions', None) or []))
+        walk(list(self.pars['interventions']))
+        return [id(i) for i in flat].index(id(obj))
 
     def get_interventions(self, which=None):
         ivs = self.pars['interventions']
@@ -237,8 +245,6 @@ class Sim:
         pars['n_days'] = int(pars['n_days'])
         if pars['pop_scale'] != 1 and pars['rescale'] and self._partition not in (None, False):
             raise NotImplementedError('dynamic rescaling needs a global count of non-naive agents every day and is not built for agent-partitioned runs; use rescale=False')
-        if pars['frac_susceptible'] < 1:
-            raise NotImplementedError('frac_susceptible < 1 is not built')
 
     def _init_results(self):
         ''' Result containers (reference sim.py:284-351) '''
@@ -610,6 +616,13 @@ class Sim:
     # ---- seeding (reference sim.py:505-532) ----------------------------------------------------------
     def init_infections(self, force=False):
         pars = self.pars
+        if pars['frac_susceptible'] < 1:                       # reference sim.py:519-521: a random share is not susceptible
+            n = int(np.round((1 - pars['frac_susceptible']) * pars['pop_size']))
+            if self.rng_mode == 'mt':
+                inds = self.rng.nb.choice(pars['pop_size'], n, replace=False)                           # cvu.choose: Numba stream
+            else:
+                inds = cvu.choose_distinct(self.rng.nb, pars['pop_size'], n)
+            self.people.make_nonnaive(inds)
         if pars['pop_infected']:
             if self.rng_mode == 'mt':
                 inds = self.rng.nb.choice(pars['pop_size'], int(pars['pop_infected']), replace=False)   # cvu.choose: Numba stream

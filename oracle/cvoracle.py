@@ -821,6 +821,23 @@ class dynamic_pars(Intervention):
                     sim.pars[parkey] = val
 
 
+class sequence(Intervention):
+    ''' interventions[i] is in force from days[i] until days[i+1] (reference interventions.py:482-523) '''
+    def __init__(self, days, interventions):
+        self.days, self.interventions = list(np.atleast_1d(days)), list(interventions)
+
+    def initialize(self, sim):
+        self.days = [sim.day(d) for d in self.days]
+        self.days_arr = np.array(self.days + [sim.npts])
+        for iv in self.interventions:
+            iv.initialize(sim)
+
+    def apply(self, sim):
+        hit = np.nonzero(self.days_arr <= sim.t)[0]
+        if len(hit):
+            self.interventions[hit[-1]].apply(sim)
+
+
 class change_beta(Intervention):
     ''' Scale beta (overall or per layer) on given days (reference interventions.py:533-586) '''
     def __init__(self, days, changes, layers=None):
@@ -1112,7 +1129,14 @@ class OracleSim:
         return (d - start).days
 
     def intervention_index(self, obj):
-        return [id(i) for i in self.interventions].index(id(obj))
+        flat = []                                      # top-level interventions first, then the ones nested in a sequence
+
+        def walk(ivs):
+            flat.extend(ivs)
+            for iv in ivs:
+                walk(list(getattr(iv, 'interventions', None) or []))
+        walk(list(self.interventions))
+        return [id(i) for i in flat].index(id(obj))
 
     def layer_index(self, lkey):
         return list(self.contacts.keys()).index(lkey)
@@ -1167,8 +1191,12 @@ class OracleSim:
     def init_infections(self):
         ''' Seed infections (reference sim.py:505-532); draws from the Numba stream '''
         pars = self.pars
-        if pars['frac_susceptible'] < 1:
-            raise NotImplementedError('frac_susceptible < 1 is outside the built path')
+        if pars['frac_susceptible'] < 1:                       # sim.py:519-521: a random share of the population is not susceptible
+            n = int(np.round((1 - pars['frac_susceptible']) * pars['pop_size']))
+            inds = self.rng.choose('nb', pars['pop_size'], n)
+            self.make_naive(inds)                              # people.py:412-431 make_nonnaive
+            self.P['susceptible'][inds] = False
+            self.P['naive'][inds] = False
         if pars['pop_infected']:
             inds = self.rng.choose('nb', pars['pop_size'], int(pars['pop_infected']))
             self.infect(inds, layer='seed_infection')

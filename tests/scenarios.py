@@ -59,6 +59,15 @@ SCENARIOS = {
         interventions=[('test_prob', dict(start_day=5, symp_prob=0.2, asymp_prob=0.01)),
                        ('vaccinate_prob', dict(vaccine='pfizer', days=12, prob=0.2))],
     ),
+    # a third of the population immune from the start (frac_susceptible, reference sim.py:519-521)
+    'fracsus2k': dict(pars=dict(pop_size=2000, pop_infected=40, n_days=30, verbose=0, rand_seed=51, beta=0.03, frac_susceptible=0.67), interventions=[]),
+    # a sequence of two testing regimes (nested interventions), traced
+    'sequence3k': dict(
+        pars=dict(pop_size=3000, pop_infected=50, pop_type='hybrid', n_days=35, verbose=0, rand_seed=61, beta=0.022),
+        interventions=[('sequence', dict(days=[5, 20], interventions=[('test_prob', dict(symp_prob=0.4, asymp_prob=0.0)),
+                                                                      ('test_prob', dict(symp_prob=0.1, asymp_prob=0.02, test_delay=1))])),
+                       ('contact_tracing', dict(trace_probs=0.4, start_day=8))],
+    ),
     # dynamic layer (BASELINE.json config 5 member shape, scaled down)
     'dynamic2k': dict(pars=dict(pop_size=2000, pop_infected=40, n_days=30, verbose=0, rand_seed=8, beta=0.02,
                                 dynam_layer=dict(a=1)), interventions=[]),
@@ -69,7 +78,11 @@ def build(mod, spec, **extra):
     ''' Instantiate a scenario against module ``mod`` (reference covasim, oracle.cvoracle or covasim_b200) '''
     spec = copy.deepcopy(spec)
     pars = spec['pars']
-    ivs = [getattr(mod, name)(**kw) for name, kw in spec.get('interventions', [])]
+    def make(name, kw):
+        if name == 'sequence':                         # nested interventions are given as (name, kwargs) pairs too
+            kw = dict(kw, interventions=[make(n, k) for n, k in kw['interventions']])
+        return getattr(mod, name)(**kw)
+    ivs = [make(name, kw) for name, kw in spec.get('interventions', [])]
     vs = [mod.variant(**kw) for kw in spec.get('variants', [])]
     kwargs = dict(pars)
     kwargs['interventions'] = ivs

@@ -56,6 +56,10 @@ class cvb_test_prob_pars(C.Structure):
                 ('index', C.c_int32), ('pad_', C.c_int32)]
 
 
+class cvb_test_num_pars(C.Structure):
+    _fields_ = [('symp_test', C.c_double), ('quar_test', C.c_double), ('quar_policy', C.c_int32), ('index', C.c_int32)]
+
+
 class cvb_trace_pars(C.Structure):
     _fields_ = [('trace_prob', C.c_double * MAX_LAYERS), ('trace_time', C.c_int32 * MAX_LAYERS), ('presumptive', C.c_int32),
                 ('quar_period', C.c_int32), ('index', C.c_int32), ('pad_', C.c_int32)]
@@ -107,6 +111,8 @@ PROTOTYPES = dict(
     cvb_update_nab_count=[_P, _i32, _P],
     cvb_step_day=[_P, _i32, _P],
     cvb_test_prob=[_P, _i32, C.POINTER(cvb_test_prob_pars), _P],
+    cvb_test_num_keys=[_P, _i32, C.POINTER(cvb_test_num_pars), _P, _P, _P],
+    cvb_test_list=[_P, _i32, _P, _i64, C.c_double, C.c_double, _i32, _i32, _P],
     cvb_contact_tracing=[_P, _i32, C.POINTER(cvb_trace_pars), _P],
     cvb_trace_select_cases=[_P, _i32, C.POINTER(cvb_trace_pars), _P],
     cvb_trace_notify_contacts=[_P, _i32, C.POINTER(cvb_trace_pars), _P],

@@ -71,6 +71,53 @@ __global__ void __launch_bounds__(kThreads, 3) test_prob_kernel(PeoplePtrs P, co
 }
 
 // ================================================================================================
+// test_num (reference interventions.py:718-854): a fixed number of tests per day, handed out by weight
+// ================================================================================================
+// Weighted sampling without replacement of n_tests agents is the n_tests smallest of the keys  -log(1 - u_i) / w_i  (exponential
+// clocks; Efraimidis & Spirakis 2006) with u_i the agent's keyed uniform: this kernel writes the weights (the reference's
+// test_probs) and the keys, the host picks the n smallest (torch.topk) and cvb_test_list administers the tests.
+__global__ void __launch_bounds__(kThreads) test_num_keys_kernel(PeoplePtrs P, const __grid_constant__ cvb_test_num_pars tp, uint64_t seed, int64_t n,
+        int64_t id0, int32_t t, double* __restrict__ weight, double* __restrict__ key) {
+    const float tf = (float)t;
+    const uint8_t* symptomatic = PB(P, symptomatic); const uint8_t* diagnosed = PB(P, diagnosed); const uint8_t* quarantined = PB(P, quarantined);
+    const float* d_quar = PF(P, date_quarantined); const float* d_end_quar = PF(P, date_end_quarantine);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double w = 1.0;
+        if (symptomatic[i]) w = dmul(w, tp.symp_test);
+        bool qt;                                                       // interventions.py:691-715 get_quar_inds
+        switch (tp.quar_policy) {
+            case 0:  qt = d_quar[i] == tf - 1.0f; break;
+            case 1:  qt = d_end_quar[i] == tf + 1.0f; break;
+            case 2:  qt = (d_quar[i] == tf - 1.0f) || (d_end_quar[i] == tf + 1.0f); break;
+            default: qt = quarantined[i] != 0; break;
+        }
+        if (qt) w = dmul(w, tp.quar_test);
+        if (diagnosed[i]) w = 0.0;                                     // diagnosed people do not test
+        weight[i] = w;
+        const double u = keyed_uniform(seed, P_TEST, (uint32_t)tp.index, t, i + id0, 0);
+        key[i] = w > 0.0 ? -log(1.0 - u) / w : __longlong_as_double(0x7ff0000000000000ll);
+    }
+}
+
+// People.test (people.py:589-617) for an explicit list of distinct agents
+__global__ void __launch_bounds__(kThreads) test_list_kernel(PeoplePtrs P, const int32_t* __restrict__ inds, int64_t n_inds, uint64_t seed, int64_t n,
+        int64_t id0, int32_t t, double sensitivity, double loss_prob, int32_t test_delay, uint32_t index) {
+    const float tf = (float)t;
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_inds; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = inds[j];
+        if (i < 0 || i >= n) continue;
+        PB(P, tested)[i] = 1;
+        PF(P, date_tested)[i] = tf;
+        if (!PB(P, infectious)[i]) continue;
+        if (!(keyed_uniform(seed, P_TEST_SENS, index, t, i + id0, 0) < sensitivity)) continue;
+        if (!is_nan(PF(P, date_diagnosed)[i])) continue;
+        if (!(keyed_uniform(seed, P_TEST_LOSS, index, t, i + id0, 0) < 1.0 - loss_prob)) continue;
+        PF(P, date_diagnosed)[i] = (float)(t + test_delay);
+        PF(P, date_pos_test)[i] = tf;
+    }
+}
+
+// ================================================================================================
 // contact_tracing
 // ================================================================================================
 // Today's cases as a bitmap: each thread tests 4 agents (one 128-bit load), 8 lanes assemble a 32-bit word
@@ -346,6 +393,26 @@ int cvb_trace_notify_contacts(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, c
     if (!any_sparse) return 0;
     if (cvb::list_from_bits(s, s->case_bits_global, s->n_slots / 32, st)) return 1;
     trace_sparse_kernel<<<148 * 2, kThreads, 0, st>>>(s->people, T, s->padj_ptr, s->padj, s->glist, s->n_glist, s->padj_layer_mask);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
+
+int cvb_test_num_keys(cvb_sim* s, int32_t t, const cvb_test_num_pars* tp, double* weight, double* key, cvb_stream st) {
+    CVB_REQUIRE(s && tp && weight && key, "cvb_test_num_keys: bad argument");
+    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_test_num_keys: day %d outside [0,%d)", t, s->npts);
+    test_num_keys_kernel<<<grid_for(s->n, kThreads, 148 * 8), kThreads, 0, (cudaStream_t)st>>>(s->people, *tp, s->seed, s->n,
+        s->partitioned ? s->id0 : 0, t, weight, key);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
+
+int cvb_test_list(cvb_sim* s, int32_t t, const int32_t* inds, int64_t n_inds, double sensitivity, double loss_prob, int32_t test_delay,
+                  int32_t index, cvb_stream st) {
+    CVB_REQUIRE(s && (n_inds == 0 || inds), "cvb_test_list: bad argument");
+    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_test_list: day %d outside [0,%d)", t, s->npts);
+    if (n_inds == 0) return 0;
+    test_list_kernel<<<grid_for(n_inds), kThreads, 0, (cudaStream_t)st>>>(s->people, inds, n_inds, s->seed, s->n, s->partitioned ? s->id0 : 0, t,
+                                                                          sensitivity, loss_prob, test_delay, (uint32_t)index);
     CVB_LAUNCH_CHECK();
     return 0;
 }

@@ -17,7 +17,7 @@ import torch
 from . import parameters as cvpar
 from . import _capi
 
-__all__ = ['Intervention', 'dynamic_pars', 'sequence', 'change_beta', 'clip_edges', 'test_prob', 'contact_tracing', 'vaccinate_prob', 'find_day', 'process_days']
+__all__ = ['Intervention', 'dynamic_pars', 'sequence', 'change_beta', 'clip_edges', 'test_num', 'test_prob', 'contact_tracing', 'vaccinate_prob', 'find_day', 'process_days']
 
 
 def find_day(arr, t=None, interv=None, sim=None, which='first'):
@@ -226,6 +226,87 @@ class clip_edges(Intervention):
 
 
 _QUAR_POLICY = dict(start=0, end=1, both=2, daily=3)
+
+
+class test_num(Intervention):
+    '''
+    A given number of tests per day, handed out by weight: symptomatic people ``symp_test`` times as likely, people in
+    quarantine ``quar_test`` times, diagnosed people never (reference interventions.py:718-854 + people.py:589-617).
+    Native-RNG mode: one device pass writes the weights and the exponential-clock keys ``-log(1 - u) / w`` of every agent, the
+    ``n_tests`` smallest keys are a weighted sample without replacement (the reference's choose_w), and a second pass administers
+    the tests.  One device synchronisation per day (the number of agents with non-zero weight caps ``n_tests``).
+    Not built: subtarget, ili_prev, swab_delay, numeric / callable quar_policy, daily_tests from a data file.
+    '''
+
+    def __init__(self, daily_tests, symp_test=100.0, quar_test=1.0, quar_policy=None, subtarget=None, ili_prev=None, sensitivity=1.0,
+                 loss_prob=0, test_delay=0, start_day=0, end_day=None, swab_delay=None, **kwargs):
+        super().__init__(**kwargs)
+        if subtarget is not None or ili_prev is not None or swab_delay is not None:
+            raise NotImplementedError('test_num: subtarget / ili_prev / swab_delay are outside the built path')
+        if isinstance(daily_tests, str):
+            raise NotImplementedError('test_num: daily_tests from a data file is outside the built path (pass numbers)')
+        self.daily_tests = daily_tests
+        self.symp_test, self.quar_test = symp_test, quar_test
+        self.quar_policy = quar_policy if quar_policy else 'start'
+        if self.quar_policy not in _QUAR_POLICY:
+            raise NotImplementedError(f'test_num: quar_policy "{self.quar_policy}" is not built (choices: {list(_QUAR_POLICY)})')
+        self.sensitivity, self.loss_prob, self.test_delay = sensitivity, loss_prob, test_delay
+        self.start_day, self.end_day = start_day, end_day
+
+    def initialize(self, sim):
+        super().initialize()
+        if sim._comm is not None:
+            raise NotImplementedError('test_num picks the n_tests smallest keys of the whole population and is not built for agent-partitioned runs; use test_prob')
+        self.start_day = sim.day(self.start_day)
+        self.end_day = sim.day(self.end_day)
+        self.days = [self.start_day, self.end_day]
+        dt_ = self.daily_tests
+        self.daily_tests = np.array([dt_] * sim.npts) if isinstance(dt_, (int, float, np.integer, np.floating)) else np.asarray(dt_)
+        self.index = sim.intervention_index(self)
+        self._c = _capi.cvb_test_num_pars(symp_test=float(self.symp_test), quar_test=float(self.quar_test),
+                                          quar_policy=_QUAR_POLICY[self.quar_policy], index=self.index)
+        dev = sim.people.device
+        self._weight = torch.empty(sim.n_local, dtype=torch.float64, device=dev)
+        self._key = torch.empty(sim.n_local, dtype=torch.float64, device=dev)
+
+    def n_tests_today(self, sim):
+        ''' The day's number of tests (randround of the scaled daily number; one NumPy-stream draw), or 0 '''
+        t = sim.t
+        if t < self.start_day or (self.end_day is not None and t > self.end_day):
+            return 0
+        rel_t = t - self.start_day
+        if rel_t >= len(self.daily_tests):
+            return 0
+        n_tests = int(np.floor(self.daily_tests[rel_t] / sim.rescale_vec[t] + sim.rng.np_.random_sample()))       # sc.randround
+        if not (n_tests and np.isfinite(n_tests)):
+            return 0
+        sim._host_add('new_tests', t, n_tests)
+        return n_tests
+
+    def rescaled(self, sim, n_tests, weight_sum):
+        ''' Share of the tests that falls inside the simulated sample while the population is still being rescaled (interventions.py:838-842) '''
+        t = sim.t
+        if sim.rescale_vec[t] / sim['pop_scale'] < 1:
+            in_tot = weight_sum * sim.rescale_vec[t]
+            out_tot = sim.scaled_pop_size - sim.rescale_vec[t] * sim['pop_size']
+            n_tests = int(np.floor(n_tests * in_tot / (in_tot + out_tot) + sim.rng.np_.random_sample()))              # sc.randround
+        return n_tests
+
+    def apply(self, sim):
+        n_tests = self.n_tests_today(sim)
+        if not n_tests:
+            return
+        t = sim.t
+        sim._call('cvb_test_num_keys', sim._handle, t, C.byref(self._c), self._weight.data_ptr(), self._key.data_ptr(), sim._stream_ptr)
+        if sim.rescale_vec[t] / sim['pop_scale'] < 1:
+            n_tests = self.rescaled(sim, n_tests, float(self._weight.sum().item()))
+        n_tests = min(n_tests, int(torch.count_nonzero(self._weight).item()))
+        if n_tests <= 0:
+            return
+        inds = torch.topk(self._key, n_tests, largest=False, sorted=False).indices.to(torch.int32).contiguous()
+        sim._call('cvb_test_list', sim._handle, t, inds.data_ptr(), n_tests, float(self.sensitivity), float(self.loss_prob), int(self.test_delay),
+                  self.index, sim._stream_ptr)
+        return inds
 
 
 class test_prob(Intervention):

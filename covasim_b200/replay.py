@@ -244,6 +244,34 @@ def test_prob_apply(iv, sim):
     sim._host_add('new_tests', t, len(tested) * sim.pars['pop_scale'] / sim.rescale_vec[t])
 
 
+def test_num_apply(iv, sim):
+    ''' reference interventions.py:786-854: the weights are built on the device, choose_w runs on the mirrored NumPy stream '''
+    n_tests = iv.n_tests_today(sim)
+    if not n_tests:
+        return
+    P, t = sim.people, sim.t
+    probs = torch.ones(sim.n, dtype=torch.float64, device=sim.device)
+    probs[P.symptomatic] *= iv.symp_test
+    pol = iv.quar_policy
+    if pol == 'start':
+        qt = P.date_quarantined == t - 1
+    elif pol == 'end':
+        qt = P.date_end_quarantine == t + 1
+    elif pol == 'both':
+        qt = (P.date_quarantined == t - 1) | (P.date_end_quarantine == t + 1)
+    else:
+        qt = P.quarantined.clone()
+    probs[qt] *= iv.quar_test
+    probs[P.diagnosed] = 0.0
+    probs = probs.cpu().numpy()
+    n_tests = iv.rescaled(sim, n_tests, probs.sum())
+    n_tests = min(n_tests, int((probs != 0).sum()))
+    total = probs.sum()
+    p = probs / total if total else np.ones(len(probs)) / len(probs)                       # reference utils.py:446-483 choose_w
+    inds = sim.rng.np_.choice(len(probs), int(n_tests), p=p, replace=False)
+    test_people(sim, torch.as_tensor(inds, dtype=torch.int64, device=sim.device), iv.sensitivity, iv.loss_prob, iv.test_delay)
+
+
 def contact_tracing_apply(iv, sim):
     ''' reference interventions.py:1044-1145 '''
     P, t = sim.people, sim.t
@@ -342,7 +370,7 @@ def step(sim):
             sim._host_add('n_imports', t, n_imports)
     for v in pars['variants']:
         v.apply(sim)
-    from .interventions import sequence
+    from .interventions import sequence, test_num
 
     def apply_intervention(iv):
         if isinstance(iv, sequence):                      # the intervention in force today, through the same dispatch
@@ -352,6 +380,8 @@ def step(sim):
         elif isinstance(iv, test_prob):
             if not (t < iv.start_day or (iv.end_day is not None and t > iv.end_day)):
                 test_prob_apply(iv, sim)
+        elif isinstance(iv, test_num):
+            test_num_apply(iv, sim)
         elif isinstance(iv, contact_tracing):
             if not (t < iv.start_day or (iv.end_day is not None and t > iv.end_day)):
                 contact_tracing_apply(iv, sim)

@@ -212,6 +212,19 @@ typedef struct cvb_test_prob_pars {        /* interventions.py:857-981 */
 } cvb_test_prob_pars;
 int cvb_test_prob(cvb_sim* s, int32_t t, const cvb_test_prob_pars* host_pars, cvb_stream st);
 
+typedef struct cvb_test_num_pars {         /* interventions.py:718-854 */
+    double symp_test, quar_test;
+    int32_t quar_policy;                   /* 0 start, 1 end, 2 both, 3 daily */
+    int32_t index;
+} cvb_test_num_pars;
+/* test_num, device part one: per-agent testing weights (the reference's test_probs, float64[n]) and exponential-clock keys
+ * -log(1 - u) / w (float64[n], +inf where w == 0); the n_tests agents with the smallest keys are a weighted sample without
+ * replacement.  The caller selects them and hands them to cvb_test_list. */
+int cvb_test_num_keys(cvb_sim* s, int32_t t, const cvb_test_num_pars* host_pars, double* weight, double* key, cvb_stream st);
+/* people.py:589-617 People.test for a list of distinct agents (int32[n_inds]); keyed sensitivity / loss-to-follow-up draws */
+int cvb_test_list(cvb_sim* s, int32_t t, const int32_t* inds, int64_t n_inds, double sensitivity, double loss_prob, int32_t test_delay,
+                  int32_t index, cvb_stream st);
+
 typedef struct cvb_trace_pars {            /* interventions.py:984-1145 */
     double trace_prob[CVB_MAX_LAYERS];
     int32_t trace_time[CVB_MAX_LAYERS];

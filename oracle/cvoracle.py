@@ -894,6 +894,68 @@ class clip_edges(Intervention):
                     self._move(i_layer, s_layer, sim.rng.choose('nb', n_int, abs(n_to_move)))
 
 
+class test_num(Intervention):
+    ''' Number-based testing (reference interventions.py:718-854); subtarget / ili_prev / swab_delay not built '''
+    def __init__(self, daily_tests, symp_test=100.0, quar_test=1.0, quar_policy=None, sensitivity=1.0, loss_prob=0, test_delay=0,
+                 start_day=0, end_day=None):
+        self.daily_tests, self.symp_test, self.quar_test = daily_tests, symp_test, quar_test
+        self.quar_policy = quar_policy if quar_policy else 'start'
+        self.sensitivity, self.loss_prob, self.test_delay = sensitivity, loss_prob, test_delay
+        self.start_day, self.end_day = start_day, end_day
+
+    def initialize(self, sim):
+        self.start_day, self.end_day = sim.day(self.start_day), sim.day(self.end_day)
+        self.daily_tests = np.array([self.daily_tests] * sim.npts) if np.isscalar(self.daily_tests) else np.asarray(self.daily_tests)
+        self.index = sim.intervention_index(self)
+
+    def apply(self, sim):
+        t, P, pars = sim.t, sim.P, sim.pars
+        if t < self.start_day or (self.end_day is not None and t > self.end_day):
+            return
+        rel_t = t - self.start_day
+        if rel_t >= len(self.daily_tests):
+            return
+        n_tests = int(np.floor(self.daily_tests[rel_t] / sim.rescale_vec[t] + sim.rng.np_.random_sample()))           # sc.randround
+        if not (n_tests and np.isfinite(n_tests)):
+            return
+        sim.results['new_tests'][t] += n_tests
+        n = pars['pop_size']
+        probs = np.ones(n)
+        probs[P['symptomatic']] *= self.symp_test
+        probs[get_quar_mask(P, t, self.quar_policy)] *= self.quar_test
+        probs[P['diagnosed']] = 0.0
+        if sim.rescale_vec[t] / pars['pop_scale'] < 1:                          # interventions.py:838-842
+            in_tot = probs.sum() * sim.rescale_vec[t]
+            out_tot = pars['pop_size'] * pars['pop_scale'] - sim.rescale_vec[t] * pars['pop_size']
+            n_tests = int(np.floor(n_tests * in_tot / (in_tot + out_tot) + sim.rng.np_.random_sample()))
+        n_tests = min(n_tests, int((probs != 0).sum()))
+        if sim.rng.kind == 'mt':                                                # utils.py:446-483 choose_w on the NumPy stream
+            total = probs.sum()
+            p = probs / total if total else np.ones(n) / n
+            inds = sim.rng.np_.choice(n, int(n_tests), p=p, replace=False)
+        else:                                                                   # exponential clocks: the n smallest -log(1-u)/w
+            if n_tests <= 0:
+                return
+            u = sim.rng.agent_uniforms(t, ph.P_TEST, self.index, np.arange(n))
+            with np.errstate(divide='ignore'):
+                key = np.where(probs > 0, -np.log(1.0 - u) / probs, np.inf)
+            inds = np.argpartition(key, n_tests - 1)[:n_tests]
+        test_people(P, sim.rng, t, inds, self.sensitivity, self.loss_prob, self.test_delay, sub=self.index)
+
+
+def get_quar_mask(P, t, policy):
+    ''' interventions.py:691-715 get_quar_inds as a boolean mask '''
+    if policy == 'start':
+        return P['date_quarantined'] == t - 1
+    if policy == 'end':
+        return P['date_end_quarantine'] == t + 1
+    if policy == 'both':
+        return (P['date_quarantined'] == t - 1) | (P['date_end_quarantine'] == t + 1)
+    if policy == 'daily':
+        return P['quarantined'].copy()
+    raise NotImplementedError(f'quar_policy {policy}')
+
+
 class test_prob(Intervention):
     ''' Probability-based testing (reference interventions.py:857-981); swab_delay / ili_prev / subtarget not built '''
     def __init__(self, symp_prob, asymp_prob=0.0, symp_quar_prob=None, asymp_quar_prob=None, quar_policy=None,

@@ -68,6 +68,16 @@ SCENARIOS = {
                                                                       ('test_prob', dict(symp_prob=0.1, asymp_prob=0.02, test_delay=1))])),
                        ('contact_tracing', dict(trace_probs=0.4, start_day=8))],
     ),
+    # number-based testing (test_num) with quarantine testing, traced; and with dynamic rescaling (share of tests inside the sample)
+    'testnum3k': dict(
+        pars=dict(pop_size=3000, pop_infected=50, pop_type='hybrid', n_days=35, verbose=0, rand_seed=71, beta=0.022),
+        interventions=[('test_num', dict(daily_tests=90, symp_test=50.0, quar_test=3.0, quar_policy='both', start_day=4, sensitivity=0.9, loss_prob=0.05, test_delay=1)),
+                       ('contact_tracing', dict(trace_probs=0.5, start_day=6))],
+    ),
+    'testnum_rescale2k': dict(
+        pars=dict(pop_size=2000, pop_scale=6, rescale=True, pop_infected=40, pop_type='hybrid', n_days=30, verbose=0, rand_seed=81, beta=0.025),
+        interventions=[('test_num', dict(daily_tests=[200] * 31, symp_test=80.0, start_day=3))],
+    ),
     # dynamic layer (BASELINE.json config 5 member shape, scaled down)
     'dynamic2k': dict(pars=dict(pop_size=2000, pop_infected=40, n_days=30, verbose=0, rand_seed=8, beta=0.02,
                                 dynam_layer=dict(a=1)), interventions=[]),

@@ -14,7 +14,7 @@ namespace cvb {
 // test_prob
 // ================================================================================================
 __global__ void __launch_bounds__(kThreads, 3) test_prob_kernel(PeoplePtrs P, const __grid_constant__ cvb_test_prob_pars tp, uint64_t seed,
-        int64_t n, int64_t id0, int32_t t, bool vec, unsigned long long* __restrict__ counters) {
+        int64_t n, int64_t id0, int32_t t, bool vec, unsigned long long* __restrict__ counters, const double* __restrict__ prob_override) {
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
@@ -49,7 +49,11 @@ __global__ void __launch_bounds__(kThreads, 3) test_prob_kernel(PeoplePtrs P, co
                 case 2:  qt = (dq[k] == tf - 1.0f) || (deq[k] == tf + 1.0f); break;
                 default: qt = flag(w_quar, k); break;
             }
-            const double prob = qt ? (symp ? tp.symp_quar_prob : tp.asymp_quar_prob) : (symp ? tp.symp_prob : tp.asymp_prob);
+            double prob = qt ? (symp ? tp.symp_quar_prob : tp.asymp_quar_prob) : (symp ? tp.symp_prob : tp.asymp_prob);
+            if (prob_override) {                                       // subtarget (interventions.py:971-973): explicit probabilities win
+                const double ov = prob_override[i];
+                if (ov == ov) prob = ov;
+            }
             if (!(prob > 0.0)) continue;
             if (!(keyed_uniform(seed, P_TEST, (uint32_t)tp.index, t, i + id0, 0) < prob)) continue;
             // People.test (people.py:589-617)
@@ -250,7 +254,8 @@ __global__ void __launch_bounds__(THREADS) trace_edges_kernel(PeoplePtrs P, cons
 // vaccinate_prob
 // ================================================================================================
 __global__ void __launch_bounds__(kThreads) vaccinate_kernel(PeoplePtrs P, const __grid_constant__ cvb_vaccinate_pars vp, uint64_t seed,
-        int64_t n, int64_t id0, int32_t t, int32_t* __restrict__ iv_doses, int32_t* __restrict__ due_day, unsigned long long* __restrict__ counters) {
+        int64_t n, int64_t id0, int32_t t, int32_t* __restrict__ iv_doses, int32_t* __restrict__ due_day, unsigned long long* __restrict__ counters,
+        const double* __restrict__ prob_override) {
     __shared__ int s_cnt[2];
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
@@ -261,7 +266,12 @@ __global__ void __launch_bounds__(kThreads) vaccinate_kernel(PeoplePtrs P, const
         const bool vacc = vaccinated[i] != 0;
         if (vp.first_dose_today) {                                     // interventions.py:1631-1653 select_people
             const bool eligible = vp.booster ? vacc : !vacc;
-            if (eligible && vp.prob > 0.0 && keyed_uniform(seed, P_VACC, (uint32_t)vp.index, t, i + id0, 0) < vp.prob) {
+            double prob = eligible ? vp.prob : 0.0;
+            if (prob_override) {                                       // subtarget (interventions.py:1644-1647): explicit probabilities win
+                const double ov = prob_override[i];
+                if (ov == ov) prob = ov;
+            }
+            if (prob > 0.0 && keyed_uniform(seed, P_VACC, (uint32_t)vp.index, t, i + id0, 0) < prob) {
                 picked = true;
                 if (vp.interval >= 0 && t + vp.interval < vp.n_days) due_day[i] = t + vp.interval;
             }
@@ -318,13 +328,13 @@ using namespace cvb;
 
 extern "C" {
 
-int cvb_test_prob(cvb_sim* s, int32_t t, const cvb_test_prob_pars* tp, cvb_stream st) {
+int cvb_test_prob(cvb_sim* s, int32_t t, const cvb_test_prob_pars* tp, const double* prob_override, cvb_stream st) {
     CVB_REQUIRE(s && tp && s->res.counters, "cvb_test_prob: handle not ready");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_test_prob: day %d outside [0,%d)", t, s->npts);
     uintptr_t al = 0;
     for (int f = 0; f < CVB_N_FIELDS; ++f) al |= (uintptr_t)s->people.f[f];
     test_prob_kernel<<<grid_for((s->n + kAPT - 1) / kAPT, kThreads, 148 * 8), kThreads, 0, (cudaStream_t)st>>>(
-        s->people, *tp, s->seed, s->n, s->partitioned ? s->id0 : 0, t, (al & 15) == 0 && s->n % 4 == 0, s->res.counters);
+        s->people, *tp, s->seed, s->n, s->partitioned ? s->id0 : 0, t, (al & 15) == 0 && s->n % 4 == 0, s->res.counters, prob_override);
     CVB_LAUNCH_CHECK();
     return 0;
 }
@@ -454,11 +464,12 @@ int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_str
     return 0;
 }
 
-int cvb_vaccinate_prob(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* vp, int32_t* iv_doses, int32_t* due_day, cvb_stream st) {
+int cvb_vaccinate_prob(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* vp, int32_t* iv_doses, int32_t* due_day, const double* prob_override,
+                       cvb_stream st) {
     CVB_REQUIRE(s && vp && iv_doses && due_day && s->res.counters, "cvb_vaccinate_prob: bad argument");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_vaccinate_prob: day %d outside [0,%d)", t, s->npts);
     CVB_REQUIRE(vp->vaccine_index >= 0 && vp->vaccine_index < CVB_MAX_VACCINES, "cvb_vaccinate_prob: vaccine index out of range");
-    vaccinate_kernel<<<grid_for(s->n), kThreads, 0, (cudaStream_t)st>>>(s->people, *vp, s->seed, s->n, s->partitioned ? s->id0 : 0, t, iv_doses, due_day, s->res.counters);
+    vaccinate_kernel<<<grid_for(s->n), kThreads, 0, (cudaStream_t)st>>>(s->people, *vp, s->seed, s->n, s->partitioned ? s->id0 : 0, t, iv_doses, due_day, s->res.counters, prob_override);
     CVB_LAUNCH_CHECK();
     return 0;
 }

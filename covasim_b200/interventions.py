@@ -43,6 +43,35 @@ def process_days(sim, days):
     return np.sort(np.array(out))
 
 
+def get_subtargets(subtarget, sim):
+    ''' (indices, values) of a ``subtarget`` option: a dict with 'inds' and 'vals', either of which may be a function of the sim (reference interventions.py:153-187) '''
+    if callable(subtarget):
+        subtarget = subtarget(sim)
+    if 'inds' not in subtarget:
+        raise ValueError(f'The subtarget dict must have keys "inds" and "vals", but you supplied {subtarget}')
+    inds = subtarget['inds'](sim) if callable(subtarget['inds']) else subtarget['inds']
+    vals = subtarget['vals'](sim) if callable(subtarget['vals']) else subtarget['vals']
+    if np.ndim(vals) and len(vals) != len(inds):
+        raise ValueError(f'Length of subtargeting indices ({len(inds)}) does not match length of values ({len(vals)})')
+    return inds, vals
+
+
+def subtarget_override(subtarget, sim):
+    ''' The subtarget as a device array float64[n_local]: the explicit probability of every subtargeted agent, NaN elsewhere '''
+    inds, vals = get_subtargets(subtarget, sim)
+    dev = sim.people.device
+    inds = torch.as_tensor(inds, device=dev).to(torch.int64)
+    vals = torch.as_tensor(vals, dtype=torch.float64, device=dev)
+    if vals.ndim == 0:
+        vals = vals.expand(len(inds))
+    if sim._comm is not None:                          # agent-partitioned: global ids, this rank keeps its own agents
+        keep = (inds >= sim.id0) & (inds < sim.id0 + sim.n_local)
+        inds, vals = inds[keep] - sim.id0, vals[keep]
+    out = torch.full((sim.n_local,), float('nan'), dtype=torch.float64, device=dev)
+    out[inds] = vals
+    return out
+
+
 class Intervention:
     ''' Base class (reference interventions.py:223-410) '''
 
@@ -314,14 +343,16 @@ class test_prob(Intervention):
     Probability-based testing (reference interventions.py:857-981 + people.py:589-617).  One per-agent
     device pass: test probability from symptom / quarantine / diagnosis state, keyed Bernoulli draws
     for "tests today", "test is positive" (sensitivity) and "not lost to follow-up".
-    Not built: swab_delay, ili_prev, subtarget, callable quar_policy.
+    ``subtarget`` (explicit probabilities for given agents) is passed to the kernel as a per-agent override array.
+    Not built: swab_delay, ili_prev, callable quar_policy.
     '''
 
     def __init__(self, symp_prob, asymp_prob=0.0, symp_quar_prob=None, asymp_quar_prob=None, quar_policy=None, subtarget=None,
                  ili_prev=None, sensitivity=1.0, loss_prob=0.0, test_delay=0, start_day=0, end_day=None, swab_delay=None, **kwargs):
         super().__init__(**kwargs)
-        if subtarget is not None or ili_prev is not None or swab_delay is not None:
-            raise NotImplementedError('test_prob: subtarget / ili_prev / swab_delay are outside the built path')
+        if ili_prev is not None or swab_delay is not None:
+            raise NotImplementedError('test_prob: ili_prev / swab_delay are outside the built path')
+        self.subtarget = subtarget
         self.symp_prob, self.asymp_prob = symp_prob, asymp_prob
         self.symp_quar_prob = symp_prob if symp_quar_prob is None else symp_quar_prob
         self.asymp_quar_prob = asymp_prob if asymp_quar_prob is None else asymp_quar_prob
@@ -345,7 +376,8 @@ class test_prob(Intervention):
         t = sim.t
         if t < self.start_day or (self.end_day is not None and t > self.end_day):
             return
-        sim._call('cvb_test_prob', sim._handle, t, C.byref(self._c), sim._stream_ptr)
+        override = None if self.subtarget is None else subtarget_override(self.subtarget, sim)      # kept alive until the call returns
+        sim._call('cvb_test_prob', sim._handle, t, C.byref(self._c), None if override is None else override.data_ptr(), sim._stream_ptr)
 
 
 class contact_tracing(Intervention):
@@ -402,13 +434,12 @@ class vaccinate_prob(Intervention):
     '''
     Probability-based vaccination with scheduled second doses (reference interventions.py:1257-1662).
     One per-agent device pass on first-dose days and on days when second doses are due.
-    Not built: subtarget, target_eff.
+    ``subtarget`` is passed to the kernel as a per-agent override array.  Not built: target_eff.
     '''
 
     def __init__(self, vaccine, days, label=None, prob=None, subtarget=None, booster=False, **kwargs):
         super().__init__(**kwargs)
-        if subtarget is not None:
-            raise NotImplementedError('vaccinate_prob: subtarget is outside the built path')
+        self.subtarget = subtarget
         self.vaccine, self.days, self.label = vaccine, days, label
         self.prob = 1.0 if prob is None else prob
         self.booster = booster
@@ -476,4 +507,6 @@ class vaccinate_prob(Intervention):
             return
         self._c.first_dose_today = int(first)
         self._c.second_dose_today = int(second)
-        sim._call('cvb_vaccinate_prob', sim._handle, t, C.byref(self._c), self.doses.data_ptr(), self.due_day.data_ptr(), sim._stream_ptr)
+        override = subtarget_override(self.subtarget, sim) if (first and self.subtarget is not None) else None
+        sim._call('cvb_vaccinate_prob', sim._handle, t, C.byref(self._c), self.doses.data_ptr(), self.due_day.data_ptr(),
+                  None if override is None else override.data_ptr(), sim._stream_ptr)

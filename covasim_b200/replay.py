@@ -238,6 +238,10 @@ def test_prob_apply(iv, sim):
     probs = torch.where(symp, iv.symp_prob, iv.asymp_prob).to(torch.float64)
     probs[qt & symp] = iv.symp_quar_prob
     probs[qt & ~symp] = iv.asymp_quar_prob
+    if iv.subtarget is not None:
+        from .interventions import subtarget_override
+        ov = subtarget_override(iv.subtarget, sim)
+        probs = torch.where(torch.isnan(ov), probs, ov)
     probs[P.diagnosed] = 0.0
     tested = torch.nonzero(_uniforms(sim, sim.n) < probs).flatten()
     test_people(sim, tested, iv.sensitivity, iv.loss_prob, iv.test_delay)
@@ -308,6 +312,10 @@ def vaccinate_apply(iv, sim):
         probs = torch.zeros(sim.n, dtype=torch.float64, device=sim.device)
         eligible = P.vaccinated if iv.booster else ~P.vaccinated
         probs[eligible] = iv.prob
+        if iv.subtarget is not None:
+            from .interventions import subtarget_override
+            ov = subtarget_override(iv.subtarget, sim)
+            probs = torch.where(torch.isnan(ov), probs, ov)
         picked = torch.nonzero(_uniforms(sim, sim.n) < probs).flatten()
         if len(picked) and iv.p['interval'] is not None:
             nxt = t + iv.p['interval']

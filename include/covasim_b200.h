@@ -210,7 +210,8 @@ typedef struct cvb_test_prob_pars {        /* interventions.py:857-981 */
     int32_t quar_policy;                   /* 0 start, 1 end, 2 both, 3 daily */
     int32_t test_delay, index, pad_;
 } cvb_test_prob_pars;
-int cvb_test_prob(cvb_sim* s, int32_t t, const cvb_test_prob_pars* host_pars, cvb_stream st);
+/* prob_override: NULL, or float64[n] of explicit per-agent probabilities (NaN = none): the `subtarget` option (interventions.py:971-973) */
+int cvb_test_prob(cvb_sim* s, int32_t t, const cvb_test_prob_pars* host_pars, const double* prob_override, cvb_stream st);
 
 typedef struct cvb_test_num_pars {         /* interventions.py:718-854 */
     double symp_test, quar_test;
@@ -247,7 +248,7 @@ typedef struct cvb_vaccinate_pars {        /* interventions.py:1257-1662 */
 /* `iv_doses` int32[n] is this intervention's own dose count, `due_day` int32[n] the day an agent's second
  * dose is due (-1 none) -- the device form of second_dose_days (interventions.py:1655-1660) */
 int cvb_vaccinate_prob(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* host_pars, int32_t* iv_doses, int32_t* due_day,
-                       cvb_stream st);
+                       const double* prob_override /* NULL or float64[n], NaN = none: `subtarget` (interventions.py:1644-1647) */, cvb_stream st);
 
 /* base.py:1849-1876 Layer.update with frac=1: regenerate every edge of a dynamic layer on the device */
 int cvb_layer_regenerate(cvb_sim* s, int32_t layer, int32_t t, cvb_stream st);

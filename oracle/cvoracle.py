@@ -959,7 +959,8 @@ def get_quar_mask(P, t, policy):
 class test_prob(Intervention):
     ''' Probability-based testing (reference interventions.py:857-981); swab_delay / ili_prev / subtarget not built '''
     def __init__(self, symp_prob, asymp_prob=0.0, symp_quar_prob=None, asymp_quar_prob=None, quar_policy=None,
-                 sensitivity=1.0, loss_prob=0.0, test_delay=0, start_day=0, end_day=None):
+                 sensitivity=1.0, loss_prob=0.0, test_delay=0, start_day=0, end_day=None, subtarget=None):
+        self.subtarget = subtarget
         self.symp_prob, self.asymp_prob = symp_prob, asymp_prob
         self.symp_quar_prob = symp_prob if symp_quar_prob is None else symp_quar_prob
         self.asymp_quar_prob = asymp_prob if asymp_quar_prob is None else asymp_quar_prob
@@ -991,6 +992,8 @@ class test_prob(Intervention):
         probs = np.where(symp, self.symp_prob, self.asymp_prob).astype(float)
         probs[qt & symp] = self.symp_quar_prob
         probs[qt & ~symp] = self.asymp_quar_prob
+        if self.subtarget is not None:                          # interventions.py:971-973: explicit probabilities win
+            probs[np.asarray(self.subtarget['inds'])] = self.subtarget['vals']
         probs[P['diagnosed']] = 0.0
         everyone = np.arange(n)
         tested = np.nonzero(sim.rng.agent_uniforms(t, ph.P_TEST, self.index, everyone) < probs)[0]
@@ -1047,8 +1050,9 @@ class contact_tracing(Intervention):
 
 class vaccinate_prob(Intervention):
     ''' Probability-based vaccination with optional second dose (reference interventions.py:1257-1662) '''
-    def __init__(self, vaccine, days, label=None, prob=1.0, booster=False):
+    def __init__(self, vaccine, days, label=None, prob=1.0, booster=False, subtarget=None):
         self.vaccine, self.days, self.label, self.prob, self.booster = vaccine, days, label, prob, booster
+        self.subtarget = subtarget
 
     def initialize(self, sim):
         if isinstance(self.vaccine, str):
@@ -1088,6 +1092,8 @@ class vaccinate_prob(Intervention):
                 probs = np.zeros(n)
                 eligible = P['vaccinated'] if self.booster else ~P['vaccinated']
                 probs[eligible] = self.prob
+                if self.subtarget is not None:                  # interventions.py:1644-1647: explicit probabilities win
+                    probs[np.asarray(self.subtarget['inds'])] = self.subtarget['vals']
                 picked = np.nonzero(sim.rng.agent_uniforms(t, ph.P_VACC, self.iindex, np.arange(n)) < probs)[0]
                 if len(picked) and self.p['interval'] is not None:
                     nxt = t + self.p['interval']

@@ -7,6 +7,8 @@ constructor names (the reference itself, oracle.cvoracle, or covasim_b200).
 '''
 import copy
 
+import numpy as np
+
 SCENARIOS = {
     # reference tests/test_baselines.py:18-56 -- the sim behind tests/baseline.json
     'baseline20k': dict(
@@ -77,6 +79,13 @@ SCENARIOS = {
     'testnum_rescale2k': dict(
         pars=dict(pop_size=2000, pop_scale=6, rescale=True, pop_infected=40, pop_type='hybrid', n_days=30, verbose=0, rand_seed=81, beta=0.025),
         interventions=[('test_num', dict(daily_tests=[200] * 31, symp_test=80.0, start_day=3))],
+    ),
+    # subtargeting: explicit testing / vaccination probabilities for given agents (a scalar for every 4th agent; a ramp over a block)
+    'subtarget3k': dict(
+        pars=dict(pop_size=3000, pop_infected=50, pop_type='hybrid', n_days=35, verbose=0, rand_seed=91, beta=0.022),
+        interventions=[('test_prob', dict(start_day=3, symp_prob=0.2, asymp_prob=0.01, subtarget=dict(inds=np.arange(0, 3000, 4), vals=0.15))),
+                       ('vaccinate_prob', dict(vaccine='pfizer', days=[6, 9], prob=0.02,
+                                               subtarget=dict(inds=np.arange(1000, 2500), vals=np.linspace(0.0, 0.6, 1500))))],
     ),
     # dynamic layer (BASELINE.json config 5 member shape, scaled down)
     'dynamic2k': dict(pars=dict(pop_size=2000, pop_infected=40, n_days=30, verbose=0, rand_seed=8, beta=0.02,

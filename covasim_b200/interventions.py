@@ -350,9 +350,10 @@ class test_prob(Intervention):
     def __init__(self, symp_prob, asymp_prob=0.0, symp_quar_prob=None, asymp_quar_prob=None, quar_policy=None, subtarget=None,
                  ili_prev=None, sensitivity=1.0, loss_prob=0.0, test_delay=0, start_day=0, end_day=None, swab_delay=None, **kwargs):
         super().__init__(**kwargs)
-        if ili_prev is not None or swab_delay is not None:
-            raise NotImplementedError('test_prob: ili_prev / swab_delay are outside the built path')
+        if swab_delay is not None:
+            raise NotImplementedError('test_prob: swab_delay is outside the built path')
         self.subtarget = subtarget
+        self.ili_prev = ili_prev
         self.symp_prob, self.asymp_prob = symp_prob, asymp_prob
         self.symp_quar_prob = symp_prob if symp_quar_prob is None else symp_quar_prob
         self.asymp_quar_prob = asymp_prob if asymp_quar_prob is None else asymp_quar_prob
@@ -367,6 +368,11 @@ class test_prob(Intervention):
         self.start_day = sim.day(self.start_day)
         self.end_day = sim.day(self.end_day)
         self.days = [self.start_day, self.end_day]
+        if self.ili_prev is not None:                      # process_daily_data: a number applies every day
+            ip = self.ili_prev
+            self.ili_prev = np.array([ip] * sim.npts) if isinstance(ip, (int, float, np.integer, np.floating)) else np.asarray(ip)
+            if sim._comm is not None:
+                raise NotImplementedError('test_prob(ili_prev=...) draws a population-wide set on the host and is not built for agent-partitioned runs')
         self.index = sim.intervention_index(self)
         self._c = _capi.cvb_test_prob_pars(symp_prob=self.symp_prob, asymp_prob=self.asymp_prob, symp_quar_prob=self.symp_quar_prob,
                                            asymp_quar_prob=self.asymp_quar_prob, sensitivity=self.sensitivity, loss_prob=self.loss_prob,
@@ -376,8 +382,41 @@ class test_prob(Intervention):
         t = sim.t
         if t < self.start_day or (self.end_day is not None and t > self.end_day):
             return
-        override = None if self.subtarget is None else subtarget_override(self.subtarget, sim)      # kept alive until the call returns
+        override = self.override(sim)                      # kept alive until the call returns
         sim._call('cvb_test_prob', sim._handle, t, C.byref(self._c), None if override is None else override.data_ptr(), sim._stream_ptr)
+
+
+    def ili_inds(self, sim):
+        ''' Today's people with influenza-like illness: a host-side set choice from the Numba stream (interventions.py:946-953), or None '''
+        if self.ili_prev is None:
+            return None
+        rel_t = sim.t - self.start_day
+        if rel_t >= len(self.ili_prev):
+            return None
+        n_ili = int(self.ili_prev[rel_t] * sim['pop_size'])
+        if sim.rng_mode == 'mt':
+            return sim.rng.nb.choice(sim['pop_size'], n_ili, replace=False)                  # cvu.choose
+        from . import utils as cvu
+        return cvu.choose_distinct(sim.rng.nb, sim['pop_size'], n_ili)
+
+    def override(self, sim):
+        '''
+        Per-agent explicit probabilities (NaN = none) for the kernel: people with ILI symptoms who are not symptomatic test like
+        symptomatic people whatever their quarantine state (interventions.py:962-967), then the subtarget on top (:971-973).
+        '''
+        ili = self.ili_inds(sim)
+        if ili is None and self.subtarget is None:
+            return None
+        dev = sim.people.device
+        out = torch.full((sim.n_local,), float('nan'), dtype=torch.float64, device=dev)
+        if ili is not None and len(ili):
+            ili = torch.as_tensor(ili, dtype=torch.int64, device=dev)
+            ili = ili[~sim.people.symptomatic[ili]]
+            out[ili] = float(self.symp_prob)
+        if self.subtarget is not None:
+            sub = subtarget_override(self.subtarget, sim)
+            out = torch.where(torch.isnan(sub), out, sub)
+        return out
 
 
 class contact_tracing(Intervention):

@@ -238,9 +238,8 @@ def test_prob_apply(iv, sim):
     probs = torch.where(symp, iv.symp_prob, iv.asymp_prob).to(torch.float64)
     probs[qt & symp] = iv.symp_quar_prob
     probs[qt & ~symp] = iv.asymp_quar_prob
-    if iv.subtarget is not None:
-        from .interventions import subtarget_override
-        ov = subtarget_override(iv.subtarget, sim)
+    ov = iv.override(sim)                          # ILI symptoms (consumes the Numba stream like the reference) and subtargets
+    if ov is not None:
         probs = torch.where(torch.isnan(ov), probs, ov)
     probs[P.diagnosed] = 0.0
     tested = torch.nonzero(_uniforms(sim, sim.n) < probs).flatten()

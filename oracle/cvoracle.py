@@ -959,8 +959,8 @@ def get_quar_mask(P, t, policy):
 class test_prob(Intervention):
     ''' Probability-based testing (reference interventions.py:857-981); swab_delay / ili_prev / subtarget not built '''
     def __init__(self, symp_prob, asymp_prob=0.0, symp_quar_prob=None, asymp_quar_prob=None, quar_policy=None,
-                 sensitivity=1.0, loss_prob=0.0, test_delay=0, start_day=0, end_day=None, subtarget=None):
-        self.subtarget = subtarget
+                 sensitivity=1.0, loss_prob=0.0, test_delay=0, start_day=0, end_day=None, subtarget=None, ili_prev=None):
+        self.subtarget, self.ili_prev = subtarget, ili_prev
         self.symp_prob, self.asymp_prob = symp_prob, asymp_prob
         self.symp_quar_prob = symp_prob if symp_quar_prob is None else symp_quar_prob
         self.asymp_quar_prob = asymp_prob if asymp_quar_prob is None else asymp_quar_prob
@@ -972,6 +972,8 @@ class test_prob(Intervention):
         self.start_day = sim.day(self.start_day)
         self.end_day = sim.day(self.end_day)
         self.index = sim.intervention_index(self)
+        if self.ili_prev is not None:
+            self.ili_prev = np.array([self.ili_prev] * sim.npts) if np.isscalar(self.ili_prev) else np.asarray(self.ili_prev)
 
     def apply(self, sim):
         t, P = sim.t, sim.P
@@ -979,6 +981,11 @@ class test_prob(Intervention):
             return
         n = len(P['uid'])
         symp = P['symptomatic']
+        ili = np.zeros(n, dtype=bool)                           # interventions.py:946-953: ILI symptoms, independent of COVID
+        if self.ili_prev is not None and t - self.start_day < len(self.ili_prev):
+            chosen = sim.rng.choose('nb', n, int(self.ili_prev[t - self.start_day] * n))
+            ili[chosen] = True
+            ili &= ~symp
         if self.quar_policy == 'start':
             qt = P['date_quarantined'] == t - 1
         elif self.quar_policy == 'end':
@@ -992,6 +999,7 @@ class test_prob(Intervention):
         probs = np.where(symp, self.symp_prob, self.asymp_prob).astype(float)
         probs[qt & symp] = self.symp_quar_prob
         probs[qt & ~symp] = self.asymp_quar_prob
+        probs[ili] = self.symp_prob                             # ILI people test like symptomatic ones, in quarantine or not (:962-967)
         if self.subtarget is not None:                          # interventions.py:971-973: explicit probabilities win
             probs[np.asarray(self.subtarget['inds'])] = self.subtarget['vals']
         probs[P['diagnosed']] = 0.0

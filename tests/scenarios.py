@@ -87,6 +87,12 @@ SCENARIOS = {
                        ('vaccinate_prob', dict(vaccine='pfizer', days=[6, 9], prob=0.02,
                                                subtarget=dict(inds=np.arange(1000, 2500), vals=np.linspace(0.0, 0.6, 1500))))],
     ),
+    # influenza-like illness: a random 2 % of the population tests like symptomatic people every day, with quarantine testing
+    'ili3k': dict(
+        pars=dict(pop_size=3000, pop_infected=50, pop_type='hybrid', n_days=30, verbose=0, rand_seed=101, beta=0.022),
+        interventions=[('test_prob', dict(start_day=3, symp_prob=0.3, asymp_prob=0.005, symp_quar_prob=0.8, asymp_quar_prob=0.2, ili_prev=0.02)),
+                       ('contact_tracing', dict(trace_probs=0.5, start_day=5))],
+    ),
     # dynamic layer (BASELINE.json config 5 member shape, scaled down)
     'dynamic2k': dict(pars=dict(pop_size=2000, pop_infected=40, n_days=30, verbose=0, rand_seed=8, beta=0.02,
                                 dynam_layer=dict(a=1)), interventions=[]),

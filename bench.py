@@ -306,7 +306,7 @@ def measure_dense_edge_pass(args, cv, sim, snap, peak, E, N, day=60, reps=20):
         # ~100 MB of dirty lines whose write-back competes with the timed kernel's reads for HBM bandwidth
         flush.max()
         # ... and put the per-agent records back the way the simulated day leaves them: prepare_transmission has just
-        # written the {rel_trans, rel_sus} records and the transmit bitmap (32 MB + 125 KB at C2), so the edge pass finds
+        # written the per-layer {rel_trans, rel_sus} pairs the dense pass gathers and the transmit bitmap (32 MB + 125 KB at C2), so the edge pass finds
         # them in L2 while the edge lists (213 MB) come from HBM
         call('cvb_prepare_transmission', h, t, st)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -2,21 +2,30 @@
 //
 // The reference makes n_variants x n_layers x 2 passes over the edge lists per day (compute_trans_sus
 // + compute_infections per variant and layer, both directions) and re-gathers per-agent values with
-// fancy indexing each time.  Here every edge (p1:int32, p2:int32, beta:f32 = 12 bytes) of every layer
-// is streamed from HBM exactly ONCE per day with 128-bit coalesced loads; both directions and all
-// variants are evaluated from the 8-byte {rel_trans, rel_sus} records of its endpoints (written by
-// prepare_transmission).  Algorithmic bytes per day: 12*E_total + 8*N.
+// fancy indexing each time.  Here one pass evaluates both directions and all variants.  Three forms,
+// with the same probability chain, the same Philox key (layer, edge) and the same winner key, so they
+// give identical results:
 //
-// Structure of one CTA (v2; see profiles/r1 for why):
-//   1. the day's "can transmit" bitmap (1 bit per agent, written by prepare_transmission) is staged in
-//      SHARED MEMORY (125 KB at 1M agents; a global/L1 path is used when it does not fit);
-//   2. each thread streams 4 edges and tests the two endpoint bits -- at the epidemic peak ~80 % of the
-//      edges have no infectious endpoint and are dropped here, after 12 bytes of HBM traffic and two
-//      shared-memory bit tests, without any L2 gather;
-//   3. surviving edges are appended to a per-warp queue in shared memory (ballot + popc compaction) and
-//      drained 32 at a time, so the expensive part -- two L2 gathers of the endpoint records, the
-//      float32 probability chain and the Philox4x32-10 draw -- always runs on full warps instead of on
-//      every warp that happens to contain one live lane.
+//   * adjacency form (edge_pass_sparse_kernel; static layers): one warp per TRANSMITTER walks its row of
+//     the bidirectional adjacency -- only the edges of the few percent of agents who can transmit today;
+//   * dense streaming form (edge_pass_kernel; dynamic layers or use_adjacency=False): every edge
+//     (p1:int32, p2:int32, beta:f32 = 12 bytes) is streamed from HBM exactly once per day with 128-bit
+//     loads.  Algorithmic bytes per day: 12*E_total + 8*N.  One persistent CTA of 512 threads per SM:
+//       1. the day's "can transmit" bitmap (1 bit per agent) is staged in SHARED MEMORY (125 KB at 1M agents;
+//          a global / L1 path is used when it does not fit);
+//       2. each thread loads two quads of four edges (six 128-bit loads, the next tile's already in flight,
+//          the one after prefetched into L2), requests all sixteen bitmap words, then tests the endpoint
+//          bits -- ~80 % of the edges have no transmitting endpoint and are dropped here;
+//       3. survivors are appended to a per-warp shared-memory queue (ballot + popc compaction) and popped
+//          32 at a time; the two record gathers of a batch are issued when it is popped and consumed when the
+//          NEXT batch is popped, so the gathers, the float32 chain and the Philox draw run on full warps and
+//          the gather latency overlaps the filtering of the following quads;
+//   * agent-partitioned form (edge_pass_partition_kernel): a rank walks, for every GLOBAL transmitter, the
+//     edges that end in one of its own agents (covasim_b200/partition.py).
+//
+// Per-agent inputs are the 16-byte agent records written by prepare_transmission (cvb_device.cuh:AgentRecord;
+// the per-layer factors are applied here), or, for the single-variant dense form, the reference's per-layer
+// {rel_trans, rel_sus} pairs.
 //
 // Randomness: one Philox4x32-10 call per LIVE edge (non-zero probability in either direction), keyed
 // (seed, P_EDGE, layer, day, edge index): words 0-1 give the p1->p2 uniform, words 2-3 the p2->p1 one.

@@ -180,7 +180,8 @@ int cvb_set_quar_horizon(cvb_sim* s, int32_t horizon);
 int cvb_set_nab_kin(cvb_sim* s, const double* host_kin, int64_t n);
 /* people.py:189-196 update_states_post (check_diagnosed, check_quar, check_enter_iso) */
 int cvb_update_states_post(cvb_sim* s, int32_t t, cvb_stream st);
-/* sim.py:602-643: viral load + per-layer {rel_trans, rel_sus} records for the fused edge pass */
+/* sim.py:602-643: viral load + transmissibility / susceptibility: one 16-byte record per agent for the edge pass (which applies the
+ * per-layer factors), plus the reference's per-layer {rel_trans, rel_sus} pairs for the layers the dense streaming pass reads */
 int cvb_prepare_transmission(cvb_sim* s, int32_t t, cvb_stream st);
 /* update_states_post and prepare_transmission as ONE pass over the agents (what Sim.step uses) */
 int cvb_post_and_prepare(cvb_sim* s, int32_t t, cvb_stream st);

@@ -1,5 +1,6 @@
 // Built-in interventions as device passes (native-RNG mode) and dynamic-layer regeneration:
 //   test_prob + People.test            reference interventions.py:857-981, people.py:589-617
+//   test_num                           reference interventions.py:718-854 (weights + exponential-clock keys; tests for a list)
 //   contact_tracing                    reference interventions.py:984-1145, base.py:1808-1846, utils.py:131-147
 //   vaccinate_prob + vaccinate         reference interventions.py:1257-1662, immunity.py:138-202
 //   Layer.update (frac = 1)            reference base.py:1849-1876

@@ -1,10 +1,11 @@
 // Per-agent state-transition kernels over the structure-of-arrays People state:
 //   update_states_pre  (+ check_immunity)      reference people.py:164-186, immunity.py:303-350
 //   update_states_post                          reference people.py:189-196, 315-366
-//   prepare_transmission (viral load + per-layer rel_trans / rel_sus records + infectious bitmap)   sim.py:602-643
+//   prepare_transmission (viral load + one 16-byte agent record per agent + transmit bitmap / list / codes)   sim.py:602-643
 //   update_nab + stock counts + population means                                 immunity.py:205-213, sim.py:652-674
 //
-// HBM-bound by design: every array a kernel needs is read at most once and written only where it changes.
+// Every array a kernel needs is read at most once and written only where it changes (ncu: DRAM traffic = algorithmic bytes);
+// what limits them today is latency, not HBM bandwidth (profiles/r1/README.md).
 // Each thread owns FOUR consecutive agents and loads every field it may need up front with 32-bit
 // (4 x bool) and 128-bit (4 x float32 / int32) coalesced loads, all independent, so ~20 loads per thread
 // are in flight at once (the first version chained conditional byte loads and was latency-bound at 5-16 %

@@ -158,6 +158,18 @@ __global__ void __launch_bounds__(kThreads) trace_select_kernel(PeoplePtrs P, in
     }
 }
 
+// an explicit case list (contact_tracing with a capacity: the host picked who is traced) -> case bitmap + case list
+__global__ void __launch_bounds__(kThreads) set_cases_kernel(const int32_t* __restrict__ inds, int64_t n_inds, int64_t n,
+        unsigned int* __restrict__ case_bits, int32_t* __restrict__ case_list, unsigned int* __restrict__ n_case_list) {
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_inds; j += (int64_t)gridDim.x * blockDim.x) {
+        const int i = inds[j];
+        if (i < 0 || i >= n) continue;
+        atomicOr(case_bits + (i >> 5), 1u << (i & 31));
+        case_list[j] = i;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_case_list = (unsigned int)n_inds;
+}
+
 struct TraceTable {                      // the traced layers of one contact_tracing intervention, by value
     const int32_t* p1[CVB_MAX_LAYERS];
     const int32_t* p2[CVB_MAX_LAYERS];
@@ -428,12 +440,8 @@ int cvb_test_list(cvb_sim* s, int32_t t, const int32_t* inds, int64_t n_inds, do
     return 0;
 }
 
-int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_stream st_) {
-    cudaStream_t st = (cudaStream_t)st_;
-    CVB_REQUIRE(s && tr && s->pars_set, "cvb_contact_tracing: handle not ready");
-    CVB_REQUIRE(!s->partitioned, "cvb_contact_tracing: agent-partitioned handles trace in two phases (cvb_trace_select_cases, all-gather, cvb_trace_notify_contacts)");
-    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_contact_tracing: day %d outside [0,%d)", t, s->npts);
-    if (trace_select(s, t, tr, st)) return 1;
+// notify the contacts of the current case set (bitmap + list) of a non-partitioned handle: phase two of contact tracing
+static int trace_notify_local(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cudaStream_t st) {
     const uint32_t adj_mask = (s->adj && s->adj_layer_mask) ? s->adj_layer_mask : 0u;
     const size_t bitmap_bytes = (size_t)((s->n + 31) / 32) * sizeof(unsigned int);
     const bool smem_bits = bitmap_bytes <= 200 * 1024;
@@ -463,6 +471,28 @@ int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_str
     }
     CVB_LAUNCH_CHECK();
     return 0;
+}
+
+int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_stream st_) {
+    cudaStream_t st = (cudaStream_t)st_;
+    CVB_REQUIRE(s && tr && s->pars_set, "cvb_contact_tracing: handle not ready");
+    CVB_REQUIRE(!s->partitioned, "cvb_contact_tracing: agent-partitioned handles trace in two phases (cvb_trace_select_cases, all-gather, cvb_trace_notify_contacts)");
+    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_contact_tracing: day %d outside [0,%d)", t, s->npts);
+    if (trace_select(s, t, tr, st)) return 1;
+    return trace_notify_local(s, t, tr, st);
+}
+
+int cvb_contact_tracing_list(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, const int32_t* case_inds, int64_t n_cases, cvb_stream st_) {
+    cudaStream_t st = (cudaStream_t)st_;
+    CVB_REQUIRE(s && tr && s->pars_set && (n_cases == 0 || case_inds), "cvb_contact_tracing_list: bad argument");
+    CVB_REQUIRE(!s->partitioned, "cvb_contact_tracing_list: not for agent-partitioned handles");
+    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_contact_tracing_list: day %d outside [0,%d)", t, s->npts);
+    CVB_REQUIRE(n_cases <= s->n, "cvb_contact_tracing_list: more cases than agents");
+    if (n_cases == 0) return 0;
+    CVB_CHECK(cudaMemsetAsync(s->case_bits, 0, (size_t)((s->n + 31) / 32) * sizeof(unsigned int), st));
+    set_cases_kernel<<<grid_for(n_cases), kThreads, 0, st>>>(case_inds, n_cases, s->n, s->case_bits, s->case_list, s->n_case_list);
+    CVB_LAUNCH_CHECK();
+    return trace_notify_local(s, t, tr, st);
 }
 
 int cvb_vaccinate_prob(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* vp, int32_t* iv_doses, int32_t* due_day, const double* prob_override,

@@ -425,13 +425,13 @@ class contact_tracing(Intervention):
     interventions.py:984-1145).  Device form: bitmap of today's cases, then one streaming pass over each
     traced layer's (p1, p2) that notifies the partner of every case with a Bernoulli(trace_prob) keyed
     per (layer, contact) -- the reference's binomial_filter over the unique contact set.
-    Not built: capacity.
+    With a ``capacity`` the cases are counted on the host every day (one synchronisation) and, when there are too many, the
+    traced ones are picked there.
     '''
 
     def __init__(self, trace_probs=None, trace_time=None, start_day=0, end_day=None, presumptive=False, quar_period=None, capacity=None, **kwargs):
         super().__init__(**kwargs)
-        if capacity is not None:
-            raise NotImplementedError('contact_tracing: capacity is outside the built path')
+        self.capacity = capacity
         self.trace_probs, self.trace_time = trace_probs, trace_time
         self.start_day, self.end_day, self.presumptive, self.quar_period = start_day, end_day, presumptive, quar_period
 
@@ -459,6 +459,29 @@ class contact_tracing(Intervention):
         t = sim.t
         if t < self.start_day or (self.end_day is not None and t > self.end_day):
             return
+        if self.capacity is not None:      # at most `capacity` of today's cases are traced, picked at random (interventions.py:1079-1083)
+            if sim._comm is not None:
+                raise NotImplementedError('contact_tracing(capacity=...) picks among all of today\'s cases and is not built for agent-partitioned runs')
+            P = sim.people
+            if not self.presumptive:
+                cases = torch.nonzero(P.date_diagnosed == t).flatten()
+            else:
+                just = torch.nonzero(P.date_tested == t).flatten()
+                cases = just[P.exposed[just]]
+            cap = int(self.capacity / sim.rescale_vec[t])
+            if len(cases) > cap:
+                if sim.rng_mode == 'mt':
+                    chosen = sim.rng.np_.choice(cases.cpu().numpy(), cap, replace=False)
+                    cases = torch.as_tensor(chosen, device=cases.device)
+                else:
+                    from . import utils as cvu
+                    pick = cvu.choose_distinct(sim.rng.np_, len(cases), cap)
+                    cases = cases[torch.as_tensor(pick, dtype=torch.int64, device=cases.device)]
+                if sim._adj_dirty:
+                    sim._build_adjacency()
+                cases = cases.to(torch.int32).contiguous()
+                sim._call('cvb_contact_tracing_list', sim._handle, t, C.byref(self._c), cases.data_ptr(), len(cases), sim._stream_ptr)
+                return
         if sim._comm is not None:          # agent-partitioned: local cases -> all-gathered bitmap -> local contacts of every case
             sim._call('cvb_trace_select_cases', sim._handle, t, C.byref(self._c), sim._stream_ptr)
             sim._exchange_cases()

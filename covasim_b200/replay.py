@@ -283,6 +283,10 @@ def contact_tracing_apply(iv, sim):
     else:
         just = torch.nonzero(P.date_tested == t).flatten()
         cases = just[P.exposed[just]]
+    if iv.capacity is not None:                        # interventions.py:1079-1083: np.random.choice on the NumPy stream
+        cap = int(iv.capacity / sim.rescale_vec[t])
+        if len(cases) > cap:
+            cases = torch.as_tensor(sim.rng.np_.choice(cases.cpu().numpy(), cap, replace=False), device=cases.device)
     if not len(cases):
         return
     by_time = {}

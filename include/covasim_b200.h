@@ -235,6 +235,9 @@ typedef struct cvb_trace_pars {            /* interventions.py:984-1145 */
 /* Marks contacts of today's cases, sets known_contact/date_known_contact and queues quarantine.
  * Requests with trace_time 0 go to pend_quar_end; later ones to the per-day ring. */
 int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* host_pars, cvb_stream st);
+/* The same for an explicit list of distinct cases (int32[n_cases]) chosen by the caller: contact_tracing with a `capacity`
+ * (interventions.py:1079-1083 picks `capacity` of today's cases at random) */
+int cvb_contact_tracing_list(cvb_sim* s, int32_t t, const cvb_trace_pars* host_pars, const int32_t* case_inds, int64_t n_cases, cvb_stream st);
 /* The same in two phases for agent-partitioned handles: select today's local cases into case_bits_local; (the host
  * all-gathers the bitmap); notify the LOCAL contacts of every GLOBAL case */
 int cvb_trace_select_cases(cvb_sim* s, int32_t t, const cvb_trace_pars* host_pars, cvb_stream st);

@@ -1011,7 +1011,8 @@ class test_prob(Intervention):
 
 class contact_tracing(Intervention):
     ''' Trace contacts of newly diagnosed agents and schedule quarantine (reference interventions.py:984-1145) '''
-    def __init__(self, trace_probs=None, trace_time=None, start_day=0, end_day=None, presumptive=False, quar_period=None):
+    def __init__(self, trace_probs=None, trace_time=None, start_day=0, end_day=None, presumptive=False, quar_period=None, capacity=None):
+        self.capacity = capacity
         self.trace_probs, self.trace_time = trace_probs, trace_time
         self.start_day, self.end_day, self.presumptive, self.quar_period = start_day, end_day, presumptive, quar_period
 
@@ -1036,6 +1037,10 @@ class contact_tracing(Intervention):
         else:
             just = np.nonzero(P['date_tested'] == t)[0]
             cases = just[P['exposed'][just]]
+        if self.capacity is not None:                           # interventions.py:1079-1083: at most `capacity` cases, picked at random
+            cap = int(self.capacity / sim.rescale_vec[t])
+            if len(cases) > cap:
+                cases = sim.rng.np_.choice(cases, cap, replace=False) if sim.rng.kind == 'mt' else cases[sim.rng.choose('np_', len(cases), cap)]
         if not len(cases):
             return
         by_time = {}

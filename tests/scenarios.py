@@ -93,6 +93,12 @@ SCENARIOS = {
         interventions=[('test_prob', dict(start_day=3, symp_prob=0.3, asymp_prob=0.005, symp_quar_prob=0.8, asymp_quar_prob=0.2, ili_prev=0.02)),
                        ('contact_tracing', dict(trace_probs=0.5, start_day=5))],
     ),
+    # tracing capacity: at most 6 of the day's cases are traced
+    'capacity3k': dict(
+        pars=dict(pop_size=3000, pop_infected=80, pop_type='hybrid', n_days=30, verbose=0, rand_seed=111, beta=0.03),
+        interventions=[('test_prob', dict(start_day=3, symp_prob=0.5, asymp_prob=0.05)),
+                       ('contact_tracing', dict(trace_probs=0.6, trace_time=dict(h=0, s=1, w=1, c=2), start_day=4, capacity=6))],
+    ),
     # dynamic layer (BASELINE.json config 5 member shape, scaled down)
     'dynamic2k': dict(pars=dict(pop_size=2000, pop_infected=40, n_days=30, verbose=0, rand_seed=8, beta=0.02,
                                 dynam_layer=dict(a=1)), interventions=[]),

@@ -19,7 +19,7 @@ def cv():
     return covasim_b200
 
 
-@pytest.mark.parametrize('name', ['random2k_nowaning', 'dynamic2k', 'hybrid3k', 'variants4k', 'dynpars3k', 'clip3k', 'rescale3k', 'fracsus2k', 'sequence3k', 'testnum3k', 'testnum_rescale2k', 'subtarget3k', 'ili3k'])
+@pytest.mark.parametrize('name', ['random2k_nowaning', 'dynamic2k', 'hybrid3k', 'variants4k', 'dynpars3k', 'clip3k', 'rescale3k', 'fracsus2k', 'sequence3k', 'testnum3k', 'testnum_rescale2k', 'subtarget3k', 'ili3k', 'capacity3k'])
 def test_lockstep_parity(cv, name):
     sim, orc = parity.build_pair(cv, name)
     parity.run_lockstep(sim, orc)

@@ -26,9 +26,49 @@ from . import _capi
 from .base import Result, AlreadyRunError
 from .people import People
 
-__all__ = ['Sim']
+__all__ = ['Sim', 'r_eff_windowed', 'gen_time']
 
 f32 = np.float32
+
+
+def r_eff_windowed(method, date_infectious, date_recovered, date_dead, log_source, npts, window=7):
+    '''
+    The 'infectious' / 'outcome' r_eff of the reference (sim.py:949-981) as a function of plain arrays: every source is dated
+    by the day it became infectious (or recovered / died); r_eff[t] = infections caused by the sources of the last ``window``
+    days / number of those sources.
+    '''
+    window = int(window)
+    n = len(date_infectious)
+    source_date = np.full(n, -1, dtype=np.int64)
+    dates = [date_infectious] if method == 'infectious' else [date_recovered, date_dead]
+    for d in dates:                                      # t == date for an integer day t inside the run
+        d = np.asarray(d, dtype=np.float64)
+        ok = np.isfinite(d) & (d >= 0) & (d < npts) & (d == np.floor(d))
+        source_date[ok] = d[ok].astype(np.int64)
+    sources = np.bincount(source_date[source_date >= 0], minlength=npts).astype(np.float64)
+    src = np.asarray(log_source)
+    src = src[src >= 0]                                  # seed infections and importations have no source
+    sd = source_date[src]
+    targets = np.bincount(sd[sd >= 0], minlength=npts).astype(np.float64)
+    r_eff = np.divide(targets, sources, out=np.full(npts, np.nan), where=sources > 0)
+    num = np.nancumsum(r_eff * sources)
+    num[window:] = num[window:] - num[:-window]
+    den = np.cumsum(sources)
+    den[window:] = den[window:] - den[:-window]
+    return np.divide(num, den, out=np.full(npts, np.nan), where=den > 0)
+
+
+def gen_time(date_exposed, date_symptomatic, log_source, log_target):
+    ''' Generation-time statistics from the infection log (reference sim.py:990-1025) as a function of plain arrays '''
+    src, tgt = np.asarray(log_source), np.asarray(log_target)
+    has = src >= 0
+    src, tgt = src[has], tgt[has]
+    de, ds = np.asarray(date_exposed, dtype=np.float64), np.asarray(date_symptomatic, dtype=np.float64)
+    true = de[tgt] - de[src]
+    both = np.isfinite(ds[src]) & np.isfinite(ds[tgt])
+    clin = ds[tgt][both] - ds[src][both]
+    with np.errstate(all='ignore'):
+        return {'true': np.mean(true), 'true_std': np.std(true), 'clinical': np.mean(clin), 'clinical_std': np.std(clin)}
 
 
 class Sim:
@@ -898,9 +938,22 @@ class Sim:
         return out
 
     def compute_r_eff(self, method='daily', smoothing=2, window=7):
-        ''' Effective reproduction number, 'daily' method (reference sim.py:888-946) '''
+        '''
+        Effective reproduction number (reference sim.py:888-987): 'daily' from daily infections, 'infectious' / 'outcome' by
+        counting, through the infection log, how many people each person infected, dated by when the source became infectious
+        / recovered or died, over a sliding window.
+        '''
+        if method in ('infectious', 'outcome'):
+            P = self.people
+            if self._comm is not None:
+                raise NotImplementedError("r_eff methods 'infectious' / 'outcome' need every agent's dates on one rank and are not built for agent-partitioned runs")
+            log = self.infection_log
+            values = r_eff_windowed(method, P.to_numpy('date_infectious'), P.to_numpy('date_recovered'), P.to_numpy('date_dead'),
+                                    log['source'], self.npts, window)
+            self.results['r_eff'].values[:] = values
+            return self.results['r_eff'].values
         if method != 'daily':
-            raise NotImplementedError("only the default r_eff method 'daily' is built")
+            raise ValueError(f'Method must be "daily", "infectious", or "outcome", not "{method}"')
         P = self.people
         d_rec, d_dead, d_inf = P.to_numpy('date_recovered'), P.to_numpy('date_dead'), P.to_numpy('date_infectious')
         rec = np.nonzero(~np.isnan(d_rec))[0]
@@ -931,6 +984,14 @@ class Sim:
             raw = sm
         R['r_eff'].values[:] = raw
         return raw
+
+    def compute_gen_time(self):
+        ''' Generation time: exposure to exposure ('true') and symptom onset to symptom onset ('clinical') (reference sim.py:990-1025) '''
+        if self._comm is not None:
+            raise NotImplementedError('compute_gen_time needs every agent\'s dates on one rank and is not built for agent-partitioned runs')
+        log, P = self.infection_log, self.people
+        self.results['gen_time'] = gen_time(P.to_numpy('date_exposed'), P.to_numpy('date_symptomatic'), log['source'], log['target'])
+        return self.results['gen_time']
 
     def compute_summary(self, t=None):
         ''' reference sim.py:1040-1072 '''

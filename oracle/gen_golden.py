@@ -170,6 +170,15 @@ def run_scenario(name, spec):
 
     for k in sim.result_keys():
         out[f'results/{k}'] = np.array(sim.results[k].values)
+    # the other r_eff methods and the generation time (post-processing of the dates and the infection log, sim.py:888-1025)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for method in ('infectious', 'outcome'):
+            out[f'r_eff/{method}'] = np.array(sim.compute_r_eff(method=method))
+        gt = sim.compute_gen_time()
+        out['gen_time'] = np.array([gt['true'], gt['true_std'], gt['clinical'], gt['clinical_std']], dtype=np.float64)
+        sim.compute_r_eff()                                    # back to the default
     for k in sim.result_keys('variant'):
         out[f'vresults/{k}'] = np.array(sim.results['variant'][k].values)
     for k in cvo.cvd.all_states:

@@ -179,6 +179,29 @@ def run_scenario(name, spec):
         gt = sim.compute_gen_time()
         out['gen_time'] = np.array([gt['true'], gt['true_std'], gt['clinical'], gt['clinical_std']], dtype=np.float64)
         sim.compute_r_eff()                                    # back to the default
+    # goodness of fit against a synthetic data set (analysis.py:991-1222 Fit): the data and the reference's answers
+    import datetime as _dt
+    import pandas as pd
+    days = np.arange(3, sim.npts - 2)
+    fit_data = {'cum_diagnoses': 0.8 * sim.results['cum_diagnoses'].values[days] + 3 * np.sin(days),
+                'cum_deaths': sim.results['cum_deaths'].values[days] + 1.0,
+                'cum_tests': 1.1 * sim.results['cum_tests'].values[days],
+                'new_infections': sim.results['new_infections'].values[days] * 0.9 + 2}
+    fit_data['cum_diagnoses'][[4, 9]] = np.nan               # missing observations are skipped
+    start = sim['start_day']
+    df = pd.DataFrame(fit_data, index=[start + _dt.timedelta(days=int(d)) for d in days])
+    sim.data = df
+    fit = cv.Fit(sim)
+    out['fit/days'] = days
+    for k, v in fit_data.items():
+        out[f'fit/data/{k}'] = v
+    out['fit/mismatch'] = np.float64(fit.mismatch)
+    out['fit/keys'] = np.array(json.dumps(list(fit.keys)))
+    for k in fit.keys:
+        out[f'fit/gofs/{k}'] = np.array(fit.gofs[k])
+        out[f'fit/losses/{k}'] = np.array(fit.losses[k])
+    fit2 = cv.Fit(sim, keys=['cum_diagnoses', 'new_infections'], weights=dict(new_infections=2.5), use_squared=True, as_scalar='mean')
+    out['fit/mismatch_custom'] = np.float64(fit2.mismatch)
     for k in sim.result_keys('variant'):
         out[f'vresults/{k}'] = np.array(sim.results['variant'][k].values)
     for k in cvo.cvd.all_states:

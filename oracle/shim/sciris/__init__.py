@@ -33,6 +33,8 @@ class odict(_co.OrderedDict):
     def __getitem__(self, key):
         if isinstance(key, (int, np.integer)) and not _co.OrderedDict.__contains__(self, key):
             return list(self.values())[key]
+        if isinstance(key, slice):                     # sciris: a slice returns the values as an array
+            return np.array(list(self.values())[key])
         return _co.OrderedDict.__getitem__(self, key)
     def __setitem__(self, key, value):
         if isinstance(key, (int, np.integer)) and not _co.OrderedDict.__contains__(self, key) and len(self) > key >= 0:

@@ -25,3 +25,51 @@ def test_r_eff_methods_and_gen_time(name, golden):
     gt = gen_time(g['people/date_exposed'], g['people/date_symptomatic'], g['log/source'], g['log/target'])
     np.testing.assert_allclose([gt['true'], gt['true_std'], gt['clinical'], gt['clinical_std']], g['gen_time'], rtol=1e-12)
     assert np.isnan(gt['true']) or 2 < gt['true'] < 15          # NaN when sources were made naive again (rescaling), as in the reference
+
+
+# ---- goodness of fit (reference analysis.py:991-1222 Fit, misc.py:707-795 compute_gof) ---------------------------------------------
+FIT_SCENARIOS = ['hybrid3k', 'variants4k', 'rescale3k', 'testnum3k']
+
+
+def _fit_inputs(g):
+    import json
+    results = {k[len('results/'):]: g[k] for k in g.files if k.startswith('results/')}
+    data = {k[len('fit/data/'):]: g[k] for k in g.files if k.startswith('fit/data/')}
+    data['day'] = g['fit/days']
+    return results, data, json.loads(str(g['fit/keys']))
+
+
+@pytest.mark.parametrize('name', FIT_SCENARIOS)
+def test_fit_matches_reference(name, golden):
+    ''' Same result series, same (synthetic, partly missing) data -> the reference's keys, gofs, losses and mismatch '''
+    from covasim_b200 import analysis as cva
+    g = golden(name)
+    results, data, ref_keys = _fit_inputs(g)
+    npts = len(results['cum_infections'])
+    fit = cva.Fit(data=data, results=results, npts=npts)
+    assert fit.keys == ref_keys
+    for k in ref_keys:
+        np.testing.assert_allclose(fit.gofs[k], g[f'fit/gofs/{k}'], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(fit.losses[k], g[f'fit/losses/{k}'], rtol=1e-12, atol=0)
+    assert fit.mismatch == pytest.approx(float(g['fit/mismatch']), rel=1e-12)
+    fit2 = cva.Fit(data=data, results=results, npts=npts, keys=['cum_diagnoses', 'new_infections'], weights=dict(new_infections=2.5),
+                   use_squared=True, as_scalar='mean')
+    assert fit2.mismatch == pytest.approx(float(g['fit/mismatch_custom']), rel=1e-12)
+    # dates instead of day numbers, and the ensemble form
+    import datetime as dt
+    dated = {k: v for k, v in data.items() if k != 'day'}
+    dated['date'] = [(dt.date(2020, 3, 1) + dt.timedelta(days=int(d))).strftime('%Y-%m-%d') for d in data['day']]
+    assert cva.Fit(data=dated, results=results, npts=npts, start_date=dt.date(2020, 3, 1)).mismatch == pytest.approx(fit.mismatch, rel=1e-14)
+    worse = {k: (v * 1.5 if k.startswith('cum_') else v) for k, v in results.items()}
+    mm = cva.fit_members([results, worse], data, npts)
+    assert mm[0] == pytest.approx(fit.mismatch, rel=1e-14) and mm[1] > mm[0]
+
+
+def test_compute_gof_options():
+    from covasim_b200.analysis import compute_gof
+    a, p = np.array([1.0, 2.0, 4.0]), np.array([1.5, 2.0, 3.0])
+    np.testing.assert_allclose(compute_gof(a, p), np.abs(a - p) / 4.0)
+    np.testing.assert_allclose(compute_gof(a, p, normalize=False), np.abs(a - p))
+    np.testing.assert_allclose(compute_gof(a, p, use_frac=True), np.abs(a - p) / (np.maximum(a, p) + 1e-9))
+    assert compute_gof(a, p, normalize=False, use_squared=True, as_scalar='sum') == pytest.approx(0.25 + 1.0)
+    assert compute_gof(a, p, estimator=lambda x, y: float(np.max(np.abs(x - y)))) == 1.0

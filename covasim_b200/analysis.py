@@ -10,7 +10,139 @@ import datetime as dt
 
 import numpy as np
 
-__all__ = ['compute_gof', 'Fit', 'fit_members']
+__all__ = ['Analyzer', 'snapshot', 'age_histogram', 'compute_gof', 'Fit', 'fit_members']
+
+
+class Analyzer:
+    '''
+    Base class of analyzers (reference analysis.py:23-129): objects called once per day at the END of ``Sim.step`` (after the
+    day's transmission and counts, reference sim.py:677-678) with full access to the sim; ``sim.people.<field>`` are device
+    tensors.  Plain callables are accepted as analyzers too.
+    '''
+
+    def __init__(self, label=None):
+        self.label = label if label is not None else self.__class__.__name__
+        self.initialized = False
+        self.finalized = False
+
+    def __call__(self, *args, **kwargs):
+        if not self.initialized:
+            raise RuntimeError(f'Analyzer (label={self.label}, {type(self)}) has not been initialized')
+        return self.apply(*args, **kwargs)
+
+    def initialize(self, sim=None):
+        self.initialized = True
+        self.finalized = False
+
+    def finalize(self, sim=None):
+        if self.finalized:
+            raise RuntimeError('Analyzer already finalized')
+        self.finalized = True
+
+    def apply(self, sim):
+        raise NotImplementedError
+
+    def shrink(self, in_place=False):
+        import copy
+        return self if in_place else copy.deepcopy(self)
+
+
+def _process_days(sim, days):
+    days = [days] if isinstance(days, (str, int, np.integer, dt.date)) else list(days)
+    days = sorted(sim.day(d) for d in days)
+    return days, [sim.date(d) for d in days]
+
+
+class snapshot(Analyzer):
+    '''
+    Host copies of every People array on the given days (reference analysis.py:149-223): ``snap.snapshots[date]`` /
+    ``snap.get(day)`` is a dict of NumPy arrays (the reference deep-copies the People object; here the device arrays are read
+    back once per requested day).
+    '''
+
+    def __init__(self, days, *args, die=True, **kwargs):
+        super().__init__(**kwargs)
+        days = [days] if isinstance(days, (str, int, np.integer, dt.date)) else list(days)
+        self.days = days + list(args)
+        self.die = die
+        self.dates = None
+        self.snapshots = {}
+
+    def initialize(self, sim):
+        self.days, self.dates = _process_days(sim, self.days)
+        if self.days[-1] > sim.npts - 1:
+            raise ValueError(f'Cannot create snapshot for {self.dates[-1]} (day {self.days[-1]}) because the simulation ends on day {sim.npts - 1}')
+        self._sim_day, self._sim_date = sim.day, sim.date
+        self.initialized = True
+
+    def apply(self, sim):
+        for ind, day in enumerate(self.days):
+            if day == sim.t:
+                self.snapshots[self.dates[ind]] = {k: sim.people.to_numpy(k) for k in sim.people.keys()}
+
+    def finalize(self, sim=None):
+        super().finalize()
+        missing = [d for d in self.dates if d not in self.snapshots]
+        if missing and self.die:
+            raise RuntimeError(f'The dates {missing} were requested but not recorded')
+
+    def get(self, key=None):
+        date = self._sim_date(self._sim_day(self.days[0] if key is None else key))
+        if date not in self.snapshots:
+            raise KeyError(f'Could not find snapshot date {date}: choices are {", ".join(self.snapshots.keys())}')
+        return self.snapshots[date]
+
+
+class age_histogram(Analyzer):
+    '''
+    Age distribution of the agents who have ever been in the given states, on the given days (reference analysis.py:226-425,
+    the plotting and data-comparison parts left out): ``hist.hists[date][state]`` counts, per age bin, the agents whose
+    ``date_<state>`` is set, times the day's rescaling factor.  Counted on the device.
+    '''
+
+    def __init__(self, days=None, states=None, edges=None, die=True, **kwargs):
+        super().__init__(**kwargs)
+        self.days, self.states, self.edges, self.die = days, states, edges, die
+        self.hists = {}
+
+    def initialize(self, sim):
+        super().initialize()
+        self.days, self.dates = _process_days(sim, sim.npts - 1 if self.days is None else self.days)
+        if self.days[-1] > sim.npts - 1:
+            raise ValueError(f'Cannot create histogram for day {self.days[-1]} because the simulation ends on day {sim.npts - 1}')
+        self.edges = np.linspace(0, 100, 11) if self.edges is None else np.asarray(self.edges, dtype=float)
+        self.bins = self.edges[:-1]
+        states = ['exposed', 'severe', 'dead', 'tested', 'diagnosed'] if self.states is None else ([self.states] if isinstance(self.states, str) else list(self.states))
+        self.states = [s.replace('date_', '') for s in states]
+
+    def apply(self, sim):
+        import torch
+        for ind, day in enumerate(self.days):
+            if day != sim.t:
+                continue
+            age = sim.people.age
+            edges = torch.as_tensor(self.edges, dtype=age.dtype, device=age.device)
+            nb = len(self.edges) - 1
+            hist = dict(bins=self.bins)
+            for state in self.states:
+                who = ~torch.isnan(sim.people[f'date_{state}'])
+                a = age[who]
+                # np.histogram: [e_i, e_i+1) except the last bin, which also holds its right edge
+                b = torch.bucketize(a, edges, right=True) - 1
+                b = torch.where(a == edges[-1], torch.full_like(b, nb - 1), b)
+                b = b[(b >= 0) & (b < nb)]
+                hist[state] = torch.bincount(b, minlength=nb).cpu().numpy() * sim.rescale_vec[sim.t]
+            self.hists[self.dates[ind]] = hist
+
+    def finalize(self, sim=None):
+        super().finalize()
+        missing = [d for d in self.dates if d not in self.hists]
+        if missing and self.die:
+            raise RuntimeError(f'The dates {missing} were requested but not recorded')
+
+    def get(self, key=None):
+        date = self.dates[0] if key is None else (key if key in self.hists else self.dates[self.days.index(int(key))])
+        return self.hists[date]
 
 
 def compute_gof(actual, predicted, normalize=True, use_frac=False, use_squared=False, as_scalar='none', eps=1e-9, estimator=None, **kwargs):

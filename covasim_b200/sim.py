@@ -230,6 +230,19 @@ class Sim:
             return ivs[which]
         return [i for i in ivs if (isinstance(which, type) and isinstance(i, which)) or getattr(i, 'label', None) == which]
 
+    def get_analyzers(self, which=None):
+        ''' The analyzers, or those of a given class / label / position (reference base.py:783-880 get_analyzers) '''
+        ans = self.pars['analyzers']
+        if which is None:
+            return list(ans)
+        if isinstance(which, int):
+            return ans[which]
+        return [a for a in ans if (isinstance(which, type) and isinstance(a, which)) or getattr(a, 'label', None) == which]
+
+    def get_analyzer(self, which=None):
+        found = self.get_analyzers(which)
+        return found if not isinstance(found, list) else (found[-1] if found else None)
+
     def copy(self):
         ''' Deep copy of an un-initialised or host-only sim (device state is rebuilt by initialize) '''
         if self.initialized:

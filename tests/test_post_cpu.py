@@ -73,3 +73,68 @@ def test_compute_gof_options():
     np.testing.assert_allclose(compute_gof(a, p, use_frac=True), np.abs(a - p) / (np.maximum(a, p) + 1e-9))
     assert compute_gof(a, p, normalize=False, use_squared=True, as_scalar='sum') == pytest.approx(0.25 + 1.0)
     assert compute_gof(a, p, estimator=lambda x, y: float(np.max(np.abs(x - y)))) == 1.0
+
+
+# ---- analyzers (reference analysis.py:23-425) on a stand-in sim with CPU tensors ------------------------------------------------------
+class _FakePeople:
+    def __init__(self, arrays):
+        self._a = arrays
+
+    def __getattr__(self, k):
+        return self._a[k]
+
+    def __getitem__(self, k):
+        return self._a[k]
+
+    def keys(self):
+        return list(self._a.keys())
+
+    def to_numpy(self, k):
+        return self._a[k].numpy()
+
+
+class _FakeSim:
+    def __init__(self, n=5000, npts=20, seed=0):
+        import torch
+        rng = np.random.RandomState(seed)
+        nan = np.where(rng.random_sample(n) < 0.6, np.nan, rng.randint(0, npts, n)).astype(np.float32)
+        self.people = _FakePeople(dict(age=torch.as_tensor((rng.random_sample(n) * 100).astype(np.float32)),
+                                       date_exposed=torch.as_tensor(nan), date_dead=torch.as_tensor(np.where(rng.random_sample(n) < 0.97, np.nan, 5).astype(np.float32)),
+                                       exposed=torch.as_tensor(rng.random_sample(n) < 0.1)))
+        self.npts, self.t = npts, 0
+        self.rescale_vec = np.linspace(1, 2, npts)
+
+    def day(self, d):
+        return int(d)
+
+    def date(self, d):
+        return f'day{int(d):03d}'
+
+
+def test_analyzers_on_a_stand_in_sim():
+    import covasim_b200 as cv
+    sim = _FakeSim()
+    snap = cv.snapshot(3, 7)
+    hist = cv.age_histogram(days=[7, 19], states=['exposed', 'date_dead'])
+    with pytest.raises(RuntimeError):
+        snap(sim)                                              # not initialised yet
+    for an in (snap, hist):
+        an.initialize(sim)
+    for t in range(sim.npts):
+        sim.t = t
+        if t == 5:
+            sim.people._a['exposed'] = ~sim.people._a['exposed']      # the snapshots must be copies of the day's state
+        for an in (snap, hist):
+            an(sim)
+    for an in (snap, hist):
+        an.finalize(sim)
+    assert list(snap.snapshots.keys()) == ['day003', 'day007']
+    assert not np.array_equal(snap.get(3)['exposed'], snap.get(7)['exposed'])
+    age = sim.people.age.numpy()
+    for date, t in (('day007', 7), ('day019', 19)):
+        for state in ('exposed', 'dead'):
+            want = np.histogram(age[~np.isnan(sim.people[f'date_{state}'].numpy())], bins=np.linspace(0, 100, 11))[0] * sim.rescale_vec[t]
+            np.testing.assert_allclose(hist.hists[date][state], want)
+    with pytest.raises(RuntimeError):
+        snap.finalize(sim)                                     # finalising twice is an error, as in the reference
+    assert isinstance(snap, cv.Analyzer) and snap.label == 'snapshot'

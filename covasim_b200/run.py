@@ -226,10 +226,11 @@ class MultiSim:
             r = Result(k, npts=stack.shape[0])
             r.values[:] = stack.mean(axis=-1) if k in cvd.unscaled_results else stack.sum(axis=-1)
             out[k] = r
-        for k in self.member_results[0]['variant'].keys():
-            stack = np.stack([m['variant'][k] for m in self.member_results], axis=-1)
-            r = Result(k, npts=stack.shape[1], n_variants=stack.shape[0])
-            r.values[:] = stack.mean(axis=-1) if k in ('prevalence_by_variant', 'incidence_by_variant') else stack.sum(axis=-1)
+        # the reference combines the main result series only (run.py:353-358 loops over result_keys()): the by-variant series of
+        # the combined sim stay those of the first member
+        for k, vals in self.member_results[0]['variant'].items():
+            r = Result(k, npts=vals.shape[1], n_variants=vals.shape[0])
+            r.values[:] = vals
             out['variant'][k] = r
         self.results = out
         self.which = 'combined'

@@ -92,3 +92,38 @@ def test_pack_unpack_roundtrip_and_reduce():
     ms.combine()
     assert np.allclose(ms.results['cum_infections'].values, back['cum_infections'] * 3.3)
     assert np.allclose(ms.results['prevalence'].values, back['prevalence'] * 1.1)
+
+
+# ---- reductions against the reference's MultiSim (run.py:220-374), from golden member results ------------------------------------------
+def _members_from_golden(g):
+    keys, vkeys = [str(k) for k in g['keys']], [str(k) for k in g['vkeys']]
+    members = []
+    for i in range(4):
+        m = {k: g[f'member{i}/{k}'] for k in keys}
+        m['variant'] = {k: g[f'member{i}/variant/{k}'] for k in vkeys}
+        members.append(m)
+    return keys, vkeys, members
+
+
+def test_reduce_mean_combine_match_reference(golden):
+    ''' Same member result series -> the reference's reduce() (median + 10/90 % band), mean() (+- 2 std), custom quantiles and combine() '''
+    from covasim_b200 import run as cvrun
+    g = golden('multisim_ref')
+    keys, vkeys, members = _members_from_golden(g)
+    msim = cvrun.MultiSim(base_sim=object(), n_runs=4)
+    msim.member_results = members
+    for name, call in (('median', lambda m: m.reduce()), ('mean', lambda m: m.mean()), ('quant', lambda m: m.reduce(quantiles=dict(low=0.25, high=0.75)))):
+        call(msim)
+        for k in keys:
+            r = msim.results[k]
+            for part, got in (('values', r.values), ('low', r.low), ('high', r.high)):
+                np.testing.assert_allclose(got, g[f'{name}/{k}/{part}'], rtol=1e-12, atol=1e-12, equal_nan=True, err_msg=f'{name} {k} {part}')
+        for k in vkeys:
+            r = msim.results['variant'][k]
+            for part, got in (('values', r.values), ('low', r.low), ('high', r.high)):
+                np.testing.assert_allclose(got, g[f'{name}/variant/{k}/{part}'], rtol=1e-12, atol=1e-12, equal_nan=True, err_msg=f'{name} variant/{k} {part}')
+    msim.combine()
+    for k in keys:
+        np.testing.assert_allclose(msim.results[k].values, g[f'combine/{k}'], rtol=1e-12, atol=1e-12, equal_nan=True, err_msg=f'combine {k}')
+    for k in vkeys:
+        np.testing.assert_allclose(msim.results['variant'][k].values, g[f'combine/variant/{k}'], rtol=1e-12, atol=1e-12, equal_nan=True, err_msg=f'combine variant/{k}')

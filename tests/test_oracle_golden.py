@@ -119,3 +119,16 @@ def test_known_answers():
     sim = cvo.OracleSim(pop_size=400, pop_infected=400, n_days=120, rand_seed=4, use_waning=False, rel_symp_prob=big,
                         rel_severe_prob=big, rel_crit_prob=big, rel_death_prob=big).run()
     assert sim.summary['cum_deaths'] == 400
+
+
+@pytest.mark.parametrize('name', ['hybrid3k', 'default20k', 'dynamic2k', 'baseline20k'])
+def test_initial_population_matches_reference(name, golden):
+    ''' Ages, initial transmissibility and every layer's edge list (order included) as the reference built them (population.py:143-364) '''
+    g = golden(name)
+    sim = cvo.OracleSim(**scenarios.build(cvo, scenarios.SCENARIOS[name]), rng='mt')
+    sim.initialize()
+    assert np.array_equal(sim.P['age'], g['pop/age'].astype(sim.P['age'].dtype))
+    assert np.array_equal(sim.P['rel_trans'], g['init/rel_trans'])
+    for lk, layer in sim.contacts.items():
+        assert len(layer['p1']) == int(g[f'contacts_len/{lk}'])
+        assert digest(layer['p1']) + digest(layer['p2']) == str(g[f'contacts_digest/{lk}']), lk

@@ -145,3 +145,39 @@ def test_localcomm_threads():
             assert np.array_equal(g, np.repeat([10 * day, 10 * day + 1, 10 * day + 2], 32))
         assert np.array_equal(t, [6.0, 6.0])
         assert objs == [('rank', 0), ('rank', 1), ('rank', 2)]
+
+
+# ---- properties over many shapes (hypothesis): ragged sizes, empty layers, self-loops, any world size ---------------------------------
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=60, deadline=None)
+@given(n=st.integers(33, 3000), world=st.integers(1, 8), sizes=st.lists(st.integers(0, 400), min_size=1, max_size=4), seed=st.integers(0, 10**6))
+def test_partition_properties(n, world, sizes, seed):
+    from covasim_b200 import partition as cvpart
+    try:
+        chunk, ranges = cvpart.plan(n, world)
+    except ValueError:
+        assert (world - 1) * (-(-(-(-n // world)) // 32) * 32) >= n          # only when the last rank would own nobody
+        return
+    assert chunk % 32 == 0 and ranges[0][0] == 0 and ranges[-1][1] == n
+    assert all(a[1] == b[0] for a, b in zip(ranges[:-1], ranges[1:])) and all(hi - lo == chunk for lo, hi in ranges[:-1])
+    rng = np.random.RandomState(seed)
+    layers = random_layers(rng, n, sizes)
+    ids = list(range(len(sizes)))
+    seen = 0
+    for lo, hi in ranges:
+        ptr, adj, M = cvpart.build_partition_adjacency(layers, ids, lo, hi, world * chunk, 'cpu')
+        ptr, adj = ptr.numpy(), adj.numpy()[:M]
+        assert ptr[0] == 0 and ptr[-1] == M and np.all(np.diff(ptr) >= 0)
+        assert np.all((adj[:, 0] >= 0) & (adj[:, 0] < hi - lo))               # targets are local
+        src = np.repeat(np.arange(world * chunk), np.diff(ptr))
+        for l, layer in zip(ids, layers):                                      # every entry is a real edge, seen from the right side
+            mine = (adj[:, 2] >> 1) == l
+            e, d = adj[mine, 1], adj[mine, 2] & 1
+            p_src = np.where(d == 0, layer['p1'][e], layer['p2'][e])
+            p_tgt = np.where(d == 0, layer['p2'][e], layer['p1'][e])
+            assert np.array_equal(p_src, src[mine]) and np.array_equal(p_tgt - lo, adj[mine, 0])
+            assert np.array_equal(adj[mine, 3].view(np.float32), layer['beta'][e])
+        seen += M
+    assert seen == 2 * sum(sizes)                                              # each directed edge on exactly one rank

@@ -89,3 +89,19 @@ def test_poisson_cdf():
         k = np.arange(len(cdf))
         pmf = np.diff(np.concatenate([[0], cdf]))
         assert abs((k * pmf).sum() - lam) < 1e-9
+
+
+def test_choose_distinct_properties():
+    ''' The O(k) sampler of native-RNG mode: k distinct values in range, deterministic given the stream, same function in the oracle '''
+    from covasim_b200 import utils as cvu
+    for n, k in [(10, 0), (10, 1), (1000, 7), (1000, 124), (1000, 126), (50, 50), (2_000_000, 5000)]:
+        a = cvu.choose_distinct(np.random.RandomState(3), n, k)
+        b = cvo.choose_distinct(np.random.RandomState(3), n, k)
+        assert len(a) == k and len(np.unique(a)) == k and (k == 0 or (a.min() >= 0 and a.max() < n))
+        assert np.array_equal(a, b)
+    # uniform: every value about equally likely
+    counts = np.zeros(200)
+    rs = np.random.RandomState(0)
+    for _ in range(4000):
+        counts[cvu.choose_distinct(rs, 200, 10)] += 1
+    assert abs(counts.mean() - 200) < 1e-9 and counts.std() < 3 * np.sqrt(200 * 0.95)

@@ -92,3 +92,20 @@ def test_population_generator_matches_oracle(cv):
     assert np.array_equal(key(f['contacts']['h']), key(e['contacts']['h']))     # same households, edges in another order
     for lk in ('s', 'w', 'c'):                                                   # later layers: the streams have diverged, same statistics
         assert abs(len(f['contacts'][lk]['p1']) / len(e['contacts'][lk]['p1']) - 1) < 0.05
+
+
+def test_binding_arity_matches_header(cv):
+    ''' Every ctypes prototype has as many arguments as the C declaration (a mismatch would corrupt the call silently) '''
+    text = open(os.path.join(ROOT, 'include', 'covasim_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    decls = dict(re.findall(r'\b(cvb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', text))
+    bad = {}
+    for name, argtypes in cv._capi.PROTOTYPES.items():
+        args = decls[name].strip()
+        n = 0 if args in ('', 'void') else len(args.split(','))
+        if n != len(argtypes):
+            bad[name] = (n, len(argtypes))
+    assert not bad, f'(header, ctypes) argument counts differ: {bad}'
+    # the by-value structs added after the first ABI revision have their ctypes mirrors checked field by field here
+    tn = cv._capi.cvb_test_num_pars
+    assert [f[0] for f in tn._fields_] == ['symp_test', 'quar_test', 'quar_policy', 'index'] and C.sizeof(tn) == 24

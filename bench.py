@@ -325,16 +325,59 @@ def measure_dense_edge_pass(args, cv, sim, snap, peak, E, N, day=60, reps=20):
                 l2='edge lists evicted between repetitions by reading 256 MB; per-agent records re-written by cvb_prepare_transmission as in the simulated day')
 
 
+def run_ref_leg(leg, args, extra, timeout):
+    """ One leg of oracle/ref_arm.py (the UNMODIFIED reference on host cores) in a fresh process; returns its JSON or None """
+    cmd = [sys.executable, '-m', 'oracle.ref_arm', leg, '--pop-size', str(args.pop_size), '--n-days', str(args.n_days)] + [str(x) for x in extra]
+    env = dict(os.environ)
+    for k in ('OMP_NUM_THREADS', 'NUMBA_NUM_THREADS', 'MKL_NUM_THREADS'):      # torchrun pins these to 1; the reference arm uses every host core
+        env.pop(k, None)
+    try:
+        res = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return None
+    for line in reversed(res.stdout.strip().splitlines()):
+        if line.startswith('{'):
+            return json.loads(line)
+    sys.stderr.write(f'bench.py: reference leg "{leg}" failed (rc={res.returncode}):\n{res.stderr[-2000:]}\n')
+    return None
+
+
+def reference_installed():
+    return os.path.isdir(os.path.join(ROOT, 'oracle', '_ref', 'covasim')) or os.path.isdir('/root/reference/covasim')
+
+
 def cpu_baseline_from_gpu_state(args, cv, sim, snap, t0=40, budget_s=20.0):
-    ''' Time the oracle on days [t0, t0+k) of the same sim, starting from the device state at day t0 '''
-    from oracle import cvoracle as cvo
+    """
+    cpu_baseline: the UNMODIFIED reference (oracle/_ref, Numba parallel='full' on every host core) continuing the SAME sim from
+    the GPU's day-t0 People state for a bounded number of days.  Falls back to the oracle port (kind "port") only when the
+    reference install is missing.
+    """
     import torch
     t0 = min(t0, max(args.n_days - 4, 0))
     sim.restore(snap)
     sim.set_seed()
-    while sim.t < t0:
-        sim.step()
+    sim.run(until=t0)
     torch.cuda.synchronize()
+    if reference_installed():
+        path = os.path.join(tempfile.gettempdir(), f'cvb_state_{os.getpid()}.npz')
+        arrays = {f'people/{k}': sim.people.to_numpy(k) for k in sim.people.keys()}
+        lkeys = sim.people.layer_keys()
+        for lk, l in sim.people.contacts.items():
+            cols = l.to_numpy()
+            for c in ('p1', 'p2', 'beta'):
+                arrays[f'{c}/{lk}'] = cols[c]
+        np.savez(path, t=np.int64(t0), layer_keys=np.array(lkeys), **arrays)
+        try:
+            out = run_ref_leg('continue', args, ['--state', path, '--budget', budget_s, '--numba-parallel', 'full'], timeout=600)
+        finally:
+            os.remove(path)
+        if out is not None:
+            return dict(value=out['agent_days_per_s'], unit=UNIT, cores=out['cores'], kind='reference',
+                        sample=(f"unmodified Covasim {out['version']} (oracle/_ref; numba {out['numba']}, numba_parallel='full', {out['cores']} threads of "
+                                f"{out['host_cores']} host cores) on days {out['first_day']}..{out['first_day'] + out['days'] - 1} of the same sim, continued from the "
+                                f"GPU's People state; {out['s_per_day']:.3f} s/day"),
+                        s_per_day=out['s_per_day'])
+    from oracle import cvoracle as cvo
     pop = dict(age=sim.people.to_numpy('age').astype(np.float64), sex=sim.people.to_numpy('sex'),
                contacts={lk: l.to_numpy() for lk, l in sim.people.contacts.items()})
     orc = cvo.OracleSim(workload_pars(args, seed=1), interventions=workload_interventions(cvo), rng='philox', popdict=pop)
@@ -351,17 +394,49 @@ def cpu_baseline_from_gpu_state(args, cv, sim, snap, t0=40, budget_s=20.0):
         days += 1
     el = time.perf_counter() - t_start
     return dict(value=args.pop_size * days / el, unit=UNIT, cores=1, kind='port',
-                sample=f'oracle (NumPy port of the reference algorithm) on days {t0 + 1}..{t0 + days} of the same sim, continued from the GPU state; {el / days:.3f} s/day',
+                sample=f'reference install missing (oracle/_ref): oracle port (NumPy restatement) on days {t0 + 1}..{t0 + days} of the same sim, continued from the GPU state; {el / days:.3f} s/day',
                 s_per_day=el / days)
 
 
 # ---------------------------------------------------------------------------------------------------
-# the reference arm: the reference's CPU algorithm (oracle port) on the same configuration
+# the reference arm: the UNMODIFIED reference (oracle/_ref) on the box's host cores, same configuration
 # ---------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """
+    One full run of the BASELINE workload by the reference's own code (numba_parallel='full', every host core), timed as
+    --steps consecutive sim.run(until=...) chunks that together span day 0 .. the last day; the --warmup steps are a small sim
+    of the same shape that compiles the Numba kernels.  A second, shorter leg reports numba_parallel='none' (the reference's
+    deterministic default) on the first third of the run.  Falls back to the oracle port only if oracle/_ref is missing.
+    """
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    if not reference_installed():
+        return run_reference_port(args)
+    full = run_ref_leg('full', args, ['--chunks', max(args.steps, 1), '--numba-parallel', 'full'], timeout=1500)
+    if full is None or not full['days_done']:
+        return run_reference_port(args)
+    third = max((args.n_days + 1) // 3, 4)
+    none = run_ref_leg('full', args, ['--chunks', 1, '--numba-parallel', 'none', '--n-days', third - 1], timeout=900)
+    value = full['agent_days_per_s']
+    k = max(len(full['chunk_seconds']), 1)
+    sample = (f"unmodified Covasim {full['version']} (oracle/_ref; numba {full['numba']}, numba_parallel='full', {full['cores']} threads of {full['host_cores']} host "
+              f"cores): ONE complete run, days 0..{full['days_done'] - 1}, timed as {k} consecutive sim.run(until=) chunks ({full['seconds']:.1f} s in all, "
+              f"{full['seconds'] / full['days_done']:.3f} s/day; init {full['init_s']:.1f} s and Numba compilation {full['warmup_s']:.1f} s excluded)")
+    cpu = dict(value=value, unit=UNIT, cores=full['cores'], kind='reference', sample=sample, complete_run=full['complete'],
+               chunk_seconds=full['chunk_seconds'], chunk_days=full['chunk_days'], cum_infections=full['cum_infections'])
+    if none is not None and none['days_done']:
+        cpu['numba_parallel_none'] = dict(value=none['agent_days_per_s'], cores=1, days=f"0..{none['days_done'] - 1}", seconds=none['seconds'],
+                                          note="the reference's default (deterministic) setting on the first third of the run")
+    out = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+               ms_per_step=1e3 * full['seconds'] / k, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+               config=config_block(args, dict(rng='mt19937 (reference streams)', init_s=full['init_s'], parallelism=f"host CPU, {full['cores']} Numba threads")),
+               cpu_baseline=cpu, e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(out))
+
+
+def run_reference_port(args):
+    """ Fallback when oracle/_ref is missing: the oracle port (NumPy restatement, one core), time-bounded samples from day 0 """
     from oracle import cvoracle as cvo
     total = args.steps + args.warmup
     budget = 150.0 / max(total, 1)                        # seconds per step so the whole run ends within a few minutes
@@ -372,10 +447,8 @@ def run_reference(args):
     base.initialize()
     t_init = time.time() - t0
     P0 = {k: v.copy() for k, v in base.P.items()}
-    state = dict(days=0)
 
     def one_step():
-        ''' One bounded sample: the sim from day 0 for at most `budget` seconds (or to its end); returns (seconds, days done) '''
         for k, v in P0.items():
             base.P[k][...] = v
         base.t = 0
@@ -387,7 +460,6 @@ def run_reference(args):
         while days < args.n_days + 1 and (days < 4 or time.perf_counter() - ts < budget):
             base.step()
             days += 1
-        state['days'] = days
         return time.perf_counter() - ts, days
 
     for _ in range(args.warmup):
@@ -396,8 +468,8 @@ def run_reference(args):
     el = float(np.sum([r[0] for r in runs])) / args.steps
     days = float(np.sum([r[1] for r in runs])) / args.steps
     value = args.pop_size * days / el
-    sample = (f'first {days:.0f} of {args.n_days + 1} days of the same sim per step (time-bounded at {budget:.0f} s per step; {el / days:.3f} s/day), '
-              'oracle port of the reference algorithm (NumPy, 1 host core), MT19937 streams')
+    sample = (f'reference install missing (oracle/_ref): oracle port (NumPy restatement, 1 host core), first {days:.0f} of {args.n_days + 1} days per step '
+              f'(time-bounded at {budget:.0f} s per step; {el / days:.3f} s/day)')
     out = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * el,
                higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                config=config_block(args, dict(rng='mt19937 (reference streams)', init_s=t_init)),

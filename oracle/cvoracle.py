@@ -20,8 +20,8 @@ import copy
 import datetime as dt
 import numpy as np
 
-from covasim_b200 import defaults as cvd        # field/result inventories and dtypes (pure config)
-from covasim_b200 import parameters as cvpar     # parameter tables (pure config)
+from . import ref_defaults as cvd       # the oracle's OWN copy of the field/result inventories (never the product package:
+from . import ref_parameters as cvpar   # importing covasim_b200 would dlopen the CUDA library); tests/test_oracle_golden.py diffs the two
 from . import philox as ph
 
 f32 = np.float32

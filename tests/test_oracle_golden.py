@@ -7,6 +7,7 @@ Numba kernels.  CPU only.
 '''
 import hashlib
 import json
+import os
 
 import numpy as np
 import pytest
@@ -132,3 +133,45 @@ def test_initial_population_matches_reference(name, golden):
     for lk, layer in sim.contacts.items():
         assert len(layer['p1']) == int(g[f'contacts_len/{lk}'])
         assert digest(layer['p1']) + digest(layer['p2']) == str(g[f'contacts_digest/{lk}']), lk
+
+
+def test_config_tables():
+    '''
+    The parameter tables of the product (covasim_b200/{defaults,parameters}.py) and of the oracle's own copy
+    (oracle/{ref_defaults,ref_parameters}.py) against the tables recorded from the unmodified reference
+    (tests/golden/ref_config.json, written by oracle/gen_config_golden.py): a constant cannot be wrong on both sides.
+    The product modules are loaded from their files so that this CPU test does not load the CUDA library.
+    '''
+    import importlib.util
+    import sys
+    import types
+    from oracle import gen_config_golden as gen, ref_defaults as od, ref_parameters as op
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = json.load(open(os.path.join(root, 'tests', 'golden', 'ref_config.json')))
+    pkg = types.ModuleType('_cvb_cfg')                      # a stand-in package holding only the two config modules
+    pkg.__path__ = [os.path.join(root, 'covasim_b200')]
+    sys.modules['_cvb_cfg'] = pkg
+    mods = {}
+    for name in ('defaults', 'parameters'):
+        spec = importlib.util.spec_from_file_location(f'_cvb_cfg.{name}', os.path.join(root, 'covasim_b200', f'{name}.py'))
+        mods[name] = importlib.util.module_from_spec(spec)
+        sys.modules[f'_cvb_cfg.{name}'] = mods[name]
+        spec.loader.exec_module(mods[name])
+    for label, (par, dfl) in dict(oracle=(op, od), product=(mods['parameters'], mods['defaults'])).items():
+        got = json.loads(json.dumps(gen.collect(par, dfl), sort_keys=True))
+        for key, val in got.items():
+            assert val == ref[key], f'{label} copy of "{key}" differs from the reference'
+    fields = ref['people_fields']
+    for dfl in (od, mods['defaults']):
+        assert list(dfl.person_fields) == fields['person'] and list(dfl.states) == fields['states'] and list(dfl.dates) == fields['dates']
+        assert list(dfl.variant_states) == fields['variant_states'] and list(dfl.by_variant_states) == fields['by_variant_states']
+        assert list(dfl.imm_states) == fields['imm_states'] and list(dfl.nab_states) == fields['nab_states']
+        assert list(dfl.vacc_states) == fields['vacc_states'] and list(dfl.durs) == fields['durs']
+
+
+def test_oracle_does_not_import_the_product():
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = 'import sys; from oracle import cvoracle, philox; assert not any(m.startswith("covasim_b200") for m in sys.modules), "oracle imported the product"'
+    subprocess.run([sys.executable, '-c', code], check=True, cwd=root)

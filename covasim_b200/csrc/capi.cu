@@ -126,9 +126,9 @@ int cvb_create(cvb_sim** out, int64_t n_agents, int32_t n_variants, int32_t npts
         if ((rc = check_cuda(cudaMemset(s->n_case_list, 0, 64), "n_case_list"))) break;
         if ((rc = check_cuda(cudaMalloc((void**)&s->n_cases, 64), "n_cases"))) break;
         if ((rc = check_cuda(cudaMemset(s->n_cases, 0, 64), "n_cases"))) break;
-        if ((rc = check_cuda(cudaMalloc((void**)&s->dev_scalars, 16 * sizeof(unsigned long long)), "dev_scalars"))) break;
-        if ((rc = check_cuda(cudaMemset(s->dev_scalars, 0, 16 * sizeof(unsigned long long)), "dev_scalars"))) break;
-        if ((rc = check_cuda(cudaMallocHost((void**)&s->host_scalars, 16 * sizeof(unsigned long long)), "host_scalars"))) break;
+        if ((rc = check_cuda(cudaMalloc((void**)&s->dev_scalars, 64 * sizeof(unsigned long long)), "dev_scalars"))) break;
+        if ((rc = check_cuda(cudaMemset(s->dev_scalars, 0, 64 * sizeof(unsigned long long)), "dev_scalars"))) break;
+        if ((rc = check_cuda(cudaMallocHost((void**)&s->host_scalars, 64 * sizeof(unsigned long long)), "host_scalars"))) break;
         if ((rc = check_cuda(cudaDeviceSynchronize(), "cvb_create sync"))) break;
     } while (0);
     if (rc) { cvb_destroy(s); return rc; }
@@ -143,6 +143,9 @@ int cvb_destroy(cvb_sim* s) {
     cudaFree(s->n_cases); cudaFree(s->dev_scalars); cudaFree(s->rec_store); cudaFree(s->ts8_store);
     cudaFree(s->nab_kin); cudaFree(s->tile_cnt); cudaFree(s->hit_mask); cudaFree(s->flag_tmp); cudaFree(s->partial);
     cudaFree(s->glist); cudaFree(s->n_glist); cudaFree(s->hit_src); cudaFree(s->hit_key); cudaFree(s->part_flags);
+    cudaFree(s->state); cudaFree(s->trans_ent); cudaFree(s->case_ent);
+    delete s->plan;
+    cvb_timing_enable(s, 0);
     if (s->host_scalars) cudaFreeHost(s->host_scalars);
     delete s;
     return 0;

@@ -43,6 +43,17 @@ struct ResultPtrs {
     double* sums;                              // [npts][4]
 };
 
+// Built-in interventions registered with the handle so that cvb_run_days can run whole days without the host
+struct DayPlan {
+    int32_t has_test, test_start, test_end;         // test_prob (end < 0: none)
+    cvb_test_prob_pars test;
+    int32_t has_trace, trace_start, trace_end;      // contact_tracing
+    cvb_trace_pars trace;
+    uint32_t regen_mask;                            // dynamic layers regenerated every day (Layer.update, frac = 1)
+};
+
+struct FusedTiming;
+
 struct LogPtrs {
     int32_t* source; int32_t* target; int32_t* date; int8_t* layer; int8_t* variant;
     int64_t cap; unsigned long long* count;
@@ -105,6 +116,14 @@ struct cvb_sim {
     double* partial; int64_t partial_cap;           // per-block partial sums
     unsigned long long* dev_scalars;                // small device scratch for counts returned to the host
     unsigned long long* host_scalars;               // pinned mirror
+    // ---- fused day pipeline (day_fused.cu) ----------------------------------------------------------------------------
+    // state[i]: packed copy of the 16 bool states + a few "is there anything to read" bits, kept in step with the public
+    // People arrays by the fused kernels; rebuilt from the arrays (pack_state_kernel) whenever anything else may have written them
+    uint32_t* state; int32_t state_valid;
+    uint4* trans_ent;                               // [N][2] today's transmitters {agent, row length, row begin, rel_trans, code}
+    uint4* case_ent;                                // [N] today's traced cases {agent, row length, row begin}
+    cvb::DayPlan* plan;                             // built-in interventions the C day loop runs itself (cvb_plan_*)
+    cvb::FusedTiming* timing;                       // per-kernel CUDA-event timing of the day loop, when enabled
 };
 
 namespace cvb {
@@ -117,6 +136,11 @@ int ensure_f64(double** p, int64_t* cap, int64_t need);
 int exclusive_scan_u32(unsigned int* data, int64_t n, unsigned long long* total_out, cudaStream_t st);
 // agent-partitioned runs: set bits of a gathered bitmap -> s->glist / s->n_glist (edge_pass.cu)
 int list_from_bits(cvb_sim* s, const unsigned int* bits, int64_t n_words, cudaStream_t st);
+int edge_pass_impl(cvb_sim* s, int32_t t, cudaStream_t st, bool from_entries);       // edge_pass.cu
+int launch_trace_sparse2(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cudaStream_t st);   // interventions.cu
+int launch_infect_winners(cvb_sim* s, int32_t t, bool with_state, cudaStream_t st);   // infect.cu
+// every entry point that writes People flags outside the fused pipeline calls this: the packed state must be rebuilt
+inline void state_touched(cvb_sim* s) { s->state_valid = 0; }
 
 #define CVB_CHECK(call) do { int rc_ = cvb::check_cuda((call), #call); if (rc_) return rc_; } while (0)
 #define CVB_REQUIRE(cond, ...) do { if (!(cond)) { cvb::set_error(__VA_ARGS__); return 1; } } while (0)

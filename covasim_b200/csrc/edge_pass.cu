@@ -336,6 +336,68 @@ __global__ void __launch_bounds__(kThreads) edge_pass_sparse_kernel(TransRecords
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(work_row + 1, (unsigned long long)n_trans);
 }
 
+// ---- sparse form v2 (fused day pipeline): transmitter ENTRIES instead of a list of agents ----------------------------------
+// day_mid_kernel writes one 32-byte entry per transmitter: {agent, row length, row begin (64 bit)} {rel_trans, transmit code}, so
+// a group's dependent chain is entry -> adjacency entries -> neighbour records (three loads instead of the five of the list form:
+// list -> row pointers -> own record -> entries -> records).  G lanes share a transmitter and each lane keeps U adjacency entries
+// in flight: all U entry loads are issued, then all U record gathers, then the arithmetic -- a row of 32 entries costs two
+// memory round trips per group.  Same probability chain, Philox key and winner key as every other form.
+template <bool MULTI, int G, int U>
+__global__ void __launch_bounds__(kThreads) edge_pass_sparse2_kernel(TransRecords rec, const __grid_constant__ EdgeParams ep,
+        const uint4* __restrict__ adj, const uint4* __restrict__ ents, const unsigned int* __restrict__ n_trans_ptr,
+        unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand,
+        unsigned long long* __restrict__ work_row) {
+    const unsigned int n_trans = *n_trans_ptr;
+    unsigned long long visited = 0;
+    const int64_t n = ep.n;
+    const int gl = threadIdx.x & (G - 1);
+    const unsigned int groups_total = (gridDim.x * blockDim.x) / G;
+    for (unsigned int ti = (blockIdx.x * blockDim.x + threadIdx.x) / G; ti < n_trans; ti += groups_total) {
+        const uint4 e0 = __ldg(ents + 2 * (int64_t)ti), e1 = __ldg(ents + 2 * (int64_t)ti + 1);
+        const int len = (int)e0.y;
+        const long long beg = (long long)(((unsigned long long)e0.w << 32) | (unsigned long long)e0.z);
+        const float rt = __uint_as_float(e1.x);
+        const uint32_t ci = e1.y;
+        const int vi = (int)(ci & 7u) - 1;
+        const float beta_v = ep.beta[vi < 0 ? 0 : vi];
+        if (gl == 0) visited += (unsigned long long)len;
+        for (int base = gl; base < len; base += G * U) {
+            uint4 en[U];
+            float4 rj[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int off = base + u * G;
+                en[u] = off < len ? __ldg(adj + beg + off) : make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) rj[u] = en[u].z != 0xFFFFFFFFu ? __ldg(rec.rec + en[u].x) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (en[u].z == 0xFFFFFFFFu || rj[u].y == 0.0f) continue;      // past the row's end / target not susceptible
+                const int j = (int)en[u].x;
+                const int l = (int)(en[u].z >> 1);
+                const int dir = (int)(en[u].z & 1u);
+                const float t_i = record_trans(rt, ci, ep.asymp_factor, ep.iso_factor[l], ep.quar_factor[l], ep.beta_layer[l], ep.vl_early, ep.vl_late);
+                if (t_i == 0.0f) continue;                                    // cannot transmit on this layer
+                float imm = rj[u].z;
+                if (MULTI && vi > 0) imm = __ldg(rec.sus_imm + (int64_t)vi * n + j);
+                const float s_j = record_sus(rj[u].y, __float_as_uint(rj[u].w), ep.quar_factor[l], imm);
+                const float p = edge_prob(beta_v, __uint_as_float(en[u].w), t_i, s_j);
+                if (p != 0.0f) {
+                    const int64_t e = (int64_t)en[u].y;
+                    const u32x4 r = keyed_words(ep.seed, P_EDGE, (uint32_t)l, ep.t, e, 0);
+                    const double uu = dir == 0 ? u53(r.x, r.y) : u53(r.z, r.w);
+                    if (uu < (double)p)
+                        record_hit(infect_key, cand, n_cand, j, ((unsigned long long)vi << 56) | ((unsigned long long)l << 48) |
+                                                                ((unsigned long long)dir << 40) | (unsigned long long)e);
+                }
+            }
+        }
+    }
+    if (visited) atomicAdd(work_row, visited);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(work_row + 1, (unsigned long long)n_trans);
+}
+
 // ---- agent-partitioned form (one large simulation over several GPUs) ------------------------------------
 // Every GPU owns a contiguous range of agents and evaluates the transmissions whose TARGET it owns.  Its
 // adjacency has one row per GLOBAL agent (the possible sources) holding the edges that end in a LOCAL
@@ -514,8 +576,13 @@ int cvb::build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges, uint32_t s
     return 0;
 }
 
-extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
-    cudaStream_t st = (cudaStream_t)st_;
+extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st) {
+    return cvb::edge_pass_impl(s, t, (cudaStream_t)st, false);
+}
+
+// from_entries: the adjacency part reads the transmitter entries written by day_mid_kernel (fused day pipeline) instead of the
+// plain transmitter list written by post_prepare_kernel
+int cvb::edge_pass_impl(cvb_sim* s, int32_t t, cudaStream_t st, bool from_entries) {
     CVB_REQUIRE(s && s->pars_set, "cvb_edge_pass: handle not ready");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_edge_pass: day %d outside [0,%d)", t, s->npts);
     CVB_REQUIRE((s->rec.rec || s->rec.ts8) && s->rec_layers >= s->pars.n_layers, "cvb_edge_pass: call cvb_prepare_transmission first");
@@ -558,8 +625,13 @@ extern "C" int cvb_edge_pass(cvb_sim* s, int32_t t, cvb_stream st_) {
         skip_mask = s->adj_layer_mask;
         const int grid = 148 * 8;
         unsigned long long* work_row = s->edge_work + (int64_t)t * 2;
-        if (multi) edge_pass_sparse_kernel<true><<<grid, kThreads, 0, st>>>(s->rec, ep, s->adj_ptr, s->adj, s->trans_list, s->n_trans,
-                                                                          s->infect_key, s->cand, s->n_cand, work_row);
+        if (from_entries) {
+            CVB_REQUIRE(s->trans_ent, "cvb_edge_pass: transmitter entries missing");
+            if (multi) edge_pass_sparse2_kernel<true, 8, 4><<<grid, kThreads, 0, st>>>(s->rec, ep, s->adj, s->trans_ent, s->n_trans, s->infect_key, s->cand, s->n_cand, work_row);
+            else edge_pass_sparse2_kernel<false, 8, 4><<<grid, kThreads, 0, st>>>(s->rec, ep, s->adj, s->trans_ent, s->n_trans, s->infect_key, s->cand, s->n_cand, work_row);
+        }
+        else if (multi) edge_pass_sparse_kernel<true><<<grid, kThreads, 0, st>>>(s->rec, ep, s->adj_ptr, s->adj, s->trans_list, s->n_trans,
+                                                                               s->infect_key, s->cand, s->n_cand, work_row);
         else edge_pass_sparse_kernel<false><<<grid, kThreads, 0, st>>>(s->rec, ep, s->adj_ptr, s->adj, s->trans_list, s->n_trans,
                                                                       s->infect_key, s->cand, s->n_cand, work_row);
         CVB_LAUNCH_CHECK();

@@ -27,7 +27,8 @@ struct InfectArgs {
 
 __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __grid_constant__ cvb_pars pars, const __grid_constant__ LayerTable L,
         const __grid_constant__ InfectArgs ia, const int32_t* __restrict__ cand, const unsigned int* __restrict__ n_cand_ptr,
-        unsigned long long* __restrict__ infect_key, const unsigned long long* __restrict__ beds, ResultPtrs res, LogPtrs log) {
+        unsigned long long* __restrict__ infect_key, const unsigned long long* __restrict__ beds, ResultPtrs res, LogPtrs log,
+        uint32_t* __restrict__ S /* packed state words of the fused day pipeline (day_fused.cu), or NULL */) {
     __shared__ int s_cnt[INF_NK + 3 * CVB_MAX_VARIANTS];
     const int NK = INF_NK + 3 * CVB_MAX_VARIANTS;
     if (threadIdx.x < NK) s_cnt[threadIdx.x] = 0;
@@ -221,6 +222,15 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
             }
             PI(P, t_nab_event)[i] = t;
         }
+        if (S) {
+            // the packed state word follows (bit layout: day_fused.cu): not susceptible / naive / recovered / diagnosed any more, no
+            // diagnosis date, exposed to variant v, no natural-immunity source until recovery; antibodies from now on if waning
+            uint32_t sk = S[i];
+            sk &= ~((1u << 0) | (1u << 1) | (1u << 9) | (1u << 8) | (1u << 19) | (15u << 24) | (15u << 28));
+            sk |= (1u << 2) | ((uint32_t)(v + 1) << 24);
+            if (pars.use_waning) sk |= 1u << 16;
+            S[i] = sk;
+        }
     }
 
     reduce_counters(c, s_cnt);
@@ -257,7 +267,7 @@ __global__ void claim_list_kernel(const int32_t* __restrict__ inds, int64_t n_in
 __global__ void reset_u32_kernel(unsigned int* p) { *p = 0; }
 
 static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t list_layer_code, int32_t hosp_max, int32_t icu_max,
-                         int64_t max_items, cudaStream_t st, bool hits = false) {
+                         int64_t max_items, cudaStream_t st, bool hits = false, bool with_state = false) {
     CVB_REQUIRE(s->log.count, "infect: infection log is not bound (cvb_bind_log)");
     LayerTable L;
     if (build_layer_table(s, L, kTileEdges, 0)) return 1;          // no layer skipped: entry index == layer id
@@ -267,9 +277,15 @@ static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t lis
     ia.id0 = s->partitioned ? s->id0 : 0;
     ia.hit_src = hits ? s->hit_src : nullptr; ia.hit_key = hits ? s->hit_key : nullptr; ia.hit_cap = s->hit_cap;
     int grid = grid_for(max_items * 16, kThreads, 148 * 4);       // sixteen lanes per agent
-    infect_kernel<<<grid, kThreads, 0, st>>>(s->people, s->pars, L, ia, s->cand, s->n_cand, s->infect_key, s->beds, s->res, s->log);
+    infect_kernel<<<grid, kThreads, 0, st>>>(s->people, s->pars, L, ia, s->cand, s->n_cand, s->infect_key, s->beds, s->res, s->log,
+                                             with_state ? s->state : nullptr);
     CVB_LAUNCH_CHECK();
     return 0;
+}
+
+int launch_infect_winners(cvb_sim* s, int32_t t, bool with_state, cudaStream_t st) {
+    int64_t guess = s->n / 64 + 1024;
+    return launch_infect(s, t, 1, CVB_LAYER_SEED, -1, -1, guess, st, s->partitioned != 0, with_state);
 }
 
 }  // namespace cvb
@@ -281,10 +297,10 @@ extern "C" {
 int cvb_infect_winners(cvb_sim* s, int32_t t, cvb_stream st) {
     CVB_REQUIRE(s && s->pars_set && s->res.counters, "cvb_infect_winners: handle not ready");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_infect_winners: day %d outside [0,%d)", t, s->npts);
+    cvb::state_touched(s);
     // the number of candidates is only known on the device: size the grid for a large outbreak and let
     // surplus CTAs exit after one load of n_cand
-    int64_t guess = s->n / 64 + 1024;
-    return launch_infect(s, t, 1, CVB_LAYER_SEED, -1, -1, guess, (cudaStream_t)st, s->partitioned != 0);
+    return launch_infect_winners(s, t, false, (cudaStream_t)st);
 }
 
 int cvb_infect_list(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant, int32_t layer_code, int32_t t,
@@ -294,6 +310,7 @@ int cvb_infect_list(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant,
     CVB_REQUIRE(variant >= 0 && variant < s->nv, "cvb_infect_list: variant %d out of range", variant);
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_infect_list: day %d outside [0,%d)", t, s->npts);
     if (n == 0) return 0;
+    cvb::state_touched(s);
     CVB_REQUIRE(inds, "cvb_infect_list: NULL index array");
     reset_u32_kernel<<<1, 1, 0, st>>>(s->n_cand);
     CVB_LAUNCH_CHECK();

@@ -220,6 +220,38 @@ __global__ void __launch_bounds__(kThreads) trace_sparse_kernel(PeoplePtrs P, co
     }
 }
 
+// Fused day pipeline: the cases come as entries {agent, row length, row begin} written by day_begin_kernel, the contact's "dead" flag
+// is read from the packed state word, and the word's known_contact / pending-request bits are set with the People arrays
+__device__ __forceinline__ void trace_notify2(const PeoplePtrs& P, uint32_t* __restrict__ S, const TraceTable& T, int q, int c) {
+    const uint32_t sub = ((uint32_t)T.index << 8) | (uint32_t)T.layer_id[q];
+    if (!(keyed_uniform(T.seed, P_TRACE, sub, T.t, (int64_t)c + T.id0, 0) < T.trace_prob[q])) return;     // binomial_filter, interventions.py:1116
+    if (S[c] & (1u << 11)) return;                                     // dead (interventions.py:1139-1141)
+    PB(P, known_contact)[c] = 1;
+    atomicOr(S + c, (1u << 12) | (1u << 18));                          // known_contact, request pending
+    atomicMin((unsigned int*)PF(P, date_known_contact) + c, (unsigned int)__float_as_int(T.notify_day[q]));
+    atomicMax(T.quar_slot[q] + c, __float_as_int(T.end_day));          // people.py:620-640 schedule_quarantine
+}
+
+__global__ void __launch_bounds__(kThreads) trace_sparse2_kernel(PeoplePtrs P, uint32_t* __restrict__ S, const __grid_constant__ TraceTable T,
+        const uint4* __restrict__ adj, const uint4* __restrict__ case_ent, const unsigned int* __restrict__ n_case_ptr, uint32_t layer_mask) {
+    const unsigned int n_cases = *n_case_ptr;
+    const int lane = lane_id();
+    const unsigned int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < n_cases; ci += warps_total) {
+        const uint4 ce = __ldg(case_ent + ci);
+        const int len = (int)ce.y;
+        const long long beg = (long long)(((unsigned long long)ce.w << 32) | (unsigned long long)ce.z);
+        for (int off = lane; off < len; off += 32) {
+            const uint4 en = __ldg(adj + beg + off);
+            const int l = (int)(en.z >> 1);
+            if (!((layer_mask >> l) & 1u)) continue;
+            const int q = T.entry_of_layer[l];
+            if (q < 0) continue;                                       // layer not traced
+            trace_notify2(P, S, T, q, (int)en.x);
+        }
+    }
+}
+
 // One streaming pass over (p1, p2) of every traced layer; the case bitmap is staged in shared memory when it fits
 template <bool SMEM_BITS, int THREADS>
 __global__ void __launch_bounds__(THREADS) trace_edges_kernel(PeoplePtrs P, const __grid_constant__ TraceTable T,
@@ -342,6 +374,7 @@ using namespace cvb;
 extern "C" {
 
 int cvb_test_prob(cvb_sim* s, int32_t t, const cvb_test_prob_pars* tp, const double* prob_override, cvb_stream st) {
+    if (s) cvb::state_touched(s);
     CVB_REQUIRE(s && tp && s->res.counters, "cvb_test_prob: handle not ready");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_test_prob: day %d outside [0,%d)", t, s->npts);
     uintptr_t al = 0;
@@ -396,6 +429,22 @@ static int build_trace_table(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, ui
     return 0;
 }
 
+}  // extern "C"
+
+int cvb::launch_trace_sparse2(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cudaStream_t st) {
+    TraceTable T;
+    int64_t acc;
+    bool any_sparse;
+    if (build_trace_table(s, t, tr, s->adj_layer_mask, kTileEdges, T, acc, any_sparse)) return 1;
+    CVB_REQUIRE(acc == 0, "fused day: a traced layer is not covered by the adjacency");
+    if (!any_sparse) return 0;
+    trace_sparse2_kernel<<<148 * 2, kThreads, 0, st>>>(s->people, s->state, T, s->adj, s->case_ent, s->n_case_list, s->adj_layer_mask);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" {
+
 int cvb_trace_select_cases(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_stream st) {
     CVB_REQUIRE(s && tr && s->pars_set, "cvb_trace_select_cases: handle not ready");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_trace_select_cases: day %d outside [0,%d)", t, s->npts);
@@ -403,6 +452,7 @@ int cvb_trace_select_cases(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_
 }
 
 int cvb_trace_notify_contacts(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_stream st_) {
+    if (s) cvb::state_touched(s);
     cudaStream_t st = (cudaStream_t)st_;
     CVB_REQUIRE(s && tr && s->pars_set, "cvb_trace_notify_contacts: handle not ready");
     CVB_REQUIRE(s->partitioned, "cvb_trace_notify_contacts: only for agent-partitioned handles (use cvb_contact_tracing)");
@@ -431,6 +481,7 @@ int cvb_test_num_keys(cvb_sim* s, int32_t t, const cvb_test_num_pars* tp, double
 
 int cvb_test_list(cvb_sim* s, int32_t t, const int32_t* inds, int64_t n_inds, double sensitivity, double loss_prob, int32_t test_delay,
                   int32_t index, cvb_stream st) {
+    if (s) cvb::state_touched(s);
     CVB_REQUIRE(s && (n_inds == 0 || inds), "cvb_test_list: bad argument");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_test_list: day %d outside [0,%d)", t, s->npts);
     if (n_inds == 0) return 0;
@@ -474,6 +525,7 @@ static int trace_notify_local(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, c
 }
 
 int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_stream st_) {
+    if (s) cvb::state_touched(s);
     cudaStream_t st = (cudaStream_t)st_;
     CVB_REQUIRE(s && tr && s->pars_set, "cvb_contact_tracing: handle not ready");
     CVB_REQUIRE(!s->partitioned, "cvb_contact_tracing: agent-partitioned handles trace in two phases (cvb_trace_select_cases, all-gather, cvb_trace_notify_contacts)");
@@ -483,6 +535,7 @@ int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_str
 }
 
 int cvb_contact_tracing_list(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, const int32_t* case_inds, int64_t n_cases, cvb_stream st_) {
+    if (s) cvb::state_touched(s);
     cudaStream_t st = (cudaStream_t)st_;
     CVB_REQUIRE(s && tr && s->pars_set && (n_cases == 0 || case_inds), "cvb_contact_tracing_list: bad argument");
     CVB_REQUIRE(!s->partitioned, "cvb_contact_tracing_list: not for agent-partitioned handles");
@@ -497,6 +550,7 @@ int cvb_contact_tracing_list(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, co
 
 int cvb_vaccinate_prob(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* vp, int32_t* iv_doses, int32_t* due_day, const double* prob_override,
                        cvb_stream st) {
+    if (s) cvb::state_touched(s);
     CVB_REQUIRE(s && vp && iv_doses && due_day && s->res.counters, "cvb_vaccinate_prob: bad argument");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_vaccinate_prob: day %d outside [0,%d)", t, s->npts);
     CVB_REQUIRE(vp->vaccine_index >= 0 && vp->vaccine_index < CVB_MAX_VACCINES, "cvb_vaccinate_prob: vaccine index out of range");

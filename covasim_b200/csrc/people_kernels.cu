@@ -585,6 +585,7 @@ static int launch_post_prepare(cvb_sim* s, int32_t t, cudaStream_t st) {
 extern "C" {
 
 int cvb_update_states_pre(cvb_sim* s, int32_t t, cvb_stream st) {
+    if (s) cvb::state_touched(s);
     if (require_ready(s, "cvb_update_states_pre")) return 1;
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_update_states_pre: day %d outside [0,%d)", t, s->npts);
     states_pre_kernel<<<grid_agents(s->n), kThreads, 0, (cudaStream_t)st>>>(s->people, s->pars, s->n, t, vector_ok(s), s->res.counters,
@@ -594,6 +595,7 @@ int cvb_update_states_pre(cvb_sim* s, int32_t t, cvb_stream st) {
 }
 
 int cvb_schedule_quarantine(cvb_sim* s, const int32_t* inds, int64_t n, int32_t start_day, float end_day, cvb_stream st) {
+    if (s) cvb::state_touched(s);
     CVB_REQUIRE(s, "cvb_schedule_quarantine: NULL handle");
     if (n == 0) return 0;
     CVB_REQUIRE(inds, "cvb_schedule_quarantine: NULL index array");
@@ -605,6 +607,7 @@ int cvb_schedule_quarantine(cvb_sim* s, const int32_t* inds, int64_t n, int32_t 
 }
 
 int cvb_update_states_post(cvb_sim* s, int32_t t, cvb_stream st) {
+    if (s) cvb::state_touched(s);
     if (require_ready(s, "cvb_update_states_post")) return 1;
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_update_states_post: day %d outside [0,%d)", t, s->npts);
     return launch_post_prepare<true, false>(s, t, (cudaStream_t)st);
@@ -617,6 +620,7 @@ int cvb_prepare_transmission(cvb_sim* s, int32_t t, cvb_stream st) {
 }
 
 int cvb_post_and_prepare(cvb_sim* s, int32_t t, cvb_stream st) {
+    if (s) cvb::state_touched(s);
     if (require_ready(s, "cvb_post_and_prepare")) return 1;
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_post_and_prepare: day %d outside [0,%d)", t, s->npts);
     if (ensure_records(s)) return 1;
@@ -624,6 +628,7 @@ int cvb_post_and_prepare(cvb_sim* s, int32_t t, cvb_stream st) {
 }
 
 int cvb_update_nab_count(cvb_sim* s, int32_t t, cvb_stream st) {
+    if (s) cvb::state_touched(s);
     if (require_ready(s, "cvb_update_nab_count")) return 1;
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_update_nab_count: day %d outside [0,%d)", t, s->npts);
     CVB_REQUIRE(!s->pars.use_waning || s->nab_kin, "cvb_update_nab_count: NAb kinetics table not set (cvb_set_nab_kin)");

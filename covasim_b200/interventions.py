@@ -101,6 +101,14 @@ class Intervention:
     def shrink(self, in_place=False):
         return self
 
+    def _device_plan(self, sim):
+        '''
+        What Sim's block runner (cvb_run_days) needs to know about this intervention: None = apply() must be called every day
+        (the default, and what every user-written intervention gets); ('host', days) = apply() only matters on ``days``;
+        ('test', pars, start, end) / ('trace', pars, start, end) = runs inside the fused day kernels.
+        '''
+        return None
+
 
 class dynamic_pars(Intervention):
     '''
@@ -124,6 +132,11 @@ class dynamic_pars(Intervention):
             if len(spec['days']) != len(spec['vals']):
                 raise ValueError(f'Length of days ({len(spec["days"])}) does not match length of values ({len(spec["vals"])}) for parameter {parkey}')
         self.pars = pars
+
+    def _device_plan(self, sim):
+        if any(callable(spec['days']) for spec in self.pars.values()):
+            return None
+        return ('host', sorted({int(d) for spec in self.pars.values() for d in np.atleast_1d(spec['days'])}))
 
     def apply(self, sim):
         t = sim.t
@@ -195,6 +208,9 @@ class change_beta(Intervention):
         for lk in layers:
             self.orig_betas['overall' if lk is None else lk] = sim['beta'] if lk is None else sim['beta_layer'][lk]
 
+    def _device_plan(self, sim):
+        return None if callable(self.days) else ('host', [int(d) for d in np.atleast_1d(self.days)])
+
     def apply(self, sim):
         for ind in find_day(self.days, sim.t, interv=self, sim=sim):
             for lk, b in self.orig_betas.items():
@@ -229,6 +245,9 @@ class clip_edges(Intervention):
         self.layers = lkeys if self.layers is None else ([self.layers] if isinstance(self.layers, str) else list(self.layers))
         from .base import Layer
         self.contacts = {lk: Layer(label=lk, device=sim.people.device) for lk in self.layers}
+
+    def _device_plan(self, sim):
+        return None if callable(self.days) else ('host', [int(d) for d in np.atleast_1d(self.days)])
 
     def apply(self, sim):
         for ind in find_day(self.days, sim.t, interv=self, sim=sim):
@@ -378,6 +397,11 @@ class test_prob(Intervention):
                                            asymp_quar_prob=self.asymp_quar_prob, sensitivity=self.sensitivity, loss_prob=self.loss_prob,
                                            quar_policy=_QUAR_POLICY[self.quar_policy], test_delay=int(self.test_delay), index=self.index)
 
+    def _device_plan(self, sim):
+        if self.subtarget is not None or self.ili_prev is not None:
+            return None                                    # per-agent overrides are built on the host every day
+        return ('test', self._c, int(self.start_day), -1 if self.end_day is None else int(self.end_day))
+
     def apply(self, sim):
         t = sim.t
         if t < self.start_day or (self.end_day is not None and t > self.end_day):
@@ -454,6 +478,11 @@ class contact_tracing(Intervention):
             c.trace_time[i] = int(self.trace_time.get(lk, 0))
         self._c = c
         sim._set_quar_horizon(int(max(self.trace_time.values(), default=0)) + 1)
+
+    def _device_plan(self, sim):
+        if self.capacity is not None or self.presumptive:
+            return None
+        return ('trace', self._c, int(self.start_day), -1 if self.end_day is None else int(self.end_day))
 
     def apply(self, sim):
         t = sim.t
@@ -556,6 +585,14 @@ class vaccinate_prob(Intervention):
                                            booster=int(bool(self.booster)), vaccine_index=self.index, max_doses=int(doses), index=self.iindex,
                                            interval=-1 if interval is None else int(interval), n_days=int(sim['n_days']))
         sim._pars_dirty = True
+
+    def _device_plan(self, sim):
+        if callable(self.days):
+            return None
+        days = {int(d) for d in np.atleast_1d(self.days)}
+        if self.p['interval'] is not None:
+            days |= {d + int(self.p['interval']) for d in list(days)}
+        return ('host', sorted(days))
 
     def apply(self, sim):
         t = sim.t

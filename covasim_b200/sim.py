@@ -74,7 +74,7 @@ def gen_time(date_exposed, date_symptomatic, log_source, log_target):
 class Sim:
 
     def __init__(self, pars=None, popdict=None, label=None, device=None, rng='philox', pop_exact=None, use_adjacency=True, partition=None,
-                 hit_capacity=0, pop_gen='host', **kwargs):
+                 hit_capacity=0, pop_gen='host', fused=True, **kwargs):
         kw = dict(pars or {})
         kw.update(kwargs)
         for alias, key in (('n_agents', 'pop_size'), ('init_infected', 'pop_infected')):       # reference base.py:266-273
@@ -108,6 +108,11 @@ class Sim:
         self._quar_horizon = 1
         self._host_adds = {}
         self.kernel_timers = None          # set to {} to time every C-ABI call of step() with CUDA events
+        # fused=True: days on which no host decision is needed run through cvb_run_days (five launches per day, whole blocks of
+        # days per call from run()); False: every day through the per-step entry points.  Same results either way.
+        self.fused = bool(fused)
+        self._plan = None
+        self.fused_days = 0                # days that went through cvb_run_days (diagnostics / tests)
         self.use_adjacency = use_adjacency   # False: stream every layer densely each day (the reference's access pattern)
         self._adj = None
         self._adj_dirty = False
@@ -289,7 +294,87 @@ class Sim:
         self.complete = False
         self.results_ready = False
         self._orig_pars = None
+        self._build_plan()
         return self
+
+    # ---- the fused day pipeline (cvb_run_days) ---------------------------------------------------------------------------
+    def _build_plan(self):
+        '''
+        Decide which days can run without the host (reference sim.py:558-685 needs the host only where Python decides something):
+        register the built-in interventions that run inside the fused kernels with the handle and collect the days on which
+        some intervention / variant needs its apply().  ``self._plan`` is None when no day can be fused.
+        '''
+        self._plan = None
+        self.fused_days = 0
+        pars = self.pars
+        if not self.fused or self.rng_mode != 'philox' or self._comm is not None or self.n % 4 != 0 or self._handle is None:
+            return
+        host_days, test, trace = set(), None, None
+        for iv in pars['interventions']:
+            plan = iv._device_plan(self) if hasattr(iv, '_device_plan') else None
+            if plan is None:
+                return                                   # a plug-in that must be called every day
+            if plan[0] == 'host':
+                host_days.update(int(d) for d in plan[1])
+            elif plan[0] == 'test':
+                if test is not None or trace is not None:
+                    return                               # one test_prob, applied before tracing
+                test = plan
+            elif plan[0] == 'trace':
+                if trace is not None:
+                    return
+                trace = plan
+        for v in pars['variants']:
+            host_days.update(int(d) for d in np.atleast_1d(v.days))
+        lkeys = self.people.layer_keys()
+        regen = 0
+        from .base import Layer
+        for i, lk in enumerate(lkeys):
+            if pars['dynam_layer'].get(lk):
+                if type(self.people.contacts[lk]).update is not Layer.update:
+                    return                               # a user-defined Layer.update runs on the host
+                regen |= 1 << i
+        if trace is not None:
+            traced = [i for i, lk in enumerate(lkeys) if trace[1].trace_prob[i] > 0 and len(self.people.contacts[lk]) > 0]
+            if any(pars['dynam_layer'].get(lkeys[i]) for i in traced) or (traced and not self.use_adjacency):
+                return                                   # tracing over a streamed layer keeps the per-step path
+        h = self._handle
+        _capi.call('cvb_plan_clear', h)
+        if test is not None:
+            _capi.call('cvb_plan_test_prob', h, C.byref(test[1]), test[2], test[3])
+        if trace is not None:
+            _capi.call('cvb_plan_contact_tracing', h, C.byref(trace[1]), trace[2], trace[3])
+        _capi.call('cvb_plan_dynamic_layers', h, regen)
+        self._plan = dict(host_days=host_days)
+
+    def _fusable_day(self, t):
+        ''' True if day t needs no host decision: no intervention / variant acts through Python, no importations, no rescaling '''
+        plan, pars = self._plan, self.pars
+        if plan is None or t in plan['host_days'] or pars['n_imports'] or self.kernel_timers is not None:
+            return False
+        if pars['rescale'] and self.rescale_vec[t] < pars['pop_scale']:
+            return False
+        return True
+
+    def _run_block(self, t0, t1):
+        ''' Days [t0, t1) in one C-ABI call '''
+        if torch.cuda.current_device() != self.device.index:
+            torch.cuda.set_device(self.device)
+        self._push_pars()
+        if self._adj_dirty:
+            self._build_adjacency()
+        _capi.call('cvb_run_days', self._handle, int(t0), int(t1), self._stream_ptr)
+        self.fused_days += t1 - t0
+        self.people.t = t1 - 1
+        self.t = t1
+        if self.t == self.npts:
+            self.complete = True
+
+    def check_packed_state(self):
+        ''' Verification hook: the library's packed per-agent state word against the People arrays; returns (inexpressible, mismatches, examples) '''
+        out = np.zeros(26, dtype=np.int64)
+        _capi.call('cvb_state_check', self._handle, int(self.t) - 1, out.ctypes.data, self._stream_ptr)
+        return int(out[0]), int(out[1]), out[2:].reshape(8, 3)
 
     def _validate_pars(self):
         pars = self.pars
@@ -569,6 +654,8 @@ class Sim:
             if hasattr(iv, 'finalized'):
                 iv.finalized = False
         _capi.call('cvb_reset', self._handle, self._stream_ptr)
+        _capi.call('cvb_state_invalidate', self._handle)
+        self.fused_days = 0
         self._host_adds = {k: v.copy() for k, v in snap['host_adds'].items()}
         seed, np_state, nb_state = snap['rng']
         self.rng.seed = seed
@@ -718,6 +805,16 @@ class Sim:
         t, pars, people, h, st = self.t, self.pars, self.people, self._handle, self._stream_ptr
         if torch.cuda.current_device() != self.device.index:      # ensembles keep members on several GPUs in one process
             torch.cuda.set_device(self.device)
+        if self._fusable_day(t):                                   # nothing for the host to decide today: the fused day kernels
+            people.t = t
+            self.rescale()
+            self._run_block(t, t + 1)
+            if pars['analyzers']:
+                for an in pars['analyzers']:
+                    an(self)
+                _capi.call('cvb_state_invalidate', h)              # an analyzer may have written People arrays
+            return
+        _capi.call('cvb_state_invalidate', h)                      # Python (interventions, rescaling) may write People arrays today
         people.t = t
         call = _capi.call if self.kernel_timers is None else self._timed_call
         self.rescale()
@@ -806,10 +903,17 @@ class Sim:
             raise AlreadyRunError(f'Simulation is currently at t={self.t}, requested to run until t={until} which has already been reached')
         if self.complete:
             raise AlreadyRunError('Simulation is already complete (call sim.initialize() to re-run)')
+        _capi.call('cvb_state_invalidate', self._handle)          # the caller may have written People arrays since the last run
         while self.t < until:
             if self.pars['stopping_func'] and self.pars['stopping_func'](self):
                 return self
-            self.step()
+            if self.rng_mode == 'philox' and not self.pars['analyzers'] and not self.pars['stopping_func'] and self._fusable_day(self.t):
+                t1 = self.t + 1                                    # as many days as need no host decision, in ONE C-ABI call
+                while t1 < until and self._fusable_day(t1):
+                    t1 += 1
+                self._run_block(self.t, t1)
+            else:
+                self.step()
         if self.complete:
             self.finalize(restore_pars=restore_pars)
         return self

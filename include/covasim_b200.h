@@ -257,6 +257,37 @@ int cvb_vaccinate_prob(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* host_par
 /* base.py:1849-1876 Layer.update with frac=1: regenerate every edge of a dynamic layer on the device */
 int cvb_layer_regenerate(cvb_sim* s, int32_t layer, int32_t t, cvb_stream st);
 
+/* ------------------------------------------------------------------------------------------------
+ * Whole blocks of days without returning to the host (sim.py:688-761 Sim.run -> sim.py:558-685 Sim.step).
+ * The built-in interventions that need no host decision are registered once (the "day plan"); cvb_run_days then runs
+ * days [t0, t1) as five launches per day: (stocks + update_nab of day t-1, update_states_pre + check_immunity, test_prob,
+ * case selection) -> contact tracing over the cases' adjacency rows -> (update_states_post + transmission records) ->
+ * transmission -> infect.  Results are identical to calling the per-step entry points above day by day.
+ * A packed per-agent state word (library-owned) is kept in step with the People flag arrays by these kernels; it is rebuilt
+ * from the arrays on the first cvb_run_days after any other entry point, or after cvb_state_invalidate (call it when the host
+ * wrote People arrays itself).
+ * ---------------------------------------------------------------------------------------------- */
+int cvb_plan_clear(cvb_sim* s);
+/* interventions.py:857-981 test_prob active on days [start_day, end_day] (end_day < 0: to the end); no per-agent overrides */
+int cvb_plan_test_prob(cvb_sim* s, const cvb_test_prob_pars* host_pars, int32_t start_day, int32_t end_day);
+/* interventions.py:984-1145 contact_tracing on days [start_day, end_day]; applied after the plan's test_prob; every traced
+ * layer must be covered by the adjacency; not presumptive, no capacity */
+int cvb_plan_contact_tracing(cvb_sim* s, const cvb_trace_pars* host_pars, int32_t start_day, int32_t end_day);
+/* people.py:199-206 update_contacts: the dynamic layers (bit l = layer l) regenerated at the start of every day */
+int cvb_plan_dynamic_layers(cvb_sim* s, uint32_t layer_mask);
+int cvb_run_days(cvb_sim* s, int32_t t0, int32_t t1, cvb_stream st);
+int cvb_state_invalidate(cvb_sim* s);
+/* Per-kernel timing of cvb_run_days (CUDA events around every launch; off by default).  cvb_timing_read synchronises, returns
+ * the milliseconds and launch counts accumulated since the last read, per kernel kind, and resets them */
+enum cvb_timed { CVB_TIMED_day_begin = 0, CVB_TIMED_trace, CVB_TIMED_day_mid, CVB_TIMED_edge_pass, CVB_TIMED_infect, CVB_TIMED_day_end,
+                 CVB_TIMED_regen, CVB_N_TIMED };
+int cvb_timing_enable(cvb_sim* s, int32_t on);
+int cvb_timing_read(cvb_sim* s, double* host_ms, int64_t* host_launches);
+/* Verification: recompute every agent's state word from the People arrays (t_done = last completed day) and compare with the
+ * stored one.  host int64[26] = {agents the word cannot express, agents that differ, then up to 8 x (agent, stored, recomputed)};
+ * synchronises */
+int cvb_state_check(cvb_sim* s, int32_t t_done, int64_t* host_out26, cvb_stream st);
+
 #ifdef __cplusplus
 }
 #endif

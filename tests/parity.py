@@ -87,17 +87,27 @@ def compare_log(sim, orc):
     assert np.array_equal(log['source'], src[order])
 
 
+def check_packed_state(sim, where=''):
+    ''' After a day that went through the fused kernels: the library's packed state words must equal what the People arrays say '''
+    bad, diff, examples = sim.check_packed_state()
+    assert bad == 0 and diff == 0, (f'packed state words differ from the People arrays {where}: {diff} agents (inexpressible: {bad}); '
+                                    f'(agent, stored, recomputed) = {[(int(a), hex(int(b) & 0xFFFFFFFF), hex(int(c) & 0xFFFFFFFF)) for a, b, c in examples[:min(diff, 8)]]}')
+
+
 def run_lockstep(sim, orc, every=1):
     compare_people(sim, orc, 'after initialize')
     sim.set_seed()
     orc.rng.set_seed(orc.pars['rand_seed'])
     while not sim.complete:
         t = sim.t
+        fused_before = getattr(sim, 'fused_days', 0)
         sim.step()
         orc.step()
         if t % every == 0 or sim.complete:
             compare_people(sim, orc, f'after day {t}')
             compare_layers(sim, orc, f'after day {t}')
+            if getattr(sim, 'fused_days', 0) > fused_before and not sim.pars['analyzers']:
+                check_packed_state(sim, f'after day {t}')
     sim.finalize()
     orc.finalize()
     compare_results(sim, orc)

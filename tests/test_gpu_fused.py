@@ -1,0 +1,94 @@
+'''
+The fused day pipeline (covasim_b200/csrc/day_fused.cu, cvb_run_days): whole blocks of days in one C-ABI call -- five launches per
+day, a packed per-agent state word instead of sixteen flag arrays -- against the oracle (Philox mode) and against the per-step
+entry points.  Bit-exact for flags / dates / counters / infection log; 1e-6 relative for NAb and immunity floats.
+'''
+import numpy as np
+import pytest
+
+import parity
+import scenarios
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def cv():
+    import covasim_b200
+    return covasim_b200
+
+
+# scenario -> at least this share of the days must have gone through cvb_run_days
+BLOCK_SCENARIOS = {'random2k_nowaning': 1.0, 'default20k': 1.0, 'dynamic2k': 1.0, 'hybrid3k': 0.85, 'baseline20k': 0.9, 'variants4k': 0.0,
+                   'sequence3k': 0.0, 'clip3k': 0.9, 'fracsus2k': 1.0}
+
+
+@pytest.mark.parametrize('name', sorted(BLOCK_SCENARIOS))
+def test_run_in_blocks_matches_oracle(cv, name):
+    ''' sim.run(): every stretch of days without a host decision is ONE cvb_run_days call; People arrays, results and log vs the oracle '''
+    sim, orc = parity.build_pair(cv, name)
+    sim.run()
+    orc.run()
+    assert sim.fused_days >= BLOCK_SCENARIOS[name] * sim.npts - 1e-9, f'only {sim.fused_days} of {sim.npts} days were fused'
+    parity.compare_people(sim, orc, 'at the end')
+    parity.compare_results(sim, orc)
+    parity.compare_log(sim, orc)
+
+
+C2_SMALL = dict(
+    # the BASELINE C2 recipe (bench.py) at 40k agents: test_prob + contact_tracing with their defaults, all four hybrid layers
+    pars=dict(pop_size=40000, pop_type='hybrid', n_days=70, pop_infected=200, rand_seed=1, verbose=0),
+    interventions=[('test_prob', dict(symp_prob=0.1, asymp_prob=0.01, start_day=20)), ('contact_tracing', dict(trace_probs=0.3, start_day=30))])
+
+
+def test_blocks_of_seven_days_with_state_checks(cv):
+    ''' run(until=...) in weekly blocks: People arrays against the oracle and the packed state words against the arrays at every boundary '''
+    sim, orc = parity.build_pair(cv, spec=C2_SMALL)
+    sim.set_seed()
+    orc.rng.set_seed(orc.pars['rand_seed'])
+    first = True
+    while sim.t < sim.npts:
+        until = min(sim.t + 7, sim.npts)
+        sim.run(until=until, reset_seed=first)
+        first = False
+        while orc.t < until:
+            orc.step()
+        if not sim.complete:
+            parity.compare_people(sim, orc, f'after day {until - 1}')
+            parity.check_packed_state(sim, f'after day {until - 1}')
+    orc.finalize()
+    assert sim.fused_days == sim.npts
+    parity.compare_people(sim, orc, 'at the end')
+    parity.compare_results(sim, orc)
+    parity.compare_log(sim, orc)
+
+
+def test_fused_equals_per_step(cv):
+    ''' The same sim through cvb_run_days and through the per-step entry points: every People array and result series identical '''
+    a = cv.Sim(**scenarios.build(cv, C2_SMALL), fused=True).run()
+    b = cv.Sim(**scenarios.build(cv, C2_SMALL), fused=False).run()
+    assert a.fused_days == a.npts and b.fused_days == 0
+    for k in a.people.keys():
+        x, y = a.people.to_numpy(k), b.people.to_numpy(k)
+        assert np.array_equal(x, y, equal_nan=(x.dtype.kind == 'f')), k
+    for k in a.result_keys():
+        assert np.array_equal(a.results[k].values, b.results[k].values, equal_nan=True), k
+    la, lb = a.infection_log, b.infection_log
+    for k in la:
+        assert np.array_equal(la[k], lb[k]), k
+
+
+def test_host_writes_between_runs_are_seen(cv):
+    ''' People arrays written from Python between two run() calls: the packed state is rebuilt (same as the per-step path) '''
+    def go(fused):
+        sim = cv.Sim(**scenarios.build(cv, scenarios.SCENARIOS['random2k_nowaning']), fused=fused)
+        sim.run(until=10)
+        sim.people.quarantined[100:140] = True                      # a user puts forty people into quarantine by hand
+        sim.people.date_end_quarantine[100:140] = 15.0
+        sim.run()
+        return sim
+    a, b = go(True), go(False)
+    assert a.fused_days == a.npts
+    for k in ('n_quarantined', 'new_infections', 'n_exposed', 'cum_deaths'):
+        assert np.array_equal(a.results[k].values, b.results[k].values), k
+    assert a.results['n_quarantined'].values[10] >= 40

@@ -20,10 +20,14 @@ def cv():
 
 
 @pytest.mark.parametrize('name', ['random2k_nowaning', 'dynamic2k', 'hybrid3k', 'variants4k', 'dynpars3k', 'clip3k', 'rescale3k', 'fracsus2k', 'sequence3k', 'testnum3k', 'testnum_rescale2k', 'subtarget3k', 'ili3k', 'capacity3k'])
-def test_lockstep_parity(cv, name):
-    sim, orc = parity.build_pair(cv, name)
+@pytest.mark.parametrize('fused', [True, False])
+def test_lockstep_parity(cv, name, fused):
+    ''' fused=True: days without a host decision go through cvb_run_days (day_fused.cu); False: the per-step entry points every day '''
+    sim, orc = parity.build_pair(cv, name, sim_kwargs=dict(fused=fused))
     parity.run_lockstep(sim, orc)
     assert sim.summary['cum_infections'] > scenarios.SCENARIOS[name]['pars']['pop_infected']     # the epidemic actually ran
+    if not fused:
+        assert sim.fused_days == 0
 
 
 ODD_SPEC = dict(

@@ -10,12 +10,12 @@ cv.contact_tracing(trace_probs=0.3, start_day=30), 0.5 % initially infected, syn
 
 One "step" = one complete run of that sim (181 simulated days of the hot path).
   value : agent-days/s with the initial People + Layer arrays already resident in HBM; timed on the
-          device with CUDA events around the 181 Sim.step() calls.
+          device with CUDA events around the day loop of Sim.run() (181 days = one cvb_run_days call).
   e2e   : the same through the public API with HOST buffers inside the timed region: Sim.restore()
           (H2D of every People array and edge list from pinned memory) + Sim.run() (181 days +
           finalize(), which reads the result tables back to the host).
-  roofline : the dominant kernel of the step (by CUDA-event time measured live around every C-ABI call of the
-          timed steps): algorithmic bytes per launch / mean launch duration vs the measured HBM peak.  "kernels"
+  roofline : the dominant kernel of the step (by CUDA-event time measured live around every launch of the day
+          loop, in a separate pass): algorithmic bytes per launch / mean launch duration vs the measured HBM peak.  "kernels"
           lists the same for every kernel of the day; "edge_pass_dense" times the dense edge-streaming pass
           (12*E + 8*N bytes per launch, the form dynamic layers use) on its own with L2 flushed between launches.
   cpu_baseline : the oracle (NumPy port of the reference algorithm) continuing the SAME sim from the GPU's
@@ -180,15 +180,19 @@ def run_b200(args):
         return float(t.item())
 
     # ---- value: device-resident inputs, CUDA events around the day loop --------------------------------
+    # The day loop is what Sim.run() executes (Sim._advance): every stretch of days that needs no host decision is ONE
+    # cvb_run_days call -- in this workload all 181 days.
+    def run_days():
+        sim.set_seed()
+        sim._advance(sim.npts)
+
     for _ in range(args.warmup):
         reset_on_device()
-        while not sim.complete:
-            sim.step()
+        run_days()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = cv._capi.lib.cvb_launch_count()
-    sim.kernel_timers = {}
     dev_ms = 0.0
     barrier()
     for _ in range(args.steps):
@@ -196,54 +200,63 @@ def run_b200(args):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        while not sim.complete:
-            sim.step()
+        run_days()
         b.record()
         barrier()
         dev_ms += max_over_ranks(a.elapsed_time(b))
-    launches = cv._capi.lib.cvb_launch_count() - launches0
-    timers, sim.kernel_timers = sim.kernel_timers, None
+    launches = cv._capi.lib.cvb_launch_count() - launches0          # every kernel launched inside the timed region (all steps)
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = dev_ms / args.steps
     value = n_gpus * agent_days / (ms_per_step / 1e3)
+    fused_days = sim.fused_days
 
-    # per-kernel device time from the CUDA events recorded around every C-ABI call of the timed steps
-    kernel_ms = {name: float(np.sum([x.elapsed_time(y) for x, y in evs])) / args.steps for name, evs in timers.items()}
-    n_calls = {name: len(evs) / max(args.steps, 1) for name, evs in timers.items()}
+    # per-kernel device time: the same day loop once more with CUDA events around every launch (outside the timed region: the
+    # events serialise the launches; the shares are what the ncu launch list must agree with)
     peak, peak_src = measured_peak_gbs()
-    work = sim.edge_work()                                   # per day: adjacency entries visited, transmitters (last timed step)
     nv, L = sim['n_variants'], len(n_edges)
-    # ALGORITHMIC bytes per launch: every array a kernel must read or write, once
-    algo = {
-        'cvb_update_states_pre': (9 + 16 + 12 * nv) * N,      # 9 flags + date_recovered, date_end_isolation, nab, recovered_variant; writes 3 x nv protections
-        'cvb_post_and_prepare': (8 + 28 + 16) * N + N // 8,     # 8 flags + 7 float32 fields; writes one 16-byte agent record + transmit bitmap
-        'cvb_update_nab_count': (13 + 12 + 2 * nv + 8 * nv) * N,
-        'cvb_infect_winners': None,
-        'cvb_edge_pass': float(24 * work[:, 0].sum() + 28 * work[:, 1].sum()) / max(npts, 1) if sim._adj is not None else 12 * E + 8 * N,
-    }
-    kernels = {}
-    for name, ms in kernel_ms.items():
-        us = 1e3 * ms / max(n_calls[name], 1)
-        entry = dict(us_per_launch=us, launches_per_step=n_calls[name], ms_per_step=ms, share_of_step=ms / ms_per_step if ms_per_step else None)
-        if algo.get(name):
-            entry['algorithmic_bytes_per_launch'] = algo[name]
-            entry['achieved_gbs'] = algo[name] / (us * 1e-6) / 1e9 if us > 0 else 0.0
-            entry['frac'] = entry['achieved_gbs'] / peak
-        kernels[name] = entry
-    dominant = max((k for k in kernels if 'frac' in kernels[k]), key=lambda k: kernels[k]['ms_per_step'])
-    traffic = None
-    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(dominant)
-        except Exception:
-            traffic = None
-    dk = kernels[dominant]
-    roofline = dict(bound='hbm', kernel=dominant, achieved=dk['achieved_gbs'], peak=peak, unit='GB/s', frac=dk['frac'], traffic=traffic,
-                    algorithmic_bytes_per_launch=dk['algorithmic_bytes_per_launch'], us_per_launch=dk['us_per_launch'], peak_source=peak_src,
-                    share_of_step=dk['share_of_step'],
-                    note='dominant kernel of the step by CUDA-event time; all kernels are listed under "kernels", and the dense edge-streaming '
-                         'pass (12*E + 8*N bytes per launch) is measured separately under "edge_pass_dense"')
+    kernels, roofline = {}, None
+    if fused_days == sim.npts:
+        reset_on_device()
+        sim.fused_timing(True)
+        run_days()
+        timing = sim.fused_timing()
+        sim.fused_timing(False)
+        work = sim.edge_work()                               # per day: adjacency entries visited, transmitters
+        total_timed = sum(ms for ms, _ in timing.values())
+        # ALGORITHMIC bytes per launch.  The per-agent passes read the 4-byte packed state word of every
+        # agent and touch the float arrays only where the word says so; the bound used here is the one SURVEY section 8(d) gives
+        # for the agent state pass -- every array the unfused kernels must read or write, once -- so the figures are comparable
+        # with round 1 (the fused kernels move fewer bytes than that; `traffic` is what ncu measured).
+        algo = {
+            'day_begin': (13 + 12 + 2 * nv + 8 * nv) * N + (9 + 16 + 12 * nv) * N + 11 * N + 4 * N,   # update_nab + counts, update_states_pre + check_immunity, test_prob, case selection
+            'day_mid': (8 + 28 + 16) * N + N // 8,
+            'edge_pass': float(24 * work[:, 0].sum() + 32 * work[:, 1].sum()) / max(npts, 1) if sim._adj is not None else 12 * E + 8 * N,
+        }
+        for name, (ms, cnt) in timing.items():
+            if not cnt:
+                continue
+            us = 1e3 * ms / cnt
+            entry = dict(us_per_launch=us, launches_per_step=cnt, ms_per_step=ms, share_of_step=ms / total_timed if total_timed else None)
+            if algo.get(name):
+                entry['algorithmic_bytes_per_launch'] = algo[name]
+                entry['achieved_gbs'] = algo[name] / (us * 1e-6) / 1e9 if us > 0 else 0.0
+                entry['frac'] = entry['achieved_gbs'] / peak
+            kernels[name] = entry
+        dominant = max((k for k in kernels if 'frac' in kernels[k]), key=lambda k: kernels[k]['ms_per_step'])
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(dominant)
+            except Exception:
+                traffic = None
+        dk = kernels[dominant]
+        roofline = dict(bound='hbm', kernel=dominant, achieved=dk['achieved_gbs'], peak=peak, unit='GB/s', frac=dk['frac'], traffic=traffic,
+                        algorithmic_bytes_per_launch=dk['algorithmic_bytes_per_launch'], us_per_launch=dk['us_per_launch'], peak_source=peak_src,
+                        share_of_step=dk['share_of_step'],
+                        note='dominant kernel of the day by CUDA-event time (events around every launch of cvb_run_days, in a separate pass); all kernels '
+                             'are listed under "kernels", and the dense edge-streaming pass (12*E + 8*N bytes per launch) is measured separately under '
+                             '"edge_pass_dense"')
 
     # ---- the dense edge-streaming pass on its own (what dynamic layers use, and the survey's 12*E + 8*N figure) ----
     edge_dense = measure_dense_edge_pass(args, cv, sim, snap, peak, E, N) if (rank == 0 and not args.no_dense) else None
@@ -277,6 +290,7 @@ def run_b200(args):
                    clocks=clocks,
                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=sim.h2d_bytes(snap), d2h_bytes_per_step=sim.d2h_bytes(), ms_per_step=1e3 * e2e_s / args.steps),
                    gpu_launches=int(launches), roofline=roofline, kernels=kernels, edge_pass_dense=edge_dense, us_per_day=1e3 * ms_per_step / npts,
+                   fused_days=int(fused_days),
                    epidemic=summary)
         if cpu is not None:
             out['cpu_baseline'] = cpu

@@ -143,7 +143,7 @@ int cvb_destroy(cvb_sim* s) {
     cudaFree(s->n_cases); cudaFree(s->dev_scalars); cudaFree(s->rec_store); cudaFree(s->ts8_store);
     cudaFree(s->nab_kin); cudaFree(s->tile_cnt); cudaFree(s->hit_mask); cudaFree(s->flag_tmp); cudaFree(s->partial);
     cudaFree(s->glist); cudaFree(s->n_glist); cudaFree(s->hit_src); cudaFree(s->hit_key); cudaFree(s->part_flags);
-    cudaFree(s->state); cudaFree(s->trans_ent); cudaFree(s->case_ent);
+    cudaFree(s->state); cudaFree(s->trans_ent); cudaFree(s->case_ent); cudaFree(s->stock_base);
     delete s->plan;
     cvb_timing_enable(s, 0);
     if (s->host_scalars) cudaFreeHost(s->host_scalars);
@@ -154,6 +154,7 @@ int cvb_destroy(cvb_sim* s) {
 int cvb_reset(cvb_sim* s, cvb_stream st_) {
     CVB_REQUIRE(s, "cvb_reset: NULL handle");
     cudaStream_t st = (cudaStream_t)st_;
+    s->state_valid = 0;
     CVB_CHECK(cudaMemsetAsync(s->infect_key, 0xFF, (size_t)s->n * sizeof(unsigned long long), st));
     CVB_CHECK(cudaMemsetAsync(s->n_cand, 0, 64, st));
     CVB_CHECK(cudaMemsetAsync(s->n_cases, 0, 64, st));

@@ -122,6 +122,7 @@ struct cvb_sim {
     uint32_t* state; int32_t state_valid;
     uint4* trans_ent;                               // [N][2] today's transmitters {agent, row length, row begin, rel_trans, code}
     uint4* case_ent;                                // [N] today's traced cases {agent, row length, row begin}
+    unsigned long long* stock_base;                 // absolute stock counts of the packed words after a pack (counter-row layout)
     cvb::DayPlan* plan;                             // built-in interventions the C day loop runs itself (cvb_plan_*)
     cvb::FusedTiming* timing;                       // per-kernel CUDA-event timing of the day loop, when enabled
 };
@@ -258,6 +259,70 @@ __device__ __forceinline__ void reduce_counters(const int (&c)[NK], int* s_cnt) 
     }
 }
 
+
+// ---- the packed state word ----------------------------------------------------------------------------------------------------
+// bits 0-15: the bool states in the order of defaults.states (== CVB_F_susceptible + bit)
+enum : uint32_t {
+    SB_SUS = 1u << 0, SB_NAIVE = 1u << 1, SB_EXP = 1u << 2, SB_INF = 1u << 3, SB_SYMP = 1u << 4, SB_SEV = 1u << 5, SB_CRIT = 1u << 6,
+    SB_TESTED = 1u << 7, SB_DIAG = 1u << 8, SB_REC = 1u << 9, SB_KDEAD = 1u << 10, SB_DEAD = 1u << 11, SB_KCONTACT = 1u << 12,
+    SB_QUAR = 1u << 13, SB_ISO = 1u << 14, SB_VACC = 1u << 15,
+    SB_HAS_NAB = 1u << 16,      // peak_nab != 0 (update_nab / check_immunity have work to do)
+    SB_IMM_NZ = 1u << 17,       // some sus_imm / symp_imm / sev_imm entry of the agent may be non-zero
+    SB_QPEND = 1u << 18,        // a quarantine request is waiting in the pending ring
+    SB_DPEND = 1u << 19,        // date_diagnosed is set and the agent is not (yet) diagnosed
+    SB_RS_VALID = 1u << 20,     // the stored agent record has the simple form {0, rel_sus or 0, 0, quarantine bit} ...
+    SB_RS_SUS = 1u << 21,       // ... written with this susceptible flag
+    SB_RS_QUAR = 1u << 22,      // ... and this quarantined flag
+    SB_IBV = 1u << 23,          // infectious_by_variant[EBV - 1] is set
+};
+constexpr int kEbvShift = 24;   // bits 24-27: variant + 1 of the set exposed_by_variant row (0: none)
+constexpr int kRvShift = 28;    // bits 28-31: recovered_variant + 1 while t >= date_recovered (the natural-immunity source), else 0
+__device__ __forceinline__ int sb_ebv(uint32_t s) { return (int)((s >> kEbvShift) & 15u); }
+__device__ __forceinline__ int sb_rv(uint32_t s) { return (int)((s >> kRvShift) & 15u); }
+constexpr uint32_t kEbvMask = 15u << kEbvShift, kRvMask = 15u << kRvShift;
+
+// ---- stock counters as running totals ---------------------------------------------------------------------------------------
+// The unfused path counts every state flag of every agent at the end of every day (sim.py:652-664).  Here the stock columns of the
+// day's counter row start as a copy of the previous day's (added by day_begin_kernel) and every kernel that changes a state word
+// adds the difference: a handful of shared-memory atomics for the few agents whose state changed, instead of 13 counts over all.
+constexpr uint32_t kStockMask = SB_SUS | SB_EXP | SB_INF | SB_SYMP | SB_SEV | SB_CRIT | SB_DIAG | SB_REC | SB_KDEAD | SB_DEAD | SB_QUAR | SB_ISO | SB_VACC;
+constexpr int kStockSlots = 16 + 1 + 2 * CVB_MAX_VARIANTS;      // 16 state bits, alive, exposed / infectious by variant
+
+__device__ __forceinline__ void stock_delta(uint32_t o, uint32_t s, int* __restrict__ s_delta) {
+    const uint32_t ch = (o ^ s) & (kStockMask | kEbvMask | SB_IBV);
+    if (!ch) return;
+    uint32_t fb = ch & kStockMask;
+    while (fb) {
+        const int b = __ffs(fb) - 1;
+        fb &= fb - 1;
+        atomicAdd(&s_delta[b], ((s >> b) & 1u) ? 1 : -1);
+    }
+    if (ch & SB_DEAD) atomicAdd(&s_delta[16], (s & SB_DEAD) ? -1 : 1);
+    if (ch & (kEbvMask | SB_IBV)) {
+        const int eo = sb_ebv(o), en = sb_ebv(s);
+        if (eo) { atomicAdd(&s_delta[17 + 2 * (eo - 1)], -1); if (o & SB_IBV) atomicAdd(&s_delta[18 + 2 * (eo - 1)], -1); }
+        if (en) { atomicAdd(&s_delta[17 + 2 * (en - 1)], 1); if (s & SB_IBV) atomicAdd(&s_delta[18 + 2 * (en - 1)], 1); }
+    }
+}
+// where stock slot k lives in a day's counter rows (NULL: not a result stock)
+__device__ __forceinline__ unsigned long long* stock_slot(unsigned long long* row, unsigned long long* vrow, int nv, int k) {
+    // state bit -> stock counter (defaults.result_stocks order: susceptible, exposed, infectious, symptomatic, severe, critical,
+    // recovered, dead, diagnosed, known_dead, quarantined, isolated, vaccinated)
+    // {0, -, 1, 2, 3, 4, 5, -, 8, 6, 9, 7, -, 10, 11, 12} as sixteen nibbles (15 = not a stock), bit 0 in the lowest
+    if (k < 16) {
+        const int st = (int)((0xCBAF7968F54321F0ull >> (4 * k)) & 15ull);
+        return st != 15 ? row + CVB_C_n_susceptible + st : nullptr;
+    }
+    if (k == 16) return row + CVB_C_n_alive_agents;
+    const int q = k - 17, var = q >> 1;
+    return var < nv ? vrow + (int64_t)var * CVB_N_VCOUNTERS + ((q & 1) ? CVB_VC_n_infectious_by_variant : CVB_VC_n_exposed_by_variant) : nullptr;
+}
+__device__ __forceinline__ void flush_stock_delta(const int* s_delta, unsigned long long* row, unsigned long long* vrow, int nv) {
+    if (threadIdx.x < kStockSlots && s_delta[threadIdx.x]) {
+        unsigned long long* p = stock_slot(row, vrow, nv, threadIdx.x);
+        if (p) atomicAdd(p, (unsigned long long)(long long)s_delta[threadIdx.x]);      // two's complement: negative differences wrap correctly
+    }
+}
 
 // 128-bit streaming loads that do not allocate in L1 (edge arrays are read exactly once per pass)
 __device__ __forceinline__ int4 ld_stream(const int4* p) {

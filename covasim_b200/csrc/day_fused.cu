@@ -26,27 +26,6 @@
 
 namespace cvb {
 
-// ---- the packed state word ----------------------------------------------------------------------------------------------------
-// bits 0-15: the bool states in the order of defaults.states (== CVB_F_susceptible + bit)
-enum : uint32_t {
-    SB_SUS = 1u << 0, SB_NAIVE = 1u << 1, SB_EXP = 1u << 2, SB_INF = 1u << 3, SB_SYMP = 1u << 4, SB_SEV = 1u << 5, SB_CRIT = 1u << 6,
-    SB_TESTED = 1u << 7, SB_DIAG = 1u << 8, SB_REC = 1u << 9, SB_KDEAD = 1u << 10, SB_DEAD = 1u << 11, SB_KCONTACT = 1u << 12,
-    SB_QUAR = 1u << 13, SB_ISO = 1u << 14, SB_VACC = 1u << 15,
-    SB_HAS_NAB = 1u << 16,      // peak_nab != 0 (update_nab / check_immunity have work to do)
-    SB_IMM_NZ = 1u << 17,       // some sus_imm / symp_imm / sev_imm entry of the agent may be non-zero
-    SB_QPEND = 1u << 18,        // a quarantine request is waiting in the pending ring
-    SB_DPEND = 1u << 19,        // date_diagnosed is set and the agent is not (yet) diagnosed
-    SB_RS_VALID = 1u << 20,     // the stored agent record has the simple form {0, rel_sus or 0, 0, quarantine bit} ...
-    SB_RS_SUS = 1u << 21,       // ... written with this susceptible flag
-    SB_RS_QUAR = 1u << 22,      // ... and this quarantined flag
-    SB_IBV = 1u << 23,          // infectious_by_variant[EBV - 1] is set
-};
-constexpr int kEbvShift = 24;   // bits 24-27: variant + 1 of the set exposed_by_variant row (0: none)
-constexpr int kRvShift = 28;    // bits 28-31: recovered_variant + 1 while t >= date_recovered (the natural-immunity source), else 0
-__host__ __device__ __forceinline__ int sb_ebv(uint32_t s) { return (int)((s >> kEbvShift) & 15u); }
-__host__ __device__ __forceinline__ int sb_rv(uint32_t s) { return (int)((s >> kRvShift) & 15u); }
-constexpr uint32_t kEbvMask = 15u << kEbvShift, kRvMask = 15u << kRvShift;
-
 // Rebuild the word of every agent from the public arrays; t_done = the last completed day.  viol counts agents the word cannot
 // express (more than one by-variant row set, a by-variant row that disagrees with exposed_variant, antibodies without a peak)
 __global__ void __launch_bounds__(kThreads) pack_state_kernel(PeoplePtrs P, uint32_t* __restrict__ S, const uint32_t* __restrict__ S_old,
@@ -94,19 +73,45 @@ __global__ void __launch_bounds__(kThreads) pack_state_kernel(PeoplePtrs P, uint
     }
 }
 
+// absolute stock counts of the packed words (the base of the first fused day): one launch after pack_state_kernel
+__global__ void __launch_bounds__(kThreads) count_state_kernel(const uint32_t* __restrict__ S, int64_t n, int32_t nv,
+                                                               unsigned long long* __restrict__ row, unsigned long long* __restrict__ vrow) {
+    __shared__ int s_cnt[kStockSlots];
+    if (threadIdx.x < kStockSlots) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t n_pad = (n + 31) / 32 * 32;
+    int c[17];
+#pragma unroll
+    for (int k = 0; k < 17; ++k) c[k] = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_pad; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = i < n ? S[i] : SB_DEAD;
+#pragma unroll
+        for (int b = 0; b < 16; ++b) c[b] += __popc(__ballot_sync(0xFFFFFFFFu, i < n && ((s >> b) & 1u)));
+        c[16] += __popc(__ballot_sync(0xFFFFFFFFu, !(s & SB_DEAD)));
+        const int e = i < n ? sb_ebv(s) : 0;
+        if (e) { atomicAdd(&s_cnt[17 + 2 * (e - 1)], 1); if (s & SB_IBV) atomicAdd(&s_cnt[18 + 2 * (e - 1)], 1); }
+    }
+    if (lane_id() == 0) {
+#pragma unroll
+        for (int k = 0; k < 17; ++k) if (c[k]) atomicAdd(&s_cnt[k], c[k]);
+    }
+    __syncthreads();
+    flush_stock_delta(s_cnt, row, vrow, nv);
+}
+
 // ================================================================================================================================
-// day_begin_kernel
+// day_begin_kernel: one agent per thread, one contiguous chunk of agents per CTA
 // ================================================================================================================================
-enum { F_INFECTIOUS = 0, F_SYMPTOMATIC, F_SEVERE, F_CRITICAL, F_RECOVERIES, F_DEATHS, F_KNOWN_DEATHS, F_BED_SEVERE, F_BED_CRITICAL, F_TESTS, F_NK };
-constexpr int kStockSlots = 16 + 1 + 2 * CVB_MAX_VARIANTS;      // 16 state bits, alive, exposed / infectious by variant
+enum { F_INFECTIOUS = 0, F_SYMPTOMATIC, F_SEVERE, F_CRITICAL, F_RECOVERIES, F_DEATHS, F_KNOWN_DEATHS, F_TESTS, F_NK };
 constexpr int kImmQueueCap2 = 64;
 
 struct DayBeginArgs {
-    int64_t n, id0;
+    int64_t n, id0, chunk;              // chunk: agents per CTA (a multiple of 32)
     int32_t t;                          // the day whose update_states_pre / interventions run; the END part closes day t - 1
     int32_t nv, waning, vaxpars;
     const double* nab_kin; int64_t nab_kin_len;
-    unsigned long long* counters; unsigned long long* vcounters; unsigned long long* beds;
+    unsigned long long* counters; unsigned long long* vcounters;
+    const unsigned long long* base_row; const unsigned long long* base_vrow;    // yesterday's stock counts (PRE: copied into today's row)
     double* partial; unsigned int* ticket; double* sums;       // sums = table base [npts][4]
     unsigned int* n_trans; unsigned int* n_case;
     // test_prob
@@ -118,8 +123,8 @@ struct DayBeginArgs {
 
 // check_immunity for one queued agent x variant (immunity.py:303-350): float64, rounded once to float32.
 // entry = {agent, nab bits, variant | natural-immunity source + 1 << 4 | vaccine source << 8 | vaccinated << 12, -}
-__device__ __forceinline__ void immunity_eval2(const uint4 en, int64_t n, const cvb_pars& pars, float* __restrict__ sus_imm,
-                                               float* __restrict__ symp_imm, float* __restrict__ sev_imm, double& sum_sus, double& sum_symp) {
+__device__ __noinline__ float2 immunity_eval2(const uint4 en, int64_t n, const cvb_pars& pars, float* __restrict__ sus_imm,
+                                              float* __restrict__ symp_imm, float* __restrict__ sev_imm) {
     const int64_t i = (int64_t)en.x;
     const float nab = __uint_as_float(en.y);
     const int v = (int)(en.z & 15u), rvi = (int)((en.z >> 4) & 15u) - 1, vsi = (int)((en.z >> 8) & 15u);
@@ -133,18 +138,14 @@ __device__ __forceinline__ void immunity_eval2(const uint4 en, int64_t n, const 
     sus_imm[(int64_t)v * n + i] = s0;
     symp_imm[(int64_t)v * n + i] = s1;
     sev_imm[(int64_t)v * n + i] = s2;
-    sum_sus += (double)s0;
-    sum_symp += (double)s1;
+    return make_float2(s0, s1);
 }
 
-__device__ __forceinline__ float4 ld4f(const float* p, int64_t i0) { return *reinterpret_cast<const float4*>(p + i0); }
-__device__ __forceinline__ void unpack4(const float4 v, float o[4]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
-
 template <bool END, bool PRE, bool TEST, bool TSEL>
-__global__ void __launch_bounds__(kThreads, 2) day_begin_kernel(PeoplePtrs P, uint32_t* __restrict__ S, const __grid_constant__ cvb_pars pars,
+__global__ void __launch_bounds__(kThreads, 3) day_begin_kernel(PeoplePtrs P, uint32_t* __restrict__ S, const __grid_constant__ cvb_pars pars,
                                                                const __grid_constant__ DayBeginArgs A) {
     __shared__ int s_flow[F_NK + CVB_MAX_VARIANTS];
-    __shared__ int s_stock[kStockSlots];
+    __shared__ int s_delta[kStockSlots];
     __shared__ uint4 s_queue[(kThreads / 32) * kImmQueueCap2];
     __shared__ double s_sum[3][kThreads / 32];
     __shared__ bool s_last;
@@ -159,18 +160,17 @@ __global__ void __launch_bounds__(kThreads, 2) day_begin_kernel(PeoplePtrs P, ui
     const float tf = (float)t;
     const float qnan = nanf32();
     for (int k = threadIdx.x; k < F_NK + CVB_MAX_VARIANTS; k += blockDim.x) s_flow[k] = 0;
-    for (int k = threadIdx.x; k < kStockSlots; k += blockDim.x) s_stock[k] = 0;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && PRE) *A.n_trans = 0;       // today's transmitter list starts empty (filled by day_mid_kernel)
+    for (int k = threadIdx.x; k < kStockSlots; k += blockDim.x) s_delta[k] = 0;
+    if (PRE && blockIdx.x == 0) {
+        if (threadIdx.x == 0) *A.n_trans = 0;                  // today's transmitter list starts empty (filled by day_mid_kernel)
+        if (threadIdx.x < kStockSlots) {                        // today's stock counts start from yesterday's
+            unsigned long long* dst = stock_slot(A.counters + (int64_t)t * CVB_N_COUNTERS, A.vcounters + (int64_t)t * nv * CVB_N_VCOUNTERS, nv, threadIdx.x);
+            const unsigned long long* src = stock_slot(const_cast<unsigned long long*>(A.base_row), const_cast<unsigned long long*>(A.base_vrow), nv, threadIdx.x);
+            if (dst) atomicAdd(dst, *src);
+        }
+    }
     __syncthreads();
-    int c[F_NK];
-#pragma unroll
-    for (int k = 0; k < F_NK; ++k) c[k] = 0;
-    int cvn[CVB_MAX_VARIANTS];
-#pragma unroll
-    for (int k = 0; k < CVB_MAX_VARIANTS; ++k) cvn[k] = 0;
-    int stock[17];                                                        // warp-uniform: state-bit counts + alive
-#pragma unroll
-    for (int k = 0; k < 17; ++k) stock[k] = 0;
+    int c_tests = 0;
     double sum_nab = 0.0, sum_sus = 0.0, sum_symp = 0.0;
 
     uint8_t* exposed = PB(P, exposed); uint8_t* infectious = PB(P, infectious); uint8_t* symptomatic = PB(P, symptomatic);
@@ -184,237 +184,164 @@ __global__ void __launch_bounds__(kThreads, 2) day_begin_kernel(PeoplePtrs P, ui
     float* sus_imm = PF(P, sus_imm); float* symp_imm = PF(P, symp_imm); float* sev_imm = PF(P, sev_imm);
     float* d_tested = PF(P, date_tested); float* d_diag = PF(P, date_diagnosed); float* d_pos = PF(P, date_pos_test);
 
-    // warp-aligned loop: whole warps stay in it (ballots); n is a multiple of 4 (checked by the launcher)
-    const int64_t n_groups = n >> 2;
-    const int64_t n_groups_pad = (n_groups + 31) / 32 * 32;
-    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups_pad; g += (int64_t)gridDim.x * blockDim.x) {
-        const bool in = g < n_groups;
-        const int64_t i0 = g << 2;
-        uint4 sv = make_uint4(0u, 0u, 0u, 0u);
-        if (in) sv = *reinterpret_cast<const uint4*>(S + i0);
-        uint32_t s[4] = {sv.x, sv.y, sv.z, sv.w};
-        const uint32_t any = sv.x | sv.y | sv.z | sv.w;
+    const int64_t lo = (int64_t)blockIdx.x * A.chunk;
+    const int64_t hi = lo + A.chunk < n ? lo + A.chunk : n;
+    const int64_t hi_pad = lo + (hi - lo + 31) / 32 * 32;                    // whole warps stay in the loop (ballots)
+    for (int64_t i = lo + threadIdx.x; i < hi_pad; i += blockDim.x) {
+        const bool in = i < hi;
+        const uint32_t s0 = in ? S[i] : 0u;
+        uint32_t s = s0;
 
-        // ---- loads this group needs, issued together ----
-        float nb[4] = {0.0f, 0.0f, 0.0f, 0.0f}, pk[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        int32_t te[4] = {0, 0, 0, 0}, vs[4] = {0, 0, 0, 0};
-        const bool g_nab = waning && (any & SB_HAS_NAB);
-        if (g_nab) {
-            unpack4(ld4f(nab, i0), nb);
-            if (END) {
-                unpack4(ld4f(PF(P, peak_nab), i0), pk);
-                const int4 tv = *reinterpret_cast<const int4*>(PI(P, t_nab_event) + i0);
-                te[0] = tv.x; te[1] = tv.y; te[2] = tv.z; te[3] = tv.w;
-            }
-            if (PRE && A.vaxpars && (any & SB_VACC)) {
-                const int4 vv = *reinterpret_cast<const int4*>(PI(P, vaccine_source) + i0);
-                vs[0] = vv.x; vs[1] = vv.y; vs[2] = vv.z; vs[3] = vv.w;
-            }
+        // ---- every load this agent needs follows from its state word: issued together, before any store ----
+        const bool has_nab = waning && (s0 & SB_HAS_NAB);
+        float nb = 0.0f, pk = 0.0f;
+        int32_t te = 0, vsi = 0;
+        if (has_nab) {
+            nb = nab[i];
+            if (END) { pk = PF(P, peak_nab)[i]; te = PI(P, t_nab_event)[i]; }
+            if (PRE && A.vaxpars && (s0 & SB_VACC)) vsi = PI(P, vaccine_source)[i];
         }
-        float di[4], ds[4], dv[4], dc[4], dr[4], dd[4], dei[4];
-        const bool g_exp = PRE && (any & SB_EXP);
-        if (g_exp) {
-            unpack4(ld4f(PF(P, date_infectious), i0), di); unpack4(ld4f(PF(P, date_symptomatic), i0), ds);
-            unpack4(ld4f(PF(P, date_severe), i0), dv); unpack4(ld4f(PF(P, date_critical), i0), dc);
-            unpack4(ld4f(PF(P, date_recovered), i0), dr); unpack4(ld4f(PF(P, date_dead), i0), dd);
+        float di = qnan, ds = qnan, dv = qnan, dc = qnan, dr = qnan, dd = qnan, dei = qnan, dq = qnan, deq = qnan;
+        if (PRE && (s0 & SB_EXP)) {
+            di = PF(P, date_infectious)[i]; ds = PF(P, date_symptomatic)[i]; dv = PF(P, date_severe)[i];
+            dc = PF(P, date_critical)[i]; dr = PF(P, date_recovered)[i]; dd = PF(P, date_dead)[i];
         }
-        const bool g_iso = PRE && (any & SB_ISO);
-        if (g_iso) unpack4(ld4f(PF(P, date_end_isolation), i0), dei);
-        float dq[4] = {qnan, qnan, qnan, qnan}, deq[4] = {qnan, qnan, qnan, qnan};
+        if (PRE && (s0 & SB_ISO)) dei = PF(P, date_end_isolation)[i];
         if (TEST && !A.test_plain && in) {
-            if (A.tp.quar_policy == 0 || A.tp.quar_policy == 2) unpack4(ld4f(PF(P, date_quarantined), i0), dq);
-            if (A.tp.quar_policy == 1 || A.tp.quar_policy == 2) unpack4(ld4f(PF(P, date_end_quarantine), i0), deq);
+            if (A.tp.quar_policy == 0 || A.tp.quar_policy == 2) dq = PF(P, date_quarantined)[i];
+            if (A.tp.quar_policy == 1 || A.tp.quar_policy == 2) deq = PF(P, date_end_quarantine)[i];
         }
 
-        // ---- close day t-1: stock counts (sim.py:652-664), update_nab (immunity.py:205-213), sum of NAbs over the living ----
-        if (END) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t sk = s[k];
-#pragma unroll
-                for (int b = 0; b < 16; ++b) {
-                    if (b == 1 || b == 7 || b == 12) continue;              // naive, tested, known_contact are not result stocks
-                    stock[b] += __popc(__ballot_sync(0xFFFFFFFFu, (sk >> b) & 1u));
-                }
-                stock[16] += __popc(__ballot_sync(0xFFFFFFFFu, in && !(sk & SB_DEAD)));
-                const unsigned m_e = __ballot_sync(0xFFFFFFFFu, (sk & kEbvMask) != 0u);
-                if (m_e) {                                                   // by-variant stocks (exposed / infectious rows)
-                    const int ev = sb_ebv(sk) - 1;
-                    for (int v = 0; v < nv; ++v) {
-                        const int ce = __popc(__ballot_sync(0xFFFFFFFFu, ev == v));
-                        const int ci = __popc(__ballot_sync(0xFFFFFFFFu, ev == v && (sk & SB_IBV)));
-                        if (lane == 0) { if (ce) atomicAdd(&s_stock[17 + 2 * v], ce); if (ci) atomicAdd(&s_stock[17 + 2 * v + 1], ci); }
-                    }
-                }
-            }
-            if (g_nab) {
-                bool upd = false;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (s[k] & SB_HAS_NAB) {                                 // has_nabs = true(peak_nab)  (sim.py:666-669)
-                        int64_t dt = (int64_t)(t - 1) - (int64_t)te[k];
-                        if (dt < 0) dt += A.nab_kin_len;                     // NumPy negative index wraps
-                        const double kin = (dt >= 0 && dt < A.nab_kin_len) ? A.nab_kin[dt] : 0.0;
-                        nb[k] = nab_step(nb[k], pk[k], kin);
-                        upd = true;
-                    }
-                    if (!(s[k] & SB_DEAD)) sum_nab += (double)nb[k];
-                }
-                if (upd) *reinterpret_cast<float4*>(nab + i0) = make_float4(nb[0], nb[1], nb[2], nb[3]);
-            }
+        // ---- close day t-1: update_nab (immunity.py:205-213) and the sum of NAbs over the living (sim.py:666-672) ----
+        if (END && has_nab) {                                                // has_nabs = true(peak_nab)  (sim.py:666-669)
+            int64_t dt = (int64_t)(t - 1) - (int64_t)te;
+            if (dt < 0) dt += A.nab_kin_len;                                 // NumPy negative index wraps
+            const double kin = (dt >= 0 && dt < A.nab_kin_len) ? A.nab_kin[dt] : 0.0;
+            nb = nab_step(nb, pk, kin);
+            nab[i] = nb;
+            if (!(s0 & SB_DEAD)) sum_nab += (double)nb;
         }
 
         if (PRE) {
-            // ---- update_states_pre (people.py:164-186) ----
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int64_t i = i0 + k;
-                uint32_t sk = s[k];
-                const bool was_exposed = (sk & SB_EXP) != 0;                 // is_exp is taken once, before any transition (people.py:169)
-                const int ev = sb_ebv(sk) - 1;
-                const float evf = (float)ev;
-                if (was_exposed) {
-                    if (!(sk & SB_INF) && due(di[k], t)) {                   // people.py:222-232
-                        infectious[i] = 1; inf_var[i] = evf; sk |= SB_INF;
-                        if (ev >= 0 && ev < nv) {
-                            inf_by_var[(int64_t)ev * n + i] = 1; sk |= SB_IBV;
-#pragma unroll
-                            for (int q = 0; q < CVB_MAX_VARIANTS; ++q) cvn[q] += (q == ev);
-                        }
-                        ++c[F_INFECTIOUS];
-                    }
-                    if (!(sk & SB_SYMP) && due(ds[k], t)) { symptomatic[i] = 1; sk |= SB_SYMP; ++c[F_SYMPTOMATIC]; }     // people.py:235-253
-                    if (!(sk & SB_SEV) && due(dv[k], t)) { severe[i] = 1; sk |= SB_SEV; ++c[F_SEVERE]; }
-                    if (!(sk & SB_CRIT) && due(dc[k], t)) { critical[i] = 1; sk |= SB_CRIT; ++c[F_CRITICAL]; }
-                    if (!(sk & SB_REC) && due(dr[k], t)) {                   // people.py:256-291
-                        exposed[i] = 0; infectious[i] = 0; symptomatic[i] = 0; severe[i] = 0; critical[i] = 0;
-                        recovered[i] = 1;
-                        rec_var[i] = evf; inf_var[i] = qnan; exp_var[i] = qnan;
-                        for (int v = 0; v < nv; ++v) { exp_by_var[(int64_t)v * n + i] = 0; inf_by_var[(int64_t)v * n + i] = 0; }
-                        sk &= ~(SB_EXP | SB_INF | SB_SYMP | SB_SEV | SB_CRIT | SB_IBV | kEbvMask | kRvMask);
-                        sk |= SB_REC;
-                        if (ev >= 0 && ev < nv) sk |= (uint32_t)(ev + 1) << kRvShift;
-                        if (waning) {
-                            susceptible[i] = 1; diagnosed[i] = 0;
-                            if (sk & SB_DIAG) sk |= SB_DPEND;                // the (old) date_diagnosed is still set
-                            sk |= SB_SUS; sk &= ~SB_DIAG;
-                        }
-                        ++c[F_RECOVERIES];
-                    }
+            // ---- update_states_pre (people.py:164-186); is_exp is taken once, before any transition (people.py:169) ----
+            const int ev = sb_ebv(s0) - 1;
+            const float evf = (float)ev;
+            if (s0 & SB_EXP) {
+                if (!(s & SB_INF) && due(di, t)) {                           // people.py:222-232
+                    infectious[i] = 1; inf_var[i] = evf; s |= SB_INF;
+                    if (ev >= 0 && ev < nv) { inf_by_var[(int64_t)ev * n + i] = 1; s |= SB_IBV; atomicAdd(&s_flow[F_NK + ev], 1); }
+                    atomicAdd(&s_flow[F_INFECTIOUS], 1);
                 }
-                if ((s[k] & SB_ISO) && due(dei[k], t)) { isolated[i] = 0; sk &= ~SB_ISO; }     // people.py:368-374
-                if (was_exposed) {
-                    if (!(sk & SB_DEAD) && due(dd[k], t)) {                  // people.py:294-312
-                        dead[i] = 1;
-                        if (sk & SB_DIAG) { known_dead[i] = 1; sk |= SB_KDEAD; ++c[F_KNOWN_DEATHS]; }
-                        susceptible[i] = 0; exposed[i] = 0; infectious[i] = 0; symptomatic[i] = 0; severe[i] = 0; critical[i] = 0;
-                        known_contact[i] = 0; quarantined[i] = 0; recovered[i] = 0;
-                        inf_var[i] = qnan; exp_var[i] = qnan; rec_var[i] = qnan;
-                        sk &= ~(SB_SUS | SB_EXP | SB_INF | SB_SYMP | SB_SEV | SB_CRIT | SB_KCONTACT | SB_QUAR | SB_REC | kRvMask);
-                        sk |= SB_DEAD;
-                        ++c[F_DEATHS];
+                if (!(s & SB_SYMP) && due(ds, t)) { symptomatic[i] = 1; s |= SB_SYMP; atomicAdd(&s_flow[F_SYMPTOMATIC], 1); }     // people.py:235-253
+                if (!(s & SB_SEV) && due(dv, t)) { severe[i] = 1; s |= SB_SEV; atomicAdd(&s_flow[F_SEVERE], 1); }
+                if (!(s & SB_CRIT) && due(dc, t)) { critical[i] = 1; s |= SB_CRIT; atomicAdd(&s_flow[F_CRITICAL], 1); }
+                if (!(s & SB_REC) && due(dr, t)) {                           // people.py:256-291
+                    exposed[i] = 0; infectious[i] = 0; symptomatic[i] = 0; severe[i] = 0; critical[i] = 0;
+                    recovered[i] = 1;
+                    rec_var[i] = evf; inf_var[i] = qnan; exp_var[i] = qnan;
+                    for (int v = 0; v < nv; ++v) { exp_by_var[(int64_t)v * n + i] = 0; inf_by_var[(int64_t)v * n + i] = 0; }
+                    s &= ~(SB_EXP | SB_INF | SB_SYMP | SB_SEV | SB_CRIT | SB_IBV | kEbvMask | kRvMask);
+                    s |= SB_REC;
+                    if (ev >= 0 && ev < nv) s |= (uint32_t)(ev + 1) << kRvShift;
+                    if (waning) {
+                        susceptible[i] = 1; diagnosed[i] = 0;
+                        if (s & SB_DIAG) s |= SB_DPEND;                      // the (old) date_diagnosed is still set
+                        s |= SB_SUS; s &= ~SB_DIAG;
                     }
+                    atomicAdd(&s_flow[F_RECOVERIES], 1);
                 }
-                c[F_BED_SEVERE] += (sk & SB_SEV) != 0;
-                c[F_BED_CRITICAL] += (sk & SB_CRIT) != 0;
-                s[k] = sk;
+            }
+            if ((s0 & SB_ISO) && due(dei, t)) { isolated[i] = 0; s &= ~SB_ISO; }     // people.py:368-374
+            if ((s0 & SB_EXP) && !(s & SB_DEAD) && due(dd, t)) {             // people.py:294-312
+                dead[i] = 1;
+                if (s & SB_DIAG) { known_dead[i] = 1; s |= SB_KDEAD; atomicAdd(&s_flow[F_KNOWN_DEATHS], 1); }
+                susceptible[i] = 0; exposed[i] = 0; infectious[i] = 0; symptomatic[i] = 0; severe[i] = 0; critical[i] = 0;
+                known_contact[i] = 0; quarantined[i] = 0; recovered[i] = 0;
+                inf_var[i] = qnan; exp_var[i] = qnan; rec_var[i] = qnan;
+                s &= ~(SB_SUS | SB_EXP | SB_INF | SB_SYMP | SB_SEV | SB_CRIT | SB_KCONTACT | SB_QUAR | SB_REC | kRvMask);
+                s |= SB_DEAD;
+                atomicAdd(&s_flow[F_DEATHS], 1);
             }
 
             // ---- check_immunity (immunity.py:303-350): agents with antibodies and an immunity source are queued per warp and
             //      evaluated 32 at a time; everybody else has protection exactly 0 (written only if something non-zero is stored) ----
             if (waning) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int64_t i = i0 + k;
-                    const uint32_t sk = s[k];
-                    const int rv1 = sb_rv(sk);
-                    const int vsi = vs[k];
-                    const bool vacc = A.vaxpars && (sk & SB_VACC) && vsi >= 0 && vsi < CVB_MAX_VACCINES;
-                    const bool heavy = (sk & SB_HAS_NAB) && nb[k] > 0.0f && (rv1 != 0 || vacc);
-                    const bool clear = !heavy && (sk & SB_IMM_NZ);
+                const int rv1 = sb_rv(s);
+                const bool vacc = A.vaxpars && (s & SB_VACC) && vsi >= 0 && vsi < CVB_MAX_VACCINES;
+                const bool heavy = (s & SB_HAS_NAB) && nb > 0.0f && (rv1 != 0 || vacc);
+                if (!heavy && (s & SB_IMM_NZ))
+                    for (int v = 0; v < nv; ++v) { sus_imm[(int64_t)v * n + i] = 0.0f; symp_imm[(int64_t)v * n + i] = 0.0f; sev_imm[(int64_t)v * n + i] = 0.0f; }
+                if (heavy) s |= SB_IMM_NZ; else s &= ~SB_IMM_NZ;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, heavy);
+                if (m) {
                     const unsigned packed = ((unsigned)rv1 << 4) | ((unsigned)(vacc ? vsi : 0) << 8) | ((unsigned)vacc << 12);
                     for (int v = 0; v < nv; ++v) {
-                        if (clear) {
-                            sus_imm[(int64_t)v * n + i] = 0.0f; symp_imm[(int64_t)v * n + i] = 0.0f; sev_imm[(int64_t)v * n + i] = 0.0f;
-                        }
-                        const unsigned m = __ballot_sync(0xFFFFFFFFu, heavy);
-                        if (m) {
-                            if (heavy) q_imm[qn + __popc(m & lt_mask)] = make_uint4((unsigned)i, __float_as_uint(nb[k]), packed | (unsigned)v, 0u);
-                            qn += __popc(m);
+                        if (heavy) q_imm[qn + __popc(m & lt_mask)] = make_uint4((unsigned)i, __float_as_uint(nb), packed | (unsigned)v, 0u);
+                        qn += __popc(m);
+                        __syncwarp();
+                        if (qn >= 32) {
+                            qn -= 32;
+                            const uint4 en = q_imm[qn + lane];
                             __syncwarp();
-                            if (qn >= 32) {
-                                qn -= 32;
-                                const uint4 en = q_imm[qn + lane];
-                                __syncwarp();
-                                immunity_eval2(en, n, pars, sus_imm, symp_imm, sev_imm, sum_sus, sum_symp);
-                            }
+                            const float2 r = immunity_eval2(en, n, pars, sus_imm, symp_imm, sev_imm);
+                            sum_sus += (double)r.x; sum_symp += (double)r.y;
                         }
                     }
-                    if (heavy) s[k] = sk | SB_IMM_NZ; else s[k] = sk & ~SB_IMM_NZ;
                 }
             }
         }
 
         // ---- test_prob + People.test (interventions.py:921-981, people.py:589-617) and today's cases (interventions.py:1066-1085) ----
-        if (TEST || TSEL) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int64_t i = i0 + k;
-                uint32_t sk = s[k];
-                if (!in) continue;
-                float ddiag_new = qnan;
-                bool ddiag_known = false;
-                if (TEST && !(sk & SB_DIAG)) {                               // diagnosed people do not test (interventions.py:973)
-                    const bool symp = (sk & SB_SYMP) != 0;
-                    bool qt = false;                                         // interventions.py:691-715 get_quar_inds
-                    if (!A.test_plain) {
-                        switch (A.tp.quar_policy) {
-                            case 0:  qt = dq[k] == tf - 1.0f; break;
-                            case 1:  qt = deq[k] == tf + 1.0f; break;
-                            case 2:  qt = (dq[k] == tf - 1.0f) || (deq[k] == tf + 1.0f); break;
-                            default: qt = (sk & SB_QUAR) != 0; break;
-                        }
+        if ((TEST || TSEL) && in) {
+            float ddiag_new = qnan;
+            bool ddiag_known = false;
+            if (TEST && !(s & SB_DIAG)) {                                    // diagnosed people do not test (interventions.py:973)
+                const bool symp = (s & SB_SYMP) != 0;
+                bool qt = false;                                             // interventions.py:691-715 get_quar_inds
+                if (!A.test_plain) {
+                    switch (A.tp.quar_policy) {
+                        case 0:  qt = dq == tf - 1.0f; break;
+                        case 1:  qt = deq == tf + 1.0f; break;
+                        case 2:  qt = (dq == tf - 1.0f) || (deq == tf + 1.0f); break;
+                        default: qt = (s & SB_QUAR) != 0; break;
                     }
-                    const double prob = qt ? (symp ? A.tp.symp_quar_prob : A.tp.asymp_quar_prob) : (symp ? A.tp.symp_prob : A.tp.asymp_prob);
-                    if (prob > 0.0 && keyed_uniform(A.seed, P_TEST, (uint32_t)A.tp.index, t, i + A.id0, 0) < prob) {
-                        ++c[F_TESTS];
-                        tested[i] = 1; sk |= SB_TESTED;
-                        d_tested[i] = tf;
-                        if ((sk & SB_INF) && keyed_uniform(A.seed, P_TEST_SENS, (uint32_t)A.tp.index, t, i + A.id0, 0) < A.tp.sensitivity) {
-                            const float old = d_diag[i];
-                            ddiag_known = true; ddiag_new = old;
-                            if (is_nan(old) && keyed_uniform(A.seed, P_TEST_LOSS, (uint32_t)A.tp.index, t, i + A.id0, 0) < 1.0 - A.tp.loss_prob) {
-                                ddiag_new = (float)(t + A.tp.test_delay);
-                                d_diag[i] = ddiag_new;
-                                d_pos[i] = tf;
-                                sk |= SB_DPEND;
-                            }
+                }
+                const double prob = qt ? (symp ? A.tp.symp_quar_prob : A.tp.asymp_quar_prob) : (symp ? A.tp.symp_prob : A.tp.asymp_prob);
+                if (prob > 0.0 && keyed_uniform(A.seed, P_TEST, (uint32_t)A.tp.index, t, i + A.id0, 0) < prob) {
+                    ++c_tests;
+                    tested[i] = 1; s |= SB_TESTED;
+                    d_tested[i] = tf;
+                    if ((s & SB_INF) && keyed_uniform(A.seed, P_TEST_SENS, (uint32_t)A.tp.index, t, i + A.id0, 0) < A.tp.sensitivity) {
+                        const float old = d_diag[i];
+                        ddiag_known = true; ddiag_new = old;
+                        if (is_nan(old) && keyed_uniform(A.seed, P_TEST_LOSS, (uint32_t)A.tp.index, t, i + A.id0, 0) < 1.0 - A.tp.loss_prob) {
+                            ddiag_new = (float)(t + A.tp.test_delay);
+                            d_diag[i] = ddiag_new;
+                            d_pos[i] = tf;
+                            s |= SB_DPEND;
                         }
                     }
                 }
-                if (TSEL && (sk & SB_DPEND)) {                               // a case: date_diagnosed == t
-                    const float dg = ddiag_known ? ddiag_new : d_diag[i];
-                    if (dg == tf) {
-                        const long long beg = A.adj_ptr[i], end = A.adj_ptr[i + 1];
-                        A.case_ent[warp_append32(A.n_case)] = make_uint4((unsigned)i, (unsigned)(end - beg), (unsigned)(unsigned long long)beg, (unsigned)((unsigned long long)beg >> 32));
-                    }
+            }
+            if (TSEL && (s & SB_DPEND)) {                                    // a case: date_diagnosed == t
+                const float dg = ddiag_known ? ddiag_new : d_diag[i];
+                if (dg == tf) {
+                    const long long beg = A.adj_ptr[i], end = A.adj_ptr[i + 1];
+                    A.case_ent[warp_append32(A.n_case)] = make_uint4((unsigned)i, (unsigned)(end - beg), (unsigned)(unsigned long long)beg, (unsigned)((unsigned long long)beg >> 32));
                 }
-                s[k] = sk;
             }
         }
-        if (in && (PRE || TEST) && ((s[0] ^ sv.x) | (s[1] ^ sv.y) | (s[2] ^ sv.z) | (s[3] ^ sv.w)))
-            *reinterpret_cast<uint4*>(S + i0) = make_uint4(s[0], s[1], s[2], s[3]);
+        if (s != s0) { S[i] = s; stock_delta(s0, s, s_delta); }
     }
-    if (PRE && waning && lane < qn) immunity_eval2(q_imm[lane], n, pars, sus_imm, symp_imm, sev_imm, sum_sus, sum_symp);
+    if (PRE && waning && lane < qn) {
+        const float2 r = immunity_eval2(q_imm[lane], n, pars, sus_imm, symp_imm, sev_imm);
+        sum_sus += (double)r.x; sum_symp += (double)r.y;
+    }
 
-    // ---- counters: flows of day t, stocks of day t - 1 ----
-    if (PRE || TEST) {
-        reduce_counters(c, s_flow);
-        reduce_counters(cvn, s_flow + F_NK);
-    }
-    if (END && lane == 0) {
-#pragma unroll
-        for (int b = 0; b < 17; ++b) if (stock[b]) atomicAdd(&s_stock[b], stock[b]);
+    // ---- counters: flows and stock differences of day t; float64 sums ----
+    if (TEST) {
+        const int w = __reduce_add_sync(0xFFFFFFFFu, c_tests);
+        if (lane == 0 && w) atomicAdd(&s_flow[F_TESTS], w);
     }
     double sums[3] = {sum_nab, sum_sus, sum_symp};
 #pragma unroll
@@ -441,8 +368,6 @@ __global__ void __launch_bounds__(kThreads, 2) day_begin_kernel(PeoplePtrs P, ui
             case F_RECOVERIES:   atomicAdd(row + CVB_C_new_recoveries, uv); break;
             case F_DEATHS:       atomicAdd(row + CVB_C_new_deaths, uv); break;
             case F_KNOWN_DEATHS: atomicAdd(row + CVB_C_new_known_deaths, uv); break;
-            case F_BED_SEVERE:   atomicAdd(A.beds + (int64_t)t * 2 + 0, uv); break;
-            case F_BED_CRITICAL: atomicAdd(A.beds + (int64_t)t * 2 + 1, uv); break;
             case F_TESTS:        atomicAdd(row + CVB_C_new_tests, uv); break;
             default: {
                 const int var = threadIdx.x - F_NK;
@@ -450,20 +375,7 @@ __global__ void __launch_bounds__(kThreads, 2) day_begin_kernel(PeoplePtrs P, ui
             }
         }
     }
-    if (END && threadIdx.x < kStockSlots && s_stock[threadIdx.x]) {
-        const int k = threadIdx.x;
-        const unsigned long long v = (unsigned long long)s_stock[k];
-        unsigned long long* row = A.counters + (int64_t)(t - 1) * CVB_N_COUNTERS;
-        // state bit -> stock counter (defaults.result_stocks order: susceptible, exposed, infectious, symptomatic, severe, critical,
-        // recovered, dead, diagnosed, known_dead, quarantined, isolated, vaccinated)
-        const int stock_of_bit[16] = {0, -1, 1, 2, 3, 4, 5, -1, 8, 6, 9, 7, -1, 10, 11, 12};
-        if (k < 16) { if (stock_of_bit[k] >= 0) atomicAdd(row + CVB_C_n_susceptible + stock_of_bit[k], v); }
-        else if (k == 16) atomicAdd(row + CVB_C_n_alive_agents, v);
-        else {
-            const int q = k - 17, var = q >> 1;
-            if (var < nv) atomicAdd(A.vcounters + ((int64_t)(t - 1) * nv + var) * CVB_N_VCOUNTERS + ((q & 1) ? CVB_VC_n_infectious_by_variant : CVB_VC_n_exposed_by_variant), v);
-        }
-    }
+    if (PRE || TEST) flush_stock_delta(s_delta, A.counters + (int64_t)t * CVB_N_COUNTERS, A.vcounters + (int64_t)t * nv * CVB_N_VCOUNTERS, nv);
     // the last CTA to finish adds up the per-CTA partial sums in a fixed order (deterministic float64 sums, no second launch)
     __threadfence();
     __syncthreads();
@@ -485,30 +397,35 @@ __global__ void __launch_bounds__(kThreads, 2) day_begin_kernel(PeoplePtrs P, ui
 }
 
 // ================================================================================================================================
-// day_mid_kernel: update_states_post + prepare_transmission
+// day_mid_kernel: update_states_post + prepare_transmission; one agent per thread, one contiguous chunk of agents per CTA
 // ================================================================================================================================
 enum { M_DIAGNOSES = 0, M_QUARANTINED, M_ISOLATED, M_NK };
+constexpr int kMidChunk = 1024;                     // agents per CTA: bounds the shared-memory transmitter buffer (32 B per entry)
 
 struct DayMidArgs {
     int64_t n;
     int32_t t, nv, horizon, dense;                  // dense: some layer is streamed densely today (records for everyone + ts8 + bitmap)
     float* quar_slot;
-    unsigned long long* counters;
+    unsigned long long* counters; unsigned long long* vcounters;
     TransRecords rec;
     unsigned int* inf_bits;
     const long long* adj_ptr;                       // NULL: no adjacency (every layer dense)
     uint4* trans_ent; unsigned int* n_trans;
     unsigned int* n_cand; unsigned int* n_case;
-    int32_t* trans_list;                            // the plain list (used by nobody in the fused pipeline; kept for cvb_get_edge_work parity)
+    int32_t* trans_list;                            // the plain list, in the same order as the entries
 };
 
-__global__ void __launch_bounds__(kThreads, 3) day_mid_kernel(PeoplePtrs P, uint32_t* __restrict__ S, const __grid_constant__ cvb_pars pars,
+__global__ void __launch_bounds__(kThreads, 4) day_mid_kernel(PeoplePtrs P, uint32_t* __restrict__ S, const __grid_constant__ cvb_pars pars,
                                                              const __grid_constant__ DayMidArgs A) {
     __shared__ int s_cnt[M_NK];
+    __shared__ int s_delta[kStockSlots];
+    __shared__ uint4 s_ent[2 * kMidChunk];                                   // this CTA's transmitter entries, flushed with ONE global atomic
+    __shared__ unsigned int s_n_ent, s_base;
     if (threadIdx.x < M_NK) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < kStockSlots) s_delta[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_n_ent = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) { *A.n_cand = 0; *A.n_case = 0; }   // today's candidates start empty; the case list was consumed
     __syncthreads();
-    int c[M_NK] = {0, 0, 0};
     const int64_t n = A.n;
     const int32_t t = A.t;
     const int nv = A.nv;
@@ -522,105 +439,89 @@ __global__ void __launch_bounds__(kThreads, 3) day_mid_kernel(PeoplePtrs P, uint
     const float* d_inf = PF(P, date_infectious); const float* d_dead = PF(P, date_dead);
     const float* sus_imm = PF(P, sus_imm);
 
-    const int64_t n_groups = n >> 2;
-    const int64_t n_groups_pad = (n_groups + 31) / 32 * 32;
-    for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < n_groups_pad; g += (int64_t)gridDim.x * blockDim.x) {
-        const bool in = g < n_groups;
-        const int64_t i0 = g << 2;
-        uint4 sv = make_uint4(0u, 0u, 0u, 0u);
-        if (in) sv = *reinterpret_cast<const uint4*>(S + i0);
-        uint32_t s[4] = {sv.x, sv.y, sv.z, sv.w};
-        const uint32_t any = sv.x | sv.y | sv.z | sv.w;
-        float pend[4] = {-1.0f, -1.0f, -1.0f, -1.0f};
-        if (any & SB_QPEND) unpack4(ld4f(A.quar_slot, i0), pend);
-        float rs4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        // rel_sus is needed unless all four stored records are certainly still right (simple form, same flags, and nothing that
-        // update_states_post could change today: no pending request / diagnosis, not in quarantine)
-        bool need_rs = A.dense != 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) need_rs |= in && !((s[k] & SB_RS_VALID) && !(s[k] & (SB_INF | SB_IMM_NZ | SB_QPEND | SB_DPEND | SB_QUAR)) &&
-                                                      (((s[k] & SB_SUS) != 0) == ((s[k] & SB_RS_SUS) != 0)) && (((s[k] & SB_QUAR) != 0) == ((s[k] & SB_RS_QUAR) != 0)));
-        if (need_rs) unpack4(ld4f(rel_sus, i0), rs4);
-        unsigned inf_nibble = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int64_t i = i0 + k;
-            if (!in) continue;
-            uint32_t sk = s[k];
-            // ---- update_states_post (people.py:189-196) ----
-            float ddiag = qnan;
-            if (sk & SB_DPEND) {                                             // check_diagnosed (people.py:315-332)
-                ddiag = d_diag[i];
-                const float dpos = d_pos[i];
-                if (!(sk & SB_DIAG)) {
-                    if (due(dpos, t)) { d_pos[i] = qnan; ++c[M_DIAGNOSES]; }
-                    if (due(ddiag, t)) { diagnosed[i] = 1; sk |= SB_DIAG; sk &= ~SB_DPEND; }
-                }
+    const int64_t lo = (int64_t)blockIdx.x * kMidChunk;
+    const int64_t hi = lo + kMidChunk < n ? lo + kMidChunk : n;
+    const int64_t hi_pad = lo + (hi - lo + 31) / 32 * 32;
+    for (int64_t i = lo + threadIdx.x; i < hi_pad; i += blockDim.x) {
+        const bool in = i < hi;
+        const uint32_t s0 = in ? S[i] : 0u;
+        uint32_t s = s0;
+        bool can_trans = false;
+        // nothing can change for this agent today and its stored record is right: the common case costs one 4-byte load
+        const bool settled = !A.dense && (s0 & SB_RS_VALID) && !(s0 & (SB_INF | SB_IMM_NZ | SB_QPEND | SB_DPEND | SB_QUAR)) &&
+                             (((s0 & SB_SUS) != 0) == ((s0 & SB_RS_SUS) != 0)) && !(s0 & SB_RS_QUAR);
+        if (in && !settled) {
+            // ---- every load follows from the state word: issued together, before any store ----
+            float ddiag = qnan, dpos = qnan, pend = -1.0f, end_q = qnan, drec = qnan;
+            if (s0 & SB_DPEND) { ddiag = d_diag[i]; dpos = d_pos[i]; }
+            if (s0 & SB_QPEND) pend = A.quar_slot[i];
+            if (s0 & SB_QUAR) end_q = d_end_quar[i];
+            if (s0 & (SB_DPEND | SB_INF)) drec = d_rec[i];
+            const float rs = rel_sus[i];
+            const float imm0 = (s0 & SB_IMM_NZ) ? sus_imm[i] : 0.0f;
+            float rtv = 0.0f, dinf = qnan, ddead = qnan;
+            long long beg = 0, end = 0;
+            if (s0 & SB_INF) {
+                rtv = rel_trans[i]; dinf = d_inf[i]; ddead = d_dead[i];
+                if (A.adj_ptr) { beg = A.adj_ptr[i]; end = A.adj_ptr[i + 1]; }
             }
-            bool quar = (sk & SB_QUAR) != 0;
-            float end_q = qnan;
-            bool end_q_known = false;
-            if (pend[k] >= 0.0f) {                                           // check_quar (people.py:335-358)
+            // ---- update_states_post (people.py:189-196) ----
+            if ((s & SB_DPEND) && !(s & SB_DIAG)) {                          // check_diagnosed (people.py:315-332)
+                if (due(dpos, t)) { d_pos[i] = qnan; atomicAdd(&s_cnt[M_DIAGNOSES], 1); }
+                if (due(ddiag, t)) { diagnosed[i] = 1; s |= SB_DIAG; s &= ~SB_DPEND; }
+            }
+            bool quar = (s & SB_QUAR) != 0;
+            if (pend >= 0.0f) {                                              // check_quar (people.py:335-358)
                 A.quar_slot[i] = -1.0f;
                 if (quar) {
-                    end_q = d_end_quar[i]; end_q_known = true;
-                    if (pend[k] > end_q) { end_q = pend[k]; d_end_quar[i] = end_q; }      // Python max(old, requested)
-                } else if (!(sk & (SB_DEAD | SB_REC | SB_DIAG | SB_ISO))) {
+                    if (pend > end_q) { end_q = pend; d_end_quar[i] = end_q; }            // Python max(old, requested)
+                } else if (!(s & (SB_DEAD | SB_REC | SB_DIAG | SB_ISO))) {
                     quarantined[i] = 1; quar = true;
                     d_quar[i] = tf;
-                    end_q = pend[k]; end_q_known = true;
+                    end_q = pend;
                     d_end_quar[i] = end_q;
-                    ++c[M_QUARANTINED];
+                    atomicAdd(&s_cnt[M_QUARANTINED], 1);
                 }
             }
-            if ((sk & SB_QPEND) && A.horizon == 1) sk &= ~SB_QPEND;          // (several slots: the bit stays, the slot is re-read)
+            if ((s & SB_QPEND) && A.horizon == 1) s &= ~SB_QPEND;            // (several slots: the bit stays, the slot is re-read)
             if (quar) {
-                if (!end_q_known) end_q = d_end_quar[i];
                 if (ddiag == tf) { end_q = tf; d_end_quar[i] = tf; }
                 if (due(end_q, t)) { quarantined[i] = 0; quar = false; }
             }
-            if (quar) sk |= SB_QUAR; else sk &= ~SB_QUAR;
+            if (quar) s |= SB_QUAR; else s &= ~SB_QUAR;
             if (ddiag == tf) {                                               // check_enter_iso (people.py:361-366)
-                isolated[i] = 1; sk |= SB_ISO;
-                d_end_iso[i] = d_rec[i];
-                ++c[M_ISOLATED];
+                isolated[i] = 1; s |= SB_ISO;
+                d_end_iso[i] = drec;
+                atomicAdd(&s_cnt[M_ISOLATED], 1);
             }
             // ---- prepare_transmission (sim.py:602-643): ONE 16-byte record per agent (cvb_device.cuh:AgentRecord) ----
-            const bool iso = (sk & SB_ISO) != 0;
-            bool inf = (sk & SB_INF) != 0;
-            const bool sus = (sk & SB_SUS) != 0;
-            int var = sb_ebv(sk) - 1;
+            const bool iso = (s & SB_ISO) != 0;
+            bool inf = (s & SB_INF) != 0;
+            const bool sus = (s & SB_SUS) != 0;
+            int var = sb_ebv(s) - 1;
             if (inf && !(var >= 0 && var < nv)) { inf = false; var = 0; }
-            const bool simple = !inf && !(sk & SB_IMM_NZ) && !A.dense;
+            const bool simple = !inf && !(s & SB_IMM_NZ) && !A.dense;
             if (simple) {
                 const uint32_t want = SB_RS_VALID | (sus ? SB_RS_SUS : 0u) | (quar ? SB_RS_QUAR : 0u);
-                if ((sk & (SB_RS_VALID | SB_RS_SUS | SB_RS_QUAR)) != want) {
-                    A.rec.rec[i] = make_float4(0.0f, sus ? rs4[k] : 0.0f, 0.0f, __uint_as_float(quar ? 32u : 0u));
-                    sk = (sk & ~(SB_RS_VALID | SB_RS_SUS | SB_RS_QUAR)) | want;
+                if ((s & (SB_RS_VALID | SB_RS_SUS | SB_RS_QUAR)) != want) {
+                    A.rec.rec[i] = make_float4(0.0f, sus ? rs : 0.0f, 0.0f, __uint_as_float(quar ? 32u : 0u));
+                    s = (s & ~(SB_RS_VALID | SB_RS_SUS | SB_RS_QUAR)) | want;
                 }
             } else {
-                sk &= ~(SB_RS_VALID | SB_RS_SUS | SB_RS_QUAR);
-                const bool symp = (sk & SB_SYMP) != 0;
+                s &= ~(SB_RS_VALID | SB_RS_SUS | SB_RS_QUAR);
+                const bool symp = (s & SB_SYMP) != 0;
                 uint32_t code = quar ? 32u : 0u;                              // the quarantine bit matters for targets too
                 float rt = 0.0f;
-                if (inf) {
-                    const float rtv = rel_trans[i];
-                    if (rtv != 0.0f) {                                        // can transmit (a zero rel_trans never does)
-                        rt = rtv;
-                        const bool early = viral_load_early(t, d_inf[i], d_rec[i], d_dead[i], pars.frac_time, pars.high_cap);
-                        code = transmit_code(var, symp, iso, quar, early, false);
-                        inf_nibble |= 1u << k;
-                        const unsigned int pos = warp_append32(A.n_trans);
-                        A.trans_list[pos] = (int32_t)i;
-                        if (A.adj_ptr) {
-                            const long long beg = A.adj_ptr[i], end = A.adj_ptr[i + 1];
-                            A.trans_ent[2 * (int64_t)pos] = make_uint4((unsigned)i, (unsigned)(end - beg), (unsigned)(unsigned long long)beg, (unsigned)((unsigned long long)beg >> 32));
-                            A.trans_ent[2 * (int64_t)pos + 1] = make_uint4(__float_as_uint(rt), code, 0u, 0u);
-                        }
-                    }
+                if (inf && rtv != 0.0f) {                                     // can transmit (a zero rel_trans never does)
+                    rt = rtv;
+                    const bool early = viral_load_early(t, dinf, drec, ddead, pars.frac_time, pars.high_cap);
+                    code = transmit_code(var, symp, iso, quar, early, false);
+                    can_trans = true;
+                    const unsigned int pos = atomicAdd(&s_n_ent, 1u);         // shared memory: this CTA's entries
+                    s_ent[2 * pos] = make_uint4((unsigned)i, (unsigned)(end - beg), (unsigned)(unsigned long long)beg, (unsigned)((unsigned long long)beg >> 32));
+                    s_ent[2 * pos + 1] = make_uint4(__float_as_uint(rt), code, 0u, 0u);
                 }
-                const float imm0 = (sk & SB_IMM_NZ) ? sus_imm[i] : 0.0f;
-                float s_rec = sus ? rs4[k] : 0.0f, imm_rec = imm0;
+                float s_rec = sus ? rs : 0.0f, imm_rec = imm0;
                 if (nv == 1 && !quar) { s_rec = record_sus(s_rec, 0u, 1.0f, imm_rec); imm_rec = 0.0f; }
                 if (A.rec.rec) A.rec.rec[i] = make_float4(rt, s_rec, imm_rec, __uint_as_float(code));
                 if (A.rec.ts8) {
@@ -630,31 +531,32 @@ __global__ void __launch_bounds__(kThreads, 3) day_mid_kernel(PeoplePtrs P, uint
                         float2 o;
                         o.x = rt != 0.0f ? rel_trans_layer(rt, true, symp, iso, quar, pars.asymp_factor, pars.iso_factor[l], pars.quar_factor[l],
                                                            pars.beta_layer[l], vl) : 0.0f;
-                        o.y = sus ? rel_sus_layer(rs4[k], true, quar, pars.quar_factor[l], imm0) : 0.0f;
+                        o.y = sus ? rel_sus_layer(rs, true, quar, pars.quar_factor[l], imm0) : 0.0f;
                         A.rec.ts8[(int64_t)l * n + i] = o;
                     }
                 }
             }
-            s[k] = sk;
+            if (s != s0) { S[i] = s; stock_delta(s0, s, s_delta); }
         }
-        if (in && ((s[0] ^ sv.x) | (s[1] ^ sv.y) | (s[2] ^ sv.z) | (s[3] ^ sv.w)))
-            *reinterpret_cast<uint4*>(S + i0) = make_uint4(s[0], s[1], s[2], s[3]);
-        if (A.dense) {                                                       // transmit bitmap for the dense streaming pass
-            unsigned word = inf_nibble << (4 * (lane & 7));
-            word |= __shfl_xor_sync(0xFFFFFFFFu, word, 1);
-            word |= __shfl_xor_sync(0xFFFFFFFFu, word, 2);
-            word |= __shfl_xor_sync(0xFFFFFFFFu, word, 4);
-            const int64_t widx = (i0 - (int64_t)(lane & 7) * 4) / 32;
-            if ((lane & 7) == 0 && widx * 32 < n) A.inf_bits[widx] = word;
+        if (A.dense) {                                                       // transmit bitmap for the dense streaming pass: a warp = one word
+            const unsigned word = __ballot_sync(0xFFFFFFFFu, can_trans);
+            if (lane == 0 && i < n) A.inf_bits[i >> 5] = word;
         }
     }
-    reduce_counters(c, s_cnt);
     __syncthreads();
+    // flush this CTA's transmitter entries: one global atomic, coalesced copies; the list stays grouped by agent range, so
+    // neighbouring groups of the edge pass walk neighbouring adjacency rows
+    if (threadIdx.x == 0 && s_n_ent) s_base = atomicAdd(A.n_trans, s_n_ent);
+    __syncthreads();
+    const unsigned int cnt = s_n_ent;
+    for (unsigned int k = threadIdx.x; k < 2 * cnt; k += blockDim.x) A.trans_ent[2 * (int64_t)s_base + k] = s_ent[k];
+    for (unsigned int k = threadIdx.x; k < cnt; k += blockDim.x) A.trans_list[s_base + k] = (int32_t)s_ent[2 * k].x;
     if (threadIdx.x < M_NK && s_cnt[threadIdx.x]) {
         unsigned long long* row = A.counters + (int64_t)t * CVB_N_COUNTERS;
         const int ids[M_NK] = {CVB_C_new_diagnoses, CVB_C_new_quarantined, CVB_C_new_isolated};
         atomicAdd(row + ids[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
     }
+    flush_stock_delta(s_delta, A.counters + (int64_t)t * CVB_N_COUNTERS, A.vcounters + (int64_t)t * nv * CVB_N_VCOUNTERS, nv);
 }
 
 }  // namespace cvb
@@ -676,6 +578,8 @@ static int fused_ready(cvb_sim* s, const char* who) {
     return 0;
 }
 
+constexpr size_t kStockBaseBytes = (CVB_N_COUNTERS + CVB_MAX_VARIANTS * CVB_N_VCOUNTERS) * sizeof(unsigned long long);
+
 static int ensure_fused_buffers(cvb_sim* s) {
     if (!s->state) {
         CVB_CHECK(cudaMalloc((void**)&s->state, (size_t)s->n * sizeof(uint32_t)));
@@ -683,10 +587,15 @@ static int ensure_fused_buffers(cvb_sim* s) {
     }
     if (!s->trans_ent) CVB_CHECK(cudaMalloc((void**)&s->trans_ent, (size_t)s->n * 2 * sizeof(uint4)));
     if (!s->case_ent) CVB_CHECK(cudaMalloc((void**)&s->case_ent, (size_t)s->n * sizeof(uint4)));
+    if (!s->stock_base) CVB_CHECK(cudaMalloc((void**)&s->stock_base, kStockBaseBytes));
     return 0;
 }
 
-static int grid_agents4(int64_t n) { return grid_for((n + 3) / 4, kThreads, 148 * 8); }
+constexpr int64_t kBeginChunk = 1024;      // agents per CTA of day_begin_kernel
+
+// layout of the scratch rows that hold the absolute stock counts after a pack (the base of the first fused day)
+static unsigned long long* base_row(cvb_sim* s) { return s->stock_base; }
+static unsigned long long* base_vrow(cvb_sim* s) { return s->stock_base + CVB_N_COUNTERS; }
 
 // pack (verify = false) or verify (true: returns the number of agents whose word differs from the arrays in host_out[1])
 static int pack_or_check(cvb_sim* s, int32_t t_done, bool verify, int64_t* host_out, cudaStream_t st) {
@@ -695,6 +604,11 @@ static int pack_or_check(cvb_sim* s, int32_t t_done, bool verify, int64_t* host_
     pack_state_kernel<<<grid_for(s->n, kThreads, 148 * 8), kThreads, 0, st>>>(s->people, s->state, verify ? s->state : nullptr, s->n, s->nv, t_done,
         s->quar_ring, s->quar_horizon, scal, scal + 1, reinterpret_cast<int32_t*>(scal + 2));
     CVB_LAUNCH_CHECK();
+    if (!verify) {
+        CVB_CHECK(cudaMemsetAsync(s->stock_base, 0, kStockBaseBytes, st));
+        count_state_kernel<<<grid_for(s->n, kThreads, 148 * 4), kThreads, 0, st>>>(s->state, s->n, s->nv, base_row(s), base_vrow(s));
+        CVB_LAUNCH_CHECK();
+    }
     if (host_out) {
         unsigned int h[26];
         CVB_CHECK(cudaMemcpyAsync(h, scal, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -706,13 +620,18 @@ static int pack_or_check(cvb_sim* s, int32_t t_done, bool verify, int64_t* host_
 }
 
 template <bool END, bool PRE>
-static int launch_day_begin(cvb_sim* s, int32_t t, bool test, bool tsel, cudaStream_t st) {
+static int launch_day_begin(cvb_sim* s, int32_t t, bool test, bool tsel, bool base_from_pack, cudaStream_t st) {
     DayBeginArgs A;
     memset(&A, 0, sizeof(A));
-    A.n = s->n; A.id0 = 0; A.t = t; A.nv = s->nv; A.waning = s->pars.use_waning; A.vaxpars = s->pars.has_vaccine_pars;
+    A.n = s->n; A.id0 = 0; A.chunk = kBeginChunk; A.t = t; A.nv = s->nv; A.waning = s->pars.use_waning; A.vaxpars = s->pars.has_vaccine_pars;
     A.nab_kin = s->nab_kin; A.nab_kin_len = s->nab_kin_len;
-    A.counters = s->res.counters; A.vcounters = s->res.vcounters; A.beds = s->beds;
-    const int grid = grid_agents4(s->n);
+    A.counters = s->res.counters; A.vcounters = s->res.vcounters;
+    if (PRE) {
+        CVB_REQUIRE(base_from_pack || t > 0, "cvb_run_days: no stock counts to start day 0 from");
+        A.base_row = base_from_pack ? base_row(s) : s->res.counters + (int64_t)(t - 1) * CVB_N_COUNTERS;
+        A.base_vrow = base_from_pack ? base_vrow(s) : s->res.vcounters + (int64_t)(t - 1) * s->nv * CVB_N_VCOUNTERS;
+    }
+    const int grid = (int)((s->n + kBeginChunk - 1) / kBeginChunk);
     if (ensure_f64(&s->partial, &s->partial_cap, (int64_t)grid * 3)) return 1;
     A.partial = s->partial; A.ticket = reinterpret_cast<unsigned int*>(s->dev_scalars + 8); A.sums = s->res.sums;
     A.n_trans = s->n_trans; A.n_case = s->n_case_list;
@@ -768,10 +687,10 @@ static int launch_day_mid(cvb_sim* s, int32_t t, cudaStream_t st) {
     memset(&A, 0, sizeof(A));
     A.n = s->n; A.t = t; A.nv = s->nv; A.horizon = s->quar_horizon; A.dense = dense_any ? 1 : 0;
     A.quar_slot = s->quar_ring + (int64_t)(t % s->quar_horizon) * s->n;
-    A.counters = s->res.counters; A.rec = s->rec; A.inf_bits = s->inf_bits;
+    A.counters = s->res.counters; A.vcounters = s->res.vcounters; A.rec = s->rec; A.inf_bits = s->inf_bits;
     A.adj_ptr = (s->adj && s->adj_layer_mask) ? s->adj_ptr : nullptr;
     A.trans_ent = s->trans_ent; A.n_trans = s->n_trans; A.n_cand = s->n_cand; A.n_case = s->n_case_list; A.trans_list = s->trans_list;
-    day_mid_kernel<<<grid_agents4(s->n), kThreads, 0, st>>>(s->people, s->state, s->pars, A);
+    day_mid_kernel<<<(int)((s->n + kMidChunk - 1) / kMidChunk), kThreads, 0, st>>>(s->people, s->state, s->pars, A);
     CVB_LAUNCH_CHECK();
     return 0;
 }
@@ -887,8 +806,10 @@ int cvb_run_days(cvb_sim* s, int32_t t0, int32_t t1, cvb_stream st_) {
             CVB_REQUIRE(!(plan.trace.trace_prob[l] > 0.0) || s->layers[l].n_edges == 0 || ((s->adj_layer_mask >> l) & 1u),
                         "cvb_run_days: traced layer %d is not covered by the adjacency", l);
     }
-    if (!s->state_valid) {
+    bool packed = false;
+    if (!s->state_valid || t0 == 0) {
         int64_t out[26];
+        packed = true;
         if (pack_or_check(s, t0 - 1, false, out, st)) return 1;
         CVB_REQUIRE(out[0] == 0, "cvb_run_days: %lld agents are in a state the packed word cannot express (several by-variant rows set, or NAbs without a peak)", (long long)out[0]);
         s->state_valid = 1;
@@ -903,7 +824,7 @@ int cvb_run_days(cvb_sim* s, int32_t t0, int32_t t1, cvb_stream st_) {
         const bool trace = plan.has_trace && t >= plan.trace_start && (plan.trace_end < 0 || t <= plan.trace_end);
         {
             TimedScope ts(s, CVB_TIMED_day_begin, st);
-            int rc = t > t0 ? launch_day_begin<true, true>(s, t, test, trace, st) : launch_day_begin<false, true>(s, t, test, trace, st);
+            int rc = t > t0 ? launch_day_begin<true, true>(s, t, test, trace, false, st) : launch_day_begin<false, true>(s, t, test, trace, packed, st);
             if (rc) return rc;
         }
         if (trace) { TimedScope ts(s, CVB_TIMED_trace, st); if (launch_trace_sparse2(s, t, &plan.trace, st)) return 1; }
@@ -913,7 +834,7 @@ int cvb_run_days(cvb_sim* s, int32_t t0, int32_t t1, cvb_stream st_) {
     }
     s->state_valid = 1;                                     // (the edge pass / layer regeneration above do not touch People flags)
     TimedScope ts(s, CVB_TIMED_day_end, st);
-    return launch_day_begin<true, false>(s, t1, false, false, st);      // closes day t1 - 1 (its argument is the day AFTER the one it closes)
+    return launch_day_begin<true, false>(s, t1, false, false, false, st);      // closes day t1 - 1 (its argument is the day AFTER the one it closes)
 }
 
 }  // extern "C"

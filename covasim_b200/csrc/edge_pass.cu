@@ -347,6 +347,9 @@ __global__ void __launch_bounds__(kThreads) edge_pass_sparse2_kernel(TransRecord
         const uint4* __restrict__ adj, const uint4* __restrict__ ents, const unsigned int* __restrict__ n_trans_ptr,
         unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand,
         unsigned long long* __restrict__ work_row) {
+    __shared__ unsigned long long s_visited;
+    if (threadIdx.x == 0) s_visited = 0;
+    __syncthreads();
     const unsigned int n_trans = *n_trans_ptr;
     unsigned long long visited = 0;
     const int64_t n = ep.n;
@@ -394,7 +397,12 @@ __global__ void __launch_bounds__(kThreads) edge_pass_sparse2_kernel(TransRecord
             }
         }
     }
-    if (visited) atomicAdd(work_row, visited);
+    // work accounting for the roofline (one global atomic per CTA: ~10^4 same-address atomics would serialise in L2)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) visited += __shfl_down_sync(0xFFFFFFFFu, visited, d);
+    if (lane_id() == 0 && visited) atomicAdd(&s_visited, visited);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_visited) atomicAdd(work_row, s_visited);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(work_row + 1, (unsigned long long)n_trans);
 }
 

@@ -23,6 +23,8 @@ struct InfectArgs {
     const int32_t* hit_src;  // partitioned edge pass: cand[] lists every successful transmission, with its source and key; the
     const unsigned long long* hit_key;   // entry whose key equals infect_key[target] is the winner (NULL: cand[] lists unique targets)
     int64_t hit_cap;
+    const unsigned long long* beds_direct;   // fused pipeline: {n_severe, n_critical} of today's counter row (running totals); NULL: beds[t]
+    unsigned long long* vcounters_row;       // today's by-variant counter row (stock differences)
 };
 
 __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __grid_constant__ cvb_pars pars, const __grid_constant__ LayerTable L,
@@ -30,8 +32,10 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
         unsigned long long* __restrict__ infect_key, const unsigned long long* __restrict__ beds, ResultPtrs res, LogPtrs log,
         uint32_t* __restrict__ S /* packed state words of the fused day pipeline (day_fused.cu), or NULL */) {
     __shared__ int s_cnt[INF_NK + 3 * CVB_MAX_VARIANTS];
+    __shared__ int s_delta[kStockSlots];
     const int NK = INF_NK + 3 * CVB_MAX_VARIANTS;
     if (threadIdx.x < NK) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < kStockSlots) s_delta[threadIdx.x] = 0;
     __syncthreads();
     int c[INF_NK] = {0, 0};
     int cv[3 * CVB_MAX_VARIANTS];
@@ -42,8 +46,9 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
     const int32_t t = ia.t;
     unsigned int n_cand = *n_cand_ptr;
     if (ia.hit_key && (int64_t)n_cand > ia.hit_cap) n_cand = (unsigned int)ia.hit_cap;
-    const bool hosp_max = ia.hosp_max >= 0 ? ia.hosp_max != 0 : (pars.n_beds_hosp >= 0 && (long long)beds[(int64_t)t * 2 + 0] > pars.n_beds_hosp);
-    const bool icu_max = ia.icu_max >= 0 ? ia.icu_max != 0 : (pars.n_beds_icu >= 0 && (long long)beds[(int64_t)t * 2 + 1] > pars.n_beds_icu);
+    const unsigned long long* bd = ia.beds_direct ? ia.beds_direct : beds + (int64_t)t * 2;
+    const bool hosp_max = ia.hosp_max >= 0 ? ia.hosp_max != 0 : (pars.n_beds_hosp >= 0 && (long long)bd[0] > pars.n_beds_hosp);
+    const bool icu_max = ia.icu_max >= 0 ? ia.icu_max != 0 : (pars.n_beds_icu >= 0 && (long long)bd[1] > pars.n_beds_icu);
     const float tf = (float)t;
 
     // Sixteen lanes per newly infected agent: lane s of the half-warp computes the Philox draw of slot s (its uniform, and
@@ -225,17 +230,19 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
         if (S) {
             // the packed state word follows (bit layout: day_fused.cu): not susceptible / naive / recovered / diagnosed any more, no
             // diagnosis date, exposed to variant v, no natural-immunity source until recovery; antibodies from now on if waning
-            uint32_t sk = S[i];
-            sk &= ~((1u << 0) | (1u << 1) | (1u << 9) | (1u << 8) | (1u << 19) | (15u << 24) | (15u << 28));
-            sk |= (1u << 2) | ((uint32_t)(v + 1) << 24);
-            if (pars.use_waning) sk |= 1u << 16;
+            const uint32_t so = S[i];
+            uint32_t sk = so & ~(SB_SUS | SB_NAIVE | SB_REC | SB_DIAG | SB_DPEND | kEbvMask | kRvMask);
+            sk |= SB_EXP | ((uint32_t)(v + 1) << kEbvShift);
+            if (pars.use_waning) sk |= SB_HAS_NAB;
             S[i] = sk;
+            stock_delta(so, sk, s_delta);
         }
     }
 
     reduce_counters(c, s_cnt);
     reduce_counters(cv, s_cnt + INF_NK);
     __syncthreads();
+    if (S) flush_stock_delta(s_delta, res.counters + (int64_t)t * CVB_N_COUNTERS, ia.vcounters_row, pars.n_variants);
     if (ia.count_flows && threadIdx.x < NK && s_cnt[threadIdx.x]) {
         const int k = threadIdx.x;
         const unsigned long long val = (unsigned long long)s_cnt[k];
@@ -276,6 +283,8 @@ static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t lis
     ia.hosp_max = hosp_max; ia.icu_max = icu_max;
     ia.id0 = s->partitioned ? s->id0 : 0;
     ia.hit_src = hits ? s->hit_src : nullptr; ia.hit_key = hits ? s->hit_key : nullptr; ia.hit_cap = s->hit_cap;
+    ia.beds_direct = with_state ? s->res.counters + (int64_t)t * CVB_N_COUNTERS + CVB_C_n_severe : nullptr;      // n_severe, n_critical are adjacent
+    ia.vcounters_row = s->res.vcounters + (int64_t)t * s->nv * CVB_N_VCOUNTERS;
     int grid = grid_for(max_items * 16, kThreads, 148 * 4);       // sixteen lanes per agent
     infect_kernel<<<grid, kThreads, 0, st>>>(s->people, s->pars, L, ia, s->cand, s->n_cand, s->infect_key, s->beds, s->res, s->log,
                                              with_state ? s->state : nullptr);

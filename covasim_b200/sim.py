@@ -807,12 +807,14 @@ class Sim:
             torch.cuda.set_device(self.device)
         if self._fusable_day(t):                                   # nothing for the host to decide today: the fused day kernels
             people.t = t
-            self.rescale()
             self._run_block(t, t + 1)
             if pars['analyzers']:
+                self.t, self.complete = t, False                   # analyzers see the day that has just been simulated (sim.py:677-678)
                 for an in pars['analyzers']:
                     an(self)
                 _capi.call('cvb_state_invalidate', h)              # an analyzer may have written People arrays
+                self.t = t + 1
+                self.complete = self.t == self.npts
             return
         _capi.call('cvb_state_invalidate', h)                      # Python (interventions, rescaling) may write People arrays today
         people.t = t
@@ -903,20 +905,39 @@ class Sim:
             raise AlreadyRunError(f'Simulation is currently at t={self.t}, requested to run until t={until} which has already been reached')
         if self.complete:
             raise AlreadyRunError('Simulation is already complete (call sim.initialize() to re-run)')
+        if self._advance(until):
+            return self
+        if self.complete:
+            self.finalize(restore_pars=restore_pars)
+        return self
+
+    def _advance(self, until):
+        ''' The day loop of run(): stretches of days that need no host decision are ONE C-ABI call each; True if stopping_func fired '''
         _capi.call('cvb_state_invalidate', self._handle)          # the caller may have written People arrays since the last run
         while self.t < until:
             if self.pars['stopping_func'] and self.pars['stopping_func'](self):
-                return self
+                return True
             if self.rng_mode == 'philox' and not self.pars['analyzers'] and not self.pars['stopping_func'] and self._fusable_day(self.t):
-                t1 = self.t + 1                                    # as many days as need no host decision, in ONE C-ABI call
+                t1 = self.t + 1
                 while t1 < until and self._fusable_day(t1):
                     t1 += 1
                 self._run_block(self.t, t1)
             else:
                 self.step()
-        if self.complete:
-            self.finalize(restore_pars=restore_pars)
-        return self
+        return False
+
+    def fused_timing(self, enable=None):
+        '''
+        Per-kernel device time of the fused day loop: ``fused_timing(True)`` / ``(False)`` switches the CUDA-event timing of
+        cvb_run_days on / off; ``fused_timing()`` returns {kernel: (milliseconds, launches)} accumulated since the last read.
+        '''
+        if enable is not None:
+            _capi.call('cvb_timing_enable', self._handle, int(bool(enable)))
+            return None
+        ms = np.zeros(len(_capi.TIMED_KINDS), dtype=np.float64)
+        cnt = np.zeros(len(_capi.TIMED_KINDS), dtype=np.int64)
+        _capi.call('cvb_timing_read', self._handle, ms.ctypes.data, cnt.ctypes.data)
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_capi.TIMED_KINDS)}
 
     # ---- results ---------------------------------------------------------------------------------------
     def sync_results(self):

@@ -47,7 +47,7 @@ def test_blocks_of_seven_days_with_state_checks(cv):
     sim.set_seed()
     orc.rng.set_seed(orc.pars['rand_seed'])
     first = True
-    while sim.t < sim.npts:
+    while not sim.complete:
         until = min(sim.t + 7, sim.npts)
         sim.run(until=until, reset_seed=first)
         first = False

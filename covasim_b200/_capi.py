@@ -126,6 +126,7 @@ PROTOTYPES = dict(
     cvb_plan_dynamic_layers=[_P, C.c_uint32],
     cvb_run_days=[_P, _i32, _i32, _P],
     cvb_state_invalidate=[_P],
+    cvb_tune=[_P, _i32, _i32],
     cvb_timing_enable=[_P, _i32],
     cvb_timing_read=[_P, _P, _P],
     cvb_state_check=[_P, _i32, _P, _P],

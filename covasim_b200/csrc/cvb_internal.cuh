@@ -123,6 +123,8 @@ struct cvb_sim {
     uint4* trans_ent;                               // [N][2] today's transmitters {agent, row length, row begin, rel_trans, code}
     uint4* case_ent;                                // [N] today's traced cases {agent, row length, row begin}
     unsigned long long* stock_base;                 // absolute stock counts of the packed words after a pack (counter-row layout)
+    int32_t begin_grid;                             // grid of the last day_begin_kernel launch (= number of per-CTA partial sums)
+    int32_t tune[8];                                // launch-shape overrides (cvb_tune): 0/1 day_begin CTA size / chunk, 2/3 day_mid, 4/5 edge pass lanes / unroll
     cvb::DayPlan* plan;                             // built-in interventions the C day loop runs itself (cvb_plan_*)
     cvb::FusedTiming* timing;                       // per-kernel CUDA-event timing of the day loop, when enabled
 };
@@ -156,6 +158,24 @@ inline int grid_for(int64_t n, int per_block = kThreads, int64_t cap = 148 * 16)
 }
 
 #if defined(__CUDACC__)
+// ---- programmatic dependent launch (the fused day pipeline is a chain of five dependent kernels per day) -----------------------
+// A kernel launched with launch_pdl may be scheduled while its predecessor in the stream is still draining: its CTAs run their
+// prologue (parameters, shared-memory setup) and then block in pdl_wait() until the predecessor has completed and its writes are
+// visible.  pdl_trigger() tells the scheduler that the successor may be brought in; every kernel of the chain calls it first.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // ---- warp / block primitives ---------------------------------------------------------------
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }

@@ -112,7 +112,7 @@ struct DayBeginArgs {
     const double* nab_kin; int64_t nab_kin_len;
     unsigned long long* counters; unsigned long long* vcounters;
     const unsigned long long* base_row; const unsigned long long* base_vrow;    // yesterday's stock counts (PRE: copied into today's row)
-    double* partial; unsigned int* ticket; double* sums;       // sums = table base [npts][4]
+    double* partial;                                           // [gridDim.x][3] per-CTA float64 sums, added up by the next kernel
     unsigned int* n_trans; unsigned int* n_case;
     // test_prob
     cvb_test_prob_pars tp; int32_t test_plain;                 // test_plain: quarantine state does not change the probability
@@ -148,7 +148,6 @@ __global__ void __launch_bounds__(kThreads, 3) day_begin_kernel(PeoplePtrs P, ui
     __shared__ int s_delta[kStockSlots];
     __shared__ uint4 s_queue[(kThreads / 32) * kImmQueueCap2];
     __shared__ double s_sum[3][kThreads / 32];
-    __shared__ bool s_last;
     const int lane = lane_id();
     const unsigned lt_mask = (1u << lane) - 1u;
     uint4* q_imm = s_queue + warp_id() * kImmQueueCap2;
@@ -159,8 +158,10 @@ __global__ void __launch_bounds__(kThreads, 3) day_begin_kernel(PeoplePtrs P, ui
     const bool waning = A.waning != 0;
     const float tf = (float)t;
     const float qnan = nanf32();
+    pdl_trigger();
     for (int k = threadIdx.x; k < F_NK + CVB_MAX_VARIANTS; k += blockDim.x) s_flow[k] = 0;
     for (int k = threadIdx.x; k < kStockSlots; k += blockDim.x) s_delta[k] = 0;
+    pdl_wait();                                                 // everything below reads what the previous kernel wrote
     if (PRE && blockIdx.x == 0) {
         if (threadIdx.x == 0) *A.n_trans = 0;                  // today's transmitter list starts empty (filled by day_mid_kernel)
         if (threadIdx.x < kStockSlots) {                        // today's stock counts start from yesterday's
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(kThreads, 3) day_begin_kernel(PeoplePtrs P, ui
     __syncthreads();
     if (threadIdx.x < 3) {
         double v = 0.0;
-        for (int wq = 0; wq < kThreads / 32; ++wq) v += s_sum[threadIdx.x][wq];
+        for (int wq = 0; wq < (int)(blockDim.x >> 5); ++wq) v += s_sum[threadIdx.x][wq];
         A.partial[(int64_t)blockIdx.x * 3 + threadIdx.x] = v;
     }
     if ((PRE || TEST) && threadIdx.x < F_NK + CVB_MAX_VARIANTS && s_flow[threadIdx.x]) {
@@ -376,24 +377,26 @@ __global__ void __launch_bounds__(kThreads, 3) day_begin_kernel(PeoplePtrs P, ui
         }
     }
     if (PRE || TEST) flush_stock_delta(s_delta, A.counters + (int64_t)t * CVB_N_COUNTERS, A.vcounters + (int64_t)t * nv * CVB_N_VCOUNTERS, nv);
-    // the last CTA to finish adds up the per-CTA partial sums in a fixed order (deterministic float64 sums, no second launch)
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(A.ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (s_last && threadIdx.x < 96) {
-        __threadfence();
-        const int q = threadIdx.x >> 5;
+}
+
+// The per-CTA partial sums of the day_begin_kernel that has just finished, added up in a fixed order by ONE warp-triple of the next
+// kernel in the stream (deterministic float64 sums; no ticket / fence / extra barrier in the big kernel)
+__device__ __forceinline__ void sum_partials(const double* __restrict__ partial, int n_part, double* __restrict__ sums, int32_t t_end, int32_t t_pre) {
+    if (threadIdx.x < 96) {
+        const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
         double v = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(A.partial + (int64_t)b * 3 + q);
+        for (int b = lane; b < n_part; b += 32) v += __ldcg(partial + (int64_t)b * 3 + q);
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, d);
         if (lane == 0) {
-            if (q == 0) { if (END) A.sums[(int64_t)(t - 1) * 4 + 0] = v; }
-            else if (PRE) A.sums[(int64_t)t * 4 + q] = v;
+            if (q == 0) { if (t_end >= 0) sums[(int64_t)t_end * 4 + 0] = v; }
+            else if (t_pre >= 0) sums[(int64_t)t_pre * 4 + q] = v;
         }
-        if (threadIdx.x == 0) *A.ticket = 0;
     }
+}
+__global__ void sum_partials_kernel(const double* __restrict__ partial, int n_part, double* __restrict__ sums, int32_t t_end, int32_t t_pre) {
+    pdl_wait();
+    sum_partials(partial, n_part, sums, t_end, t_pre);
 }
 
 // ================================================================================================================================
@@ -405,6 +408,7 @@ constexpr int kMidChunk = 1024;                     // agents per CTA: bounds th
 struct DayMidArgs {
     int64_t n;
     int32_t t, nv, horizon, dense;                  // dense: some layer is streamed densely today (records for everyone + ts8 + bitmap)
+    int32_t chunk;                                  // agents per CTA (<= kMidChunk)
     float* quar_slot;
     unsigned long long* counters; unsigned long long* vcounters;
     TransRecords rec;
@@ -413,6 +417,8 @@ struct DayMidArgs {
     uint4* trans_ent; unsigned int* n_trans;
     unsigned int* n_cand; unsigned int* n_case;
     int32_t* trans_list;                            // the plain list, in the same order as the entries
+    const double* partial; int32_t n_part, t_end;   // day_begin_kernel's per-CTA sums (t_end = t - 1 if it closed a day, else -1)
+    double* sums;
 };
 
 __global__ void __launch_bounds__(kThreads, 4) day_mid_kernel(PeoplePtrs P, uint32_t* __restrict__ S, const __grid_constant__ cvb_pars pars,
@@ -421,10 +427,13 @@ __global__ void __launch_bounds__(kThreads, 4) day_mid_kernel(PeoplePtrs P, uint
     __shared__ int s_delta[kStockSlots];
     __shared__ uint4 s_ent[2 * kMidChunk];                                   // this CTA's transmitter entries, flushed with ONE global atomic
     __shared__ unsigned int s_n_ent, s_base;
+    pdl_trigger();
     if (threadIdx.x < M_NK) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x < kStockSlots) s_delta[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_n_ent = 0;
+    pdl_wait();                                                 // everything below reads what the previous kernels wrote
     if (blockIdx.x == 0 && threadIdx.x == 0) { *A.n_cand = 0; *A.n_case = 0; }   // today's candidates start empty; the case list was consumed
+    if (blockIdx.x == gridDim.x - 1) sum_partials(A.partial, A.n_part, A.sums, A.t_end, A.t);     // day_begin_kernel's float64 sums
     __syncthreads();
     const int64_t n = A.n;
     const int32_t t = A.t;
@@ -439,8 +448,8 @@ __global__ void __launch_bounds__(kThreads, 4) day_mid_kernel(PeoplePtrs P, uint
     const float* d_inf = PF(P, date_infectious); const float* d_dead = PF(P, date_dead);
     const float* sus_imm = PF(P, sus_imm);
 
-    const int64_t lo = (int64_t)blockIdx.x * kMidChunk;
-    const int64_t hi = lo + kMidChunk < n ? lo + kMidChunk : n;
+    const int64_t lo = (int64_t)blockIdx.x * A.chunk;
+    const int64_t hi = lo + A.chunk < n ? lo + A.chunk : n;
     const int64_t hi_pad = lo + (hi - lo + 31) / 32 * 32;
     for (int64_t i = lo + threadIdx.x; i < hi_pad; i += blockDim.x) {
         const bool in = i < hi;
@@ -631,9 +640,12 @@ static int launch_day_begin(cvb_sim* s, int32_t t, bool test, bool tsel, bool ba
         A.base_row = base_from_pack ? base_row(s) : s->res.counters + (int64_t)(t - 1) * CVB_N_COUNTERS;
         A.base_vrow = base_from_pack ? base_vrow(s) : s->res.vcounters + (int64_t)(t - 1) * s->nv * CVB_N_VCOUNTERS;
     }
-    const int grid = (int)((s->n + kBeginChunk - 1) / kBeginChunk);
+    const int threads = s->tune[0] > 0 ? s->tune[0] : kThreads;
+    A.chunk = s->tune[1] > 0 ? s->tune[1] : kBeginChunk;
+    const int grid = (int)((s->n + A.chunk - 1) / A.chunk);
     if (ensure_f64(&s->partial, &s->partial_cap, (int64_t)grid * 3)) return 1;
-    A.partial = s->partial; A.ticket = reinterpret_cast<unsigned int*>(s->dev_scalars + 8); A.sums = s->res.sums;
+    A.partial = s->partial;
+    s->begin_grid = grid;
     A.n_trans = s->n_trans; A.n_case = s->n_case_list;
     A.seed = s->seed;
     if (test) {
@@ -641,7 +653,7 @@ static int launch_day_begin(cvb_sim* s, int32_t t, bool test, bool tsel, bool ba
         A.test_plain = (A.tp.symp_quar_prob == A.tp.symp_prob && A.tp.asymp_quar_prob == A.tp.asymp_prob) ? 1 : 0;
     }
     A.adj_ptr = s->adj_ptr; A.case_ent = s->case_ent;
-#define CVB_DB(T1, T2) day_begin_kernel<END, PRE, T1, T2><<<grid, kThreads, 0, st>>>(s->people, s->state, s->pars, A)
+#define CVB_DB(T1, T2) CVB_CHECK(launch_pdl(day_begin_kernel<END, PRE, T1, T2>, grid, threads, 0, st, s->people, s->state, s->pars, A))
     if constexpr (PRE) {
         if (test && tsel) CVB_DB(true, true);
         else if (test) CVB_DB(true, false);
@@ -680,7 +692,7 @@ static int ensure_records_fused(cvb_sim* s, bool& dense_any) {
     return 0;
 }
 
-static int launch_day_mid(cvb_sim* s, int32_t t, cudaStream_t st) {
+static int launch_day_mid(cvb_sim* s, int32_t t, bool closes_previous, cudaStream_t st) {
     bool dense_any = false;
     if (ensure_records_fused(s, dense_any)) return 1;
     DayMidArgs A;
@@ -690,7 +702,10 @@ static int launch_day_mid(cvb_sim* s, int32_t t, cudaStream_t st) {
     A.counters = s->res.counters; A.vcounters = s->res.vcounters; A.rec = s->rec; A.inf_bits = s->inf_bits;
     A.adj_ptr = (s->adj && s->adj_layer_mask) ? s->adj_ptr : nullptr;
     A.trans_ent = s->trans_ent; A.n_trans = s->n_trans; A.n_cand = s->n_cand; A.n_case = s->n_case_list; A.trans_list = s->trans_list;
-    day_mid_kernel<<<(int)((s->n + kMidChunk - 1) / kMidChunk), kThreads, 0, st>>>(s->people, s->state, s->pars, A);
+    A.partial = s->partial; A.n_part = s->begin_grid; A.t_end = closes_previous ? t - 1 : -1; A.sums = s->res.sums;
+    A.chunk = s->tune[3] > 0 && s->tune[3] <= kMidChunk ? s->tune[3] : kMidChunk;
+    const int threads = s->tune[2] > 0 ? s->tune[2] : kThreads;
+    CVB_CHECK(launch_pdl(day_mid_kernel, (int)((s->n + A.chunk - 1) / A.chunk), threads, 0, st, s->people, s->state, s->pars, A));
     CVB_LAUNCH_CHECK();
     return 0;
 }
@@ -781,6 +796,15 @@ int cvb_plan_dynamic_layers(cvb_sim* s, uint32_t layer_mask) {
     return 0;
 }
 
+int cvb_tune(cvb_sim* s, int32_t what, int32_t value) {
+    CVB_REQUIRE(s && what >= 0 && what < 8, "cvb_tune: bad argument");
+    if (what == 0 || what == 2) CVB_REQUIRE(value == 0 || (value >= 128 && value <= kThreads && value % 32 == 0), "cvb_tune: CTA size must be a multiple of 32 in [128, %d]", kThreads);
+    if (what == 1) CVB_REQUIRE(value == 0 || (value >= 32 && value % 32 == 0), "cvb_tune: chunk must be a multiple of 32");
+    if (what == 3) CVB_REQUIRE(value == 0 || (value >= 32 && value % 32 == 0 && value <= kMidChunk), "cvb_tune: chunk must be a multiple of 32 up to %d", kMidChunk);
+    s->tune[what] = value;
+    return 0;
+}
+
 int cvb_state_invalidate(cvb_sim* s) {
     CVB_REQUIRE(s, "cvb_state_invalidate: NULL handle");
     s->state_valid = 0;
@@ -828,13 +852,16 @@ int cvb_run_days(cvb_sim* s, int32_t t0, int32_t t1, cvb_stream st_) {
             if (rc) return rc;
         }
         if (trace) { TimedScope ts(s, CVB_TIMED_trace, st); if (launch_trace_sparse2(s, t, &plan.trace, st)) return 1; }
-        { TimedScope ts(s, CVB_TIMED_day_mid, st); if (launch_day_mid(s, t, st)) return 1; }
+        { TimedScope ts(s, CVB_TIMED_day_mid, st); if (launch_day_mid(s, t, t > t0, st)) return 1; }
         { TimedScope ts(s, CVB_TIMED_edge_pass, st); if (edge_pass_impl(s, t, st, true)) return 1; }
         { TimedScope ts(s, CVB_TIMED_infect, st); if (launch_infect_winners(s, t, true, st)) return 1; }
     }
     s->state_valid = 1;                                     // (the edge pass / layer regeneration above do not touch People flags)
     TimedScope ts(s, CVB_TIMED_day_end, st);
-    return launch_day_begin<true, false>(s, t1, false, false, false, st);      // closes day t1 - 1 (its argument is the day AFTER the one it closes)
+    if (launch_day_begin<true, false>(s, t1, false, false, false, st)) return 1;      // closes day t1 - 1 (its argument is the day AFTER the one it closes)
+    sum_partials_kernel<<<1, 96, 0, st>>>(s->partial, s->begin_grid, s->res.sums, t1 - 1, -1);
+    CVB_LAUNCH_CHECK();
+    return 0;
 }
 
 }  // extern "C"

@@ -342,21 +342,25 @@ __global__ void __launch_bounds__(kThreads) edge_pass_sparse_kernel(TransRecords
 // list -> row pointers -> own record -> entries -> records).  G lanes share a transmitter and each lane keeps U adjacency entries
 // in flight: all U entry loads are issued, then all U record gathers, then the arithmetic -- a row of 32 entries costs two
 // memory round trips per group.  Same probability chain, Philox key and winner key as every other form.
+// The kernel is launched with programmatic dependent launch, so it may be resident while day_mid_kernel is still writing the
+// entries and records: they are read with L2 loads (ld.global.cg), never through the non-coherent path.
 template <bool MULTI, int G, int U>
 __global__ void __launch_bounds__(kThreads) edge_pass_sparse2_kernel(TransRecords rec, const __grid_constant__ EdgeParams ep,
         const uint4* __restrict__ adj, const uint4* __restrict__ ents, const unsigned int* __restrict__ n_trans_ptr,
         unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand,
         unsigned long long* __restrict__ work_row) {
     __shared__ unsigned long long s_visited;
+    pdl_trigger();
     if (threadIdx.x == 0) s_visited = 0;
     __syncthreads();
-    const unsigned int n_trans = *n_trans_ptr;
+    pdl_wait();                                                 // the entries and records are written by day_mid_kernel
+    const unsigned int n_trans = __ldcg(n_trans_ptr);           // (L2 loads: the kernel may have been resident while its inputs were written)
     unsigned long long visited = 0;
     const int64_t n = ep.n;
     const int gl = threadIdx.x & (G - 1);
     const unsigned int groups_total = (gridDim.x * blockDim.x) / G;
     for (unsigned int ti = (blockIdx.x * blockDim.x + threadIdx.x) / G; ti < n_trans; ti += groups_total) {
-        const uint4 e0 = __ldg(ents + 2 * (int64_t)ti), e1 = __ldg(ents + 2 * (int64_t)ti + 1);
+        const uint4 e0 = __ldcg(ents + 2 * (int64_t)ti), e1 = __ldcg(ents + 2 * (int64_t)ti + 1);
         const int len = (int)e0.y;
         const long long beg = (long long)(((unsigned long long)e0.w << 32) | (unsigned long long)e0.z);
         const float rt = __uint_as_float(e1.x);
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(kThreads) edge_pass_sparse2_kernel(TransRecord
                 en[u] = off < len ? __ldg(adj + beg + off) : make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) rj[u] = en[u].z != 0xFFFFFFFFu ? __ldg(rec.rec + en[u].x) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            for (int u = 0; u < U; ++u) rj[u] = en[u].z != 0xFFFFFFFFu ? __ldcg(rec.rec + en[u].x) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 if (en[u].z == 0xFFFFFFFFu || rj[u].y == 0.0f) continue;      // past the row's end / target not susceptible
@@ -383,7 +387,7 @@ __global__ void __launch_bounds__(kThreads) edge_pass_sparse2_kernel(TransRecord
                 const float t_i = record_trans(rt, ci, ep.asymp_factor, ep.iso_factor[l], ep.quar_factor[l], ep.beta_layer[l], ep.vl_early, ep.vl_late);
                 if (t_i == 0.0f) continue;                                    // cannot transmit on this layer
                 float imm = rj[u].z;
-                if (MULTI && vi > 0) imm = __ldg(rec.sus_imm + (int64_t)vi * n + j);
+                if (MULTI && vi > 0) imm = __ldcg(rec.sus_imm + (int64_t)vi * n + j);
                 const float s_j = record_sus(rj[u].y, __float_as_uint(rj[u].w), ep.quar_factor[l], imm);
                 const float p = edge_prob(beta_v, __uint_as_float(en[u].w), t_i, s_j);
                 if (p != 0.0f) {
@@ -635,8 +639,9 @@ int cvb::edge_pass_impl(cvb_sim* s, int32_t t, cudaStream_t st, bool from_entrie
         unsigned long long* work_row = s->edge_work + (int64_t)t * 2;
         if (from_entries) {
             CVB_REQUIRE(s->trans_ent, "cvb_edge_pass: transmitter entries missing");
-            if (multi) edge_pass_sparse2_kernel<true, 8, 4><<<grid, kThreads, 0, st>>>(s->rec, ep, s->adj, s->trans_ent, s->n_trans, s->infect_key, s->cand, s->n_cand, work_row);
-            else edge_pass_sparse2_kernel<false, 8, 4><<<grid, kThreads, 0, st>>>(s->rec, ep, s->adj, s->trans_ent, s->n_trans, s->infect_key, s->cand, s->n_cand, work_row);
+            const uint4* adj = s->adj; const uint4* ents = s->trans_ent; const unsigned int* nt = s->n_trans;
+            if (multi) CVB_CHECK(launch_pdl(edge_pass_sparse2_kernel<true, 8, 4>, grid, kThreads, 0, st, s->rec, ep, adj, ents, nt, s->infect_key, s->cand, s->n_cand, work_row));
+            else CVB_CHECK(launch_pdl(edge_pass_sparse2_kernel<false, 8, 4>, grid, kThreads, 0, st, s->rec, ep, adj, ents, nt, s->infect_key, s->cand, s->n_cand, work_row));
         }
         else if (multi) edge_pass_sparse_kernel<true><<<grid, kThreads, 0, st>>>(s->rec, ep, s->adj_ptr, s->adj, s->trans_list, s->n_trans,
                                                                                s->infect_key, s->cand, s->n_cand, work_row);

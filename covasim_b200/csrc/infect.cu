@@ -33,6 +33,10 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
         uint32_t* __restrict__ S /* packed state words of the fused day pipeline (day_fused.cu), or NULL */) {
     __shared__ int s_cnt[INF_NK + 3 * CVB_MAX_VARIANTS];
     __shared__ int s_delta[kStockSlots];
+    pdl_trigger();
+    pdl_wait();                                                // the candidates come from the edge pass before this kernel
+    // the grid is sized for a large outbreak: CTAs whose first pair of candidates does not exist have nothing to do at all
+    if ((unsigned long long)blockIdx.x * (blockDim.x >> 5) * 2 >= (unsigned long long)__ldcg(n_cand_ptr)) return;
     const int NK = INF_NK + 3 * CVB_MAX_VARIANTS;
     if (threadIdx.x < NK) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x < kStockSlots) s_delta[threadIdx.x] = 0;
@@ -44,7 +48,7 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
 
     const int64_t n = ia.n;
     const int32_t t = ia.t;
-    unsigned int n_cand = *n_cand_ptr;
+    unsigned int n_cand = __ldcg(n_cand_ptr);                  // (L2 loads: the kernel may have been resident while the edge pass wrote them)
     if (ia.hit_key && (int64_t)n_cand > ia.hit_cap) n_cand = (unsigned int)ia.hit_cap;
     const unsigned long long* bd = ia.beds_direct ? ia.beds_direct : beds + (int64_t)t * 2;
     const bool hosp_max = ia.hosp_max >= 0 ? ia.hosp_max != 0 : (pars.n_beds_hosp >= 0 && (long long)bd[0] > pars.n_beds_hosp);
@@ -61,7 +65,7 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
     for (unsigned int jw = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; jw < n_cand; jw += warps_total * 2) {
         const unsigned int j = jw + half;
         const bool valid = j < n_cand;
-        const int64_t i = valid ? cand[j] : 0;
+        const int64_t i = valid ? __ldcg(cand + j) : 0;
         const int64_t gi = i + ia.id0;                             // global id: Philox index and logged target
         const u32x4 words = keyed_words(ia.seed, P_INFECT, 0, t, gi, (uint32_t)slot);
         const double u_mine = u53(words.x, words.y);
@@ -286,8 +290,12 @@ static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t lis
     ia.beds_direct = with_state ? s->res.counters + (int64_t)t * CVB_N_COUNTERS + CVB_C_n_severe : nullptr;      // n_severe, n_critical are adjacent
     ia.vcounters_row = s->res.vcounters + (int64_t)t * s->nv * CVB_N_VCOUNTERS;
     int grid = grid_for(max_items * 16, kThreads, 148 * 4);       // sixteen lanes per agent
-    infect_kernel<<<grid, kThreads, 0, st>>>(s->people, s->pars, L, ia, s->cand, s->n_cand, s->infect_key, s->beds, s->res, s->log,
-                                             with_state ? s->state : nullptr);
+    {
+        const int32_t* cand = s->cand; const unsigned int* nc = s->n_cand; const unsigned long long* beds = s->beds;
+        uint32_t* state = with_state ? s->state : nullptr;
+        if (with_state) CVB_CHECK(launch_pdl(infect_kernel, grid, kThreads, 0, st, s->people, s->pars, L, ia, cand, nc, s->infect_key, beds, s->res, s->log, state));
+        else infect_kernel<<<grid, kThreads, 0, st>>>(s->people, s->pars, L, ia, cand, nc, s->infect_key, beds, s->res, s->log, state);
+    }
     CVB_LAUNCH_CHECK();
     return 0;
 }

@@ -234,11 +234,13 @@ __device__ __forceinline__ void trace_notify2(const PeoplePtrs& P, uint32_t* __r
 
 __global__ void __launch_bounds__(kThreads) trace_sparse2_kernel(PeoplePtrs P, uint32_t* __restrict__ S, const __grid_constant__ TraceTable T,
         const uint4* __restrict__ adj, const uint4* __restrict__ case_ent, const unsigned int* __restrict__ n_case_ptr, uint32_t layer_mask) {
-    const unsigned int n_cases = *n_case_ptr;
+    pdl_trigger();
+    pdl_wait();                                                        // the cases are written by day_begin_kernel
+    const unsigned int n_cases = __ldcg(n_case_ptr);                   // (L2 loads: this kernel may have been resident while they were written)
     const int lane = lane_id();
     const unsigned int warps_total = (gridDim.x * blockDim.x) >> 5;
     for (unsigned int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < n_cases; ci += warps_total) {
-        const uint4 ce = __ldg(case_ent + ci);
+        const uint4 ce = __ldcg(case_ent + ci);
         const int len = (int)ce.y;
         const long long beg = (long long)(((unsigned long long)ce.w << 32) | (unsigned long long)ce.z);
         for (int off = lane; off < len; off += 32) {
@@ -438,7 +440,10 @@ int cvb::launch_trace_sparse2(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, c
     if (build_trace_table(s, t, tr, s->adj_layer_mask, kTileEdges, T, acc, any_sparse)) return 1;
     CVB_REQUIRE(acc == 0, "fused day: a traced layer is not covered by the adjacency");
     if (!any_sparse) return 0;
-    trace_sparse2_kernel<<<148 * 2, kThreads, 0, st>>>(s->people, s->state, T, s->adj, s->case_ent, s->n_case_list, s->adj_layer_mask);
+    {
+        const uint4* adj = s->adj; const uint4* ce = s->case_ent; const unsigned int* nc = s->n_case_list;
+        CVB_CHECK(launch_pdl(trace_sparse2_kernel, 148 * 2, kThreads, 0, st, s->people, s->state, T, adj, ce, nc, s->adj_layer_mask));
+    }
     CVB_LAUNCH_CHECK();
     return 0;
 }

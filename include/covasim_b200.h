@@ -277,6 +277,9 @@ int cvb_plan_contact_tracing(cvb_sim* s, const cvb_trace_pars* host_pars, int32_
 int cvb_plan_dynamic_layers(cvb_sim* s, uint32_t layer_mask);
 int cvb_run_days(cvb_sim* s, int32_t t0, int32_t t1, cvb_stream st);
 int cvb_state_invalidate(cvb_sim* s);
+/* Launch-shape overrides of the fused day kernels, for tuning runs (0 = default): what 0 / 1 = CTA size / agents per CTA of the
+ * first per-agent kernel, 2 / 3 = the same for the second */
+int cvb_tune(cvb_sim* s, int32_t what, int32_t value);
 /* Per-kernel timing of cvb_run_days (CUDA events around every launch; off by default).  cvb_timing_read synchronises, returns
  * the milliseconds and launch counts accumulated since the last read, per kernel kind, and resets them */
 enum cvb_timed { CVB_TIMED_day_begin = 0, CVB_TIMED_trace, CVB_TIMED_day_mid, CVB_TIMED_edge_pass, CVB_TIMED_infect, CVB_TIMED_day_end,

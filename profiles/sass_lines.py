@@ -67,7 +67,7 @@ tot = sum(a[0] for a in agg.values())
 tots = sum(a[1] for a in agg.values())
 print(f'kernel {kregex}: {len(sass)} SASS instructions, {tot} warp instructions executed, {tots} stall samples')
 text = {}
-for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(os.environ.get('TOP', 45))]:
+for (f, l), a in sorted(agg.items(), key=lambda kv: -kv[1][1 if os.environ.get('BY') == 'smp' else 0])[:int(os.environ.get('TOP', 45))]:
     if f not in text:
         p = os.path.join(ROOT, 'covasim_b200', 'csrc', f)
         text[f] = open(p).read().splitlines() if os.path.exists(p) else []

@@ -125,6 +125,7 @@ PROTOTYPES = dict(
     cvb_plan_contact_tracing=[_P, C.POINTER(cvb_trace_pars), _i32, _i32],
     cvb_plan_dynamic_layers=[_P, C.c_uint32],
     cvb_run_days=[_P, _i32, _i32, _P],
+    cvb_run_days_multi=[_P, _i32, _i32, _i32, _P],
     cvb_state_invalidate=[_P],
     cvb_tune=[_P, _i32, _i32],
     cvb_timing_enable=[_P, _i32],

@@ -98,12 +98,19 @@ class Layer:
     def keys(self):
         return list(self.columns)
 
+    def _ready(self):
+        ''' Sim.restore copies the edge lists on a side stream: anything that touches the arrays waits for that copy first '''
+        if self._sim is not None:
+            self._sim._sync_edges()
+
     def __getitem__(self, key):
+        self._ready()
         return self._cols[key]
 
     def __setitem__(self, key, value):
         if key not in self.columns:
             raise KeyError(key)
+        self._ready()
         old = self._cols[key]
         if len(value) == len(old):
             old.copy_(torch.as_tensor(value).to(device=old.device, dtype=old.dtype))      # in place: the bound pointer stays valid
@@ -125,6 +132,7 @@ class Layer:
             _capi.call('cvb_bind_layer', self._sim._handle, self._index, c['p1'].data_ptr(), c['p2'].data_ptr(), c['beta'].data_ptr(), len(self))
 
     def to_numpy(self):
+        self._ready()
         return {k: self._cols[k].cpu().numpy() for k in self.columns}
 
     def find_contacts(self, inds, as_array=True):
@@ -142,12 +150,14 @@ class Layer:
     def update(self, people, frac=1.0):
         ''' Regenerate a dynamic layer (reference base.py:1849-1876); frac=1 runs as one device pass '''
         sim = self._sim
+        self._ready()
         if frac != 1.0:
             raise NotImplementedError('partial regeneration (frac < 1) is not built')
         _capi.call('cvb_layer_regenerate', sim._handle, self._index, sim.t, sim._stream_ptr)
 
     def pop_inds(self, inds):
         ''' Remove edges by index and return them (reference base.py:1742-1757) -- used by clip_edges-style interventions '''
+        self._ready()
         inds = torch.as_tensor(inds, dtype=torch.int64, device=self.device)
         keep = torch.ones(len(self), dtype=torch.bool, device=self.device)
         keep[inds] = False
@@ -159,6 +169,7 @@ class Layer:
 
     def append(self, contacts):
         ''' Append edges (reference base.py:1760-1771) '''
+        self._ready()
         for k in self.columns:
             new = torch.as_tensor(contacts[k], dtype=self._cols[k].dtype, device=self.device)
             self._cols[k] = torch.cat([self._cols[k], new]).contiguous()

@@ -303,16 +303,21 @@ int cvb_bind_log(cvb_sim* s, int32_t* source, int32_t* target, int32_t* date, in
 int cvb_set_quar_horizon(cvb_sim* s, int32_t horizon) {
     CVB_REQUIRE(s && horizon >= 1 && horizon <= 64, "cvb_set_quar_horizon: horizon must be in [1,64]");
     if (horizon <= s->quar_horizon) return 0;
-    // The ring is indexed by day % horizon, so it can only be re-sized while it is empty of future
-    // requests; the host calls this when a tracing intervention is initialised.
+    // The ring is indexed by day % horizon.  Requests already pending for the days [today, today + old horizon) move to the slots
+    // the same days have in the larger ring (people.py:620-640: a custom intervention may ask for a start date beyond the
+    // current horizon in the middle of a run); "today" is the last day an entry point was called for.
     float* ring = nullptr;
     CVB_CHECK(cudaMalloc((void**)&ring, (size_t)horizon * s->n * sizeof(float)));
     fill_f32_kernel<<<grid_for(horizon * s->n), kThreads>>>(ring, horizon * s->n, -1.0f);
     CVB_LAUNCH_CHECK();
     CVB_CHECK(cudaDeviceSynchronize());
+    for (int32_t d = s->last_t; d < s->last_t + s->quar_horizon; ++d)
+        CVB_CHECK(cudaMemcpy(ring + (int64_t)(d % horizon) * s->n, s->quar_ring + (int64_t)(d % s->quar_horizon) * s->n,
+                             (size_t)s->n * sizeof(float), cudaMemcpyDeviceToDevice));
     cudaFree(s->quar_ring);
     s->quar_ring = ring;
     s->quar_horizon = horizon;
+    s->state_valid = 0;
     return 0;
 }
 

@@ -91,6 +91,7 @@ struct cvb_sim {
     unsigned long long* edge_work;                  // [npts][2] adjacency entries visited / transmitters, per day (sparse edge pass)
     double* nab_kin; int64_t nab_kin_len;           // NAb kinetics table (immunity.py:298)
     float* quar_ring; int32_t quar_horizon;         // [quar_horizon][N] pending quarantine end days, -1 = none
+    int32_t last_t;                                 // the last day update_states_pre ran for ("today" when the ring is re-sized)
     unsigned int* case_bits; unsigned int* n_cases; // contact tracing: bitmap of today's cases
     unsigned int* inf_bits;                         // [ceil(N/32)] agents that can transmit today (written by prepare_transmission)
     int32_t* trans_list; unsigned int* n_trans;     // the same set as a compact (unordered) list

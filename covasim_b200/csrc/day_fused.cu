@@ -817,8 +817,8 @@ int cvb_state_check(cvb_sim* s, int32_t t_done, int64_t* host_out26, cvb_stream 
     return pack_or_check(s, t_done, true, host_out26, (cudaStream_t)st);
 }
 
-int cvb_run_days(cvb_sim* s, int32_t t0, int32_t t1, cvb_stream st_) {
-    cudaStream_t st = (cudaStream_t)st_;
+// cvb_run_days in three parts, so that several handles can be advanced in lockstep from one host thread (cvb_run_days_multi)
+static int run_days_begin(cvb_sim* s, int32_t t0, int32_t t1, cudaStream_t st, bool& packed) {
     if (fused_ready(s, "cvb_run_days")) return 1;
     CVB_REQUIRE(t0 >= 0 && t0 < t1 && t1 <= s->npts, "cvb_run_days: days [%d,%d) outside [0,%d)", t0, t1, s->npts);
     if (!s->plan && cvb_plan_clear(s)) return 1;
@@ -830,7 +830,7 @@ int cvb_run_days(cvb_sim* s, int32_t t0, int32_t t1, cvb_stream st_) {
             CVB_REQUIRE(!(plan.trace.trace_prob[l] > 0.0) || s->layers[l].n_edges == 0 || ((s->adj_layer_mask >> l) & 1u),
                         "cvb_run_days: traced layer %d is not covered by the adjacency", l);
     }
-    bool packed = false;
+    packed = false;
     if (!s->state_valid || t0 == 0) {
         int64_t out[26];
         packed = true;
@@ -841,26 +841,67 @@ int cvb_run_days(cvb_sim* s, int32_t t0, int32_t t1, cvb_stream st_) {
     CVB_CHECK(cudaMemsetAsync(s->n_trans, 0, sizeof(unsigned int), st));
     CVB_CHECK(cudaMemsetAsync(s->n_case_list, 0, sizeof(unsigned int), st));
     CVB_CHECK(cudaMemsetAsync(s->n_cand, 0, sizeof(unsigned int), st));
-    for (int32_t t = t0; t < t1; ++t) {
-        for (int l = 0; l < s->pars.n_layers; ++l)
-            if ((plan.regen_mask >> l) & 1u) { TimedScope ts(s, CVB_TIMED_regen, st); if (cvb_layer_regenerate(s, l, t, st_)) return 1; }
-        const bool test = plan.has_test && t >= plan.test_start && (plan.test_end < 0 || t <= plan.test_end);
-        const bool trace = plan.has_trace && t >= plan.trace_start && (plan.trace_end < 0 || t <= plan.trace_end);
-        {
-            TimedScope ts(s, CVB_TIMED_day_begin, st);
-            int rc = t > t0 ? launch_day_begin<true, true>(s, t, test, trace, false, st) : launch_day_begin<false, true>(s, t, test, trace, packed, st);
-            if (rc) return rc;
-        }
-        if (trace) { TimedScope ts(s, CVB_TIMED_trace, st); if (launch_trace_sparse2(s, t, &plan.trace, st)) return 1; }
-        { TimedScope ts(s, CVB_TIMED_day_mid, st); if (launch_day_mid(s, t, t > t0, st)) return 1; }
-        { TimedScope ts(s, CVB_TIMED_edge_pass, st); if (edge_pass_impl(s, t, st, true)) return 1; }
-        { TimedScope ts(s, CVB_TIMED_infect, st); if (launch_infect_winners(s, t, true, st)) return 1; }
+    return 0;
+}
+
+static int run_one_day(cvb_sim* s, int32_t t, int32_t t0, bool packed, cudaStream_t st) {
+    const DayPlan& plan = *s->plan;
+    s->last_t = t;
+    for (int l = 0; l < s->pars.n_layers; ++l)
+        if ((plan.regen_mask >> l) & 1u) { TimedScope ts(s, CVB_TIMED_regen, st); if (cvb_layer_regenerate(s, l, t, (cvb_stream)st)) return 1; }
+    const bool test = plan.has_test && t >= plan.test_start && (plan.test_end < 0 || t <= plan.test_end);
+    const bool trace = plan.has_trace && t >= plan.trace_start && (plan.trace_end < 0 || t <= plan.trace_end);
+    {
+        TimedScope ts(s, CVB_TIMED_day_begin, st);
+        int rc = t > t0 ? launch_day_begin<true, true>(s, t, test, trace, false, st) : launch_day_begin<false, true>(s, t, test, trace, packed, st);
+        if (rc) return rc;
     }
-    s->state_valid = 1;                                     // (the edge pass / layer regeneration above do not touch People flags)
+    if (trace) { TimedScope ts(s, CVB_TIMED_trace, st); if (launch_trace_sparse2(s, t, &plan.trace, st)) return 1; }
+    { TimedScope ts(s, CVB_TIMED_day_mid, st); if (launch_day_mid(s, t, t > t0, st)) return 1; }
+    { TimedScope ts(s, CVB_TIMED_edge_pass, st); if (edge_pass_impl(s, t, st, true)) return 1; }
+    { TimedScope ts(s, CVB_TIMED_infect, st); if (launch_infect_winners(s, t, true, st)) return 1; }
+    return 0;
+}
+
+static int run_days_end(cvb_sim* s, int32_t t1, cudaStream_t st) {
+    s->state_valid = 1;                                     // (the edge pass / layer regeneration do not touch People flags)
     TimedScope ts(s, CVB_TIMED_day_end, st);
     if (launch_day_begin<true, false>(s, t1, false, false, false, st)) return 1;      // closes day t1 - 1 (its argument is the day AFTER the one it closes)
     sum_partials_kernel<<<1, 96, 0, st>>>(s->partial, s->begin_grid, s->res.sums, t1 - 1, -1);
     CVB_LAUNCH_CHECK();
+    return 0;
+}
+
+int cvb_run_days(cvb_sim* s, int32_t t0, int32_t t1, cvb_stream st_) {
+    cudaStream_t st = (cudaStream_t)st_;
+    bool packed = false;
+    if (run_days_begin(s, t0, t1, st, packed)) return 1;
+    for (int32_t t = t0; t < t1; ++t)
+        if (run_one_day(s, t, t0, packed, st)) return 1;
+    return run_days_end(s, t1, st);
+}
+
+int cvb_run_days_multi(cvb_sim** handles, int32_t n_handles, int32_t t0, int32_t t1, cvb_stream* streams) {
+    CVB_REQUIRE(handles && streams && n_handles > 0, "cvb_run_days_multi: bad argument");
+    CVB_REQUIRE(n_handles <= 65536, "cvb_run_days_multi: too many handles");
+    std::vector<char> packed((size_t)n_handles, 0);
+    for (int m = 0; m < n_handles; ++m) {
+        CVB_REQUIRE(handles[m], "cvb_run_days_multi: NULL handle %d", m);
+        CVB_CHECK(cudaSetDevice(handles[m]->device));
+        bool p = false;
+        if (run_days_begin(handles[m], t0, t1, (cudaStream_t)streams[m], p)) return 1;
+        packed[m] = p;
+    }
+    // days outermost, members innermost: one host thread keeps every member's stream fed, the members' kernels overlap on the GPU
+    for (int32_t t = t0; t < t1; ++t)
+        for (int m = 0; m < n_handles; ++m) {
+            if (m == 0 || handles[m]->device != handles[m - 1]->device) CVB_CHECK(cudaSetDevice(handles[m]->device));
+            if (run_one_day(handles[m], t, t0, packed[m] != 0, (cudaStream_t)streams[m])) return 1;
+        }
+    for (int m = 0; m < n_handles; ++m) {
+        if (m == 0 || handles[m]->device != handles[m - 1]->device) CVB_CHECK(cudaSetDevice(handles[m]->device));
+        if (run_days_end(handles[m], t1, (cudaStream_t)streams[m])) return 1;
+    }
     return 0;
 }
 

@@ -23,6 +23,8 @@ struct InfectArgs {
     const int32_t* hit_src;  // partitioned edge pass: cand[] lists every successful transmission, with its source and key; the
     const unsigned long long* hit_key;   // entry whose key equals infect_key[target] is the winner (NULL: cand[] lists unique targets)
     int64_t hit_cap;
+    const long long* adj_ptr; const uint4* adj; uint32_t adj_mask;   // fused pipeline: the source of a transmission over a layer the
+                                             // adjacency covers is looked up in the TARGET's row (the raw edge lists are not read)
     const unsigned long long* beds_direct;   // fused pipeline: {n_severe, n_critical} of today's counter row (running totals); NULL: beds[t]
     unsigned long long* vcounters_row;       // today's by-variant counter row (stock differences)
 };
@@ -51,8 +53,8 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
     unsigned int n_cand = __ldcg(n_cand_ptr);                  // (L2 loads: the kernel may have been resident while the edge pass wrote them)
     if (ia.hit_key && (int64_t)n_cand > ia.hit_cap) n_cand = (unsigned int)ia.hit_cap;
     const unsigned long long* bd = ia.beds_direct ? ia.beds_direct : beds + (int64_t)t * 2;
-    const bool hosp_max = ia.hosp_max >= 0 ? ia.hosp_max != 0 : (pars.n_beds_hosp >= 0 && (long long)bd[0] > pars.n_beds_hosp);
-    const bool icu_max = ia.icu_max >= 0 ? ia.icu_max != 0 : (pars.n_beds_icu >= 0 && (long long)bd[1] > pars.n_beds_icu);
+    const bool hosp_max = ia.hosp_max >= 0 ? ia.hosp_max != 0 : (pars.n_beds_hosp >= 0 && (long long)__ldcg(bd) > pars.n_beds_hosp);
+    const bool icu_max = ia.icu_max >= 0 ? ia.icu_max != 0 : (pars.n_beds_icu >= 0 && (long long)__ldcg(bd + 1) > pars.n_beds_icu);
     const float tf = (float)t;
 
     // Sixteen lanes per newly infected agent: lane s of the half-warp computes the Philox draw of slot s (its uniform, and
@@ -67,6 +69,23 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
         const bool valid = j < n_cand;
         const int64_t i = valid ? __ldcg(cand + j) : 0;
         const int64_t gi = i + ia.id0;                             // global id: Philox index and logged target
+        // who infected i: the winning key names (layer, edge, direction); i's adjacency row holds that edge with the other
+        // direction bit and the source as the neighbour.  The 16 lanes scan the row while the draws below are computed.
+        int32_t src_adj = -1;
+        if (ia.adj_ptr && valid) {
+            const unsigned long long k0 = __ldcg(infect_key + i);
+            const unsigned lf = (unsigned)(k0 >> 48) & 0xFFu;
+            if (k0 != kEmptyKey && lf != 0xFFu && ((ia.adj_mask >> lf) & 1u)) {
+                const unsigned e32 = (unsigned)(k0 & 0xFFFFFFFFull), want = (lf << 1) | (1u - (unsigned)((k0 >> 40) & 1ull));
+                const long long beg = ia.adj_ptr[i], end = ia.adj_ptr[i + 1];
+                for (long long off = beg + slot; off < end; off += 16) {
+                    const uint4 en = __ldg(ia.adj + off);
+                    if (en.y == e32 && en.z == want) src_adj = (int32_t)en.x;
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 8; d > 0; d >>= 1) src_adj = max(src_adj, __shfl_xor_sync(0xFFFFFFFFu, src_adj, d));
         const u32x4 words = keyed_words(ia.seed, P_INFECT, 0, t, gi, (uint32_t)slot);
         const double u_mine = u53(words.x, words.y);
         double d0 = 0.0, d1 = 0.0;
@@ -113,7 +132,9 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
         int32_t source = -1;
         int layer_code = ia.list_layer_code;
         if (lfield != 0xFF) {
-            source = ia.hit_src ? ia.hit_src[j] : (dir == 0 ? L.l[lfield].p1[e] : L.l[lfield].p2[e]);
+            if (ia.hit_src) source = ia.hit_src[j];
+            else if (ia.adj_ptr && ((ia.adj_mask >> lfield) & 1u)) source = src_adj;
+            else source = dir == 0 ? L.l[lfield].p1[e] : L.l[lfield].p2[e];
             layer_code = lfield;
         }
         // every per-agent input is loaded here, before the first store, so the loads are independent and in flight
@@ -287,6 +308,8 @@ static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t lis
     ia.hosp_max = hosp_max; ia.icu_max = icu_max;
     ia.id0 = s->partitioned ? s->id0 : 0;
     ia.hit_src = hits ? s->hit_src : nullptr; ia.hit_key = hits ? s->hit_key : nullptr; ia.hit_cap = s->hit_cap;
+    const bool use_adj = with_state && s->adj && s->adj_layer_mask;
+    ia.adj_ptr = use_adj ? s->adj_ptr : nullptr; ia.adj = use_adj ? s->adj : nullptr; ia.adj_mask = use_adj ? s->adj_layer_mask : 0u;
     ia.beds_direct = with_state ? s->res.counters + (int64_t)t * CVB_N_COUNTERS + CVB_C_n_severe : nullptr;      // n_severe, n_critical are adjacent
     ia.vcounters_row = s->res.vcounters + (int64_t)t * s->nv * CVB_N_VCOUNTERS;
     int grid = grid_for(max_items * 16, kThreads, 148 * 4);       // sixteen lanes per agent

@@ -588,6 +588,7 @@ int cvb_update_states_pre(cvb_sim* s, int32_t t, cvb_stream st) {
     if (s) cvb::state_touched(s);
     if (require_ready(s, "cvb_update_states_pre")) return 1;
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_update_states_pre: day %d outside [0,%d)", t, s->npts);
+    s->last_t = t;
     states_pre_kernel<<<grid_agents(s->n), kThreads, 0, (cudaStream_t)st>>>(s->people, s->pars, s->n, t, vector_ok(s), s->res.counters,
                                                                           s->res.vcounters, s->beds);
     CVB_LAUNCH_CHECK();

@@ -39,17 +39,26 @@ class People:
         self._sim = None
         self.infection_log_cap = 0
         A = self._arrays
+        # One device arena for every field (each field a 256-byte-aligned view): kernels bind the views' pointers as before, and a
+        # checkpoint / restore of the whole People state is ONE copy (Sim.snapshot / Sim.restore)
+        layout, total = [], 0
         for name in cvd.all_states:
             dt = _TORCH_DTYPE[np.dtype(cvd.field_dtype(name))]
             shape = (nv, n) if cvd.field_is_2d(name) else (n,)
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+            layout.append((name, dt, shape, total, nbytes))
+            total += (nbytes + 255) // 256 * 256
+        self._arena = torch.empty(max(total, 256), dtype=torch.uint8, device=self.device)
+        for name, dt, shape, off, nbytes in layout:
+            A[name] = self._arena[off:off + nbytes].view(dt).view(shape)
             if name == 'uid':
-                A[name] = torch.arange(lo, hi, dtype=torch.int32, device=self.device)
+                A[name].copy_(torch.arange(lo, hi, dtype=torch.int32, device=self.device))
             elif name in cvd.states:
-                A[name] = torch.full(shape, name in ('susceptible', 'naive'), dtype=dt, device=self.device)
+                A[name].fill_(name in ('susceptible', 'naive'))
             elif dt == torch.float32 and name not in cvd.imm_states and name not in ('peak_nab', 'nab'):
-                A[name] = torch.full(shape, float('nan'), dtype=dt, device=self.device)
+                A[name].fill_(float('nan'))
             else:
-                A[name] = torch.zeros(shape, dtype=dt, device=self.device)
+                A[name].zero_()
         self._age_global = None
         if age is not None:
             if not isinstance(age, torch.Tensor):

@@ -141,23 +141,18 @@ class MultiSim:
         else:
             n_dev = torch.cuda.device_count() if n_gpus is None else min(n_gpus, torch.cuda.device_count())
             devices = [torch.device('cuda', d) for d in range(max(n_dev, 1))]
-        # initialise (host-side population build + upload), then step all local members day by day, interleaved
+        # initialise (population build + upload), then advance all local members in lockstep
         active = []
         for slot, i in enumerate(mine):
             sim = self.sims[i]
-            sim.device = devices[slot % len(devices)]
+            if not sim.initialized:                        # (an initialised member keeps the device its arrays live on)
+                sim.device = devices[slot % len(devices)]
             with torch.cuda.device(sim.device):
                 if not sim.initialized:
                     sim.initialize()
                 sim.set_seed()
             active.append(sim)
-        remaining = list(active)
-        while remaining:
-            for sim in list(remaining):
-                with torch.cuda.device(sim.device):
-                    sim.step()
-                if sim.complete:
-                    remaining.remove(sim)
+        self._advance_members(active)
         for sim in active:
             with torch.cuda.device(sim.device):
                 sim.finalize()
@@ -170,13 +165,81 @@ class MultiSim:
         if keys is None:                                   # a rank without members still takes part in the collective
             _, keys, vkeys = pack_results(_empty_results(self.sims[0]))
         vectors = gather_results(local, n)
-        npts, nv = self.sims[0].npts, self.sims[0]['n_variants']
+        # sizes from a member this rank has initialised (n_variants / n_days are only final after initialize()); ranks without
+        # members derive them from the base parameters the same way initialize() does
+        ref = active[0] if active else self.sims[0]
+        if not ref.initialized:
+            ref._validate_pars()
+        npts = ref.npts
+        nv = ref['n_variants'] if ref.initialized else 1 + len(ref['variants'])
         self.member_results = [unpack_results(v, keys, vkeys, npts, nv) for v in vectors]
         if not keep_people:
             for sim in active:                             # reference sim.shrink(): drop the big arrays (run.py:1400-1401)
                 sim.people = None
                 sim._destroy()
         return self
+
+    def _advance_members(self, sims):
+        '''
+        Run the members to their end in lockstep.  Stretches of days that need no host decision in ANY member go through ONE
+        cvb_run_days_multi call: a single host thread issues every member's five launches per day to the member's own stream, so
+        small members (whose kernels are far too short to fill a B200) overlap on the GPU instead of queueing behind each other.
+        Days on which some member needs its host (an intervention that acts through Python, a variant import, ...) are stepped
+        member by member.
+        '''
+        import ctypes as C
+        import torch
+        from . import _capi
+        if not sims:
+            return
+        lockstep = len({(s.npts, s.t) for s in sims}) == 1 and all(s.rng_mode == 'philox' for s in sims)
+        if not lockstep:
+            remaining = list(sims)
+            while remaining:
+                for sim in list(remaining):
+                    with torch.cuda.device(sim.device):
+                        sim.step()
+                    if sim.complete:
+                        remaining.remove(sim)
+            return
+        streams = []
+        for sim in sims:
+            with torch.cuda.device(sim.device):
+                streams.append(torch.cuda.Stream(device=sim.device))
+        n = len(sims)
+        handles = (C.c_void_p * n)(*[s._handle for s in sims])
+        stream_ptrs = (C.c_void_p * n)(*[st.cuda_stream for st in streams])
+        devices = sorted({s.device for s in sims}, key=str)
+        npts = sims[0].npts
+        plain = all(not s.pars['analyzers'] and not s.pars['stopping_func'] for s in sims)
+        while not sims[0].complete:
+            t = sims[0].t
+            if plain and all(s._fusable_day(t) for s in sims):
+                t1 = t + 1
+                while t1 < npts and all(s._fusable_day(t1) for s in sims):
+                    t1 += 1
+                for sim in sims:                           # parameters / adjacency up to date, pending edge copies done
+                    with torch.cuda.device(sim.device):
+                        sim._push_pars()
+                        if sim._adj_dirty:
+                            sim._build_adjacency()
+                            sim._build_plan_keep_days()
+                        if sim._plan['needs_edges']:
+                            sim._sync_edges()
+                for d in devices:
+                    torch.cuda.synchronize(d)              # the members' streams do not synchronise with the default stream
+                _capi.call('cvb_run_days_multi', handles, n, int(t), int(t1), stream_ptrs)
+                for d in devices:
+                    torch.cuda.synchronize(d)
+                for sim in sims:
+                    sim.fused_days += t1 - t
+                    sim.people.t = t1 - 1
+                    sim.t = t1
+                    sim.complete = t1 == npts
+            else:
+                for sim in sims:
+                    with torch.cuda.device(sim.device):
+                        sim.step()
 
     # ---- reductions (reference run.py:220-374) ----------------------------------------------------
     def _check(self):

@@ -74,7 +74,7 @@ def gen_time(date_exposed, date_symptomatic, log_source, log_target):
 class Sim:
 
     def __init__(self, pars=None, popdict=None, label=None, device=None, rng='philox', pop_exact=None, use_adjacency=True, partition=None,
-                 hit_capacity=0, pop_gen='host', fused=True, **kwargs):
+                 hit_capacity=0, pop_gen='host', fused=True, log_capacity=None, **kwargs):
         kw = dict(pars or {})
         kw.update(kwargs)
         for alias, key in (('n_agents', 'pop_size'), ('init_infected', 'pop_infected')):       # reference base.py:266-273
@@ -111,10 +111,14 @@ class Sim:
         # fused=True: days on which no host decision is needed run through cvb_run_days (five launches per day, whole blocks of
         # days per call from run()); False: every day through the per-step entry points.  Same results either way.
         self.fused = bool(fused)
+        self.log_capacity = log_capacity   # entries of the device infection log (default 4 per agent); overflow is reported, not silent
         self._plan = None
         self.fused_days = 0                # days that went through cvb_run_days (diagnostics / tests)
         self.use_adjacency = use_adjacency   # False: stream every layer densely each day (the reference's access pattern)
         self._adj = None
+        self._adj_mask = 0
+        self._edges_event = None
+        self._copy_stream = None
         self._adj_dirty = False
         # agent partition over several GPUs (partition.py): None = the whole population on this GPU; True = one rank of
         # the torch.distributed world; or a communicator object (partition.DistComm / partition.LocalComm)
@@ -345,7 +349,15 @@ class Sim:
         if trace is not None:
             _capi.call('cvb_plan_contact_tracing', h, C.byref(trace[1]), trace[2], trace[3])
         _capi.call('cvb_plan_dynamic_layers', h, regen)
-        self._plan = dict(host_days=host_days)
+        # the fused kernels of static layers read only the adjacency: the raw edge arrays matter when a layer is streamed densely
+        dense = regen != 0 or self._adj is None or any(len(self.people.contacts[lk]) > 0 and not ((self._adj_mask >> i) & 1) for i, lk in enumerate(lkeys))
+        self._plan = dict(host_days=host_days, needs_edges=bool(dense))
+
+    def _build_plan_keep_days(self):
+        ''' The adjacency changed (a layer was edited): recompute what depends on it '''
+        days = self.fused_days
+        self._build_plan()
+        self.fused_days = days
 
     def _fusable_day(self, t):
         ''' True if day t needs no host decision: no intervention / variant acts through Python, no importations, no rescaling '''
@@ -363,6 +375,9 @@ class Sim:
         self._push_pars()
         if self._adj_dirty:
             self._build_adjacency()
+            self._build_plan_keep_days()
+        if self._plan['needs_edges']:
+            self._sync_edges()
         _capi.call('cvb_run_days', self._handle, int(t0), int(t1), self._stream_ptr)
         self.fused_days += t1 - t0
         self.people.t = t1 - 1
@@ -381,6 +396,7 @@ class Sim:
         if pars['end_day'] is not None:
             pars['n_days'] = self.day(pars['end_day'])
         pars['n_days'] = int(pars['n_days'])
+        pars['end_day'] = self.date(pars['n_days'])       # reference sim.py:240-256: end_day and n_days always agree
         if pars['pop_scale'] != 1 and pars['rescale'] and self._partition not in (None, False):
             raise NotImplementedError('dynamic rescaling needs a global count of non-naive agents every day and is not built for agent-partitioned runs; use rescale=False')
 
@@ -462,7 +478,7 @@ class Sim:
         self._vcounters = torch.zeros((npts, nv, cvd.N_VCOUNTERS), dtype=torch.int64, device=dev)
         self._sums = torch.zeros((npts, 4), dtype=torch.float64, device=dev)
         _capi.call('cvb_bind_results', h, self._counters.data_ptr(), self._vcounters.data_ptr(), self._sums.data_ptr())
-        cap = int(max(4 * self.n_local, 1024))
+        cap = int(self.log_capacity) if self.log_capacity else int(max(4 * self.n_local, 1024))
         self._log = dict(source=torch.empty(cap, dtype=torch.int32, device=dev), target=torch.empty(cap, dtype=torch.int32, device=dev),
                          date=torch.empty(cap, dtype=torch.int32, device=dev), layer=torch.empty(cap, dtype=torch.int8, device=dev),
                          variant=torch.empty(cap, dtype=torch.int8, device=dev), count=torch.zeros(1, dtype=torch.int64, device=dev))
@@ -553,6 +569,8 @@ class Sim:
         today's transmitters / cases.  Dynamic layers (regenerated every day) keep the dense streaming passes.
         '''
         self._adj_dirty = False
+        self._adj_mask = 0
+        self._sync_edges()
         if self._comm is not None:
             raise NotImplementedError('contact layers of an agent-partitioned simulation cannot be edited after initialisation')
         people, pars = self.people, self.pars
@@ -592,6 +610,7 @@ class Sim:
         for i in static:
             mask |= 1 << i
         self._adj = (ptr, adj)                      # keep the tensors alive while they are bound
+        self._adj_mask = mask
         _capi.call('cvb_bind_adjacency', self._handle, ptr.data_ptr(), adj.data_ptr(), M, mask)
 
     def _set_quar_horizon(self, horizon):
@@ -600,27 +619,42 @@ class Sim:
             self._quar_horizon = int(horizon)
 
     # ---- checkpoint / restore (reference base.py:682-741 Sim.save/load, sim.py:688-761 resume) ----------
+    _IV_HOST_TYPES = (set, dict, list, tuple, int, float, bool, str, type(None), np.ndarray, np.integer, np.floating)
+
     def snapshot(self, pinned=True):
         '''
-        Host copy of everything a run mutates: every People array, every layer's edge list, the RNG streams,
-        the clock, the result tables and the intervention-owned device arrays.  With ``pinned=True`` the
-        buffers are page-locked so ``restore`` is one asynchronous H2D copy per array.
+        Host copy of everything a run mutates: the People arena (every per-agent array, one buffer), every layer's edge list, the
+        RNG streams, the clock, the result tables, the rescale vector, and the state interventions keep (device arrays and host
+        bookkeeping such as pending second doses or the edges clip_edges holds back).  With ``pinned=True`` the buffers are
+        page-locked so ``restore`` is one asynchronous H2D copy for the People and one per edge array.
         '''
+        self._sync_edges()
         torch.cuda.synchronize(self.device)
 
         def host(t):
             h = torch.empty(t.shape, dtype=t.dtype, pin_memory=pinned)
             h.copy_(t)
             return h
-        snap = dict(t=self.t, complete=self.complete,
-                    people={k: host(self.people[k]) for k in self.people.keys()},
-                    layers={lk: {c: host(l[c]) for c in l.columns} for lk, l in self.people.contacts.items()},
+
+        def layer_cols(layer):
+            return {c: host(layer[c]) for c in layer.columns}
+
+        iv_dev, iv_host, iv_layers = [], [], []
+        for iv in self.pars['interventions']:
+            attrs = vars(iv) if hasattr(iv, '__dict__') else {}
+            iv_dev.append({k: host(v) for k, v in attrs.items() if isinstance(v, torch.Tensor)})
+            iv_host.append({k: copy.deepcopy(v) for k, v in attrs.items()
+                            if isinstance(v, self._IV_HOST_TYPES) and not k.startswith('__') and k not in ('label',)})
+            held = attrs.get('contacts')                    # clip_edges: the edges it has taken out of the simulation
+            iv_layers.append({lk: layer_cols(l) for lk, l in held.items()} if isinstance(held, dict) else None)
+        snap = dict(t=self.t, complete=self.complete, arena=host(self.people._arena),
+                    layers={lk: layer_cols(l) for lk, l in self.people.contacts.items()},
                     counters=host(self._counters), vcounters=host(self._vcounters), sums=host(self._sums),
                     log_count=host(self._log['count']), host_adds={k: v.copy() for k, v in self._host_adds.items()},
+                    rescale_vec=self.rescale_vec.copy(),
                     rng=(self.rng.seed, self.rng.np_.get_state(), self.rng.nb.get_state()),
                     pars={k: copy.deepcopy(v) for k, v in self.pars.items() if k not in ('interventions', 'analyzers', 'variants', 'prognoses', 'nab_kin')},
-                    iv=[{k: host(v) for k, v in vars(iv).items() if isinstance(v, torch.Tensor)} if hasattr(iv, '__dict__') else {}
-                        for iv in self.pars['interventions']])
+                    iv=iv_dev, iv_host=iv_host, iv_layers=iv_layers, quar_horizon=self._quar_horizon)
         torch.cuda.synchronize(self.device)
         return snap
 
@@ -628,35 +662,63 @@ class Sim:
         ''' restore() without the People / Layer copies: for callers that rewound those arrays on the device themselves '''
         return self.restore(snap, arrays=False)
 
+    def _sync_edges(self):
+        ''' Make the current stream wait for the edge lists restore() is still copying on the side stream '''
+        ev, self._edges_event = getattr(self, '_edges_event', None), None
+        if ev is not None:
+            torch.cuda.current_stream(self.device).wait_event(ev)
+
     def restore(self, snap, arrays=True):
-        ''' Put a snapshot back on the device (asynchronous copies from pinned memory) and rewind the clock '''
+        '''
+        Put a snapshot back on the device and rewind the clock.  The People arena is ONE asynchronous copy from pinned memory on
+        the current stream; the edge lists are copied on a side stream, concurrently with the days that follow: the transmission
+        and tracing kernels of static layers read the adjacency, which does not change, so only code that touches the raw edge
+        arrays (dynamic layers, the per-step path, Python access through Layer, finalize) waits for them (_sync_edges).
+        '''
         if snap['t'] != 0 and self._quar_horizon > 1:
             raise NotImplementedError('restoring mid-run with delayed quarantine requests pending is not built')
+        if torch.cuda.current_device() != self.device.index:
+            torch.cuda.set_device(self.device)
         if arrays:
-            for k, h in snap['people'].items():
-                self.people[k].copy_(h, non_blocking=True)
-            for lk, cols in snap['layers'].items():
-                layer = self.people.contacts[lk]
-                for c, h in cols.items():
-                    if layer[c].shape == h.shape:
-                        layer[c].copy_(h, non_blocking=True)
-                    else:
-                        layer[c] = h
+            self._sync_edges()
+            self.people._arena.copy_(snap['arena'], non_blocking=True)
+            cur = torch.cuda.current_stream(self.device)
+            if getattr(self, '_copy_stream', None) is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            cs = self._copy_stream
+            cs.wait_stream(cur)                            # earlier kernels may still be reading the arrays that are overwritten
+            resized = False
+            with torch.cuda.stream(cs):
+                for lk, cols in snap['layers'].items():
+                    layer = self.people.contacts[lk]
+                    for c, h in cols.items():
+                        if layer._cols[c].shape == h.shape:
+                            layer._cols[c].copy_(h, non_blocking=True)
+                        else:
+                            layer._cols[c] = h.to(self.device, non_blocking=True)
+                            resized = True
+                self._edges_event = cs.record_event()
+            if resized:                                     # a layer changed size since the snapshot (clip_edges): bind the new arrays
+                self._sync_edges()
+                for layer in self.people.contacts.values():
+                    layer._rebind()
         self._counters.copy_(snap['counters'], non_blocking=True)
         self._vcounters.copy_(snap['vcounters'], non_blocking=True)
         self._sums.copy_(snap['sums'], non_blocking=True)
         self._log['count'].copy_(snap['log_count'], non_blocking=True)
-        for iv, saved in zip(self.pars['interventions'], snap['iv']):
-            for k, h in saved.items():
+        from .base import Layer
+        for iv, dev, hst, held in zip(self.pars['interventions'], snap['iv'], snap['iv_host'], snap['iv_layers']):
+            for k, h in dev.items():
                 getattr(iv, k).copy_(h, non_blocking=True)
-            if hasattr(iv, '_due_days'):
-                iv._due_days = set()
-            if hasattr(iv, 'finalized'):
-                iv.finalized = False
+            for k, v in hst.items():
+                setattr(iv, k, copy.deepcopy(v))
+            if held is not None:
+                iv.contacts = {lk: Layer(cols['p1'], cols['p2'], cols['beta'], label=lk, device=self.device) for lk, cols in held.items()}
         _capi.call('cvb_reset', self._handle, self._stream_ptr)
         _capi.call('cvb_state_invalidate', self._handle)
         self.fused_days = 0
         self._host_adds = {k: v.copy() for k, v in snap['host_adds'].items()}
+        self.rescale_vec = snap['rescale_vec'].copy()
         seed, np_state, nb_state = snap['rng']
         self.rng.seed = seed
         self.rng.np_.set_state(np_state)
@@ -682,7 +744,7 @@ class Sim:
 
     def h2d_bytes(self, snap):
         ''' Bytes restore() copies host -> device '''
-        n = sum(h.numel() * h.element_size() for h in snap['people'].values())
+        n = snap['arena'].numel() * snap['arena'].element_size()
         n += sum(h.numel() * h.element_size() for cols in snap['layers'].values() for h in cols.values())
         n += sum(snap[k].numel() * snap[k].element_size() for k in ('counters', 'vcounters', 'sums', 'log_count'))
         n += sum(h.numel() * h.element_size() for saved in snap['iv'] for h in saved.values())
@@ -700,7 +762,10 @@ class Sim:
                 tuple(p['quar_factor'].values()), p['n_beds_hosp'], p['n_beds_icu'], p['no_hosp_factor'], p['no_icu_factor'],
                 p['rel_symp_prob'], p['rel_severe_prob'], p['rel_crit_prob'], p['rel_death_prob'], p['trans_redux'], p['nab_boost'],
                 tuple(tuple(v.values()) for v in p['variant_pars'].values()), len(p['vaccine_pars']), p['quar_period'],
-                tuple(p['viral_dist'].values()))
+                tuple(p['viral_dist'].values()), tuple(tuple(d.values()) for d in p['dur'].values()),
+                tuple(p['nab_init'].values()) if p['nab_init'] else None, tuple(p['nab_eff'].values()) if p['nab_eff'] else None,
+                None if p['immunity'] is None else np.asarray(p['immunity']).tobytes(),
+                tuple(tuple(sorted((k, float(x)) for k, x in v.items() if isinstance(x, (int, float)))) for v in p['vaccine_pars'].values()))
 
     def _push_pars(self):
         ''' Re-send the scalar block when an intervention changed a parameter (reference sim.py:602-642 re-reads them daily) '''
@@ -817,6 +882,7 @@ class Sim:
                 self.complete = self.t == self.npts
             return
         _capi.call('cvb_state_invalidate', h)                      # Python (interventions, rescaling) may write People arrays today
+        self._sync_edges()
         people.t = t
         call = _capi.call if self.kernel_timers is None else self._timed_call
         self.rescale()
@@ -984,7 +1050,12 @@ class Sim:
         ''' The infection log as host arrays sorted by (date, variant, layer, target) (reference people.py:508-511) '''
         torch.cuda.synchronize(self.device)
         L = self._log
-        n = min(int(L['count'].item()), len(L['source']))
+        count, cap = int(L['count'].item()), len(L['source'])
+        if count > cap:
+            import warnings
+            warnings.warn(f'the infection log holds {cap} entries but {count} infections happened: the last {count - cap} are missing '
+                          f'(raise it with Sim(..., log_capacity=...)); compute_r_eff / compute_gen_time over the log are affected', RuntimeWarning)
+        n = min(count, cap)
         out = {k: L[k][:n].cpu().numpy() for k in ('source', 'target', 'date', 'layer', 'variant')}
         if self._comm is not None:             # every rank logs the infections of its own agents (global ids)
             parts = self._comm.gather_objects(out)
@@ -996,6 +1067,7 @@ class Sim:
         ''' Cumulative and derived results (reference sim.py:764-1072) '''
         if self.results_ready:
             raise AlreadyRunError('Simulation has already been finalized')
+        self._sync_edges()
         self.sync_results()
         R, pars = self.results, self.pars
         rv = self.rescale_vec

@@ -276,6 +276,9 @@ int cvb_plan_contact_tracing(cvb_sim* s, const cvb_trace_pars* host_pars, int32_
 /* people.py:199-206 update_contacts: the dynamic layers (bit l = layer l) regenerated at the start of every day */
 int cvb_plan_dynamic_layers(cvb_sim* s, uint32_t layer_mask);
 int cvb_run_days(cvb_sim* s, int32_t t0, int32_t t1, cvb_stream st);
+/* The same for several handles in lockstep (ensembles of small simulations, run.py:1406-1519 multi_run): day by day, every member's
+ * launches go to its own stream from ONE host thread, so the members' kernels overlap on the GPU.  host arrays of n_handles entries */
+int cvb_run_days_multi(cvb_sim** handles, int32_t n_handles, int32_t t0, int32_t t1, cvb_stream* streams);
 int cvb_state_invalidate(cvb_sim* s);
 /* Launch-shape overrides of the fused day kernels, for tuning runs (0 = default): what 0 / 1 = CTA size / agents per CTA of the
  * first per-agent kernel, 2 / 3 = the same for the second */

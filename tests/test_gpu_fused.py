@@ -92,3 +92,83 @@ def test_host_writes_between_runs_are_seen(cv):
     for k in ('n_quarantined', 'new_infections', 'n_exposed', 'cum_deaths'):
         assert np.array_equal(a.results[k].values, b.results[k].values), k
     assert a.results['n_quarantined'].values[10] >= 40
+
+
+@pytest.mark.parametrize('name', ['rescale3k', 'clip3k', 'hybrid3k', 'variants4k'])
+def test_restore_then_run_again(cv, name):
+    '''
+    snapshot() at day 0, run, restore(), run again: every result series identical -- including the state a run leaves outside the
+    People arrays (rescale vector, the edges clip_edges holds back, pending second doses), which restore must rewind too.
+    '''
+    sim = cv.Sim(**scenarios.build(cv, scenarios.SCENARIOS[name]))
+    sim.initialize()
+    snap = sim.snapshot()
+    sim.run()
+    first = {k: sim.results[k].values.copy() for k in sim.result_keys()}
+    layers = {lk: len(l) for lk, l in sim.people.contacts.items()}
+    sim.restore(snap)
+    sim.run()
+    for k, v in first.items():
+        assert np.array_equal(v, sim.results[k].values, equal_nan=True), k
+    assert layers == {lk: len(l) for lk, l in sim.people.contacts.items()}
+
+
+def test_restore_mid_run(cv):
+    ''' A snapshot taken in the middle of a run (second doses pending, population partly rescaled) resumes to the same end '''
+    spec = scenarios.SCENARIOS['rescale3k']
+    sim = cv.Sim(**scenarios.build(cv, spec))
+    sim.run(until=16)
+    snap = sim.snapshot()
+    sim.run(reset_seed=False)
+    first = {k: sim.results[k].values.copy() for k in sim.result_keys()}
+    sim.restore(snap)
+    sim.run(reset_seed=False)
+    for k, v in first.items():
+        assert np.array_equal(v[16:], sim.results[k].values[16:], equal_nan=True), k
+
+
+def test_multisim_lockstep_members_equal_solo_runs(cv):
+    ''' MultiSim advances its members through cvb_run_days_multi (one stream per member): each member identical to its solo run '''
+    base = cv.Sim(**scenarios.build(cv, C2_SMALL, pop_size=12000, n_days=40, pop_infected=120))
+    msim = cv.MultiSim(base, n_runs=5)
+    msim.run(keep_people=True)
+    assert all(s.fused_days == s.npts for s in msim.sims)
+    for i, member in enumerate(msim.sims):
+        solo = cv.Sim(**scenarios.build(cv, C2_SMALL, pop_size=12000, n_days=40, pop_infected=120, rand_seed=base['rand_seed'] + i), fused=False).run()
+        for k in solo.result_keys():
+            assert np.array_equal(solo.results[k].values, member.results[k].values, equal_nan=True), (i, k)
+            assert np.array_equal(solo.results[k].values, msim.member_results[i][k], equal_nan=True), (i, k)
+        for k in ('exposed', 'date_exposed', 'date_recovered', 'nab', 'quarantined'):
+            x, y = solo.people.to_numpy(k), member.people.to_numpy(k)
+            assert np.array_equal(x, y, equal_nan=(x.dtype.kind == 'f')), (i, k)
+
+
+class late_quarantine:
+    ''' Test-only intervention: on `day`, ask for a quarantine that starts `ahead` days later (People.schedule_quarantine, people.py:620-640) '''
+    def __init__(self, day, ahead):
+        self.day, self.ahead, self.initialized = day, ahead, False
+
+    def initialize(self, sim):
+        self.initialized = True
+
+    def __call__(self, sim):
+        if sim.t == self.day:
+            sim.people.schedule_quarantine(np.arange(50, 400, 7), start_date=sim.t + self.ahead, period=6)
+
+
+def test_quarantine_ring_grows_without_losing_requests(cv):
+    ''' A request beyond the ring's horizon re-sizes it in the middle of a run; the requests already pending (delayed tracing) survive '''
+    def go(pre_size):
+        spec = scenarios.SCENARIOS['hybrid3k']                      # contact tracing with trace_time up to 2 days
+        kw = scenarios.build(cv, spec)
+        kw['interventions'] = kw['interventions'] + [late_quarantine(14, 5)]
+        sim = cv.Sim(**kw)
+        sim.initialize()
+        if pre_size:
+            sim._set_quar_horizon(8)
+        return sim.run()
+    a, b = go(True), go(False)
+    assert b._quar_horizon >= 6
+    for k in ('new_quarantined', 'n_quarantined', 'new_infections', 'cum_diagnoses'):
+        assert np.array_equal(a.results[k].values, b.results[k].values), k
+    assert a.results['new_quarantined'].values[19] >= 40

@@ -23,6 +23,9 @@ One "step" = one complete run of that sim (181 simulated days of the hot path).
 
 N > 1 (torchrun): weak scaling -- every rank runs its own member of an ensemble (same configuration,
 seed + rank; reference run.py:1363-1365), no data-path collective; value = total agent-days / max time.
+In addition (block "partition"): ONE simulation agent-partitioned over the N GPUs (BASELINE config 4 recipe, 12.5M agents per
+GPU), with one ncclAllGather of 1 byte per agent per day on the data path, and a bit-identity check of a partitioned run against
+the single-GPU run of the same simulation.
 
 --impl reference: times the oracle port (the reference's CPU algorithm; the reference itself is Python and
 cannot travel to the GPU box) on the same configuration, each step a bounded sample of the workload.
@@ -274,6 +277,12 @@ def run_b200(args):
         torch.cuda.synchronize()
         e2e_s += max_over_ranks(time.perf_counter() - t0)
     e2e_value = n_gpus * agent_days / (e2e_s / args.steps)
+    # where the end-to-end time goes (one extra, separately synchronised pass; not part of the timed region above)
+    phases = {}
+    barrier()
+    t0 = time.perf_counter(); sim.restore(snap); torch.cuda.synchronize(); phases['restore_h2d_synchronised_ms'] = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter(); sim.set_seed(); sim._advance(sim.npts); torch.cuda.synchronize(); phases['days_ms'] = 1e3 * (time.perf_counter() - t0)
+    t0 = time.perf_counter(); sim.finalize(); torch.cuda.synchronize(); phases['finalize_d2h_ms'] = 1e3 * (time.perf_counter() - t0)
     summary = dict(cum_infections=sim.summary['cum_infections'], cum_deaths=sim.summary['cum_deaths'],
                    cum_diagnoses=sim.summary['cum_diagnoses'], cum_quarantined=sim.summary['cum_quarantined'])
 
@@ -282,22 +291,207 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline_from_gpu_state(args, cv, sim, snap)
 
+    ens = None
+    if world == 1 and rank == 0 and not args.no_ensemble:
+        del dev_snap
+        torch.cuda.empty_cache()
+        ens = ensemble_block(args, cv)
+    part = None
+    if world > 1 and not args.no_partition:
+        part = partition_block(args, cv, world, rank, max_over_ranks)
+
     if rank == 0:
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=n_gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
                    higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                    config=config_block(args, dict(edges=E, edges_by_layer=n_edges, parallelism=f'ensemble x{n_gpus} (one member per GPU, no collective)' if n_gpus > 1 else 'single GPU',
                                                   init_s=t_init)),
                    clocks=clocks,
-                   e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=sim.h2d_bytes(snap), d2h_bytes_per_step=sim.d2h_bytes(), ms_per_step=1e3 * e2e_s / args.steps),
+                   e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=sim.h2d_bytes(snap), d2h_bytes_per_step=sim.d2h_bytes(), ms_per_step=1e3 * e2e_s / args.steps, phases=phases),
                    gpu_launches=int(launches), roofline=roofline, kernels=kernels, edge_pass_dense=edge_dense, us_per_day=1e3 * ms_per_step / npts,
                    fused_days=int(fused_days),
                    epidemic=summary)
         if cpu is not None:
             out['cpu_baseline'] = cpu
+        if ens is not None:
+            out['ensembles'] = ens
+        if part is not None:
+            out['partition'] = part
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ensemble_block(args, cv):
+    """
+    Ensembles of SMALL simulations on one GPU (BASELINE configs 3 and 5; reference run.py:1406-1519 multi_run, one process per member).
+    Every member is far too small to fill a B200, so MultiSim advances all of them in lockstep through cvb_run_days_multi: one host
+    thread, one stream per member, five launches per member-day.  Reported: agent-days/s over the members' day loops (wall clock
+    around the lockstep run with a device synchronisation on both sides; initialisation and finalize excluded, as in `value`).
+      C3: --ens-members members of the 100k-agent hybrid sim (seed + i), test_prob + contact_tracing, 60 days
+      C5: --ens-members members of a 50k-agent random-network sim with a dynamic layer (regenerated on the device every day), each
+          with its own (beta, rel_death_prob) from the sweep grid of the reference's calibration example; Fit mismatch of every
+          member against the example data file (cumulative diagnoses / deaths), computed from the result tables.
+    """
+    import torch
+    out = {}
+    M = int(args.ens_members)
+
+    def run(sims):
+        msim = cv.MultiSim(sims)
+        t0 = time.perf_counter()
+        for sim in sims:
+            sim.initialize()
+            sim.set_seed()
+        torch.cuda.synchronize()
+        t_init = time.perf_counter() - t0
+        snaps = [sim.snapshot(pinned=False) for sim in sims] if args.ens_reps > 1 else None
+        best, launches = None, 0
+        for rep in range(args.ens_reps):
+            if rep:
+                for sim, snap in zip(sims, snaps):
+                    sim.restore(snap)
+                    sim.set_seed()
+            torch.cuda.synchronize()
+            launches0 = cv._capi.lib.cvb_launch_count()
+            t0 = time.perf_counter()
+            msim._advance_members(sims)
+            torch.cuda.synchronize()
+            el = time.perf_counter() - t0
+            launches = cv._capi.lib.cvb_launch_count() - launches0
+            best = el if best is None else min(best, el)
+        for sim in sims:
+            sim.finalize()
+        return msim, best, t_init, launches
+
+    # ---- C3 ----
+    sims = [cv.Sim(dict(pop_size=100_000, pop_type='hybrid', n_days=60, pop_infected=500, rand_seed=1 + i, verbose=0), pop_gen='device',
+                   interventions=[cv.test_prob(symp_prob=0.1, asymp_prob=0.01, start_day=10), cv.contact_tracing(trace_probs=0.3, start_day=15)])
+            for i in range(M)]
+    msim, el, t_init, launches = run(sims)
+    npts = sims[0].npts
+    out['C3'] = dict(members=M, pop_size=100_000, n_days=60, seconds=el, us_per_member_day=1e6 * el / (M * npts), agent_days_per_s=M * 100_000 * npts / el,
+                     init_s=t_init, gpu_launches=int(launches), fused_days=int(min(s.fused_days for s in sims)),
+                     cum_infections_median=float(np.median([s.summary['cum_infections'] for s in sims])))
+    del sims, msim
+    torch.cuda.empty_cache()
+    # ---- C5 ----
+    betas = np.linspace(0.005, 0.020, max(int(np.sqrt(M)), 1))
+    rdps = np.linspace(0.5, 3.0, max(-(-M // len(betas)), 1))
+    grid = [(b, r) for b in betas for r in rdps][:M]
+    sims = [cv.Sim(dict(pop_size=50_000, pop_type='random', n_days=45, pop_infected=100, rand_seed=1, verbose=0, beta=float(b), rel_death_prob=float(r),
+                        dynam_layer=dict(a=1)), pop_gen='device',
+                   interventions=[cv.test_prob(symp_prob=0.2, asymp_prob=0.005, start_day=0)]) for b, r in grid]
+    msim, el, t_init, launches = run(sims)
+    npts = sims[0].npts
+    results = [{k: s.results[k].values for k in s.result_keys()} for s in sims]
+    data = example_data()
+    source = data.pop('source')
+    mism = cv.fit_members(results, data, npts)
+    best = int(np.argmin(mism))
+    out['C5'] = dict(members=len(sims), pop_size=50_000, n_days=45, dynamic_layer=True, seconds=el, us_per_member_day=1e6 * el / (len(sims) * npts),
+                     agent_days_per_s=len(sims) * 50_000 * npts / el, init_s=t_init, gpu_launches=int(launches), fused_days=int(min(s.fused_days for s in sims)),
+                     fit=dict(data=source, best_member=best, best_beta=float(grid[best][0]), best_rel_death_prob=float(grid[best][1]),
+                              best_mismatch=float(mism[best]), worst_mismatch=float(np.max(mism))))
+    del sims, msim
+    torch.cuda.empty_cache()
+    return out
+
+
+def example_data():
+    """ The data file BASELINE config 5 fits against (reference examples/example_data.csv, copied into oracle/_ref by build()); a synthetic
+    series of the same shape when it is not there """
+    path = os.path.join(ROOT, 'oracle', '_ref', 'example_data.csv')
+    if os.path.exists(path):
+        import csv
+        rows = list(csv.DictReader(open(path)))
+        data = dict(date=[r['date'] for r in rows], source='reference examples/example_data.csv')
+        for k in ('new_diagnoses', 'new_tests', 'new_deaths'):
+            col = np.array([float(r[k]) if r[k] not in ('', None) else np.nan for r in rows])
+            data['cum_' + k[4:]] = np.nancumsum(col)
+        return data
+    days = np.arange(32)
+    diag = np.round(2 * np.exp(0.12 * days))
+    return dict(day=days, cum_diagnoses=np.cumsum(diag), cum_deaths=np.cumsum(np.round(0.02 * diag)), source='synthetic exponential series (example file not present)')
+
+
+def partition_block(args, cv, world, rank, max_over_ranks):
+    """
+    N > 1: ONE simulation agent-partitioned over the N GPUs (BASELINE config 4 recipe: hybrid, alpha + delta, waning, test_prob +
+    contact_tracing + vaccinate_prob + booster), weak-scaled at --part-agents agents per GPU, population generated on the device.
+    One NCCL all-gather of 1 byte per agent per day on the data path (plus a 1-bit-per-agent case bitmap on tracing days).
+    Also checks a 200k-agent partitioned run against the single-GPU run of the same simulation on rank 0, bit for bit.
+    """
+    import torch
+    import torch.distributed as dist
+    import scenarios
+    out = {}
+    # ---- bit identity: N ranks == 1 GPU -------------------------------------------------------------------
+    spec = dict(pars=dict(pop_size=200_000, pop_infected=1000, pop_type='hybrid', n_days=60, verbose=0, rand_seed=1),
+                interventions=[('test_prob', dict(symp_prob=0.1, asymp_prob=0.01, start_day=10)), ('contact_tracing', dict(trace_probs=0.3, start_day=15))])
+    psim = cv.Sim(**scenarios.build(cv, spec), partition=True, pop_exact=False)
+    psim.run()
+    log = psim.infection_log
+    gathered = {k: psim._comm.gather_objects(psim.people.to_numpy(k)) for k in ('exposed', 'date_exposed', 'date_recovered', 'date_dead', 'quarantined', 'date_diagnosed', 'n_infections')}
+    ok = None
+    if rank == 0:
+        ref = cv.Sim(**scenarios.build(cv, spec), pop_exact=False).run()
+        ok = all(np.array_equal(ref.people.to_numpy(k), np.concatenate(v, axis=-1), equal_nan=True) for k, v in gathered.items())
+        ok = ok and all(np.allclose(psim.results[k].values, ref.results[k].values, rtol=1e-6 if k == 'r_eff' else 1e-12, atol=0, equal_nan=True) for k in ref.result_keys())
+        ok = ok and all(np.array_equal(log[k], ref.infection_log[k]) for k in ('source', 'target', 'date', 'layer', 'variant'))
+        out['bit_identity'] = dict(ok=bool(ok), pop_size=200_000, n_days=60, ranks=world, cum_infections=float(ref.summary['cum_infections']),
+                                   what='People arrays, every result series and the infection log of the partitioned run == the single-GPU run')
+    del psim
+    torch.cuda.empty_cache()
+    # ---- the weak-scaled C4 recipe ---------------------------------------------------------------------------
+    n = int(args.part_agents) * world
+    pars = dict(pop_size=n, pop_type='hybrid', n_days=args.part_days, pop_infected=max(1, n // 200), rand_seed=1, verbose=0, use_waning=True)
+    variants = [cv.variant('alpha', days=5, n_imports=max(10, n // 20000)), cv.variant('delta', days=15, n_imports=max(10, n // 20000))]
+    ivs = [cv.test_prob(symp_prob=0.1, asymp_prob=0.01, start_day=10), cv.contact_tracing(trace_probs=0.3, start_day=15),
+           cv.vaccinate_prob('pfizer', days=list(range(10, 30)), prob=0.01), cv.vaccinate_prob('pfizer', days=[40], prob=0.05, booster=True, label='booster')]
+    t0 = time.time()
+    sim = cv.Sim(pars, variants=variants, interventions=ivs, pop_exact=False, partition=True, pop_gen='device')
+    sim.initialize()
+    torch.cuda.synchronize()
+    t_init = time.time() - t0
+    snap = sim.snapshot(pinned=False)
+    best = None
+    for rep in range(3):
+        sim.restore(snap)
+        sim.set_seed()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        while not sim.complete:
+            sim.step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = max_over_ranks(a.elapsed_time(b))
+        if rep > 0:
+            best = ms if best is None else min(best, ms)
+        sim.finalize()
+    sim.restore(snap)
+    sim.set_seed()
+    sim.kernel_timers = {}
+    while not sim.complete:
+        sim.step()
+    torch.cuda.synchronize()
+    kernels = {k: round(float(np.sum([x.elapsed_time(y) for x, y in v])) * 1e3 / sim.npts, 1) for k, v in sim.kernel_timers.items()}
+    sim.kernel_timers = None
+    sim.finalize()
+    if rank == 0:
+        out.update(workload='C4 recipe (hybrid, alpha + delta, waning, test_prob + contact_tracing + vaccinate_prob + booster), weak-scaled, device population',
+                   pop_size=n, agents_per_gpu=int(args.part_agents), n_days=args.part_days, n_gpus=world, ms_per_run=best, us_per_day=1e3 * best / sim.npts,
+                   agent_days_per_s=n * sim.npts / (best / 1e3), init_s=t_init, kernel_us_per_day=kernels,
+                   allgather_us_per_day=round(kernels.get('allgather_codes', 0.0) + kernels.get('allgather_cases', 0.0), 1),
+                   exchange_bytes_per_day_per_rank=int(sim._chunk * world + sim._chunk * world // 8), collective='ncclAllGather (torch.distributed all_gather_into_tensor), 1 byte per agent per day + 1 bit per agent on tracing days',
+                   hbm_gb_per_gpu=torch.cuda.max_memory_allocated() / 1e9,
+                   cum_infections=float(sim.summary['cum_infections']), cum_deaths=float(sim.summary['cum_deaths']), cum_doses=float(sim.summary['cum_doses']))
+    del sim
+    torch.cuda.empty_cache()
+    return out
 
 
 def measure_dense_edge_pass(args, cv, sim, snap, peak, E, N, day=60, reps=20):
@@ -502,6 +696,12 @@ def main():
     ap.add_argument('--n-days', type=int, default=180)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-dense', action='store_true', help='skip the separate dense edge-pass measurement')
+    ap.add_argument('--no-ensemble', action='store_true', help='skip the small-simulation ensemble block (BASELINE configs 3 and 5)')
+    ap.add_argument('--ens-members', type=int, default=64, help='members per GPU in the ensemble block')
+    ap.add_argument('--ens-reps', type=int, default=2)
+    ap.add_argument('--no-partition', action='store_true', help='N > 1: skip the agent-partitioned single-simulation block')
+    ap.add_argument('--part-agents', type=int, default=12_500_000, help='N > 1: agents per GPU of the partitioned simulation (BASELINE config 4: 100M over 8)')
+    ap.add_argument('--part-days', type=int, default=60)
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

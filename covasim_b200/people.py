@@ -114,6 +114,26 @@ class People:
     def to_numpy(self, key):
         return self._arrays[key].cpu().numpy()
 
+    def to_numpy_many(self, keys):
+        ''' Several fields to the host through ONE pinned staging buffer (one synchronisation instead of one pageable copy per field) '''
+        arrs = [self._arrays[k] for k in keys]
+        if not arrs or not arrs[0].is_cuda:
+            return [a.cpu().numpy() for a in arrs]
+        sizes = [a.numel() * a.element_size() for a in arrs]
+        offs = np.concatenate([[0], np.cumsum([(sz + 255) // 256 * 256 for sz in sizes])]).astype(np.int64)
+        need = int(offs[-1])
+        stage = getattr(self, '_stage', None)
+        if stage is None or stage.numel() < need:
+            stage = torch.empty(need, dtype=torch.uint8, pin_memory=True)
+            object.__setattr__(self, '_stage', stage)
+        views = []
+        for a, off, sz in zip(arrs, offs[:-1], sizes):
+            v = stage[int(off):int(off) + sz].view(a.dtype).view(a.shape)
+            v.copy_(a, non_blocking=True)
+            views.append(v)
+        torch.cuda.current_stream(self.device).synchronize()
+        return [v.numpy().copy() for v in views]
+
     # ---- counting helpers (reference base.py:1091-1145) -----------------------------------------
     def true(self, key):
         return cvu.true(self[key])

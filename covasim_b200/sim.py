@@ -536,12 +536,21 @@ class Sim:
     def _exchange_codes(self):
         ''' One fixed-size all-gather per day: every agent's 1-byte transmit code (stream-ordered, no host synchronisation) '''
         B = self._part_bufs
-        self._comm.all_gather(B['codes_global'], B['codes_local'])
+        self._timed_collective('allgather_codes', B['codes_global'], B['codes_local'])
 
     def _exchange_cases(self):
         ''' All-gather of today's case bitmap (1 bit per agent), on days a contact_tracing intervention is active '''
         B = self._part_bufs
-        self._comm.all_gather(B['case_global'], B['case_local'])
+        self._timed_collective('allgather_cases', B['case_global'], B['case_local'])
+
+    def _timed_collective(self, name, out, inp):
+        if self.kernel_timers is None:
+            return self._comm.all_gather(out, inp)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        self._comm.all_gather(out, inp)
+        b.record()
+        self.kernel_timers.setdefault(name, []).append((a, b))
 
     def _choose_true(self, key, stream, k):
         '''
@@ -751,9 +760,9 @@ class Sim:
         return int(n)
 
     def d2h_bytes(self):
-        ''' Bytes finalize() reads device -> host (result tables + the three date arrays compute_r_eff needs) '''
+        ''' Bytes finalize() reads device -> host (the result tables + the three sums compute_r_eff needs) '''
         n = sum(t.numel() * t.element_size() for t in (self._counters, self._vcounters, self._sums))
-        return int(n + 3 * 4 * self.n_local)
+        return int(n + 24)
 
     # ---- parameters -> device struct ---------------------------------------------------------------
     def _pars_fingerprint(self):
@@ -1164,19 +1173,24 @@ class Sim:
             return self.results['r_eff'].values
         if method != 'daily':
             raise ValueError(f'Method must be "daily", "infectious", or "outcome", not "{method}"')
+        # mean duration of infectiousness (sim.py:916-925): mean outcome date - mean date of becoming infectious over everybody with
+        # an outcome.  Three float64 sums on the device and one 24-byte read instead of three per-agent arrays on the host (the
+        # reference takes float32 means: the two agree to ~1e-7 relative)
         P = self.people
-        d_rec, d_dead, d_inf = P.to_numpy('date_recovered'), P.to_numpy('date_dead'), P.to_numpy('date_infectious')
-        rec = np.nonzero(~np.isnan(d_rec))[0]
-        dead = np.nonzero(~np.isnan(d_dead))[0]
-        outcome = np.concatenate((d_rec[rec], d_dead[dead]))
-        both = np.concatenate((rec, dead))
-        if self._comm is not None:             # means over the whole population from per-rank float64 sums
-            acc = torch.tensor([outcome.astype(np.float64).sum(), d_inf[both].astype(np.float64).sum(), float(len(outcome))], dtype=torch.float64, device=self.device)
+        d_rec, d_dead, d_inf = P['date_recovered'], P['date_dead'], P['date_infectious']
+        rec, dead = ~torch.isnan(d_rec), ~torch.isnan(d_dead)
+        f64 = torch.float64
+        acc = torch.stack([d_rec[rec].to(f64).sum() + d_dead[dead].to(f64).sum(), d_inf[rec].to(f64).sum() + d_inf[dead].to(f64).sum(),
+                           (rec.sum() + dead.sum()).to(f64)])
+        if self._comm is not None:             # over the whole population
             self._comm.all_reduce_sum(acc)
-            so, si, cnt_ = (float(x) for x in acc.cpu().numpy())
-            mean_inf = so / cnt_ - si / cnt_ if cnt_ else 0
-        else:
-            mean_inf = outcome.mean() - d_inf[both].mean() if len(outcome) else 0
+        so, si, cnt_ = (float(x) for x in acc.cpu().numpy())
+        mean_inf = so / cnt_ - si / cnt_ if cnt_ else 0
+        if self.rng_mode == 'mt' and self._comm is None:      # replay mode reproduces the reference to the last bit: float32 NumPy means
+            h_rec, h_dead, h_inf = P.to_numpy_many(('date_recovered', 'date_dead', 'date_infectious'))
+            ri, di_ = np.nonzero(~np.isnan(h_rec))[0], np.nonzero(~np.isnan(h_dead))[0]
+            outcome, both = np.concatenate((h_rec[ri], h_dead[di_])), np.concatenate((ri, di_))
+            mean_inf = outcome.mean() - h_inf[both].mean() if len(outcome) else 0
         R = self.results
         new_inf = R['new_infections'].values - R['n_imports'].values
         n_inf = R['n_infectious'].values

@@ -10,7 +10,9 @@ from oracle import cvoracle as cvo
 # float fields compared with a relative tolerance (float64 pow / exp / log / cos on the device differ from
 # glibc's by <= 2 ulp before the result is rounded to float32); everything else must be bit-identical
 TOL_FIELDS = {'sus_imm': 1e-6, 'symp_imm': 1e-6, 'sev_imm': 1e-6, 'peak_nab': 1e-6, 'nab': 1e-6}
-LOOSE_RESULTS = {'pop_nabs': 1e-6, 'pop_protection': 1e-6, 'pop_symp_protection': 1e-6}
+# r_eff: the mean infectious duration is a float64 device sum here and a float32 NumPy mean in the oracle / reference (whose own
+# cv.diff_sims compares with np.isclose, rtol 1e-5)
+LOOSE_RESULTS = {'pop_nabs': 1e-6, 'pop_protection': 1e-6, 'pop_symp_protection': 1e-6, 'r_eff': 1e-6}
 
 
 def build_pair(cv, name=None, spec=None, sim_kwargs=None, **extra):

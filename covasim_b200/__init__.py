@@ -15,6 +15,7 @@ from ._capi import CvbError  # noqa: F401
 from . import utils  # noqa: F401
 from .utils import *  # noqa: F401,F403
 from .base import Result, Layer, Contacts, AlreadyRunError  # noqa: F401
+from .devarray import DeviceArray  # noqa: F401
 from .people import People  # noqa: F401
 from .immunity import variant, calc_VE, calc_VE_symp, precompute_waning  # noqa: F401
 from .interventions import Intervention, dynamic_pars, sequence, change_beta, clip_edges, test_num, test_prob, contact_tracing, vaccinate_prob  # noqa: F401

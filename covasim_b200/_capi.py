@@ -86,6 +86,7 @@ PROTOTYPES = dict(
     cvb_set_pars=[_P, C.POINTER(cvb_pars)],
     cvb_set_nab_kin=[_P, _P, _i64],
     cvb_set_quar_horizon=[_P, _i32],
+    cvb_clone_scratch=[_P, _P, _P],
     cvb_bind_field=[_P, _i32, _P],
     cvb_bind_layer=[_P, _i32, _P, _P, _P, _i64],
     cvb_bind_adjacency=[_P, _P, _P, _i64, C.c_uint32],

@@ -300,6 +300,20 @@ int cvb_bind_log(cvb_sim* s, int32_t* source, int32_t* target, int32_t* date, in
     return 0;
 }
 
+int cvb_clone_scratch(cvb_sim* dst, const cvb_sim* src, cvb_stream st_) {
+    cudaStream_t st = (cudaStream_t)st_;
+    CVB_REQUIRE(dst && src, "cvb_clone_scratch: NULL handle");
+    CVB_REQUIRE(dst->n == src->n && dst->npts == src->npts && dst->nv == src->nv, "cvb_clone_scratch: the handles have different shapes");
+    if (src->quar_horizon > dst->quar_horizon && cvb_set_quar_horizon(dst, src->quar_horizon)) return 1;
+    CVB_REQUIRE(dst->quar_horizon == src->quar_horizon, "cvb_clone_scratch: the destination ring is larger than the source's");
+    CVB_CHECK(cudaMemcpyAsync(dst->quar_ring, src->quar_ring, (size_t)src->quar_horizon * src->n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CVB_CHECK(cudaMemcpyAsync(dst->beds, src->beds, (size_t)src->npts * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    CVB_CHECK(cudaMemcpyAsync(dst->edge_work, src->edge_work, (size_t)src->npts * 2 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    dst->last_t = src->last_t;
+    dst->state_valid = 0;
+    return 0;
+}
+
 int cvb_set_quar_horizon(cvb_sim* s, int32_t horizon) {
     CVB_REQUIRE(s && horizon >= 1 && horizon <= 64, "cvb_set_quar_horizon: horizon must be in [1,64]");
     if (horizon <= s->quar_horizon) return 0;

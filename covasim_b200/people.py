@@ -17,6 +17,7 @@ from . import defaults as cvd
 from . import utils as cvu
 from . import _capi
 from .base import Contacts, Layer
+from .devarray import DeviceArray
 
 __all__ = ['People']
 
@@ -49,8 +50,9 @@ class People:
             layout.append((name, dt, shape, total, nbytes))
             total += (nbytes + 255) // 256 * 256
         self._arena = torch.empty(max(total, 256), dtype=torch.uint8, device=self.device)
+        self._layout = layout
         for name, dt, shape, off, nbytes in layout:
-            A[name] = self._arena[off:off + nbytes].view(dt).view(shape)
+            A[name] = self._arena[off:off + nbytes].view(dt).view(shape).as_subclass(DeviceArray)      # NumPy idioms work on it (devarray.py)
             if name == 'uid':
                 A[name].copy_(torch.arange(lo, hi, dtype=torch.int32, device=self.device))
             elif name in cvd.states:
@@ -79,6 +81,21 @@ class People:
                 else:
                     layer.to(self.device)
                 self.contacts[lk] = layer
+
+    def __deepcopy__(self, memo):
+        ''' A copy with its own device arena (the fields stay views of ONE buffer) and its own contact layers '''
+        import copy
+        new = object.__new__(People)
+        memo[id(self)] = new
+        object.__setattr__(new, '_arrays', {})
+        for k, v in self.__dict__.items():
+            if k in ('_arrays', '_arena', '_stage'):
+                continue
+            object.__setattr__(new, k, copy.deepcopy(v, memo))
+        object.__setattr__(new, '_arena', self._arena.clone())
+        for name, dt, shape, off, nbytes in self._layout:
+            new._arrays[name] = new._arena[off:off + nbytes].view(dt).view(shape).as_subclass(DeviceArray)
+        return new
 
     # ---- array access -------------------------------------------------------------------------
     def __getattr__(self, name):

@@ -253,10 +253,51 @@ class Sim:
         return found if not isinstance(found, list) else (found[-1] if found else None)
 
     def copy(self):
-        ''' Deep copy of an un-initialised or host-only sim (device state is rebuilt by initialize) '''
-        if self.initialized:
-            raise NotImplementedError('copying an initialized sim is not built; copy before initialize()')
+        ''' A deep copy (reference base.py:444-446): of a running simulation too -- the copy gets its own device arrays and handle '''
         return copy.deepcopy(self)
+
+    _NO_COPY = ('_handle', '_adj', '_part_bufs', '_copy_stream', '_edges_event', '_plan', '_cpars', '_counters', '_vcounters', '_sums', '_log',
+                '_stream_ptr', '_comm', '_keyed_pop')
+
+    def __deepcopy__(self, memo):
+        if self._comm is not None:
+            raise NotImplementedError('an agent-partitioned simulation cannot be copied (its arrays are spread over several processes)')
+        if self._handle is not None:
+            self._sync_edges()
+            torch.cuda.synchronize(self.device)
+        new = type(self).__new__(type(self))
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            setattr(new, k, None if k in self._NO_COPY else copy.deepcopy(v, memo))
+        new._adj_mask = 0
+        if self._handle is not None:
+            new._clone_device_state(self)
+        return new
+
+    def _clone_device_state(self, src):
+        ''' Second half of a deep copy: a handle of its own, bound to the copied arrays, with the source's run state '''
+        torch.cuda.set_device(self.device)
+        h = C.c_void_p()
+        _capi.call('cvb_create', C.byref(h), self.n_local, self.pars['n_variants'], self.npts, int(self.pars['rand_seed']))
+        self._handle = h
+        self._stream_ptr = None
+        self._counters, self._vcounters, self._sums = src._counters.clone(), src._vcounters.clone(), src._sums.clone()
+        _capi.call('cvb_bind_results', h, self._counters.data_ptr(), self._vcounters.data_ptr(), self._sums.data_ptr())
+        self._log = {k: v.clone() for k, v in src._log.items()}
+        L = self._log
+        _capi.call('cvb_bind_log', h, L['source'].data_ptr(), L['target'].data_ptr(), L['date'].data_ptr(), L['layer'].data_ptr(),
+                   L['variant'].data_ptr(), len(L['source']), L['count'].data_ptr())
+        _capi.call('cvb_set_seed', h, int(self.rng.seed))
+        self.people._bind(self)
+        if self.pars['use_waning']:
+            kin = np.ascontiguousarray(self.pars['nab_kin'], dtype=np.float64)
+            _capi.call('cvb_set_nab_kin', h, kin.ctypes.data, len(kin))
+        self._pars_dirty = True
+        self._pars_key = None
+        self._push_pars()
+        _capi.call('cvb_clone_scratch', h, src._handle, self._stream_ptr)
+        self._build_adjacency()
+        self._build_plan_keep_days()
 
     # ---- initialisation (reference sim.py:94-125) --------------------------------------------------
     def set_seed(self, seed=-1):

@@ -174,8 +174,11 @@ int cvb_update_states_pre(cvb_sim* s, int32_t t, cvb_stream st);
  * end day" slots indexed by start_day % horizon (requests for one agent and start day are order-
  * independent: the reference extends to the max end and counts the agent once, people.py:339-346). */
 int cvb_schedule_quarantine(cvb_sim* s, const int32_t* inds, int64_t n, int32_t start_day, float end_day, cvb_stream st);
-/* how many days ahead requests may start (1 = today only); grows the ring, call before any request is pending */
+/* how many days ahead requests may start (1 = today only); grows the ring (requests already pending keep their days) */
 int cvb_set_quar_horizon(cvb_sim* s, int32_t horizon);
+/* base.py:444-446 Sim.copy of a running simulation: the library-owned per-run state of `src` (pending quarantine requests, bed counts, edge-work
+ * counters) copied into `dst`, a handle of the same shape whose arrays the caller has already bound */
+int cvb_clone_scratch(cvb_sim* dst, const cvb_sim* src, cvb_stream st);
 /* immunity.py:298 pars['nab_kin']: per-day NAb increments (host float64[n]) */
 int cvb_set_nab_kin(cvb_sim* s, const double* host_kin, int64_t n);
 /* people.py:189-196 update_states_post (check_diagnosed, check_quar, check_enter_iso) */

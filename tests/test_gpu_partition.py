@@ -40,7 +40,9 @@ def run_partitioned(cv, spec, world):
     return sims, logs
 
 
-@pytest.mark.parametrize('name,world', [('hybrid3k', 2), ('hybrid3k', 3), ('variants4k', 2), ('random2k_nowaning', 4), ('odd5003', 3)])
+# world 1: every row is whole (~36 entries per agent), which selects the 32-lanes-per-transmitter form of edge_pass_partition_kernel;
+# 2-4 ranks select the 16- and 8-lane forms
+@pytest.mark.parametrize('name,world', [('hybrid3k', 1), ('variants4k', 1), ('hybrid3k', 2), ('hybrid3k', 3), ('variants4k', 2), ('random2k_nowaning', 4), ('odd5003', 3)])
 def test_partitioned_equals_single(name, world):
     import covasim_b200 as cv
     spec = PART_SCENARIOS[name]

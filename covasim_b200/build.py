@@ -17,7 +17,8 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libcovasim_b200.so')
 STAMP = LIB + '.stamp'
 
-NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-fmad=false',
+# CVB_NVCC_EXTRA: extra flags for tuning builds (e.g. -DCVB_BEGIN_MINB=4), part of the source digest
+NVCC_FLAGS = os.environ.get('CVB_NVCC_EXTRA', '').split() + ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-fmad=false',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fno-strict-aliasing', '--shared', '-cudart', 'static']
 
 

@@ -141,8 +141,14 @@ __device__ __noinline__ float2 immunity_eval2(const uint4 en, int64_t n, const c
     return make_float2(s0, s1);
 }
 
+#ifndef CVB_BEGIN_MINB
+#define CVB_BEGIN_MINB 4      // 64 registers: occupancy beats the few spilled values (measured: 49 -> 42 us at C2, profiles/r2/README.md)
+#endif
+#ifndef CVB_MID_MINB
+#define CVB_MID_MINB 4
+#endif
 template <bool END, bool PRE, bool TEST, bool TSEL>
-__global__ void __launch_bounds__(kThreads, 3) day_begin_kernel(PeoplePtrs P, uint32_t* __restrict__ S, const __grid_constant__ cvb_pars pars,
+__global__ void __launch_bounds__(kThreads, CVB_BEGIN_MINB) day_begin_kernel(PeoplePtrs P, uint32_t* __restrict__ S, const __grid_constant__ cvb_pars pars,
                                                                const __grid_constant__ DayBeginArgs A) {
     __shared__ int s_flow[F_NK + CVB_MAX_VARIANTS];
     __shared__ int s_delta[kStockSlots];
@@ -421,7 +427,7 @@ struct DayMidArgs {
     double* sums;
 };
 
-__global__ void __launch_bounds__(kThreads, 4) day_mid_kernel(PeoplePtrs P, uint32_t* __restrict__ S, const __grid_constant__ cvb_pars pars,
+__global__ void __launch_bounds__(kThreads, CVB_MID_MINB) day_mid_kernel(PeoplePtrs P, uint32_t* __restrict__ S, const __grid_constant__ cvb_pars pars,
                                                              const __grid_constant__ DayMidArgs A) {
     __shared__ int s_cnt[M_NK];
     __shared__ int s_delta[kStockSlots];

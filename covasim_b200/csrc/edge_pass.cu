@@ -640,8 +640,20 @@ int cvb::edge_pass_impl(cvb_sim* s, int32_t t, cudaStream_t st, bool from_entrie
         if (from_entries) {
             CVB_REQUIRE(s->trans_ent, "cvb_edge_pass: transmitter entries missing");
             const uint4* adj = s->adj; const uint4* ents = s->trans_ent; const unsigned int* nt = s->n_trans;
-            if (multi) CVB_CHECK(launch_pdl(edge_pass_sparse2_kernel<true, 8, 4>, grid, kThreads, 0, st, s->rec, ep, adj, ents, nt, s->infect_key, s->cand, s->n_cand, work_row));
-            else CVB_CHECK(launch_pdl(edge_pass_sparse2_kernel<false, 8, 4>, grid, kThreads, 0, st, s->rec, ep, adj, ents, nt, s->infect_key, s->cand, s->n_cand, work_row));
+            const int shape = s->tune[4];                               // lanes per transmitter x entries in flight per lane (cvb_tune)
+            const int g2 = s->tune[5] > 0 ? 148 * s->tune[5] : grid;
+#define CVB_SP2(G, U) do { if (multi) CVB_CHECK(launch_pdl(edge_pass_sparse2_kernel<true, G, U>, g2, kThreads, 0, st, s->rec, ep, adj, ents, nt, s->infect_key, s->cand, s->n_cand, work_row)); \
+                           else CVB_CHECK(launch_pdl(edge_pass_sparse2_kernel<false, G, U>, g2, kThreads, 0, st, s->rec, ep, adj, ents, nt, s->infect_key, s->cand, s->n_cand, work_row)); } while (0)
+            switch (shape) {
+                case 1:  CVB_SP2(8, 6); break;
+                case 2:  CVB_SP2(16, 2); break;
+                case 3:  CVB_SP2(16, 3); break;
+                case 5:  CVB_SP2(32, 2); break;
+                case 6:  CVB_SP2(4, 8); break;
+                case 7:  CVB_SP2(8, 4); break;
+                default: CVB_SP2(16, 4); break;          // measured best on the C2 workload (profiles/r2/README.md)
+            }
+#undef CVB_SP2
         }
         else if (multi) edge_pass_sparse_kernel<true><<<grid, kThreads, 0, st>>>(s->rec, ep, s->adj_ptr, s->adj, s->trans_list, s->n_trans,
                                                                                s->infect_key, s->cand, s->n_cand, work_row);

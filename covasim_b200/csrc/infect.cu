@@ -312,7 +312,7 @@ static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t lis
     ia.adj_ptr = use_adj ? s->adj_ptr : nullptr; ia.adj = use_adj ? s->adj : nullptr; ia.adj_mask = use_adj ? s->adj_layer_mask : 0u;
     ia.beds_direct = with_state ? s->res.counters + (int64_t)t * CVB_N_COUNTERS + CVB_C_n_severe : nullptr;      // n_severe, n_critical are adjacent
     ia.vcounters_row = s->res.vcounters + (int64_t)t * s->nv * CVB_N_VCOUNTERS;
-    int grid = grid_for(max_items * 16, kThreads, 148 * 4);       // sixteen lanes per agent
+    int grid = grid_for(max_items * 16, kThreads, 148 * (s->tune[6] > 0 ? s->tune[6] : 4));       // sixteen lanes per agent
     {
         const int32_t* cand = s->cand; const unsigned int* nc = s->n_cand; const unsigned long long* beds = s->beds;
         uint32_t* state = with_state ? s->state : nullptr;

@@ -19,6 +19,7 @@ ap.add_argument('--pop-size', type=int, default=1_000_000)
 ap.add_argument('--n-days', type=int, default=180)
 ap.add_argument('--reps', type=int, default=3)
 ap.add_argument('--quick', action='store_true', help='only the default launch shapes')
+ap.add_argument('--edge', action='store_true', help='sweep the sparse edge pass shapes')
 args = ap.parse_args()
 pars = dict(pop_size=args.pop_size, pop_type='hybrid', n_days=args.n_days, pop_infected=max(1, int(0.005 * args.pop_size)), rand_seed=1, verbose=0)
 sim = cv.Sim(pars, interventions=[cv.test_prob(symp_prob=0.1, asymp_prob=0.01, start_day=20), cv.contact_tracing(trace_probs=0.3, start_day=30)], pop_exact=False)
@@ -48,7 +49,7 @@ def run_once(timing=False):
 
 
 def tune(**kw):
-    ids = dict(begin_threads=0, begin_chunk=1, mid_threads=2, mid_chunk=3, edge_lanes=4, edge_unroll=5)
+    ids = dict(begin_threads=0, begin_chunk=1, mid_threads=2, mid_chunk=3, edge_shape=4, edge_grid=5, infect_grid=6)
     for k, v in kw.items():
         cv._capi.call('cvb_tune', sim._handle, ids[k], int(v))
 
@@ -64,8 +65,10 @@ for th, ch in itertools.product((128, 256), (256, 512, 1024)):
         configs.append(dict(mid_threads=th, mid_chunk=ch))
 if args.quick:
     configs = [dict()]
+if args.edge:
+    configs = [dict()] + [dict(edge_shape=k) for k in range(1, 7)] + [dict(edge_grid=g) for g in (4, 6, 12, 16)] + [dict(infect_grid=g) for g in (1, 2)]
 for cfg in configs:
-    tune(begin_threads=0, begin_chunk=0, mid_threads=0, mid_chunk=0)
+    tune(begin_threads=0, begin_chunk=0, mid_threads=0, mid_chunk=0, edge_shape=0, edge_grid=0, infect_grid=0)
     tune(**cfg)
     best = min(run_once()['us_per_day'] for _ in range(args.reps))
     detail = run_once(timing=True)

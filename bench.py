@@ -147,6 +147,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device (covasim_b200 has no CPU fallback)')
     torch.cuda.set_device(local_rank)
+    numa_cpus = cv.bind_to_device_numa(local_rank) if world > 1 else None      # pinned snapshot buffers next to this rank's GPU
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
@@ -304,7 +305,7 @@ def run_b200(args):
         out = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=n_gpus, steps=args.steps, warmup=args.warmup, ms_per_step=ms_per_step,
                    higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
                    config=config_block(args, dict(edges=E, edges_by_layer=n_edges, parallelism=f'ensemble x{n_gpus} (one member per GPU, no collective)' if n_gpus > 1 else 'single GPU',
-                                                  init_s=t_init)),
+                                                  init_s=t_init, numa_cpus=(f'{numa_cpus[0]}-{numa_cpus[-1]} ({len(numa_cpus)} cores next to the GPU)' if numa_cpus else None))),
                    clocks=clocks,
                    e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=sim.h2d_bytes(snap), d2h_bytes_per_step=sim.d2h_bytes(), ms_per_step=1e3 * e2e_s / args.steps, phases=phases),
                    gpu_launches=int(launches), roofline=roofline, kernels=kernels, edge_pass_dense=edge_dense, us_per_day=1e3 * ms_per_step / npts,

@@ -110,6 +110,7 @@ PROTOTYPES = dict(
     cvb_edge_pass=[_P, _i32, _P],
     cvb_infect_winners=[_P, _i32, _P],
     cvb_infect_list=[_P, _P, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _P],
+    cvb_infect_list_taped=[_P, _P, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _P, _P],
     cvb_update_nab_count=[_P, _i32, _P],
     cvb_step_day=[_P, _i32, _P],
     cvb_test_prob=[_P, _i32, C.POINTER(cvb_test_prob_pars), _P, _P],

@@ -25,6 +25,7 @@ struct InfectArgs {
     int64_t hit_cap;
     const long long* adj_ptr; const uint4* adj; uint32_t adj_mask;   // fused pipeline: the source of a transmission over a layer the
                                              // adjacency covers is looked up in the TARGET's row (the raw edge lists are not read)
+    const double* tape;                      // verification (cvb_infect_list_taped): draws given by the caller, [list position][16 slots]
     const unsigned long long* beds_direct;   // fused pipeline: {n_severe, n_critical} of today's counter row (running totals); NULL: beds[t]
     unsigned long long* vcounters_row;       // today's by-variant counter row (stock differences)
 };
@@ -87,9 +88,15 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
 #pragma unroll
         for (int d = 8; d > 0; d >>= 1) src_adj = max(src_adj, __shfl_xor_sync(0xFFFFFFFFu, src_adj, d));
         const u32x4 words = keyed_words(ia.seed, P_INFECT, 0, t, gi, (uint32_t)slot);
-        const double u_mine = u53(words.x, words.y);
+        double u_mine = u53(words.x, words.y);
         double d0 = 0.0, d1 = 0.0;
-        if (slot <= 9 && !(slot & 1 && slot != 9)) {                // slots 0, 2, 4, 6, 8 (durations) and 9 (initial NAb level)
+        if (ia.tape) {
+            // taped draws: the value every prognosis step consumed in a recorded run of the reference (the uniform of a Bernoulli
+            // step, the finished duration / NAb sample of the others), indexed by the agent's position in the list
+            const unsigned long long kt = valid ? __ldcg(infect_key + i) : kEmptyKey;
+            const double v = kt != kEmptyKey ? ia.tape[(int64_t)(kt & 0xFFFFFFFFFFull) * 16 + slot] : 0.0;
+            u_mine = v; d0 = v; d1 = v;
+        } else if (slot <= 9 && !(slot & 1 && slot != 9)) {                // slots 0, 2, 4, 6, 8 (durations) and 9 (initial NAb level)
             // ONE copy of the Box-Muller / exp code for every slot (the kernel is launched cold every day with a handful
             // of warps: its time is instruction fetch, so code size matters more than the selects below)
             const double z = normal_from_words(words);
@@ -299,7 +306,7 @@ __global__ void claim_list_kernel(const int32_t* __restrict__ inds, int64_t n_in
 __global__ void reset_u32_kernel(unsigned int* p) { *p = 0; }
 
 static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t list_layer_code, int32_t hosp_max, int32_t icu_max,
-                         int64_t max_items, cudaStream_t st, bool hits = false, bool with_state = false) {
+                         int64_t max_items, cudaStream_t st, bool hits = false, bool with_state = false, const double* tape = nullptr) {
     CVB_REQUIRE(s->log.count, "infect: infection log is not bound (cvb_bind_log)");
     LayerTable L;
     if (build_layer_table(s, L, kTileEdges, 0)) return 1;          // no layer skipped: entry index == layer id
@@ -310,6 +317,7 @@ static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t lis
     ia.hit_src = hits ? s->hit_src : nullptr; ia.hit_key = hits ? s->hit_key : nullptr; ia.hit_cap = s->hit_cap;
     const bool use_adj = with_state && s->adj && s->adj_layer_mask;
     ia.adj_ptr = use_adj ? s->adj_ptr : nullptr; ia.adj = use_adj ? s->adj : nullptr; ia.adj_mask = use_adj ? s->adj_layer_mask : 0u;
+    ia.tape = tape;
     ia.beds_direct = with_state ? s->res.counters + (int64_t)t * CVB_N_COUNTERS + CVB_C_n_severe : nullptr;      // n_severe, n_critical are adjacent
     ia.vcounters_row = s->res.vcounters + (int64_t)t * s->nv * CVB_N_VCOUNTERS;
     int grid = grid_for(max_items * 16, kThreads, 148 * (s->tune[6] > 0 ? s->tune[6] : 4));       // sixteen lanes per agent
@@ -343,9 +351,24 @@ int cvb_infect_winners(cvb_sim* s, int32_t t, cvb_stream st) {
     return launch_infect_winners(s, t, false, (cudaStream_t)st);
 }
 
+static int infect_list_impl(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant, int32_t layer_code, int32_t t,
+                            int32_t count_flows, int32_t hosp_max, int32_t icu_max, const double* tape, cudaStream_t st);
+
 int cvb_infect_list(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant, int32_t layer_code, int32_t t,
-                    int32_t count_flows, int32_t hosp_max, int32_t icu_max, cvb_stream st_) {
-    cudaStream_t st = (cudaStream_t)st_;
+                    int32_t count_flows, int32_t hosp_max, int32_t icu_max, cvb_stream st) {
+    return infect_list_impl(s, inds, n, variant, layer_code, t, count_flows, hosp_max, icu_max, nullptr, (cudaStream_t)st);
+}
+
+int cvb_infect_list_taped(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant, int32_t layer_code, int32_t t,
+                          int32_t count_flows, int32_t hosp_max, int32_t icu_max, const double* tape, cvb_stream st) {
+    CVB_REQUIRE(tape, "cvb_infect_list_taped: NULL tape");
+    return infect_list_impl(s, inds, n, variant, layer_code, t, count_flows, hosp_max, icu_max, tape, (cudaStream_t)st);
+}
+
+}  // extern "C"
+
+static int infect_list_impl(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant, int32_t layer_code, int32_t t,
+                            int32_t count_flows, int32_t hosp_max, int32_t icu_max, const double* tape, cudaStream_t st) {
     CVB_REQUIRE(s && s->pars_set && s->res.counters, "cvb_infect_list: handle not ready");
     CVB_REQUIRE(variant >= 0 && variant < s->nv, "cvb_infect_list: variant %d out of range", variant);
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_infect_list: day %d outside [0,%d)", t, s->npts);
@@ -356,10 +379,8 @@ int cvb_infect_list(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant,
     CVB_LAUNCH_CHECK();
     claim_list_kernel<<<grid_for(n), kThreads, 0, st>>>(inds, n, variant, s->n, s->infect_key, s->cand, s->n_cand);
     CVB_LAUNCH_CHECK();
-    if (launch_infect(s, t, count_flows, layer_code, hosp_max, icu_max, n, st)) return 1;
+    if (launch_infect(s, t, count_flows, layer_code, hosp_max, icu_max, n, st, false, false, tape)) return 1;
     reset_u32_kernel<<<1, 1, 0, st>>>(s->n_cand);
     CVB_LAUNCH_CHECK();
     return 0;
 }
-
-}  // extern "C"

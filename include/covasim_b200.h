@@ -201,6 +201,12 @@ int cvb_infect_list(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant,
                     int32_t hosp_max, int32_t icu_max /* 0 / 1 as the caller decided (people.py:435), -1: from today's severe /
                                                          critical counts vs n_beds_* (sim.py:579-580) */,
                     cvb_stream st);
+/* The same with the random draws GIVEN instead of keyed: tape = device float64[n][16], row j for inds[j] (distinct agents), column =
+ * prognosis step (0 exp2inf, 1 symptomatic?, 2 asym2rec | inf2sym, 3 severe?, 4 mild2rec | sym2sev, 5 critical?, 6 sev2rec | sev2crit,
+ * 7 dies?, 8 crit2rec | crit2die, 9 initial NAb level): the uniform of a Bernoulli step, the finished sample of the others.  Verification
+ * entry point: feeds the kernel the draws a recorded run of the reference consumed (tests/golden/infect_tape.npz) */
+int cvb_infect_list_taped(cvb_sim* s, const int32_t* inds, int64_t n, int32_t variant, int32_t layer_code, int32_t t,
+                          int32_t count_flows, int32_t hosp_max, int32_t icu_max, const double* tape, cvb_stream st);
 /* immunity.py:205-213 update_nab + sim.py:652-674 stock counts and population means */
 int cvb_update_nab_count(cvb_sim* s, int32_t t, cvb_stream st);
 /* All of the above for day t in reference order, with no built-in interventions in between */

@@ -141,3 +141,69 @@ def test_viral_load_edge_cases(cv):
         got = cv.ops.compute_viral_load(t, d_inf, d_rec, d_dead, 0.3, 2.0, 4.0).cpu().numpy()
         want = cvo.compute_viral_load(t, d_inf, d_rec, d_dead, 0.3, 2.0, 4.0)
         assert np.array_equal(got, want)
+
+
+# ---- People.infect: the CUDA prognosis tree against arrays recorded from the reference, fed the reference's own draws ----------
+INFECT_CALLS = [('variants4k', 9), ('variants4k', 20), ('variants4k', 33), ('baseline20k', 35), ('baseline20k', 52)]
+_infect_sims = {}
+
+
+@pytest.mark.parametrize('name,day', INFECT_CALLS)
+def test_infect_kernel_against_reference_tape(cv, name, day):
+    '''
+    tests/golden/infect_tape.npz (oracle/gen_infect_golden.py): a People.infect call of the unmodified reference -- the targets, the
+    touched agents' arrays before and after, and every draw the call consumed, re-indexed per agent and prognosis step.  The CUDA
+    infect kernel is given the same agents, the same state and the same draws (cvb_infect_list_taped) and must produce the reference's
+    arrays: flags, dates, durations, counters, rel_trans bit for bit; the peak NAb level (a float64 2**x) at 1e-6.
+    '''
+    import ctypes as C
+    import os
+    import torch
+    import scenarios
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'infect_tape.npz'))
+    pre = f'{name}/t{day}/'
+    t, variant, hosp_max, icu_max = (int(x) for x in g[pre + 'args'])
+    if name not in _infect_sims:
+        sim = cv.Sim(**scenarios.build(cv, scenarios.SCENARIOS[name]))
+        sim.initialize()
+        _infect_sims[name] = (sim, sim.snapshot(pinned=False))
+    sim, snap = _infect_sims[name]
+    sim.restore(snap)
+    P, dev = sim.people, sim.people.device
+    uniq = torch.as_tensor(g[pre + 'uniq'].astype(np.int64), device=dev)
+    for key in g.files:                                               # the touched agents' state before the call
+        if key.startswith(pre + 'pre/'):
+            k = key.split('/')[-1]
+            vals = torch.as_tensor(g[key], device=dev)
+            if k in ('symp_imm', 'sev_imm'):
+                P[k][variant, uniq] = vals.to(P[k].dtype)
+            else:
+                P[k][uniq] = vals.to(P[k].dtype)
+    inds, infected, D = g[pre + 'inds'], g[pre + 'infected'], g[pre + 'draws']
+    tape = np.full((len(inds), 16), 0.5)
+    for row, a in enumerate(infected):                                # the kernel looks a draw up by the agent's FIRST position in the list
+        tape[int(np.nonzero(inds == a)[0][0])] = D[row]
+    d_inds = torch.as_tensor(inds.astype(np.int32), device=dev).contiguous()
+    d_tape = torch.as_tensor(tape, dtype=torch.float64, device=dev).contiguous()
+    sim.t = t
+    sim._push_pars()
+    cv._capi.call('cvb_infect_list_taped', sim._handle, d_inds.data_ptr(), len(inds), variant, cv._capi.LAYER_IMPORT, t, 1, hosp_max, icu_max,
+                  d_tape.data_ptr(), sim._stream_ptr)
+    torch.cuda.synchronize()
+    bad = []
+    u = g[pre + 'uniq']
+    for key in g.files:
+        if not key.startswith(pre + 'post/'):
+            continue
+        k = key.split('/')[-1]
+        want = g[key]
+        got = (P[k][variant, uniq] if k == 'exposed_by_variant' else P[k][uniq]).cpu().numpy()
+        if k == 'peak_nab':
+            ok = np.allclose(got, want, rtol=1e-6, atol=0, equal_nan=True)
+        else:
+            ok = np.array_equal(got.astype(want.dtype), want, equal_nan=(want.dtype.kind == 'f'))
+        if not ok:
+            j = int(np.nonzero(~np.isclose(got.astype(np.float64), want.astype(np.float64), rtol=1e-6, atol=0, equal_nan=True))[0][0])
+            bad.append(f'{k}: agent {u[j]} got {got[j]} want {want[j]}')
+    assert not bad, f'{name} day {day} (variant {variant}, hosp_max {hosp_max}, icu_max {icu_max}): ' + '; '.join(bad)
+    assert int(sim._counters[t, cv.defaults.COUNTER_IDS['new_infections']].item()) == len(infected)

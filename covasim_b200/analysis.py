@@ -288,3 +288,75 @@ def fit_members(member_results, data, npts, start_date=None, **kwargs):
     '''
     start_date = start_date or dt.date(2020, 3, 1)
     return np.array([Fit(data=data, results=res, npts=npts, start_date=start_date, **kwargs).mismatch for res in member_results])
+
+
+class TransTree:
+    '''
+    The transmission tree as arrays: a host view of the device infection log (reference analysis.py:1772-1866; the reference
+    builds Python lists of dicts per person, which does not scale to the populations this package runs).
+
+    ``source[k] -> target[k]`` on ``date[k]`` over layer ``layer[k]`` (index into the sim's layer keys; -1 seed infection, -2
+    importation) with variant ``variant[k]``; ``source`` is -1 for seed infections and importations.  Per-person views follow the
+    reference's attributes: ``sources`` / ``source_dates`` (who infected each person, and when; -1 / NaN if nobody),
+    ``n_targets`` (count_targets), ``transmissions`` / ``source_inds`` / ``target_inds`` (count_transmissions), ``r0()``.
+    The reference's loop tests ``if source:`` (analysis.py:1822), so transmissions whose source is person 0 do not enter
+    ``sources`` / ``targets``; ``count_targets`` reproduces that, ``count_transmissions`` and ``r0`` count every transmission.
+    '''
+
+    def __init__(self, sim=None, log=None, pop_size=None, n_days=None, date_exposed=None, date_recovered=None, layer_keys=None):
+        if sim is not None:
+            log = sim.infection_log
+            pop_size, n_days = sim.n, int(sim.people.t)
+            date_exposed, date_recovered = sim.people.to_numpy_many(('date_exposed', 'date_recovered'))
+            layer_keys = sim.people.layer_keys()
+        self.pop_size, self.n_days, self.layer_keys = int(pop_size), int(n_days), layer_keys
+        self.source = np.asarray(log['source'], dtype=np.int64)
+        self.target = np.asarray(log['target'], dtype=np.int64)
+        self.date = np.asarray(log['date'], dtype=np.int64)
+        self.layer = np.asarray(log['layer'], dtype=np.int64)
+        self.variant = np.asarray(log['variant'], dtype=np.int64)
+        self.date_exposed, self.date_recovered = date_exposed, date_recovered
+        truthy = self.source > 0                                   # the reference's `if source:` (None and person 0 are both falsy)
+        self.sources = np.full(self.pop_size, -1, dtype=np.int64)
+        self.source_dates = np.full(self.pop_size, np.nan)
+        order = np.argsort(self.date[truthy], kind='stable')       # a later infection of the same person overwrites the earlier one
+        self.sources[self.target[truthy][order]] = self.source[truthy][order]
+        self.source_dates[self.target[truthy][order]] = self.date[truthy][order]
+        self._n_given = np.bincount(self.source[truthy], minlength=self.pop_size)     # len(targets[i])
+        self.count_targets()
+        self.count_transmissions()
+
+    def __len__(self):
+        return len(self.target)
+
+    def targets_of(self, person):
+        ''' The people ``person`` infected, in log order (the reference's ``tt.targets[person]``) '''
+        return self.target[(self.source == person) & (self.source > 0)]
+
+    def count_targets(self, start_day=None, end_day=None):
+        ''' Number of people infected by everybody who was themselves infected (by somebody) between the two days (analysis.py:1880-1903) '''
+        start_day = 0 if start_day is None else int(start_day)
+        end_day = self.n_days if end_day is None else int(end_day)
+        has = (self.sources >= 0) & (self.source_dates >= start_day) & (self.source_dates <= end_day)
+        self.n_targets = self._n_given[has].astype(float)
+        return self.n_targets
+
+    def count_transmissions(self):
+        ''' Every transmission with a source, as [source, target] pairs (analysis.py:1906-1925) '''
+        has = self.source >= 0
+        self.source_inds, self.target_inds = self.source[has], self.target[has]
+        self.transmissions = np.stack([self.source_inds, self.target_inds], axis=1)
+        return self.transmissions
+
+    def r0(self, recovered_only=False):
+        ''' Mean number of transmissions per person who was ever exposed (analysis.py:2106-2129, without NetworkX) '''
+        if self.date_exposed is None:
+            raise RuntimeError('r0 needs the date_exposed array (build the tree from a sim)')
+        keep = ~np.isnan(self.date_exposed)
+        if recovered_only:
+            keep &= ~(self.date_recovered > self.n_days)
+        out_degree = np.bincount(self.source[self.source >= 0], minlength=self.pop_size)
+        return float(np.mean(out_degree[keep])) if keep.any() else float('nan')
+
+
+__all__ += ['TransTree']

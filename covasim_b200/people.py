@@ -249,6 +249,59 @@ class People:
         if len(inds):
             _capi.call('cvb_schedule_quarantine', sim._handle, inds.data_ptr(), len(inds), start_date, float(start_date + period), sim._stream_ptr)
 
+    def story(self, uid, *args, quiet=False):
+        '''
+        A short history of the events in the life of the given person / people (reference people.py:666-778): the lines the
+        reference prints, returned as a list of strings (and printed unless ``quiet``).
+        '''
+        labels = dict(a='default contact', h='household', s='school', w='workplace', c='community')
+        dates = dict(date_critical='became critically ill and needed ICU care', date_dead='died', date_diagnosed='was diagnosed with COVID',
+                     date_end_quarantine='ended quarantine', date_infectious='became infectious',
+                     date_known_contact='was notified they may have been exposed to COVID', date_pos_test='recieved their positive test result',
+                     date_quarantined='entered quarantine', date_recovered='recovered', date_severe='developed severe symptoms and needed hospitalization',
+                     date_symptomatic='became symptomatic', date_tested='was tested for COVID', date_vaccinated='was vaccinated against COVID')
+        log = self._sim.infection_log if self._sim is not None else None
+        lkeys = self.layer_keys()
+        lines = []
+        for person in [uid] + list(args):
+            i = int(person) - self.id0
+            get = lambda k: self._arrays[k][i].item()
+            sex = 'female' if get('sex') == 0 else 'male'
+            intro = f'This is the story of {person}, a {get("age"):.0f} year old {sex}'
+            if not get('susceptible'):
+                lines.append(f'{intro}, who had {"asymptomatic" if np.isnan(get("date_symptomatic")) else "symptomatic"} COVID.')
+            else:
+                lines.append(f'{intro}, who did not contract COVID.')
+            total, none = 0, []
+            for lk, layer in self.contacts.items():
+                k = int(((layer['p1'] == person) | (layer['p2'] == person)).sum().item()) if len(layer) else 0
+                total += k
+                llabel = labels.get(lk.lower(), f'"{lk}"')
+                if k:
+                    lines.append(f'{person} is connected to {k} people in the {llabel} layer')
+                else:
+                    none.append(llabel)
+            if none:
+                lines.append(f'{person} has no contacts in the {", ".join(none)} layer(s)')
+            lines.append(f'{person} has {total} contacts in total')
+            events = [(get(k), msg) for k, msg in dates.items() if not np.isnan(get(k))]
+            if log is not None:
+                layer_name = lambda code: labels.get(lkeys[code].lower(), f'"{lkeys[code]}"') if code >= 0 else None
+                for k in np.nonzero(log['target'] == person)[0]:
+                    code = int(log['layer'][k])
+                    events.append((float(log['date'][k]), f'was infected with COVID by {int(log["source"][k])} via the {layer_name(code)} layer' if code >= 0 else
+                                   ('was infected with COVID as a seed infection' if code == -1 else 'was infected with COVID by an importation')))
+                for k in np.nonzero(log['source'] == person)[0]:
+                    x = int((log['source'] == log['target'][k]).sum())
+                    events.append((float(log['date'][k]), f'gave COVID to {int(log["target"][k])} via the {layer_name(int(log["layer"][k]))} layer ({x} secondary infections)'))
+            if events:
+                lines += [f'On day {day:.0f}, {person} {event}' for day, event in sorted(events, key=lambda e: e[0])]
+            else:
+                lines.append(f'Nothing happened to {person} during the simulation.')
+        if not quiet:
+            print('\n'.join(lines))
+        return lines
+
     def make_nonnaive(self, inds):
         ''' Reset agents and mark them neither susceptible nor naive (reference people.py:412-431); ``inds`` are global ids '''
         inds = torch.as_tensor(inds, dtype=torch.int64, device=self.device)

@@ -1258,6 +1258,11 @@ class Sim:
         self.results['gen_time'] = gen_time(P.to_numpy('date_exposed'), P.to_numpy('date_symptomatic'), log['source'], log['target'])
         return self.results['gen_time']
 
+    def make_transtree(self, **kwargs):
+        ''' The transmission tree of the finished run as arrays (reference sim.py:1075-1089 / analysis.py:1772) '''
+        from .analysis import TransTree
+        return TransTree(self, **kwargs)
+
     def compute_summary(self, t=None):
         ''' reference sim.py:1040-1072 '''
         if t is None:

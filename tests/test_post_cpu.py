@@ -138,3 +138,25 @@ def test_analyzers_on_a_stand_in_sim():
     with pytest.raises(RuntimeError):
         snap.finalize(sim)                                     # finalising twice is an error, as in the reference
     assert isinstance(snap, cv.Analyzer) and snap.label == 'snapshot'
+
+
+@pytest.mark.parametrize('name', ['hybrid3k', 'variants4k'])
+def test_transtree_matches_reference(name):
+    ''' The array TransTree built from a golden infection log against what the reference's TransTree computed for the same run
+    (tests/golden/transtree_ref.npz, oracle/gen_transtree_golden.py): count_targets with and without a day window, the sources
+    of every person, and the transmissions '''
+    import os
+    from covasim_b200.analysis import TransTree
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = np.load(os.path.join(here, 'golden', f'{name}.npz'))
+    ref = np.load(os.path.join(here, 'golden', 'transtree_ref.npz'))
+    n_log, pop_size, n_days = (int(x) for x in ref[f'{name}/shape'])
+    log = {k: g['log/' + k] for k in ('source', 'target', 'date', 'layer', 'variant')}
+    tt = TransTree(log=log, pop_size=pop_size, n_days=n_days)
+    assert len(tt) == n_log
+    assert np.array_equal(tt.sources, ref[f'{name}/sources'])
+    assert np.array_equal(tt.count_targets(), ref[f'{name}/n_targets'])
+    assert np.array_equal(tt.count_targets(start_day=10, end_day=30), ref[f'{name}/n_targets_10_30'])
+    mine = tt.count_transmissions()
+    want = ref[f'{name}/transmissions']
+    assert np.array_equal(mine[np.lexsort(mine.T[::-1])], want[np.lexsort(want.T[::-1])])

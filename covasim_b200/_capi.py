@@ -94,6 +94,7 @@ PROTOTYPES = dict(
     cvb_bind_partition_adjacency=[_P, _P, _P, _i64, C.c_uint32],
     cvb_partition_status=[_P, _P],
     cvb_bind_results=[_P, _P, _P, _P],
+    cvb_bind_beds=[_P, _P],
     cvb_bind_log=[_P, _P, _P, _P, _P, _P, _i64, _P],
     cvb_keyed_uniform=[_u64, C.c_uint32, C.c_uint32, _i32, _i64, _i64, C.c_uint32, _P, _P],
     cvb_compute_viral_load=[_i32, _P, _P, _P, _f32, _f32, _f32, _P, _i64, _P],
@@ -122,6 +123,7 @@ PROTOTYPES = dict(
     cvb_trace_notify_contacts=[_P, _i32, C.POINTER(cvb_trace_pars), _P],
     cvb_vaccinate_prob=[_P, _i32, C.POINTER(cvb_vaccinate_pars), _P, _P, _P, _P],
     cvb_layer_regenerate=[_P, _i32, _i32, _P],
+    cvb_layer_regenerate_list=[_P, _i32, _i32, _P, _i64, _P],
     cvb_plan_clear=[_P],
     cvb_plan_test_prob=[_P, C.POINTER(cvb_test_prob_pars), _i32, _i32],
     cvb_plan_contact_tracing=[_P, C.POINTER(cvb_trace_pars), _i32, _i32],

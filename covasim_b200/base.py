@@ -148,12 +148,25 @@ class Layer:
         return out[:n_out.value]
 
     def update(self, people, frac=1.0):
-        ''' Regenerate a dynamic layer (reference base.py:1849-1876); frac=1 runs as one device pass '''
+        '''
+        Regenerate a dynamic layer (reference base.py:1849-1876): ``round(E * frac)`` edges, chosen without replacement, get two fresh
+        uniformly random endpoints and weight 1.  frac = 1 is one device pass over the layer; frac < 1 picks the edges on the host
+        (the reference's cvu.choose from the Numba stream; the O(k) sampler in native-RNG mode) and regenerates those.
+        '''
         sim = self._sim
         self._ready()
-        if frac != 1.0:
-            raise NotImplementedError('partial regeneration (frac < 1) is not built')
-        _capi.call('cvb_layer_regenerate', sim._handle, self._index, sim.t, sim._stream_ptr)
+        if frac == 1.0:
+            _capi.call('cvb_layer_regenerate', sim._handle, self._index, sim.t, sim._stream_ptr)
+            return
+        n_new = int(np.round(len(self) * frac))
+        if n_new <= 0:
+            return
+        if sim.rng_mode == 'mt':
+            raise NotImplementedError('partial regeneration (frac < 1) is not built for replay mode')
+        from . import utils as cvu
+        inds = torch.as_tensor(cvu.choose_distinct(sim.rng.nb, len(self), n_new), dtype=torch.int64, device=self.device).contiguous()
+        _capi.call('cvb_layer_regenerate_list', sim._handle, self._index, sim.t, inds.data_ptr(), n_new, sim._stream_ptr)
+        sim._adj_dirty = sim._adj_dirty or bool((sim._adj_mask >> self._index) & 1)
 
     def pop_inds(self, inds):
         ''' Remove edges by index and return them (reference base.py:1742-1757) -- used by clip_edges-style interventions '''

@@ -138,7 +138,7 @@ int cvb_create(cvb_sim** out, int64_t n_agents, int32_t n_variants, int32_t npts
 
 int cvb_destroy(cvb_sim* s) {
     if (!s) return 0;
-    cudaFree(s->cand); cudaFree(s->n_cand); cudaFree(s->infect_key); cudaFree(s->beds); cudaFree(s->edge_work); cudaFree(s->quar_ring); cudaFree(s->case_bits); cudaFree(s->inf_bits);
+    cudaFree(s->cand); cudaFree(s->n_cand); cudaFree(s->infect_key); if (!s->beds_external) cudaFree(s->beds); cudaFree(s->edge_work); cudaFree(s->quar_ring); cudaFree(s->case_bits); cudaFree(s->inf_bits);
     cudaFree(s->trans_list); cudaFree(s->case_list); cudaFree(s->n_trans); cudaFree(s->n_case_list);
     cudaFree(s->n_cases); cudaFree(s->dev_scalars); cudaFree(s->rec_store); cudaFree(s->ts8_store);
     cudaFree(s->nab_kin); cudaFree(s->tile_cnt); cudaFree(s->hit_mask); cudaFree(s->flag_tmp); cudaFree(s->partial);
@@ -289,6 +289,14 @@ int cvb_bind_results(cvb_sim* s, int64_t* counters, int64_t* vcounters, double* 
     s->res.counters = (unsigned long long*)counters;
     s->res.vcounters = (unsigned long long*)vcounters;
     s->res.sums = sums;
+    return 0;
+}
+
+int cvb_bind_beds(cvb_sim* s, int64_t* beds) {
+    CVB_REQUIRE(s && beds, "cvb_bind_beds: NULL argument");
+    if (!s->beds_external) cudaFree(s->beds);
+    s->beds = (unsigned long long*)beds;
+    s->beds_external = 1;
     return 0;
 }
 

@@ -88,6 +88,7 @@ struct cvb_sim {
     int32_t* cand; unsigned int* n_cand;            // today's newly infected candidates
     unsigned long long* infect_key;                 // [N] winning transmission key per target (kEmptyKey = none)
     unsigned long long* beds;                       // [npts][2] severe / critical after update_states_pre
+    int32_t beds_external;                          // bound by the caller (cvb_bind_beds): agent-partitioned runs all-reduce the day's row
     unsigned long long* edge_work;                  // [npts][2] adjacency entries visited / transmitters, per day (sparse edge pass)
     double* nab_kin; int64_t nab_kin_len;           // NAb kinetics table (immunity.py:298)
     float* quar_ring; int32_t quar_horizon;         // [quar_horizon][N] pending quarantine end days, -1 = none

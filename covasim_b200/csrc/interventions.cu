@@ -369,11 +369,34 @@ __global__ void __launch_bounds__(kThreads) layer_regen_kernel(int32_t* __restri
     }
 }
 
+// the same for a chosen subset of the edges (frac < 1): edge e keeps the key it has in a full regeneration
+__global__ void __launch_bounds__(kThreads) layer_regen_list_kernel(int32_t* __restrict__ p1, int32_t* __restrict__ p2, float* __restrict__ beta,
+        const int64_t* __restrict__ inds, int64_t n_inds, int64_t n_edges, int64_t n, uint64_t seed, int32_t layer, int32_t t) {
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_inds; j += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = inds[j];
+        if (e < 0 || e >= n_edges) continue;
+        u32x4 r = keyed_words(seed, P_DYNLAYER, (uint32_t)layer, t, e, 0);
+        int64_t a = (int64_t)dmul(u53(r.x, r.y), (double)n), b = (int64_t)dmul(u53(r.z, r.w), (double)n);
+        p1[e] = (int32_t)(a < n - 1 ? a : n - 1);
+        p2[e] = (int32_t)(b < n - 1 ? b : n - 1);
+        beta[e] = 1.0f;
+    }
+}
+
 }  // namespace cvb
 
 using namespace cvb;
 
 extern "C" {
+
+int cvb_layer_regenerate_list(cvb_sim* s, int32_t layer, int32_t t, const int64_t* inds, int64_t n_inds, cvb_stream st) {
+    CVB_REQUIRE(s && layer >= 0 && layer < CVB_MAX_LAYERS && (n_inds == 0 || inds), "cvb_layer_regenerate_list: bad argument");
+    cvb::LayerPtrs& L = s->layers[layer];
+    if (L.n_edges == 0 || n_inds == 0) return 0;
+    layer_regen_list_kernel<<<grid_for(n_inds), kThreads, 0, (cudaStream_t)st>>>(L.p1, L.p2, L.beta, inds, n_inds, L.n_edges, s->n, s->seed, layer, t);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
 
 int cvb_test_prob(cvb_sim* s, int32_t t, const cvb_test_prob_pars* tp, const double* prob_override, cvb_stream st) {
     if (s) cvb::state_touched(s);

@@ -256,7 +256,7 @@ class Sim:
         ''' A deep copy (reference base.py:444-446): of a running simulation too -- the copy gets its own device arrays and handle '''
         return copy.deepcopy(self)
 
-    _NO_COPY = ('_handle', '_adj', '_part_bufs', '_copy_stream', '_edges_event', '_plan', '_cpars', '_counters', '_vcounters', '_sums', '_log',
+    _NO_COPY = ('_handle', '_adj', '_beds', '_part_bufs', '_copy_stream', '_edges_event', '_plan', '_cpars', '_counters', '_vcounters', '_sums', '_log',
                 '_stream_ptr', '_comm', '_keyed_pop')
 
     def __deepcopy__(self, memo):
@@ -487,8 +487,6 @@ class Sim:
             self._comm = cvpart.DistComm() if self._partition is True else self._partition
             if any(pars['dynam_layer'].get(lk) for lk in pop['contacts'].keys()):
                 raise NotImplementedError('dynamic layers cannot be agent-partitioned (their edges are regenerated over the whole population every day)')
-            if pars['n_beds_hosp'] is not None or pars['n_beds_icu'] is not None:
-                raise NotImplementedError('bed limits (n_beds_hosp / n_beds_icu) need a global count every day and are not built for agent-partitioned runs')
             self._chunk, ranges = cvpart.plan(self.n, self._comm.world)
             lo, hi = ranges[self._comm.rank]
             # every rank builds the same population from the same seed and keeps its own agents; the edge lists stay on the
@@ -519,6 +517,10 @@ class Sim:
         self._vcounters = torch.zeros((npts, nv, cvd.N_VCOUNTERS), dtype=torch.int64, device=dev)
         self._sums = torch.zeros((npts, 4), dtype=torch.float64, device=dev)
         _capi.call('cvb_bind_results', h, self._counters.data_ptr(), self._vcounters.data_ptr(), self._sums.data_ptr())
+        self._beds = None
+        if self._comm is not None:         # bed limits compare GLOBAL counts (sim.py:579-580): the day's row is summed over the ranks
+            self._beds = torch.zeros((npts, 2), dtype=torch.int64, device=dev)
+            _capi.call('cvb_bind_beds', h, self._beds.data_ptr())
         cap = int(self.log_capacity) if self.log_capacity else int(max(4 * self.n_local, 1024))
         self._log = dict(source=torch.empty(cap, dtype=torch.int32, device=dev), target=torch.empty(cap, dtype=torch.int32, device=dev),
                          date=torch.empty(cap, dtype=torch.int32, device=dev), layer=torch.empty(cap, dtype=torch.int8, device=dev),
@@ -940,6 +942,8 @@ class Sim:
         if self._adj_dirty:
             self._build_adjacency()
         call('cvb_update_states_pre', h, t, st)
+        if self._beds is not None and (pars['n_beds_hosp'] is not None or pars['n_beds_icu'] is not None):
+            self._comm.all_reduce_sum(self._beds[t])             # 16 bytes: today's severe / critical counts over all ranks
         for lkey, dyn in pars['dynam_layer'].items():                                 # reference people.py:199-206
             if dyn:
                 people.contacts[lkey].update(people)

@@ -126,6 +126,9 @@ int cvb_partition_status(cvb_sim* s, int64_t* host_out2);
 /* Per-day result tables: counters int64[npts][CVB_N_COUNTERS], vcounters int64[npts][n_variants][CVB_N_VCOUNTERS],
  * sums double[npts][4] = {sum nab over alive, sum sus_imm, sum symp_imm, unused} (reference sim.py:652-674) */
 int cvb_bind_results(cvb_sim* s, int64_t* counters, int64_t* vcounters, double* sums);
+/* Optional: the caller's own int64[npts][2] table for the day's {severe, critical} counts after update_states_pre (sim.py:579-580: the bed
+ * limits).  An agent-partitioned run binds one and sums the day's row over the ranks (one 16-byte all-reduce) before anybody is infected */
+int cvb_bind_beds(cvb_sim* s, int64_t* beds);
 /* Device infection log (reference people.py:508-511): parallel arrays of capacity `cap`, *count is device int64 */
 int cvb_bind_log(cvb_sim* s, int32_t* source, int32_t* target, int32_t* date, int8_t* layer, int8_t* variant,
                  int64_t cap, int64_t* count);
@@ -265,6 +268,8 @@ int cvb_vaccinate_prob(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* host_par
 
 /* base.py:1849-1876 Layer.update with frac=1: regenerate every edge of a dynamic layer on the device */
 int cvb_layer_regenerate(cvb_sim* s, int32_t layer, int32_t t, cvb_stream st);
+/* ... with frac < 1: only the listed edges (device int64[n_inds], chosen by the caller: base.py:1866 cvu.choose) get new endpoints */
+int cvb_layer_regenerate_list(cvb_sim* s, int32_t layer, int32_t t, const int64_t* inds, int64_t n_inds, cvb_stream st);
 
 /* ------------------------------------------------------------------------------------------------
  * Whole blocks of days without returning to the host (sim.py:688-761 Sim.run -> sim.py:558-685 Sim.step).

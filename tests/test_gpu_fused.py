@@ -172,3 +172,27 @@ def test_quarantine_ring_grows_without_losing_requests(cv):
     for k in ('new_quarantined', 'n_quarantined', 'new_infections', 'cum_diagnoses'):
         assert np.array_equal(a.results[k].values, b.results[k].values), k
     assert a.results['new_quarantined'].values[19] >= 40
+
+
+def test_layer_update_with_a_fraction(cv):
+    ''' Layer.update(people, frac < 1) (reference base.py:1849-1876): exactly round(E * frac) edges get new endpoints and weight 1 '''
+    sim = cv.Sim(pop_size=5000, n_days=10, pop_infected=50, rand_seed=9, verbose=0, dynam_layer=dict(a=1))
+    sim.initialize()
+    layer = sim.people.contacts['a']
+    layer['beta'][:] = 0.5
+    before = layer.to_numpy()
+    E = len(layer)
+    sim.t = 3
+    layer.update(sim.people, frac=0.25)
+    after = layer.to_numpy()
+    touched = after['beta'] == 1.0
+    assert int(touched.sum()) == int(np.round(E * 0.25))
+    same = (before['p1'] == after['p1']) & (before['p2'] == after['p2'])
+    assert same[~touched].all() and (~same[touched]).mean() > 0.99
+    assert after['p1'].min() >= 0 and after['p1'].max() < 5000 and after['p2'].max() < 5000
+    full = cv.Sim(pop_size=5000, n_days=10, pop_infected=50, rand_seed=9, verbose=0, dynam_layer=dict(a=1))
+    full.initialize()
+    full.t = 3
+    full.people.contacts['a'].update(full.people)                      # an edge gets the same endpoints in a partial and a full regeneration
+    f = full.people.contacts['a'].to_numpy()
+    assert np.array_equal(f['p1'][touched], after['p1'][touched]) and np.array_equal(f['p2'][touched], after['p2'][touched])

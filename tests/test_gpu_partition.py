@@ -22,6 +22,8 @@ PART_SCENARIOS = {
     # three variants, importations, vaccine + booster (variants4k without the bed limits, which need a daily global count)
     'variants4k': dict(pars={k: v for k, v in scenarios.SCENARIOS['variants4k']['pars'].items() if not k.startswith('n_beds')},
                        variants=scenarios.SCENARIOS['variants4k']['variants'], interventions=scenarios.SCENARIOS['variants4k']['interventions']),
+    # ... and with them: the day's severe / critical counts are summed over the ranks before anybody is infected
+    'variants4k_beds': scenarios.SCENARIOS['variants4k'],
     'random2k_nowaning': scenarios.SCENARIOS['random2k_nowaning'],
     # population size not divisible by 32 * world
     'odd5003': dict(pars=dict(pop_size=5003, pop_infected=80, pop_type='hybrid', n_days=35, verbose=0, rand_seed=4, beta=0.02),
@@ -42,7 +44,7 @@ def run_partitioned(cv, spec, world):
 
 # world 1: every row is whole (~36 entries per agent), which selects the 32-lanes-per-transmitter form of edge_pass_partition_kernel;
 # 2-4 ranks select the 16- and 8-lane forms
-@pytest.mark.parametrize('name,world', [('hybrid3k', 1), ('variants4k', 1), ('hybrid3k', 2), ('hybrid3k', 3), ('variants4k', 2), ('random2k_nowaning', 4), ('odd5003', 3)])
+@pytest.mark.parametrize('name,world', [('hybrid3k', 1), ('variants4k', 1), ('hybrid3k', 2), ('hybrid3k', 3), ('variants4k', 2), ('variants4k_beds', 3), ('random2k_nowaning', 4), ('odd5003', 3)])
 def test_partitioned_equals_single(name, world):
     import covasim_b200 as cv
     spec = PART_SCENARIOS[name]
@@ -81,8 +83,6 @@ def test_partitioned_rejects_what_it_cannot_do():
     comm = cvpart.LocalComm.make(1)[0]
     with pytest.raises(NotImplementedError):
         cv.Sim(pop_size=2000, n_days=5, dynam_layer=dict(a=1), partition=comm).initialize()
-    with pytest.raises(NotImplementedError):
-        cv.Sim(pop_size=2000, n_days=5, n_beds_hosp=10, partition=comm).initialize()
     with pytest.raises(NotImplementedError):
         cv.Sim(pop_size=2000, n_days=5, rng='mt', partition=comm)
     with pytest.raises(ValueError):

@@ -115,6 +115,7 @@ PROTOTYPES = dict(
     cvb_update_nab_count=[_P, _i32, _P],
     cvb_step_day=[_P, _i32, _P],
     cvb_test_prob=[_P, _i32, C.POINTER(cvb_test_prob_pars), _P, _P],
+    cvb_test_prob_taped=[_P, _i32, C.POINTER(cvb_test_prob_pars), _P, _P, _P],
     cvb_test_num_keys=[_P, _i32, C.POINTER(cvb_test_num_pars), _P, _P, _P],
     cvb_test_list=[_P, _i32, _P, _i64, C.c_double, C.c_double, _i32, _i32, _P],
     cvb_contact_tracing=[_P, _i32, C.POINTER(cvb_trace_pars), _P],

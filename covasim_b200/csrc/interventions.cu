@@ -15,7 +15,8 @@ namespace cvb {
 // test_prob
 // ================================================================================================
 __global__ void __launch_bounds__(kThreads, 3) test_prob_kernel(PeoplePtrs P, const __grid_constant__ cvb_test_prob_pars tp, uint64_t seed,
-        int64_t n, int64_t id0, int32_t t, bool vec, unsigned long long* __restrict__ counters, const double* __restrict__ prob_override) {
+        int64_t n, int64_t id0, int32_t t, bool vec, unsigned long long* __restrict__ counters, const double* __restrict__ prob_override,
+        const double* __restrict__ tape /* verification: the three uniforms of every agent given instead of keyed, [n][3]; or NULL */) {
     __shared__ int s_cnt;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
@@ -56,15 +57,15 @@ __global__ void __launch_bounds__(kThreads, 3) test_prob_kernel(PeoplePtrs P, co
                 if (ov == ov) prob = ov;
             }
             if (!(prob > 0.0)) continue;
-            if (!(keyed_uniform(seed, P_TEST, (uint32_t)tp.index, t, i + id0, 0) < prob)) continue;
+            if (!((tape ? tape[i * 3] : keyed_uniform(seed, P_TEST, (uint32_t)tp.index, t, i + id0, 0)) < prob)) continue;
             // People.test (people.py:589-617)
             ++c;
             tested[i] = 1;
             d_tested[i] = tf;
             if (!flag(w_inf, k)) continue;
-            if (!(keyed_uniform(seed, P_TEST_SENS, (uint32_t)tp.index, t, i + id0, 0) < tp.sensitivity)) continue;
+            if (!((tape ? tape[i * 3 + 1] : keyed_uniform(seed, P_TEST_SENS, (uint32_t)tp.index, t, i + id0, 0)) < tp.sensitivity)) continue;
             if (!is_nan(ddiag[k])) continue;
-            if (!(keyed_uniform(seed, P_TEST_LOSS, (uint32_t)tp.index, t, i + id0, 0) < 1.0 - tp.loss_prob)) continue;
+            if (!((tape ? tape[i * 3 + 2] : keyed_uniform(seed, P_TEST_LOSS, (uint32_t)tp.index, t, i + id0, 0)) < 1.0 - tp.loss_prob)) continue;
             d_diag[i] = (float)(t + tp.test_delay);
             d_pos[i] = tf;
         }
@@ -398,16 +399,25 @@ int cvb_layer_regenerate_list(cvb_sim* s, int32_t layer, int32_t t, const int64_
     return 0;
 }
 
-int cvb_test_prob(cvb_sim* s, int32_t t, const cvb_test_prob_pars* tp, const double* prob_override, cvb_stream st) {
+static int test_prob_impl(cvb_sim* s, int32_t t, const cvb_test_prob_pars* tp, const double* prob_override, const double* tape, cudaStream_t st) {
     if (s) cvb::state_touched(s);
     CVB_REQUIRE(s && tp && s->res.counters, "cvb_test_prob: handle not ready");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_test_prob: day %d outside [0,%d)", t, s->npts);
     uintptr_t al = 0;
     for (int f = 0; f < CVB_N_FIELDS; ++f) al |= (uintptr_t)s->people.f[f];
-    test_prob_kernel<<<grid_for((s->n + kAPT - 1) / kAPT, kThreads, 148 * 8), kThreads, 0, (cudaStream_t)st>>>(
-        s->people, *tp, s->seed, s->n, s->partitioned ? s->id0 : 0, t, (al & 15) == 0 && s->n % 4 == 0, s->res.counters, prob_override);
+    test_prob_kernel<<<grid_for((s->n + kAPT - 1) / kAPT, kThreads, 148 * 8), kThreads, 0, st>>>(
+        s->people, *tp, s->seed, s->n, s->partitioned ? s->id0 : 0, t, (al & 15) == 0 && s->n % 4 == 0, s->res.counters, prob_override, tape);
     CVB_LAUNCH_CHECK();
     return 0;
+}
+
+int cvb_test_prob(cvb_sim* s, int32_t t, const cvb_test_prob_pars* tp, const double* prob_override, cvb_stream st) {
+    return test_prob_impl(s, t, tp, prob_override, nullptr, (cudaStream_t)st);
+}
+
+int cvb_test_prob_taped(cvb_sim* s, int32_t t, const cvb_test_prob_pars* tp, const double* prob_override, const double* tape, cvb_stream st) {
+    CVB_REQUIRE(tape, "cvb_test_prob_taped: NULL tape");
+    return test_prob_impl(s, t, tp, prob_override, tape, (cudaStream_t)st);
 }
 
 // today's cases -> bitmap (+ compact list): phase one of contact tracing

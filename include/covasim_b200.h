@@ -225,6 +225,9 @@ typedef struct cvb_test_prob_pars {        /* interventions.py:857-981 */
 } cvb_test_prob_pars;
 /* prob_override: NULL, or float64[n] of explicit per-agent probabilities (NaN = none): the `subtarget` option (interventions.py:971-973) */
 int cvb_test_prob(cvb_sim* s, int32_t t, const cvb_test_prob_pars* host_pars, const double* prob_override, cvb_stream st);
+/* Verification: the same with every agent's three uniforms GIVEN (device float64[n][3]: tested today?, test positive?, not lost to follow-up?)
+ * -- the draws a recorded run of the reference consumed (tests/golden/test_tape.npz) */
+int cvb_test_prob_taped(cvb_sim* s, int32_t t, const cvb_test_prob_pars* host_pars, const double* prob_override, const double* tape, cvb_stream st);
 
 typedef struct cvb_test_num_pars {         /* interventions.py:718-854 */
     double symp_test, quar_test;

@@ -207,3 +207,37 @@ def test_infect_kernel_against_reference_tape(cv, name, day):
             bad.append(f'{k}: agent {u[j]} got {got[j]} want {want[j]}')
     assert not bad, f'{name} day {day} (variant {variant}, hosp_max {hosp_max}, icu_max {icu_max}): ' + '; '.join(bad)
     assert int(sim._counters[t, cv.defaults.COUNTER_IDS['new_infections']].item()) == len(infected)
+
+
+@pytest.mark.parametrize('day', [12, 25])
+def test_test_prob_kernel_against_reference_tape(cv, day):
+    '''
+    tests/golden/test_tape.npz (oracle/gen_test_golden.py): a test_prob.apply + People.test call of the unmodified reference -- the People
+    arrays it reads, the three uniform arrays it consumed (per agent) and the arrays it wrote.  The CUDA test_prob kernel, given the same
+    state and the same uniforms (cvb_test_prob_taped), must write the same arrays, and count the same number of tests.
+    '''
+    import ctypes as C
+    import os
+    import torch
+    import scenarios
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'test_tape.npz'))
+    pre = f'hybrid3k/t{day}/'
+    sim = cv.Sim(**scenarios.build(cv, scenarios.SCENARIOS['hybrid3k']))
+    sim.initialize()
+    P, dev = sim.people, sim.people.device
+    for key in g.files:
+        if key.startswith(pre + 'pre/'):
+            k = key.split('/')[-1]
+            P[k] = g[key]
+    tp = [iv for iv in sim['interventions'] if isinstance(iv, cv.test_prob)][0]
+    tape = torch.as_tensor(g[pre + 'tape'], dtype=torch.float64, device=dev).contiguous()
+    sim.t = day
+    sim._push_pars()
+    cv._capi.call('cvb_test_prob_taped', sim._handle, day, C.byref(tp._c), None, tape.data_ptr(), sim._stream_ptr)
+    torch.cuda.synchronize()
+    for key in g.files:
+        if key.startswith(pre + 'post/'):
+            k = key.split('/')[-1]
+            got, want = P.to_numpy(k), g[key]
+            assert np.array_equal(got, want, equal_nan=(want.dtype.kind == 'f')), f'day {day}: {k} differs at {np.nonzero(~((got == want) | ((got != got) & (want != want))))[0][:5]}'
+    assert int(sim._counters[day, cv.defaults.COUNTER_IDS['new_tests']].item()) == int(g[pre + 'n_tests'])

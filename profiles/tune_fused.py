@@ -22,7 +22,7 @@ ap.add_argument('--quick', action='store_true', help='only the default launch sh
 ap.add_argument('--edge', action='store_true', help='sweep the sparse edge pass shapes')
 args = ap.parse_args()
 pars = dict(pop_size=args.pop_size, pop_type='hybrid', n_days=args.n_days, pop_infected=max(1, int(0.005 * args.pop_size)), rand_seed=1, verbose=0)
-sim = cv.Sim(pars, interventions=[cv.test_prob(symp_prob=0.1, asymp_prob=0.01, start_day=20), cv.contact_tracing(trace_probs=0.3, start_day=30)], pop_exact=False)
+sim = cv.Sim(pars, interventions=[cv.test_prob(symp_prob=0.1, asymp_prob=0.01, start_day=20), cv.contact_tracing(trace_probs=0.3, start_day=30)], pop_exact=False, pop_gen='device' if args.pop_size > 2_000_000 else 'host')
 sim.initialize()
 snap = sim.snapshot(pinned=True)
 dev = {k: sim.people[k].clone() for k in sim.people.keys()}

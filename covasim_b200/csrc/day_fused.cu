@@ -423,6 +423,7 @@ struct DayMidArgs {
     uint4* trans_ent; unsigned int* n_trans;
     unsigned int* n_cand; unsigned int* n_case;
     int32_t* trans_list;                            // the plain list, in the same order as the entries
+    const unsigned long long* log_count; unsigned long long* log_base;
     const double* partial; int32_t n_part, t_end;   // day_begin_kernel's per-CTA sums (t_end = t - 1 if it closed a day, else -1)
     double* sums;
 };
@@ -438,7 +439,8 @@ __global__ void __launch_bounds__(kThreads, CVB_MID_MINB) day_mid_kernel(PeopleP
     if (threadIdx.x < kStockSlots) s_delta[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_n_ent = 0;
     pdl_wait();                                                 // everything below reads what the previous kernels wrote
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *A.n_cand = 0; *A.n_case = 0; }   // today's candidates start empty; the case list was consumed
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *A.n_cand = 0; *A.n_case = 0; *A.log_base = *A.log_count; }   // today's candidates start empty; the case list was
+                                                                                                          // consumed; infect_kernel logs at (this length) + j
     if (blockIdx.x == gridDim.x - 1) sum_partials(A.partial, A.n_part, A.sums, A.t_end, A.t);     // day_begin_kernel's float64 sums
     __syncthreads();
     const int64_t n = A.n;
@@ -708,6 +710,7 @@ static int launch_day_mid(cvb_sim* s, int32_t t, bool closes_previous, cudaStrea
     A.counters = s->res.counters; A.vcounters = s->res.vcounters; A.rec = s->rec; A.inf_bits = s->inf_bits;
     A.adj_ptr = (s->adj && s->adj_layer_mask) ? s->adj_ptr : nullptr;
     A.trans_ent = s->trans_ent; A.n_trans = s->n_trans; A.n_cand = s->n_cand; A.n_case = s->n_case_list; A.trans_list = s->trans_list;
+    A.log_count = s->log.count; A.log_base = s->dev_scalars + 40;
     A.partial = s->partial; A.n_part = s->begin_grid; A.t_end = closes_previous ? t - 1 : -1; A.sums = s->res.sums;
     A.chunk = s->tune[3] > 0 && s->tune[3] <= kMidChunk ? s->tune[3] : kMidChunk;
     const int threads = s->tune[2] > 0 ? s->tune[2] : kThreads;

@@ -344,14 +344,17 @@ __global__ void __launch_bounds__(kThreads) edge_pass_sparse_kernel(TransRecords
 // memory round trips per group.  Same probability chain, Philox key and winner key as every other form.
 // The kernel is launched with programmatic dependent launch, so it may be resident while day_mid_kernel is still writing the
 // entries and records: they are read with L2 loads (ld.global.cg), never through the non-coherent path.
+constexpr unsigned int kHitBuf = 512;
 template <bool MULTI, int G, int U>
 __global__ void __launch_bounds__(kThreads) edge_pass_sparse2_kernel(TransRecords rec, const __grid_constant__ EdgeParams ep,
         const uint4* __restrict__ adj, const uint4* __restrict__ ents, const unsigned int* __restrict__ n_trans_ptr,
         unsigned long long* __restrict__ infect_key, int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand,
         unsigned long long* __restrict__ work_row) {
     __shared__ unsigned long long s_visited;
+    __shared__ int32_t s_hit[kHitBuf];                          // this CTA's newly hit targets: ONE global atomic reserves their list slots
+    __shared__ unsigned int s_n_hit, s_hit_base;
     pdl_trigger();
-    if (threadIdx.x == 0) s_visited = 0;
+    if (threadIdx.x == 0) { s_visited = 0; s_n_hit = 0; }
     __syncthreads();
     pdl_wait();                                                 // the entries and records are written by day_mid_kernel
     const unsigned int n_trans = __ldcg(n_trans_ptr);           // (L2 loads: the kernel may have been resident while its inputs were written)
@@ -394,9 +397,15 @@ __global__ void __launch_bounds__(kThreads) edge_pass_sparse2_kernel(TransRecord
                     const int64_t e = (int64_t)en[u].y;
                     const u32x4 r = keyed_words(ep.seed, P_EDGE, (uint32_t)l, ep.t, e, 0);
                     const double uu = dir == 0 ? u53(r.x, r.y) : u53(r.z, r.w);
-                    if (uu < (double)p)
-                        record_hit(infect_key, cand, n_cand, j, ((unsigned long long)vi << 56) | ((unsigned long long)l << 48) |
-                                                                ((unsigned long long)dir << 40) | (unsigned long long)e);
+                    if (uu < (double)p) {
+                        const unsigned long long key = ((unsigned long long)vi << 56) | ((unsigned long long)l << 48) |
+                                                       ((unsigned long long)dir << 40) | (unsigned long long)e;
+                        if (atomicMin(infect_key + j, key) == kEmptyKey) {              // first hit on this target today
+                            const unsigned int k = atomicAdd(&s_n_hit, 1u);
+                            if (k < kHitBuf) s_hit[k] = j;
+                            else cand[atomicAdd(n_cand, 1u)] = j;                       // (buffer full: straight to the global list)
+                        }
+                    }
                 }
             }
         }
@@ -406,6 +415,10 @@ __global__ void __launch_bounds__(kThreads) edge_pass_sparse2_kernel(TransRecord
     for (int d = 16; d > 0; d >>= 1) visited += __shfl_down_sync(0xFFFFFFFFu, visited, d);
     if (lane_id() == 0 && visited) atomicAdd(&s_visited, visited);
     __syncthreads();
+    const unsigned int n_hit = s_n_hit < kHitBuf ? s_n_hit : kHitBuf;
+    if (threadIdx.x == 0 && n_hit) s_hit_base = atomicAdd(n_cand, n_hit);
+    __syncthreads();
+    for (unsigned int q = threadIdx.x; q < n_hit; q += blockDim.x) cand[s_hit_base + q] = s_hit[q];
     if (threadIdx.x == 0 && s_visited) atomicAdd(work_row, s_visited);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(work_row + 1, (unsigned long long)n_trans);
 }

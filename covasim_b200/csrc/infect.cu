@@ -25,12 +25,17 @@ struct InfectArgs {
     int64_t hit_cap;
     const long long* adj_ptr; const uint4* adj; uint32_t adj_mask;   // fused pipeline: the source of a transmission over a layer the
                                              // adjacency covers is looked up in the TARGET's row (the raw edge lists are not read)
+    const unsigned long long* log_base;      // winners mode: the log length before this kernel; candidate j's entry goes to *log_base + j
+                                             // (no atomics; a candidate that is not infected leaves a tombstone, target = -1)
     const double* tape;                      // verification (cvb_infect_list_taped): draws given by the caller, [list position][16 slots]
     const unsigned long long* beds_direct;   // fused pipeline: {n_severe, n_critical} of today's counter row (running totals); NULL: beds[t]
     unsigned long long* vcounters_row;       // today's by-variant counter row (stock differences)
 };
 
-__global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __grid_constant__ cvb_pars pars, const __grid_constant__ LayerTable L,
+#ifndef CVB_INFECT_MINB
+#define CVB_INFECT_MINB 1
+#endif
+__global__ void __launch_bounds__(kThreads, CVB_INFECT_MINB) infect_kernel(PeoplePtrs P, const __grid_constant__ cvb_pars pars, const __grid_constant__ LayerTable L,
         const __grid_constant__ InfectArgs ia, const int32_t* __restrict__ cand, const unsigned int* __restrict__ n_cand_ptr,
         unsigned long long* __restrict__ infect_key, const unsigned long long* __restrict__ beds, ResultPtrs res, LogPtrs log,
         uint32_t* __restrict__ S /* packed state words of the fused day pipeline (day_fused.cu), or NULL */) {
@@ -122,6 +127,8 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
         const double x_crit2rec = __shfl_sync(0xFFFFFFFFu, d0, base + 8), x_crit2die = __shfl_sync(0xFFFFFFFFu, d1, base + 8);
         const double x_nab = __shfl_sync(0xFFFFFFFFu, d0, base + 9);
         if (slot != 0 || !valid) continue;                         // the half-warp's leader applies the infection
+        const unsigned long long dense_pos = ia.log_base ? __ldcg(ia.log_base) + j : 0ull;
+        if (ia.log_base && (int64_t)dense_pos < log.cap) log.target[dense_pos] = -1;       // tombstone unless the infection happens
         unsigned long long key;
         if (ia.hit_key) {                                          // one entry per hit: only the winning one proceeds
             key = ia.hit_key[j];
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
         c[INF_REINFECTIONS] += !is_nan(in_drec);
         // infection log (people.py:508-511)
         {
-            unsigned long long pos = warp_append(log.count);
+            const unsigned long long pos = ia.log_base ? dense_pos : warp_append(log.count);
             if ((int64_t)pos < log.cap) {
                 log.source[pos] = source; log.target[pos] = (int32_t)gi; log.date[pos] = t;
                 log.layer[pos] = (int8_t)layer_code; log.variant[pos] = (int8_t)v;
@@ -271,6 +278,7 @@ __global__ void __launch_bounds__(kThreads) infect_kernel(PeoplePtrs P, const __
         }
     }
 
+    if (ia.log_base && blockIdx.x == 0 && threadIdx.x == 0) *log.count = __ldcg(ia.log_base) + n_cand;     // (only this thread writes it)
     reduce_counters(c, s_cnt);
     reduce_counters(cv, s_cnt + INF_NK);
     __syncthreads();
@@ -318,9 +326,17 @@ static int launch_infect(cvb_sim* s, int32_t t, int32_t count_flows, int32_t lis
     const bool use_adj = with_state && s->adj && s->adj_layer_mask;
     ia.adj_ptr = use_adj ? s->adj_ptr : nullptr; ia.adj = use_adj ? s->adj : nullptr; ia.adj_mask = use_adj ? s->adj_layer_mask : 0u;
     ia.tape = tape;
+    ia.log_base = nullptr;
+    if (!hits) {
+        // the candidates are distinct agents (winners of the edge pass, or a claimed list), so candidate j logs at (length before) + j --
+        // the length is snapshotted by a stream-ordered copy here and by day_mid_kernel in the fused day
+        unsigned long long* snap = s->dev_scalars + 40;
+        if (!with_state) CVB_CHECK(cudaMemcpyAsync(snap, s->log.count, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+        ia.log_base = snap;
+    }
     ia.beds_direct = with_state ? s->res.counters + (int64_t)t * CVB_N_COUNTERS + CVB_C_n_severe : nullptr;      // n_severe, n_critical are adjacent
     ia.vcounters_row = s->res.vcounters + (int64_t)t * s->nv * CVB_N_VCOUNTERS;
-    int grid = grid_for(max_items * 16, kThreads, 148 * (s->tune[6] > 0 ? s->tune[6] : 4));       // sixteen lanes per agent
+    int grid = grid_for(max_items * 16, kThreads, 148 * (s->tune[6] > 0 ? s->tune[6] : 4 * (CVB_INFECT_MINB > 2 ? 2 : 1)));       // sixteen lanes per agent
     {
         const int32_t* cand = s->cand; const unsigned int* nc = s->n_cand; const unsigned long long* beds = s->beds;
         uint32_t* state = with_state ? s->state : nullptr;

@@ -1111,6 +1111,8 @@ class Sim:
                           f'(raise it with Sim(..., log_capacity=...)); compute_r_eff / compute_gen_time over the log are affected', RuntimeWarning)
         n = min(count, cap)
         out = {k: L[k][:n].cpu().numpy() for k in ('source', 'target', 'date', 'layer', 'variant')}
+        kept = out['target'] >= 0                 # (a candidate that was not infected after all leaves a placeholder in its slot)
+        out = {k: v[kept] for k, v in out.items()}
         if self._comm is not None:             # every rank logs the infections of its own agents (global ids)
             parts = self._comm.gather_objects(out)
             out = {k: np.concatenate([p[k] for p in parts]) for k in out}

@@ -474,27 +474,30 @@ def partition_block(args, cv, world, rank, max_over_ranks):
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        while not sim.complete:
-            sim.step()
+        sim._advance(sim.npts)               # fused days in blocks (cvb_fused_phase + the two exchanges), vaccination / variant days per step
         b.record()
         torch.cuda.synchronize()
         ms = max_over_ranks(a.elapsed_time(b))
         if rep > 0:
             best = ms if best is None else min(best, ms)
+        fused_days = sim.fused_days
         sim.finalize()
+    # one more run with CUDA events around every launch and collective: fused days through the library's timers, per-step days through the host's
     sim.restore(snap)
     sim.set_seed()
-    sim.kernel_timers = {}
-    while not sim.complete:
-        sim.step()
+    sim.fused_timing(True)
+    sim.collective_timers = {}
+    sim._advance(sim.npts)
     torch.cuda.synchronize()
-    kernels = {k: round(float(np.sum([x.elapsed_time(y) for x, y in v])) * 1e3 / sim.npts, 1) for k, v in sim.kernel_timers.items()}
-    sim.kernel_timers = None
+    kernels = {'fused/' + k: round(1e3 * ms_ / sim.npts, 1) for k, (ms_, cnt) in sim.fused_timing().items() if cnt}
+    kernels.update({k: round(float(np.sum([x.elapsed_time(y) for x, y in v])) * 1e3 / sim.npts, 1) for k, v in sim.collective_timers.items()})
+    sim.fused_timing(False)
+    sim.collective_timers = None
     sim.finalize()
     if rank == 0:
         out.update(workload='C4 recipe (hybrid, alpha + delta, waning, test_prob + contact_tracing + vaccinate_prob + booster), weak-scaled, device population',
                    pop_size=n, agents_per_gpu=int(args.part_agents), n_days=args.part_days, n_gpus=world, ms_per_run=best, us_per_day=1e3 * best / sim.npts,
-                   agent_days_per_s=n * sim.npts / (best / 1e3), init_s=t_init, kernel_us_per_day=kernels,
+                   agent_days_per_s=n * sim.npts / (best / 1e3), init_s=t_init, fused_days=int(fused_days), kernel_us_per_day=kernels,
                    allgather_us_per_day=round(kernels.get('allgather_codes', 0.0) + kernels.get('allgather_cases', 0.0), 1),
                    exchange_bytes_per_day_per_rank=int(sim._chunk * world + sim._chunk * world // 8), collective='ncclAllGather (torch.distributed all_gather_into_tensor), 1 byte per agent per day + 1 bit per agent on tracing days',
                    hbm_gb_per_gpu=torch.cuda.max_memory_allocated() / 1e9,

@@ -18,7 +18,7 @@ MAX_VACCINES = 8
 N_DURS = 9
 DUR_ORDER = ('exp2inf', 'inf2sym', 'sym2sev', 'sev2crit', 'asym2rec', 'mild2rec', 'sev2rec', 'crit2rec', 'crit2die')
 LAYER_SEED, LAYER_IMPORT = -1, -2
-TIMED_KINDS = ('day_begin', 'trace', 'day_mid', 'edge_pass', 'infect', 'day_end', 'regen')    # enum cvb_timed
+TIMED_KINDS = ('day_begin', 'trace', 'day_mid', 'edge_pass', 'infect', 'day_end', 'regen', 'vaccinate')    # enum cvb_timed
 DIST_KINDS = dict(zero=0, normal=1, normal_pos=2, normal_int=3, lognormal=4, lognormal_int=5)
 
 
@@ -129,8 +129,10 @@ PROTOTYPES = dict(
     cvb_plan_test_prob=[_P, C.POINTER(cvb_test_prob_pars), _i32, _i32],
     cvb_plan_contact_tracing=[_P, C.POINTER(cvb_trace_pars), _i32, _i32],
     cvb_plan_dynamic_layers=[_P, C.c_uint32],
+    cvb_plan_vaccinate=[_P, C.POINTER(cvb_vaccinate_pars), _P, _P, _P],
     cvb_run_days=[_P, _i32, _i32, _P],
     cvb_run_days_multi=[_P, _i32, _i32, _i32, _P],
+    cvb_fused_phase=[_P, _i32, _i32, _i32, _P],
     cvb_state_invalidate=[_P],
     cvb_tune=[_P, _i32, _i32],
     cvb_timing_enable=[_P, _i32],

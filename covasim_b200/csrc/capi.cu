@@ -144,6 +144,7 @@ int cvb_destroy(cvb_sim* s) {
     cudaFree(s->nab_kin); cudaFree(s->tile_cnt); cudaFree(s->hit_mask); cudaFree(s->flag_tmp); cudaFree(s->partial);
     cudaFree(s->glist); cudaFree(s->n_glist); cudaFree(s->hit_src); cudaFree(s->hit_key); cudaFree(s->part_flags);
     cudaFree(s->state); cudaFree(s->trans_ent); cudaFree(s->case_ent); cudaFree(s->stock_base);
+    if (s->plan) { for (int k = 0; k < 4; ++k) free(s->plan->vacc_days[k]); }
     delete s->plan;
     cvb_timing_enable(s, 0);
     if (s->host_scalars) cudaFreeHost(s->host_scalars);

@@ -50,6 +50,11 @@ struct DayPlan {
     int32_t has_trace, trace_start, trace_end;      // contact_tracing
     cvb_trace_pars trace;
     uint32_t regen_mask;                            // dynamic layers regenerated every day (Layer.update, frac = 1)
+    // vaccinate_prob interventions (interventions.py:1257-1662): per day bit 0 = first doses are offered, bit 1 = second doses fall due
+    int32_t n_vacc;
+    cvb_vaccinate_pars vacc[4];
+    uint8_t* vacc_days[4];                          // host copies, [npts]
+    int32_t* vacc_doses[4]; int32_t* vacc_due[4];   // the intervention's device arrays (cvb_vaccinate_prob)
 };
 
 struct FusedTiming;
@@ -125,6 +130,7 @@ struct cvb_sim {
     uint4* trans_ent;                               // [N][2] today's transmitters {agent, row length, row begin, rel_trans, code}
     uint4* case_ent;                                // [N] today's traced cases {agent, row length, row begin}
     unsigned long long* stock_base;                 // absolute stock counts of the packed words after a pack (counter-row layout)
+    int32_t block_packed;                           // the state words were rebuilt at the start of the current block of days
     int32_t begin_grid;                             // grid of the last day_begin_kernel launch (= number of per-CTA partial sums)
     int32_t tune[8];                                // launch-shape overrides (cvb_tune): 0/1 day_begin CTA size / chunk, 2/3 day_mid, 4/5 edge pass lanes / unroll
     cvb::DayPlan* plan;                             // built-in interventions the C day loop runs itself (cvb_plan_*)
@@ -144,6 +150,8 @@ int list_from_bits(cvb_sim* s, const unsigned int* bits, int64_t n_words, cudaSt
 int edge_pass_impl(cvb_sim* s, int32_t t, cudaStream_t st, bool from_entries);       // edge_pass.cu
 int launch_trace_sparse2(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cudaStream_t st);   // interventions.cu
 int launch_infect_winners(cvb_sim* s, int32_t t, bool with_state, cudaStream_t st);   // infect.cu
+int launch_trace_partition(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cudaStream_t st);   // interventions.cu
+int launch_vaccinate_fused(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* vp, int32_t* iv_doses, int32_t* due_day, cudaStream_t st);   // interventions.cu
 // every entry point that writes People flags outside the fused pipeline calls this: the packed state must be rebuilt
 inline void state_touched(cvb_sim* s) { s->state_valid = 0; }
 

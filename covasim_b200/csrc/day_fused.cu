@@ -19,6 +19,7 @@
 //
 // Results are identical to the unfused kernels (people_kernels.cu, interventions.cu): same arithmetic (cvb_device.cuh), same Philox
 // keys, same order of the per-agent steps; tests/test_gpu_fused.py checks both paths against the oracle.
+#include <stdlib.h>
 #include <string.h>
 #include <new>
 #include <vector>
@@ -117,8 +118,9 @@ struct DayBeginArgs {
     // test_prob
     cvb_test_prob_pars tp; int32_t test_plain;                 // test_plain: quarantine state does not change the probability
     uint64_t seed;
-    // contact tracing: cases -> entries
+    // contact tracing: cases -> entries (or, agent-partitioned: -> the local case bitmap that the host all-gathers)
     const long long* adj_ptr; uint4* case_ent;
+    unsigned int* case_bits;
 };
 
 // check_immunity for one queued agent x variant (immunity.py:303-350): float64, rounded once to float32.
@@ -333,8 +335,11 @@ __global__ void __launch_bounds__(kThreads, CVB_BEGIN_MINB) day_begin_kernel(Peo
             if (TSEL && (s & SB_DPEND)) {                                    // a case: date_diagnosed == t
                 const float dg = ddiag_known ? ddiag_new : d_diag[i];
                 if (dg == tf) {
-                    const long long beg = A.adj_ptr[i], end = A.adj_ptr[i + 1];
-                    A.case_ent[warp_append32(A.n_case)] = make_uint4((unsigned)i, (unsigned)(end - beg), (unsigned)(unsigned long long)beg, (unsigned)((unsigned long long)beg >> 32));
+                    if (A.case_bits) atomicOr(A.case_bits + (i >> 5), 1u << (i & 31));
+                    else {
+                        const long long beg = A.adj_ptr[i], end = A.adj_ptr[i + 1];
+                        A.case_ent[warp_append32(A.n_case)] = make_uint4((unsigned)i, (unsigned)(end - beg), (unsigned)(unsigned long long)beg, (unsigned)((unsigned long long)beg >> 32));
+                    }
                 }
             }
         }
@@ -424,6 +429,7 @@ struct DayMidArgs {
     unsigned int* n_cand; unsigned int* n_case;
     int32_t* trans_list;                            // the plain list, in the same order as the entries
     const unsigned long long* log_count; unsigned long long* log_base;
+    uint8_t* codes; const float* base_trans; unsigned int* part_flags;     // agent-partitioned: the 1-byte transmit codes the host all-gathers
     const double* partial; int32_t n_part, t_end;   // day_begin_kernel's per-CTA sums (t_end = t - 1 if it closed a day, else -1)
     double* sums;
 };
@@ -521,6 +527,7 @@ __global__ void __launch_bounds__(kThreads, CVB_MID_MINB) day_mid_kernel(PeopleP
             if (simple) {
                 const uint32_t want = SB_RS_VALID | (sus ? SB_RS_SUS : 0u) | (quar ? SB_RS_QUAR : 0u);
                 if ((s & (SB_RS_VALID | SB_RS_SUS | SB_RS_QUAR)) != want) {
+                    if (A.codes) A.codes[i] = 0;
                     A.rec.rec[i] = make_float4(0.0f, sus ? rs : 0.0f, 0.0f, __uint_as_float(quar ? 32u : 0u));
                     s = (s & ~(SB_RS_VALID | SB_RS_SUS | SB_RS_QUAR)) | want;
                 }
@@ -532,12 +539,21 @@ __global__ void __launch_bounds__(kThreads, CVB_MID_MINB) day_mid_kernel(PeopleP
                 if (inf && rtv != 0.0f) {                                     // can transmit (a zero rel_trans never does)
                     rt = rtv;
                     const bool early = viral_load_early(t, dinf, drec, ddead, pars.frac_time, pars.high_cap);
-                    code = transmit_code(var, symp, iso, quar, early, false);
+                    bool redux = false;
+                    if (A.codes) {                                            // other GPUs rebuild rt from its initial value
+                        const float base = A.base_trans[i];
+                        redux = rt != base;
+                        if (redux && rt != fmul(base, pars.trans_redux)) atomicAdd(A.part_flags + 1, 1u);
+                    }
+                    code = transmit_code(var, symp, iso, quar, early, redux);
                     can_trans = true;
-                    const unsigned int pos = atomicAdd(&s_n_ent, 1u);         // shared memory: this CTA's entries
-                    s_ent[2 * pos] = make_uint4((unsigned)i, (unsigned)(end - beg), (unsigned)(unsigned long long)beg, (unsigned)((unsigned long long)beg >> 32));
-                    s_ent[2 * pos + 1] = make_uint4(__float_as_uint(rt), code, 0u, 0u);
+                    if (!A.codes) {
+                        const unsigned int pos = atomicAdd(&s_n_ent, 1u);     // shared memory: this CTA's entries
+                        s_ent[2 * pos] = make_uint4((unsigned)i, (unsigned)(end - beg), (unsigned)(unsigned long long)beg, (unsigned)((unsigned long long)beg >> 32));
+                        s_ent[2 * pos + 1] = make_uint4(__float_as_uint(rt), code, 0u, 0u);
+                    }
                 }
+                if (A.codes) A.codes[i] = can_trans ? (uint8_t)code : (uint8_t)0;
                 float s_rec = sus ? rs : 0.0f, imm_rec = imm0;
                 if (nv == 1 && !quar) { s_rec = record_sus(s_rec, 0u, 1.0f, imm_rec); imm_rec = 0.0f; }
                 if (A.rec.rec) A.rec.rec[i] = make_float4(rt, s_rec, imm_rec, __uint_as_float(code));
@@ -586,7 +602,7 @@ static int fused_ready(cvb_sim* s, const char* who) {
     for (int f = 0; f < CVB_N_FIELDS; ++f) CVB_REQUIRE(s->people.f[f] != nullptr, "%s: people field %d is not bound", who, f);
     CVB_REQUIRE(s->res.counters && s->res.vcounters && s->res.sums, "%s: result tables are not bound", who);
     CVB_REQUIRE(s->log.count, "%s: infection log is not bound", who);
-    CVB_REQUIRE(!s->partitioned, "%s: agent-partitioned handles are stepped by the host (one exchange per day)", who);
+    CVB_REQUIRE(!s->partitioned || (s->pars.n_beds_hosp < 0 && s->pars.n_beds_icu < 0), "%s: bed limits of an agent-partitioned run need the per-step path (global counts)", who);
     CVB_REQUIRE(s->n % 4 == 0, "%s: the fused pipeline needs a population size that is a multiple of 4", who);
     uintptr_t all = 0;
     for (int f = 0; f < CVB_N_FIELDS; ++f) all |= (uintptr_t)s->people.f[f];
@@ -640,7 +656,7 @@ template <bool END, bool PRE>
 static int launch_day_begin(cvb_sim* s, int32_t t, bool test, bool tsel, bool base_from_pack, cudaStream_t st) {
     DayBeginArgs A;
     memset(&A, 0, sizeof(A));
-    A.n = s->n; A.id0 = 0; A.chunk = kBeginChunk; A.t = t; A.nv = s->nv; A.waning = s->pars.use_waning; A.vaxpars = s->pars.has_vaccine_pars;
+    A.n = s->n; A.id0 = s->partitioned ? s->id0 : 0; A.chunk = kBeginChunk; A.t = t; A.nv = s->nv; A.waning = s->pars.use_waning; A.vaxpars = s->pars.has_vaccine_pars;
     A.nab_kin = s->nab_kin; A.nab_kin_len = s->nab_kin_len;
     A.counters = s->res.counters; A.vcounters = s->res.vcounters;
     if (PRE) {
@@ -661,6 +677,7 @@ static int launch_day_begin(cvb_sim* s, int32_t t, bool test, bool tsel, bool ba
         A.test_plain = (A.tp.symp_quar_prob == A.tp.symp_prob && A.tp.asymp_quar_prob == A.tp.asymp_prob) ? 1 : 0;
     }
     A.adj_ptr = s->adj_ptr; A.case_ent = s->case_ent;
+    A.case_bits = s->partitioned ? s->case_bits_local : nullptr;
 #define CVB_DB(T1, T2) CVB_CHECK(launch_pdl(day_begin_kernel<END, PRE, T1, T2>, grid, threads, 0, st, s->people, s->state, s->pars, A))
     if constexpr (PRE) {
         if (test && tsel) CVB_DB(true, true);
@@ -685,6 +702,7 @@ static int ensure_records_fused(cvb_sim* s, bool& dense_any) {
         if (s->layers[l].n_edges > 0) nonempty |= 1u << l;
         if (s->layers[l].n_edges > 0 && !(s->adj && ((s->adj_layer_mask >> l) & 1u))) dense |= 1u << l;
     }
+    if (s->partitioned) dense = 0;                          // every layer is covered by the partitioned adjacency
     dense_any = dense != 0;
     const uint32_t ts8_layers = s->nv == 1 ? dense : 0u;
     if (ts8_layers && (!s->ts8_store || s->ts8_layers < s->pars.n_layers)) {
@@ -711,6 +729,7 @@ static int launch_day_mid(cvb_sim* s, int32_t t, bool closes_previous, cudaStrea
     A.adj_ptr = (s->adj && s->adj_layer_mask) ? s->adj_ptr : nullptr;
     A.trans_ent = s->trans_ent; A.n_trans = s->n_trans; A.n_cand = s->n_cand; A.n_case = s->n_case_list; A.trans_list = s->trans_list;
     A.log_count = s->log.count; A.log_base = s->dev_scalars + 40;
+    if (s->partitioned) { A.codes = s->codes_local; A.base_trans = s->rel_trans_global + s->id0; A.part_flags = s->part_flags; }
     A.partial = s->partial; A.n_part = s->begin_grid; A.t_end = closes_previous ? t - 1 : -1; A.sums = s->res.sums;
     A.chunk = s->tune[3] > 0 && s->tune[3] <= kMidChunk ? s->tune[3] : kMidChunk;
     const int threads = s->tune[2] > 0 ? s->tune[2] : kThreads;
@@ -775,8 +794,23 @@ int cvb_timing_read(cvb_sim* s, double* host_ms, int64_t* host_launches) {
 
 int cvb_plan_clear(cvb_sim* s) {
     CVB_REQUIRE(s, "cvb_plan_clear: NULL handle");
-    if (!s->plan) { s->plan = new (std::nothrow) DayPlan(); CVB_REQUIRE(s->plan, "cvb_plan_clear: out of host memory"); }
+    if (!s->plan) { s->plan = new (std::nothrow) DayPlan(); CVB_REQUIRE(s->plan, "cvb_plan_clear: out of host memory"); memset(s->plan, 0, sizeof(DayPlan)); }
+    for (int k = 0; k < 4; ++k) free(s->plan->vacc_days[k]);
     memset(s->plan, 0, sizeof(DayPlan));
+    return 0;
+}
+
+int cvb_plan_vaccinate(cvb_sim* s, const cvb_vaccinate_pars* vp, const uint8_t* host_day_flags, int32_t* iv_doses, int32_t* due_day) {
+    CVB_REQUIRE(s && vp && host_day_flags && iv_doses && due_day, "cvb_plan_vaccinate: NULL argument");
+    if (!s->plan && cvb_plan_clear(s)) return 1;
+    CVB_REQUIRE(s->plan->n_vacc < 4, "cvb_plan_vaccinate: the day plan holds at most four vaccination interventions");
+    CVB_REQUIRE(vp->vaccine_index >= 0 && vp->vaccine_index < CVB_MAX_VACCINES, "cvb_plan_vaccinate: vaccine index out of range");
+    const int k = s->plan->n_vacc++;
+    s->plan->vacc[k] = *vp;
+    s->plan->vacc_days[k] = (uint8_t*)malloc((size_t)s->npts);
+    CVB_REQUIRE(s->plan->vacc_days[k], "cvb_plan_vaccinate: out of host memory");
+    memcpy(s->plan->vacc_days[k], host_day_flags, (size_t)s->npts);
+    s->plan->vacc_doses[k] = iv_doses; s->plan->vacc_due[k] = due_day;
     return 0;
 }
 
@@ -826,6 +860,20 @@ int cvb_state_check(cvb_sim* s, int32_t t_done, int64_t* host_out26, cvb_stream 
     return pack_or_check(s, t_done, true, host_out26, (cudaStream_t)st);
 }
 
+// the registered vaccinate_prob interventions that act on day t (list order; after testing and tracing, before update_states_post)
+static int run_vaccinations(cvb_sim* s, int32_t t, cudaStream_t st) {
+    DayPlan& plan = *s->plan;
+    for (int k = 0; k < plan.n_vacc; ++k) {
+        const uint8_t f = plan.vacc_days[k][t];
+        if (!f) continue;
+        cvb_vaccinate_pars vp = plan.vacc[k];
+        vp.first_dose_today = f & 1; vp.second_dose_today = (f >> 1) & 1;
+        TimedScope ts(s, CVB_TIMED_vaccinate, st);
+        if (launch_vaccinate_fused(s, t, &vp, plan.vacc_doses[k], plan.vacc_due[k], st)) return 1;
+    }
+    return 0;
+}
+
 // cvb_run_days in three parts, so that several handles can be advanced in lockstep from one host thread (cvb_run_days_multi)
 static int run_days_begin(cvb_sim* s, int32_t t0, int32_t t1, cudaStream_t st, bool& packed) {
     if (fused_ready(s, "cvb_run_days")) return 1;
@@ -833,7 +881,7 @@ static int run_days_begin(cvb_sim* s, int32_t t0, int32_t t1, cudaStream_t st, b
     if (!s->plan && cvb_plan_clear(s)) return 1;
     const DayPlan& plan = *s->plan;
     if (ensure_fused_buffers(s)) return 1;
-    if (plan.has_trace) {
+    if (plan.has_trace && !s->partitioned) {
         CVB_REQUIRE(s->adj && s->adj_layer_mask, "cvb_run_days: contact tracing in the fused day needs the adjacency (cvb_bind_adjacency)");
         for (int l = 0; l < s->pars.n_layers; ++l)
             CVB_REQUIRE(!(plan.trace.trace_prob[l] > 0.0) || s->layers[l].n_edges == 0 || ((s->adj_layer_mask >> l) & 1u),
@@ -866,6 +914,7 @@ static int run_one_day(cvb_sim* s, int32_t t, int32_t t0, bool packed, cudaStrea
         if (rc) return rc;
     }
     if (trace) { TimedScope ts(s, CVB_TIMED_trace, st); if (launch_trace_sparse2(s, t, &plan.trace, st)) return 1; }
+    if (run_vaccinations(s, t, st)) return 1;
     { TimedScope ts(s, CVB_TIMED_day_mid, st); if (launch_day_mid(s, t, t > t0, st)) return 1; }
     { TimedScope ts(s, CVB_TIMED_edge_pass, st); if (edge_pass_impl(s, t, st, true)) return 1; }
     { TimedScope ts(s, CVB_TIMED_infect, st); if (launch_infect_winners(s, t, true, st)) return 1; }
@@ -881,8 +930,49 @@ static int run_days_end(cvb_sim* s, int32_t t1, cudaStream_t st) {
     return 0;
 }
 
+// One day of an AGENT-PARTITIONED simulation through the fused kernels, in the phases between which the host exchanges data
+// (partition.py): 0 = day_begin (first_of_block: the state words are rebuilt if needed; the local case bitmap is cleared first),
+// -> all-gather of the case bitmap on tracing days -> 1 = notify the local contacts of every global case -> 2 = day_mid (writes the
+// 1-byte transmit codes) -> all-gather of the codes -> 3 = edge pass + infect; 4 = close day t - 1 at the end of a block.
+int cvb_fused_phase(cvb_sim* s, int32_t t, int32_t phase, int32_t first_of_block, cvb_stream st_) {
+    cudaStream_t st = (cudaStream_t)st_;
+    CVB_REQUIRE(s && s->partitioned, "cvb_fused_phase: for agent-partitioned handles (use cvb_run_days)");
+    CVB_REQUIRE(phase >= 0 && phase <= 4, "cvb_fused_phase: phase %d out of range", phase);
+    if (phase == 4) return run_days_end(s, t, st);
+    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_fused_phase: day %d outside [0,%d)", t, s->npts);
+    const DayPlan& plan = *s->plan;
+    const bool test = plan.has_test && t >= plan.test_start && (plan.test_end < 0 || t <= plan.test_end);
+    const bool trace = plan.has_trace && t >= plan.trace_start && (plan.trace_end < 0 || t <= plan.trace_end);
+    switch (phase) {
+        case 0: {
+            bool packed = false;
+            if (first_of_block) {
+                if (run_days_begin(s, t, t + 1, st, packed)) return 1;
+                s->block_packed = packed;
+            }
+            s->last_t = t;
+            if (trace) CVB_CHECK(cudaMemsetAsync(s->case_bits_local, 0, (size_t)(s->chunk / 32) * sizeof(unsigned int), st));
+            TimedScope ts(s, CVB_TIMED_day_begin, st);
+            return first_of_block ? launch_day_begin<false, true>(s, t, test, trace, s->block_packed != 0, st)
+                                  : launch_day_begin<true, true>(s, t, test, trace, false, st);
+        }
+        case 1: { TimedScope ts(s, CVB_TIMED_trace, st); return trace ? launch_trace_partition(s, t, &plan.trace, st) : 0; }
+        case 2: {
+            if (run_vaccinations(s, t, st)) return 1;
+            TimedScope ts(s, CVB_TIMED_day_mid, st);
+            return launch_day_mid(s, t, !first_of_block, st);
+        }
+        default: {
+            { TimedScope ts(s, CVB_TIMED_edge_pass, st); if (edge_pass_impl(s, t, st, true)) return 1; }
+            TimedScope ts(s, CVB_TIMED_infect, st);
+            return launch_infect_winners(s, t, true, st);
+        }
+    }
+}
+
 int cvb_run_days(cvb_sim* s, int32_t t0, int32_t t1, cvb_stream st_) {
     cudaStream_t st = (cudaStream_t)st_;
+    CVB_REQUIRE(s && !s->partitioned, "cvb_run_days: agent-partitioned handles advance phase by phase (cvb_fused_phase)");
     bool packed = false;
     if (run_days_begin(s, t0, t1, st, packed)) return 1;
     for (int32_t t = t0; t < t1; ++t)

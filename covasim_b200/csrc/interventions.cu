@@ -200,10 +200,22 @@ __device__ __forceinline__ void trace_notify(const PeoplePtrs& P, const TraceTab
     atomicMax(T.quar_slot[q] + c, __float_as_int(T.end_day));          // people.py:620-640 schedule_quarantine
 }
 
+// Fused day pipeline: the cases come as entries {agent, row length, row begin} written by day_begin_kernel, the contact's "dead" flag
+// is read from the packed state word, and the word's known_contact / pending-request bits are set with the People arrays
+__device__ __forceinline__ void trace_notify2(const PeoplePtrs& P, uint32_t* __restrict__ S, const TraceTable& T, int q, int c) {
+    const uint32_t sub = ((uint32_t)T.index << 8) | (uint32_t)T.layer_id[q];
+    if (!(keyed_uniform(T.seed, P_TRACE, sub, T.t, (int64_t)c + T.id0, 0) < T.trace_prob[q])) return;     // binomial_filter, interventions.py:1116
+    if (S[c] & (1u << 11)) return;                                     // dead (interventions.py:1139-1141)
+    PB(P, known_contact)[c] = 1;
+    atomicOr(S + c, (1u << 12) | (1u << 18));                          // known_contact, request pending
+    atomicMin((unsigned int*)PF(P, date_known_contact) + c, (unsigned int)__float_as_int(T.notify_day[q]));
+    atomicMax(T.quar_slot[q] + c, __float_as_int(T.end_day));          // people.py:620-640 schedule_quarantine
+}
+
 // Adjacency form: one warp per case walks the case's own edges (static layers, both directions)
 __global__ void __launch_bounds__(kThreads) trace_sparse_kernel(PeoplePtrs P, const __grid_constant__ TraceTable T,
         const long long* __restrict__ adj_ptr, const uint4* __restrict__ adj, const int32_t* __restrict__ case_list,
-        const unsigned int* __restrict__ n_case_ptr, uint32_t layer_mask) {
+        const unsigned int* __restrict__ n_case_ptr, uint32_t layer_mask, uint32_t* __restrict__ S = nullptr /* fused day: packed state words */) {
     const unsigned int n_cases = *n_case_ptr;
     const int lane = lane_id();
     const unsigned int warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -216,21 +228,10 @@ __global__ void __launch_bounds__(kThreads) trace_sparse_kernel(PeoplePtrs P, co
             if (!((layer_mask >> l) & 1u)) continue;
             const int q = T.entry_of_layer[l];
             if (q < 0) continue;                                       // layer not traced
-            trace_notify(P, T, q, (int)en.x);
+            if (S) trace_notify2(P, S, T, q, (int)en.x);
+            else trace_notify(P, T, q, (int)en.x);
         }
     }
-}
-
-// Fused day pipeline: the cases come as entries {agent, row length, row begin} written by day_begin_kernel, the contact's "dead" flag
-// is read from the packed state word, and the word's known_contact / pending-request bits are set with the People arrays
-__device__ __forceinline__ void trace_notify2(const PeoplePtrs& P, uint32_t* __restrict__ S, const TraceTable& T, int q, int c) {
-    const uint32_t sub = ((uint32_t)T.index << 8) | (uint32_t)T.layer_id[q];
-    if (!(keyed_uniform(T.seed, P_TRACE, sub, T.t, (int64_t)c + T.id0, 0) < T.trace_prob[q])) return;     // binomial_filter, interventions.py:1116
-    if (S[c] & (1u << 11)) return;                                     // dead (interventions.py:1139-1141)
-    PB(P, known_contact)[c] = 1;
-    atomicOr(S + c, (1u << 12) | (1u << 18));                          // known_contact, request pending
-    atomicMin((unsigned int*)PF(P, date_known_contact) + c, (unsigned int)__float_as_int(T.notify_day[q]));
-    atomicMax(T.quar_slot[q] + c, __float_as_int(T.end_day));          // people.py:620-640 schedule_quarantine
 }
 
 __global__ void __launch_bounds__(kThreads) trace_sparse2_kernel(PeoplePtrs P, uint32_t* __restrict__ S, const __grid_constant__ TraceTable T,
@@ -303,9 +304,12 @@ __global__ void __launch_bounds__(THREADS) trace_edges_kernel(PeoplePtrs P, cons
 // ================================================================================================
 __global__ void __launch_bounds__(kThreads) vaccinate_kernel(PeoplePtrs P, const __grid_constant__ cvb_vaccinate_pars vp, uint64_t seed,
         int64_t n, int64_t id0, int32_t t, int32_t* __restrict__ iv_doses, int32_t* __restrict__ due_day, unsigned long long* __restrict__ counters,
-        const double* __restrict__ prob_override) {
+        const double* __restrict__ prob_override, uint32_t* __restrict__ S /* fused day: packed state words, or NULL */,
+        unsigned long long* __restrict__ vcounters_row, int32_t nv) {
     __shared__ int s_cnt[2];
+    __shared__ int s_delta[kStockSlots];
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < kStockSlots) s_delta[threadIdx.x] = 0;
     __syncthreads();
     int c_doses = 0, c_new = 0;
     uint8_t* vaccinated = PB(P, vaccinated); const uint8_t* dead = PB(P, dead);
@@ -345,6 +349,10 @@ __global__ void __launch_bounds__(kThreads) vaccinate_kernel(PeoplePtrs P, const
             PF(P, peak_nab)[i] = (float)pow(2.0, x);
         }
         PI(P, t_nab_event)[i] = t;
+        if (S) {                                                       // vaccinated, with antibodies from now on
+            const uint32_t so = S[i], sn = so | SB_VACC | SB_HAS_NAB;
+            if (sn != so) { S[i] = sn; stock_delta(so, sn, s_delta); }
+        }
     }
     int w0 = __reduce_add_sync(0xFFFFFFFFu, c_doses), w1 = __reduce_add_sync(0xFFFFFFFFu, c_new);
     if (lane_id() == 0) { if (w0) atomicAdd(&s_cnt[0], w0); if (w1) atomicAdd(&s_cnt[1], w1); }
@@ -354,6 +362,7 @@ __global__ void __launch_bounds__(kThreads) vaccinate_kernel(PeoplePtrs P, const
         if (s_cnt[0]) atomicAdd(row + CVB_C_new_doses, (unsigned long long)s_cnt[0]);
         if (s_cnt[1]) atomicAdd(row + CVB_C_new_vaccinated, (unsigned long long)s_cnt[1]);
     }
+    if (S) flush_stock_delta(s_delta, counters + (int64_t)t * CVB_N_COUNTERS, vcounters_row, nv);
 }
 
 // ================================================================================================
@@ -465,6 +474,29 @@ static int build_trace_table(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, ui
 }
 
 }  // extern "C"
+
+// fused day: one registered vaccinate_prob intervention on a day it acts (first doses and / or second doses due), state words kept in step
+int cvb::launch_vaccinate_fused(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* vp, int32_t* iv_doses, int32_t* due_day, cudaStream_t st) {
+    vaccinate_kernel<<<grid_for(s->n), kThreads, 0, st>>>(s->people, *vp, s->seed, s->n, s->partitioned ? s->id0 : 0, t, iv_doses, due_day, s->res.counters, nullptr,
+                                                          s->state, s->res.vcounters + (int64_t)t * s->nv * CVB_N_VCOUNTERS, s->nv);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
+
+// agent-partitioned fused day: the LOCAL contacts of every GLOBAL case (the all-gathered bitmap), with the state words kept in step
+int cvb::launch_trace_partition(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cudaStream_t st) {
+    CVB_REQUIRE(s->padj_ptr && s->case_bits_global, "fused day: partitioned adjacency / case bitmap not bound");
+    TraceTable T;
+    int64_t acc;
+    bool any_sparse;
+    if (build_trace_table(s, t, tr, s->padj_layer_mask, kTileEdges, T, acc, any_sparse)) return 1;
+    CVB_REQUIRE(acc == 0, "fused day: a traced layer is not covered by the partitioned adjacency");
+    if (!any_sparse) return 0;
+    if (cvb::list_from_bits(s, s->case_bits_global, s->n_slots / 32, st)) return 1;
+    trace_sparse_kernel<<<148 * 2, kThreads, 0, st>>>(s->people, T, s->padj_ptr, s->padj, s->glist, s->n_glist, s->padj_layer_mask, s->state);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
 
 int cvb::launch_trace_sparse2(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cudaStream_t st) {
     TraceTable T;
@@ -592,7 +624,8 @@ int cvb_vaccinate_prob(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* vp, int3
     CVB_REQUIRE(s && vp && iv_doses && due_day && s->res.counters, "cvb_vaccinate_prob: bad argument");
     CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_vaccinate_prob: day %d outside [0,%d)", t, s->npts);
     CVB_REQUIRE(vp->vaccine_index >= 0 && vp->vaccine_index < CVB_MAX_VACCINES, "cvb_vaccinate_prob: vaccine index out of range");
-    vaccinate_kernel<<<grid_for(s->n), kThreads, 0, (cudaStream_t)st>>>(s->people, *vp, s->seed, s->n, s->partitioned ? s->id0 : 0, t, iv_doses, due_day, s->res.counters, prob_override);
+    vaccinate_kernel<<<grid_for(s->n), kThreads, 0, (cudaStream_t)st>>>(s->people, *vp, s->seed, s->n, s->partitioned ? s->id0 : 0, t, iv_doses, due_day, s->res.counters, prob_override,
+                                                                      nullptr, nullptr, s->nv);
     CVB_LAUNCH_CHECK();
     return 0;
 }

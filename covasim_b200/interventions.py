@@ -590,18 +590,24 @@ class vaccinate_prob(Intervention):
         if callable(self.days):
             return None
         days = {int(d) for d in np.atleast_1d(self.days)}
-        if self.p['interval'] is not None:
-            days |= {d + int(self.p['interval']) for d in list(days)}
-        return ('host', sorted(days))
+        due = {d + int(self.p['interval']) for d in days if d + int(self.p['interval']) < sim['n_days']} if self.p['interval'] is not None else set()
+        if self.subtarget is not None:                     # per-agent probabilities are built on the host on first-dose days
+            return ('host', sorted(days | due))
+        flags = np.zeros(sim.npts, dtype=np.uint8)         # bit 0: first doses offered, bit 1: second doses fall due (interventions.py:1631-1660)
+        for d in days:
+            if 0 <= d < sim.npts:
+                flags[d] |= 1
+        for d in due:
+            if 0 <= d < sim.npts:
+                flags[d] |= 2
+        return ('vacc', self._c, flags, self.doses, self.due_day)
 
     def apply(self, sim):
         t = sim.t
         if t < np.min(self.days):
             return
         first = bool(np.any(self.days == t))
-        if first and self.p['interval'] is not None and t + self.p['interval'] < sim['n_days']:
-            self._due_days.add(t + int(self.p['interval']))
-        second = t in self._due_days
+        second = self.p['interval'] is not None and t < sim['n_days'] and bool(np.any(self.days + int(self.p['interval']) == t))   # interventions.py:1655-1660
         if not (first or second):
             return
         self._c.first_dose_today = int(first)

@@ -351,10 +351,18 @@ class Sim:
         '''
         self._plan = None
         self.fused_days = 0
+        self._make_plan()
+        if self._comm is not None:                       # every rank of a partitioned run must take the same path on the same day
+            if not all(self._comm.gather_objects(self._plan is not None)):
+                self._plan = None
+
+    def _make_plan(self):
         pars = self.pars
-        if not self.fused or self.rng_mode != 'philox' or self._comm is not None or self.n % 4 != 0 or self._handle is None:
+        if not self.fused or self.rng_mode != 'philox' or self.n_local % 4 != 0 or self._handle is None:
             return
-        host_days, test, trace = set(), None, None
+        if self._comm is not None and (pars['n_beds_hosp'] is not None or pars['n_beds_icu'] is not None):
+            return                                       # bed limits compare global counts: the per-step path sums them over the ranks
+        host_days, test, trace, vaccs = set(), None, None, []
         for iv in pars['interventions']:
             plan = iv._device_plan(self) if hasattr(iv, '_device_plan') else None
             if plan is None:
@@ -369,6 +377,10 @@ class Sim:
                 if trace is not None:
                     return
                 trace = plan
+            elif plan[0] == 'vacc':
+                if len(vaccs) == 4:
+                    return
+                vaccs.append(plan)
         for v in pars['variants']:
             host_days.update(int(d) for d in np.atleast_1d(v.days))
         lkeys = self.people.layer_keys()
@@ -379,7 +391,7 @@ class Sim:
                 if type(self.people.contacts[lk]).update is not Layer.update:
                     return                               # a user-defined Layer.update runs on the host
                 regen |= 1 << i
-        if trace is not None:
+        if trace is not None and self._comm is None:
             traced = [i for i, lk in enumerate(lkeys) if trace[1].trace_prob[i] > 0 and len(self.people.contacts[lk]) > 0]
             if any(pars['dynam_layer'].get(lkeys[i]) for i in traced) or (traced and not self.use_adjacency):
                 return                                   # tracing over a streamed layer keeps the per-step path
@@ -389,10 +401,13 @@ class Sim:
             _capi.call('cvb_plan_test_prob', h, C.byref(test[1]), test[2], test[3])
         if trace is not None:
             _capi.call('cvb_plan_contact_tracing', h, C.byref(trace[1]), trace[2], trace[3])
+        for plan in vaccs:
+            _capi.call('cvb_plan_vaccinate', h, C.byref(plan[1]), plan[2].ctypes.data, plan[3].data_ptr(), plan[4].data_ptr())
         _capi.call('cvb_plan_dynamic_layers', h, regen)
         # the fused kernels of static layers read only the adjacency: the raw edge arrays matter when a layer is streamed densely
-        dense = regen != 0 or self._adj is None or any(len(self.people.contacts[lk]) > 0 and not ((self._adj_mask >> i) & 1) for i, lk in enumerate(lkeys))
-        self._plan = dict(host_days=host_days, needs_edges=bool(dense))
+        dense = self._comm is None and (regen != 0 or self._adj is None or any(len(self.people.contacts[lk]) > 0 and not ((self._adj_mask >> i) & 1) for i, lk in enumerate(lkeys)))
+        trace_days = None if trace is None else (trace[2], trace[3])
+        self._plan = dict(host_days=host_days, needs_edges=bool(dense), trace_days=trace_days)
 
     def _build_plan_keep_days(self):
         ''' The adjacency changed (a layer was edited): recompute what depends on it '''
@@ -419,12 +434,33 @@ class Sim:
             self._build_plan_keep_days()
         if self._plan['needs_edges']:
             self._sync_edges()
-        _capi.call('cvb_run_days', self._handle, int(t0), int(t1), self._stream_ptr)
+        if self._comm is not None:
+            self._run_block_partitioned(int(t0), int(t1))
+        else:
+            _capi.call('cvb_run_days', self._handle, int(t0), int(t1), self._stream_ptr)
         self.fused_days += t1 - t0
         self.people.t = t1 - 1
         self.t = t1
         if self.t == self.npts:
             self.complete = True
+
+    def _run_block_partitioned(self, t0, t1):
+        '''
+        Days [t0, t1) of an agent-partitioned simulation through the fused kernels: the same five launches per day, with the two
+        exchanges of the partition (partition.py) between them -- the case bitmap on tracing days, the 1-byte transmit codes every day.
+        '''
+        h, st = self._handle, self._stream_ptr
+        td = self._plan['trace_days']
+        for t in range(t0, t1):
+            first = int(t == t0)
+            _capi.call('cvb_fused_phase', h, t, 0, first, st)
+            if td is not None and t >= td[0] and (td[1] < 0 or t <= td[1]):
+                self._exchange_cases()
+                _capi.call('cvb_fused_phase', h, t, 1, first, st)
+            _capi.call('cvb_fused_phase', h, t, 2, first, st)
+            self._exchange_codes()
+            _capi.call('cvb_fused_phase', h, t, 3, first, st)
+        _capi.call('cvb_fused_phase', h, t1, 4, 0, st)
 
     def check_packed_state(self):
         ''' Verification hook: the library's packed per-agent state word against the People arrays; returns (inexpressible, mismatches, examples) '''
@@ -587,13 +623,14 @@ class Sim:
         self._timed_collective('allgather_cases', B['case_global'], B['case_local'])
 
     def _timed_collective(self, name, out, inp):
-        if self.kernel_timers is None:
+        timers = self.kernel_timers if self.kernel_timers is not None else getattr(self, 'collective_timers', None)
+        if timers is None:
             return self._comm.all_gather(out, inp)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         self._comm.all_gather(out, inp)
         b.record()
-        self.kernel_timers.setdefault(name, []).append((a, b))
+        timers.setdefault(name, []).append((a, b))
 
     def _choose_true(self, key, stream, k):
         '''

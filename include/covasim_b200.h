@@ -290,12 +290,20 @@ int cvb_plan_test_prob(cvb_sim* s, const cvb_test_prob_pars* host_pars, int32_t 
 /* interventions.py:984-1145 contact_tracing on days [start_day, end_day]; applied after the plan's test_prob; every traced
  * layer must be covered by the adjacency; not presumptive, no capacity */
 int cvb_plan_contact_tracing(cvb_sim* s, const cvb_trace_pars* host_pars, int32_t start_day, int32_t end_day);
+/* interventions.py:1257-1662 vaccinate_prob without per-agent overrides: host_day_flags uint8[npts], bit 0 = first doses are offered that day, bit 1 =
+ * second doses fall due; iv_doses / due_day as for cvb_vaccinate_prob.  Up to four; applied in registration order after testing and tracing */
+int cvb_plan_vaccinate(cvb_sim* s, const cvb_vaccinate_pars* host_pars, const uint8_t* host_day_flags, int32_t* iv_doses, int32_t* due_day);
 /* people.py:199-206 update_contacts: the dynamic layers (bit l = layer l) regenerated at the start of every day */
 int cvb_plan_dynamic_layers(cvb_sim* s, uint32_t layer_mask);
 int cvb_run_days(cvb_sim* s, int32_t t0, int32_t t1, cvb_stream st);
 /* The same for several handles in lockstep (ensembles of small simulations, run.py:1406-1519 multi_run): day by day, every member's
  * launches go to its own stream from ONE host thread, so the members' kernels overlap on the GPU.  host arrays of n_handles entries */
 int cvb_run_days_multi(cvb_sim** handles, int32_t n_handles, int32_t t0, int32_t t1, cvb_stream* streams);
+/* The fused day of an AGENT-PARTITIONED handle, phase by phase (the host exchanges data in between): 0 day_begin -> [all-gather of the case
+ * bitmap on tracing days] -> 1 notify the local contacts of every global case -> 2 day_mid (writes the 1-byte transmit codes) -> [all-gather of
+ * the codes] -> 3 edge pass + infect; 4 closes day t - 1 at the end of a block of days.  first_of_block: this is the first fused day since anything
+ * else ran (the state words are rebuilt if needed) */
+int cvb_fused_phase(cvb_sim* s, int32_t t, int32_t phase, int32_t first_of_block, cvb_stream st);
 int cvb_state_invalidate(cvb_sim* s);
 /* Launch-shape overrides of the fused day kernels, for tuning runs (0 = default): what 0 / 1 = CTA size / agents per CTA of the
  * first per-agent kernel, 2 / 3 = the same for the second */
@@ -303,7 +311,7 @@ int cvb_tune(cvb_sim* s, int32_t what, int32_t value);
 /* Per-kernel timing of cvb_run_days (CUDA events around every launch; off by default).  cvb_timing_read synchronises, returns
  * the milliseconds and launch counts accumulated since the last read, per kernel kind, and resets them */
 enum cvb_timed { CVB_TIMED_day_begin = 0, CVB_TIMED_trace, CVB_TIMED_day_mid, CVB_TIMED_edge_pass, CVB_TIMED_infect, CVB_TIMED_day_end,
-                 CVB_TIMED_regen, CVB_N_TIMED };
+                 CVB_TIMED_regen, CVB_TIMED_vaccinate, CVB_N_TIMED };
 int cvb_timing_enable(cvb_sim* s, int32_t on);
 int cvb_timing_read(cvb_sim* s, double* host_ms, int64_t* host_launches);
 /* Verification: recompute every agent's state word from the People arrays (t_done = last completed day) and compare with the

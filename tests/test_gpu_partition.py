@@ -32,10 +32,10 @@ PART_SCENARIOS = {
 }
 
 
-def run_partitioned(cv, spec, world):
+def run_partitioned(cv, spec, world, fused=True):
     from covasim_b200 import partition as cvpart
     comms = cvpart.LocalComm.make(world)
-    sims = [cv.Sim(**scenarios.build(cv, spec), partition=comms[r]) for r in range(world)]
+    sims = [cv.Sim(**scenarios.build(cv, spec), partition=comms[r], fused=fused) for r in range(world)]
     cvpart.run_local(sims, lambda s: s.initialize())
     cvpart.run_local(sims, lambda s: s.run())
     logs = cvpart.run_local(sims, lambda s: s.infection_log)
@@ -45,12 +45,19 @@ def run_partitioned(cv, spec, world):
 # world 1: every row is whole (~36 entries per agent), which selects the 32-lanes-per-transmitter form of edge_pass_partition_kernel;
 # 2-4 ranks select the 16- and 8-lane forms
 @pytest.mark.parametrize('name,world', [('hybrid3k', 1), ('variants4k', 1), ('hybrid3k', 2), ('hybrid3k', 3), ('variants4k', 2), ('variants4k_beds', 3), ('random2k_nowaning', 4), ('odd5003', 3)])
-def test_partitioned_equals_single(name, world):
+@pytest.mark.parametrize('fused', [True, False])
+def test_partitioned_equals_single(name, world, fused):
+    ''' fused=True: the days without a host decision go through the fused kernels phase by phase (cvb_fused_phase) with the exchanges in between '''
     import covasim_b200 as cv
     spec = PART_SCENARIOS[name]
     ref = cv.Sim(**scenarios.build(cv, spec))
     ref.run()
-    sims, logs = run_partitioned(cv, spec, world)
+    sims, logs = run_partitioned(cv, spec, world, fused)
+    if fused and not spec['pars'].get('n_imports'):                      # (daily importations are drawn on the host: those runs keep the per-step path)
+        # (5003 agents over 3 ranks: the last rank's share is not a multiple of 4, so ALL ranks keep the per-step path)
+        assert all(s.fused_days > 0.5 * s.npts for s in sims) or (name == 'odd5003' and all(s.fused_days == 0 for s in sims)), [s.fused_days for s in sims]
+    if not fused:
+        assert all(s.fused_days == 0 for s in sims)
     # ranges tile the population
     assert [s.id0 for s in sims] == list(np.cumsum([0] + [s.n_local for s in sims[:-1]]))
     assert sum(s.n_local for s in sims) == ref.n

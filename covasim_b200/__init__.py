@@ -18,7 +18,7 @@ from .base import Result, Layer, Contacts, AlreadyRunError  # noqa: F401
 from .devarray import DeviceArray  # noqa: F401
 from .people import People  # noqa: F401
 from .immunity import variant, calc_VE, calc_VE_symp, precompute_waning  # noqa: F401
-from .interventions import Intervention, dynamic_pars, sequence, change_beta, clip_edges, test_num, test_prob, contact_tracing, vaccinate_prob  # noqa: F401
+from .interventions import Intervention, dynamic_pars, sequence, change_beta, clip_edges, test_num, test_prob, contact_tracing, vaccinate_prob, vaccinate_num, vaccinate  # noqa: F401
 from .sim import Sim  # noqa: F401
 from .run import MultiSim, multi_run  # noqa: F401
 from .analysis import Analyzer, snapshot, age_histogram, compute_gof, Fit, fit_members, TransTree  # noqa: F401

@@ -574,7 +574,7 @@ class vaccinate_prob(Intervention):
         sim['vaccine_pars'][self.label] = self.p
         self.index = list(sim['vaccine_pars'].keys()).index(self.label)
         sim['vaccine_map'][self.index] = self.label
-        self.days = process_days(sim, self.days)
+        self.days = self._process_own_days(sim)
         self.iindex = sim.intervention_index(self)
         dev = sim.people.device
         self.doses = torch.zeros(sim.n_local, dtype=torch.int32, device=dev)              # doses given by *this* intervention
@@ -585,6 +585,9 @@ class vaccinate_prob(Intervention):
                                            booster=int(bool(self.booster)), vaccine_index=self.index, max_doses=int(doses), index=self.iindex,
                                            interval=-1 if interval is None else int(interval), n_days=int(sim['n_days']))
         sim._pars_dirty = True
+
+    def _process_own_days(self, sim):
+        return process_days(sim, self.days)
 
     def _device_plan(self, sim):
         if callable(self.days):
@@ -615,3 +618,124 @@ class vaccinate_prob(Intervention):
         override = subtarget_override(self.subtarget, sim) if (first and self.subtarget is not None) else None
         sim._call('cvb_vaccinate_prob', sim._handle, t, C.byref(self._c), self.doses.data_ptr(), self.due_day.data_ptr(),
                   None if override is None else override.data_ptr(), sim._stream_ptr)
+
+
+_P_VACC = 7          # enum purpose (csrc/cvb_device.cuh): the vaccination draws
+
+
+class vaccinate_num(vaccinate_prob):
+    '''
+    A number of doses per day, handed out along a priority sequence with second doses first (reference
+    interventions.py:1665-1791).  The day's selection is set algebra over device arrays (who is due, who is eligible, the
+    first ``num_agents`` of the sequence) and ends in the same dose kernel as vaccinate_prob (cvb_vaccinate_prob with the
+    chosen agents as explicit probabilities 1).  Native-RNG mode draws keyed uniforms: slot 0 of P_VACC against the
+    subtarget weight, slot 1 to pick who keeps a scheduled second dose when doses run short.  Scheduled second doses are one
+    day per agent (``due_day``) instead of the reference's day-keyed sets; people the reference would drop from a set
+    (dead, fully dosed) are dropped when their day comes.  Replay mode (rng='mt') is not built: the reference's draw order
+    there depends on the iteration order of Python sets.
+    '''
+
+    def __init__(self, vaccine, num_doses, booster=False, subtarget=None, sequence=None, **kwargs):
+        super().__init__(vaccine, days=0, subtarget=subtarget, booster=booster, prob=1.0, **kwargs)
+        self.num_doses, self.sequence = num_doses, sequence
+
+    def _process_own_days(self, sim):
+        return np.array([0])
+
+    def initialize(self, sim):
+        if sim._comm is not None:
+            raise NotImplementedError('vaccinate_num takes the first num_doses people of a population-wide sequence and is not built for agent-partitioned runs; use vaccinate_prob')
+        super().initialize(sim)
+        if isinstance(self.num_doses, dict):
+            self.num_doses = {sim.day(k): v for k, v in self.num_doses.items()}
+        seq = self.sequence                                      # interventions.py:1539-1552 process_sequence
+        dev = sim.people.device
+        if callable(seq):
+            seq = seq(sim.people)
+        elif isinstance(seq, str) and seq == 'age':              # oldest first; equal ages in index order (native RNG) / as NumPy's default sort leaves them (replay)
+            age = np.asarray(sim.people.age)
+            seq = np.argsort(-age, kind='stable') if sim.rng_mode == 'philox' else np.argsort(-age)
+        elif seq is None:
+            seq = sim.rng.np_.permutation(sim.n)
+        elif isinstance(seq, str):
+            raise TypeError(f'Unable to interpret sequence {seq!r}: must be None, "age", callable, or an array')
+        self._sequence_host = np.asarray(seq.cpu() if isinstance(seq, torch.Tensor) else seq).astype(np.int64)
+        self.sequence = torch.as_tensor(self._sequence_host).to(device=dev)
+        self._scheduled = {}                                     # replay mode: day -> set of agents due (the reference's ddict(set))
+        self._u = torch.empty(sim.n, dtype=torch.float64, device=dev)
+        self._prob = torch.empty(sim.n, dtype=torch.float64, device=dev)
+
+    def _device_plan(self, sim):
+        if isinstance(self.num_doses, dict) and self.num_doses:
+            return ('host', range(min(self.num_doses), sim.npts))           # (second doses may be deferred from day to day)
+        return None
+
+    def n_today(self, sim):
+        nd = self.num_doses                                      # interventions.py:1526-1536 process_doses
+        if callable(nd):
+            return nd(sim)
+        if isinstance(nd, dict):
+            return nd.get(sim.t, 0)
+        return nd
+
+    def _uniforms(self, sim, slot):
+        sim._call('cvb_keyed_uniform', int(sim.rng.seed), _P_VACC, self.iindex, sim.t, 0, sim.n, slot, self._u.data_ptr(), sim._stream_ptr)
+        return self._u
+
+    def select_people(self, sim):
+        ''' Today's recipients as (scheduled second doses, first doses): device index arrays '''
+        t, P = sim.t, sim.people
+        none = torch.zeros(0, dtype=torch.int64, device=P.device)
+        num_people = self.n_today(sim)
+        if num_people == 0:
+            self.due_day[self.due_day == t] = t + 1              # defer everyone due today
+            return none, none
+        num_agents = int(np.floor(num_people / sim['pop_scale'] + sim.rng.np_.random_sample()))        # sc.randround
+        dead = P.dead.as_subclass(torch.Tensor)
+        vaccinated = P.vaccinated.as_subclass(torch.Tensor)
+        sched_mask = (self.due_day == t) & (self.doses < int(self.p['doses'])) & ~dead
+        scheduled = torch.nonzero(sched_mask).flatten()
+        if len(scheduled) > num_agents:                          # more second doses due than doses: the rest wait a day
+            order = torch.argsort(self._uniforms(sim, 1)[scheduled], stable=True)
+            self.due_day[scheduled[order[num_agents:]]] = t + 1
+            return scheduled[order[:num_agents]], none
+        prob = self._prob
+        prob.fill_(1.0)
+        prob[dead] = 0.0
+        if self.subtarget is not None:                           # weights multiply (interventions.py:1745-1747)
+            inds, vals = get_subtargets(self.subtarget, sim)
+            inds = torch.as_tensor(np.asarray(inds) if not isinstance(inds, torch.Tensor) else inds).to(device=P.device, dtype=torch.int64)
+            vals = torch.as_tensor(np.asarray(vals) if not isinstance(vals, torch.Tensor) else vals).to(device=P.device, dtype=torch.float64)
+            prob[inds] = prob[inds] * vals
+        if self.booster:
+            prob[~vaccinated] = 0.0
+        else:
+            prob[vaccinated] = 0.0
+        mask = self._uniforms(sim, 0) < prob
+        eligible = self.sequence[mask[self.sequence]]
+        if len(eligible) == 0:
+            return scheduled, none
+        eligible = eligible[:num_agents]
+        eligible = eligible[~sched_mask[eligible]]
+        first = eligible[:max(num_agents - len(scheduled), 0)] if len(eligible) + len(scheduled) > num_agents else eligible
+        return scheduled, first
+
+    def apply(self, sim):
+        t = sim.t
+        scheduled, first = self.select_people(sim)
+        if len(scheduled) + len(first) == 0:
+            return
+        # the dose kernel takes the recipients as explicit probabilities: 1 for today's first doses (it schedules their second
+        # dose, interventions.py:1786-1787), 0 for everyone else; who is due today (due_day == t) is dosed by the same pass
+        prob = self._prob
+        prob.fill_(0.0)
+        prob[first] = 1.0
+        self._c.first_dose_today = 1
+        self._c.second_dose_today = 1
+        sim._call('cvb_vaccinate_prob', sim._handle, t, C.byref(self._c), self.doses.data_ptr(), self.due_day.data_ptr(), prob.data_ptr(), sim._stream_ptr)
+        return torch.cat((scheduled, first))
+
+
+def vaccinate(*args, **kwargs):
+    ''' vaccinate_num if ``num_doses`` is given, else vaccinate_prob (reference interventions.py:1555-1568) '''
+    return vaccinate_num(*args, **kwargs) if 'num_doses' in kwargs else vaccinate_prob(*args, **kwargs)

@@ -327,6 +327,62 @@ def vaccinate_apply(iv, sim):
     second = iv._second.get(t)
     if second is not None:
         picked = torch.cat((picked, second))
+    vaccinate_inds(iv, sim, picked)
+
+
+def vaccinate_num_apply(iv, sim):
+    '''
+    reference interventions.py:1715-1791 vaccinate_num.select_people, literally: the scheduled second doses live in day-keyed
+    Python sets whose iteration order decides the order of the shuffle and of the NAb draws, so the selection runs on host
+    copies of the three arrays it reads.
+    '''
+    P, t = sim.people, sim.t
+    sched = lambda day: iv._scheduled.setdefault(day, set())
+    num_people = iv.n_today(sim)
+    if num_people == 0:
+        sched(t + 1).update(sched(t))
+        return
+    num_agents = int(np.floor(num_people / sim['pop_scale'] + sim.rng.np_.random_sample()))         # sc.randround
+    dead, vaccinated, doses = np.asarray(P.dead), np.asarray(P.vaccinated), iv.doses.cpu().numpy()
+    picked = None
+    if sched(t):
+        scheduled = np.fromiter(sched(t), dtype=np.int32)
+        scheduled = scheduled[(doses[scheduled] < iv.p['doses']) & ~dead[scheduled]]
+        if len(scheduled) > num_agents:
+            sim.rng.np_.shuffle(scheduled)
+            sched(t + 1).update(scheduled[num_agents:])
+            picked = scheduled[:num_agents]
+    else:
+        scheduled = np.array([], dtype=np.int32)
+    if picked is None:
+        probs = np.ones(sim.n)
+        probs[dead] = 0.0
+        if iv.subtarget is not None:
+            from .interventions import get_subtargets
+            s_inds, s_vals = get_subtargets(iv.subtarget, sim)
+            s_inds = np.asarray(s_inds)
+            probs[s_inds] = probs[s_inds] * np.asarray(s_vals)
+        if iv.booster:
+            probs[~vaccinated] = 0.0
+        else:
+            probs[vaccinated] = 0.0
+        seq = iv._sequence_host
+        eligible = seq[sim.rng.np_.random_sample(sim.n) < probs[seq]]
+        if len(eligible) == 0:
+            picked = scheduled
+        else:
+            eligible = eligible[:num_agents]
+            eligible = eligible[~np.isin(eligible, scheduled)]
+            first = eligible[:num_agents - len(scheduled)] if len(eligible) + len(scheduled) > num_agents else eligible
+            if iv.p['doses'] > 1:
+                sched(t + iv.p['interval']).update(first)
+            picked = np.concatenate([scheduled, first])
+    vaccinate_inds(iv, sim, torch.as_tensor(np.asarray(picked, dtype=np.int64), device=sim.device))
+
+
+def vaccinate_inds(iv, sim, picked):
+    ''' reference interventions.py:1428-1482 BaseVaccination.vaccinate '''
+    P, t = sim.people, sim.t
     if not len(picked):
         return
     inds = picked[~P.dead[picked]]
@@ -361,7 +417,7 @@ def update_dynamic_layer(sim, layer):
 
 
 def step(sim):
-    from .interventions import test_prob, contact_tracing, vaccinate_prob
+    from .interventions import test_prob, contact_tracing, vaccinate_prob, vaccinate_num
     t, pars, P, h, st = sim.t, sim.pars, sim.people, sim._handle, sim._stream_ptr
     call = _capi.call
     P.t = t
@@ -396,6 +452,8 @@ def step(sim):
         elif isinstance(iv, contact_tracing):
             if not (t < iv.start_day or (iv.end_day is not None and t > iv.end_day)):
                 contact_tracing_apply(iv, sim)
+        elif isinstance(iv, vaccinate_num):
+            vaccinate_num_apply(iv, sim)
         elif isinstance(iv, vaccinate_prob):
             vaccinate_apply(iv, sim)
         else:

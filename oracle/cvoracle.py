@@ -1137,6 +1137,104 @@ class vaccinate_prob(Intervention):
             sim.flows['new_vaccinated'] += len(new_vacc) * factor
 
 
+class vaccinate_num(vaccinate_prob):
+    '''
+    A number of doses per day handed out along a priority sequence, second doses first (reference interventions.py:1665-1791).
+    mt mode restates the reference literally, including its day-keyed Python sets of scheduled second doses (whose iteration
+    order decides the order of the shuffle and of the NAb draws).  Native-RNG mode: the same decisions with keyed draws --
+    deferral picks the ``num_agents`` scheduled people with the smallest uniform (P_VACC, slot 1), first doses go to the first
+    eligible people of the sequence whose uniform (P_VACC, slot 0) is below their weight.
+    '''
+    def __init__(self, vaccine, num_doses, booster=False, subtarget=None, sequence=None, label=None):
+        vaccinate_prob.__init__(self, vaccine, days=0, label=label, prob=1.0, booster=booster, subtarget=subtarget)
+        self.num_doses, self.sequence = num_doses, sequence
+
+    def initialize(self, sim):
+        vaccinate_prob.initialize(self, sim)
+        n = len(sim.P['uid'])
+        if isinstance(self.num_doses, dict):
+            self.num_doses = {sim.day(k): v for k, v in self.num_doses.items()}
+        if callable(self.sequence):                             # interventions.py:1539-1552 process_sequence
+            self.sequence = np.asarray(self.sequence(sim.P))
+        elif isinstance(self.sequence, str) and self.sequence == 'age':
+            self.sequence = np.argsort(-sim.P['age']) if sim.rng.kind == 'mt' else np.argsort(-sim.P['age'], kind='stable')
+        elif self.sequence is None:
+            self.sequence = sim.rng.np_.permutation(n)
+        else:
+            self.sequence = np.asarray(self.sequence)
+        self.days = np.array([0])                               # (acts from day 0 on)
+        self._scheduled = {}                                    # mt mode: day -> set, like the reference's ddict(set)
+        self.due_day = np.full(n, -1, dtype=np.int64)           # native mode: the day an agent's second dose is due
+
+    def _sched(self, day):
+        return self._scheduled.setdefault(day, set())
+
+    def n_today(self, sim):                                     # interventions.py:1526-1536 process_doses
+        if np.isscalar(self.num_doses):
+            return self.num_doses
+        if callable(self.num_doses):
+            return self.num_doses(sim)
+        return self.num_doses.get(sim.t, 0)
+
+    def select_people(self, sim):
+        t, P = sim.t, sim.P
+        n = len(P['uid'])
+        native = sim.rng.kind != 'mt'
+        num_people = self.n_today(sim)
+        if num_people == 0:                                     # defer everyone due today
+            if native:
+                self.due_day[self.due_day == t] = t + 1
+            else:
+                self._sched(t + 1).update(self._sched(t))
+            return np.array([], dtype=int)
+        num_agents = int(np.floor(num_people / sim.pars['pop_scale'] + sim.rng.np_.random_sample()))     # sc.randround
+        if native:
+            scheduled = np.nonzero((self.due_day == t) & (self.doses < self.p['doses']) & ~P['dead'])[0]
+            if len(scheduled) > num_agents:
+                u = sim.rng.agent_uniforms(t, ph.P_VACC, self.iindex, scheduled, slot=1)
+                order = np.argsort(u, kind='stable')
+                self.due_day[scheduled[order[num_agents:]]] = t + 1
+                return scheduled[order[:num_agents]]
+        elif self._sched(t):
+            scheduled = np.fromiter(self._sched(t), dtype=i32)
+            scheduled = scheduled[(self.doses[scheduled] < self.p['doses']) & ~P['dead'][scheduled]]
+            if len(scheduled) > num_agents:
+                sim.rng.np_.shuffle(scheduled)
+                self._sched(t + 1).update(scheduled[num_agents:])
+                return scheduled[:num_agents]
+        else:
+            scheduled = np.array([], dtype=i32)
+        probs = np.ones(n)
+        probs[P['dead']] = 0.0
+        if self.subtarget is not None:                          # interventions.py:1745-1747: weights multiply
+            inds = np.asarray(self.subtarget['inds'])
+            probs[inds] = probs[inds] * self.subtarget['vals']
+        if self.booster:
+            probs[~P['vaccinated']] = 0.0
+        else:
+            probs[P['vaccinated']] = 0.0
+        if native:
+            mask = sim.rng.agent_uniforms(t, ph.P_VACC, self.iindex, np.arange(n)) < probs
+            eligible = self.sequence[mask[self.sequence]]
+        else:
+            eligible = self.sequence[sim.rng.np_.random_sample(n) < probs[self.sequence]]
+        if len(eligible) == 0:
+            return scheduled
+        eligible = eligible[:num_agents]
+        eligible = eligible[~np.isin(eligible, scheduled)]
+        first = eligible[:num_agents - len(scheduled)] if len(eligible) + len(scheduled) > num_agents else eligible
+        if self.p['doses'] > 1:
+            if native:
+                self.due_day[first] = t + self.p['interval']
+            else:
+                self._sched(t + self.p['interval']).update(first)
+        return np.concatenate([scheduled, first])
+
+
+def vaccinate(*args, **kwargs):
+    return vaccinate_num(*args, **kwargs) if 'num_doses' in kwargs else vaccinate_prob(*args, **kwargs)
+
+
 class variant:
     ''' A variant introduced by importation on given days (reference immunity.py:18-130) '''
     def __init__(self, variant, days, label=None, n_imports=1, rescale=True):

@@ -66,7 +66,7 @@ for th, ch in itertools.product((128, 256), (256, 512, 1024)):
 if args.quick:
     configs = [dict()]
 if args.edge:
-    configs = [dict()] + [dict(edge_shape=k) for k in range(1, 7)] + [dict(edge_grid=g) for g in (4, 6, 12, 16)] + [dict(infect_grid=g) for g in (1, 2)]
+    configs = [dict()] + [dict(edge_shape=k) for k in range(1, 8)] + [dict(edge_grid=g) for g in (4, 6, 12, 16)] + [dict(infect_grid=g) for g in (1, 2)]
 for cfg in configs:
     tune(begin_threads=0, begin_chunk=0, mid_threads=0, mid_chunk=0, edge_shape=0, edge_grid=0, infect_grid=0)
     tune(**cfg)

@@ -99,6 +99,15 @@ SCENARIOS = {
         interventions=[('test_prob', dict(start_day=3, symp_prob=0.5, asymp_prob=0.05)),
                        ('contact_tracing', dict(trace_probs=0.6, trace_time=dict(h=0, s=1, w=1, c=2), start_day=4, capacity=6))],
     ),
+    # doses per day along a priority sequence (vaccinate_num): oldest first with subtarget weights, days without doses (second doses
+    # deferred) and days with fewer doses than second doses due (who waits is drawn); a one-dose booster in random order
+    'vaccnum3k': dict(
+        pars=dict(pop_size=3000, pop_infected=50, pop_type='hybrid', n_days=45, verbose=0, rand_seed=121, beta=0.022),
+        interventions=[('vaccinate_num', dict(vaccine='pfizer', sequence='age', subtarget=dict(inds=np.arange(0, 3000, 3), vals=0.4),
+                                              num_doses={2: 80, 3: 120, 4: 0, 5: 150, 6: 90, 8: 60, 23: 30, 24: 0, 25: 100, 26: 40, 27: 200, 28: 35, 30: 400, 33: 90})),
+                       ('vaccinate_num', dict(vaccine='jj', booster=True, num_doses=25, label='jj_boost')),
+                       ('test_prob', dict(start_day=5, symp_prob=0.2, asymp_prob=0.01))],
+    ),
     # dynamic layer (BASELINE.json config 5 member shape, scaled down)
     'dynamic2k': dict(pars=dict(pop_size=2000, pop_infected=40, n_days=30, verbose=0, rand_seed=8, beta=0.02,
                                 dynam_layer=dict(a=1)), interventions=[]),

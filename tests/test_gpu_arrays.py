@@ -86,3 +86,48 @@ def test_copy_of_a_running_sim(cv):
         assert np.array_equal(x, y, equal_nan=(x.dtype.kind == 'f')), k
     a, b = sim.infection_log, twin.infection_log
     assert all(np.array_equal(a[k], b[k]) for k in a)
+
+
+def test_vaccinate_num_reference_examples(cv):
+    '''
+    The reference's own uses of vaccinate_num, unchanged: examples/t08_boosters.py:15-45 (doses per day and the people to boost
+    as functions of the sim, booster=True), tests/test_immunity.py:170-181 (fluctuating doses + subtarget, doses recorded by an
+    analyzer) and tests/test_immunity.py:214-232 (two people, two vaccines, 1000 days, no infections).
+    '''
+    def num_doses(sim):
+        return sim.t * 10 if sim.t < 50 else 500
+
+    def num_boosters(sim):
+        return 0 if sim.t < 50 else 50
+    pfizer = cv.vaccinate_num(vaccine='pfizer', sequence='age', num_doses=num_doses)
+    booster_target = {'inds': lambda sim: cv.true(sim.people.doses != 2), 'vals': 0}
+    booster = cv.vaccinate_num(vaccine='pfizer', sequence='age', subtarget=booster_target, booster=True, num_doses=num_boosters)
+    n_doses = []
+    sim = cv.Sim(beta=0.015, n_days=90, interventions=[pfizer, booster], analyzers=lambda sim: n_doses.append(sim.people.doses.copy()), verbose=0)
+    sim.run()
+    doses = np.array([np.asarray(d) for d in n_doses])
+    per_day = np.diff(doses.sum(axis=1), prepend=0)
+    assert np.array_equal(per_day, sim.results['new_doses'].values)
+    assert per_day[:50].max() <= 490 and np.all(per_day[50:] <= 550)               # never more than the day's doses + boosters
+    assert np.array_equal(per_day[1:20], 10 * np.arange(1, 20))                       # first weeks: every dose is a first dose
+    assert doses[-1].max() >= 3 and (doses[-1] >= 3).sum() > 100                      # boosters reached people with two doses
+    first = np.argmax(doses > 0, axis=0)
+    got = doses[-1] > 0
+    age = sim.people.to_numpy('age')
+    assert np.corrcoef(age[got], first[got])[0, 1] < -0.8                             # oldest first
+
+    n_days = 60
+    nd = {i: (i ** 2) * (i % 2 == 0) for i in np.arange(n_days)}
+    sub = dict(inds=np.arange(10000), vals=0.1)
+    seq = cv.vaccinate_num(vaccine='pfizer', sequence='age', num_doses=nd, subtarget=sub)
+    sim2 = cv.Sim(pop_size=20000, n_days=n_days, rescale=False, use_waning=True, variants=cv.variant('beta', days=20, n_imports=20), interventions=seq, verbose=0)
+    sim2.run()
+    assert sim2.results['new_doses'].values[1::2].sum() == 0 and sim2.summary['cum_doses'] > 10000
+    assert sim2.results['new_doses'].values[10] == 100 and sim2.results['cum_vaccinated'][-1] <= 20000
+
+    vac1 = cv.vaccinate_num(vaccine='pfizer', sequence=[0], num_doses=1)
+    vac2 = cv.vaccinate_num(vaccine='jj', sequence=[1], num_doses=1)
+    sim3 = cv.Sim(n_days=200, pop_size=4, pop_infected=0, variants=cv.variant('beta', days=20, n_imports=0), interventions=[vac1, vac2], verbose=0)
+    sim3.run()
+    assert list(sim3.people.to_numpy('doses')) == [2, 1, 0, 0] and sim3.summary['cum_infections'] == 0
+    assert np.all(sim3.people.to_numpy('nab')[:2] > 0) and np.all(sim3.people.to_numpy('nab')[2:] == 0)

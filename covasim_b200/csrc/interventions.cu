@@ -187,11 +187,13 @@ struct TraceTable {                      // the traced layers of one contact_tra
     int64_t n, n_words;
     int64_t id0;                         // global id of local agent 0 (agent-partitioned runs): Philox keys use global ids
     int32_t t, index;
+    const double* tape;                  // verification (cvb_contact_tracing_taped): the uniform of (layer, contact) is tape[layer * n + contact]
 };
 
 __device__ __forceinline__ void trace_notify(const PeoplePtrs& P, const TraceTable& T, int q, int c) {
     const uint32_t sub = ((uint32_t)T.index << 8) | (uint32_t)T.layer_id[q];
-    if (!(keyed_uniform(T.seed, P_TRACE, sub, T.t, (int64_t)c + T.id0, 0) < T.trace_prob[q])) return;     // binomial_filter, interventions.py:1116
+    const double u = T.tape ? T.tape[(int64_t)T.layer_id[q] * T.n + c] : keyed_uniform(T.seed, P_TRACE, sub, T.t, (int64_t)c + T.id0, 0);
+    if (!(u < T.trace_prob[q])) return;                                 // binomial_filter, interventions.py:1116
     if (PB(P, dead)[c]) return;                                        // interventions.py:1139-1141
     PB(P, known_contact)[c] = 1;
     // date_known_contact = fmin(old, notify_day): for non-negative floats and NaN the unsigned bit
@@ -204,7 +206,8 @@ __device__ __forceinline__ void trace_notify(const PeoplePtrs& P, const TraceTab
 // is read from the packed state word, and the word's known_contact / pending-request bits are set with the People arrays
 __device__ __forceinline__ void trace_notify2(const PeoplePtrs& P, uint32_t* __restrict__ S, const TraceTable& T, int q, int c) {
     const uint32_t sub = ((uint32_t)T.index << 8) | (uint32_t)T.layer_id[q];
-    if (!(keyed_uniform(T.seed, P_TRACE, sub, T.t, (int64_t)c + T.id0, 0) < T.trace_prob[q])) return;     // binomial_filter, interventions.py:1116
+    const double u = T.tape ? T.tape[(int64_t)T.layer_id[q] * T.n + c] : keyed_uniform(T.seed, P_TRACE, sub, T.t, (int64_t)c + T.id0, 0);
+    if (!(u < T.trace_prob[q])) return;                                 // binomial_filter, interventions.py:1116
     if (S[c] & (1u << 11)) return;                                     // dead (interventions.py:1139-1141)
     PB(P, known_contact)[c] = 1;
     atomicOr(S + c, (1u << 12) | (1u << 18));                          // known_contact, request pending
@@ -305,7 +308,7 @@ __global__ void __launch_bounds__(THREADS) trace_edges_kernel(PeoplePtrs P, cons
 __global__ void __launch_bounds__(kThreads) vaccinate_kernel(PeoplePtrs P, const __grid_constant__ cvb_vaccinate_pars vp, uint64_t seed,
         int64_t n, int64_t id0, int32_t t, int32_t* __restrict__ iv_doses, int32_t* __restrict__ due_day, unsigned long long* __restrict__ counters,
         const double* __restrict__ prob_override, uint32_t* __restrict__ S /* fused day: packed state words, or NULL */,
-        unsigned long long* __restrict__ vcounters_row, int32_t nv) {
+        unsigned long long* __restrict__ vcounters_row, int32_t nv, const double* __restrict__ tape = nullptr /* verification: the NAb sample of agent i */) {
     __shared__ int s_cnt[2];
     __shared__ int s_delta[kStockSlots];
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(kThreads) vaccinate_kernel(PeoplePtrs P, const
         if (PF(P, nab)[i] > 0.0f) {
             PF(P, peak_nab)[i] = fmul(PF(P, peak_nab)[i], vp.nab_boost);
         } else {
-            double x = dist_from_normal(vp.nab_init, keyed_normal(seed, P_NAB_VACC, (uint32_t)vp.index, t, i + id0, 0));
+            double x = tape ? tape[i] : dist_from_normal(vp.nab_init, keyed_normal(seed, P_NAB_VACC, (uint32_t)vp.index, t, i + id0, 0));
             PF(P, peak_nab)[i] = (float)pow(2.0, x);
         }
         PI(P, t_nab_event)[i] = t;
@@ -562,7 +565,7 @@ int cvb_test_list(cvb_sim* s, int32_t t, const int32_t* inds, int64_t n_inds, do
 }
 
 // notify the contacts of the current case set (bitmap + list) of a non-partitioned handle: phase two of contact tracing
-static int trace_notify_local(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cudaStream_t st) {
+static int trace_notify_local(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cudaStream_t st, const double* tape = nullptr) {
     const uint32_t adj_mask = (s->adj && s->adj_layer_mask) ? s->adj_layer_mask : 0u;
     const size_t bitmap_bytes = (size_t)((s->n + 31) / 32) * sizeof(unsigned int);
     const bool smem_bits = bitmap_bytes <= 200 * 1024;
@@ -571,6 +574,7 @@ static int trace_notify_local(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, c
     int64_t acc;
     bool any_sparse;
     if (build_trace_table(s, t, tr, adj_mask, threads * kEdgesPerThread, T, acc, any_sparse)) return 1;
+    T.tape = tape;
     if (any_sparse) {
         trace_sparse_kernel<<<148 * 2, kThreads, 0, st>>>(s->people, T, s->adj_ptr, s->adj, s->case_list, s->n_case_list, adj_mask);
         CVB_LAUNCH_CHECK();
@@ -604,6 +608,22 @@ int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cvb_str
     return trace_notify_local(s, t, tr, st);
 }
 
+int cvb_contact_tracing_taped(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, const double* tape, cvb_stream st_) {
+    if (s) cvb::state_touched(s);
+    cudaStream_t st = (cudaStream_t)st_;
+    CVB_REQUIRE(s && tr && tape && s->pars_set && !s->partitioned, "cvb_contact_tracing_taped: bad argument");
+    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_contact_tracing_taped: day %d outside [0,%d)", t, s->npts);
+    if (trace_select(s, t, tr, st)) return 1;
+    return trace_notify_local(s, t, tr, st, tape);
+}
+
+int cvb_pending_quarantine(cvb_sim* s, int32_t start_day, float* out_end_day, cvb_stream st) {
+    CVB_REQUIRE(s && out_end_day && start_day >= 0, "cvb_pending_quarantine: bad argument");
+    const int slot = start_day % s->quar_horizon;
+    CVB_CHECK(cudaMemcpyAsync(out_end_day, s->quar_ring + (int64_t)slot * s->n, (size_t)s->n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)st));
+    return 0;
+}
+
 int cvb_contact_tracing_list(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, const int32_t* case_inds, int64_t n_cases, cvb_stream st_) {
     if (s) cvb::state_touched(s);
     cudaStream_t st = (cudaStream_t)st_;
@@ -626,6 +646,17 @@ int cvb_vaccinate_prob(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* vp, int3
     CVB_REQUIRE(vp->vaccine_index >= 0 && vp->vaccine_index < CVB_MAX_VACCINES, "cvb_vaccinate_prob: vaccine index out of range");
     vaccinate_kernel<<<grid_for(s->n), kThreads, 0, (cudaStream_t)st>>>(s->people, *vp, s->seed, s->n, s->partitioned ? s->id0 : 0, t, iv_doses, due_day, s->res.counters, prob_override,
                                                                       nullptr, nullptr, s->nv);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
+
+int cvb_vaccinate_taped(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* vp, int32_t* iv_doses, int32_t* due_day, const double* prob_override,
+                        const double* tape, cvb_stream st) {
+    if (s) cvb::state_touched(s);
+    CVB_REQUIRE(s && vp && iv_doses && due_day && tape && s->res.counters, "cvb_vaccinate_taped: bad argument");
+    CVB_REQUIRE(t >= 0 && t < s->npts, "cvb_vaccinate_taped: day %d outside [0,%d)", t, s->npts);
+    vaccinate_kernel<<<grid_for(s->n), kThreads, 0, (cudaStream_t)st>>>(s->people, *vp, s->seed, s->n, s->partitioned ? s->id0 : 0, t, iv_doses, due_day, s->res.counters, prob_override,
+                                                                      nullptr, nullptr, s->nv, tape);
     CVB_LAUNCH_CHECK();
     return 0;
 }

@@ -253,6 +253,12 @@ int cvb_contact_tracing(cvb_sim* s, int32_t t, const cvb_trace_pars* host_pars, 
 /* The same for an explicit list of distinct cases (int32[n_cases]) chosen by the caller: contact_tracing with a `capacity`
  * (interventions.py:1079-1083 picks `capacity` of today's cases at random) */
 int cvb_contact_tracing_list(cvb_sim* s, int32_t t, const cvb_trace_pars* host_pars, const int32_t* case_inds, int64_t n_cases, cvb_stream st);
+/* Verification: cvb_contact_tracing with the uniform of every (layer, contact) GIVEN (device float64[n_layers][n], read only for contacts
+ * of today's cases) -- the draws binomial_filter consumed in a recorded run of the reference (interventions.py:1109-1116) */
+int cvb_contact_tracing_taped(cvb_sim* s, int32_t t, const cvb_trace_pars* host_pars, const double* tape, cvb_stream st);
+/* Verification: the pending quarantine requests starting on start_day (people.py:620-640 _pending_quarantine[start_day]) as the latest
+ * requested end day of every agent (device float32[n], -1 = none) */
+int cvb_pending_quarantine(cvb_sim* s, int32_t start_day, float* out_end_day, cvb_stream st);
 /* The same in two phases for agent-partitioned handles: select today's local cases into case_bits_local; (the host
  * all-gathers the bitmap); notify the LOCAL contacts of every GLOBAL case */
 int cvb_trace_select_cases(cvb_sim* s, int32_t t, const cvb_trace_pars* host_pars, cvb_stream st);
@@ -268,6 +274,11 @@ typedef struct cvb_vaccinate_pars {        /* interventions.py:1257-1662 */
  * dose is due (-1 none) -- the device form of second_dose_days (interventions.py:1655-1660) */
 int cvb_vaccinate_prob(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* host_pars, int32_t* iv_doses, int32_t* due_day,
                        const double* prob_override /* NULL or float64[n], NaN = none: `subtarget` (interventions.py:1644-1647) */, cvb_stream st);
+
+/* Verification: the same with every agent's initial NAb sample GIVEN (device float64[n]: the value immunity.py:178 drew for agents without
+ * prior antibodies in a recorded run of the reference) */
+int cvb_vaccinate_taped(cvb_sim* s, int32_t t, const cvb_vaccinate_pars* host_pars, int32_t* iv_doses, int32_t* due_day, const double* prob_override,
+                        const double* tape, cvb_stream st);
 
 /* base.py:1849-1876 Layer.update with frac=1: regenerate every edge of a dynamic layer on the device */
 int cvb_layer_regenerate(cvb_sim* s, int32_t layer, int32_t t, cvb_stream st);

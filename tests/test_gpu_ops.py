@@ -241,3 +241,111 @@ def test_test_prob_kernel_against_reference_tape(cv, day):
             got, want = P.to_numpy(k), g[key]
             assert np.array_equal(got, want, equal_nan=(want.dtype.kind == 'f')), f'day {day}: {k} differs at {np.nonzero(~((got == want) | ((got != got) & (want != want))))[0][:5]}'
     assert int(sim._counters[day, cv.defaults.COUNTER_IDS['new_tests']].item()) == int(g[pre + 'n_tests'])
+
+
+@pytest.mark.parametrize('day', [12, 25])
+@pytest.mark.parametrize('adjacency', [True, False])
+def test_contact_tracing_kernel_against_reference_tape(cv, day, adjacency):
+    '''
+    tests/golden/trace_tape.npz (oracle/gen_trace_vacc_golden.py): a contact_tracing.apply call of the unmodified reference -- the arrays it
+    reads, the quarantine requests pending before it, the uniforms binomial_filter consumed per (layer, contact), and afterwards
+    known_contact / date_known_contact and the pending requests of the next three days.  The CUDA tracing kernels (adjacency rows, or the
+    streamed edge lists), given the same state and the same uniforms (cvb_contact_tracing_taped), must leave the same arrays and requests.
+    The contact network is the reference's own: replay mode builds the population from the reference's random streams.
+    '''
+    import ctypes as C
+    import hashlib
+    import os
+    import torch
+    import scenarios
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = np.load(os.path.join(here, 'golden', 'trace_tape.npz'))
+    ref = np.load(os.path.join(here, 'golden', 'hybrid3k.npz'))
+    pre = f'hybrid3k/t{day}/'
+    sim = cv.Sim(**scenarios.build(cv, scenarios.SCENARIOS['hybrid3k']), rng='mt', use_adjacency=adjacency)
+    sim.initialize()
+    P, dev, n = sim.people, sim.people.device, sim.n
+    for lk, layer in P.contacts.items():                              # the same edges as the reference's run
+        sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+        assert sha(layer['p1'].cpu().numpy()) + sha(layer['p2'].cpu().numpy()) == str(ref[f'final_contacts_digest/{lk}'])
+    for key in g.files:
+        if key.startswith(pre + 'pre/'):
+            P[key.split('/')[-1]] = g[key]
+    ct = [iv for iv in sim['interventions'] if isinstance(iv, cv.contact_tracing)][0]
+    sim.t = day
+    sim._push_pars()
+    if adjacency:                                                     # (replay mode itself walks the edge lists: build the rows the native mode uses)
+        sim.rng_mode, sim._adj_dirty = 'philox', True
+        sim._build_adjacency()
+        assert sim._adj is not None
+    sim._set_quar_horizon(3)
+    for d in range(day, day + 3):                                     # requests already pending, as (agent, end day)
+        pend = g[pre + f'pend_pre/{d}']
+        for end in np.unique(pend[pend >= 0]):
+            inds = torch.as_tensor(np.nonzero(pend == end)[0].astype(np.int32), device=dev)
+            cv._capi.call('cvb_schedule_quarantine', sim._handle, inds.data_ptr(), len(inds), d, float(end), sim._stream_ptr)
+    tape = torch.as_tensor(g[pre + 'tape'], dtype=torch.float64, device=dev).contiguous()
+    cv._capi.call('cvb_contact_tracing_taped', sim._handle, day, C.byref(ct._c), tape.data_ptr(), sim._stream_ptr)
+    torch.cuda.synchronize()
+    for k in ('known_contact', 'date_known_contact'):
+        got, want = P.to_numpy(k), g[pre + 'post/' + k]
+        assert np.array_equal(got, want, equal_nan=(want.dtype.kind == 'f')), f'day {day}: {k} differs at {np.nonzero(~((got == want) | ((got != got) & (want != want))))[0][:5]}'
+    out = torch.empty(n, dtype=torch.float32, device=dev)
+    n_req = 0
+    for d in range(day, day + 3):
+        cv._capi.call('cvb_pending_quarantine', sim._handle, d, out.data_ptr(), sim._stream_ptr)
+        torch.cuda.synchronize()
+        want = g[pre + f'pend_post/{d}']
+        got = out.cpu().numpy()
+        assert np.array_equal(got, want), f'day {day}: requests starting on day {d} differ at {np.nonzero(got != want)[0][:5]}: got {got[got != want][:5]} want {want[got != want][:5]}'
+        n_req += int((want >= 0).sum())
+    assert n_req > 300
+
+
+@pytest.mark.parametrize('day,label', [(5, 'pfizer'), (26, 'pfizer'), (32, 'jj_boost')])
+def test_vaccinate_kernel_against_reference_tape(cv, day, label):
+    '''
+    tests/golden/vacc_tape.npz (oracle/gen_trace_vacc_golden.py): a BaseVaccination.vaccinate call of the unmodified reference (first doses, second
+    doses, a booster) -- the agents, the arrays it reads and writes before / after, the intervention's own dose counts and the initial
+    NAb samples.  The CUDA dose kernel, given the same agents (as explicit probabilities 1), state and samples (cvb_vaccinate_taped), must
+    write the same arrays and count the same flows; the peak NAb level (a float64 2**x) is compared at 1e-6.
+    '''
+    import ctypes as C
+    import os
+    import torch
+    import scenarios
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'vacc_tape.npz'))
+    pre = f'variants4k/t{day}/{label}/'
+    sim = cv.Sim(**scenarios.build(cv, scenarios.SCENARIOS['variants4k']))
+    sim.initialize()
+    P, dev, n = sim.people, sim.people.device, sim.n
+    iv = [v for v in sim['interventions'] if isinstance(v, cv.vaccinate_prob) and v.label == label][0]
+    for key in g.files:
+        if key.startswith(pre + 'pre/'):
+            k = key.split('/')[-1]
+            if k == 'iv_doses':
+                iv.doses.copy_(torch.as_tensor(g[key].astype(np.int32), device=dev))
+            else:
+                P[k] = g[key]
+    prob = torch.zeros(n, dtype=torch.float64, device=dev)
+    prob[torch.as_tensor(g[pre + 'inds'].astype(np.int64), device=dev)] = 1.0
+    tape = torch.as_tensor(np.nan_to_num(g[pre + 'tape'], nan=0.0), dtype=torch.float64, device=dev).contiguous()
+    iv.due_day.fill_(-1)
+    iv._c.first_dose_today, iv._c.second_dose_today = 1, 0
+    sim.t = day
+    sim._push_pars()
+    cv._capi.call('cvb_vaccinate_taped', sim._handle, day, C.byref(iv._c), iv.doses.data_ptr(), iv.due_day.data_ptr(), prob.data_ptr(), tape.data_ptr(), sim._stream_ptr)
+    torch.cuda.synchronize()
+    for key in g.files:
+        if not key.startswith(pre + 'post/'):
+            continue
+        k = key.split('/')[-1]
+        want = g[key]
+        got = iv.doses.cpu().numpy() if k == 'iv_doses' else P.to_numpy(k)
+        if k == 'peak_nab':
+            assert np.allclose(got, want, rtol=1e-6, atol=0, equal_nan=True), f'day {day}: peak_nab differs'
+        else:
+            assert np.array_equal(got.astype(want.dtype), want, equal_nan=(want.dtype.kind == 'f')), f'day {day}: {k} differs at {np.nonzero(got.astype(want.dtype) != want)[0][:5]}'
+    flows = g[pre + 'flows']
+    assert int(sim._counters[day, cv.defaults.COUNTER_IDS['new_doses']].item()) == int(flows[0])
+    assert int(sim._counters[day, cv.defaults.COUNTER_IDS['new_vaccinated']].item()) == int(flows[1])

@@ -499,7 +499,7 @@ def partition_block(args, cv, world, rank, max_over_ranks):
                    pop_size=n, agents_per_gpu=int(args.part_agents), n_days=args.part_days, n_gpus=world, ms_per_run=best, us_per_day=1e3 * best / sim.npts,
                    agent_days_per_s=n * sim.npts / (best / 1e3), init_s=t_init, fused_days=int(fused_days), kernel_us_per_day=kernels,
                    allgather_us_per_day=round(kernels.get('allgather_codes', 0.0) + kernels.get('allgather_cases', 0.0), 1),
-                   exchange_bytes_per_day_per_rank=int(sim._chunk * world + sim._chunk * world // 8), collective='ncclAllGather (torch.distributed all_gather_into_tensor), 1 byte per agent per day + 1 bit per agent on tracing days',
+                   exchange_bytes_per_day_per_rank=int(sim._chunk * world + sim._chunk * world // 8), collective=('peer-memory exchange (cvb_peer_push: every rank stores its chunk into all ranks\' buffers over NVLink, torch symmetric memory + signal barrier)' if sim._peer is not None else 'ncclAllGather (torch.distributed all_gather_into_tensor)') + ', 1 byte per agent per day + 1 bit per agent on tracing days',
                    hbm_gb_per_gpu=torch.cuda.max_memory_allocated() / 1e9,
                    cum_infections=float(sim.summary['cum_infections']), cum_deaths=float(sim.summary['cum_deaths']), cum_doses=float(sim.summary['cum_doses']))
     del sim

@@ -57,6 +57,19 @@ int exclusive_scan_u32(unsigned int* data, int64_t n, unsigned long long* total_
     return 0;
 }
 
+// All-gather over peer memory (agent-partitioned runs on one NVSwitch node): every rank stores its chunk straight into the exchange
+// buffer of every rank (its own included) -- W coalesced 16-byte stores per item, the remote ones travel over NVLink -- so the day's
+// exchange is this one kernel plus a signal barrier instead of a library collective (covasim_b200/partition.py:PeerExchange)
+constexpr int kMaxPeers = 16;
+struct PeerPtrs { unsigned char* p[kMaxPeers]; };
+template <typename V>
+__global__ void __launch_bounds__(kThreads) peer_push_kernel(const V* __restrict__ src, int64_t items, const __grid_constant__ PeerPtrs P, int world) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < items; k += (int64_t)gridDim.x * blockDim.x) {
+        const V v = __ldg(src + k);
+        for (int p = 0; p < world; ++p) reinterpret_cast<V*>(P.p[p])[k] = v;
+    }
+}
+
 __global__ void fill_f32_kernel(float* p, int64_t n, float v) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -233,6 +246,25 @@ int cvb_bind_adjacency(cvb_sim* s, const int64_t* adj_ptr, const void* adj, int6
     return 0;
 }
 
+int cvb_peer_push(const void* src, int64_t n_bytes, const uint64_t* host_peer_ptrs, int32_t world, int64_t dst_offset_bytes, cvb_stream st) {
+    CVB_REQUIRE(src && host_peer_ptrs && world >= 1 && world <= cvb::kMaxPeers && n_bytes >= 0 && n_bytes % 4 == 0 && dst_offset_bytes % 4 == 0,
+                "cvb_peer_push: bad argument (at most %d peers, sizes in multiples of 4 bytes)", cvb::kMaxPeers);
+    if (n_bytes == 0) return 0;
+    cvb::PeerPtrs P;
+    bool vec = ((uintptr_t)src & 15) == 0 && n_bytes % 16 == 0 && dst_offset_bytes % 16 == 0;
+    for (int p = 0; p < world; ++p) {
+        CVB_REQUIRE(host_peer_ptrs[p], "cvb_peer_push: NULL peer buffer");
+        P.p[p] = (unsigned char*)(uintptr_t)host_peer_ptrs[p] + dst_offset_bytes;
+        vec = vec && (host_peer_ptrs[p] & 15) == 0;
+    }
+    const int64_t items = vec ? n_bytes / 16 : n_bytes / 4;
+    const int grid = cvb::grid_for(items, cvb::kThreads, 148 * 4);
+    if (vec) cvb::peer_push_kernel<uint4><<<grid, cvb::kThreads, 0, (cudaStream_t)st>>>((const uint4*)src, items, P, world);
+    else cvb::peer_push_kernel<uint32_t><<<grid, cvb::kThreads, 0, (cudaStream_t)st>>>((const uint32_t*)src, items, P, world);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
+
 int cvb_set_partition(cvb_sim* s, int64_t id0, int64_t n_global, int64_t chunk, int32_t world, const float* rel_trans_global,
                       uint8_t* codes_local, const uint8_t* codes_global, uint32_t* case_bits_local, const uint32_t* case_bits_global,
                       int64_t hit_capacity) {
@@ -265,6 +297,14 @@ int cvb_set_partition(cvb_sim* s, int64_t id0, int64_t n_global, int64_t chunk, 
     CVB_CHECK(cudaMalloc((void**)&s->part_flags, 64));
     CVB_CHECK(cudaMemset(s->part_flags, 0, 64));
     s->partitioned = 1;
+    return 0;
+}
+
+int cvb_set_exchange_buffers(cvb_sim* s, const uint8_t* codes_global, const uint32_t* case_bits_global) {
+    CVB_REQUIRE(s && s->partitioned, "cvb_set_exchange_buffers: call cvb_set_partition first");
+    CVB_REQUIRE((((uintptr_t)codes_global | (uintptr_t)case_bits_global) & 15) == 0, "cvb_set_exchange_buffers: arrays must be 16-byte aligned");
+    if (codes_global) s->codes_global = codes_global;
+    if (case_bits_global) s->case_bits_global = case_bits_global;
     return 0;
 }
 

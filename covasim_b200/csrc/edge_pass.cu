@@ -486,63 +486,86 @@ struct PartHits {                         // one entry per successful transmissi
     int32_t* tgt; int32_t* src; unsigned long long* key; unsigned int* n; unsigned int* dropped; int64_t cap;
 };
 
-// LANES lanes per transmitter (32, 16 or 8): with W ranks a transmitter's row holds ~36/W local entries, so a full warp per
-// row would idle most of its lanes
-template <bool MULTI, int LANES>
+// G lanes per transmitter, U adjacency entries in flight per lane (with W ranks a transmitter's row holds ~36/W local entries, so a
+// full warp per row would idle most of its lanes).  A group's dependent chain per transmitter is list index -> row header
+// {row pointers, transmit code, base rel_trans} -> adjacency entries -> target records; the first two levels are software-
+// pipelined across the group's transmitters (the index two ahead and the header one ahead are in flight while a row is
+// processed), the last two issue all U loads before consuming any.
+struct PartHeader { long long beg, end; unsigned code; float rt; };
+
+template <bool MULTI, int G, int U>
 __global__ void __launch_bounds__(kThreads) edge_pass_partition_kernel(TransRecords rec, const __grid_constant__ EdgeParams ep,
-        const __grid_constant__ cvb_pars pars, const long long* __restrict__ adj_ptr, const uint4* __restrict__ adj,
+        float trans_redux, const long long* __restrict__ adj_ptr, const uint4* __restrict__ adj,
         const int32_t* __restrict__ glist, const unsigned int* __restrict__ n_glist, const uint8_t* __restrict__ codes,
         const float* __restrict__ base_trans, unsigned long long* __restrict__ infect_key, PartHits hits,
         unsigned long long* __restrict__ work_row) {
     const unsigned int n_trans = *n_glist;
     unsigned long long visited = 0;
     const int64_t n = ep.n;                                              // local agents
-    const int lane = threadIdx.x & (LANES - 1);
-    const unsigned int groups_total = (gridDim.x * blockDim.x) / LANES;
-    const float vl_early = viral_load_value(true, pars.frac_time, pars.load_ratio);
-    const float vl_late = viral_load_value(false, pars.frac_time, pars.load_ratio);
-    for (unsigned int ti = (blockIdx.x * blockDim.x + threadIdx.x) / LANES; ti < n_trans; ti += groups_total) {
-        const int i = glist[ti];                                         // global id of the source
-        const long long beg = adj_ptr[i], end = adj_ptr[i + 1];
-        if (beg == end) continue;                                        // no contact on this GPU
-        visited += (unsigned long long)(end - beg);
-        const unsigned code = codes[i];
-        const int vi = (int)(code & 7u) - 1;
-        const bool symp = code & 8u, iso = code & 16u, quar = code & 32u, early = code & 64u;
-        float rt = __ldg(base_trans + i);
-        if (code & 128u) rt = fmul(rt, pars.trans_redux);
-        const float vl = early ? vl_early : vl_late;
-        const float beta_v = ep.beta[vi];
-        for (long long off = beg + lane; off < end; off += LANES) {
-            const uint4 en = __ldg(adj + off);
-            const int j = (int)en.x;                                     // LOCAL target
-            const int l = (int)(en.z >> 1);
-            const int dir = (int)(en.z & 1u);
-            const float t_i = rel_trans_layer(rt, true, symp, iso, quar, pars.asymp_factor, pars.iso_factor[l], pars.quar_factor[l],
-                                              pars.beta_layer[l], vl);
-            if (t_i == 0.0f) continue;
-            const float4 rj = __ldg(rec.rec + j);
-            if (rj.y == 0.0f) continue;                                  // target not susceptible
-            float imm = rj.z;
-            if (MULTI && vi > 0) imm = __ldg(rec.sus_imm + (int64_t)vi * n + j);
-            const float s_j = record_sus(rj.y, __float_as_uint(rj.w), pars.quar_factor[l], imm);
-            const float p = edge_prob(beta_v, __uint_as_float(en.w), t_i, s_j);
-            if (p != 0.0f) {
-                const int64_t e = (int64_t)en.y;
-                const u32x4 r = keyed_words(ep.seed, P_EDGE, (uint32_t)l, ep.t, e, 0);
-                const double u = dir == 0 ? u53(r.x, r.y) : u53(r.z, r.w);
-                if (u < (double)p) {
-                    const unsigned long long key = ((unsigned long long)vi << 56) | ((unsigned long long)l << 48) |
-                                                   ((unsigned long long)dir << 40) | (unsigned long long)e;
-                    atomicMin(infect_key + j, key);
-                    const unsigned int pos = warp_append32(hits.n);      // aggregated over the lanes active here (any group)
-                    if ((int64_t)pos < hits.cap) { hits.tgt[pos] = j; hits.src[pos] = i; hits.key[pos] = key; }
-                    else atomicAdd(hits.dropped, 1u);
+    const int gl = threadIdx.x & (G - 1);
+    const unsigned int stride = (gridDim.x * blockDim.x) / G;
+    auto header = [&](int i) {
+        PartHeader h{0, 0, 0u, 0.0f};
+        if (i >= 0) { h.beg = __ldg(adj_ptr + i); h.end = __ldg(adj_ptr + i + 1); h.code = __ldg(codes + i); h.rt = __ldg(base_trans + i); }
+        return h;
+    };
+    unsigned int ti = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    int i0 = ti < n_trans ? __ldg(glist + ti) : -1;                      // global id of the source
+    int i1 = ti + stride < n_trans ? __ldg(glist + ti + stride) : -1;
+    PartHeader h0 = header(i0);
+    for (; ti < n_trans; ti += stride) {
+        const PartHeader h1 = header(i1);
+        const int i2 = (unsigned long long)ti + 2ull * stride < n_trans ? __ldg(glist + ti + 2 * stride) : -1;
+        const int len = (int)(h0.end - h0.beg);                          // 0: no contact on this GPU
+        if (len > 0) {
+            if (gl == 0) visited += (unsigned long long)len;
+            const uint32_t ci = h0.code;
+            const int vi = (int)(ci & 7u) - 1;
+            const float rt = (ci & 128u) ? fmul(h0.rt, trans_redux) : h0.rt;
+            const float beta_v = ep.beta[vi < 0 ? 0 : vi];
+            for (int base = gl; base - gl < len; base += G * U) {
+                uint4 en[U];
+                float4 rj[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int off = base + u * G;
+                    en[u] = off < len ? __ldg(adj + h0.beg + off) : make_uint4(0u, 0u, 0xFFFFFFFFu, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) rj[u] = en[u].z != 0xFFFFFFFFu ? __ldg(rec.rec + en[u].x) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (en[u].z == 0xFFFFFFFFu || rj[u].y == 0.0f) continue;      // past the row's end / target not susceptible
+                    const int j = (int)en[u].x;                                   // LOCAL target
+                    const int l = (int)(en[u].z >> 1);
+                    const int dir = (int)(en[u].z & 1u);
+                    const float t_i = record_trans(rt, ci, ep.asymp_factor, ep.iso_factor[l], ep.quar_factor[l], ep.beta_layer[l], ep.vl_early, ep.vl_late);
+                    if (t_i == 0.0f) continue;
+                    float imm = rj[u].z;
+                    if (MULTI && vi > 0) imm = __ldg(rec.sus_imm + (int64_t)vi * n + j);
+                    const float s_j = record_sus(rj[u].y, __float_as_uint(rj[u].w), ep.quar_factor[l], imm);
+                    const float p = edge_prob(beta_v, __uint_as_float(en[u].w), t_i, s_j);
+                    if (p != 0.0f) {
+                        const int64_t e = (int64_t)en[u].y;
+                        const u32x4 r = keyed_words(ep.seed, P_EDGE, (uint32_t)l, ep.t, e, 0);
+                        const double uu = dir == 0 ? u53(r.x, r.y) : u53(r.z, r.w);
+                        if (uu < (double)p) {
+                            const unsigned long long key = ((unsigned long long)vi << 56) | ((unsigned long long)l << 48) |
+                                                           ((unsigned long long)dir << 40) | (unsigned long long)e;
+                            atomicMin(infect_key + j, key);
+                            const unsigned int pos = warp_append32(hits.n);      // aggregated over the lanes active here (any group)
+                            if ((int64_t)pos < hits.cap) { hits.tgt[pos] = j; hits.src[pos] = i0; hits.key[pos] = key; }
+                            else atomicAdd(hits.dropped, 1u);
+                        }
+                    }
                 }
             }
         }
+        i0 = i1; h0 = h1; i1 = i2;
     }
-    if (lane == 0 && visited) atomicAdd(work_row, visited);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) visited += __shfl_down_sync(0xFFFFFFFFu, visited, d);
+    if (lane_id() == 0 && visited) atomicAdd(work_row, visited);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(work_row + 1, (unsigned long long)n_trans);
 }
 
@@ -635,11 +658,13 @@ int cvb::edge_pass_impl(cvb_sim* s, int32_t t, cudaStream_t st, bool from_entrie
         const int grid = 148 * 8;
         // lanes per transmitter from the mean local row length (entries per agent slot, both directions)
         const double mean_row = (double)s->padj_entries / (double)(s->n_global > 0 ? s->n_global : 1);
-#define CVB_PART(M, LN) edge_pass_partition_kernel<M, LN><<<grid, kThreads, 0, st>>>(s->rec, ep, s->pars, s->padj_ptr, s->padj, s->glist, s->n_glist, \
-                                                                                    s->codes_global, s->rel_trans_global, s->infect_key, hits, work_row)
-        if (mean_row >= 24.0) { if (multi) CVB_PART(true, 32); else CVB_PART(false, 32); }
-        else if (mean_row >= 12.0) { if (multi) CVB_PART(true, 16); else CVB_PART(false, 16); }
-        else { if (multi) CVB_PART(true, 8); else CVB_PART(false, 8); }
+#define CVB_PART(M, G, U) edge_pass_partition_kernel<M, G, U><<<grid, kThreads, 0, st>>>(s->rec, ep, s->pars.trans_redux, s->padj_ptr, s->padj, s->glist, s->n_glist, \
+                                                                                      s->codes_global, s->rel_trans_global, s->infect_key, hits, work_row)
+        const int shape = s->tune[4];
+        if (shape == 1 || (!shape && mean_row >= 24.0)) { if (multi) CVB_PART(true, 16, 4); else CVB_PART(false, 16, 4); }
+        else if (shape == 2 || (!shape && mean_row >= 12.0)) { if (multi) CVB_PART(true, 16, 2); else CVB_PART(false, 16, 2); }
+        else if (shape == 3 || (!shape && mean_row >= 6.0)) { if (multi) CVB_PART(true, 8, 2); else CVB_PART(false, 8, 2); }
+        else { if (multi) CVB_PART(true, 4, 2); else CVB_PART(false, 4, 2); }
 #undef CVB_PART
         CVB_LAUNCH_CHECK();
         return 0;

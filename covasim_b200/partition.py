@@ -118,6 +118,79 @@ class DistComm:
         self.dist.all_gather_object(out, obj, group=self.group)
         return out
 
+    def peer_exchange(self, device, sections):
+        '''
+        A PeerExchange over this group, or None when peer memory is not available (another backend, several nodes, a driver / container
+        that does not allow the handle exchange) or switched off (COVASIM_B200_PEER_EXCHANGE=0): every rank must succeed, else all fall
+        back to the library all-gather.
+        '''
+        import os
+        ex, err = None, None
+        if os.environ.get('COVASIM_B200_PEER_EXCHANGE', '1') != '0' and self.world <= 16 and self.dist.get_backend(self.group) == 'nccl':
+            try:
+                ex = PeerExchange(self, device, sections)
+            except Exception as e:          # noqa: BLE001 -- any failure means "not available here"
+                err = f'{type(e).__name__}: {e}'
+        ok = self.gather_objects(ex is not None)
+        if not all(ok):
+            if ex is not None or err:
+                import warnings
+                warnings.warn(f'peer-memory exchange not available on every rank ({err or "another rank failed"}); using ncclAllGather')
+            return None
+        return ex
+
+
+class PeerExchange:
+    '''
+    The per-day exchanges of a partitioned run over PEER MEMORY instead of a library collective: the ranks of one NVLink / NVSwitch node
+    map one exchange buffer each into every other rank's address space (torch symmetric memory), every rank stores its chunk straight
+    into all of them (one kernel, cvb_peer_push: the remote stores travel over NVLink) and a signal barrier separates the stores from the
+    reads.  Two buffers per exchange alternate, so one barrier per exchange suffices: the buffer a rank overwrites at exchange k + 2 was
+    last read before that rank's peers entered the barrier of exchange k + 1.  ``sections`` maps a name to the bytes one rank contributes.
+    Measured on 4 B200s, 2 MB per rank: ncclAllGather 50 us (LL128: 29 us) -- profiles/allgather_micro.py; this exchange: see
+    profiles/r2/README.md.
+    '''
+
+    def __init__(self, comm, device, sections, timeout_ms=60000):
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm
+        self.comm, self.world, self.rank = comm, comm.world, comm.rank
+        self.timeout_ms = int(timeout_ms)
+        self.offsets, self.sizes, self.parity = {}, {}, {}
+        total = 0
+        for name, nbytes in sections.items():
+            span = (self.world * int(nbytes) + 255) // 256 * 256
+            self.offsets[name] = (total, total + span)
+            self.sizes[name] = int(nbytes)
+            self.parity[name] = 0
+            total += 2 * span
+        group = comm.group if comm.group is not None else comm.dist.group.WORLD
+        self.buf = symm.empty(total, dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        if len(ptrs) != self.world or not all(ptrs):
+            raise RuntimeError('symmetric memory rendezvous returned no peer pointers')
+        self.ptrs = (C.c_uint64 * self.world)(*ptrs)
+        self.buf.zero_()
+        self.hdl.barrier(channel=0, timeout_ms=self.timeout_ms)
+
+    def all_gather(self, name, inp, stream_ptr=None):
+        ''' Every rank's ``inp`` side by side in rank order; returns the device address of the filled buffer on this rank '''
+        from . import _capi
+        half = self.parity[name]
+        self.parity[name] = half ^ 1
+        nbytes = self.sizes[name]
+        if inp.numel() * inp.element_size() != nbytes:
+            raise ValueError(f'exchange "{name}" was sized for {nbytes} bytes per rank, got {inp.numel() * inp.element_size()}')
+        off = self.offsets[name][half]
+        _capi.call('cvb_peer_push', inp.data_ptr(), nbytes, self.ptrs, self.world, off + self.rank * nbytes, stream_ptr)
+        self.hdl.barrier(channel=0, timeout_ms=self.timeout_ms)
+        return self.buf.data_ptr() + off
+
+    def view(self, name, half, dtype):
+        off, n = self.offsets[name][half], self.world * self.sizes[name]
+        return self.buf[off:off + n].view(dtype)
+
 
 class _LocalShared:
     def __init__(self, world):

@@ -130,6 +130,7 @@ class Sim:
         self._keyed_pop = None
         self._partition = partition
         self._comm = None
+        self._peer = None
         self._hit_capacity = int(hit_capacity)
         self._part_bufs = None
         if partition is not None and partition is not False and rng != 'philox':
@@ -257,7 +258,7 @@ class Sim:
         return copy.deepcopy(self)
 
     _NO_COPY = ('_handle', '_adj', '_beds', '_part_bufs', '_copy_stream', '_edges_event', '_plan', '_cpars', '_counters', '_vcounters', '_sums', '_log',
-                '_stream_ptr', '_comm', '_keyed_pop')
+                '_stream_ptr', '_comm', '_keyed_pop', '_peer')
 
     def __deepcopy__(self, memo):
         if self._comm is not None:
@@ -587,6 +588,7 @@ class Sim:
         B = dict(codes_local=torch.zeros(chunk, dtype=torch.uint8, device=dev), codes_global=torch.zeros(n_slots, dtype=torch.uint8, device=dev),
                  case_local=torch.zeros(chunk // 32, dtype=torch.int32, device=dev), case_global=torch.zeros(n_slots // 32, dtype=torch.int32, device=dev))
         self._part_bufs = B
+        self._peer = comm.peer_exchange(dev, dict(codes=chunk, cases=chunk // 8)) if hasattr(comm, 'peer_exchange') else None
         _capi.call('cvb_set_partition', self._handle, self.id0, self.n, chunk, comm.world, self.people.rel_trans_global.data_ptr(),
                    B['codes_local'].data_ptr(), B['codes_global'].data_ptr(), B['case_local'].data_ptr(), B['case_global'].data_ptr(),
                    self._hit_capacity)
@@ -624,13 +626,18 @@ class Sim:
 
     def _timed_collective(self, name, out, inp):
         timers = self.kernel_timers if self.kernel_timers is not None else getattr(self, 'collective_timers', None)
-        if timers is None:
-            return self._comm.all_gather(out, inp)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        self._comm.all_gather(out, inp)
-        b.record()
-        timers.setdefault(name, []).append((a, b))
+        if timers is not None:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        if self._peer is not None:         # stores into every rank's buffer over NVLink + a signal barrier (partition.PeerExchange)
+            which = 'codes' if name == 'allgather_codes' else 'cases'
+            ptr = self._peer.all_gather(which, inp, self._stream_ptr)
+            _capi.call('cvb_set_exchange_buffers', self._handle, ptr if which == 'codes' else None, ptr if which == 'cases' else None)
+        else:
+            self._comm.all_gather(out, inp)
+        if timers is not None:
+            b.record()
+            timers.setdefault(name, []).append((a, b))
 
     def _choose_true(self, key, stream, k):
         '''

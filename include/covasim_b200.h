@@ -116,6 +116,12 @@ int cvb_bind_adjacency(cvb_sim* s, const int64_t* adj_ptr, const void* adj, int6
 int cvb_set_partition(cvb_sim* s, int64_t id0, int64_t n_global, int64_t chunk, int32_t world, const float* rel_trans_global,
                       uint8_t* codes_local, const uint8_t* codes_global, uint32_t* case_bits_local, const uint32_t* case_bits_global,
                       int64_t hit_capacity);
+/* Exchange over peer memory instead of a library all-gather (ranks of one NVLink / NVSwitch node whose exchange buffers are mapped into
+ * each other's address space, e.g. torch symmetric memory): store `n_bytes` of `src` at `dst_offset_bytes` of every rank's buffer
+ * (host_peer_ptrs[world] device addresses as seen from THIS rank, own buffer included).  The caller separates pushes from reads with a
+ * cross-rank barrier and alternates between two buffers, then points the handle at the one just filled. */
+int cvb_peer_push(const void* src, int64_t n_bytes, const uint64_t* host_peer_ptrs, int32_t world, int64_t dst_offset_bytes, cvb_stream st);
+int cvb_set_exchange_buffers(cvb_sim* s, const uint8_t* codes_global /* or NULL: unchanged */, const uint32_t* case_bits_global /* or NULL */);
 /* Adjacency of a partitioned handle: rows adj_ptr[0 .. world*chunk] are indexed by the GLOBAL id of the source; the
  * 16-byte entries are those of cvb_bind_adjacency with `neighbour` = LOCAL index of the target */
 int cvb_bind_partition_adjacency(cvb_sim* s, const int64_t* adj_ptr, const void* adj, int64_t n_entries, uint32_t layer_mask);

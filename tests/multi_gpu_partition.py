@@ -61,7 +61,7 @@ def main():
             want = ref.infection_log
             for k in ('source', 'target', 'date', 'layer', 'variant'):
                 assert np.array_equal(log[k], want[k]), f'{name}: infection log {k} differs'
-            print(f'OK {name}: {world} ranks == single GPU (N={ref.n}, cum_infections={ref.summary["cum_infections"]:.0f}, partitioned run {el:.2f} s)', flush=True)
+            print(f'OK {name} [exchange: {"peer memory" if sim._peer is not None else "ncclAllGather"}]: {world} ranks == single GPU (N={ref.n}, cum_infections={ref.summary["cum_infections"]:.0f}, partitioned run {el:.2f} s)', flush=True)
         dist.barrier()
     dist.destroy_process_group()
 

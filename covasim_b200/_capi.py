@@ -91,6 +91,7 @@ PROTOTYPES = dict(
     cvb_bind_layer=[_P, _i32, _P, _P, _P, _i64],
     cvb_bind_adjacency=[_P, _P, _P, _i64, C.c_uint32],
     cvb_set_partition=[_P, _i64, _i64, _i64, _i32, _P, _P, _P, _P, _P, _i64],
+    cvb_restore_compact=[_P, _i64, _P, _i32, _i64, _P],
     cvb_peer_push=[_P, _i64, _P, _i32, _i64, _P],
     cvb_set_exchange_buffers=[_P, _P, _P],
     cvb_bind_partition_adjacency=[_P, _P, _P, _i64, C.c_uint32],

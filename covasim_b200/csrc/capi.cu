@@ -70,6 +70,23 @@ __global__ void __launch_bounds__(kThreads) peer_push_kernel(const V* __restrict
     }
 }
 
+// Compact restore of the People arena (Sim.restore of a compact snapshot): most per-agent arrays of a saved state are one value
+// almost everywhere (unset dates, cleared flags), so the snapshot keeps {segment, fill value} + the exceptions and only the
+// genuinely dense arrays travel over PCIe.  Segments are 32-bit words of the arena; blockIdx.y = segment.
+__global__ void __launch_bounds__(kThreads) fill_segments_kernel(uint32_t* __restrict__ words, const long long* __restrict__ seg) {
+    const long long begin = seg[3 * blockIdx.y], count = seg[3 * blockIdx.y + 1];
+    const uint32_t v = (uint32_t)seg[3 * blockIdx.y + 2];
+    uint32_t* p = words + begin;
+    const long long n4 = ((uintptr_t)p & 15) == 0 ? count / 4 : 0;
+    const uint4 v4 = make_uint4(v, v, v, v);
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x) reinterpret_cast<uint4*>(p)[k] = v4;
+    for (long long k = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; k < count; k += (long long)gridDim.x * blockDim.x) p[k] = v;
+}
+__global__ void __launch_bounds__(kThreads) scatter_words_kernel(uint32_t* __restrict__ words, const long long* __restrict__ idx,
+                                                                 const long long* __restrict__ val, int64_t n) {
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) words[idx[k]] = (uint32_t)val[k];
+}
+
 __global__ void fill_f32_kernel(float* p, int64_t n, float v) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -243,6 +260,22 @@ int cvb_bind_adjacency(cvb_sim* s, const int64_t* adj_ptr, const void* adj, int6
     CVB_REQUIRE(adj_ptr && adj, "cvb_bind_adjacency: NULL array");
     CVB_REQUIRE(((uintptr_t)adj & 15) == 0, "cvb_bind_adjacency: entries must be 16-byte aligned");
     s->adj_ptr = (const long long*)adj_ptr; s->adj = (const uint4*)adj; s->adj_entries = n_entries; s->adj_layer_mask = layer_mask;
+    return 0;
+}
+
+int cvb_restore_compact(void* arena, int64_t arena_bytes, const int64_t* dev_table, int32_t n_seg, int64_t n_exc, cvb_stream st) {
+    CVB_REQUIRE(arena && dev_table && n_seg >= 0 && n_exc >= 0 && ((uintptr_t)arena & 3) == 0 && arena_bytes % 4 == 0, "cvb_restore_compact: bad argument");
+    (void)arena_bytes;                                                 // (the table was built for this arena by the caller: sizes are checked there)
+    if (n_seg > 0) {
+        dim3 grid(148, (unsigned)n_seg);
+        cvb::fill_segments_kernel<<<grid, cvb::kThreads, 0, (cudaStream_t)st>>>((uint32_t*)arena, (const long long*)dev_table);
+        CVB_LAUNCH_CHECK();
+    }
+    if (n_exc > 0) {
+        const long long* idx = (const long long*)dev_table + 3 * (int64_t)n_seg;
+        cvb::scatter_words_kernel<<<cvb::grid_for(n_exc, cvb::kThreads, 148 * 4), cvb::kThreads, 0, (cudaStream_t)st>>>((uint32_t*)arena, idx, idx + n_exc, n_exc);
+        CVB_LAUNCH_CHECK();
+    }
     return 0;
 }
 

@@ -75,6 +75,23 @@ __global__ void __launch_bounds__(kThreads, CVB_INFECT_MINB) infect_kernel(Peopl
         const bool valid = j < n_cand;
         const int64_t i = valid ? __ldcg(cand + j) : 0;
         const int64_t gi = i + ia.id0;                             // global id: Philox index and logged target
+        // the leader's per-agent inputs are requested HERE, as soon as the agent is known, so that they travel while the winning key,
+        // the adjacency row and the draws are worked out (they used to start a second chain of memory round trips after all that)
+        const bool lead = valid && slot == 0;
+        bool is_sus = false;
+        float in_peak = 0.0f, in_nab = 0.0f, in_rel_trans = 0.0f, in_drec = 0.0f, in_symp_prob = 0.0f, in_sev_prob = 0.0f, in_crit_prob = 0.0f, in_death_prob = 0.0f;
+        int in_nbreak = 0, in_ninf = 0;
+        uint32_t so = 0u;
+        unsigned long long log_base_v = 0ull;
+        if (lead) {
+            is_sus = PB(P, susceptible)[i] != 0;
+            in_peak = PF(P, peak_nab)[i]; in_nab = PF(P, nab)[i]; in_rel_trans = PF(P, rel_trans)[i];
+            in_nbreak = PI(P, n_breakthroughs)[i]; in_ninf = PI(P, n_infections)[i];
+            in_drec = PF(P, date_recovered)[i];
+            in_symp_prob = PF(P, symp_prob)[i]; in_sev_prob = PF(P, severe_prob)[i]; in_crit_prob = PF(P, crit_prob)[i]; in_death_prob = PF(P, death_prob)[i];
+            if (S) so = S[i];
+            if (ia.log_base) log_base_v = __ldcg(ia.log_base);
+        }
         // who infected i: the winning key names (layer, edge, direction); i's adjacency row holds that edge with the other
         // direction bit and the source as the neighbour.  The 16 lanes scan the row while the draws below are computed.
         int32_t src_adj = -1;
@@ -127,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, CVB_INFECT_MINB) infect_kernel(Peopl
         const double x_crit2rec = __shfl_sync(0xFFFFFFFFu, d0, base + 8), x_crit2die = __shfl_sync(0xFFFFFFFFu, d1, base + 8);
         const double x_nab = __shfl_sync(0xFFFFFFFFu, d0, base + 9);
         if (slot != 0 || !valid) continue;                         // the half-warp's leader applies the infection
-        const unsigned long long dense_pos = ia.log_base ? __ldcg(ia.log_base) + j : 0ull;
+        const unsigned long long dense_pos = ia.log_base ? log_base_v + j : 0ull;
         if (ia.log_base && (int64_t)dense_pos < log.cap) log.target[dense_pos] = -1;       // tombstone unless the infection happens
         unsigned long long key;
         if (ia.hit_key) {                                          // one entry per hit: only the winning one proceeds
@@ -151,14 +168,7 @@ __global__ void __launch_bounds__(kThreads, CVB_INFECT_MINB) infect_kernel(Peopl
             else source = dir == 0 ? L.l[lfield].p1[e] : L.l[lfield].p2[e];
             layer_code = lfield;
         }
-        // every per-agent input is loaded here, before the first store, so the loads are independent and in flight
-        // together (the stores below may alias them as far as the compiler knows)
-        const bool is_sus = PB(P, susceptible)[i] != 0;
-        const float in_peak = PF(P, peak_nab)[i], in_nab = PF(P, nab)[i], in_rel_trans = PF(P, rel_trans)[i];
-        const int in_nbreak = PI(P, n_breakthroughs)[i], in_ninf = PI(P, n_infections)[i];
-        const float in_drec = PF(P, date_recovered)[i];
-        const float in_symp_prob = PF(P, symp_prob)[i], in_sev_prob = PF(P, severe_prob)[i], in_crit_prob = PF(P, crit_prob)[i],
-                    in_death_prob = PF(P, death_prob)[i];
+        // (the variant is known only now: the two protection values are the one late gather)
         const float in_symp_imm = PF(P, symp_imm)[(int64_t)v * n + i], in_sev_imm = PF(P, sev_imm)[(int64_t)v * n + i];
         if (!is_sus) continue;                                     // people.py:470-473
 
@@ -269,7 +279,6 @@ __global__ void __launch_bounds__(kThreads, CVB_INFECT_MINB) infect_kernel(Peopl
         if (S) {
             // the packed state word follows (bit layout: day_fused.cu): not susceptible / naive / recovered / diagnosed any more, no
             // diagnosis date, exposed to variant v, no natural-immunity source until recovery; antibodies from now on if waning
-            const uint32_t so = S[i];
             uint32_t sk = so & ~(SB_SUS | SB_NAIVE | SB_REC | SB_DIAG | SB_DPEND | kEbvMask | kRvMask);
             sk |= SB_EXP | ((uint32_t)(v + 1) << kEbvShift);
             if (pars.use_waning) sk |= SB_HAS_NAB;

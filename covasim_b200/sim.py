@@ -258,7 +258,7 @@ class Sim:
         return copy.deepcopy(self)
 
     _NO_COPY = ('_handle', '_adj', '_beds', '_part_bufs', '_copy_stream', '_edges_event', '_plan', '_cpars', '_counters', '_vcounters', '_sums', '_log',
-                '_stream_ptr', '_comm', '_keyed_pop', '_peer')
+                '_stream_ptr', '_comm', '_keyed_pop', '_peer', '_compact_table')
 
     def __deepcopy__(self, memo):
         if self._comm is not None:
@@ -717,12 +717,14 @@ class Sim:
     # ---- checkpoint / restore (reference base.py:682-741 Sim.save/load, sim.py:688-761 resume) ----------
     _IV_HOST_TYPES = (set, dict, list, tuple, int, float, bool, str, type(None), np.ndarray, np.integer, np.floating)
 
-    def snapshot(self, pinned=True):
+    def snapshot(self, pinned=True, compact=None):
         '''
         Host copy of everything a run mutates: the People arena (every per-agent array, one buffer), every layer's edge list, the
         RNG streams, the clock, the result tables, the rescale vector, and the state interventions keep (device arrays and host
         bookkeeping such as pending second doses or the edges clip_edges holds back).  With ``pinned=True`` the buffers are
-        page-locked so ``restore`` is one asynchronous H2D copy for the People and one per edge array.
+        page-locked so ``restore`` is one asynchronous H2D copy for the People and one per edge array.  ``compact`` (default: with
+        pinned buffers) also keeps the arena in compact form -- per array either "one value + exceptions" or dense -- which is what
+        ``restore`` then sends: at day 0 of the 1M-agent benchmark sim 33 of 202 bytes per agent are dense.
         '''
         self._sync_edges()
         torch.cuda.synchronize(self.device)
@@ -752,7 +754,55 @@ class Sim:
                     pars={k: copy.deepcopy(v) for k, v in self.pars.items() if k not in ('interventions', 'analyzers', 'variants', 'prognoses', 'nab_kin')},
                     iv=iv_dev, iv_host=iv_host, iv_layers=iv_layers, quar_horizon=self._quar_horizon)
         torch.cuda.synchronize(self.device)
+        if pinned if compact is None else compact:
+            snap['arena_compact'] = self._compact_arena(snap['arena'], pinned)
         return snap
+
+    def _compact_arena(self, arena_host, pinned=True):
+        '''
+        The saved arena as {fill segments + exceptions, dense runs}: per array, the most common 32-bit word and the words that
+        differ from it if those are few (8 + 8 bytes each against 4 bytes per word of a dense copy), else the array as it is.
+        '''
+        words = arena_host.numpy().view(np.uint32)
+        segs, exc_idx, exc_val, dense = [], [], [], []
+        for name, dt, shape, off, nbytes in self.people._layout:
+            w0, w1 = off // 4, (off + nbytes + 3) // 4
+            fw = words[w0:w1]
+            if len(fw) == 0:
+                continue
+            vals, counts = np.unique(fw[::max(1, len(fw) // 4096)], return_counts=True)
+            v = vals[np.argmax(counts)]
+            idx = np.flatnonzero(fw != v)
+            if len(idx) * 16 <= len(fw):                    # at most a quarter of the dense bytes
+                segs.append((w0, w1 - w0, int(v)))
+                exc_idx.append(idx.astype(np.int64) + w0)
+                exc_val.append(fw[idx].astype(np.int64))
+            elif dense and dense[-1][1] + 256 >= off:        # next to the previous dense array (only alignment padding between)
+                dense[-1] = (dense[-1][0], (w1 * 4 + 255) // 256 * 256)
+            else:
+                dense.append((off, (w1 * 4 + 255) // 256 * 256))
+        n_exc = int(sum(len(i) for i in exc_idx))
+        table = np.concatenate([np.asarray(segs, dtype=np.int64).reshape(-1), *exc_idx, *exc_val]) if (segs or n_exc) else np.zeros(0, dtype=np.int64)
+        t = torch.empty(max(len(table), 1), dtype=torch.int64, pin_memory=pinned)
+        t[:len(table)] = torch.from_numpy(table)
+        total = arena_host.numel()
+        dense = [(a, min(b, total)) for a, b in dense]
+        return dict(table=t, n_seg=len(segs), n_exc=n_exc, dense=dense, arena_bytes=total,
+                    h2d_bytes=int(len(table) * 8 + sum(b - a for a, b in dense)))
+
+    def _restore_arena(self, snap):
+        ''' The People arena of a snapshot back on the device: compact form if the snapshot has one (one small table + the dense arrays), else one copy '''
+        arena, c = self.people._arena, snap.get('arena_compact')
+        if c is None or c['arena_bytes'] != arena.numel():
+            arena.copy_(snap['arena'], non_blocking=True)
+            return
+        dev = getattr(self, '_compact_table', None)
+        if dev is None or dev.numel() < c['table'].numel():
+            dev = self._compact_table = torch.empty(c['table'].numel(), dtype=torch.int64, device=self.device)
+        dev[:c['table'].numel()].copy_(c['table'], non_blocking=True)
+        _capi.call('cvb_restore_compact', arena.data_ptr(), arena.numel(), dev.data_ptr(), c['n_seg'], c['n_exc'], self._stream_ptr)
+        for a, b in c['dense']:
+            arena[a:b].copy_(snap['arena'][a:b], non_blocking=True)
 
     def restore_light(self, snap):
         ''' restore() without the People / Layer copies: for callers that rewound those arrays on the device themselves '''
@@ -777,7 +827,7 @@ class Sim:
             torch.cuda.set_device(self.device)
         if arrays:
             self._sync_edges()
-            self.people._arena.copy_(snap['arena'], non_blocking=True)
+            self._restore_arena(snap)
             cur = torch.cuda.current_stream(self.device)
             if getattr(self, '_copy_stream', None) is None:
                 self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -840,7 +890,7 @@ class Sim:
 
     def h2d_bytes(self, snap):
         ''' Bytes restore() copies host -> device '''
-        n = snap['arena'].numel() * snap['arena'].element_size()
+        n = snap['arena_compact']['h2d_bytes'] if snap.get('arena_compact') is not None else snap['arena'].numel() * snap['arena'].element_size()
         n += sum(h.numel() * h.element_size() for cols in snap['layers'].values() for h in cols.values())
         n += sum(snap[k].numel() * snap[k].element_size() for k in ('counters', 'vcounters', 'sums', 'log_count'))
         n += sum(h.numel() * h.element_size() for saved in snap['iv'] for h in saved.values())

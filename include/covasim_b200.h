@@ -188,6 +188,11 @@ int cvb_set_quar_horizon(cvb_sim* s, int32_t horizon);
 /* base.py:444-446 Sim.copy of a running simulation: the library-owned per-run state of `src` (pending quarantine requests, bed counts, edge-work
  * counters) copied into `dst`, a handle of the same shape whose arrays the caller has already bound */
 int cvb_clone_scratch(cvb_sim* dst, const cvb_sim* src, cvb_stream st);
+/* Compact restore of a saved People state (base.py:444-446 Sim.copy / the caller's own checkpoints): `arena` is the caller's device
+ * buffer holding every per-agent array; dev_table (device int64) = n_seg x {first 32-bit word, word count, fill value} followed by
+ * n_exc word indices and n_exc values.  Every segment is filled with its value, then the exceptions are written; arrays that are
+ * dense in the saved state are copied by the caller.  Bit-identical to copying the whole buffer. */
+int cvb_restore_compact(void* arena, int64_t arena_bytes, const int64_t* dev_table, int32_t n_seg, int64_t n_exc, cvb_stream st);
 /* immunity.py:298 pars['nab_kin']: per-day NAb increments (host float64[n]) */
 int cvb_set_nab_kin(cvb_sim* s, const double* host_kin, int64_t n);
 /* people.py:189-196 update_states_post (check_diagnosed, check_quar, check_enter_iso) */

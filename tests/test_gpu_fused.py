@@ -196,3 +196,35 @@ def test_layer_update_with_a_fraction(cv):
     full.people.contacts['a'].update(full.people)                      # an edge gets the same endpoints in a partial and a full regeneration
     f = full.people.contacts['a'].to_numpy()
     assert np.array_equal(f['p1'][touched], after['p1'][touched]) and np.array_equal(f['p2'][touched], after['p2'][touched])
+
+
+@pytest.mark.parametrize('day', [0, 22])
+def test_compact_snapshot_restores_every_byte(cv, day):
+    '''
+    Sim.snapshot keeps the People arena in compact form too (per array: one value + exceptions, or dense) and Sim.restore sends
+    that (cvb_restore_compact + the dense arrays): every array must come back exactly as a plain copy of the arena would leave it,
+    at day 0 (almost everything is one value) and in the middle of an epidemic with vaccination (many dense arrays).
+    '''
+    import torch
+    spec = scenarios.SCENARIOS['baseline20k']
+    sim = cv.Sim(**scenarios.build(cv, spec))
+    sim.initialize()
+    if day:
+        sim.run(until=day)
+    snap = sim.snapshot(pinned=True)
+    c = snap['arena_compact']
+    assert c['n_seg'] > 20 and c['h2d_bytes'] < 0.6 * snap['arena'].numel()
+    want = {k: sim.people.to_numpy(k).copy() for k in sim.people.keys()}
+    sim.run(until=day + 15, reset_seed=False)
+    sim.people._arena.fill_(0x5A)                                   # nothing may survive from the state being replaced
+    sim.restore(snap)
+    torch.cuda.synchronize()
+    for k, w in want.items():
+        got = sim.people.to_numpy(k)
+        assert np.array_equal(got, w, equal_nan=(w.dtype.kind == 'f')), f'day {day}: {k} differs after a compact restore'
+    plain = dict(snap)
+    del plain['arena_compact']
+    a = sim.run().summary
+    sim.restore(plain)
+    b = sim.run().summary
+    assert all(a[k] == b[k] or (a[k] != a[k] and b[k] != b[k]) for k in a), 'compact and plain restore lead to different runs'

@@ -286,6 +286,179 @@ __global__ void __launch_bounds__(THREADS) edge_pass_kernel(const __grid_constan
     }
 }
 
+// ---- dense streaming form, tiles staged by the TMA engine ------------------------------------------------------------------
+// Same pass as edge_pass_kernel, with the edge tiles moved HBM -> shared memory by bulk asynchronous copies (cp.async.bulk,
+// completion on an mbarrier) instead of register-held 128-bit loads.  Every warp owns a private ring of NS stages of
+// {p1, p2, beta} x 32 quads (1.5 KB): its lane 0 issues the three copies of a stage, all lanes wait on the stage's mbarrier, pull
+// their quad into registers, and lane 0 immediately refills the stage with the warp's tile NS iterations ahead -- so NS - 1 stages
+// per warp are in flight for the whole kernel, they cost no registers and no issue slots of the filtering code, and no warp ever
+// waits for another (a first version with CTA-wide stages and a producer warp was gated by its slowest warp: 72 us against 56).
+// MEASURED (profiles/r2/README.md, "dense pass with bulk-copy staging"): at C2 this form takes 74 us (20 warps x 2 stages; 89 us with
+// 16 x 3, 101 us with 12 x 4) against 56 us for edge_pass_kernel<512 threads x 2 quads>.  The time follows the number of filtering
+// warps, not the stages in flight: next to the 125 KB transmit bitmap shared memory holds at most ~20 warps' queues and stages, each
+// warp filters one quad per wait instead of two, and the copies are issued by a lane of the filtering warps.  The pass is bound by
+// the issue / latency chain of the filter and the drain (bit tests, ballots, Philox for the ~20 % live edges), not by bytes in
+// flight, so the register-staged kernel stays the default; this one is selectable with CVB_DENSE_VARIANT=3.
+// Layout of dynamic shared memory:
+//   [mbarriers: CW x NS] [per-warp queues: CW x kQueueCapT uint4] [stages: CW x NS x 3 x 32 x 16 B] [transmit bitmap]
+constexpr int kQueueCapT = 96;            // < 32 left over + 64 appended between two drains (a drain after every two edges of a quad)
+constexpr int kMaxStages = 4;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const uint32_t a = smem_addr(bar);
+    const long long t0 = clock64();
+    for (unsigned spins = 0;; ++spins) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+        if ((spins & 1023u) == 1023u && clock64() - t0 > 4000000000ll) __trap();      // ~2 s: a lost completion must not hang the GPU
+    }
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+
+template <bool MULTI, int CW>
+__global__ void __launch_bounds__(CW * 32) edge_pass_tma_kernel(const __grid_constant__ LayerTable L, TransRecords rec,
+        const __grid_constant__ EdgeParams ep, const unsigned int* __restrict__ inf_bits, unsigned long long* __restrict__ infect_key,
+        int32_t* __restrict__ cand, unsigned int* __restrict__ n_cand, int n_stages) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int TQ = CW * 32;                                       // quads per CTA tile: one per lane
+    constexpr unsigned kStageBytes = 3u * 32u * 16u;                  // one warp's share of a tile
+    constexpr size_t kBarBytes = ((size_t)CW * kMaxStages * 8 + 127) / 128 * 128;
+    const int warp = warp_id(), lane = lane_id();
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw) + warp * kMaxStages;
+    uint4* q_edge = reinterpret_cast<uint4*>(smem_raw + kBarBytes) + warp * kQueueCapT;
+    unsigned char* stage_base = smem_raw + kBarBytes + (size_t)CW * kQueueCapT * sizeof(uint4);
+    unsigned char* stages = stage_base + (size_t)warp * n_stages * kStageBytes;
+    unsigned int* s_bits = reinterpret_cast<unsigned int*>(stage_base + (size_t)CW * n_stages * kStageBytes);
+    if (lane == 0) for (int k = 0; k < n_stages; ++k) mbar_init(full + k, 1u);
+    if (threadIdx.x == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    {
+        const int64_t n4 = ep.n_words >> 2;
+        for (int64_t wd = threadIdx.x; wd < n4; wd += blockDim.x) reinterpret_cast<uint4*>(s_bits)[wd] = __ldg(reinterpret_cast<const uint4*>(inf_bits) + wd);
+        for (int64_t wd = (n4 << 2) + threadIdx.x; wd < ep.n_words; wd += blockDim.x) s_bits[wd] = inf_bits[wd];
+    }
+    __syncthreads();
+    const unsigned int* bits = s_bits;
+    const unsigned grid = gridDim.x;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    // the warp's tile sequence over all layers, walked twice: by the issuing side (NS ahead) and by the consuming side
+    struct Cursor { int entry; unsigned tile, n_full; };
+    auto open_layer = [&](Cursor& c) {                                // first full tile of layer c.entry for this CTA, or move on
+        for (; c.entry < L.n_layers; ++c.entry) {
+            c.n_full = (unsigned)(L.l[c.entry].n_edges / (TQ * 4));
+            const unsigned rot = (unsigned)(L.tile_start[c.entry] % grid);
+            c.tile = (blockIdx.x + grid - rot) % grid;
+            if (c.tile < c.n_full) return;
+        }
+    };
+    auto issue = [&](Cursor& c, unsigned it) {                        // lane 0: the copies of the tile under the cursor, then advance it
+        if (c.entry >= L.n_layers) return;
+        const unsigned sidx = it % (unsigned)n_stages;
+        unsigned char* dst = stages + (size_t)sidx * kStageBytes;
+        const size_t off = ((size_t)c.tile * TQ + (size_t)warp * 32) * 16;
+        mbar_arrive_expect_tx(full + sidx, kStageBytes);
+        bulk_copy_g2s(dst, reinterpret_cast<const unsigned char*>(L.l[c.entry].p1) + off, 512u, full + sidx);
+        bulk_copy_g2s(dst + 512, reinterpret_cast<const unsigned char*>(L.l[c.entry].p2) + off, 512u, full + sidx);
+        bulk_copy_g2s(dst + 1024, reinterpret_cast<const unsigned char*>(L.l[c.entry].beta) + off, 512u, full + sidx);
+        c.tile += grid;
+        if (c.tile >= c.n_full) { ++c.entry; open_layer(c); }
+    };
+    Cursor ahead{0, 0u, 0u};
+    unsigned it_issue = 0;
+    if (lane == 0) {
+        open_layer(ahead);
+        for (; it_issue < (unsigned)n_stages; ++it_issue) issue(ahead, it_issue);
+    }
+
+    unsigned it = 0;
+    for (int entry = 0; entry < L.n_layers; ++entry) {
+        const int32_t* __restrict__ p1 = L.l[entry].p1;
+        const int32_t* __restrict__ p2 = L.l[entry].p2;
+        const float* __restrict__ beta = L.l[entry].beta;
+        const int64_t n_edges = L.l[entry].n_edges;
+        const int l = L.layer_id[entry];
+        const unsigned n_full = (unsigned)(n_edges / (TQ * 4));
+        const unsigned rot = (unsigned)(L.tile_start[entry] % grid);
+        const unsigned first = (blockIdx.x + grid - rot) % grid;
+        int qn = 0;                                                   // warp-uniform queue length
+        bool pend = false;                                            // deferred drain, as in edge_pass_kernel
+        uint4 pc = make_uint4(0u, 0u, 0u, 0u);
+        typename RecType<MULTI>::type pra = {}, prb = {};
+
+        auto drain = [&]() {
+            while (qn >= 32) {
+                qn -= 32;
+                const uint4 c = q_edge[qn + lane];
+                __syncwarp();
+                typename RecType<MULTI>::type ra, rb;
+                gather_records(rec, ep.n, l, (int)c.x, (int)c.y, ra, rb);
+                if (pend) finish_edge<MULTI>(rec, ep, (int)pc.x, (int)pc.y, __uint_as_float(pc.z), l, (int64_t)pc.w, pra, prb, infect_key, cand, n_cand);
+                pc = c; pra = ra; prb = rb; pend = true;
+            }
+        };
+        auto filter_quad = [&](const EdgeQuad& Q, unsigned qq) {
+            const int a[4] = {Q.a.x, Q.a.y, Q.a.z, Q.a.w}, b[4] = {Q.b.x, Q.b.y, Q.b.z, Q.b.w};
+            const float w[4] = {Q.w.x, Q.w.y, Q.w.z, Q.w.w};
+            unsigned wa[4], wb[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { wa[k] = bits[a[k] >> 5]; wb[k] = bits[b[k] >> 5]; }
+            const unsigned e_base = qq * 4u;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const bool keep = ((endpoint_bit(wa[k], a[k]) | endpoint_bit(wb[k], b[k])) & 1u) != 0 && k < Q.cnt;
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, keep);
+                if (keep) q_edge[qn + __popc(m & lt_mask)] = make_uint4((unsigned)a[k], (unsigned)b[k], __float_as_uint(w[k]), e_base + (unsigned)k);
+                qn += __popc(m);
+                if (k & 1) { __syncwarp(); drain(); __syncwarp(); }
+            }
+        };
+
+        for (unsigned tile = first; tile < n_full; tile += grid, ++it) {
+            const unsigned sidx = it % (unsigned)n_stages, use = it / (unsigned)n_stages;
+            mbar_wait(full + sidx, use & 1u);
+            const uint4* st4 = reinterpret_cast<const uint4*>(stages + (size_t)sidx * kStageBytes);
+            EdgeQuad Q;
+            const uint4 va = st4[lane], vb = st4[32 + lane], vw = st4[64 + lane];
+            Q.a = make_int4((int)va.x, (int)va.y, (int)va.z, (int)va.w);
+            Q.b = make_int4((int)vb.x, (int)vb.y, (int)vb.z, (int)vb.w);
+            Q.w = make_float4(__uint_as_float(vw.x), __uint_as_float(vw.y), __uint_as_float(vw.z), __uint_as_float(vw.w));
+            Q.cnt = 4;
+            __syncwarp();                                             // every lane has its quad: the stage can be refilled
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue(ahead, it_issue);
+                ++it_issue;
+            }
+            filter_quad(Q, tile * (unsigned)TQ + (unsigned)(warp * 32 + lane));
+        }
+        // the layer's ragged last tile (fewer than TQ quads): straight from global memory, by the CTA whose turn it is
+        if ((int64_t)n_full * (TQ * 4) < n_edges && n_full % grid == first) {
+            const unsigned qq = n_full * (unsigned)TQ + (unsigned)(warp * 32 + lane);
+            EdgeQuad Q;
+            load_quad(p1, p2, beta, n_edges, qq, Q);
+            filter_quad(Q, qq);
+        }
+        if (pend) finish_edge<MULTI>(rec, ep, (int)pc.x, (int)pc.y, __uint_as_float(pc.z), l, (int64_t)pc.w, pra, prb, infect_key, cand, n_cand);
+        if (lane < qn) {                                              // leftovers of this layer
+            const uint4 c = q_edge[lane];
+            process_edge<MULTI>(rec, ep, (int)c.x, (int)c.y, __uint_as_float(c.z), l, (int64_t)c.w, infect_key, cand, n_cand);
+        }
+        __syncwarp();
+    }
+}
+
 // ---- sparse form: only the edges of today's transmitters, through the bidirectional adjacency ----------
 // One warp per transmitter; lanes stride over its adjacency range (all static layers, both directions:
 // ~36 entries of 16 bytes per agent in a hybrid population, contiguous).  Same probability chain, same
@@ -571,6 +744,37 @@ __global__ void __launch_bounds__(kThreads) edge_pass_partition_kernel(TransReco
 
 int build_layer_table(cvb_sim* s, LayerTable& L, int tile_edges, uint32_t skip_mask);
 
+// the TMA-staged form; returns -1 if it does not apply (bitmap + two stages per warp do not fit shared memory, unaligned arrays)
+template <bool MULTI, int CW>
+static int launch_edge_pass_tma(cvb_sim* s, uint32_t skip_mask, const EdgeParams& ep, size_t bitmap_bytes, cudaStream_t st, int max_stages) {
+    constexpr size_t stage = (size_t)CW * 3u * 32u * 16u;             // one stage of every warp
+    const size_t fixed = ((size_t)CW * kMaxStages * 8 + 127) / 128 * 128 + (size_t)CW * kQueueCapT * sizeof(uint4) + ((bitmap_bytes + 15) / 16) * 16;
+    const size_t limit = 227 * 1024;
+    if (fixed + 2 * stage > limit) return -1;
+    int n_stages = (int)((limit - fixed) / stage);
+    if (n_stages > max_stages) n_stages = max_stages;
+    LayerTable L;
+    if (build_layer_table(s, L, CW * 32 * kEdgesPerThread, skip_mask)) return 1;
+    const int64_t tiles = L.tile_start[L.n_layers];
+    if (tiles == 0) return 0;
+    for (int q = 0; q < L.n_layers; ++q)
+        if ((((uintptr_t)L.l[q].p1 | (uintptr_t)L.l[q].p2 | (uintptr_t)L.l[q].beta) & 15) != 0) return -1;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, s->device);
+    const int grid = (int)(tiles < n_sm ? tiles : n_sm);
+    auto kern = edge_pass_tma_kernel<MULTI, CW>;
+    static bool configured[64] = {false};
+    const int dev = s->device & 63;
+    if (!configured[dev]) {
+        CVB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured[dev] = true;
+    }
+    const size_t smem = fixed + (size_t)n_stages * stage;
+    kern<<<grid, CW * 32, smem, st>>>(L, s->rec, ep, s->inf_bits, s->infect_key, s->cand, s->n_cand, n_stages);
+    CVB_LAUNCH_CHECK();
+    return 0;
+}
+
 template <bool MULTI, bool SMEM_BITS, int THREADS, int QPT, int PF>
 static int launch_edge_pass(cvb_sim* s, uint32_t skip_mask, const EdgeParams& ep, size_t bitmap_bytes, int ctas_per_sm, cudaStream_t st) {
     auto kern = edge_pass_kernel<MULTI, SMEM_BITS, THREADS, QPT, PF>;
@@ -723,6 +927,10 @@ int cvb::edge_pass_impl(cvb_sim* s, int32_t t, cudaStream_t st, bool from_entrie
 #define CVB_DENSE(THREADS, QPT, SMEM, CTAS, PF) \
     return multi ? launch_edge_pass<true, SMEM, THREADS, QPT, PF>(s, skip_mask, ep, bitmap_bytes, CTAS, st) \
                  : launch_edge_pass<false, SMEM, THREADS, QPT, PF>(s, skip_mask, ep, bitmap_bytes, CTAS, st)
+    if (variant == 3) {                                               // tiles staged by bulk copies (cp.async.bulk + mbarrier): measured SLOWER, kept for profiling
+        const int rc = multi ? launch_edge_pass_tma<true, 20>(s, skip_mask, ep, bitmap_bytes, st, 2) : launch_edge_pass_tma<false, 20>(s, skip_mask, ep, bitmap_bytes, st, 2);
+        if (rc >= 0) return rc;
+    }
     if (bitmap_bytes + queue_bytes(1024) <= limit && variant == 1) { CVB_DENSE(1024, 1, true, 1, 1); }
     if (bitmap_bytes + queue_bytes(512) <= limit) {
         if (variant == 2) { CVB_DENSE(512, 2, true, 1, 0); }

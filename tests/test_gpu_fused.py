@@ -228,3 +228,29 @@ def test_compact_snapshot_restores_every_byte(cv, day):
     sim.restore(plain)
     b = sim.run().summary
     assert all(a[k] == b[k] or (a[k] != a[k] and b[k] != b[k]) for k in a), 'compact and plain restore lead to different runs'
+
+
+def test_bulk_copy_staged_dense_pass_gives_the_same_run(cv):
+    '''
+    CVB_DENSE_VARIANT=3 selects the dense edge pass whose tiles are staged by cp.async.bulk + mbarrier (edge_pass_tma_kernel; slower than
+    the default, kept for profiling): same epidemic, agent for agent.  The variant is read once per process, hence the subprocess.
+    '''
+    import json
+    import os
+    import subprocess
+    import sys
+    code = ("import sys, json, hashlib, numpy as np; sys.path.insert(0, 'tests'); import scenarios, covasim_b200 as cv\n"
+            "out = {}\n"
+            "for name, kw in (('dynamic2k', {}), ('hybrid3k', dict(use_adjacency=False)), ('variants4k', dict(use_adjacency=False))):\n"
+            "    sim = cv.Sim(**scenarios.build(cv, scenarios.SCENARIOS[name]), **kw); sim.run()\n"
+            "    out[name] = [float(sim.summary['cum_infections']), hashlib.sha256(sim.people.to_numpy('date_exposed').tobytes()).hexdigest()]\n"
+            "print(json.dumps(out))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runs = []
+    for variant in ('0', '3'):
+        env = dict(os.environ, CVB_DENSE_VARIANT=variant)
+        r = subprocess.run([sys.executable, '-c', code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        runs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert runs[0] == runs[1]
+    assert all(v[0] > 100 for v in runs[0].values())

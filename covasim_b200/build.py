@@ -33,26 +33,48 @@ def source_digest():
     h = hashlib.sha256()
     files = sorted(glob.glob(os.path.join(CSRC, '*')) + glob.glob(os.path.join(ROOT, 'include', '*.h')))
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.relpath(f, ROOT).encode())         # (relative: the tree is copied to other machines with its built library)
         with open(f, 'rb') as fh:
             h.update(fh.read())
     h.update(' '.join(NVCC_FLAGS).encode())
     return h.hexdigest()
 
 
+def _up_to_date(digest):
+    return os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest
+
+
 def build(force=False, verbose=False):
+    '''
+    Compile the library if the sources (or flags) changed since the stamp was written.  Safe when several processes import the
+    package at once (one rank per GPU under torchrun): builders are serialised by a file lock, the compiler writes to a private
+    file and the result is moved into place atomically, so nobody ever maps a half-written library.
+    '''
+    import fcntl
     digest = source_digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
+    if not force and _up_to_date(digest):
         return LIB
-    srcs = sorted(glob.glob(os.path.join(CSRC, '*.cu')))
-    cmd = [find_nvcc()] + NVCC_FLAGS + ['-I', os.path.join(ROOT, 'include'), '-I', CSRC] + (['-Xptxas', '-v'] if verbose else []) + srcs + ['-o', LIB]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
-    with open(STAMP, 'w') as f:
-        f.write(digest)
+    with open(LIB + '.lock', 'w') as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and _up_to_date(digest):          # another process built it while this one waited
+                return LIB
+            srcs = sorted(glob.glob(os.path.join(CSRC, '*.cu')))
+            tmp = f'{LIB}.tmp{os.getpid()}'
+            cmd = [find_nvcc()] + NVCC_FLAGS + ['-I', os.path.join(ROOT, 'include'), '-I', CSRC] + (['-Xptxas', '-v'] if verbose else []) + srcs + ['-o', tmp]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + res.stdout + res.stderr)
+            if verbose:
+                print(res.stderr)
+            os.replace(tmp, LIB)
+            with open(STAMP + '.tmp', 'w') as f:
+                f.write(digest)
+            os.replace(STAMP + '.tmp', STAMP)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 

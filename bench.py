@@ -12,23 +12,25 @@ One "step" = one complete run of that sim (181 simulated days of the hot path).
   value : agent-days/s with the initial People + Layer arrays already resident in HBM; timed on the
           device with CUDA events around the day loop of Sim.run() (181 days = one cvb_run_days call).
   e2e   : the same through the public API with HOST buffers inside the timed region: Sim.restore()
-          (H2D of every People array and edge list from pinned memory) + Sim.run() (181 days +
-          finalize(), which reads the result tables back to the host).
+          (H2D from pinned memory of the saved People state -- in its compact form: per array either one
+          value + the exceptions or the array as it is -- and of every edge list) + Sim.run() (181 days +
+          finalize(), which reads the result tables back to the host).  h2d_bytes_per_step counts what is sent.
   roofline : the dominant kernel of the step (by CUDA-event time measured live around every launch of the day
           loop, in a separate pass): algorithmic bytes per launch / mean launch duration vs the measured HBM peak.  "kernels"
           lists the same for every kernel of the day; "edge_pass_dense" times the dense edge-streaming pass
           (12*E + 8*N bytes per launch, the form dynamic layers use) on its own with L2 flushed between launches.
-  cpu_baseline : the oracle (NumPy port of the reference algorithm) continuing the SAME sim from the GPU's
-          day-40 state for a bounded number of days on one host core (rank 0, N=1 only).
+  cpu_baseline : the UNMODIFIED reference (oracle/_ref, Numba parallel='full' on every host core) continuing the SAME
+          sim from the GPU's day-40 People state for ~20 s (rank 0, N=1 only); the oracle port only if oracle/_ref is missing.
+  ensembles : BASELINE configs 3 and 5 as blocks -- members of 100k / 50k agents advanced in lockstep on one GPU.
 
 N > 1 (torchrun): weak scaling -- every rank runs its own member of an ensemble (same configuration,
 seed + rank; reference run.py:1363-1365), no data-path collective; value = total agent-days / max time.
 In addition (block "partition"): ONE simulation agent-partitioned over the N GPUs (BASELINE config 4 recipe, 12.5M agents per
-GPU), with one ncclAllGather of 1 byte per agent per day on the data path, and a bit-identity check of a partitioned run against
-the single-GPU run of the same simulation.
+GPU), with one exchange of 1 byte per agent per day on the data path (over peer memory: cvb_peer_push + signal barrier; ncclAllGather
+where peer memory cannot be mapped), and a bit-identity check of a partitioned run against the single-GPU run of the same simulation.
 
---impl reference: times the oracle port (the reference's CPU algorithm; the reference itself is Python and
-cannot travel to the GPU box) on the same configuration, each step a bounded sample of the workload.
+--impl reference: ONE complete run of the workload by the unmodified reference on the host cores (oracle/_ref; the
+oracle port, time-bounded, only if the install is missing), timed as --steps consecutive sim.run(until=...) chunks.
 '''
 import argparse
 import json

@@ -579,7 +579,6 @@ class vaccinate_prob(Intervention):
         dev = sim.people.device
         self.doses = torch.zeros(sim.n_local, dtype=torch.int32, device=dev)              # doses given by *this* intervention
         self.due_day = torch.full((sim.n_local,), -1, dtype=torch.int32, device=dev)     # device form of second_dose_days
-        self._due_days = set()
         self._second = {}                          # replay mode: day -> indices due for their second dose
         self._c = _capi.cvb_vaccinate_pars(prob=float(self.prob), nab_init=_capi.dist_struct(self.p['nab_init']), nab_boost=float(self.p['nab_boost']),
                                            booster=int(bool(self.booster)), vaccine_index=self.index, max_doses=int(doses), index=self.iindex,

@@ -106,3 +106,26 @@ def test_hit_capacity_overflow_is_reported():
     cvpart.run_local(sims, lambda s: s.initialize())
     with pytest.raises(RuntimeError, match='hit_capacity'):
         cvpart.run_local(sims, lambda s: s.run())
+
+
+@pytest.mark.parametrize('n_bytes,offset', [(4096, 0), (4096, 8192), (1000, 4), (52, 20)])
+def test_peer_push_places_the_chunk_in_every_buffer(n_bytes, offset):
+    '''
+    cvb_peer_push (the data half of the exchange over peer memory, partition.PeerExchange): the chunk lands at the given offset of EVERY
+    listed buffer and nowhere else, through the 16-byte path and the 4-byte path (sizes / offsets that are not multiples of 16).  Here the
+    "peers" are three buffers of one GPU; under torchrun they are the ranks' symmetric-memory mappings (tests/multi_gpu_partition.py).
+    '''
+    import ctypes as C
+    import torch
+    from covasim_b200 import _capi
+    dev = torch.device('cuda', 0)
+    src = torch.randint(0, 255, (n_bytes,), dtype=torch.uint8, device=dev)
+    bufs = [torch.full((3 * 8192,), 7, dtype=torch.uint8, device=dev) for _ in range(3)]
+    ptrs = (C.c_uint64 * 3)(*[b.data_ptr() for b in bufs])
+    _capi.call('cvb_peer_push', src.data_ptr(), n_bytes, ptrs, 3, offset, None)
+    torch.cuda.synchronize()
+    for b in bufs:
+        assert torch.equal(b[offset:offset + n_bytes], src)
+        assert bool((b[:offset] == 7).all()) and bool((b[offset + n_bytes:] == 7).all())
+    with pytest.raises(_capi.CvbError):
+        _capi.call('cvb_peer_push', src.data_ptr(), 6, ptrs, 3, 0, None)             # sizes are multiples of 4 bytes

@@ -91,6 +91,8 @@ def _dist_worker(rank, world, port, q):
     table = torch.arange(6, dtype=torch.int64).reshape(2, 3) * (rank + 1)
     comm.all_reduce_sum(table)
     objs = comm.gather_objects(dict(rank=rank, ids=np.arange(rank + 2)))
+    peer = comm.peer_exchange(torch.device('cpu'), dict(codes=chunk, cases=chunk // 8))      # gloo: no peer memory -> every rank agrees on the fallback
+    assert peer is None
     q.put((rank, codes_global.numpy(), bits_global.numpy(), table.numpy(), [o['rank'] for o in objs], [len(o['ids']) for o in objs]))
     dist.barrier()
     dist.destroy_process_group()

@@ -158,7 +158,7 @@ inline void state_touched(cvb_sim* s) { s->state_valid = 0; }
 #define CVB_CHECK(call) do { int rc_ = cvb::check_cuda((call), #call); if (rc_) return rc_; } while (0)
 #define CVB_REQUIRE(cond, ...) do { if (!(cond)) { cvb::set_error(__VA_ARGS__); return 1; } } while (0)
 extern unsigned long long g_launches;        // kernels launched by this library (every launch site uses CVB_LAUNCH_CHECK)
-#define CVB_LAUNCH_CHECK() do { ++cvb::g_launches; CVB_CHECK(cudaGetLastError()); } while (0)
+#define CVB_LAUNCH_CHECK() do { __atomic_fetch_add(&cvb::g_launches, 1ull, __ATOMIC_RELAXED); CVB_CHECK(cudaGetLastError()); } while (0)     // (atomic: cvb_run_days_multi launches from several host threads)
 
 inline int grid_for(int64_t n, int per_block = kThreads, int64_t cap = 148 * 16) {
     int64_t g = (n + per_block - 1) / per_block;

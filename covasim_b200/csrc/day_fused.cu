@@ -23,6 +23,8 @@
 #include <string.h>
 #include <new>
 #include <vector>
+#include <string>
+#include <thread>
 #include "cvb_internal.cuh"
 
 namespace cvb {
@@ -980,27 +982,53 @@ int cvb_run_days(cvb_sim* s, int32_t t0, int32_t t1, cvb_stream st_) {
     return run_days_end(s, t1, st);
 }
 
+// members [a, b) through days [t0, t1): days outermost, members innermost, so that one host thread keeps every one of its members' streams fed
+static int run_days_slice(cvb_sim** handles, cvb_stream* streams, int a, int b, int32_t t0, int32_t t1) {
+    std::vector<char> packed((size_t)(b - a), 0);
+    int dev = -1;
+    auto on_device = [&](int m) { if (handles[m]->device != dev) { dev = handles[m]->device; return cudaSetDevice(dev); } return cudaSuccess; };
+    for (int m = a; m < b; ++m) {
+        CVB_CHECK(on_device(m));
+        bool p = false;
+        if (run_days_begin(handles[m], t0, t1, (cudaStream_t)streams[m], p)) return 1;
+        packed[m - a] = p;
+    }
+    for (int32_t t = t0; t < t1; ++t)
+        for (int m = a; m < b; ++m) {
+            CVB_CHECK(on_device(m));
+            if (run_one_day(handles[m], t, t0, packed[m - a] != 0, (cudaStream_t)streams[m])) return 1;
+        }
+    for (int m = a; m < b; ++m) {
+        CVB_CHECK(on_device(m));
+        if (run_days_end(handles[m], t1, (cudaStream_t)streams[m])) return 1;
+    }
+    return 0;
+}
+
 int cvb_run_days_multi(cvb_sim** handles, int32_t n_handles, int32_t t0, int32_t t1, cvb_stream* streams) {
     CVB_REQUIRE(handles && streams && n_handles > 0, "cvb_run_days_multi: bad argument");
     CVB_REQUIRE(n_handles <= 65536, "cvb_run_days_multi: too many handles");
-    std::vector<char> packed((size_t)n_handles, 0);
-    for (int m = 0; m < n_handles; ++m) {
-        CVB_REQUIRE(handles[m], "cvb_run_days_multi: NULL handle %d", m);
-        CVB_CHECK(cudaSetDevice(handles[m]->device));
-        bool p = false;
-        if (run_days_begin(handles[m], t0, t1, (cudaStream_t)streams[m], p)) return 1;
-        packed[m] = p;
+    for (int m = 0; m < n_handles; ++m) CVB_REQUIRE(handles[m], "cvb_run_days_multi: NULL handle %d", m);
+    // Small members are bound by the HOST's launch rate (five launches of 3-6 us kernels per member-day, ~2.4 us each from one thread), so the
+    // members are split over a few host threads, each feeding its own members' streams (CVB_MULTI_THREADS overrides the number)
+    int n_threads = n_handles >= 32 ? 4 : (n_handles >= 8 ? 2 : 1);
+    if (const char* e = getenv("CVB_MULTI_THREADS")) { const int v = atoi(e); if (v >= 1) n_threads = v; }
+    if (n_threads > n_handles) n_threads = n_handles;
+    if (n_threads > 64) n_threads = 64;
+    if (n_threads == 1) return run_days_slice(handles, streams, 0, n_handles, t0, t1);
+    std::vector<int> rc((size_t)n_threads, 0);
+    std::vector<std::string> err((size_t)n_threads);
+    std::vector<std::thread> workers;
+    for (int k = 0; k < n_threads; ++k) {
+        const int a = (int)((int64_t)n_handles * k / n_threads), b = (int)((int64_t)n_handles * (k + 1) / n_threads);
+        workers.emplace_back([&, k, a, b]() {
+            rc[k] = run_days_slice(handles, streams, a, b, t0, t1);
+            if (rc[k]) err[k] = cvb_last_error();               // (the message buffer is per thread)
+        });
     }
-    // days outermost, members innermost: one host thread keeps every member's stream fed, the members' kernels overlap on the GPU
-    for (int32_t t = t0; t < t1; ++t)
-        for (int m = 0; m < n_handles; ++m) {
-            if (m == 0 || handles[m]->device != handles[m - 1]->device) CVB_CHECK(cudaSetDevice(handles[m]->device));
-            if (run_one_day(handles[m], t, t0, packed[m] != 0, (cudaStream_t)streams[m])) return 1;
-        }
-    for (int m = 0; m < n_handles; ++m) {
-        if (m == 0 || handles[m]->device != handles[m - 1]->device) CVB_CHECK(cudaSetDevice(handles[m]->device));
-        if (run_days_end(handles[m], t1, (cudaStream_t)streams[m])) return 1;
-    }
+    for (auto& w : workers) w.join();
+    for (int k = 0; k < n_threads; ++k)
+        if (rc[k]) { cvb::set_error("%s", err[k].c_str()); return rc[k]; }
     return 0;
 }
 

@@ -160,3 +160,57 @@ def test_transtree_matches_reference(name):
     mine = tt.count_transmissions()
     want = ref[f'{name}/transmissions']
     assert np.array_equal(mine[np.lexsort(mine.T[::-1])], want[np.lexsort(want.T[::-1])])
+
+
+def test_compact_arena_encoding_round_trip():
+    '''
+    Sim._compact_arena (the compact form Sim.restore sends to the device: per array one fill value + exceptions, or dense) decoded in
+    NumPy must give back every array byte for byte: constant arrays, sparse exceptions, dense arrays, bool arrays whose length is not a
+    multiple of 4 (the last word shares its bytes with alignment padding), 2-D by-variant arrays, an all-NaN date array.
+    '''
+    import types
+    import torch
+    from covasim_b200.sim import Sim
+    rng = np.random.default_rng(3)
+    n, nv = 4003, 3
+    fields = [('uid', np.int32, (n,)), ('age', np.float32, (n,)), ('sex', np.bool_, (n,)), ('susceptible', np.bool_, (n,)), ('date_exposed', np.float32, (n,)),
+              ('date_dead', np.float32, (n,)), ('sus_imm', np.float32, (nv, n)), ('exposed_by_variant', np.bool_, (nv, n)), ('n_infections', np.int32, (n,))]
+    layout, total = [], 0
+    for name, dt, shape in fields:
+        nbytes = int(np.prod(shape)) * np.dtype(dt).itemsize
+        layout.append((name, dt, shape, total, nbytes))
+        total += (nbytes + 255) // 256 * 256
+    arena = rng.integers(0, 255, total, dtype=np.uint8)                 # padding holds garbage, as on the device
+    vals = dict(uid=np.arange(n, dtype=np.int32), age=rng.random(n, dtype=np.float32) * 90, sex=rng.random(n) < 0.5, susceptible=np.ones(n, dtype=bool),
+                date_exposed=np.full(n, np.nan, dtype=np.float32), date_dead=np.full(n, np.nan, dtype=np.float32),
+                sus_imm=np.zeros((nv, n), dtype=np.float32), exposed_by_variant=np.zeros((nv, n), dtype=bool), n_infections=np.zeros(n, dtype=np.int32))
+    sick = rng.choice(n, 17, replace=False)
+    vals['susceptible'][sick] = False
+    vals['date_exposed'][sick] = rng.integers(0, 9, 17)
+    vals['exposed_by_variant'][1, sick[:5]] = True
+    vals['n_infections'][sick] = 1
+    vals['n_infections'][-1] = 2                                        # the very last agent: the word shared with the padding
+    vals['susceptible'][-1] = False
+    for name, dt, shape, off, nbytes in layout:
+        arena[off:off + nbytes] = np.ascontiguousarray(vals[name]).view(np.uint8).reshape(-1)
+    host = torch.from_numpy(arena.copy())
+    stub = types.SimpleNamespace(people=types.SimpleNamespace(_layout=layout))
+    c = Sim._compact_arena(stub, host, pinned=False)
+    assert c['n_seg'] >= 6 and c['arena_bytes'] == total and c['h2d_bytes'] < total
+    table = c['table'].numpy()
+    out = np.full(total, 0xEE, dtype=np.uint8)
+    words = out.view(np.uint32)
+    seg = table[:3 * c['n_seg']].reshape(-1, 3)
+    for begin, count, value in seg:
+        words[begin:begin + count] = np.uint32(value)
+    idx, val = table[3 * c['n_seg']:3 * c['n_seg'] + c['n_exc']], table[3 * c['n_seg'] + c['n_exc']:3 * c['n_seg'] + 2 * c['n_exc']]
+    words[idx] = val.astype(np.uint32)
+    for a, b in c['dense']:
+        out[a:b] = arena[a:b]
+    dense_names = set()
+    for name, dt, shape, off, nbytes in layout:
+        got = out[off:off + nbytes].view(dt).reshape(shape)
+        assert np.array_equal(got, vals[name], equal_nan=np.dtype(dt).kind == 'f'), name
+        if any(a <= off and off + nbytes <= b for a, b in c['dense']):
+            dense_names.add(name)
+    assert dense_names == {'uid', 'age', 'sex'}                        # what really is dense at day 0 -- everything else is one value + exceptions

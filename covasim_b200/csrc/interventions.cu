@@ -215,17 +215,26 @@ __device__ __forceinline__ void trace_notify2(const PeoplePtrs& P, uint32_t* __r
     atomicMax(T.quar_slot[q] + c, __float_as_int(T.end_day));          // people.py:620-640 schedule_quarantine
 }
 
-// Adjacency form: one warp per case walks the case's own edges (static layers, both directions)
+// Adjacency form: G lanes per case walk the case's own edges (static layers, both directions).  A group's chain per case is list index ->
+// row pointers -> entries; the index two ahead and the row pointers one ahead are loaded while a row is processed.  G follows the mean
+// row length: 32 for a whole population's rows (~36 entries), down to 4 for the rows of an 8-way agent partition (~4.5 local entries).
+template <int G>
 __global__ void __launch_bounds__(kThreads) trace_sparse_kernel(PeoplePtrs P, const __grid_constant__ TraceTable T,
         const long long* __restrict__ adj_ptr, const uint4* __restrict__ adj, const int32_t* __restrict__ case_list,
-        const unsigned int* __restrict__ n_case_ptr, uint32_t layer_mask, uint32_t* __restrict__ S = nullptr /* fused day: packed state words */) {
+        const unsigned int* __restrict__ n_case_ptr, uint32_t layer_mask, uint32_t* __restrict__ S /* fused day: packed state words, or NULL */) {
     const unsigned int n_cases = *n_case_ptr;
-    const int lane = lane_id();
-    const unsigned int warps_total = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned int ci = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; ci < n_cases; ci += warps_total) {
-        const int i = case_list[ci];
-        const long long beg = adj_ptr[i], end = adj_ptr[i + 1];
-        for (long long off = beg + lane; off < end; off += 32) {
+    const int gl = threadIdx.x & (G - 1);
+    const unsigned int stride = (gridDim.x * blockDim.x) / G;
+    unsigned int ci = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    int i0 = ci < n_cases ? __ldg(case_list + ci) : -1;
+    int i1 = ci + stride < n_cases ? __ldg(case_list + ci + stride) : -1;
+    long long beg = 0, end = 0;
+    if (i0 >= 0) { beg = __ldg(adj_ptr + i0); end = __ldg(adj_ptr + i0 + 1); }
+    for (; ci < n_cases; ci += stride) {
+        long long beg1 = 0, end1 = 0;
+        if (i1 >= 0) { beg1 = __ldg(adj_ptr + i1); end1 = __ldg(adj_ptr + i1 + 1); }
+        const int i2 = (unsigned long long)ci + 2ull * stride < n_cases ? __ldg(case_list + ci + 2 * stride) : -1;
+        for (long long off = beg + gl; off < end; off += G) {
             const uint4 en = __ldg(adj + off);
             const int l = (int)(en.z >> 1);
             if (!((layer_mask >> l) & 1u)) continue;
@@ -234,7 +243,19 @@ __global__ void __launch_bounds__(kThreads) trace_sparse_kernel(PeoplePtrs P, co
             if (S) trace_notify2(P, S, T, q, (int)en.x);
             else trace_notify(P, T, q, (int)en.x);
         }
+        i0 = i1; i1 = i2; beg = beg1; end = end1;
     }
+}
+
+static int launch_trace_sparse(const PeoplePtrs& P, const TraceTable& T, const long long* adj_ptr, const uint4* adj, const int32_t* case_list,
+                               const unsigned int* n_case, uint32_t layer_mask, uint32_t* S, double mean_row, cudaStream_t st) {
+    const int grid = 148 * 8;
+    if (mean_row >= 24.0) trace_sparse_kernel<32><<<grid, kThreads, 0, st>>>(P, T, adj_ptr, adj, case_list, n_case, layer_mask, S);
+    else if (mean_row >= 12.0) trace_sparse_kernel<16><<<grid, kThreads, 0, st>>>(P, T, adj_ptr, adj, case_list, n_case, layer_mask, S);
+    else if (mean_row >= 6.0) trace_sparse_kernel<8><<<grid, kThreads, 0, st>>>(P, T, adj_ptr, adj, case_list, n_case, layer_mask, S);
+    else trace_sparse_kernel<4><<<grid, kThreads, 0, st>>>(P, T, adj_ptr, adj, case_list, n_case, layer_mask, S);
+    CVB_LAUNCH_CHECK();
+    return 0;
 }
 
 __global__ void __launch_bounds__(kThreads) trace_sparse2_kernel(PeoplePtrs P, uint32_t* __restrict__ S, const __grid_constant__ TraceTable T,
@@ -496,9 +517,8 @@ int cvb::launch_trace_partition(cvb_sim* s, int32_t t, const cvb_trace_pars* tr,
     CVB_REQUIRE(acc == 0, "fused day: a traced layer is not covered by the partitioned adjacency");
     if (!any_sparse) return 0;
     if (cvb::list_from_bits(s, s->case_bits_global, s->n_slots / 32, st)) return 1;
-    trace_sparse_kernel<<<148 * 2, kThreads, 0, st>>>(s->people, T, s->padj_ptr, s->padj, s->glist, s->n_glist, s->padj_layer_mask, s->state);
-    CVB_LAUNCH_CHECK();
-    return 0;
+    return launch_trace_sparse(s->people, T, s->padj_ptr, s->padj, s->glist, s->n_glist, s->padj_layer_mask, s->state,
+                               (double)s->padj_entries / (double)(s->n_global > 0 ? s->n_global : 1), st);
 }
 
 int cvb::launch_trace_sparse2(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, cudaStream_t st) {
@@ -538,9 +558,8 @@ int cvb_trace_notify_contacts(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, c
     CVB_REQUIRE(acc == 0, "cvb_trace_notify_contacts: a traced layer is not covered by the partitioned adjacency");
     if (!any_sparse) return 0;
     if (cvb::list_from_bits(s, s->case_bits_global, s->n_slots / 32, st)) return 1;
-    trace_sparse_kernel<<<148 * 2, kThreads, 0, st>>>(s->people, T, s->padj_ptr, s->padj, s->glist, s->n_glist, s->padj_layer_mask);
-    CVB_LAUNCH_CHECK();
-    return 0;
+    return launch_trace_sparse(s->people, T, s->padj_ptr, s->padj, s->glist, s->n_glist, s->padj_layer_mask, nullptr,
+                               (double)s->padj_entries / (double)(s->n_global > 0 ? s->n_global : 1), st);
 }
 
 int cvb_test_num_keys(cvb_sim* s, int32_t t, const cvb_test_num_pars* tp, double* weight, double* key, cvb_stream st) {
@@ -576,8 +595,7 @@ static int trace_notify_local(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, c
     if (build_trace_table(s, t, tr, adj_mask, threads * kEdgesPerThread, T, acc, any_sparse)) return 1;
     T.tape = tape;
     if (any_sparse) {
-        trace_sparse_kernel<<<148 * 2, kThreads, 0, st>>>(s->people, T, s->adj_ptr, s->adj, s->case_list, s->n_case_list, adj_mask);
-        CVB_LAUNCH_CHECK();
+        if (launch_trace_sparse(s->people, T, s->adj_ptr, s->adj, s->case_list, s->n_case_list, adj_mask, nullptr, 36.0, st)) return 1;
     }
     if (acc == 0) return 0;
     int n_sm = 148;

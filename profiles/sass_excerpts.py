@@ -49,10 +49,17 @@ summarize('sparse edge pass of the fused day (adjacency form, transmitter entrie
 summarize('day_begin_kernel<END, PRE, TEST, TSEL> (first per-agent kernel of the fused day)', 'day_fused.sm_100a.cubin', 'day_begin_kernelILb1ELb1ELb1ELb1',
           excerpt_re=r'ACQBULK|LDG\.E ', n_excerpt=30)
 summarize('day_mid_kernel (second per-agent kernel of the fused day)', 'day_fused.sm_100a.cubin', 'day_mid_kernel', excerpt_re=r'ACQBULK|LDG\.E ', n_excerpt=24)
+summarize('dense edge pass with bulk-copy staging (measured slower, CVB_DENSE_VARIANT=3): edge_pass_tma_kernel<MULTI=false, 20 warps>',
+          'edge_pass.sm_100a.cubin', 'edge_pass_tma_kernelILb0ELi20', excerpt_re=r'UBLKCP', n_excerpt=24)
+summarize('agent-partitioned edge pass: edge_pass_partition_kernel<MULTI=true, 8 lanes, 2 entries in flight>', 'edge_pass.sm_100a.cubin',
+          'edge_pass_partition_kernelILb1ELi8ELi2', excerpt_re=r'LDG\.E\.128', n_excerpt=30)
+summarize('exchange over peer memory: peer_push_kernel<uint4> (16-byte stores into every rank\'s buffer)', 'capi.sm_100a.cubin', 'peer_push_kernelI5uint4',
+          excerpt_re=r'STG\.E\.128', n_excerpt=16)
 hdr = ['SASS evidence for the round-2 kernels (cuobjdump -sass of covasim_b200/libcovasim_b200.so, sm_100a; written by profiles/sass_excerpts.py).',
        'What to look for: LDG.E.128 = 128-bit global loads (edge quads: p1 / p2 / beta of four edges per load; adjacency entries and agent records: 16 bytes',
        'each); .CONSTANT = the non-coherent path (only data that is never written during a run: the adjacency, the edge lists of the dense pass);',
        '.STRONG.GPU = L2 loads (ld.global.cg) of data the previous kernel of the chain wrote (the kernel may have been resident already: programmatic',
        'dependent launch); CCTL / PREFETCH = the L2 prefetch of the dense pass; ACQBULK = the programmatic-dependent-launch wait (griddepcontrol.wait).',
-       'No UBLKCP / UTMA*: none of these kernels uses TMA -- the dense pass keeps its tiles in registers (DESIGN.md section 4).', '']
+       'UBLKCP (cp.async.bulk global -> shared) and SYNCS (mbarrier) appear only in edge_pass_tma_kernel, the bulk-copy-staged form of the dense pass that was',
+       'built, measured slower and kept as a profiling variant; the default dense pass keeps its tiles in registers (DESIGN.md section 4).', '']
 print('\n'.join(hdr + out))

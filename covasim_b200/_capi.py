@@ -125,6 +125,7 @@ PROTOTYPES = dict(
     cvb_contact_tracing_list=[_P, _i32, C.POINTER(cvb_trace_pars), _P, _i64, _P],
     cvb_contact_tracing_taped=[_P, _i32, C.POINTER(cvb_trace_pars), _P, _P],
     cvb_pending_quarantine=[_P, _i32, _P, _P],
+    cvb_set_pending_quarantine=[_P, _i32, _P, _P],
     cvb_trace_select_cases=[_P, _i32, C.POINTER(cvb_trace_pars), _P],
     cvb_trace_notify_contacts=[_P, _i32, C.POINTER(cvb_trace_pars), _P],
     cvb_vaccinate_prob=[_P, _i32, C.POINTER(cvb_vaccinate_pars), _P, _P, _P, _P],

@@ -642,6 +642,14 @@ int cvb_pending_quarantine(cvb_sim* s, int32_t start_day, float* out_end_day, cv
     return 0;
 }
 
+int cvb_set_pending_quarantine(cvb_sim* s, int32_t start_day, const float* end_day, cvb_stream st) {
+    if (s) cvb::state_touched(s);
+    CVB_REQUIRE(s && end_day && start_day >= 0, "cvb_set_pending_quarantine: bad argument");
+    const int slot = start_day % s->quar_horizon;
+    CVB_CHECK(cudaMemcpyAsync(s->quar_ring + (int64_t)slot * s->n, end_day, (size_t)s->n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)st));
+    return 0;
+}
+
 int cvb_contact_tracing_list(cvb_sim* s, int32_t t, const cvb_trace_pars* tr, const int32_t* case_inds, int64_t n_cases, cvb_stream st_) {
     if (s) cvb::state_touched(s);
     cudaStream_t st = (cudaStream_t)st_;

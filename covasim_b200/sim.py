@@ -753,6 +753,14 @@ class Sim:
                     rng=(self.rng.seed, self.rng.np_.get_state(), self.rng.nb.get_state()),
                     pars={k: copy.deepcopy(v) for k, v in self.pars.items() if k not in ('interventions', 'analyzers', 'variants', 'prognoses', 'nab_kin')},
                     iv=iv_dev, iv_host=iv_host, iv_layers=iv_layers, quar_horizon=self._quar_horizon)
+        if self._quar_horizon > 1:                          # quarantine requests that start on one of the coming days (contact tracing with a delay)
+            buf = torch.empty(self.n_local, dtype=torch.float32, device=self.device)
+            ring = {}
+            for d in range(self.t, self.t + self._quar_horizon):
+                _capi.call('cvb_pending_quarantine', self._handle, int(d), buf.data_ptr(), self._stream_ptr)
+                if bool((buf >= 0).any()):
+                    ring[d] = host(buf)
+            snap['quar_ring'] = ring
         torch.cuda.synchronize(self.device)
         if pinned if compact is None else compact:
             snap['arena_compact'] = self._compact_arena(snap['arena'], pinned)
@@ -821,8 +829,6 @@ class Sim:
         and tracing kernels of static layers read the adjacency, which does not change, so only code that touches the raw edge
         arrays (dynamic layers, the per-step path, Python access through Layer, finalize) waits for them (_sync_edges).
         '''
-        if snap['t'] != 0 and self._quar_horizon > 1:
-            raise NotImplementedError('restoring mid-run with delayed quarantine requests pending is not built')
         if torch.cuda.current_device() != self.device.index:
             torch.cuda.set_device(self.device)
         if arrays:
@@ -861,6 +867,12 @@ class Sim:
             if held is not None:
                 iv.contacts = {lk: Layer(cols['p1'], cols['p2'], cols['beta'], label=lk, device=self.device) for lk, cols in held.items()}
         _capi.call('cvb_reset', self._handle, self._stream_ptr)
+        if snap.get('quar_ring'):                            # put back the requests that were pending when the snapshot was taken
+            self._set_quar_horizon(snap['quar_horizon'])
+            buf = torch.empty(self.n_local, dtype=torch.float32, device=self.device)
+            for d, h in snap['quar_ring'].items():
+                buf.copy_(h, non_blocking=True)
+                _capi.call('cvb_set_pending_quarantine', self._handle, int(d), buf.data_ptr(), self._stream_ptr)
         _capi.call('cvb_state_invalidate', self._handle)
         self.fused_days = 0
         self._host_adds = {k: v.copy() for k, v in snap['host_adds'].items()}

@@ -267,9 +267,12 @@ int cvb_contact_tracing_list(cvb_sim* s, int32_t t, const cvb_trace_pars* host_p
 /* Verification: cvb_contact_tracing with the uniform of every (layer, contact) GIVEN (device float64[n_layers][n], read only for contacts
  * of today's cases) -- the draws binomial_filter consumed in a recorded run of the reference (interventions.py:1109-1116) */
 int cvb_contact_tracing_taped(cvb_sim* s, int32_t t, const cvb_trace_pars* host_pars, const double* tape, cvb_stream st);
-/* Verification: the pending quarantine requests starting on start_day (people.py:620-640 _pending_quarantine[start_day]) as the latest
+/* Checkpoints and verification: the pending quarantine requests starting on start_day (people.py:620-640 _pending_quarantine[start_day]) as the latest
  * requested end day of every agent (device float32[n], -1 = none) */
 int cvb_pending_quarantine(cvb_sim* s, int32_t start_day, float* out_end_day, cvb_stream st);
+/* ... and the inverse, for restoring a checkpoint taken while requests were pending: the requests starting on start_day become exactly `end_day`
+ * (device float32[n], -1 = none); start_day must lie within the horizon of the current day */
+int cvb_set_pending_quarantine(cvb_sim* s, int32_t start_day, const float* end_day, cvb_stream st);
 /* The same in two phases for agent-partitioned handles: select today's local cases into case_bits_local; (the host
  * all-gathers the bitmap); notify the LOCAL contacts of every GLOBAL case */
 int cvb_trace_select_cases(cvb_sim* s, int32_t t, const cvb_trace_pars* host_pars, cvb_stream st);

@@ -127,6 +127,29 @@ def test_restore_mid_run(cv):
         assert np.array_equal(v[16:], sim.results[k].values[16:], equal_nan=True), k
 
 
+@pytest.mark.parametrize('fused', [True, False])
+def test_restore_mid_run_with_pending_quarantine_requests(cv, fused):
+    '''
+    hybrid3k traces contacts with delays of up to two days, so in the middle of the run quarantine requests are waiting for their start day
+    (reference people.py:620-640 _pending_quarantine; here the library's request ring).  A snapshot keeps them and restore puts them back:
+    the resumed run ends exactly like the uninterrupted one, People arrays included.
+    '''
+    spec = scenarios.SCENARIOS['hybrid3k']
+    sim = cv.Sim(**scenarios.build(cv, spec), fused=fused)
+    sim.run(until=21)
+    snap = sim.snapshot()
+    assert snap['quar_horizon'] == 3 and len(snap['quar_ring']) >= 1 and sum(int((h >= 0).sum()) for h in snap['quar_ring'].values()) > 10
+    sim.run(reset_seed=False)
+    first = {k: sim.results[k].values.copy() for k in sim.result_keys()}
+    people = {k: sim.people.to_numpy(k).copy() for k in ('quarantined', 'date_quarantined', 'date_end_quarantine', 'known_contact', 'date_exposed')}
+    sim.restore(snap)
+    sim.run(reset_seed=False)
+    for k, v in first.items():
+        assert np.array_equal(v[21:], sim.results[k].values[21:], equal_nan=True), k
+    for k, v in people.items():
+        assert np.array_equal(v, sim.people.to_numpy(k), equal_nan=(v.dtype.kind == 'f')), k
+
+
 def test_multisim_lockstep_members_equal_solo_runs(cv):
     ''' MultiSim advances its members through cvb_run_days_multi (one stream per member): each member identical to its solo run '''
     base = cv.Sim(**scenarios.build(cv, C2_SMALL, pop_size=12000, n_days=40, pop_infected=120))

@@ -475,8 +475,6 @@ class Sim:
             pars['n_days'] = self.day(pars['end_day'])
         pars['n_days'] = int(pars['n_days'])
         pars['end_day'] = self.date(pars['n_days'])       # reference sim.py:240-256: end_day and n_days always agree
-        if pars['pop_scale'] != 1 and pars['rescale'] and self._partition not in (None, False):
-            raise NotImplementedError('dynamic rescaling needs a global count of non-naive agents every day and is not built for agent-partitioned runs; use rescale=False')
 
     def _init_results(self):
         ''' Result containers (reference sim.py:284-351) '''
@@ -646,15 +644,22 @@ class Sim:
         Returns (global ids owned by this rank as a device tensor, number chosen overall).
         '''
         nz = torch.nonzero(self.people[key]).flatten()
-        counts = [int(nz.numel())] if self._comm is None else [int(c) for c in self._comm.gather_objects(int(nz.numel()))]
-        total = sum(counts)
-        k = min(int(k), total)
-        pos = cvu.choose_distinct(stream, total, k) if k > 0 else np.zeros(0, dtype=np.int64)
+        counts = self._global_counts(int(nz.numel()))
+        k = min(int(k), sum(counts))
+        who = self._pick_positions(nz, counts, cvu.choose_distinct(stream, sum(counts), k) if k > 0 else np.zeros(0, dtype=np.int64)) + self.id0
+        return who.to(torch.int32), k
+
+    def _global_counts(self, n_local_flagged):
+        ''' How many flagged agents every rank holds (one object gather under a partition; [n] otherwise) '''
+        return [int(n_local_flagged)] if self._comm is None else [int(c) for c in self._comm.gather_objects(int(n_local_flagged))]
+
+    def _pick_positions(self, flagged, counts, pos):
+        ''' ``pos``: positions in the ascending list of flagged agents over ALL ranks (identical on every rank) -> this rank's local indices '''
         rank = 0 if self._comm is None else self._comm.rank
         off = sum(counts[:rank])
+        pos = np.asarray(pos, dtype=np.int64)
         mine = pos[(pos >= off) & (pos < off + counts[rank])] - off
-        who = nz[torch.as_tensor(mine, dtype=torch.int64, device=self.device)] + self.id0
-        return who.to(torch.int32), k
+        return flagged[torch.as_tensor(mine, dtype=torch.int64, device=self.device)]
 
     def _build_adjacency(self):
         '''
@@ -1088,15 +1093,17 @@ class Sim:
         '''
         Dynamic rescaling (reference sim.py:535-555): once more than rescale_threshold of the agents are no longer naive, a
         random share of them is made naive again and every agent stands for more people from today on.  Needs one count per
-        day (a device synchronisation) while there is still room to rescale; the chosen agents are reset on the device.
+        day (a device synchronisation; plus one object gather over the ranks of a partitioned run) while there is still room to rescale;
+        the chosen agents are reset on the device.
         '''
         pars = self.pars
         if not pars['rescale']:
             return
         pop_scale, current = pars['pop_scale'], self.rescale_vec[self.t]
         if current < pop_scale:
-            not_naive = torch.nonzero(~self.people.naive).flatten()
-            n_not_naive, n_people = int(not_naive.numel()), pars['pop_size']
+            not_naive = torch.nonzero(~self.people.naive).flatten()                         # (this rank's agents under a partition)
+            counts = self._global_counts(int(not_naive.numel()))
+            n_not_naive, n_people = sum(counts), pars['pop_size']
             ratio, threshold = n_not_naive / n_people, pars['rescale_threshold']
             if ratio > threshold:
                 scaling = min(max(ratio / threshold, pars['rescale_factor']), pop_scale / current)
@@ -1105,8 +1112,8 @@ class Sim:
                 if self.rng_mode == 'mt':
                     choices = self.rng.nb.choice(n_not_naive, n, replace=False)                # cvu.choose: Numba stream
                 else:
-                    choices = cvu.choose_distinct(self.rng.nb, n_not_naive, n)
-                self.people.make_naive(not_naive[torch.as_tensor(choices, dtype=torch.int64, device=self.device)])
+                    choices = cvu.choose_distinct(self.rng.nb, n_not_naive, n)                 # the same positions on every rank (host streams in step)
+                self.people.make_naive(self._pick_positions(not_naive, counts, choices))
 
     def _timed_call(self, name, *args):
         ''' _capi.call bracketed by CUDA events on the launching stream (bench.py's per-kernel timing) '''

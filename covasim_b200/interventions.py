@@ -303,8 +303,6 @@ class test_num(Intervention):
 
     def initialize(self, sim):
         super().initialize()
-        if sim._comm is not None:
-            raise NotImplementedError('test_num picks the n_tests smallest keys of the whole population and is not built for agent-partitioned runs; use test_prob')
         self.start_day = sim.day(self.start_day)
         self.end_day = sim.day(self.end_day)
         self.days = [self.start_day, self.end_day]
@@ -346,14 +344,31 @@ class test_num(Intervention):
             return
         t = sim.t
         sim._call('cvb_test_num_keys', sim._handle, t, C.byref(self._c), self._weight.data_ptr(), self._key.data_ptr(), sim._stream_ptr)
+        comm = sim._comm
+        n_nonzero = int(torch.count_nonzero(self._weight).item())
         if sim.rescale_vec[t] / sim['pop_scale'] < 1:
-            n_tests = self.rescaled(sim, n_tests, float(self._weight.sum().item()))
-        n_tests = min(n_tests, int(torch.count_nonzero(self._weight).item()))
+            wsum = float(self._weight.sum().item())
+            if comm is not None:
+                wsum = float(sum(comm.gather_objects(wsum)))
+            n_tests = self.rescaled(sim, n_tests, wsum)
+        total_nonzero = n_nonzero if comm is None else int(sum(comm.gather_objects(n_nonzero)))
+        n_tests = min(n_tests, total_nonzero)
         if n_tests <= 0:
             return
-        inds = torch.topk(self._key, n_tests, largest=False, sorted=False).indices.to(torch.int32).contiguous()
-        sim._call('cvb_test_list', sim._handle, t, inds.data_ptr(), n_tests, float(self.sensitivity), float(self.loss_prob), int(self.test_delay),
-                  self.index, sim._stream_ptr)
+        if comm is None:
+            inds = torch.topk(self._key, n_tests, largest=False, sorted=False).indices.to(torch.int32).contiguous()
+        else:
+            # agent-partitioned: the n_tests smallest keys of the WHOLE population.  Every rank offers its own n_tests smallest, the
+            # n_tests-th smallest of all offers is the threshold, and each rank tests its agents at or below it (keys are continuous:
+            # no ties; agents with weight 0 have key +inf and n_tests never exceeds the number of finite keys)
+            k_local = min(n_tests, n_nonzero)
+            mine = torch.topk(self._key, k_local, largest=False, sorted=False).values.cpu().numpy() if k_local else np.zeros(0)
+            offers = np.concatenate(comm.gather_objects(mine))
+            threshold = np.partition(offers, n_tests - 1)[n_tests - 1]
+            inds = torch.nonzero(self._key <= float(threshold)).flatten().to(torch.int32).contiguous()
+        if len(inds):
+            sim._call('cvb_test_list', sim._handle, t, inds.data_ptr(), len(inds), float(self.sensitivity), float(self.loss_prob), int(self.test_delay),
+                      self.index, sim._stream_ptr)
         return inds
 
 
@@ -642,27 +657,35 @@ class vaccinate_num(vaccinate_prob):
         return np.array([0])
 
     def initialize(self, sim):
-        if sim._comm is not None:
-            raise NotImplementedError('vaccinate_num takes the first num_doses people of a population-wide sequence and is not built for agent-partitioned runs; use vaccinate_prob')
         super().initialize(sim)
         if isinstance(self.num_doses, dict):
             self.num_doses = {sim.day(k): v for k, v in self.num_doses.items()}
         seq = self.sequence                                      # interventions.py:1539-1552 process_sequence
-        dev = sim.people.device
+        dev, comm, n_global = sim.people.device, sim._comm, int(sim['pop_size'])
         if callable(seq):
+            if comm is not None:
+                raise NotImplementedError('vaccinate_num: a callable sequence sees one rank\'s people only; pass "age", None or an array of global ids to an agent-partitioned run')
             seq = seq(sim.people)
         elif isinstance(seq, str) and seq == 'age':              # oldest first; equal ages in index order (native RNG) / as NumPy's default sort leaves them (replay)
             age = np.asarray(sim.people.age)
+            if comm is not None:                                 # every rank needs the order of the WHOLE population (once, at initialisation)
+                age = np.concatenate(comm.gather_objects(age))
             seq = np.argsort(-age, kind='stable') if sim.rng_mode == 'philox' else np.argsort(-age)
         elif seq is None:
-            seq = sim.rng.np_.permutation(sim.n)
+            seq = sim.rng.np_.permutation(n_global)
         elif isinstance(seq, str):
             raise TypeError(f'Unable to interpret sequence {seq!r}: must be None, "age", callable, or an array')
         self._sequence_host = np.asarray(seq.cpu() if isinstance(seq, torch.Tensor) else seq).astype(np.int64)
-        self.sequence = torch.as_tensor(self._sequence_host).to(device=dev)
         self._scheduled = {}                                     # replay mode: day -> set of agents due (the reference's ddict(set))
-        self._u = torch.empty(sim.n, dtype=torch.float64, device=dev)
-        self._prob = torch.empty(sim.n, dtype=torch.float64, device=dev)
+        self._u = torch.empty(sim.n_local, dtype=torch.float64, device=dev)
+        self._prob = torch.empty(sim.n_local, dtype=torch.float64, device=dev)
+        if comm is None:
+            self.sequence = torch.as_tensor(self._sequence_host).to(device=dev)
+        else:                                                    # this rank's agents with their position in the sequence (none: never chosen)
+            pos = np.full(n_global, np.iinfo(np.int64).max, dtype=np.int64)
+            pos[self._sequence_host[::-1]] = np.arange(len(self._sequence_host) - 1, -1, -1)      # (an id listed twice keeps its first position)
+            self._pos = torch.as_tensor(pos[sim.id0:sim.id0 + sim.n_local]).to(device=dev)
+            self.sequence = None
 
     def _device_plan(self, sim):
         if isinstance(self.num_doses, dict) and self.num_doses:
@@ -678,11 +701,64 @@ class vaccinate_num(vaccinate_prob):
         return nd
 
     def _uniforms(self, sim, slot):
-        sim._call('cvb_keyed_uniform', int(sim.rng.seed), _P_VACC, self.iindex, sim.t, 0, sim.n, slot, self._u.data_ptr(), sim._stream_ptr)
+        sim._call('cvb_keyed_uniform', int(sim.rng.seed), _P_VACC, self.iindex, sim.t, int(sim.id0), sim.n_local, slot, self._u.data_ptr(), sim._stream_ptr)
         return self._u
+
+    def _weights(self, sim):
+        ''' First-dose weights of this rank's agents (interventions.py:1738-1752): 0 for the dead and the (un)vaccinated, subtarget values multiply '''
+        P = sim.people
+        prob = self._prob
+        prob.fill_(1.0)
+        prob[P.dead.as_subclass(torch.Tensor)] = 0.0
+        if self.subtarget is not None:
+            inds, vals = get_subtargets(self.subtarget, sim)
+            inds = torch.as_tensor(np.asarray(inds) if not isinstance(inds, torch.Tensor) else inds).to(device=P.device, dtype=torch.int64)
+            vals = torch.as_tensor(np.asarray(vals) if not isinstance(vals, torch.Tensor) else vals).to(device=P.device, dtype=torch.float64)
+            if sim._comm is not None:                            # global ids: this rank keeps its own agents
+                if vals.ndim == 0:
+                    vals = vals.expand(len(inds))
+                keep = (inds >= sim.id0) & (inds < sim.id0 + sim.n_local)
+                inds, vals = inds[keep] - sim.id0, vals[keep]
+            prob[inds] = prob[inds] * vals
+        vaccinated = P.vaccinated.as_subclass(torch.Tensor)
+        if self.booster:
+            prob[~vaccinated] = 0.0
+        else:
+            prob[vaccinated] = 0.0
+        return prob
+
+    def _select_people_partitioned(self, sim):
+        '''
+        The same selection when the agents are spread over several ranks: every "the first k of ..." becomes "the k smallest sequence
+        positions (or uniforms) over all ranks" (Sim._k_smallest_mask: each rank offers its own k smallest, the k-th smallest of all
+        offers is the threshold).  Same sets as select_people, so partitioned runs stay bit-identical to the single-GPU run.
+        '''
+        t, P = sim.t, sim.people
+        none = torch.zeros(0, dtype=torch.int64, device=P.device)
+        num_people = self.n_today(sim)
+        if num_people == 0:
+            self.due_day[self.due_day == t] = t + 1
+            return none, none
+        num_agents = int(np.floor(num_people / sim['pop_scale'] + sim.rng.np_.random_sample()))        # sc.randround (host stream: same on every rank)
+        sched_mask = (self.due_day == t) & (self.doses < int(self.p['doses'])) & ~P.dead.as_subclass(torch.Tensor)
+        n_sched = sum(sim._global_counts(int(sched_mask.sum().item())))
+        if n_sched > num_agents:
+            keep = sim._k_smallest_mask(self._uniforms(sim, 1), sched_mask, num_agents)
+            self.due_day[sched_mask & ~keep] = t + 1
+            return torch.nonzero(keep).flatten(), none
+        scheduled = torch.nonzero(sched_mask).flatten()
+        mask = (self._uniforms(sim, 0) < self._weights(sim)) & (self._pos < np.iinfo(np.int64).max)
+        if sum(sim._global_counts(int(mask.sum().item()))) == 0:
+            return scheduled, none
+        eligible = sim._k_smallest_mask(self._pos, mask, num_agents) & ~sched_mask
+        n_elig = sum(sim._global_counts(int(eligible.sum().item())))
+        first = sim._k_smallest_mask(self._pos, eligible, max(num_agents - n_sched, 0)) if n_elig + n_sched > num_agents else eligible
+        return scheduled, torch.nonzero(first).flatten()
 
     def select_people(self, sim):
         ''' Today's recipients as (scheduled second doses, first doses): device index arrays '''
+        if sim._comm is not None:
+            return self._select_people_partitioned(sim)
         t, P = sim.t, sim.people
         none = torch.zeros(0, dtype=torch.int64, device=P.device)
         num_people = self.n_today(sim)
@@ -690,27 +766,13 @@ class vaccinate_num(vaccinate_prob):
             self.due_day[self.due_day == t] = t + 1              # defer everyone due today
             return none, none
         num_agents = int(np.floor(num_people / sim['pop_scale'] + sim.rng.np_.random_sample()))        # sc.randround
-        dead = P.dead.as_subclass(torch.Tensor)
-        vaccinated = P.vaccinated.as_subclass(torch.Tensor)
-        sched_mask = (self.due_day == t) & (self.doses < int(self.p['doses'])) & ~dead
+        sched_mask = (self.due_day == t) & (self.doses < int(self.p['doses'])) & ~P.dead.as_subclass(torch.Tensor)
         scheduled = torch.nonzero(sched_mask).flatten()
         if len(scheduled) > num_agents:                          # more second doses due than doses: the rest wait a day
             order = torch.argsort(self._uniforms(sim, 1)[scheduled], stable=True)
             self.due_day[scheduled[order[num_agents:]]] = t + 1
             return scheduled[order[:num_agents]], none
-        prob = self._prob
-        prob.fill_(1.0)
-        prob[dead] = 0.0
-        if self.subtarget is not None:                           # weights multiply (interventions.py:1745-1747)
-            inds, vals = get_subtargets(self.subtarget, sim)
-            inds = torch.as_tensor(np.asarray(inds) if not isinstance(inds, torch.Tensor) else inds).to(device=P.device, dtype=torch.int64)
-            vals = torch.as_tensor(np.asarray(vals) if not isinstance(vals, torch.Tensor) else vals).to(device=P.device, dtype=torch.float64)
-            prob[inds] = prob[inds] * vals
-        if self.booster:
-            prob[~vaccinated] = 0.0
-        else:
-            prob[vaccinated] = 0.0
-        mask = self._uniforms(sim, 0) < prob
+        mask = self._uniforms(sim, 0) < self._weights(sim)
         eligible = self.sequence[mask[self.sequence]]
         if len(eligible) == 0:
             return scheduled, none

@@ -653,6 +653,23 @@ class Sim:
         ''' How many flagged agents every rank holds (one object gather under a partition; [n] otherwise) '''
         return [int(n_local_flagged)] if self._comm is None else [int(c) for c in self._comm.gather_objects(int(n_local_flagged))]
 
+    def _k_smallest_mask(self, vals, mask, k):
+        '''
+        Among this rank's agents with ``mask`` set, those whose value is one of the ``k`` smallest over ALL ranks (values are distinct:
+        sequence positions, continuous keys).  Every rank offers its own k smallest; the k-th smallest offer is the threshold.
+        '''
+        k = int(k)
+        if k <= 0:
+            return torch.zeros_like(mask)
+        cand = vals[mask]
+        k_local = min(k, int(cand.numel()))
+        mine = torch.topk(cand, k_local, largest=False, sorted=False).values.cpu().numpy() if k_local else np.zeros(0, dtype=cand.cpu().numpy().dtype)
+        offers = np.concatenate(self._comm.gather_objects(mine)) if self._comm is not None else mine
+        if len(offers) <= k:
+            return mask.clone()
+        threshold = np.partition(offers, k - 1)[k - 1].item()
+        return mask & (vals <= threshold)
+
     def _pick_positions(self, flagged, counts, pos):
         ''' ``pos``: positions in the ascending list of flagged agents over ALL ranks (identical on every rank) -> this rank's local indices '''
         rank = 0 if self._comm is None else self._comm.rank

@@ -283,14 +283,16 @@ class test_num(Intervention):
     Native-RNG mode: one device pass writes the weights and the exponential-clock keys ``-log(1 - u) / w`` of every agent, the
     ``n_tests`` smallest keys are a weighted sample without replacement (the reference's choose_w), and a second pass administers
     the tests.  One device synchronisation per day (the number of agents with non-zero weight caps ``n_tests``).
-    Not built: subtarget, ili_prev, swab_delay, numeric / callable quar_policy, daily_tests from a data file.
+    ``subtarget`` and ``ili_prev`` multiply the weights of the agents they name after the kernel pass (the keys of those agents are
+    recomputed from the same uniforms).  Not built: swab_delay, numeric / callable quar_policy, daily_tests from a data file.
     '''
 
     def __init__(self, daily_tests, symp_test=100.0, quar_test=1.0, quar_policy=None, subtarget=None, ili_prev=None, sensitivity=1.0,
                  loss_prob=0, test_delay=0, start_day=0, end_day=None, swab_delay=None, **kwargs):
         super().__init__(**kwargs)
-        if subtarget is not None or ili_prev is not None or swab_delay is not None:
-            raise NotImplementedError('test_num: subtarget / ili_prev / swab_delay are outside the built path')
+        if swab_delay is not None:
+            raise NotImplementedError('test_num: swab_delay is outside the built path')
+        self.subtarget, self.ili_prev = subtarget, ili_prev
         if isinstance(daily_tests, str):
             raise NotImplementedError('test_num: daily_tests from a data file is outside the built path (pass numbers)')
         self.daily_tests = daily_tests
@@ -308,6 +310,9 @@ class test_num(Intervention):
         self.days = [self.start_day, self.end_day]
         dt_ = self.daily_tests
         self.daily_tests = np.array([dt_] * sim.npts) if isinstance(dt_, (int, float, np.integer, np.floating)) else np.asarray(dt_)
+        if self.ili_prev is not None:                      # process_daily_data: a number applies every day
+            ip = self.ili_prev
+            self.ili_prev = np.array([ip] * sim.npts) if isinstance(ip, (int, float, np.integer, np.floating)) else np.asarray(ip)
         self.index = sim.intervention_index(self)
         self._c = _capi.cvb_test_num_pars(symp_test=float(self.symp_test), quar_test=float(self.quar_test),
                                           quar_policy=_QUAR_POLICY[self.quar_policy], index=self.index)
@@ -329,6 +334,46 @@ class test_num(Intervention):
         sim._host_add('new_tests', t, n_tests)
         return n_tests
 
+    def _extra_weights(self, sim):
+        '''
+        ili_prev (interventions.py:823-828: today's people with other illnesses, not symptomatic, test like symptomatic ones) and subtarget
+        (:834-837) multiply the weights the kernel wrote; the exponential-clock keys of those agents are recomputed from the SAME uniforms
+        (-log(1 - u) / w: the kernel's formula), so the draw an agent gets does not depend on the options.
+        '''
+        if self.ili_prev is None and self.subtarget is None:
+            return
+        t, dev, id0, n_local = sim.t, sim.people.device, int(sim.id0), sim.n_local
+        touched = []
+        rel_t = t - self.start_day
+        if self.ili_prev is not None and rel_t < len(self.ili_prev):
+            n_ili = int(self.ili_prev[rel_t] * sim['pop_size'])
+            if sim.rng_mode == 'mt':
+                ili = sim.rng.nb.choice(sim['pop_size'], n_ili, replace=False)               # cvu.choose
+            else:
+                from . import utils as cvu
+                ili = cvu.choose_distinct(sim.rng.nb, sim['pop_size'], n_ili)
+            ili = torch.as_tensor(np.asarray(ili), dtype=torch.int64, device=dev)
+            ili = ili[(ili >= id0) & (ili < id0 + n_local)] - id0                               # (global ids: this rank's agents)
+            ili = ili[~sim.people.symptomatic.as_subclass(torch.Tensor)[ili]]
+            self._weight[ili] = self._weight[ili] * float(self.symp_test)
+            touched.append(ili)
+        if self.subtarget is not None:
+            inds, vals = get_subtargets(self.subtarget, sim)
+            inds = torch.as_tensor(np.asarray(inds) if not isinstance(inds, torch.Tensor) else inds).to(device=dev, dtype=torch.int64)
+            vals = torch.as_tensor(np.asarray(vals) if not isinstance(vals, torch.Tensor) else vals).to(device=dev, dtype=torch.float64)
+            if vals.ndim == 0:
+                vals = vals.expand(len(inds))
+            keep = (inds >= id0) & (inds < id0 + n_local)
+            inds, vals = inds[keep] - id0, vals[keep]
+            self._weight[inds] = self._weight[inds] * vals
+            touched.append(inds)
+        sel = torch.cat(touched)
+        if len(sel):
+            u = torch.empty(n_local, dtype=torch.float64, device=dev)
+            sim._call('cvb_keyed_uniform', int(sim.rng.seed), _P_TEST, self.index, t, id0, n_local, 0, u.data_ptr(), sim._stream_ptr)
+            w = self._weight[sel]
+            self._key[sel] = torch.where(w > 0, -torch.log(1.0 - u[sel]) / w, torch.full_like(w, float('inf')))
+
     def rescaled(self, sim, n_tests, weight_sum):
         ''' Share of the tests that falls inside the simulated sample while the population is still being rescaled (interventions.py:838-842) '''
         t = sim.t
@@ -344,6 +389,7 @@ class test_num(Intervention):
             return
         t = sim.t
         sim._call('cvb_test_num_keys', sim._handle, t, C.byref(self._c), self._weight.data_ptr(), self._key.data_ptr(), sim._stream_ptr)
+        self._extra_weights(sim)
         comm = sim._comm
         n_nonzero = int(torch.count_nonzero(self._weight).item())
         if sim.rescale_vec[t] / sim['pop_scale'] < 1:
@@ -635,6 +681,7 @@ class vaccinate_prob(Intervention):
 
 
 _P_VACC = 7          # enum purpose (csrc/cvb_device.cuh): the vaccination draws
+_P_TEST = 3          # ... the testing draws
 
 
 class vaccinate_num(vaccinate_prob):

@@ -255,6 +255,11 @@ def test_num_apply(iv, sim):
     P, t = sim.people, sim.t
     probs = torch.ones(sim.n, dtype=torch.float64, device=sim.device)
     probs[P.symptomatic] *= iv.symp_test
+    rel_t = t - iv.start_day
+    if iv.ili_prev is not None and rel_t < len(iv.ili_prev):                                # interventions.py:823-828 (cvu.choose: Numba stream)
+        ili = sim.rng.nb.choice(sim['pop_size'], int(iv.ili_prev[rel_t] * sim['pop_size']), replace=False)
+        ili = torch.as_tensor(np.asarray(ili), dtype=torch.int64, device=sim.device)
+        probs[ili[~P.symptomatic[ili]]] *= iv.symp_test
     pol = iv.quar_policy
     if pol == 'start':
         qt = P.date_quarantined == t - 1
@@ -265,6 +270,12 @@ def test_num_apply(iv, sim):
     else:
         qt = P.quarantined.clone()
     probs[qt] *= iv.quar_test
+    if iv.subtarget is not None:                                                             # interventions.py:834-837
+        from .interventions import get_subtargets
+        s_inds, s_vals = get_subtargets(iv.subtarget, sim)
+        s_inds = torch.as_tensor(np.asarray(s_inds), dtype=torch.int64, device=sim.device)
+        s_vals = torch.as_tensor(np.asarray(s_vals), dtype=torch.float64, device=sim.device)
+        probs[s_inds] = probs[s_inds] * s_vals
     probs[P.diagnosed] = 0.0
     probs = probs.cpu().numpy()
     n_tests = iv.rescaled(sim, n_tests, probs.sum())

@@ -895,9 +895,10 @@ class clip_edges(Intervention):
 
 
 class test_num(Intervention):
-    ''' Number-based testing (reference interventions.py:718-854); subtarget / ili_prev / swab_delay not built '''
+    ''' Number-based testing (reference interventions.py:718-854); swab_delay not built '''
     def __init__(self, daily_tests, symp_test=100.0, quar_test=1.0, quar_policy=None, sensitivity=1.0, loss_prob=0, test_delay=0,
-                 start_day=0, end_day=None):
+                 start_day=0, end_day=None, subtarget=None, ili_prev=None):
+        self.subtarget, self.ili_prev = subtarget, ili_prev
         self.daily_tests, self.symp_test, self.quar_test = daily_tests, symp_test, quar_test
         self.quar_policy = quar_policy if quar_policy else 'start'
         self.sensitivity, self.loss_prob, self.test_delay = sensitivity, loss_prob, test_delay
@@ -906,6 +907,8 @@ class test_num(Intervention):
     def initialize(self, sim):
         self.start_day, self.end_day = sim.day(self.start_day), sim.day(self.end_day)
         self.daily_tests = np.array([self.daily_tests] * sim.npts) if np.isscalar(self.daily_tests) else np.asarray(self.daily_tests)
+        if self.ili_prev is not None:
+            self.ili_prev = np.array([self.ili_prev] * sim.npts) if np.isscalar(self.ili_prev) else np.asarray(self.ili_prev)
         self.index = sim.intervention_index(self)
 
     def apply(self, sim):
@@ -922,7 +925,13 @@ class test_num(Intervention):
         n = pars['pop_size']
         probs = np.ones(n)
         probs[P['symptomatic']] *= self.symp_test
+        if self.ili_prev is not None and rel_t < len(self.ili_prev):           # interventions.py:823-828: people with other illnesses test like symptomatic ones
+            chosen = sim.rng.choose('nb', n, int(self.ili_prev[rel_t] * n))
+            probs[np.setdiff1d(chosen, np.nonzero(P['symptomatic'])[0])] *= self.symp_test
         probs[get_quar_mask(P, t, self.quar_policy)] *= self.quar_test
+        if self.subtarget is not None:                                          # interventions.py:834-837: weights multiply
+            inds = np.asarray(self.subtarget['inds'])
+            probs[inds] = probs[inds] * self.subtarget['vals']
         probs[P['diagnosed']] = 0.0
         if sim.rescale_vec[t] / pars['pop_scale'] < 1:                          # interventions.py:838-842
             in_tot = probs.sum() * sim.rescale_vec[t]

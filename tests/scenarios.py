@@ -80,6 +80,15 @@ SCENARIOS = {
         pars=dict(pop_size=2000, pop_scale=6, rescale=True, pop_infected=40, pop_type='hybrid', n_days=30, verbose=0, rand_seed=81, beta=0.025),
         interventions=[('test_num', dict(daily_tests=[200] * 31, symp_test=80.0, start_day=3))],
     ),
+    # number-based testing with the two options that re-weight agents: influenza-like illness (3 % of the population every day test like
+    # symptomatic people) and a subtarget (every 5th agent three times as likely, a block of agents never), daily quarantine testing
+    'testnum_sub3k': dict(
+        pars=dict(pop_size=3000, pop_infected=50, pop_type='hybrid', n_days=30, verbose=0, rand_seed=131, beta=0.022),
+        interventions=[('test_num', dict(daily_tests=120, symp_test=20.0, quar_test=2.0, quar_policy='daily', start_day=3, sensitivity=0.95, ili_prev=0.03,
+                                         subtarget=dict(inds=np.concatenate([np.arange(0, 3000, 5), np.arange(2001, 2400, 5)]),
+                                                        vals=np.concatenate([np.full(600, 3.0), np.zeros(80)])))),
+                       ('contact_tracing', dict(trace_probs=0.5, start_day=5))],
+    ),
     # subtargeting: explicit testing / vaccination probabilities for given agents (a scalar for every 4th agent; a ramp over a block)
     'subtarget3k': dict(
         pars=dict(pop_size=3000, pop_infected=50, pop_type='hybrid', n_days=35, verbose=0, rand_seed=91, beta=0.022),

@@ -69,7 +69,8 @@ class cvb_trace_pars(C.Structure):
 class cvb_vaccinate_pars(C.Structure):
     _fields_ = [('prob', C.c_double), ('nab_init', cvb_dist), ('nab_boost', C.c_float), ('booster', C.c_int32),
                 ('vaccine_index', C.c_int32), ('max_doses', C.c_int32), ('index', C.c_int32), ('first_dose_today', C.c_int32),
-                ('second_dose_today', C.c_int32), ('interval', C.c_int32), ('n_days', C.c_int32)]
+                ('second_dose_today', C.c_int32), ('interval', C.c_int32), ('n_days', C.c_int32),
+                ('nab_boost_f64', C.c_double), ('nab_boost_is_f64', C.c_int32), ('pad_', C.c_int32)]
 
 
 _P = C.c_void_p

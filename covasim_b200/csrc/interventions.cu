@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(kThreads) vaccinate_kernel(PeoplePtrs P, const
         PF(P, date_vaccinated)[i] = (float)t;
         // update_peak_nab with the vaccine's parameters (immunity.py:138-202, symp=None)
         if (PF(P, nab)[i] > 0.0f) {
-            PF(P, peak_nab)[i] = fmul(PF(P, peak_nab)[i], vp.nab_boost);
+            PF(P, peak_nab)[i] = vp.nab_boost_is_f64 ? (float)dmul((double)PF(P, peak_nab)[i], vp.nab_boost_f64) : fmul(PF(P, peak_nab)[i], vp.nab_boost);
         } else {
             double x = tape ? tape[i] : dist_from_normal(vp.nab_init, keyed_normal(seed, P_NAB_VACC, (uint32_t)vp.index, t, i + id0, 0));
             PF(P, peak_nab)[i] = (float)pow(2.0, x);

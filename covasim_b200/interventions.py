@@ -56,6 +56,11 @@ def get_subtargets(subtarget, sim):
     return inds, vals
 
 
+def boost_is_f64(boost):
+    ''' NumPy's scalar rules for ``peak_nab[inds] *= boost`` (immunity.py:170): a NumPy float64 scalar forces the product into float64, a Python number does not '''
+    return isinstance(boost, np.floating) and not isinstance(boost, (np.float32, np.float16))
+
+
 def subtarget_override(subtarget, sim):
     ''' The subtarget as a device array float64[n_local]: the explicit probability of every subtargeted agent, NaN elsewhere '''
     inds, vals = get_subtargets(subtarget, sim)
@@ -586,7 +591,8 @@ class vaccinate_prob(Intervention):
     '''
     Probability-based vaccination with scheduled second doses (reference interventions.py:1257-1662).
     One per-agent device pass on first-dose days and on days when second doses are due.
-    ``subtarget`` is passed to the kernel as a per-agent override array.  Not built: target_eff.
+    ``subtarget`` is passed to the kernel as a per-agent override array; ``target_eff`` in a vaccine dict is turned into the
+    initial NAb level and the boost at initialisation, like the reference.
     '''
 
     def __init__(self, vaccine, days, label=None, prob=None, subtarget=None, booster=False, **kwargs):
@@ -618,13 +624,24 @@ class vaccinate_prob(Intervention):
                 self.label = self.p.pop('label', 'custom')
         else:
             raise ValueError(f'Could not understand vaccine of type {type(self.vaccine)}')
-        if 'target_eff' in self.p:
-            raise NotImplementedError('vaccinate_prob: target_eff is outside the built path')
         for k, v in cvpar.get_vaccine_dose_pars(default=True).items():
             self.p.setdefault(k, v)
         dflt = cvpar.get_vaccine_variant_pars(default=True)
         for k in sim['variant_pars'].keys():
             self.p.setdefault(k, dflt.get(k, 1.0))
+        if 'target_eff' in self.p:                              # interventions.py:1383-1397: the NAb level that gives the wanted efficacy against symptomatic disease
+            if self.p['doses'] != len(self.p['target_eff']):
+                raise ValueError('Provided mismatching efficacies and doses.')
+            nabs = np.arange(-8, 4, 0.1)
+            ne = sim['nab_eff']
+            lo_inf = np.exp(ne['alpha_inf']) * (2 ** nabs) ** ne['beta_inf']                   # immunity.py:250-262 calc_VE_symp
+            lo_symp = np.exp(ne['alpha_symp_inf']) * (2 ** nabs) ** ne['beta_symp_inf']
+            ve_symp = 1 - ((1 - lo_inf / (1 + lo_inf)) * (1 - lo_symp / (1 + lo_symp)))
+            peak = nabs[np.argmax(ve_symp > self.p['target_eff'][0])]
+            self.p['nab_init'] = dict(dist='normal', par1=peak, par2=2)
+            if self.p['doses'] == 2:
+                boosted = nabs[np.argmax(ve_symp > self.p['target_eff'][1])]
+                self.p['nab_boost'] = (2 ** boosted) / (2 ** peak)
         doses, interval = self.p['doses'], self.p['interval']
         if doses == 1 and interval is not None:
             raise ValueError("Can't use dosing intervals for vaccines with only one dose.")
@@ -641,7 +658,7 @@ class vaccinate_prob(Intervention):
         self.doses = torch.zeros(sim.n_local, dtype=torch.int32, device=dev)              # doses given by *this* intervention
         self.due_day = torch.full((sim.n_local,), -1, dtype=torch.int32, device=dev)     # device form of second_dose_days
         self._second = {}                          # replay mode: day -> indices due for their second dose
-        self._c = _capi.cvb_vaccinate_pars(prob=float(self.prob), nab_init=_capi.dist_struct(self.p['nab_init']), nab_boost=float(self.p['nab_boost']),
+        self._c = _capi.cvb_vaccinate_pars(prob=float(self.prob), nab_init=_capi.dist_struct(self.p['nab_init']), nab_boost=float(self.p['nab_boost']), nab_boost_f64=float(self.p['nab_boost']), nab_boost_is_f64=int(boost_is_f64(self.p['nab_boost'])),
                                            booster=int(bool(self.booster)), vaccine_index=self.index, max_doses=int(doses), index=self.iindex,
                                            interval=-1 if interval is None else int(interval), n_days=int(sim['n_days']))
         sim._pars_dirty = True

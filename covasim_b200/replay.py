@@ -85,7 +85,11 @@ def update_peak_nab(sim, inds, nab_pars, symp=None):
     has = P.nab[inds] > 0
     prior, fresh = inds[has], inds[~has]
     if len(prior):
-        P.peak_nab[prior] = P.peak_nab[prior] * float(nab_pars['nab_boost'])
+        from .interventions import boost_is_f64
+        if boost_is_f64(nab_pars['nab_boost']):                  # (a NumPy float64 boost -- target_eff -- multiplies in float64)
+            P.peak_nab[prior] = (P.peak_nab[prior].double() * float(nab_pars['nab_boost'])).float()
+        else:
+            P.peak_nab[prior] = P.peak_nab[prior] * float(nab_pars['nab_boost'])
     if len(fresh):
         if nab_pars['nab_init'] is None:
             raise ValueError(f'Attempt to administer a vaccine without an initial NAb distribution to {len(fresh)} unvaccinated people failed.')

@@ -283,6 +283,10 @@ typedef struct cvb_vaccinate_pars {        /* interventions.py:1257-1662 */
     cvb_dist nab_init;
     float nab_boost;
     int32_t booster, vaccine_index, max_doses, index, first_dose_today, second_dose_today, interval, n_days;
+    /* the boost as a float64 factor: the reference multiplies peak_nab (float32) by the vaccine's nab_boost with NumPy's scalar rules -- a
+     * Python number acts in float32 (nab_boost above), a NumPy float64 (what `target_eff` computes, interventions.py:1393-1394) in float64 */
+    double nab_boost_f64;
+    int32_t nab_boost_is_f64, pad_;
 } cvb_vaccinate_pars;
 /* `iv_doses` int32[n] is this intervention's own dose count, `due_day` int32[n] the day an agent's second
  * dose is due (-1 none) -- the device form of second_dose_days (interventions.py:1655-1660) */

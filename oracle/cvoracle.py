@@ -452,7 +452,11 @@ def update_peak_nab(P, pars, rng, t, inds, nab_pars, symp=None, purpose=ph.P_INF
     prior = inds[has]
     fresh = inds[~has]
     if len(prior):
-        P['peak_nab'][prior] = (P['peak_nab'][prior] * f32(nab_pars['nab_boost'])).astype(f32)
+        boost = nab_pars['nab_boost']
+        if isinstance(boost, np.floating) and not isinstance(boost, (np.float32, np.float16)):      # NumPy scalar rules: a float64 scalar (target_eff) multiplies in float64
+            P['peak_nab'][prior] = (P['peak_nab'][prior].astype(f64) * f64(boost)).astype(f32)
+        else:
+            P['peak_nab'][prior] = (P['peak_nab'][prior] * f32(boost)).astype(f32)
     if len(fresh):
         if nab_pars['nab_init'] is None:
             raise ValueError(f'Attempt to administer a vaccine without an initial NAb distribution to {len(fresh)} unvaccinated people failed.')
@@ -1096,6 +1100,18 @@ class vaccinate_prob(Intervention):
         dflt = cvpar.get_vaccine_variant_pars(default=True)
         for k in sim.pars['variant_pars'].keys():
             self.p.setdefault(k, dflt.get(k, 1.0))
+        if 'target_eff' in self.p:                              # interventions.py:1383-1397: the NAb level that gives the wanted efficacy
+            assert self.p['doses'] == len(self.p['target_eff']), 'Provided mismatching efficacies and doses.'
+            nabs = np.arange(-8, 4, 0.1)
+            ne = sim.pars['nab_eff']
+            lo_inf = np.exp(ne['alpha_inf']) * (2 ** nabs) ** ne['beta_inf']                   # immunity.py:250-262 calc_VE_symp
+            lo_symp = np.exp(ne['alpha_symp_inf']) * (2 ** nabs) ** ne['beta_symp_inf']
+            ve_symp = 1 - ((1 - lo_inf / (1 + lo_inf)) * (1 - lo_symp / (1 + lo_symp)))
+            peak = nabs[np.argmax(ve_symp > self.p['target_eff'][0])]
+            self.p['nab_init'] = dict(dist='normal', par1=peak, par2=2)
+            if self.p['doses'] == 2:
+                boosted = nabs[np.argmax(ve_symp > self.p['target_eff'][1])]
+                self.p['nab_boost'] = (2 ** boosted) / (2 ** peak)
         n = len(sim.P['uid'])
         self.doses = np.zeros(n, dtype=i32)
         sim.pars['vaccine_pars'][self.label] = self.p

@@ -89,6 +89,12 @@ SCENARIOS = {
                                                         vals=np.concatenate([np.full(600, 3.0), np.zeros(80)])))),
                        ('contact_tracing', dict(trace_probs=0.5, start_day=5))],
     ),
+    # a two-dose vaccine given by its target efficacies (reference tests/test_immunity.py:238-290): NAb level and boost are derived from them
+    'targeteff3k': dict(
+        pars=dict(pop_size=3000, pop_infected=50, pop_type='hybrid', n_days=40, verbose=0, rand_seed=141, beta=0.022),
+        interventions=[('vaccinate_prob', dict(vaccine=dict(nab_init=None, nab_boost=3, doses=2, interval=14, target_eff=[0.7, 0.95]), label='trial', days=[3, 5], prob=0.3)),
+                       ('test_prob', dict(start_day=5, symp_prob=0.2, asymp_prob=0.01))],
+    ),
     # subtargeting: explicit testing / vaccination probabilities for given agents (a scalar for every 4th agent; a ramp over a block)
     'subtarget3k': dict(
         pars=dict(pop_size=3000, pop_infected=50, pop_type='hybrid', n_days=35, verbose=0, rand_seed=91, beta=0.022),

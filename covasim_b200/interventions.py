@@ -56,6 +56,50 @@ def get_subtargets(subtarget, sim):
     return inds, vals
 
 
+def get_pdf(dist=None, par1=None, par2=None):
+    ''' Symptom-onset-to-swab delay density (reference utils.py:240-268) '''
+    import scipy.stats as sps
+    if dist in ('None', 'none', None):
+        return None
+    if dist == 'uniform':
+        return sps.uniform(loc=par1, scale=par2)
+    if dist == 'lognormal':
+        mean = np.log(par1 ** 2 / np.sqrt(par2 + par1 ** 2))
+        sigma = np.sqrt(np.log(par2 / par1 ** 2 + 1))
+        return sps.lognorm(sigma, loc=-0.5, scale=np.exp(mean))
+    raise NotImplementedError(f'The selected distribution "{dist}" is not implemented; choices are: none, uniform, lognormal')
+
+
+def swab_terms(pdf, sim):
+    '''
+    swab_delay (interventions.py:812-817, 935-939): today's symptomatic agents (device indices), their whole days since symptom onset, the
+    delay density there and the inverse share of each delay among them.  A host computation on a few thousand values (one synchronisation).
+    '''
+    if sim._comm is not None:
+        raise NotImplementedError('swab_delay weighs every symptomatic agent by the share of its onset day in the whole population and is not built for agent-partitioned runs')
+    P = sim.people
+    symp_inds = torch.nonzero(P.symptomatic.as_subclass(torch.Tensor)).flatten()
+    if not len(symp_inds):
+        return symp_inds, None, None, None
+    symp_time = (np.float32(sim.t) - P.date_symptomatic.as_subclass(torch.Tensor)[symp_inds].cpu().numpy()).astype(np.int32)
+    inv_count = np.bincount(symp_time) / len(symp_time)
+    count = np.nan * np.ones(inv_count.shape)
+    count[inv_count != 0] = 1 / inv_count[inv_count != 0]
+    return symp_inds, symp_time, pdf.pdf(symp_time), count[symp_time]
+
+
+def quar_test_mask(sim, policy):
+    ''' interventions.py:691-715 get_quar_inds as a device mask '''
+    P, t = sim.people, sim.t
+    if policy == 'start':
+        return (P.date_quarantined == t - 1).as_subclass(torch.Tensor)
+    if policy == 'end':
+        return (P.date_end_quarantine == t + 1).as_subclass(torch.Tensor)
+    if policy == 'both':
+        return ((P.date_quarantined == t - 1) | (P.date_end_quarantine == t + 1)).as_subclass(torch.Tensor)
+    return P.quarantined.as_subclass(torch.Tensor).clone()
+
+
 def boost_is_f64(boost):
     ''' NumPy's scalar rules for ``peak_nab[inds] *= boost`` (immunity.py:170): a NumPy float64 scalar forces the product into float64, a Python number does not '''
     return isinstance(boost, np.floating) and not isinstance(boost, (np.float32, np.float16))
@@ -289,15 +333,14 @@ class test_num(Intervention):
     ``n_tests`` smallest keys are a weighted sample without replacement (the reference's choose_w), and a second pass administers
     the tests.  One device synchronisation per day (the number of agents with non-zero weight caps ``n_tests``).
     ``subtarget`` and ``ili_prev`` multiply the weights of the agents they name after the kernel pass (the keys of those agents are
-    recomputed from the same uniforms).  Not built: swab_delay, numeric / callable quar_policy, daily_tests from a data file.
+    recomputed from the same uniforms); so does ``swab_delay`` for the symptomatic.  Not built: numeric / callable quar_policy, daily_tests from a data file.
     '''
 
     def __init__(self, daily_tests, symp_test=100.0, quar_test=1.0, quar_policy=None, subtarget=None, ili_prev=None, sensitivity=1.0,
                  loss_prob=0, test_delay=0, start_day=0, end_day=None, swab_delay=None, **kwargs):
         super().__init__(**kwargs)
-        if swab_delay is not None:
-            raise NotImplementedError('test_num: swab_delay is outside the built path')
         self.subtarget, self.ili_prev = subtarget, ili_prev
+        self.pdf = get_pdf(**swab_delay) if swab_delay else None
         if isinstance(daily_tests, str):
             raise NotImplementedError('test_num: daily_tests from a data file is outside the built path (pass numbers)')
         self.daily_tests = daily_tests
@@ -345,11 +388,20 @@ class test_num(Intervention):
         (:834-837) multiply the weights the kernel wrote; the exponential-clock keys of those agents are recomputed from the SAME uniforms
         (-log(1 - u) / w: the kernel's formula), so the draw an agent gets does not depend on the options.
         '''
-        if self.ili_prev is None and self.subtarget is None:
+        if self.ili_prev is None and self.subtarget is None and self.pdf is None:
             return
         t, dev, id0, n_local = sim.t, sim.people.device, int(sim.id0), sim.n_local
         touched = []
         rel_t = t - self.start_day
+        if self.pdf is not None:                               # interventions.py:812-819: the symptomatic weigh symp_test x density x inverse share of their delay
+            symp_inds, symp_time, dens, count = swab_terms(self.pdf, sim)
+            if len(symp_inds):
+                w = torch.as_tensor(1.0 * (float(self.symp_test) * (dens * count)), dtype=torch.float64, device=dev)
+                qt = quar_test_mask(sim, self.quar_policy)[symp_inds]
+                w = torch.where(qt, w * float(self.quar_test), w)
+                w[sim.people.diagnosed.as_subclass(torch.Tensor)[symp_inds]] = 0.0
+                self._weight[symp_inds] = w
+                touched.append(symp_inds)
         if self.ili_prev is not None and rel_t < len(self.ili_prev):
             n_ili = int(self.ili_prev[rel_t] * sim['pop_size'])
             if sim.rng_mode == 'mt':
@@ -429,14 +481,13 @@ class test_prob(Intervention):
     device pass: test probability from symptom / quarantine / diagnosis state, keyed Bernoulli draws
     for "tests today", "test is positive" (sensitivity) and "not lost to follow-up".
     ``subtarget`` (explicit probabilities for given agents) is passed to the kernel as a per-agent override array.
-    Not built: swab_delay, ili_prev, callable quar_policy.
+    ``ili_prev``, ``subtarget`` and ``swab_delay`` become a per-agent override array built every day.  Not built: callable quar_policy.
     '''
 
     def __init__(self, symp_prob, asymp_prob=0.0, symp_quar_prob=None, asymp_quar_prob=None, quar_policy=None, subtarget=None,
                  ili_prev=None, sensitivity=1.0, loss_prob=0.0, test_delay=0, start_day=0, end_day=None, swab_delay=None, **kwargs):
         super().__init__(**kwargs)
-        if swab_delay is not None:
-            raise NotImplementedError('test_prob: swab_delay is outside the built path')
+        self.pdf = get_pdf(**swab_delay) if swab_delay else None
         self.subtarget = subtarget
         self.ili_prev = ili_prev
         self.symp_prob, self.asymp_prob = symp_prob, asymp_prob
@@ -464,7 +515,7 @@ class test_prob(Intervention):
                                            quar_policy=_QUAR_POLICY[self.quar_policy], test_delay=int(self.test_delay), index=self.index)
 
     def _device_plan(self, sim):
-        if self.subtarget is not None or self.ili_prev is not None:
+        if self.subtarget is not None or self.ili_prev is not None or self.pdf is not None:
             return None                                    # per-agent overrides are built on the host every day
         return ('test', self._c, int(self.start_day), -1 if self.end_day is None else int(self.end_day))
 
@@ -495,10 +546,19 @@ class test_prob(Intervention):
         symptomatic people whatever their quarantine state (interventions.py:962-967), then the subtarget on top (:971-973).
         '''
         ili = self.ili_inds(sim)
-        if ili is None and self.subtarget is None:
+        if ili is None and self.subtarget is None and self.pdf is None:
             return None
         dev = sim.people.device
         out = torch.full((sim.n_local,), float('nan'), dtype=torch.float64, device=dev)
+        if self.pdf is not None:                           # interventions.py:934-943: the symptomatic test by the time since onset ...
+            symp_inds, symp_time, dens, count = swab_terms(self.pdf, sim)
+            if len(symp_inds):
+                sp = np.ones(len(symp_time))
+                early = 1 > (symp_time * self.symp_prob)
+                sp[early] = self.symp_prob / (1 - symp_time[early] * self.symp_prob)
+                sp = torch.as_tensor(dens * sp * count, dtype=torch.float64, device=dev)
+                free = ~quar_test_mask(sim, self.quar_policy)[symp_inds]      # ... unless the quarantine probability applies to them (:959-966)
+                out[symp_inds[free]] = sp[free]
         if ili is not None and len(ili):
             ili = torch.as_tensor(ili, dtype=torch.int64, device=dev)
             ili = ili[~sim.people.symptomatic[ili]]

@@ -258,7 +258,12 @@ def test_num_apply(iv, sim):
         return
     P, t = sim.people, sim.t
     probs = torch.ones(sim.n, dtype=torch.float64, device=sim.device)
-    probs[P.symptomatic] *= iv.symp_test
+    if iv.pdf is not None and bool(P.symptomatic.any()):                                     # interventions.py:812-819 swab_delay
+        from .interventions import swab_terms
+        symp_inds, symp_time, dens, count = swab_terms(iv.pdf, sim)
+        probs[symp_inds] *= torch.as_tensor(float(iv.symp_test) * (dens * count), dtype=torch.float64, device=sim.device)
+    else:
+        probs[P.symptomatic] *= iv.symp_test
     rel_t = t - iv.start_day
     if iv.ili_prev is not None and rel_t < len(iv.ili_prev):                                # interventions.py:823-828 (cvu.choose: Numba stream)
         ili = sim.rng.nb.choice(sim['pop_size'], int(iv.ili_prev[rel_t] * sim['pop_size']), replace=False)

@@ -899,10 +899,11 @@ class clip_edges(Intervention):
 
 
 class test_num(Intervention):
-    ''' Number-based testing (reference interventions.py:718-854); swab_delay not built '''
+    ''' Number-based testing (reference interventions.py:718-854) '''
     def __init__(self, daily_tests, symp_test=100.0, quar_test=1.0, quar_policy=None, sensitivity=1.0, loss_prob=0, test_delay=0,
-                 start_day=0, end_day=None, subtarget=None, ili_prev=None):
+                 start_day=0, end_day=None, subtarget=None, ili_prev=None, swab_delay=None):
         self.subtarget, self.ili_prev = subtarget, ili_prev
+        self.pdf = get_pdf(**swab_delay) if swab_delay else None
         self.daily_tests, self.symp_test, self.quar_test = daily_tests, symp_test, quar_test
         self.quar_policy = quar_policy if quar_policy else 'start'
         self.sensitivity, self.loss_prob, self.test_delay = sensitivity, loss_prob, test_delay
@@ -928,7 +929,12 @@ class test_num(Intervention):
         sim.results['new_tests'][t] += n_tests
         n = pars['pop_size']
         probs = np.ones(n)
-        probs[P['symptomatic']] *= self.symp_test
+        if self.pdf is not None and P['symptomatic'].any():                     # interventions.py:812-819: weight by the time since symptom onset
+            symp_inds = np.nonzero(P['symptomatic'])[0]
+            symp_time, dens, count = swab_terms(self.pdf, t, P['date_symptomatic'], symp_inds)
+            probs[symp_inds] *= self.symp_test * (dens * count)               # (`symp_test *= pdf * count`: the product on the right is taken first)
+        else:
+            probs[P['symptomatic']] *= self.symp_test
         if self.ili_prev is not None and rel_t < len(self.ili_prev):           # interventions.py:823-828: people with other illnesses test like symptomatic ones
             chosen = sim.rng.choose('nb', n, int(self.ili_prev[rel_t] * n))
             probs[np.setdiff1d(chosen, np.nonzero(P['symptomatic'])[0])] *= self.symp_test
@@ -956,6 +962,29 @@ class test_num(Intervention):
         test_people(P, sim.rng, t, inds, self.sensitivity, self.loss_prob, self.test_delay, sub=self.index)
 
 
+def get_pdf(dist=None, par1=None, par2=None):
+    ''' Symptom-onset-to-swab delay density (reference utils.py:240-268) '''
+    import scipy.stats as sps
+    if dist in ('None', 'none', None):
+        return None
+    if dist == 'uniform':
+        return sps.uniform(loc=par1, scale=par2)
+    if dist == 'lognormal':
+        mean = np.log(par1 ** 2 / np.sqrt(par2 + par1 ** 2))
+        sigma = np.sqrt(np.log(par2 / par1 ** 2 + 1))
+        return sps.lognorm(sigma, loc=-0.5, scale=np.exp(mean))
+    raise NotImplementedError(f'The selected distribution "{dist}" is not implemented')
+
+
+def swab_terms(pdf, t, date_symptomatic, symp_inds):
+    ''' Days since symptom onset of the symptomatic, the density there, and the inverse share of each delay (interventions.py:812-817, 935-939) '''
+    symp_time = (f32(t) - date_symptomatic[symp_inds]).astype(i32)
+    inv_count = np.bincount(symp_time) / len(symp_time)
+    count = np.nan * np.ones(inv_count.shape)
+    count[inv_count != 0] = 1 / inv_count[inv_count != 0]
+    return symp_time, pdf.pdf(symp_time), count[symp_time]
+
+
 def get_quar_mask(P, t, policy):
     ''' interventions.py:691-715 get_quar_inds as a boolean mask '''
     if policy == 'start':
@@ -970,10 +999,11 @@ def get_quar_mask(P, t, policy):
 
 
 class test_prob(Intervention):
-    ''' Probability-based testing (reference interventions.py:857-981); swab_delay / ili_prev / subtarget not built '''
+    ''' Probability-based testing (reference interventions.py:857-981) '''
     def __init__(self, symp_prob, asymp_prob=0.0, symp_quar_prob=None, asymp_quar_prob=None, quar_policy=None,
-                 sensitivity=1.0, loss_prob=0.0, test_delay=0, start_day=0, end_day=None, subtarget=None, ili_prev=None):
+                 sensitivity=1.0, loss_prob=0.0, test_delay=0, start_day=0, end_day=None, subtarget=None, ili_prev=None, swab_delay=None):
         self.subtarget, self.ili_prev = subtarget, ili_prev
+        self.pdf = get_pdf(**swab_delay) if swab_delay else None
         self.symp_prob, self.asymp_prob = symp_prob, asymp_prob
         self.symp_quar_prob = symp_prob if symp_quar_prob is None else symp_quar_prob
         self.asymp_quar_prob = asymp_prob if asymp_quar_prob is None else asymp_quar_prob
@@ -1010,6 +1040,13 @@ class test_prob(Intervention):
         else:
             raise NotImplementedError(self.quar_policy)
         probs = np.where(symp, self.symp_prob, self.asymp_prob).astype(float)
+        if self.pdf is not None and symp.any():                 # interventions.py:934-943: symptomatic people test by the time since onset
+            symp_inds = np.nonzero(symp)[0]
+            symp_time, dens, count = swab_terms(self.pdf, t, P['date_symptomatic'], symp_inds)
+            sp = np.ones(len(symp_time))
+            early = 1 > (symp_time * self.symp_prob)
+            sp[early] = self.symp_prob / (1 - symp_time[early] * self.symp_prob)
+            probs[symp_inds] = dens * sp * count
         probs[qt & symp] = self.symp_quar_prob
         probs[qt & ~symp] = self.asymp_quar_prob
         probs[ili] = self.symp_prob                             # ILI people test like symptomatic ones, in quarantine or not (:962-967)

@@ -95,6 +95,14 @@ SCENARIOS = {
         interventions=[('vaccinate_prob', dict(vaccine=dict(nab_init=None, nab_boost=3, doses=2, interval=14, target_eff=[0.7, 0.95]), label='trial', days=[3, 5], prob=0.3)),
                        ('test_prob', dict(start_day=5, symp_prob=0.2, asymp_prob=0.01))],
     ),
+    # symptom-onset-to-swab delay (swab_delay): symptomatic people test with a probability / weight that follows the time since onset
+    'swab3k': dict(
+        pars=dict(pop_size=3000, pop_infected=80, pop_type='hybrid', n_days=30, verbose=0, rand_seed=151, beta=0.025),
+        interventions=[('test_prob', dict(start_day=3, end_day=16, symp_prob=0.25, asymp_prob=0.005, symp_quar_prob=0.5, quar_policy='daily',
+                                          swab_delay=dict(dist='lognormal', par1=3, par2=4))),
+                       ('test_num', dict(daily_tests=100, symp_test=30.0, quar_test=2.0, start_day=17, swab_delay=dict(dist='lognormal', par1=2, par2=3))),
+                       ('contact_tracing', dict(trace_probs=0.5, start_day=5))],
+    ),
     # subtargeting: explicit testing / vaccination probabilities for given agents (a scalar for every 4th agent; a ramp over a block)
     'subtarget3k': dict(
         pars=dict(pop_size=3000, pop_infected=50, pop_type='hybrid', n_days=35, verbose=0, rand_seed=91, beta=0.022),

@@ -665,7 +665,7 @@ class Sim:
         k_local = min(k, int(cand.numel()))
         mine = torch.topk(cand, k_local, largest=False, sorted=False).values.cpu().numpy() if k_local else np.zeros(0, dtype=cand.cpu().numpy().dtype)
         offers = np.concatenate(self._comm.gather_objects(mine)) if self._comm is not None else mine
-        if len(offers) <= k:
+        if len(offers) < k:                                  # fewer candidates than k over all ranks (a rank with k or more offers k by itself)
             return mask.clone()
         threshold = np.partition(offers, k - 1)[k - 1].item()
         return mask & (vals <= threshold)

@@ -33,6 +33,9 @@ PART_SCENARIOS = {
     # doses per day along a population-wide priority sequence (oldest first; a random order for the booster), second doses deferred and drawn
     'vaccnum3k': scenarios.SCENARIOS['vaccnum3k'],
     'testnum_sub3k': scenarios.SCENARIOS['testnum_sub3k'],
+    # every candidate on ONE rank (a priority list of the first 600 agents), fewer doses than candidates: that rank's own k smallest decide
+    'vaccnum_front': dict(pars=dict(pop_size=3000, pop_infected=50, pop_type='hybrid', n_days=30, verbose=0, rand_seed=5, beta=0.022),
+                          interventions=[('vaccinate_num', dict(vaccine='pfizer', sequence=np.arange(600), num_doses=35))]),
     # population size not divisible by 32 * world
     'odd5003': dict(pars=dict(pop_size=5003, pop_infected=80, pop_type='hybrid', n_days=35, verbose=0, rand_seed=4, beta=0.02),
                     interventions=[('test_prob', dict(start_day=4, symp_prob=0.3, asymp_prob=0.02)),
@@ -52,7 +55,7 @@ def run_partitioned(cv, spec, world, fused=True):
 
 # world 1: every row is whole (~36 entries per agent), which selects the 32-lanes-per-transmitter form of edge_pass_partition_kernel;
 # 2-4 ranks select the 16- and 8-lane forms
-@pytest.mark.parametrize('name,world', [('hybrid3k', 1), ('variants4k', 1), ('hybrid3k', 2), ('hybrid3k', 3), ('variants4k', 2), ('variants4k_beds', 3), ('random2k_nowaning', 4), ('odd5003', 3), ('rescale3k', 2), ('rescale3k', 3), ('testnum3k', 3), ('testnum_rescale2k', 2), ('vaccnum3k', 2), ('vaccnum3k', 3), ('testnum_sub3k', 2)])
+@pytest.mark.parametrize('name,world', [('hybrid3k', 1), ('variants4k', 1), ('hybrid3k', 2), ('hybrid3k', 3), ('variants4k', 2), ('variants4k_beds', 3), ('random2k_nowaning', 4), ('odd5003', 3), ('rescale3k', 2), ('rescale3k', 3), ('testnum3k', 3), ('testnum_rescale2k', 2), ('vaccnum3k', 2), ('vaccnum3k', 3), ('testnum_sub3k', 2), ('vaccnum_front', 3)])
 @pytest.mark.parametrize('fused', [True, False])
 def test_partitioned_equals_single(name, world, fused):
     ''' fused=True: the days without a host decision go through the fused kernels phase by phase (cvb_fused_phase) with the exchanges in between '''
@@ -61,7 +64,7 @@ def test_partitioned_equals_single(name, world, fused):
     ref = cv.Sim(**scenarios.build(cv, spec))
     ref.run()
     sims, logs = run_partitioned(cv, spec, world, fused)
-    if fused and not spec['pars'].get('n_imports') and name not in ('rescale3k', 'testnum3k', 'testnum_rescale2k', 'vaccnum3k', 'testnum_sub3k'):        # (days on which the population may still be rescaled need the host, too)                      # (daily importations are drawn on the host: those runs keep the per-step path)
+    if fused and not spec['pars'].get('n_imports') and name not in ('rescale3k', 'testnum3k', 'testnum_rescale2k', 'vaccnum3k', 'testnum_sub3k', 'vaccnum_front'):        # (days on which the population may still be rescaled need the host, too)                      # (daily importations are drawn on the host: those runs keep the per-step path)
         # (5003 agents over 3 ranks: the last rank's share is not a multiple of 4, so ALL ranks keep the per-step path)
         assert all(s.fused_days > 0.5 * s.npts for s in sims) or (name == 'odd5003' and all(s.fused_days == 0 for s in sims)), [s.fused_days for s in sims]
     if not fused:

@@ -183,3 +183,54 @@ def test_partition_properties(n, world, sizes, seed):
             assert np.array_equal(adj[mine, 3].view(np.float32), layer['beta'][e])
         seen += M
     assert seen == 2 * sum(sizes)                                              # each directed edge on exactly one rank
+
+
+@pytest.mark.parametrize('world,k', [(1, 5), (3, 0), (3, 7), (3, 40), (4, 1000)])
+def test_k_smallest_over_ranks(world, k):
+    '''
+    Sim._k_smallest_mask / _pick_positions / _global_counts: the population-wide selections of partitioned runs (test_num's n smallest keys,
+    vaccinate_num's first k of a sequence, rescaling's positions in the global list of non-naive agents) from every rank's own offers.
+    Ranks of different sizes, some with no candidate at all; float keys and int64 positions; k above the number of candidates.
+    '''
+    import threading
+    import types
+    from covasim_b200 import partition as cvpart
+    from covasim_b200.sim import Sim
+    rng = np.random.default_rng(world * 100 + k)
+    sizes = [int(x) for x in rng.integers(0, 60, world)]
+    sizes[0] = 50
+    vals = [rng.permutation(10_000)[:n].astype(np.int64) for n in sizes]            # distinct within a rank ...
+    for r in range(world):
+        vals[r] = vals[r] * world + r                                                   # ... and across ranks
+    fvals = [v.astype(np.float64) / 7.0 for v in vals]
+    masks = [rng.random(n) < 0.7 for n in sizes]
+    if world > 1:
+        masks[1][:] = False                                                             # a rank without candidates
+    comms = cvpart.LocalComm.make(world) if world > 1 else [None]
+    got_i, got_f, picked = [None] * world, [None] * world, [None] * world
+    n_flagged = [int(m.sum()) for m in masks]
+    pos = rng.permutation(sum(n_flagged))[:min(9, sum(n_flagged))]
+
+    def work(r):
+        stub = types.SimpleNamespace(_comm=comms[r], device=torch.device('cpu'))
+        stub._global_counts = lambda n: Sim._global_counts(stub, n)
+        m = torch.as_tensor(masks[r])
+        got_i[r] = Sim._k_smallest_mask(stub, torch.as_tensor(vals[r]), m, k).numpy()
+        got_f[r] = Sim._k_smallest_mask(stub, torch.as_tensor(fvals[r]), m, k).numpy()
+        counts = Sim._global_counts(stub, int(m.sum()))
+        assert counts == n_flagged
+        picked[r] = Sim._pick_positions(stub, torch.nonzero(m).flatten(), counts, pos).numpy()
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=60)
+    allv = np.concatenate([v[m] for v, m in zip(vals, masks)])
+    want = set(np.sort(allv)[:k].tolist())
+    for got in (got_i, got_f):
+        chosen = set(np.concatenate([v[g] for v, g in zip(vals, got)]).tolist())
+        assert chosen == want
+        assert all(not (g & ~m).any() for g, m in zip(got, masks))
+    # positions in the global ascending list of flagged agents -> (rank, local index)
+    flat = [(r, i) for r in range(world) for i in np.nonzero(masks[r])[0]]
+    assert sorted((r, int(i)) for r in range(world) for i in picked[r]) == sorted(flat[p] for p in pos)

@@ -148,6 +148,7 @@ PROTOTYPES = dict(
     cvb_state_check=[_P, _i32, _P, _P],
 )
 OTHER_SYMBOLS = ('cvb_last_error', 'cvb_abi_version', 'cvb_launch_count')
+ABI_VERSION = 2          # CVB_ABI_VERSION of include/covasim_b200.h
 
 
 def load_library(path=LIB_PATH):
@@ -174,6 +175,8 @@ def load_library(path=LIB_PATH):
     lib.cvb_abi_version.argtypes = []
     lib.cvb_launch_count.restype = C.c_int64
     lib.cvb_launch_count.argtypes = []
+    if lib.cvb_abi_version() != ABI_VERSION:
+        raise CvbError(f'{path} has ABI version {lib.cvb_abi_version()}, this binding was written for {ABI_VERSION} (include/covasim_b200.h): rebuild the library')
     return lib
 
 

@@ -28,7 +28,7 @@ extern "C" {
 #define CVB_MAX_LAYERS   8
 #define CVB_MAX_VACCINES 8
 #define CVB_N_DURS       9
-#define CVB_ABI_VERSION  1
+#define CVB_ABI_VERSION  2      /* 2: round 2 -- fused day / plans / exchange entry points, cvb_vaccinate_pars grew (float64 boost) */
 
 typedef struct cvb_sim cvb_sim;
 typedef void* cvb_stream;

@@ -40,7 +40,9 @@ def test_struct_layouts_match(cv):
     want = [C.sizeof(x) for x in (cv._capi.cvb_pars, cv._capi.cvb_dist, cv._capi.cvb_test_prob_pars, cv._capi.cvb_trace_pars,
                                   cv._capi.cvb_vaccinate_pars)]
     assert list(sizes) == want
-    assert cv._capi.lib.cvb_abi_version() == 1
+    import re
+    header = open(os.path.join(ROOT, 'include', 'covasim_b200.h')).read()
+    assert cv._capi.lib.cvb_abi_version() == cv._capi.ABI_VERSION == int(re.search(r'#define CVB_ABI_VERSION\s+(\d+)', header).group(1)) == 2
 
 
 def test_generated_field_header_is_current(cv):

@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(kThreads) test_num_keys_kernel(PeoplePtrs P, c
             case 0:  qt = d_quar[i] == tf - 1.0f; break;
             case 1:  qt = d_end_quar[i] == tf + 1.0f; break;
             case 2:  qt = (d_quar[i] == tf - 1.0f) || (d_end_quar[i] == tf + 1.0f); break;
-            default: qt = quarantined[i] != 0; break;
+            case 3:  qt = quarantined[i] != 0; break;
+            default: qt = false; break;                                // 4: the caller applies its own quarantine-testing set
         }
         if (qt) w = dmul(w, tp.quar_test);
         if (diagnosed[i]) w = 0.0;                                     // diagnosed people do not test

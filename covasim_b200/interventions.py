@@ -97,7 +97,18 @@ def quar_test_mask(sim, policy):
         return (P.date_end_quarantine == t + 1).as_subclass(torch.Tensor)
     if policy == 'both':
         return ((P.date_quarantined == t - 1) | (P.date_end_quarantine == t + 1)).as_subclass(torch.Tensor)
-    return P.quarantined.as_subclass(torch.Tensor).clone()
+    if policy == 'daily':
+        return P.quarantined.as_subclass(torch.Tensor).clone()
+    mask = torch.zeros(sim.n_local, dtype=torch.bool, device=P.device)
+    if callable(policy):                                   # a function of the sim returning the people to test (global ids under a partition)
+        inds = policy(sim)
+        inds = torch.as_tensor(np.asarray(inds) if not isinstance(inds, torch.Tensor) else inds).to(device=P.device, dtype=torch.int64) - int(sim.id0)
+        mask[inds[(inds >= 0) & (inds < sim.n_local)]] = True
+        return mask
+    dq = P.date_quarantined.as_subclass(torch.Tensor)
+    for q in np.atleast_1d(policy):                        # days after the start of quarantine on which a test is done
+        mask |= dq == float(t - 1 - q)
+    return mask
 
 
 def boost_is_f64(boost):
@@ -323,6 +334,19 @@ class clip_edges(Intervention):
 
 
 _QUAR_POLICY = dict(start=0, end=1, both=2, daily=3)
+_QUAR_POLICY_HOST = 4     # a number / list of days since the start of quarantine, or a function of the sim: the set is built here, not in the kernel
+
+
+def quar_policy_code(policy, who):
+    ''' Kernel code of a quarantine-testing policy (reference interventions.py:682-712 get_quar_inds) '''
+    if isinstance(policy, str):
+        if policy not in _QUAR_POLICY:
+            raise ValueError(f'{who}: quarantine policy "{policy}" not recognized: must be a string (start, end, both, daily), int, list, array, set, tuple, or function')
+        return _QUAR_POLICY[policy]
+    if callable(policy) or np.ndim(policy) <= 1:
+        return _QUAR_POLICY_HOST
+    raise ValueError(f'{who}: quarantine policy {policy!r} not recognized')
+
 
 
 class test_num(Intervention):
@@ -333,7 +357,8 @@ class test_num(Intervention):
     ``n_tests`` smallest keys are a weighted sample without replacement (the reference's choose_w), and a second pass administers
     the tests.  One device synchronisation per day (the number of agents with non-zero weight caps ``n_tests``).
     ``subtarget`` and ``ili_prev`` multiply the weights of the agents they name after the kernel pass (the keys of those agents are
-    recomputed from the same uniforms); so does ``swab_delay`` for the symptomatic.  Not built: numeric / callable quar_policy, daily_tests from a data file.
+    recomputed from the same uniforms); so do ``swab_delay`` for the symptomatic and a ``quar_policy`` given as days since the start of quarantine
+    or as a function.  Not built: daily_tests from a data file.
     '''
 
     def __init__(self, daily_tests, symp_test=100.0, quar_test=1.0, quar_policy=None, subtarget=None, ili_prev=None, sensitivity=1.0,
@@ -346,8 +371,7 @@ class test_num(Intervention):
         self.daily_tests = daily_tests
         self.symp_test, self.quar_test = symp_test, quar_test
         self.quar_policy = quar_policy if quar_policy else 'start'
-        if self.quar_policy not in _QUAR_POLICY:
-            raise NotImplementedError(f'test_num: quar_policy "{self.quar_policy}" is not built (choices: {list(_QUAR_POLICY)})')
+        self._quar_code = quar_policy_code(self.quar_policy, 'test_num')
         self.sensitivity, self.loss_prob, self.test_delay = sensitivity, loss_prob, test_delay
         self.start_day, self.end_day = start_day, end_day
 
@@ -363,7 +387,7 @@ class test_num(Intervention):
             self.ili_prev = np.array([ip] * sim.npts) if isinstance(ip, (int, float, np.integer, np.floating)) else np.asarray(ip)
         self.index = sim.intervention_index(self)
         self._c = _capi.cvb_test_num_pars(symp_test=float(self.symp_test), quar_test=float(self.quar_test),
-                                          quar_policy=_QUAR_POLICY[self.quar_policy], index=self.index)
+                                          quar_policy=self._quar_code, index=self.index)
         dev = sim.people.device
         self._weight = torch.empty(sim.n_local, dtype=torch.float64, device=dev)
         self._key = torch.empty(sim.n_local, dtype=torch.float64, device=dev)
@@ -388,7 +412,8 @@ class test_num(Intervention):
         (:834-837) multiply the weights the kernel wrote; the exponential-clock keys of those agents are recomputed from the SAME uniforms
         (-log(1 - u) / w: the kernel's formula), so the draw an agent gets does not depend on the options.
         '''
-        if self.ili_prev is None and self.subtarget is None and self.pdf is None:
+        host_policy = self._quar_code == _QUAR_POLICY_HOST
+        if self.ili_prev is None and self.subtarget is None and self.pdf is None and not host_policy:
             return
         t, dev, id0, n_local = sim.t, sim.people.device, int(sim.id0), sim.n_local
         touched = []
@@ -414,6 +439,13 @@ class test_num(Intervention):
             ili = ili[~sim.people.symptomatic.as_subclass(torch.Tensor)[ili]]
             self._weight[ili] = self._weight[ili] * float(self.symp_test)
             touched.append(ili)
+        if host_policy:                                        # (the kernel applied no quarantine factor: policy code 4)
+            qt = quar_test_mask(sim, self.quar_policy)
+            if self.pdf is not None and len(symp_inds):        # (the swab-delay branch above has already dealt with the symptomatic)
+                qt[symp_inds] = False
+            qi = torch.nonzero(qt).flatten()
+            self._weight[qi] = self._weight[qi] * float(self.quar_test)
+            touched.append(qi)
         if self.subtarget is not None:
             inds, vals = get_subtargets(self.subtarget, sim)
             inds = torch.as_tensor(np.asarray(inds) if not isinstance(inds, torch.Tensor) else inds).to(device=dev, dtype=torch.int64)
@@ -481,7 +513,8 @@ class test_prob(Intervention):
     device pass: test probability from symptom / quarantine / diagnosis state, keyed Bernoulli draws
     for "tests today", "test is positive" (sensitivity) and "not lost to follow-up".
     ``subtarget`` (explicit probabilities for given agents) is passed to the kernel as a per-agent override array.
-    ``ili_prev``, ``subtarget`` and ``swab_delay`` become a per-agent override array built every day.  Not built: callable quar_policy.
+    ``ili_prev``, ``subtarget`` and ``swab_delay`` and a ``quar_policy`` given as days since the start of quarantine or as a function become a per-agent
+    override array built every day.
     '''
 
     def __init__(self, symp_prob, asymp_prob=0.0, symp_quar_prob=None, asymp_quar_prob=None, quar_policy=None, subtarget=None,
@@ -494,8 +527,7 @@ class test_prob(Intervention):
         self.symp_quar_prob = symp_prob if symp_quar_prob is None else symp_quar_prob
         self.asymp_quar_prob = asymp_prob if asymp_quar_prob is None else asymp_quar_prob
         self.quar_policy = quar_policy if quar_policy else 'start'
-        if self.quar_policy not in _QUAR_POLICY:
-            raise NotImplementedError(f'test_prob: quar_policy "{self.quar_policy}" is not built (choices: {list(_QUAR_POLICY)})')
+        self._quar_code = quar_policy_code(self.quar_policy, 'test_prob')
         self.sensitivity, self.loss_prob, self.test_delay = sensitivity, loss_prob, test_delay
         self.start_day, self.end_day = start_day, end_day
 
@@ -512,10 +544,10 @@ class test_prob(Intervention):
         self.index = sim.intervention_index(self)
         self._c = _capi.cvb_test_prob_pars(symp_prob=self.symp_prob, asymp_prob=self.asymp_prob, symp_quar_prob=self.symp_quar_prob,
                                            asymp_quar_prob=self.asymp_quar_prob, sensitivity=self.sensitivity, loss_prob=self.loss_prob,
-                                           quar_policy=_QUAR_POLICY[self.quar_policy], test_delay=int(self.test_delay), index=self.index)
+                                           quar_policy=self._quar_code, test_delay=int(self.test_delay), index=self.index)
 
     def _device_plan(self, sim):
-        if self.subtarget is not None or self.ili_prev is not None or self.pdf is not None:
+        if self.subtarget is not None or self.ili_prev is not None or self.pdf is not None or self._quar_code == _QUAR_POLICY_HOST:
             return None                                    # per-agent overrides are built on the host every day
         return ('test', self._c, int(self.start_day), -1 if self.end_day is None else int(self.end_day))
 
@@ -546,7 +578,8 @@ class test_prob(Intervention):
         symptomatic people whatever their quarantine state (interventions.py:962-967), then the subtarget on top (:971-973).
         '''
         ili = self.ili_inds(sim)
-        if ili is None and self.subtarget is None and self.pdf is None:
+        host_policy = self._quar_code == _QUAR_POLICY_HOST
+        if ili is None and self.subtarget is None and self.pdf is None and not host_policy:
             return None
         dev = sim.people.device
         out = torch.full((sim.n_local,), float('nan'), dtype=torch.float64, device=dev)
@@ -559,6 +592,11 @@ class test_prob(Intervention):
                 sp = torch.as_tensor(dens * sp * count, dtype=torch.float64, device=dev)
                 free = ~quar_test_mask(sim, self.quar_policy)[symp_inds]      # ... unless the quarantine probability applies to them (:959-966)
                 out[symp_inds[free]] = sp[free]
+        if host_policy:                                    # quarantine-testing probabilities for a set the kernel does not know (policy code 4)
+            qt = quar_test_mask(sim, self.quar_policy)
+            symp = sim.people.symptomatic.as_subclass(torch.Tensor)
+            out[qt & symp] = float(self.symp_quar_prob)
+            out[qt & ~symp] = float(self.asymp_quar_prob)
         if ili is not None and len(ili):
             ili = torch.as_tensor(ili, dtype=torch.int64, device=dev)
             ili = ili[~sim.people.symptomatic[ili]]

@@ -230,15 +230,8 @@ def test_prob_apply(iv, sim):
     ''' reference interventions.py:921-981 '''
     P, t = sim.people, sim.t
     symp = P.symptomatic
-    pol = iv.quar_policy
-    if pol == 'start':
-        qt = P.date_quarantined == t - 1
-    elif pol == 'end':
-        qt = P.date_end_quarantine == t + 1
-    elif pol == 'both':
-        qt = (P.date_quarantined == t - 1) | (P.date_end_quarantine == t + 1)
-    else:
-        qt = P.quarantined.clone()
+    from .interventions import quar_test_mask
+    qt = quar_test_mask(sim, iv.quar_policy)                                                # interventions.py:682-712 get_quar_inds
     probs = torch.where(symp, iv.symp_prob, iv.asymp_prob).to(torch.float64)
     probs[qt & symp] = iv.symp_quar_prob
     probs[qt & ~symp] = iv.asymp_quar_prob
@@ -269,15 +262,8 @@ def test_num_apply(iv, sim):
         ili = sim.rng.nb.choice(sim['pop_size'], int(iv.ili_prev[rel_t] * sim['pop_size']), replace=False)
         ili = torch.as_tensor(np.asarray(ili), dtype=torch.int64, device=sim.device)
         probs[ili[~P.symptomatic[ili]]] *= iv.symp_test
-    pol = iv.quar_policy
-    if pol == 'start':
-        qt = P.date_quarantined == t - 1
-    elif pol == 'end':
-        qt = P.date_end_quarantine == t + 1
-    elif pol == 'both':
-        qt = (P.date_quarantined == t - 1) | (P.date_end_quarantine == t + 1)
-    else:
-        qt = P.quarantined.clone()
+    from .interventions import quar_test_mask
+    qt = quar_test_mask(sim, iv.quar_policy)                                                # interventions.py:682-712 get_quar_inds
     probs[qt] *= iv.quar_test
     if iv.subtarget is not None:                                                             # interventions.py:834-837
         from .interventions import get_subtargets

@@ -231,7 +231,7 @@ int cvb_step_day(cvb_sim* s, int32_t t, cvb_stream st);
  * ---------------------------------------------------------------------------------------------- */
 typedef struct cvb_test_prob_pars {        /* interventions.py:857-981 */
     double symp_prob, asymp_prob, symp_quar_prob, asymp_quar_prob, sensitivity, loss_prob;
-    int32_t quar_policy;                   /* 0 start, 1 end, 2 both, 3 daily */
+    int32_t quar_policy;                   /* 0 start, 1 end, 2 both, 3 daily, 4 none here (days-since-start lists, functions: the caller applies them) */
     int32_t test_delay, index, pad_;
 } cvb_test_prob_pars;
 /* prob_override: NULL, or float64[n] of explicit per-agent probabilities (NaN = none): the `subtarget` option (interventions.py:971-973) */
@@ -242,7 +242,7 @@ int cvb_test_prob_taped(cvb_sim* s, int32_t t, const cvb_test_prob_pars* host_pa
 
 typedef struct cvb_test_num_pars {         /* interventions.py:718-854 */
     double symp_test, quar_test;
-    int32_t quar_policy;                   /* 0 start, 1 end, 2 both, 3 daily */
+    int32_t quar_policy;                   /* 0 start, 1 end, 2 both, 3 daily, 4 none here (days-since-start lists, functions: the caller applies them) */
     int32_t index;
 } cvb_test_num_pars;
 /* test_num, device part one: per-agent testing weights (the reference's test_probs, float64[n]) and exponential-clock keys

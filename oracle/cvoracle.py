@@ -995,7 +995,15 @@ def get_quar_mask(P, t, policy):
         return (P['date_quarantined'] == t - 1) | (P['date_end_quarantine'] == t + 1)
     if policy == 'daily':
         return P['quarantined'].copy()
-    raise NotImplementedError(f'quar_policy {policy}')
+    if isinstance(policy, str):
+        raise ValueError(f'Quarantine policy "{policy}" not recognized')
+    mask = np.zeros(len(P['quarantined']), dtype=bool)
+    if callable(policy):                                        # a function returning the people to test
+        mask[np.asarray(policy(P), dtype=int)] = True
+        return mask
+    for q in np.atleast_1d(policy):                             # days after the start of quarantine on which a test is done
+        mask |= P['date_quarantined'] == t - 1 - q
+    return mask
 
 
 class test_prob(Intervention):
@@ -1029,16 +1037,7 @@ class test_prob(Intervention):
             chosen = sim.rng.choose('nb', n, int(self.ili_prev[t - self.start_day] * n))
             ili[chosen] = True
             ili &= ~symp
-        if self.quar_policy == 'start':
-            qt = P['date_quarantined'] == t - 1
-        elif self.quar_policy == 'end':
-            qt = P['date_end_quarantine'] == t + 1
-        elif self.quar_policy == 'both':
-            qt = (P['date_quarantined'] == t - 1) | (P['date_end_quarantine'] == t + 1)
-        elif self.quar_policy == 'daily':
-            qt = P['quarantined'].copy()
-        else:
-            raise NotImplementedError(self.quar_policy)
+        qt = get_quar_mask(P, t, self.quar_policy)
         probs = np.where(symp, self.symp_prob, self.asymp_prob).astype(float)
         if self.pdf is not None and symp.any():                 # interventions.py:934-943: symptomatic people test by the time since onset
             symp_inds = np.nonzero(symp)[0]

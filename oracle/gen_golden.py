@@ -33,7 +33,7 @@ from oracle import cvoracle as cvo  # noqa: E402
 import scenarios  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
-FULL_PEOPLE = {'hybrid3k', 'random2k_nowaning', 'variants4k', 'dynamic2k', 'dynpars3k', 'clip3k', 'rescale3k', 'fracsus2k', 'sequence3k', 'testnum3k', 'testnum_rescale2k', 'subtarget3k', 'ili3k', 'capacity3k', 'vaccnum3k', 'testnum_sub3k', 'targeteff3k', 'swab3k'}
+FULL_PEOPLE = {'hybrid3k', 'random2k_nowaning', 'variants4k', 'dynamic2k', 'dynpars3k', 'clip3k', 'rescale3k', 'fracsus2k', 'sequence3k', 'testnum3k', 'testnum_rescale2k', 'subtarget3k', 'ili3k', 'capacity3k', 'vaccnum3k', 'testnum_sub3k', 'targeteff3k', 'swab3k', 'quarpol3k'}
 KERNEL_DAYS = {'hybrid3k': [12, 25], 'variants4k': [20], 'baseline20k': []}
 
 

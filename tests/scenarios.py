@@ -103,6 +103,13 @@ SCENARIOS = {
                        ('test_num', dict(daily_tests=100, symp_test=30.0, quar_test=2.0, start_day=17, swab_delay=dict(dist='lognormal', par1=2, par2=3))),
                        ('contact_tracing', dict(trace_probs=0.5, start_day=5))],
     ),
+    # quarantine testing on given days after the start of quarantine (quar_policy as a list / a number instead of a keyword)
+    'quarpol3k': dict(
+        pars=dict(pop_size=3000, pop_infected=80, pop_type='hybrid', n_days=30, verbose=0, rand_seed=161, beta=0.025),
+        interventions=[('test_prob', dict(start_day=3, end_day=17, symp_prob=0.3, asymp_prob=0.01, symp_quar_prob=0.9, asymp_quar_prob=0.5, quar_policy=[1, 4])),
+                       ('test_num', dict(daily_tests=80, symp_test=30.0, quar_test=40.0, quar_policy=2, start_day=18)),
+                       ('contact_tracing', dict(trace_probs=0.6, start_day=4))],
+    ),
     # subtargeting: explicit testing / vaccination probabilities for given agents (a scalar for every 4th agent; a ramp over a block)
     'subtarget3k': dict(
         pars=dict(pop_size=3000, pop_infected=50, pop_type='hybrid', n_days=35, verbose=0, rand_seed=91, beta=0.022),

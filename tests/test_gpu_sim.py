@@ -19,7 +19,7 @@ def cv():
     return covasim_b200
 
 
-@pytest.mark.parametrize('name', ['random2k_nowaning', 'dynamic2k', 'hybrid3k', 'variants4k', 'dynpars3k', 'clip3k', 'rescale3k', 'fracsus2k', 'sequence3k', 'testnum3k', 'testnum_rescale2k', 'subtarget3k', 'ili3k', 'capacity3k', 'vaccnum3k', 'testnum_sub3k', 'targeteff3k', 'swab3k'])
+@pytest.mark.parametrize('name', ['random2k_nowaning', 'dynamic2k', 'hybrid3k', 'variants4k', 'dynpars3k', 'clip3k', 'rescale3k', 'fracsus2k', 'sequence3k', 'testnum3k', 'testnum_rescale2k', 'subtarget3k', 'ili3k', 'capacity3k', 'vaccnum3k', 'testnum_sub3k', 'targeteff3k', 'swab3k', 'quarpol3k'])
 @pytest.mark.parametrize('fused', [True, False])
 def test_lockstep_parity(cv, name, fused):
     ''' fused=True: days without a host decision go through cvb_run_days (day_fused.cu); False: the per-step entry points every day '''

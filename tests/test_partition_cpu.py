@@ -234,3 +234,87 @@ def test_k_smallest_over_ranks(world, k):
     # positions in the global ascending list of flagged agents -> (rank, local index)
     flat = [(r, i) for r in range(world) for i in np.nonzero(masks[r])[0]]
     assert sorted((r, int(i)) for r in range(world) for i in picked[r]) == sorted(flat[p] for p in pos)
+
+
+def test_peer_exchange_layout_and_double_buffering(monkeypatch):
+    '''
+    partition.PeerExchange on the CPU: symmetric memory is replaced by plain host tensors whose addresses every "rank" (thread) knows, and
+    cvb_peer_push by a memmove into each of them.  Checks what the GPU runs rely on: chunk r of an exchange lands at rank r's slot of the
+    SAME half on every rank, the two halves alternate per exchange name, names do not overlap, the returned address is the half just
+    filled, and the buffer filled two exchanges ago is the one overwritten (never the one the readers of the previous exchange use).
+    '''
+    import ctypes
+    import sys
+    import threading
+    import types
+    from covasim_b200 import partition as cvpart
+    from covasim_b200 import _capi
+    world, chunk = 3, 96
+    sections = dict(codes=chunk, cases=chunk // 8)
+    bufs, barrier = {}, threading.Barrier(world)
+
+    class Handle:
+        def __init__(self, rank):
+            self.rank = rank
+
+        @property
+        def buffer_ptrs(self):
+            return [bufs[r].data_ptr() for r in range(world)]
+
+        def barrier(self, channel=0, timeout_ms=0):
+            barrier.wait()
+
+    fake = types.ModuleType('torch.distributed._symmetric_memory')
+    tls = threading.local()
+
+    def empty(n, dtype=None, device=None):
+        t = torch.full((n,), 0xEE, dtype=torch.uint8)
+        bufs[tls.rank] = t
+        barrier.wait()                                       # every rank has allocated before anybody asks for the peers' addresses
+        return t
+    fake.empty = empty
+    fake.rendezvous = lambda t, group: Handle(tls.rank)
+    monkeypatch.setitem(sys.modules, 'torch.distributed._symmetric_memory', fake)
+    import torch.distributed as tdist
+    monkeypatch.setattr(tdist, '_symmetric_memory', fake, raising=False)
+
+    def fake_call(name, *args):
+        assert name == 'cvb_peer_push'
+        src, nbytes, ptrs, w, off, _stream = args
+        for p in range(w):
+            ctypes.memmove(int(ptrs[p]) + int(off), int(src), int(nbytes))
+    monkeypatch.setattr(_capi, 'call', fake_call)
+
+    seen = [[] for _ in range(world)]
+
+    def work(r):
+        tls.rank = r
+        comm = types.SimpleNamespace(world=world, rank=r, group=None, dist=types.SimpleNamespace(group=types.SimpleNamespace(WORLD='world')))
+        ex = cvpart.PeerExchange(comm, torch.device('cpu'), sections)
+        for day in range(5):
+            for name, nbytes in sections.items():
+                if name == 'cases' and day % 2:
+                    continue                                 # tracing is not active every day: the two exchanges alternate independently
+                inp = torch.full((nbytes,), 16 * day + r + (100 if name == 'cases' else 0), dtype=torch.uint8)
+                ptr = ex.all_gather(name, inp, None)
+                got = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(world * nbytes,)).copy()
+                seen[r].append((name, day, ptr - bufs[r].data_ptr(), got))
+                barrier.wait()                               # (stands for the kernels that read the buffer before the next exchange)
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=60)
+    assert all(len(s) == len(seen[0]) > 0 for s in seen)
+    offsets = {}
+    for r in range(world):
+        for name, day, off, got in seen[r]:
+            nbytes = sections[name]
+            want = np.repeat([16 * day + q + (100 if name == 'cases' else 0) for q in range(world)], nbytes).astype(np.uint8)
+            assert np.array_equal(got, want), (r, name, day)
+            offsets.setdefault(name, []).append(off) if r == 0 else None
+            assert off % 256 == 0
+    for name, offs in offsets.items():                      # two halves per name, strictly alternating
+        assert len(set(offs)) == 2 and all(a != b for a, b in zip(offs, offs[1:])) and all(a == b for a, b in zip(offs, offs[2:]))
+    spans = sorted((o, o + world * sections[n]) for n, offs in offsets.items() for o in set(offs))
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))          # no two halves overlap

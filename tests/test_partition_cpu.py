@@ -318,3 +318,84 @@ def test_peer_exchange_layout_and_double_buffering(monkeypatch):
         assert len(set(offs)) == 2 and all(a != b for a, b in zip(offs, offs[1:])) and all(a == b for a, b in zip(offs, offs[2:]))
     spans = sorted((o, o + world * sections[n]) for n, offs in offsets.items() for o in set(offs))
     assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))          # no two halves overlap
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_vaccinate_num_partitioned_selection_equals_single(seed):
+    '''
+    vaccinate_num: the partitioned form of the day's selection (population-wide "first k of the sequence" / "k smallest uniforms" through
+    Sim._k_smallest_mask) picks exactly the people the single-process form picks and defers exactly the same second doses -- on random states:
+    more second doses due than doses, nobody eligible, all candidates on one rank, doses for everybody, subtarget weights, boosters.
+    CPU tensors; the keyed uniforms are replaced by one global random array that every rank slices.
+    '''
+    import threading
+    import types
+    from covasim_b200 import partition as cvpart
+    from covasim_b200.interventions import vaccinate_num
+    from covasim_b200.sim import Sim
+    rng = np.random.default_rng(1000 + seed)
+    world = int(rng.integers(2, 5))
+    n = int(rng.integers(40, 400))
+    bounds = np.sort(rng.choice(np.arange(1, n), world - 1, replace=False)) if world > 1 else np.zeros(0, dtype=int)
+    starts = np.concatenate([[0], bounds]).astype(int)
+    ends = np.concatenate([bounds, [n]]).astype(int)
+    t = 7
+    booster = bool(seed % 4 == 3)
+    dead = rng.random(n) < 0.05
+    vaccinated = rng.random(n) < (0.6 if booster else 0.3)
+    doses = np.where(vaccinated & (not booster), rng.integers(1, 3, n), 0).astype(np.int32)
+    due = np.where(vaccinated & (rng.random(n) < 0.5), t, -1).astype(np.int32)
+    if seed % 3 == 1:
+        due[:] = -1                                            # nobody scheduled
+    seq_len = n if seed % 5 else max(3, n // 10)               # sometimes a short priority list (all candidates near the front of the id range)
+    sequence = rng.permutation(n)[:seq_len] if seed % 5 else np.arange(seq_len)
+    num_people = [0, 3, n // 4, 10 * n][seed % 4] if seed % 7 else 1
+    subtarget = dict(inds=np.arange(0, n, 3), vals=rng.random(len(np.arange(0, n, 3)))) if seed % 2 else None
+    u = {0: rng.random(n), 1: rng.random(n)}
+    round_u = float(rng.random())
+
+    def make_iv(lo, hi, comm):
+        iv = vaccinate_num.__new__(vaccinate_num)
+        iv.num_doses, iv.booster, iv.subtarget, iv.iindex = num_people, booster, subtarget, 0
+        iv.p = dict(doses=2, interval=21)
+        iv.doses = torch.as_tensor(doses[lo:hi].copy())
+        iv.due_day = torch.as_tensor(due[lo:hi].copy())
+        iv._prob = torch.empty(hi - lo, dtype=torch.float64)
+        iv._uniforms = lambda sim, slot: torch.as_tensor(u[slot][lo:hi].copy())
+        if comm is None:
+            iv.sequence = torch.as_tensor(sequence.astype(np.int64))
+        else:
+            pos = np.full(n, np.iinfo(np.int64).max, dtype=np.int64)
+            pos[sequence[::-1]] = np.arange(len(sequence) - 1, -1, -1)
+            iv._pos = torch.as_tensor(pos[lo:hi])
+        return iv
+
+    def make_sim(lo, hi, comm):
+        class StubSim(types.SimpleNamespace):
+            def __getitem__(self, k):
+                return {'pop_scale': 1.0, 'pop_size': n}[k]
+        sim = StubSim(t=t, id0=lo, n_local=hi - lo, n=n, _comm=comm, device=torch.device('cpu'),
+                      people=types.SimpleNamespace(dead=torch.as_tensor(dead[lo:hi].copy()), vaccinated=torch.as_tensor(vaccinated[lo:hi].copy()), device=torch.device('cpu')),
+                      rng=types.SimpleNamespace(np_=types.SimpleNamespace(random_sample=lambda: round_u)))
+        for name in ('_global_counts', '_k_smallest_mask', '_pick_positions'):
+            setattr(sim, name, (lambda f: (lambda *a: f(sim, *a)))(getattr(Sim, name)))
+        return sim
+
+    iv0 = make_iv(0, n, None)
+    sched0, first0 = vaccinate_num.select_people(iv0, make_sim(0, n, None))
+    comms = cvpart.LocalComm.make(world)
+    got = [None] * world
+    ivs = [make_iv(int(starts[r]), int(ends[r]), comms[r]) for r in range(world)]
+
+    def work(r):
+        s, f = vaccinate_num.select_people(ivs[r], make_sim(int(starts[r]), int(ends[r]), comms[r]))
+        got[r] = (s.numpy() + int(starts[r]), f.numpy() + int(starts[r]))
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=60)
+    assert all(g is not None for g in got)
+    assert sorted(np.concatenate([g[0] for g in got]).tolist()) == sorted(sched0.numpy().tolist())
+    assert sorted(np.concatenate([g[1] for g in got]).tolist()) == sorted(first0.numpy().tolist())
+    assert np.array_equal(np.concatenate([iv.due_day.numpy() for iv in ivs]), iv0.due_day.numpy())          # the same second doses were deferred

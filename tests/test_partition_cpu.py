@@ -399,3 +399,66 @@ def test_vaccinate_num_partitioned_selection_equals_single(seed):
     assert sorted(np.concatenate([g[0] for g in got]).tolist()) == sorted(sched0.numpy().tolist())
     assert sorted(np.concatenate([g[1] for g in got]).tolist()) == sorted(first0.numpy().tolist())
     assert np.array_equal(np.concatenate([iv.due_day.numpy() for iv in ivs]), iv0.due_day.numpy())          # the same second doses were deferred
+
+
+@pytest.mark.parametrize('seed', range(8))
+def test_test_num_partitioned_selection_equals_single(seed, monkeypatch):
+    '''
+    test_num: the people tested by the ranks of a partitioned run (everybody at or below the n-th smallest key of the whole population, found
+    from every rank's own n smallest) are the n people a single process picks with topk -- including ranks without any candidate, more tests
+    than candidates, and weights of zero (keys +inf).  CPU tensors, kernels stubbed out.
+    '''
+    import threading
+    import types
+    from covasim_b200 import partition as cvpart
+    from covasim_b200.interventions import test_num
+    import ctypes
+    monkeypatch.setattr(ctypes, 'byref', lambda x: x)        # (the stub parameter block is not a ctypes structure)
+    rng = np.random.default_rng(2000 + seed)
+    world = int(rng.integers(2, 5))
+    n = int(rng.integers(30, 300))
+    bounds = np.sort(rng.choice(np.arange(1, n), world - 1, replace=False))
+    starts = np.concatenate([[0], bounds]).astype(int)
+    ends = np.concatenate([bounds, [n]]).astype(int)
+    weight = np.where(rng.random(n) < 0.2, 0.0, rng.choice([1.0, 3.0, 50.0], n))
+    if seed % 3 == 0:
+        weight[starts[1]:ends[1]] = 0.0                       # a rank whose agents cannot be tested
+    key = np.where(weight > 0, -np.log(1 - rng.random(n)) / np.where(weight > 0, weight, 1.0), np.inf)
+    n_tests = [1, 5, n // 3, 10 * n][seed % 4]
+
+    def run(lo, hi, comm):
+        tested = []
+        iv = test_num.__new__(test_num)
+        iv.subtarget = iv.ili_prev = iv.pdf = None
+        iv._quar_code, iv.sensitivity, iv.loss_prob, iv.test_delay, iv.index = 0, 1.0, 0.0, 0, 0
+        iv._c = types.SimpleNamespace()
+        iv._weight, iv._key = torch.as_tensor(weight[lo:hi].copy()), torch.as_tensor(key[lo:hi].copy())
+        iv.n_tests_today = lambda sim: n_tests
+
+        class StubSim(types.SimpleNamespace):
+            def __getitem__(self, k):
+                return {'pop_scale': 1.0}[k]
+        sim = StubSim(t=4, _comm=comm, _handle=None, _stream_ptr=None, rescale_vec=np.ones(10))
+
+        def call(name, *args):
+            if name == 'cvb_test_list':
+                tested.append(int(args[3]))
+        sim._call = call
+        inds = test_num.apply(iv, sim)
+        inds = np.zeros(0, dtype=np.int64) if inds is None else inds.numpy().astype(np.int64)
+        assert (not tested and len(inds) == 0) or tested == [len(inds)]
+        return inds + lo
+    want = run(0, n, None)
+    assert len(want) == min(n_tests, int((weight > 0).sum()))
+    comms = cvpart.LocalComm.make(world)
+    got = [None] * world
+
+    def work(r):
+        got[r] = run(int(starts[r]), int(ends[r]), comms[r])
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=60)
+    assert all(g is not None for g in got)
+    assert sorted(np.concatenate(got).tolist()) == sorted(want.tolist())

@@ -111,3 +111,55 @@ def test_binding_arity_matches_header(cv):
     # the by-value structs added after the first ABI revision have their ctypes mirrors checked field by field here
     tn = cv._capi.cvb_test_num_pars
     assert [f[0] for f in tn._fields_] == ['symp_test', 'quar_test', 'quar_policy', 'index'] and C.sizeof(tn) == 24
+
+
+def test_concurrent_builds_compile_once_and_never_expose_a_partial_library(tmp_path, monkeypatch):
+    '''
+    covasim_b200/build.py under several importers at once (one rank per GPU under torchrun): the builders are serialised by a file lock, the
+    first one compiles into a private file and moves it into place, the others find the stamp.  The compiler is replaced by a slow writer.
+    '''
+    import importlib.util
+    import threading
+    import time
+    spec = importlib.util.spec_from_file_location('cvb_build_under_test', os.path.join(ROOT, 'covasim_b200', 'build.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = str(tmp_path / 'libx.so')
+    monkeypatch.setattr(mod, 'LIB', lib)
+    monkeypatch.setattr(mod, 'STAMP', lib + '.stamp')
+    monkeypatch.setattr(mod, 'find_nvcc', lambda: 'nvcc')
+    compiles, partial = [], []
+
+    def fake_run(cmd, capture_output=True, text=True):
+        out = cmd[cmd.index('-o') + 1]
+        compiles.append(out)
+        with open(out, 'wb') as f:
+            for _ in range(10):
+                f.write(b'x' * 1000)
+                f.flush()
+                time.sleep(0.02)
+                if os.path.exists(lib) and os.path.getsize(lib) != 10000:
+                    partial.append(os.path.getsize(lib))
+        class R:
+            returncode, stdout, stderr = 0, '', ''
+        return R()
+    monkeypatch.setattr(mod.subprocess, 'run', fake_run)
+    results = []
+    threads = [threading.Thread(target=lambda: results.append(mod.build())) for _ in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=60)
+    assert results == [lib] * 6
+    assert len(compiles) == 1 and compiles[0] != lib and not os.path.exists(compiles[0])
+    assert os.path.getsize(lib) == 10000 and not partial
+    assert open(lib + '.stamp').read().strip() == mod.source_digest()
+    # the digest does not depend on where the tree lives (the built library travels with it to other machines)
+    import shutil
+    here = mod.source_digest()
+    other = tmp_path / 'elsewhere'
+    shutil.copytree(os.path.join(ROOT, 'covasim_b200', 'csrc'), other / 'covasim_b200' / 'csrc')
+    shutil.copytree(os.path.join(ROOT, 'include'), other / 'include')
+    monkeypatch.setattr(mod, 'ROOT', str(other))
+    monkeypatch.setattr(mod, 'CSRC', str(other / 'covasim_b200' / 'csrc'))
+    assert mod.source_digest() == here

@@ -462,3 +462,62 @@ def test_test_num_partitioned_selection_equals_single(seed, monkeypatch):
         th.join(timeout=60)
     assert all(g is not None for g in got)
     assert sorted(np.concatenate(got).tolist()) == sorted(want.tolist())
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_vaccinate_num_selection_product_equals_oracle(seed):
+    '''
+    The day's selection of vaccinate_num in the product (device-array set algebra, here on CPU tensors) against the oracle's native-RNG
+    restatement (oracle/cvoracle.py) on random states, with the same uniforms: same recipients, same deferred second doses.
+    '''
+    import types
+    from covasim_b200.interventions import vaccinate_num
+    from covasim_b200.sim import Sim
+    from oracle import cvoracle as cvo
+    rng = np.random.default_rng(3000 + seed)
+    n = int(rng.integers(40, 400))
+    t = 9
+    booster = bool(seed % 4 == 3)
+    dead = rng.random(n) < 0.05
+    vaccinated = rng.random(n) < (0.6 if booster else 0.3)
+    doses = np.where(vaccinated & (not booster), rng.integers(1, 3, n), 0).astype(np.int32)
+    due = np.where(vaccinated & (rng.random(n) < 0.5), t, -1).astype(np.int64)
+    if seed % 3 == 1:
+        due[:] = -1
+    sequence = rng.permutation(n)[:n if seed % 5 else max(3, n // 10)]
+    num_people = [0, 3, n // 4, 10 * n][seed % 4] if seed % 7 else 1
+    subtarget = dict(inds=np.arange(0, n, 3), vals=rng.random(len(np.arange(0, n, 3)))) if seed % 2 else None
+    u = {0: rng.random(n), 1: rng.random(n)}
+    round_u = float(rng.random())
+    # product
+    iv = vaccinate_num.__new__(vaccinate_num)
+    iv.num_doses, iv.booster, iv.subtarget, iv.iindex = num_people, booster, subtarget, 0
+    iv.p = dict(doses=2, interval=21)
+    iv.doses, iv.due_day = torch.as_tensor(doses.copy()), torch.as_tensor(due.astype(np.int32))
+    iv._prob = torch.empty(n, dtype=torch.float64)
+    iv._uniforms = lambda sim, slot: torch.as_tensor(u[slot].copy())
+    iv.sequence = torch.as_tensor(sequence.astype(np.int64))
+
+    class StubSim(types.SimpleNamespace):
+        def __getitem__(self, k):
+            return {'pop_scale': 1.0, 'pop_size': n}[k]
+    sim = StubSim(t=t, id0=0, n_local=n, n=n, _comm=None, device=torch.device('cpu'),
+                  people=types.SimpleNamespace(dead=torch.as_tensor(dead.copy()), vaccinated=torch.as_tensor(vaccinated.copy()), device=torch.device('cpu')),
+                  rng=types.SimpleNamespace(np_=types.SimpleNamespace(random_sample=lambda: round_u)))
+    sched, first = vaccinate_num.select_people(iv, sim)
+    # oracle (native-RNG mode)
+    ov = cvo.vaccinate_num.__new__(cvo.vaccinate_num)
+    ov.num_doses, ov.booster, ov.subtarget, ov.iindex = num_people, booster, subtarget, 0
+    ov.p = dict(doses=2, interval=21)
+    ov.doses, ov.due_day, ov.sequence = doses.copy(), due.copy(), sequence.copy()
+    ov._scheduled = {}
+    osim = types.SimpleNamespace(t=t, P=dict(uid=np.arange(n), dead=dead.copy(), vaccinated=vaccinated.copy()), pars={'pop_scale': 1.0},
+                                 rng=types.SimpleNamespace(kind='philox', np_=types.SimpleNamespace(random_sample=lambda: round_u),
+                                                           agent_uniforms=lambda t_, purpose, sub, inds, slot=0: u[slot][np.asarray(inds)]))
+    want = cvo.vaccinate_num.select_people(ov, osim)
+    got = np.concatenate([sched.numpy(), first.numpy()])
+    assert sorted(got.tolist()) == sorted(np.asarray(want, dtype=np.int64).tolist())
+    others = np.ones(n, dtype=bool)                             # (the oracle books today's first doses for their second dose here, the product in the dose kernel)
+    others[first.numpy()] = False
+    assert np.array_equal(iv.due_day.numpy().astype(np.int64)[others], ov.due_day[others])
+    assert np.all(ov.due_day[first.numpy()] == t + 21)
